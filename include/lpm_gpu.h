@@ -1,0 +1,243 @@
+/*
+ * lpm_gpu.h -- C ABI of liblpmgpu.so: the B200 (sm_100a) replacement for
+ * lpm-v2's O(N^2) direct-sum hot path.
+ *
+ * Every entry point is what the reference's Fortran would bind through
+ * ISO_C_BINDING for this path (see lpm_v2_b200/fortran/lpm_gpu.f90 and
+ * INTEGRATION.md).  Plain pointers and sizes only.  File:line citations are
+ * into the lpm-v2 source tree.
+ *
+ * Conventions
+ *   - all functions returning int: 0 (LPM_OK) on success, non-zero on error;
+ *     lpm_gpu_last_error() gives the message (the Fortran shim forwards it to
+ *     LogMessage(log, ERROR_LOGGING_LEVEL, ...), matching the reference's
+ *     "log, never abort" behaviour, src/Logger.f90:158-160).
+ *   - there is NO CPU fallback: without a usable sm_100 device every compute
+ *     entry point fails with LPM_ERR_NO_DEVICE.
+ *   - arrays are contiguous real(c_double) / integer(c_int32_t), length n.
+ *   - mask: int32, non-zero = active (Fortran side: merge(1,0,activeMask)).
+ *   - target ranges [ibeg, iend) are 0-based half-open; the reference slice
+ *     indexStart(r)..indexEnd(r) (src/MPISetup.f90:132-146) is
+ *     [indexStart-1, indexEnd).
+ *   - "host" entry points take host pointers and are synchronous: outputs
+ *     are complete on return.  "_dev" entry points take device pointers on
+ *     the current CUDA device and enqueue on `stream` (a cudaStream_t passed
+ *     as void*; NULL = default stream) without synchronising.
+ */
+#ifndef LPM_GPU_H
+#define LPM_GPU_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+enum {
+    LPM_OK = 0,
+    LPM_ERR_INVALID = 1,      /* bad argument */
+    LPM_ERR_NO_DEVICE = 2,    /* no CUDA device / not sm_100 / library not initialised */
+    LPM_ERR_CUDA = 3,         /* CUDA runtime error (message in lpm_gpu_last_error) */
+    LPM_ERR_COMM = 4,         /* NCCL / peer-access error */
+    LPM_ERR_NOMEM = 5
+};
+
+/* mesh seed identifiers, src/TypeDefs.f90:66-73 */
+enum {
+    LPM_TRI_HEX_SEED = 201,
+    LPM_QUAD_RECT_SEED = 202,
+    LPM_ICOS_TRI_SPHERE_SEED = 205,
+    LPM_CUBED_SPHERE_SEED = 206,
+    LPM_BETA_PLANE_SEED = 207
+};
+
+/* ---------------------------------------------------------------- runtime */
+
+/* Replaces MPI_INIT + MPI_COMM_SIZE for this path (examples/BVESingleGaussianVortex.f90:102-104).
+ * Single-process mode: claims ndev_requested devices (0 = all visible), enables
+ * peer access between them.  ndev_used may be NULL. */
+int lpm_gpu_init(int ndev_requested, int* ndev_used);
+int lpm_gpu_finalize(void);
+const char* lpm_gpu_last_error(void);
+int lpm_gpu_device_count(void);       /* devices claimed by lpm_gpu_init (0 before) */
+
+/* Multi-process mode (one MPI rank / process per GPU): bind this process to
+ * `device`, then build an NCCL communicator.  The 128-byte id comes from
+ * lpm_comm_unique_id on rank 0 and is distributed by the host program
+ * (MPI_BCAST in Fortran, torch.distributed in bench.py). */
+int lpm_gpu_init_rank(int device);
+int lpm_comm_unique_id(char id[128]);
+int lpm_comm_init_rank(int world_size, int rank, const char id[128]);
+int lpm_comm_world_size(void);
+int lpm_comm_rank(void);
+
+/* Replaces the MPI_BCAST loop that follows every direct sum
+ * (src/SphereBVESolver.f90:422-429): every rank contributes
+ * buf[start_r .. end_r) for each of the ncomp device arrays, ranges from
+ * lpm_load_balance; in place; ragged last slice allowed. */
+int lpm_comm_allgather_slices_dev(int ncomp, double* const* bufs, int64_t n, void* stream);
+
+/* Optional: page-lock host arrays the solver owns (at New), release at Delete. */
+int lpm_gpu_pin(void* ptr, int64_t bytes);
+int lpm_gpu_unpin(void* ptr);
+
+/* src/MPISetup.f90:132-146 LoadBalance.  Outputs are 1-based inclusive like
+ * the reference's indexStart/indexEnd/messageLength (arrays of nprocs). */
+int lpm_load_balance(int64_t n_items, int nprocs, int64_t* index_start, int64_t* index_end, int64_t* message_length);
+
+/* The active-source index list the device compaction builds == Fortran
+ * pack([(j,j=1,n)], mask), 0-based; exposed for the bit-exact check. */
+int lpm_active_list(int64_t n, const int32_t* mask, int32_t* list, int64_t* count);
+
+/* ------------------------------------------------- direct sums, host API */
+
+/* BVESphereVelocity, src/SphereBVESolver.f90:377-430; also
+ * setVelocityFromVorticity, src/SphereBVE.f90:489-531. */
+int lpm_bve_velocity(int64_t n, const double* x, const double* y, const double* z,
+                     const double* relvort, const double* area, const int32_t* mask,
+                     double radius, double* u, double* v, double* w);
+
+/* SetStreamFunctionsOnMesh, src/SphereBVE.f90:445-485. */
+int lpm_bve_stream(int64_t n, const double* x, const double* y, const double* z,
+                   const double* relvort, const double* absvort, const double* area,
+                   const int32_t* mask, double radius, double* relstream, double* absstream);
+
+/* planarIncompressibleVelocity, src/PlaneIncompressibleSolver.f90:278-316;
+ * setVelocityFromVorticity, src/PlanarIncompressible.f90:426-466. */
+int lpm_plane_velocity(int64_t n, const double* x, const double* y, const double* vort,
+                       const double* area, const int32_t* mask, double* u, double* v);
+
+/* SetStreamFunctionOnMesh, src/PlanarIncompressible.f90:470-505. */
+int lpm_plane_stream(int64_t n, const double* x, const double* y, const double* vort,
+                     const double* area, const int32_t* mask, double* psi);
+
+/* BetaPlaneVelocity, src/BetaPlaneSolver.f90:227-267;
+ * setVelocityFromVorticity, src/BetaPlane.f90:359-397. */
+int lpm_betaplane_velocity(int64_t n, const double* x, const double* y, const double* relvort,
+                           const double* area, const int32_t* mask, double* u, double* v);
+
+/* SetStreamFunctionsOnMesh, src/BetaPlane.f90:399-442. */
+int lpm_betaplane_stream(int64_t n, const double* x, const double* y, const double* relvort,
+                         const double* absvort, const double* area, const int32_t* mask,
+                         double* relstream, double* absstream);
+
+/* PSESphereLaplacianAtParticles, src/PSEDirectSum.f90:502-535.
+ * sphere_radius is the module-global SphereRadius (src/TypeDefs.f90:74). */
+int lpm_pse_laplacian_sphere(int64_t n, const double* x, const double* y, const double* z,
+                             const double* f, const double* area, const int32_t* mask,
+                             double eps, double sphere_radius, double* lap);
+
+/* PSEPlaneLaplacianAtParticles, src/PSEDirectSum.f90:467-500. */
+int lpm_pse_laplacian_plane(int64_t n, const double* x, const double* y,
+                            const double* f, const double* area, const int32_t* mask,
+                            double eps, double* lap);
+
+/* -------------------------- direct sums, device API (one rank's slice) */
+
+int lpm_bve_velocity_dev(int64_t n, const double* x, const double* y, const double* z,
+                         const double* relvort, const double* area, const int32_t* mask,
+                         double radius, int64_t ibeg, int64_t iend,
+                         double* u, double* v, double* w, void* stream);
+int lpm_bve_stream_dev(int64_t n, const double* x, const double* y, const double* z,
+                       const double* relvort, const double* absvort, const double* area,
+                       const int32_t* mask, double radius, int64_t ibeg, int64_t iend,
+                       double* relstream, double* absstream, void* stream);
+int lpm_plane_velocity_dev(int64_t n, const double* x, const double* y, const double* vort,
+                           const double* area, const int32_t* mask, int64_t ibeg, int64_t iend,
+                           double* u, double* v, void* stream);
+int lpm_plane_stream_dev(int64_t n, const double* x, const double* y, const double* vort,
+                         const double* area, const int32_t* mask, int64_t ibeg, int64_t iend,
+                         double* psi, void* stream);
+int lpm_betaplane_velocity_dev(int64_t n, const double* x, const double* y, const double* relvort,
+                               const double* area, const int32_t* mask, int64_t ibeg, int64_t iend,
+                               double* u, double* v, void* stream);
+int lpm_betaplane_stream_dev(int64_t n, const double* x, const double* y, const double* relvort,
+                             const double* absvort, const double* area, const int32_t* mask,
+                             int64_t ibeg, int64_t iend, double* relstream, double* absstream, void* stream);
+int lpm_pse_laplacian_sphere_dev(int64_t n, const double* x, const double* y, const double* z,
+                                 const double* f, const double* area, const int32_t* mask,
+                                 double eps, double sphere_radius, int64_t ibeg, int64_t iend,
+                                 double* lap, void* stream);
+int lpm_pse_laplacian_plane_dev(int64_t n, const double* x, const double* y,
+                                const double* f, const double* area, const int32_t* mask,
+                                double eps, int64_t ibeg, int64_t iend, double* lap, void* stream);
+
+/* ------------------------------------------- resident solvers (RK4 step) */
+
+/* type BVESolver + New/Timestep/Delete, src/SphereBVESolver.f90:38-72,112-168,219-353.
+ * All state lives on the device(s); Timestep runs the 4 stages, the final
+ * velocity evaluation (:345-346) and, if with_stream != 0, the stream
+ * functions (:352 -> src/SphereBVE.f90:445-485) without host round trips. */
+typedef struct lpm_bve_solver lpm_bve_solver;
+/* absvort (the materially conserved absVort field, src/SphereBVE.f90:346) may be NULL if
+ * stream functions are never requested. */
+int lpm_bve_solver_new(int64_t n, const double* x, const double* y, const double* z,
+                       const double* relvort, const double* absvort,
+                       const double* u, const double* v, const double* w,
+                       const double* area, const int32_t* mask, double radius, double rotation_rate,
+                       lpm_bve_solver** out);
+int lpm_bve_solver_timestep(lpm_bve_solver* s, double dt, int with_stream);
+/* copies back particles x,y,z, relVort, velocity (and stream functions; any pointer may be NULL) */
+int lpm_bve_solver_get_state(lpm_bve_solver* s, double* x, double* y, double* z, double* relvort,
+                             double* u, double* v, double* w, double* relstream, double* absstream);
+/* TotalKE / TotalEnstrophy, src/SphereBVE.f90:410-441 (device reductions) */
+int lpm_bve_solver_diagnostics(lpm_bve_solver* s, double* total_ke, double* total_enstrophy);
+int lpm_bve_solver_delete(lpm_bve_solver* s);
+
+/* type PlaneSolver, src/PlaneIncompressibleSolver.f90:37-59,171-259. */
+typedef struct lpm_plane_solver lpm_plane_solver;
+int lpm_plane_solver_new(int64_t n, const double* x, const double* y, const double* vort,
+                         const double* u, const double* v, const double* area, const int32_t* mask,
+                         lpm_plane_solver** out);
+int lpm_plane_solver_timestep(lpm_plane_solver* s, double dt, int with_stream);
+int lpm_plane_solver_get_state(lpm_plane_solver* s, double* x, double* y, double* u, double* v, double* psi);
+int lpm_plane_solver_delete(lpm_plane_solver* s);
+
+/* type BetaPlaneSolver, src/BetaPlaneSolver.f90:36-56,142-219. */
+typedef struct lpm_betaplane_solver lpm_betaplane_solver;
+int lpm_betaplane_solver_new(int64_t n, const double* x, const double* y, const double* relvort,
+                             const double* absvort, const double* u, const double* v,
+                             const double* area, const int32_t* mask, double beta,
+                             lpm_betaplane_solver** out);
+int lpm_betaplane_solver_timestep(lpm_betaplane_solver* s, double dt, int with_stream);
+int lpm_betaplane_solver_get_state(lpm_betaplane_solver* s, double* x, double* y, double* relvort,
+                                   double* u, double* v, double* relstream, double* absstream);
+int lpm_betaplane_solver_delete(lpm_betaplane_solver* s);
+
+/* -------------------------------------------------------- measurement */
+
+/* Dependent-free DFMA probe: runs `iters` rounds of independent FMA chains on
+ * every SM and returns the achieved FP64 TFLOP/s (2 flop per DFMA) -- the
+ * measured denominator for the FP64 roofline. */
+int lpm_fp64_peak_probe(int iters, double* tflops, double* ms);
+
+/* Time of the last direct-sum main kernel on this device (ms, CUDA events on
+ * the launching stream), and the number of kernel launches the library has
+ * issued since lpm_gpu_init / the last call with reset != 0. */
+int lpm_last_kernel_ms(double* ms);
+int64_t lpm_launch_count(int reset);
+/* 1: record events around each main kernel (adds a sync at query time only). */
+int lpm_set_profiling(int enable);
+/* Tuning knob for benchmarks: select the BVE kernel variant. */
+int lpm_set_bve_variant(int variant);
+
+/* ------------------------------------------------------ mesh (host only) */
+
+/* Uniformly refined PolyMesh2d particle set in the reference's insertion
+ * order: src/PolyMesh2d.f90:135-195, src/Faces.f90:529-858. */
+typedef struct lpm_mesh lpm_mesh;
+int lpm_mesh_create(int seed_kind, int init_nest, double amp_factor, lpm_mesh** out);
+void lpm_mesh_destroy(lpm_mesh* m);
+int64_t lpm_mesh_num_particles(const lpm_mesh* m);
+int64_t lpm_mesh_num_faces(const lpm_mesh* m);        /* whole quadtree */
+int64_t lpm_mesh_num_edges(const lpm_mesh* m);        /* whole binary tree */
+int64_t lpm_mesh_num_leaf_faces(const lpm_mesh* m);
+int64_t lpm_mesh_num_leaf_edges(const lpm_mesh* m);
+double lpm_mesh_max_edge_length(const lpm_mesh* m);   /* src/Edges.f90:260-275 */
+int lpm_mesh_get_particles(const lpm_mesh* m, double* x, double* y, double* z, double* area, int32_t* is_active);
+int lpm_mesh_get_leaf_faces(const lpm_mesh* m, int32_t* verts, int32_t* center);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* LPM_GPU_H */

@@ -1,0 +1,177 @@
+"""numpy-facing wrappers of the C ABI (host buffers in, host buffers out).
+
+These are the calls the reference's patched private kernels make through
+ISO_C_BINDING (lpm_v2_b200/fortran/lpm_gpu.f90); the tests drive the same
+entry points through ctypes.  Nothing here computes: every function forwards
+to liblpmgpu.so and raises LpmError on a non-zero return.
+"""
+import ctypes as C
+
+import numpy as np
+
+from ._lib import lib, check, LpmError  # noqa: F401
+
+_d = C.POINTER(C.c_double)
+_i32 = C.POINTER(C.c_int32)
+
+
+def _f64(a):
+    a = np.ascontiguousarray(a, dtype=np.float64)
+    return a
+
+
+def _pd(a):
+    return a.ctypes.data_as(_d)
+
+
+def _mask(m):
+    """logical(klog) -> int32 (merge(1,0,mask) on the Fortran side)."""
+    m = np.asarray(m)
+    if m.dtype != np.int32:
+        m = (m != 0).astype(np.int32)
+    return np.ascontiguousarray(m)
+
+
+def init(ndev=0):
+    """lpm_gpu_init: claim `ndev` devices (0 = all) in single-process mode."""
+    used = C.c_int(0)
+    check(lib.lpm_gpu_init(int(ndev), C.byref(used)))
+    return used.value
+
+
+def init_rank(device):
+    check(lib.lpm_gpu_init_rank(int(device)))
+
+
+def finalize():
+    check(lib.lpm_gpu_finalize())
+
+
+def device_count():
+    return lib.lpm_gpu_device_count()
+
+
+def comm_unique_id():
+    buf = C.create_string_buffer(128)
+    check(lib.lpm_comm_unique_id(buf))
+    return buf.raw
+
+
+def comm_init_rank(world, rank, uid):
+    check(lib.lpm_comm_init_rank(int(world), int(rank), C.create_string_buffer(uid, 128)))
+
+
+def load_balance(n_items, nprocs):
+    """MPISetup%indexStart/indexEnd/messageLength (1-based, inclusive)."""
+    s = np.zeros(nprocs, np.int64)
+    e = np.zeros(nprocs, np.int64)
+    m = np.zeros(nprocs, np.int64)
+    p = C.POINTER(C.c_int64)
+    check(lib.lpm_load_balance(int(n_items), int(nprocs), s.ctypes.data_as(p), e.ctypes.data_as(p), m.ctypes.data_as(p)))
+    return s, e, m
+
+
+def active_list(mask):
+    m = _mask(mask)
+    out = np.zeros(m.size, np.int32)
+    cnt = C.c_int64(0)
+    check(lib.lpm_active_list(m.size, m.ctypes.data_as(_i32), out.ctypes.data_as(_i32), C.byref(cnt)))
+    return out[:cnt.value].copy()
+
+
+def bve_velocity(x, y, z, relvort, area, mask, radius=1.0):
+    x, y, z, relvort, area = map(_f64, (x, y, z, relvort, area))
+    m = _mask(mask)
+    n = x.size
+    u, v, w = (np.empty(n) for _ in range(3))
+    check(lib.lpm_bve_velocity(n, _pd(x), _pd(y), _pd(z), _pd(relvort), _pd(area), m.ctypes.data_as(_i32),
+                               float(radius), _pd(u), _pd(v), _pd(w)))
+    return u, v, w
+
+
+def bve_stream(x, y, z, relvort, absvort, area, mask, radius=1.0):
+    x, y, z, relvort, absvort, area = map(_f64, (x, y, z, relvort, absvort, area))
+    m = _mask(mask)
+    n = x.size
+    rs, as_ = np.empty(n), np.empty(n)
+    check(lib.lpm_bve_stream(n, _pd(x), _pd(y), _pd(z), _pd(relvort), _pd(absvort), _pd(area),
+                             m.ctypes.data_as(_i32), float(radius), _pd(rs), _pd(as_)))
+    return rs, as_
+
+
+def plane_velocity(x, y, vort, area, mask):
+    x, y, vort, area = map(_f64, (x, y, vort, area))
+    m = _mask(mask)
+    n = x.size
+    u, v = np.empty(n), np.empty(n)
+    check(lib.lpm_plane_velocity(n, _pd(x), _pd(y), _pd(vort), _pd(area), m.ctypes.data_as(_i32), _pd(u), _pd(v)))
+    return u, v
+
+
+def plane_stream(x, y, vort, area, mask):
+    x, y, vort, area = map(_f64, (x, y, vort, area))
+    m = _mask(mask)
+    psi = np.empty(x.size)
+    check(lib.lpm_plane_stream(x.size, _pd(x), _pd(y), _pd(vort), _pd(area), m.ctypes.data_as(_i32), _pd(psi)))
+    return psi
+
+
+def betaplane_velocity(x, y, relvort, area, mask):
+    x, y, relvort, area = map(_f64, (x, y, relvort, area))
+    m = _mask(mask)
+    n = x.size
+    u, v = np.empty(n), np.empty(n)
+    check(lib.lpm_betaplane_velocity(n, _pd(x), _pd(y), _pd(relvort), _pd(area), m.ctypes.data_as(_i32), _pd(u), _pd(v)))
+    return u, v
+
+
+def betaplane_stream(x, y, relvort, absvort, area, mask):
+    x, y, relvort, absvort, area = map(_f64, (x, y, relvort, absvort, area))
+    m = _mask(mask)
+    n = x.size
+    rs, as_ = np.empty(n), np.empty(n)
+    check(lib.lpm_betaplane_stream(n, _pd(x), _pd(y), _pd(relvort), _pd(absvort), _pd(area),
+                                   m.ctypes.data_as(_i32), _pd(rs), _pd(as_)))
+    return rs, as_
+
+
+def pse_laplacian_sphere(x, y, z, f, area, mask, eps, sphere_radius=1.0):
+    x, y, z, f, area = map(_f64, (x, y, z, f, area))
+    m = _mask(mask)
+    lap = np.empty(x.size)
+    check(lib.lpm_pse_laplacian_sphere(x.size, _pd(x), _pd(y), _pd(z), _pd(f), _pd(area), m.ctypes.data_as(_i32),
+                                       float(eps), float(sphere_radius), _pd(lap)))
+    return lap
+
+
+def pse_laplacian_plane(x, y, f, area, mask, eps):
+    x, y, f, area = map(_f64, (x, y, f, area))
+    m = _mask(mask)
+    lap = np.empty(x.size)
+    check(lib.lpm_pse_laplacian_plane(x.size, _pd(x), _pd(y), _pd(f), _pd(area), m.ctypes.data_as(_i32),
+                                      float(eps), _pd(lap)))
+    return lap
+
+
+def fp64_peak_probe(iters=4096):
+    tf, ms = C.c_double(0), C.c_double(0)
+    check(lib.lpm_fp64_peak_probe(int(iters), C.byref(tf), C.byref(ms)))
+    return tf.value, ms.value
+
+
+def set_profiling(on):
+    check(lib.lpm_set_profiling(1 if on else 0))
+
+
+def set_bve_variant(v):
+    check(lib.lpm_set_bve_variant(int(v)))
+
+
+def last_kernel_ms():
+    ms = C.c_double(0)
+    check(lib.lpm_last_kernel_ms(C.byref(ms)))
+    return ms.value
+
+
+def launch_count(reset=False):
+    return int(lib.lpm_launch_count(1 if reset else 0))

@@ -1,0 +1,121 @@
+// common.cuh -- runtime plumbing shared by every entry point of liblpmgpu.so:
+// error reporting, per-device context (stream, workspace, profiling events).
+#pragma once
+#include <cuda_runtime.h>
+
+#include <cstdarg>
+#include <cstdint>
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "lpm_gpu.h"
+
+namespace lpm {
+
+// ---- error reporting (src/Logger.f90:158-160: log, never abort) -------------
+inline std::string& last_error_ref()
+{
+    static thread_local std::string s;
+    return s;
+}
+inline int set_error(int code, const char* fmt, ...)
+{
+    char buf[1024];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof(buf), fmt, ap);
+    va_end(ap);
+    last_error_ref() = buf;
+    return code;
+}
+
+#define LPM_CUDA(expr)                                                                         \
+    do {                                                                                       \
+        cudaError_t _e = (expr);                                                               \
+        if (_e != cudaSuccess)                                                                 \
+            return ::lpm::set_error(LPM_ERR_CUDA, "%s:%d: %s failed: %s", __FILE__, __LINE__,  \
+                                    #expr, cudaGetErrorString(_e));                            \
+    } while (0)
+
+#define LPM_TRY(expr)                 \
+    do {                              \
+        int _r = (expr);              \
+        if (_r != LPM_OK) return _r;  \
+    } while (0)
+
+// ---- growable device buffer --------------------------------------------------
+struct DevBuf {
+    void* p = nullptr;
+    size_t cap = 0;
+    int reserve(size_t bytes)
+    {
+        if (bytes <= cap) return LPM_OK;
+        if (p) { cudaFree(p); p = nullptr; cap = 0; }
+        size_t want = bytes + bytes / 8 + 256;
+        cudaError_t e = cudaMalloc(&p, want);
+        if (e != cudaSuccess) {
+            p = nullptr;
+            return set_error(LPM_ERR_NOMEM, "cudaMalloc(%zu bytes) failed: %s", want, cudaGetErrorString(e));
+        }
+        cap = want;
+        return LPM_OK;
+    }
+    void release()
+    {
+        if (p) cudaFree(p);
+        p = nullptr; cap = 0;
+    }
+    template <class T> T* as() const { return reinterpret_cast<T*>(p); }
+};
+
+// Scratch a direct sum needs on one device.  Reused across calls.
+struct Workspace {
+    DevBuf scan;        // int32 [n+1]   exclusive prefix of mask
+    DevBuf blocksums;   // int32 [nblocks+1]
+    DevBuf active;      // int32 [nsrc]  compact -> particle index
+    DevBuf sources;     // double [nsrc_pad * NS]
+    DevBuf partial;     // double [nchunks * NA * ntgt]
+    DevBuf staging[12]; // host API: device copies of the caller's arrays
+    DevBuf reduce;      // small reduction scratch
+    void release()
+    {
+        scan.release(); blocksums.release(); active.release(); sources.release(); partial.release();
+        reduce.release();
+        for (auto& s : staging) s.release();
+    }
+};
+
+struct Device {
+    int id = -1;
+    int sm_count = 0;
+    cudaStream_t stream = nullptr;       // library-owned stream (host API, resident solvers)
+    cudaEvent_t ev_begin = nullptr, ev_end = nullptr, ev_done = nullptr;
+    bool timed = false;                  // ev_begin/ev_end hold a measurement
+    Workspace ws;
+};
+
+struct Runtime {
+    bool initialised = false;
+    bool rank_mode = false;              // one process per GPU (lpm_gpu_init_rank)
+    std::vector<Device> devs;            // devices this process drives
+    bool profiling = false;
+    int64_t launches = 0;
+    int bve_variant = 0;
+    // NCCL (rank mode)
+    void* nccl_lib = nullptr;
+    void* comm = nullptr;
+    int world = 1, rank = 0;
+};
+
+inline Runtime& rt()
+{
+    static Runtime r;
+    return r;
+}
+
+inline void count_launch(int k = 1) { rt().launches += k; }
+
+}  // namespace lpm

@@ -1,0 +1,247 @@
+// directsum.cuh -- the tiled O(N*F) direct-sum engine for sm_100a.
+//
+// One kernel template drives every pair kernel of the hot path (BVE velocity,
+// planar / beta-plane Biot-Savart, PSE Laplacians, stream functions).  The
+// reference evaluates, for each target i of a rank's slice, the masked loop
+// over j /= i (e.g. src/SphereBVESolver.f90:396-420).  Here:
+//
+//   * sources are the compacted active particles (stable order == Fortran
+//     pack(), see scan.cuh) stored AoS, NS doubles per source, padded with
+//     null sources to a whole number of tiles;
+//   * work item = (target block, source chunk).  A CTA holds BLOCK*T targets
+//     in registers (T per thread, strided by BLOCK so loads coalesce) and
+//     streams the chunk's sources through shared memory in TS-source tiles
+//     with a two-stage TMA bulk-copy (cp.async.bulk + mbarrier) pipeline;
+//     every lane reads the same source (LDS.128 broadcast);
+//   * the self interaction j == i is excluded only in the (at most
+//     BLOCK*T/TS + 1) tiles that overlap the CTA's own compact index range --
+//     all other tiles run the unchecked loop;
+//   * chunk partial sums go to scratch and are added in chunk order by the
+//     finalize kernel, so a target's result does not depend on the launch
+//     geometry, the slice it belongs to, or the number of GPUs.
+#pragma once
+#include <cuda_runtime.h>
+
+#include <cstdint>
+
+namespace lpm {
+
+constexpr int kMaxChunks = 16;      // upper bound on source chunks per evaluation
+constexpr int kChunkMin = 8192;     // do not split the source list finer than this
+constexpr int kTile = 256;          // sources per shared-memory tile (all kernels)
+
+struct DsGeom {
+    int64_t tbeg, tend;     // target range, global particle indices [tbeg, tend)
+    int32_t nsrc;           // active sources
+    int32_t nsrc_pad;       // padded to a multiple of kTile
+    int32_t chunk;          // sources per chunk (multiple of kTile)
+    int32_t nchunks;
+    int32_t ntblocks;       // target blocks = ceil((tend-tbeg) / (BLOCK*T))
+    int64_t ntgt;           // tend - tbeg
+};
+
+// Source chunking depends on the number of active sources only.
+inline void ds_chunks(int64_t nsrc, int32_t* nsrc_pad, int32_t* chunk, int32_t* nchunks)
+{
+    int64_t pad = (nsrc + kTile - 1) / kTile * kTile;
+    if (pad == 0) pad = kTile;
+    int64_t nc = (pad + kChunkMin - 1) / kChunkMin;
+    if (nc > kMaxChunks) nc = kMaxChunks;
+    if (nc < 1) nc = 1;
+    int64_t ch = (pad + nc - 1) / nc;
+    ch = (ch + kTile - 1) / kTile * kTile;
+    nc = (pad + ch - 1) / ch;
+    *nsrc_pad = (int32_t)pad; *chunk = (int32_t)ch; *nchunks = (int32_t)nc;
+}
+
+// ---- mbarrier / TMA bulk copy (PTX) ------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p)
+{
+    return (uint32_t)__cvta_generic_to_shared(p);
+}
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes)
+                 : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity)
+{
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+    return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity)
+{
+    // Bounded: a lost copy traps instead of hanging the device.
+    for (uint32_t it = 0; it < (1u << 26); ++it)
+        if (mbar_try_wait(bar, parity)) return;
+    __trap();
+}
+__device__ __forceinline__ void tma_bulk_g2s(void* dst_smem, const void* src_gmem, uint32_t bytes, uint64_t* bar)
+{
+    asm volatile(
+        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+            smem_u32(dst_smem)),
+        "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
+        : "memory");
+}
+
+// ---- the kernel ---------------------------------------------------------------
+//
+// K (pair functor) provides:
+//   NS, NA            doubles per source record / accumulators per target
+//   SKIP_SELF         exclude j == i (velocity, stream fn) or not (PSE)
+//   Params            kernel-wide constants + target array pointers
+//   Tgt               per-target registers
+//   load_target(p,i)  -> Tgt
+//   pair<CHECK>(p, tgt, s[NS], acc[NA], skip)
+//   finalize(p, tgt, acc, i)   writes the outputs of target i
+//
+// partial layout: [(chunk*NA + a) * ntgt + local_target]
+template <class K, int T, int BLOCK, int U>
+__global__ void __launch_bounds__(BLOCK)
+ds_kernel(const typename K::Params prm, const DsGeom g, const double* __restrict__ src,
+          const int32_t* __restrict__ scan, double* __restrict__ partial)
+{
+    constexpr int NS = K::NS, NA = K::NA, TS = kTile;
+    constexpr uint32_t kTileBytes = TS * NS * sizeof(double);
+    __shared__ __align__(128) double tile[2][TS * NS];
+    __shared__ __align__(8) uint64_t full[2];
+
+    const int tid = threadIdx.x;
+    const int tb = blockIdx.x % g.ntblocks;         // chunk is the slow index: CTAs that run
+    const int ck = blockIdx.x / g.ntblocks;         // together read the same sources (L2)
+    const int64_t blk0 = g.tbeg + (int64_t)tb * (BLOCK * T);
+
+    typename K::Tgt tg[T];
+    double acc[T][NA];
+    int32_t self[T];
+    bool live[T];
+#pragma unroll
+    for (int t = 0; t < T; ++t) {
+        int64_t i = blk0 + t * BLOCK + tid;
+        live[t] = i < g.tend;
+        if (!live[t]) i = g.tend - 1;
+        tg[t] = K::load_target(prm, i);
+        if (K::SKIP_SELF) {
+            int32_t a = scan[i], b = scan[i + 1];
+            self[t] = (b > a && live[t]) ? a : -1;
+        } else {
+            self[t] = -1;
+        }
+#pragma unroll
+        for (int a = 0; a < NA; ++a) acc[t][a] = 0.0;
+    }
+    // compact indices of this CTA's own targets: [selflo, selfhi)
+    int32_t selflo = 0, selfhi = 0;
+    if (K::SKIP_SELF) {
+        int64_t blk1 = blk0 + BLOCK * T;
+        if (blk1 > g.tend) blk1 = g.tend;
+        selflo = scan[blk0];
+        selfhi = scan[blk1];
+    }
+
+    const int32_t s0 = ck * g.chunk;
+    int32_t s1 = s0 + g.chunk;
+    if (s1 > g.nsrc_pad) s1 = g.nsrc_pad;
+    const int ntiles = (s1 - s0) / TS;
+
+    if (tid == 0) {
+        mbar_init(&full[0], 1);
+        mbar_init(&full[1], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    if (tid == 0) {
+#pragma unroll
+        for (int s = 0; s < 2; ++s)
+            if (s < ntiles) {
+                mbar_expect_tx(&full[s], kTileBytes);
+                tma_bulk_g2s(tile[s], src + (size_t)(s0 + s * TS) * NS, kTileBytes, &full[s]);
+            }
+    }
+
+    for (int k = 0; k < ntiles; ++k) {
+        const int st = k & 1;
+        mbar_wait(&full[st], (k >> 1) & 1);
+        const double* sm = tile[st];
+        const int32_t j0 = s0 + k * TS;
+        const bool check = K::SKIP_SELF && (j0 < selfhi) && (j0 + TS > selflo);
+        if (!check) {
+#pragma unroll U
+            for (int j = 0; j < TS; ++j) {
+                double s[NS];
+                const double2* p2 = reinterpret_cast<const double2*>(sm + j * NS);
+#pragma unroll
+                for (int q = 0; q < NS / 2; ++q) {
+                    double2 v = p2[q];
+                    s[2 * q] = v.x; s[2 * q + 1] = v.y;
+                }
+#pragma unroll
+                for (int t = 0; t < T; ++t) K::template pair<false>(prm, tg[t], s, acc[t], false);
+            }
+        } else {
+#pragma unroll 1
+            for (int j = 0; j < TS; ++j) {
+                double s[NS];
+                const double2* p2 = reinterpret_cast<const double2*>(sm + j * NS);
+#pragma unroll
+                for (int q = 0; q < NS / 2; ++q) {
+                    double2 v = p2[q];
+                    s[2 * q] = v.x; s[2 * q + 1] = v.y;
+                }
+#pragma unroll
+                for (int t = 0; t < T; ++t) K::template pair<true>(prm, tg[t], s, acc[t], (j0 + j) == self[t]);
+            }
+        }
+        __syncthreads();    // everyone is done with tile[st]
+        if (tid == 0 && k + 2 < ntiles) {
+            mbar_expect_tx(&full[st], kTileBytes);
+            tma_bulk_g2s(tile[st], src + (size_t)(s0 + (k + 2) * TS) * NS, kTileBytes, &full[st]);
+        }
+    }
+
+    if (g.nchunks == 1) {
+#pragma unroll
+        for (int t = 0; t < T; ++t)
+            if (live[t]) K::finalize(prm, tg[t], acc[t], blk0 + t * BLOCK + tid);
+    } else {
+#pragma unroll
+        for (int t = 0; t < T; ++t) {
+            if (!live[t]) continue;
+            const int64_t li = blk0 + t * BLOCK + tid - g.tbeg;
+#pragma unroll
+            for (int a = 0; a < NA; ++a) partial[((size_t)ck * NA + a) * g.ntgt + li] = acc[t][a];
+        }
+    }
+}
+
+// Adds the chunk partials in chunk order and writes the outputs.
+template <class K>
+__global__ void __launch_bounds__(256)
+ds_finalize_kernel(const typename K::Params prm, const DsGeom g, const double* __restrict__ partial)
+{
+    const int64_t li = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (li >= g.ntgt) return;
+    double acc[K::NA];
+#pragma unroll
+    for (int a = 0; a < K::NA; ++a) acc[a] = 0.0;
+    for (int c = 0; c < g.nchunks; ++c)
+#pragma unroll
+        for (int a = 0; a < K::NA; ++a) acc[a] = __dadd_rn(acc[a], partial[((size_t)c * K::NA + a) * g.ntgt + li]);
+    const int64_t i = g.tbeg + li;
+    typename K::Tgt tg = K::load_target(prm, i);
+    K::finalize(prm, tg, acc, i);
+}
+
+}  // namespace lpm

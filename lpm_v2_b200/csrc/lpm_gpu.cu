@@ -1,0 +1,484 @@
+// lpm_gpu.cu -- extern "C" entry points of liblpmgpu.so (see include/lpm_gpu.h).
+//
+// Host API:   stage the caller's arrays on every claimed device, run each
+//             device's LoadBalance slice, copy the slices back.
+// Device API: one slice on the current device / given stream (rank mode).
+#include "runtime.cuh"
+#include "ops.cuh"
+#include "solvers.cuh"
+
+using namespace lpm;
+
+// ============================================================== runtime
+extern "C" const char* lpm_gpu_last_error(void) { return last_error_ref().c_str(); }
+
+extern "C" int lpm_gpu_device_count(void) { return rt().initialised ? (int)rt().devs.size() : 0; }
+
+static int claim_devices(const std::vector<int>& ids)
+{
+    Runtime& R = rt();
+    R.devs.clear();
+    R.devs.resize(ids.size());
+    for (size_t k = 0; k < ids.size(); ++k) LPM_TRY(init_device(R.devs[k], ids[k]));
+    // peer access between every pair (single-process multi-GPU all-gather by peer stores)
+    for (size_t a = 0; a < ids.size(); ++a)
+        for (size_t b = 0; b < ids.size(); ++b) {
+            if (a == b) continue;
+            int can = 0;
+            LPM_CUDA(cudaDeviceCanAccessPeer(&can, ids[a], ids[b]));
+            if (!can)
+                return set_error(LPM_ERR_COMM, "device %d cannot access peer %d; multi-GPU mode needs NVLink/P2P",
+                                 ids[a], ids[b]);
+            LPM_CUDA(cudaSetDevice(ids[a]));
+            cudaError_t e = cudaDeviceEnablePeerAccess(ids[b], 0);
+            if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled)
+                return set_error(LPM_ERR_COMM, "cudaDeviceEnablePeerAccess(%d->%d): %s", ids[a], ids[b],
+                                 cudaGetErrorString(e));
+            cudaGetLastError();
+        }
+    LPM_CUDA(cudaSetDevice(ids[0]));
+    R.initialised = true;
+    R.launches = 0;
+    return LPM_OK;
+}
+
+extern "C" int lpm_gpu_init(int ndev_requested, int* ndev_used)
+{
+    Runtime& R = rt();
+    if (R.initialised) {
+        if (ndev_used) *ndev_used = (int)R.devs.size();
+        return LPM_OK;
+    }
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess || count == 0) {
+        cudaGetLastError();
+        return set_error(LPM_ERR_NO_DEVICE, "no CUDA device visible (%s); liblpmgpu has no CPU fallback",
+                         e != cudaSuccess ? cudaGetErrorString(e) : "device count 0");
+    }
+    if (ndev_requested < 0 || ndev_requested > count)
+        return set_error(LPM_ERR_INVALID, "requested %d devices, %d visible", ndev_requested, count);
+    int use = ndev_requested == 0 ? count : ndev_requested;
+    if (use > kMaxRep) use = kMaxRep;
+    std::vector<int> ids(use);
+    for (int k = 0; k < use; ++k) ids[k] = k;
+    R.rank_mode = false;
+    R.world = 1; R.rank = 0;
+    LPM_TRY(claim_devices(ids));
+    if (ndev_used) *ndev_used = use;
+    return LPM_OK;
+}
+
+extern "C" int lpm_gpu_init_rank(int device)
+{
+    Runtime& R = rt();
+    if (R.initialised) {
+        if (R.rank_mode && R.devs.size() == 1 && R.devs[0].id == device) return LPM_OK;
+        return set_error(LPM_ERR_INVALID, "liblpmgpu already initialised with a different configuration");
+    }
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess || count == 0) {
+        cudaGetLastError();
+        return set_error(LPM_ERR_NO_DEVICE, "no CUDA device visible (%s); liblpmgpu has no CPU fallback",
+                         e != cudaSuccess ? cudaGetErrorString(e) : "device count 0");
+    }
+    if (device < 0 || device >= count) return set_error(LPM_ERR_INVALID, "device %d of %d", device, count);
+    R.rank_mode = true;
+    R.world = 1; R.rank = 0;
+    return claim_devices({device});
+}
+
+extern "C" int lpm_gpu_finalize(void)
+{
+    Runtime& R = rt();
+    if (!R.initialised) return LPM_OK;
+    if (R.comm && nccl().loaded) nccl().CommDestroy(R.comm);
+    R.comm = nullptr;
+    for (auto& d : R.devs) {
+        cudaSetDevice(d.id);
+        cudaStreamSynchronize(d.stream);
+        d.ws.release();
+        cudaEventDestroy(d.ev_begin); cudaEventDestroy(d.ev_end); cudaEventDestroy(d.ev_done);
+        cudaStreamDestroy(d.stream);
+    }
+    R.devs.clear();
+    R.initialised = false;
+    R.world = 1; R.rank = 0;
+    return LPM_OK;
+}
+
+extern "C" int lpm_comm_unique_id(char id[128])
+{
+    LPM_TRY(load_nccl());
+    NcclApi::UniqueId u;
+    LPM_NCCL(nccl().GetUniqueId(&u));
+    memcpy(id, u.internal, 128);
+    return LPM_OK;
+}
+
+extern "C" int lpm_comm_init_rank(int world_size, int rank, const char id[128])
+{
+    Runtime& R = rt();
+    LPM_TRY(require_init());
+    if (!R.rank_mode) return set_error(LPM_ERR_INVALID, "lpm_comm_init_rank needs lpm_gpu_init_rank (one process per GPU)");
+    if (world_size < 1 || rank < 0 || rank >= world_size) return set_error(LPM_ERR_INVALID, "bad rank %d/%d", rank, world_size);
+    R.world = world_size; R.rank = rank;
+    if (world_size == 1) return LPM_OK;
+    LPM_TRY(load_nccl());
+    NcclApi::UniqueId u;
+    memcpy(u.internal, id, 128);
+    LPM_CUDA(cudaSetDevice(R.devs[0].id));
+    LPM_NCCL(nccl().CommInitRank(&R.comm, world_size, u, rank));
+    return LPM_OK;
+}
+
+extern "C" int lpm_comm_world_size(void) { return rt().world; }
+extern "C" int lpm_comm_rank(void) { return rt().rank; }
+
+extern "C" int lpm_comm_allgather_slices_dev(int ncomp, double* const* bufs, int64_t n, void* stream)
+{
+    LPM_TRY(require_init());
+    return allgather_slices(ncomp, bufs, n, (cudaStream_t)stream);
+}
+
+extern "C" int lpm_gpu_pin(void* ptr, int64_t bytes)
+{
+    LPM_TRY(require_init());
+    LPM_CUDA(cudaHostRegister(ptr, (size_t)bytes, cudaHostRegisterPortable));
+    return LPM_OK;
+}
+extern "C" int lpm_gpu_unpin(void* ptr)
+{
+    LPM_TRY(require_init());
+    LPM_CUDA(cudaHostUnregister(ptr));
+    return LPM_OK;
+}
+
+extern "C" int lpm_load_balance(int64_t n_items, int nprocs, int64_t* index_start, int64_t* index_end,
+                                int64_t* message_length)
+{
+    if (nprocs < 1 || n_items < 0) return set_error(LPM_ERR_INVALID, "lpm_load_balance(%lld, %d)", (long long)n_items, nprocs);
+    for (int r = 0; r < nprocs; ++r) {
+        int64_t b, e;
+        load_balance0(n_items, nprocs, r, &b, &e);
+        index_start[r] = b + 1;
+        index_end[r] = e;
+        if (message_length) message_length[r] = e - b;
+    }
+    return LPM_OK;
+}
+
+extern "C" int lpm_set_profiling(int enable) { rt().profiling = enable != 0; return LPM_OK; }
+extern "C" int lpm_set_bve_variant(int variant) { rt().bve_variant = variant; return LPM_OK; }
+extern "C" int64_t lpm_launch_count(int reset)
+{
+    int64_t v = rt().launches;
+    if (reset) rt().launches = 0;
+    return v;
+}
+extern "C" int lpm_last_kernel_ms(double* ms)
+{
+    Device* d = nullptr;
+    LPM_TRY(current_device(&d));
+    if (!d->timed) return set_error(LPM_ERR_INVALID, "no timed kernel (lpm_set_profiling(1) first)");
+    LPM_CUDA(cudaEventSynchronize(d->ev_end));
+    float f = 0;
+    LPM_CUDA(cudaEventElapsedTime(&f, d->ev_begin, d->ev_end));
+    *ms = f;
+    return LPM_OK;
+}
+
+// ---- FP64 peak probe ----------------------------------------------------------
+__global__ void __launch_bounds__(256) dfma_probe_kernel(int iters, double seed, double* sink)
+{
+    double a[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) a[k] = seed + k * 1e-3 + threadIdx.x * 1e-6;
+    const double m = 0.999999, c = 1e-7;
+    for (int it = 0; it < iters; ++it) {
+#pragma unroll
+        for (int r = 0; r < 8; ++r)
+#pragma unroll
+            for (int k = 0; k < 8; ++k) a[k] = fma(a[k], m, c);
+    }
+    double s = 0;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) s += a[k];
+    if (s == 123.456) sink[0] = s;
+}
+
+extern "C" int lpm_fp64_peak_probe(int iters, double* tflops, double* ms)
+{
+    Device* d = nullptr;
+    LPM_TRY(current_device(&d));
+    if (iters < 1) iters = 1;
+    LPM_TRY(d->ws.reduce.reserve(256));
+    const int blocks = d->sm_count * 8;
+    cudaEvent_t e0, e1;
+    LPM_CUDA(cudaEventCreate(&e0));
+    LPM_CUDA(cudaEventCreate(&e1));
+    dfma_probe_kernel<<<blocks, 256, 0, d->stream>>>(iters / 8 + 1, 1.0, d->ws.reduce.as<double>());   // warm-up
+    LPM_CUDA(cudaEventRecord(e0, d->stream));
+    dfma_probe_kernel<<<blocks, 256, 0, d->stream>>>(iters, 1.0, d->ws.reduce.as<double>());
+    LPM_CUDA(cudaEventRecord(e1, d->stream));
+    LPM_CUDA(cudaEventSynchronize(e1));
+    count_launch(2);
+    float f = 0;
+    LPM_CUDA(cudaEventElapsedTime(&f, e0, e1));
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
+    double flop = 2.0 * 64.0 * (double)iters * 256.0 * blocks;
+    if (tflops) *tflops = flop / (f * 1e-3) / 1e12;
+    if (ms) *ms = f;
+    return LPM_OK;
+}
+
+// ============================================================== active list
+extern "C" int lpm_active_list(int64_t n, const int32_t* mask, int32_t* list, int64_t* count)
+{
+    LPM_TRY(require_init());
+    Device& d = rt().devs[0];
+    LPM_CUDA(cudaSetDevice(d.id));
+    LPM_TRY(d.ws.staging[0].reserve((size_t)n * sizeof(int32_t)));
+    LPM_CUDA(cudaMemcpyAsync(d.ws.staging[0].p, mask, (size_t)n * sizeof(int32_t), cudaMemcpyHostToDevice, d.stream));
+    MaskPlan mp;
+    int rc = build_mask_plan(d.stream, n, d.ws.staging[0].as<int32_t>(), mp);
+    if (rc == LPM_OK) {
+        if (count) *count = mp.nsrc;
+        if (list && mp.nsrc > 0) {
+            cudaError_t e = cudaMemcpy(list, mp.active.p, (size_t)mp.nsrc * sizeof(int32_t), cudaMemcpyDeviceToHost);
+            if (e != cudaSuccess) rc = set_error(LPM_ERR_CUDA, "copy of active list failed: %s", cudaGetErrorString(e));
+        }
+    }
+    mp.release();
+    return rc;
+}
+
+// ============================================================== direct sums
+//
+// One description per kernel: how to pack sources and fill Params from the
+// staged device arrays.  `in[]` are the input arrays in header order (after
+// n), `out[]` the outputs; all device pointers.
+namespace {
+
+// Device API body: one slice on the current device.
+template <class Op>
+int run_dev(const Args& a, int64_t ibeg, int64_t iend, double* const* out, void* stream)
+{
+    Device* dev = nullptr;
+    LPM_TRY(current_device(&dev));
+    if (a.n <= 0) return set_error(LPM_ERR_INVALID, "n = %lld", (long long)a.n);
+    if (ibeg < 0 || iend > a.n || ibeg > iend)
+        return set_error(LPM_ERR_INVALID, "target range [%lld, %lld) outside [0, %lld)", (long long)ibeg, (long long)iend, (long long)a.n);
+    cudaStream_t st = (cudaStream_t)stream;
+    static thread_local MaskPlan mp;    // rebuilt per call; buffers reused
+    LPM_TRY(build_mask_plan(st, a.n, a.mask, mp));
+    LPM_TRY(Op::pack(*dev, st, mp, a));
+    typename Op::K::Params prm = Op::params(a);
+    set_outs(prm.out, out);
+    return direct_sum<typename Op::K>(*dev, st, mp, ibeg, iend, prm, Op::variant());
+}
+
+// Host API body: every claimed device (single-process mode) or this rank's
+// device (rank mode) evaluates its LoadBalance slice.
+template <class Op>
+int run_host(const Args& host, double* const* out_host)
+{
+    Runtime& R = rt();
+    LPM_TRY(require_init());
+    const int64_t n = host.n;
+    if (n <= 0) return set_error(LPM_ERR_INVALID, "n = %lld", (long long)n);
+    for (int k = 0; k < Op::NIN; ++k)
+        if (!host.in[k]) return set_error(LPM_ERR_INVALID, "null input array %d", k);
+    for (int k = 0; k < Op::NOUT; ++k)
+        if (!out_host[k]) return set_error(LPM_ERR_INVALID, "null output array %d", k);
+    if (!host.mask) return set_error(LPM_ERR_INVALID, "null mask");
+    const size_t nb = (size_t)n * sizeof(double);
+    const int nparts = R.rank_mode ? R.world : (int)R.devs.size();
+    int rc = LPM_OK;
+    static thread_local MaskPlan plans[kMaxRep];
+    for (size_t g = 0; g < R.devs.size() && rc == LPM_OK; ++g) {
+        Device& dev = R.devs[g];
+        auto body = [&]() -> int {
+            LPM_CUDA(cudaSetDevice(dev.id));
+            Args a = host;
+            for (int k = 0; k < Op::NIN; ++k) {
+                LPM_TRY(dev.ws.staging[k].reserve(nb));
+                LPM_CUDA(cudaMemcpyAsync(dev.ws.staging[k].p, host.in[k], nb, cudaMemcpyHostToDevice, dev.stream));
+                a.in[k] = dev.ws.staging[k].as<double>();
+            }
+            DevBuf& mbuf = dev.ws.staging[8];
+            LPM_TRY(mbuf.reserve((size_t)n * sizeof(int32_t)));
+            LPM_CUDA(cudaMemcpyAsync(mbuf.p, host.mask, (size_t)n * sizeof(int32_t), cudaMemcpyHostToDevice, dev.stream));
+            a.mask = mbuf.as<int32_t>();
+            double* out[4];
+            for (int k = 0; k < Op::NOUT; ++k) {
+                LPM_TRY(dev.ws.staging[9 + k].reserve(nb));
+                out[k] = dev.ws.staging[9 + k].as<double>();
+            }
+            LPM_TRY(build_mask_plan(dev.stream, n, a.mask, plans[g]));
+            LPM_TRY(Op::pack(dev, dev.stream, plans[g], a));
+            typename Op::K::Params prm = Op::params(a);
+            set_outs(prm.out, out);
+            int64_t b, e;
+            load_balance0(n, nparts, R.rank_mode ? R.rank : (int)g, &b, &e);
+            LPM_TRY(direct_sum<typename Op::K>(dev, dev.stream, plans[g], b, e, prm, Op::variant()));
+            if (R.rank_mode) {
+                LPM_TRY(allgather_slices(Op::NOUT, out, n, dev.stream));
+                b = 0; e = n;
+            }
+            for (int k = 0; k < Op::NOUT; ++k)
+                if (e > b)
+                    LPM_CUDA(cudaMemcpyAsync(out_host[k] + b, out[k] + b, (size_t)(e - b) * sizeof(double),
+                                             cudaMemcpyDeviceToHost, dev.stream));
+            return LPM_OK;
+        };
+        rc = body();
+    }
+    for (auto& dev : R.devs) {
+        cudaSetDevice(dev.id);
+        cudaError_t e = cudaStreamSynchronize(dev.stream);
+        if (e != cudaSuccess && rc == LPM_OK) rc = set_error(LPM_ERR_CUDA, "stream sync: %s", cudaGetErrorString(e));
+    }
+    cudaSetDevice(R.devs[0].id);
+    return rc;
+}
+
+}  // namespace
+
+// ---- BVE ----------------------------------------------------------------------
+extern "C" int lpm_bve_velocity(int64_t n, const double* x, const double* y, const double* z, const double* relvort,
+                                const double* area, const int32_t* mask, double radius, double* u, double* v, double* w)
+{
+    Args a{n, {x, y, z, relvort, area}, mask, {radius}};
+    double* out[3] = {u, v, w};
+    return run_host<OpBveVel>(a, out);
+}
+extern "C" int lpm_bve_velocity_dev(int64_t n, const double* x, const double* y, const double* z, const double* relvort,
+                                    const double* area, const int32_t* mask, double radius, int64_t ibeg, int64_t iend,
+                                    double* u, double* v, double* w, void* stream)
+{
+    Args a{n, {x, y, z, relvort, area}, mask, {radius}};
+    double* out[3] = {u, v, w};
+    return run_dev<OpBveVel>(a, ibeg, iend, out, stream);
+}
+extern "C" int lpm_bve_stream(int64_t n, const double* x, const double* y, const double* z, const double* relvort,
+                              const double* absvort, const double* area, const int32_t* mask, double radius,
+                              double* relstream, double* absstream)
+{
+    Args a{n, {x, y, z, relvort, absvort, area}, mask, {radius}};
+    double* out[2] = {relstream, absstream};
+    return run_host<OpBveStream>(a, out);
+}
+extern "C" int lpm_bve_stream_dev(int64_t n, const double* x, const double* y, const double* z, const double* relvort,
+                                  const double* absvort, const double* area, const int32_t* mask, double radius,
+                                  int64_t ibeg, int64_t iend, double* relstream, double* absstream, void* stream)
+{
+    Args a{n, {x, y, z, relvort, absvort, area}, mask, {radius}};
+    double* out[2] = {relstream, absstream};
+    return run_dev<OpBveStream>(a, ibeg, iend, out, stream);
+}
+
+// ---- plane --------------------------------------------------------------------
+extern "C" int lpm_plane_velocity(int64_t n, const double* x, const double* y, const double* vort, const double* area,
+                                  const int32_t* mask, double* u, double* v)
+{
+    Args a{n, {x, y, vort, area}, mask, {}};
+    double* out[2] = {u, v};
+    return run_host<OpPlaneVel>(a, out);
+}
+extern "C" int lpm_plane_velocity_dev(int64_t n, const double* x, const double* y, const double* vort,
+                                      const double* area, const int32_t* mask, int64_t ibeg, int64_t iend, double* u,
+                                      double* v, void* stream)
+{
+    Args a{n, {x, y, vort, area}, mask, {}};
+    double* out[2] = {u, v};
+    return run_dev<OpPlaneVel>(a, ibeg, iend, out, stream);
+}
+extern "C" int lpm_plane_stream(int64_t n, const double* x, const double* y, const double* vort, const double* area,
+                                const int32_t* mask, double* psi)
+{
+    Args a{n, {x, y, vort, area}, mask, {}};
+    double* out[1] = {psi};
+    return run_host<OpPlaneStream>(a, out);
+}
+extern "C" int lpm_plane_stream_dev(int64_t n, const double* x, const double* y, const double* vort, const double* area,
+                                    const int32_t* mask, int64_t ibeg, int64_t iend, double* psi, void* stream)
+{
+    Args a{n, {x, y, vort, area}, mask, {}};
+    double* out[1] = {psi};
+    return run_dev<OpPlaneStream>(a, ibeg, iend, out, stream);
+}
+
+// ---- beta plane ---------------------------------------------------------------
+extern "C" int lpm_betaplane_velocity(int64_t n, const double* x, const double* y, const double* relvort,
+                                      const double* area, const int32_t* mask, double* u, double* v)
+{
+    Args a{n, {x, y, relvort, area}, mask, {}};
+    double* out[2] = {u, v};
+    return run_host<OpBetaVel>(a, out);
+}
+extern "C" int lpm_betaplane_velocity_dev(int64_t n, const double* x, const double* y, const double* relvort,
+                                          const double* area, const int32_t* mask, int64_t ibeg, int64_t iend,
+                                          double* u, double* v, void* stream)
+{
+    Args a{n, {x, y, relvort, area}, mask, {}};
+    double* out[2] = {u, v};
+    return run_dev<OpBetaVel>(a, ibeg, iend, out, stream);
+}
+extern "C" int lpm_betaplane_stream(int64_t n, const double* x, const double* y, const double* relvort,
+                                    const double* absvort, const double* area, const int32_t* mask, double* relstream,
+                                    double* absstream)
+{
+    Args a{n, {x, y, relvort, absvort, area}, mask, {}};
+    double* out[2] = {relstream, absstream};
+    return run_host<OpBetaStream>(a, out);
+}
+extern "C" int lpm_betaplane_stream_dev(int64_t n, const double* x, const double* y, const double* relvort,
+                                        const double* absvort, const double* area, const int32_t* mask, int64_t ibeg,
+                                        int64_t iend, double* relstream, double* absstream, void* stream)
+{
+    Args a{n, {x, y, relvort, absvort, area}, mask, {}};
+    double* out[2] = {relstream, absstream};
+    return run_dev<OpBetaStream>(a, ibeg, iend, out, stream);
+}
+
+// ---- PSE ----------------------------------------------------------------------
+extern "C" int lpm_pse_laplacian_sphere(int64_t n, const double* x, const double* y, const double* z, const double* f,
+                                        const double* area, const int32_t* mask, double eps, double sphere_radius,
+                                        double* lap)
+{
+    if (!(eps > 0.0) || !(sphere_radius > 0.0)) return set_error(LPM_ERR_INVALID, "eps and sphere_radius must be positive");
+    Args a{n, {x, y, z, f, area}, mask, {eps, sphere_radius}};
+    double* out[1] = {lap};
+    return run_host<OpPseSphere>(a, out);
+}
+extern "C" int lpm_pse_laplacian_sphere_dev(int64_t n, const double* x, const double* y, const double* z,
+                                            const double* f, const double* area, const int32_t* mask, double eps,
+                                            double sphere_radius, int64_t ibeg, int64_t iend, double* lap, void* stream)
+{
+    if (!(eps > 0.0) || !(sphere_radius > 0.0)) return set_error(LPM_ERR_INVALID, "eps and sphere_radius must be positive");
+    Args a{n, {x, y, z, f, area}, mask, {eps, sphere_radius}};
+    double* out[1] = {lap};
+    return run_dev<OpPseSphere>(a, ibeg, iend, out, stream);
+}
+extern "C" int lpm_pse_laplacian_plane(int64_t n, const double* x, const double* y, const double* f, const double* area,
+                                       const int32_t* mask, double eps, double* lap)
+{
+    if (!(eps > 0.0)) return set_error(LPM_ERR_INVALID, "eps must be positive");
+    Args a{n, {x, y, f, area}, mask, {eps}};
+    double* out[1] = {lap};
+    return run_host<OpPsePlane>(a, out);
+}
+extern "C" int lpm_pse_laplacian_plane_dev(int64_t n, const double* x, const double* y, const double* f,
+                                           const double* area, const int32_t* mask, double eps, int64_t ibeg,
+                                           int64_t iend, double* lap, void* stream)
+{
+    if (!(eps > 0.0)) return set_error(LPM_ERR_INVALID, "eps must be positive");
+    Args a{n, {x, y, f, area}, mask, {eps}};
+    double* out[1] = {lap};
+    return run_dev<OpPsePlane>(a, ibeg, iend, out, stream);
+}
+
+// ============================================================== resident solvers
+#include "solvers_api.inc"

@@ -1,0 +1,190 @@
+// ops.cuh -- one description per direct sum: how to pack the active particles
+// into source records and how to fill the kernel Params from device arrays.
+// `in[]` are the input arrays in include/lpm_gpu.h order (after n); all device
+// pointers.  Shared by the one-shot entry points and the resident solvers.
+#pragma once
+#include "runtime.cuh"
+
+namespace lpm {
+
+struct Args {
+    int64_t n;
+    const double* in[8];
+    const int32_t* mask;
+    double sc[3];           // scalar arguments (radius / eps / sphere radius)
+};
+
+inline unsigned pack_grid(int32_t nsrc_pad) { return (unsigned)((nsrc_pad + 255) / 256); }
+
+template <int NO>
+inline void set_outs(Outs<NO>& o, double* const* out)
+{
+    o.nrep = 1;
+    for (int k = 0; k < NO; ++k) o.p[0][k] = out[k];
+}
+
+// ---- BVE velocity: in = x y z relvort area; sc = radius; out = u v w
+struct OpBveVel {
+    using K = BveVel;
+    static constexpr int NIN = 5, NOUT = 3;
+    static int pack(Device& dev, cudaStream_t st, const MaskPlan& mp, const Args& a)
+    {
+        int32_t pad;
+        LPM_TRY(reserve_sources<K>(dev, mp, &pad));
+        pack_bve_vel<<<pack_grid(pad), 256, 0, st>>>(mp.nsrc, pad, mp.active.as<int32_t>(), a.in[0], a.in[1], a.in[2],
+                                                     a.in[3], a.in[4], a.sc[0], dev.ws.sources.as<double>());
+        count_launch();
+        return LPM_OK;
+    }
+    static K::Params params(const Args& a)
+    {
+        K::Params p{};
+        p.x = a.in[0]; p.y = a.in[1]; p.z = a.in[2];
+        p.R2 = a.sc[0] * a.sc[0];
+        return p;
+    }
+    static int variant() { return rt().bve_variant; }
+};
+
+// ---- BVE stream: in = x y z relvort absvort area; sc = radius; out = relstream absstream
+struct OpBveStream {
+    using K = BveStream;
+    static constexpr int NIN = 6, NOUT = 2;
+    static int pack(Device& dev, cudaStream_t st, const MaskPlan& mp, const Args& a)
+    {
+        int32_t pad;
+        LPM_TRY(reserve_sources<K>(dev, mp, &pad));
+        pack_bve_stream<<<pack_grid(pad), 256, 0, st>>>(mp.nsrc, pad, mp.active.as<int32_t>(), a.in[0], a.in[1], a.in[2],
+                                                        a.in[3], a.in[4], a.in[5], a.sc[0], dev.ws.sources.as<double>());
+        count_launch();
+        return LPM_OK;
+    }
+    static K::Params params(const Args& a)
+    {
+        K::Params p{};
+        p.x = a.in[0]; p.y = a.in[1]; p.z = a.in[2];
+        p.R2 = a.sc[0] * a.sc[0];
+        return p;
+    }
+    static int variant() { return 0; }
+};
+
+// ---- planar velocity / stream: in = x y vort area
+template <class KK, bool STREAM>
+struct OpPlane {
+    using K = KK;
+    static constexpr int NIN = 4, NOUT = STREAM ? 1 : 2;
+    static int pack(Device& dev, cudaStream_t st, const MaskPlan& mp, const Args& a)
+    {
+        int32_t pad;
+        LPM_TRY(reserve_sources<K>(dev, mp, &pad));
+        const double inv_norm = STREAM ? 1.0 / (4.0 * LPM_PI) : 1.0 / (2.0 * LPM_PI);
+        pack_plane<<<pack_grid(pad), 256, 0, st>>>(mp.nsrc, pad, mp.active.as<int32_t>(), a.in[0], a.in[1], a.in[2],
+                                                   a.in[3], inv_norm, dev.ws.sources.as<double>());
+        count_launch();
+        return LPM_OK;
+    }
+    static typename K::Params params(const Args& a)
+    {
+        typename K::Params p{};
+        p.x = a.in[0]; p.y = a.in[1];
+        return p;
+    }
+    static int variant() { return 0; }
+};
+using OpPlaneVel = OpPlane<PlaneVel, false>;
+using OpPlaneStream = OpPlane<PlaneStream, true>;
+
+// ---- beta-plane velocity: in = x y relvort area;  stream: in = x y relvort absvort area
+struct OpBetaVel {
+    using K = BetaVel;
+    static constexpr int NIN = 4, NOUT = 2;
+    static int pack(Device& dev, cudaStream_t st, const MaskPlan& mp, const Args& a)
+    {
+        int32_t pad;
+        LPM_TRY(reserve_sources<K>(dev, mp, &pad));
+        pack_beta<<<pack_grid(pad), 256, 0, st>>>(mp.nsrc, pad, mp.active.as<int32_t>(), a.in[0], a.in[1], a.in[2],
+                                                  nullptr, a.in[3], 0, dev.ws.sources.as<double>());
+        count_launch();
+        return LPM_OK;
+    }
+    static K::Params params(const Args& a)
+    {
+        K::Params p{};
+        p.x = a.in[0]; p.y = a.in[1];
+        return p;
+    }
+    static int variant() { return 0; }
+};
+struct OpBetaStream {
+    using K = BetaStream;
+    static constexpr int NIN = 5, NOUT = 2;
+    static int pack(Device& dev, cudaStream_t st, const MaskPlan& mp, const Args& a)
+    {
+        int32_t pad;
+        LPM_TRY(reserve_sources<K>(dev, mp, &pad));
+        pack_beta<<<pack_grid(pad), 256, 0, st>>>(mp.nsrc, pad, mp.active.as<int32_t>(), a.in[0], a.in[1], a.in[2],
+                                                  a.in[3], a.in[4], 1, dev.ws.sources.as<double>());
+        count_launch();
+        return LPM_OK;
+    }
+    static K::Params params(const Args& a)
+    {
+        K::Params p{};
+        p.x = a.in[0]; p.y = a.in[1];
+        return p;
+    }
+    static int variant() { return 0; }
+};
+
+// ---- PSE sphere: in = x y z f area; sc = eps, sphere_radius
+struct OpPseSphere {
+    using K = PseSphere;
+    static constexpr int NIN = 5, NOUT = 1;
+    static int pack(Device& dev, cudaStream_t st, const MaskPlan& mp, const Args& a)
+    {
+        int32_t pad;
+        LPM_TRY(reserve_sources<K>(dev, mp, &pad));
+        pack_pse_sphere<<<pack_grid(pad), 256, 0, st>>>(mp.nsrc, pad, mp.active.as<int32_t>(), a.in[0], a.in[1], a.in[2],
+                                                        a.in[3], a.in[4], a.sc[0], dev.ws.sources.as<double>());
+        count_launch();
+        return LPM_OK;
+    }
+    static K::Params params(const Args& a)
+    {
+        K::Params p{};
+        p.x = a.in[0]; p.y = a.in[1]; p.z = a.in[2]; p.f = a.in[3];
+        const double eps = a.sc[0], sr = a.sc[1];
+        p.rad_over_eps = sr / eps;
+        const double theta_cut = kPseCut * eps / sr;
+        p.cos_cut = (theta_cut < LPM_PI) ? cos(theta_cut) : -2.0;
+        p.inv_eps2 = 1.0 / (eps * eps);
+        return p;
+    }
+    static int variant() { return 0; }
+};
+
+// ---- PSE plane: in = x y f area; sc = eps
+struct OpPsePlane {
+    using K = PsePlane;
+    static constexpr int NIN = 4, NOUT = 1;
+    static int pack(Device& dev, cudaStream_t st, const MaskPlan& mp, const Args& a)
+    {
+        int32_t pad;
+        LPM_TRY(reserve_sources<K>(dev, mp, &pad));
+        pack_pse_plane<<<pack_grid(pad), 256, 0, st>>>(mp.nsrc, pad, mp.active.as<int32_t>(), a.in[0], a.in[1], a.in[2],
+                                                       a.in[3], a.sc[0], dev.ws.sources.as<double>());
+        count_launch();
+        return LPM_OK;
+    }
+    static K::Params params(const Args& a)
+    {
+        K::Params p{};
+        p.x = a.in[0]; p.y = a.in[1]; p.f = a.in[2];
+        p.inv_eps2 = 1.0 / (a.sc[0] * a.sc[0]);
+        return p;
+    }
+    static int variant() { return 0; }
+};
+
+}  // namespace lpm

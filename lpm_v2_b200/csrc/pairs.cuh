@@ -1,0 +1,456 @@
+// pairs.cuh -- the pair kernels of the hot path, as functors for ds_kernel,
+// plus the kernels that pack the active particles into source records.
+//
+// Each functor cites the reference loop it replaces.  All arithmetic is FP64
+// (the reference's real(kreal) = kind(0.d0), src/TypeDefs.f90:25).  Constant
+// factors that the reference recomputes per pair (1/(4 pi R), 1/(2 pi), ...)
+// are folded into the per-source strength at pack time.
+#pragma once
+#include <cuda_runtime.h>
+#include <math_constants.h>
+
+#include <cstdint>
+
+namespace lpm {
+
+// src/TypeDefs.f90:31
+#define LPM_PI 3.1415926535897932384626433832795027975
+
+constexpr int kMaxRep = 8;      // output replicas (peer GPUs) one finalize can write
+
+// Output arrays of one direct sum, optionally replicated on peer devices: the
+// finalize step stores each result to every replica, which is the all-gather
+// of the reference's MPI_BCAST loop done with NVLink peer stores.
+template <int NO>
+struct Outs {
+    int nrep;
+    double* p[kMaxRep][NO];
+    __device__ __forceinline__ void store(int o, int64_t i, double v) const
+    {
+#pragma unroll 1
+        for (int r = 0; r < nrep; ++r) p[r][o][i] = v;
+    }
+};
+
+// 1/d for d > 0 to <= 1 ulp: MUFU.RCP64H seed (>= 20 bits) and one cubic
+// Newton step, r0 (1 + e + e^2) with e = 1 - d r0: 3 DFMA, relative error
+// e^3 < 2^-57 before rounding.  (An IEEE divide costs ~10 DFMA-pipe slots.)
+__device__ __forceinline__ double rcp_fast(double d)
+{
+    double r0;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r0) : "d"(d));
+    double e = fma(-d, r0, 1.0);
+    double t = fma(e, e, e);
+    return fma(r0, t, r0);
+}
+
+// =============================================================================
+// BVE velocity.  src/SphereBVESolver.f90:396-420 (== src/SphereBVE.f90:497-521):
+//   strength = -zeta_j A_j / (4 pi R (R^2 - x_i.x_j));  u_i += (x_i cross x_j) strength
+// Factored as u_i = x_i cross a_i,  a_i = sum_j P_j / (R^2 - x_i.x_j),
+// P_j = -zeta_j A_j/(4 pi R) x_j : 3 DFMA (denominator) + 3 (reciprocal) +
+// 3 (accumulate) + 1 MUFU per pair instead of the ~25 flops + divide as written.
+// Source record: x, y, z, Px, Py, Pz.
+struct BveVel {
+    static constexpr int NS = 6, NA = 3;
+    static constexpr bool SKIP_SELF = true;
+    struct Params {
+        const double *x, *y, *z;
+        double R2;
+        Outs<3> out;
+    };
+    struct Tgt { double x, y, z; };
+    __device__ static __forceinline__ Tgt load_target(const Params& p, int64_t i)
+    {
+        return Tgt{p.x[i], p.y[i], p.z[i]};
+    }
+    template <bool CHECK>
+    __device__ static __forceinline__ void pair(const Params& p, const Tgt& t, const double (&s)[NS],
+                                                double (&acc)[NA], bool skip)
+    {
+        double d = fma(-t.x, s[0], p.R2);
+        d = fma(-t.y, s[1], d);
+        d = fma(-t.z, s[2], d);
+        double r = rcp_fast(d);
+        if (CHECK) r = skip ? 0.0 : r;
+        acc[0] = fma(r, s[3], acc[0]);
+        acc[1] = fma(r, s[4], acc[1]);
+        acc[2] = fma(r, s[5], acc[2]);
+    }
+    __device__ static __forceinline__ void finalize(const Params& p, const Tgt& t, const double (&a)[NA], int64_t i)
+    {
+        p.out.store(0, i, fma(t.y, a[2], -(t.z * a[1])));
+        p.out.store(1, i, fma(t.z, a[0], -(t.x * a[2])));
+        p.out.store(2, i, fma(t.x, a[1], -(t.y * a[0])));
+    }
+};
+
+__global__ void pack_bve_vel(int32_t nsrc, int32_t nsrc_pad, const int32_t* __restrict__ active,
+                             const double* __restrict__ x, const double* __restrict__ y,
+                             const double* __restrict__ z, const double* __restrict__ zeta,
+                             const double* __restrict__ area, double R, double* __restrict__ src)
+{
+    int32_t c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= nsrc_pad) return;
+    double r[6] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0};     // null source: d = R^2, P = 0
+    if (c < nsrc) {
+        int32_t j = active[c];
+        double s = -zeta[j] * area[j] / (4.0 * LPM_PI * R);
+        r[0] = x[j]; r[1] = y[j]; r[2] = z[j];
+        r[3] = s * r[0]; r[4] = s * r[1]; r[5] = s * r[2];
+    }
+    double2* o = reinterpret_cast<double2*>(src + (size_t)c * 6);
+    o[0] = make_double2(r[0], r[1]); o[1] = make_double2(r[2], r[3]); o[2] = make_double2(r[4], r[5]);
+}
+
+// =============================================================================
+// BVE stream functions.  src/SphereBVE.f90:454-475:
+//   g = -log(R^2 - x_i.x_j)/(4 pi);  relStream_i += g zeta_j A_j;  absStream_i += g omega_j A_j
+// Source record: x, y, z, -zeta A/(4 pi), -omega A/(4 pi), 0.
+struct BveStream {
+    static constexpr int NS = 6, NA = 2;
+    static constexpr bool SKIP_SELF = true;
+    struct Params {
+        const double *x, *y, *z;
+        double R2;
+        Outs<2> out;
+    };
+    struct Tgt { double x, y, z; };
+    __device__ static __forceinline__ Tgt load_target(const Params& p, int64_t i)
+    {
+        return Tgt{p.x[i], p.y[i], p.z[i]};
+    }
+    template <bool CHECK>
+    __device__ static __forceinline__ void pair(const Params& p, const Tgt& t, const double (&s)[NS],
+                                                double (&acc)[NA], bool skip)
+    {
+        double d = fma(-t.x, s[0], p.R2);
+        d = fma(-t.y, s[1], d);
+        d = fma(-t.z, s[2], d);
+        if (CHECK) d = skip ? 1.0 : d;      // log(1) = 0 removes the pair
+        double l = log(d);
+        acc[0] = fma(l, s[3], acc[0]);
+        acc[1] = fma(l, s[4], acc[1]);
+    }
+    __device__ static __forceinline__ void finalize(const Params& p, const Tgt&, const double (&a)[NA], int64_t i)
+    {
+        p.out.store(0, i, a[0]);
+        p.out.store(1, i, a[1]);
+    }
+};
+
+__global__ void pack_bve_stream(int32_t nsrc, int32_t nsrc_pad, const int32_t* __restrict__ active,
+                                const double* __restrict__ x, const double* __restrict__ y,
+                                const double* __restrict__ z, const double* __restrict__ zeta,
+                                const double* __restrict__ omega, const double* __restrict__ area,
+                                double R, double* __restrict__ src)
+{
+    int32_t c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= nsrc_pad) return;
+    double r[6] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0};     // null source: log(R^2) * 0
+    if (c < nsrc) {
+        int32_t j = active[c];
+        r[0] = x[j]; r[1] = y[j]; r[2] = z[j];
+        r[3] = -zeta[j] * area[j] / (4.0 * LPM_PI);
+        r[4] = -omega[j] * area[j] / (4.0 * LPM_PI);
+    }
+    double2* o = reinterpret_cast<double2*>(src + (size_t)c * 6);
+    o[0] = make_double2(r[0], r[1]); o[1] = make_double2(r[2], r[3]); o[2] = make_double2(r[4], r[5]);
+}
+
+// =============================================================================
+// Planar Biot-Savart (singular).  src/PlaneIncompressibleSolver.f90:294-307
+// (== src/PlanarIncompressible.f90:437-456):
+//   strength = omega_j A_j / (2 pi ((x_i-x_j)^2 + (y_i-y_j)^2))
+//   u_i -= (y_i-y_j) strength;  v_i += (x_i-x_j) strength
+// Source record: x, y, omega A/(2 pi), 0.
+struct PlaneVel {
+    static constexpr int NS = 4, NA = 2;
+    static constexpr bool SKIP_SELF = true;
+    struct Params {
+        const double *x, *y;
+        Outs<2> out;
+    };
+    struct Tgt { double x, y; };
+    __device__ static __forceinline__ Tgt load_target(const Params& p, int64_t i) { return Tgt{p.x[i], p.y[i]}; }
+    template <bool CHECK>
+    __device__ static __forceinline__ void pair(const Params&, const Tgt& t, const double (&s)[NS],
+                                                double (&acc)[NA], bool skip)
+    {
+        double dx = t.x - s[0], dy = t.y - s[1];
+        double r2 = fma(dx, dx, dy * dy);
+        double w = rcp_fast(r2) * s[2];
+        if (CHECK) w = skip ? 0.0 : w;
+        acc[0] = fma(-dy, w, acc[0]);
+        acc[1] = fma(dx, w, acc[1]);
+    }
+    __device__ static __forceinline__ void finalize(const Params& p, const Tgt&, const double (&a)[NA], int64_t i)
+    {
+        p.out.store(0, i, a[0]);
+        p.out.store(1, i, a[1]);
+    }
+};
+
+// Null source for the planar kernels: far away (r^2 ~ 2e300, finite) with zero strength.
+#define LPM_PLANE_FAR 1.0e150
+
+__global__ void pack_plane(int32_t nsrc, int32_t nsrc_pad, const int32_t* __restrict__ active,
+                           const double* __restrict__ x, const double* __restrict__ y,
+                           const double* __restrict__ vort, const double* __restrict__ area,
+                           double inv_norm, double* __restrict__ src)
+{
+    int32_t c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= nsrc_pad) return;
+    double r[4] = {LPM_PLANE_FAR, LPM_PLANE_FAR, 0.0, 0.0};
+    if (c < nsrc) {
+        int32_t j = active[c];
+        r[0] = x[j]; r[1] = y[j];
+        r[2] = vort[j] * area[j] * inv_norm;      // 1/(2 pi) velocity, 1/(4 pi) stream fn
+    }
+    double2* o = reinterpret_cast<double2*>(src + (size_t)c * 4);
+    o[0] = make_double2(r[0], r[1]); o[1] = make_double2(r[2], r[3]);
+}
+
+// Planar stream function.  src/PlanarIncompressible.f90:481-497:
+//   psi_i += log(sqrt(r^2))/(2 pi) omega_j A_j  ==  log(r^2) omega_j A_j/(4 pi)
+struct PlaneStream {
+    static constexpr int NS = 4, NA = 1;
+    static constexpr bool SKIP_SELF = true;
+    struct Params {
+        const double *x, *y;
+        Outs<1> out;
+    };
+    struct Tgt { double x, y; };
+    __device__ static __forceinline__ Tgt load_target(const Params& p, int64_t i) { return Tgt{p.x[i], p.y[i]}; }
+    template <bool CHECK>
+    __device__ static __forceinline__ void pair(const Params&, const Tgt& t, const double (&s)[NS],
+                                                double (&acc)[NA], bool skip)
+    {
+        double dx = t.x - s[0], dy = t.y - s[1];
+        double r2 = fma(dx, dx, dy * dy);
+        if (CHECK) r2 = skip ? 1.0 : r2;
+        acc[0] = fma(log(r2), s[2], acc[0]);
+    }
+    __device__ static __forceinline__ void finalize(const Params& p, const Tgt&, const double (&a)[NA], int64_t i)
+    {
+        p.out.store(0, i, a[0]);
+    }
+};
+
+// =============================================================================
+// Beta-plane (x-periodic, period 1) Biot-Savart.  src/BetaPlaneSolver.f90:243-258
+// (== src/BetaPlane.f90:369-388):
+//   strength = 0.5 zeta_j A_j / (cosh(2 pi dy) - cos(2 pi dx))
+//   u_i -= sinh(2 pi dy) strength;  v_i += sin(2 pi dx) strength
+// With S = sinh(pi dy), C = cosh(pi dy), s = sin(pi dx), c = cos(pi dx):
+//   cosh(2 pi dy) - cos(2 pi dx) = 2 (S^2 + s^2)   (no cancellation for near pairs),
+//   sinh(2 pi dy) = 2 S C,  sin(2 pi dx) = 2 s c,
+// and S, C, s, c follow from per-particle sinh/cosh(pi y), sin/cos(pi x) by
+// the addition formulas, so no transcendental is evaluated per pair.
+// Source record: sh, ch, sn, cs, zeta A / 2, 0.
+struct BetaVel {
+    static constexpr int NS = 6, NA = 2;
+    static constexpr bool SKIP_SELF = true;
+    struct Params {
+        const double *x, *y;
+        Outs<2> out;
+    };
+    struct Tgt { double sh, ch, sn, cs; };
+    __device__ static __forceinline__ Tgt load_target(const Params& p, int64_t i)
+    {
+        Tgt t;
+        double a = LPM_PI * p.y[i];
+        t.sh = sinh(a); t.ch = cosh(a);
+        sincospi(p.x[i], &t.sn, &t.cs);
+        return t;
+    }
+    template <bool CHECK>
+    __device__ static __forceinline__ void pair(const Params&, const Tgt& t, const double (&s)[NS],
+                                                double (&acc)[NA], bool skip)
+    {
+        double S = fma(t.sh, s[1], -(t.ch * s[0]));
+        double C = fma(t.ch, s[1], -(t.sh * s[0]));
+        double sn = fma(t.sn, s[3], -(t.cs * s[2]));
+        double cs = fma(t.cs, s[3], t.sn * s[2]);
+        double den = fma(S, S, sn * sn);
+        double w = rcp_fast(den) * s[4];
+        if (CHECK) w = skip ? 0.0 : w;
+        acc[0] = fma(-(S * C), w, acc[0]);
+        acc[1] = fma(sn * cs, w, acc[1]);
+    }
+    __device__ static __forceinline__ void finalize(const Params& p, const Tgt&, const double (&a)[NA], int64_t i)
+    {
+        p.out.store(0, i, a[0]);
+        p.out.store(1, i, a[1]);
+    }
+};
+
+// Beta-plane stream functions.  src/BetaPlane.f90:409-431:
+//   g = log(cosh(2 pi dy) - cos(2 pi dx))/(4 pi) = log(2 (S^2 + s^2))/(4 pi)
+// Source record: sh, ch, sn, cs, zeta A/(4 pi), omega A/(4 pi).
+struct BetaStream {
+    static constexpr int NS = 6, NA = 2;
+    static constexpr bool SKIP_SELF = true;
+    using Params = BetaVel::Params;
+    using Tgt = BetaVel::Tgt;
+    __device__ static __forceinline__ Tgt load_target(const Params& p, int64_t i) { return BetaVel::load_target(p, i); }
+    template <bool CHECK>
+    __device__ static __forceinline__ void pair(const Params&, const Tgt& t, const double (&s)[NS],
+                                                double (&acc)[NA], bool skip)
+    {
+        double S = fma(t.sh, s[1], -(t.ch * s[0]));
+        double sn = fma(t.sn, s[3], -(t.cs * s[2]));
+        double den = 2.0 * fma(S, S, sn * sn);
+        if (CHECK) den = skip ? 1.0 : den;
+        double l = log(den);
+        acc[0] = fma(l, s[4], acc[0]);
+        acc[1] = fma(l, s[5], acc[1]);
+    }
+    __device__ static __forceinline__ void finalize(const Params& p, const Tgt&, const double (&a)[NA], int64_t i)
+    {
+        p.out.store(0, i, a[0]);
+        p.out.store(1, i, a[1]);
+    }
+};
+
+// mode 0: velocity record (zeta A/2, 0); mode 1: stream record (zeta A/(4 pi), omega A/(4 pi)).
+// Null source: sh = ch = 1e10 gives S = 1e10 (sh_i - ch_i) /= 0 for every target; zero strength.
+__global__ void pack_beta(int32_t nsrc, int32_t nsrc_pad, const int32_t* __restrict__ active,
+                          const double* __restrict__ x, const double* __restrict__ y,
+                          const double* __restrict__ zeta, const double* __restrict__ omega,
+                          const double* __restrict__ area, int mode, double* __restrict__ src)
+{
+    int32_t c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= nsrc_pad) return;
+    double r[6] = {1.0e10, 1.0e10, 0.0, 1.0, 0.0, 0.0};
+    if (c < nsrc) {
+        int32_t j = active[c];
+        double a = LPM_PI * y[j];
+        r[0] = sinh(a); r[1] = cosh(a);
+        sincospi(x[j], &r[2], &r[3]);
+        if (mode == 0) {
+            r[4] = 0.5 * zeta[j] * area[j];
+        } else {
+            r[4] = zeta[j] * area[j] / (4.0 * LPM_PI);
+            r[5] = omega[j] * area[j] / (4.0 * LPM_PI);
+        }
+    }
+    double2* o = reinterpret_cast<double2*>(src + (size_t)c * 6);
+    o[0] = make_double2(r[0], r[1]); o[1] = make_double2(r[2], r[3]); o[2] = make_double2(r[4], r[5]);
+}
+
+// =============================================================================
+// PSE Laplacian.  src/PSEDirectSum.f90:467-535, kernel :622-627:
+//   lap_i = eps^-2 sum_{j active} (f_j - f_i) eta(d_ij/eps)/eps^2 A_j,
+//   eta(k) = (40 - 40 k^2 + 10 k^4 - 2/3 k^6) exp(-k^2)/pi
+// j == i is included (the term is exactly zero).  eta decays like exp(-k^2):
+// pairs with k > kPseCut contribute < 1e-23 of eta(0) and are skipped.
+constexpr double kPseCut = 8.0;
+
+__device__ __forceinline__ double pse_eta_pi(double k2)    // pi * eta
+{
+    double poly = fma(fma(fma(-2.0 / 3.0, k2, 10.0), k2, -40.0), k2, 40.0);
+    return poly * exp(-k2);
+}
+
+// Sphere: d_ij = atan2(|x_i cross x_j|, x_i.x_j) * SphereRadius  (src/SphereGeometry.f90:107-125).
+// Source record: x, y, z, f, A/(pi eps^2), |x_j|.
+struct PseSphere {
+    static constexpr int NS = 6, NA = 1;
+    static constexpr bool SKIP_SELF = false;
+    struct Params {
+        const double *x, *y, *z, *f;
+        double rad_over_eps;     // SphereRadius / eps
+        double cos_cut;          // cos(kPseCut eps / SphereRadius), or -2 if the cut-off exceeds pi
+        double inv_eps2;
+        Outs<1> out;
+    };
+    struct Tgt { double x, y, z, f, thr; };
+    __device__ static __forceinline__ Tgt load_target(const Params& p, int64_t i)
+    {
+        Tgt t{p.x[i], p.y[i], p.z[i], p.f[i], 0.0};
+        t.thr = p.cos_cut * sqrt(t.x * t.x + t.y * t.y + t.z * t.z);
+        return t;
+    }
+    template <bool CHECK>
+    __device__ static __forceinline__ void pair(const Params& p, const Tgt& t, const double (&s)[NS],
+                                                double (&acc)[NA], bool)
+    {
+        double dot = fma(t.x, s[0], fma(t.y, s[1], t.z * s[2]));
+        if (dot < t.thr * s[5]) return;           // angle beyond the cut-off
+        double c0 = fma(t.y, s[2], -(s[1] * t.z));
+        double c1 = fma(s[0], t.z, -(t.x * s[2]));
+        double c2 = fma(t.x, s[1], -(s[0] * t.y));
+        double cn = sqrt(fma(c0, c0, fma(c1, c1, c2 * c2)));
+        double k = atan2(cn, dot) * p.rad_over_eps;
+        acc[0] = fma((s[3] - t.f) * pse_eta_pi(k * k), s[4], acc[0]);
+    }
+    __device__ static __forceinline__ void finalize(const Params& p, const Tgt&, const double (&a)[NA], int64_t i)
+    {
+        p.out.store(0, i, a[0] * p.inv_eps2);
+    }
+};
+
+__global__ void pack_pse_sphere(int32_t nsrc, int32_t nsrc_pad, const int32_t* __restrict__ active,
+                                const double* __restrict__ x, const double* __restrict__ y,
+                                const double* __restrict__ z, const double* __restrict__ f,
+                                const double* __restrict__ area, double eps, double* __restrict__ src)
+{
+    int32_t c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= nsrc_pad) return;
+    double r[6] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0};     // null source: zero area
+    if (c < nsrc) {
+        int32_t j = active[c];
+        r[0] = x[j]; r[1] = y[j]; r[2] = z[j]; r[3] = f[j];
+        r[4] = area[j] / (LPM_PI * eps * eps);
+        r[5] = sqrt(r[0] * r[0] + r[1] * r[1] + r[2] * r[2]);
+    }
+    double2* o = reinterpret_cast<double2*>(src + (size_t)c * 6);
+    o[0] = make_double2(r[0], r[1]); o[1] = make_double2(r[2], r[3]); o[2] = make_double2(r[4], r[5]);
+}
+
+// Plane: d_ij = ChordDistance with z = 0 (src/SphereGeometry.f90:67-73, src/Particles.f90:663-670).
+// Source record: x, y, f, A/(pi eps^2).
+struct PsePlane {
+    static constexpr int NS = 4, NA = 1;
+    static constexpr bool SKIP_SELF = false;
+    struct Params {
+        const double *x, *y, *f;
+        double inv_eps2;
+        Outs<1> out;
+    };
+    struct Tgt { double x, y, f; };
+    __device__ static __forceinline__ Tgt load_target(const Params& p, int64_t i) { return Tgt{p.x[i], p.y[i], p.f[i]}; }
+    template <bool CHECK>
+    __device__ static __forceinline__ void pair(const Params& p, const Tgt& t, const double (&s)[NS],
+                                                double (&acc)[NA], bool)
+    {
+        double dx = s[0] - t.x, dy = s[1] - t.y;
+        double k2 = fma(dx, dx, dy * dy) * p.inv_eps2;
+        if (k2 > kPseCut * kPseCut) return;
+        acc[0] = fma((s[2] - t.f) * pse_eta_pi(k2), s[3], acc[0]);
+    }
+    __device__ static __forceinline__ void finalize(const Params& p, const Tgt&, const double (&a)[NA], int64_t i)
+    {
+        p.out.store(0, i, a[0] * p.inv_eps2);
+    }
+};
+
+__global__ void pack_pse_plane(int32_t nsrc, int32_t nsrc_pad, const int32_t* __restrict__ active,
+                               const double* __restrict__ x, const double* __restrict__ y,
+                               const double* __restrict__ f, const double* __restrict__ area,
+                               double eps, double* __restrict__ src)
+{
+    int32_t c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= nsrc_pad) return;
+    double r[4] = {0.0, 0.0, 0.0, 0.0};
+    if (c < nsrc) {
+        int32_t j = active[c];
+        r[0] = x[j]; r[1] = y[j]; r[2] = f[j];
+        r[3] = area[j] / (LPM_PI * eps * eps);
+    }
+    double2* o = reinterpret_cast<double2*>(src + (size_t)c * 4);
+    o[0] = make_double2(r[0], r[1]); o[1] = make_double2(r[2], r[3]);
+}
+
+}  // namespace lpm

@@ -1,0 +1,265 @@
+// runtime.cuh -- device claiming, NCCL (loaded lazily with dlopen), the mask
+// plan and the direct-sum launcher.
+#pragma once
+#include <dlfcn.h>
+
+#include <algorithm>
+
+#include "common.cuh"
+#include "directsum.cuh"
+#include "pairs.cuh"
+#include "scan.cuh"
+
+namespace lpm {
+
+// ---------------------------------------------------------------- devices
+inline int init_device(Device& d, int id)
+{
+    d.id = id;
+    LPM_CUDA(cudaSetDevice(id));
+    cudaDeviceProp prop;
+    LPM_CUDA(cudaGetDeviceProperties(&prop, id));
+    if (prop.major != 10)
+        return set_error(LPM_ERR_NO_DEVICE, "device %d (%s) is sm_%d%d; liblpmgpu is built for sm_100a only", id,
+                         prop.name, prop.major, prop.minor);
+    d.sm_count = prop.multiProcessorCount;
+    LPM_CUDA(cudaStreamCreateWithFlags(&d.stream, cudaStreamNonBlocking));
+    LPM_CUDA(cudaEventCreate(&d.ev_begin));
+    LPM_CUDA(cudaEventCreate(&d.ev_end));
+    LPM_CUDA(cudaEventCreateWithFlags(&d.ev_done, cudaEventDisableTiming));
+    return LPM_OK;
+}
+
+inline int require_init()
+{
+    if (!rt().initialised)
+        return set_error(LPM_ERR_NO_DEVICE, "liblpmgpu: not initialised (call lpm_gpu_init or lpm_gpu_init_rank); "
+                                            "there is no CPU fallback");
+    return LPM_OK;
+}
+
+// the Device entry for the CUDA device that is current on this thread
+inline int current_device(Device** out)
+{
+    LPM_TRY(require_init());
+    int id = -1;
+    LPM_CUDA(cudaGetDevice(&id));
+    for (auto& d : rt().devs)
+        if (d.id == id) { *out = &d; return LPM_OK; }
+    return set_error(LPM_ERR_NO_DEVICE, "current CUDA device %d was not claimed by lpm_gpu_init", id);
+}
+
+// ---------------------------------------------------------------- NCCL
+// Only the handful of entry points the slice exchange needs, resolved at
+// run time so the library loads (and single-GPU runs work) without NCCL.
+struct NcclApi {
+    typedef struct { char internal[128]; } UniqueId;
+    int (*GetUniqueId)(UniqueId*) = nullptr;
+    int (*CommInitRank)(void**, int, UniqueId, int) = nullptr;
+    int (*CommDestroy)(void*) = nullptr;
+    int (*Broadcast)(const void*, void*, size_t, int, int, void*, cudaStream_t) = nullptr;
+    int (*GroupStart)() = nullptr;
+    int (*GroupEnd)() = nullptr;
+    const char* (*GetErrorString)(int) = nullptr;
+    bool loaded = false;
+};
+inline NcclApi& nccl()
+{
+    static NcclApi a;
+    return a;
+}
+inline int load_nccl()
+{
+    NcclApi& a = nccl();
+    if (a.loaded) return LPM_OK;
+    void* h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_NOLOAD);     // the copy torch already mapped, if any
+    if (!h) h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+    if (!h) h = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
+    if (!h) return set_error(LPM_ERR_COMM, "cannot load libnccl.so.2: %s", dlerror());
+    rt().nccl_lib = h;
+#define LPM_SYM(field, name)                                                            \
+    *(void**)(&a.field) = dlsym(h, name);                                               \
+    if (!a.field) return set_error(LPM_ERR_COMM, "libnccl: missing symbol %s", name)
+    LPM_SYM(GetUniqueId, "ncclGetUniqueId");
+    LPM_SYM(CommInitRank, "ncclCommInitRank");
+    LPM_SYM(CommDestroy, "ncclCommDestroy");
+    LPM_SYM(Broadcast, "ncclBroadcast");
+    LPM_SYM(GroupStart, "ncclGroupStart");
+    LPM_SYM(GroupEnd, "ncclGroupEnd");
+    LPM_SYM(GetErrorString, "ncclGetErrorString");
+#undef LPM_SYM
+    a.loaded = true;
+    return LPM_OK;
+}
+#define LPM_NCCL(expr)                                                                              \
+    do {                                                                                            \
+        int _r = (expr);                                                                            \
+        if (_r != 0)                                                                                \
+            return ::lpm::set_error(LPM_ERR_COMM, "%s failed: %s", #expr, nccl().GetErrorString(_r)); \
+    } while (0)
+
+// src/MPISetup.f90:132-146 LoadBalance, 0-based half-open form
+inline void load_balance0(int64_t n, int nprocs, int r, int64_t* beg, int64_t* end)
+{
+    int64_t chunk = n / nprocs;
+    *beg = (int64_t)r * chunk;
+    *end = (r == nprocs - 1) ? n : (int64_t)(r + 1) * chunk;
+}
+
+// In-place exchange of every rank's slice (the reference's loop of MPI_BCAST
+// rooted at each rank in turn, src/SphereBVESolver.f90:422-429), as one NCCL group.
+inline int allgather_slices(int ncomp, double* const* bufs, int64_t n, cudaStream_t st)
+{
+    Runtime& R = rt();
+    if (R.world <= 1) return LPM_OK;
+    if (!R.comm) return set_error(LPM_ERR_COMM, "world size %d but no communicator (lpm_comm_init_rank)", R.world);
+    LPM_NCCL(nccl().GroupStart());
+    for (int r = 0; r < R.world; ++r) {
+        int64_t b, e;
+        load_balance0(n, R.world, r, &b, &e);
+        if (e <= b) continue;
+        for (int c = 0; c < ncomp; ++c)
+            LPM_NCCL(nccl().Broadcast(bufs[c] + b, bufs[c] + b, (size_t)(e - b), /*ncclDouble*/ 8, r, R.comm, st));
+    }
+    LPM_NCCL(nccl().GroupEnd());
+    return LPM_OK;
+}
+
+// ---------------------------------------------------------------- mask plan
+struct MaskPlan {
+    int64_t n = 0;
+    int32_t nsrc = 0;
+    DevBuf scan, active, blocksums;
+    void release() { scan.release(); active.release(); blocksums.release(); }
+};
+
+// Scans the device mask; synchronises `st` once to read the active count.
+inline int build_mask_plan(cudaStream_t st, int64_t n, const int32_t* mask_dev, MaskPlan& mp)
+{
+    if (n <= 0 || n > 0x7ffffff0LL) return set_error(LPM_ERR_INVALID, "particle count %lld out of range", (long long)n);
+    const int nblocks = (int)((n + kScanBlock - 1) / kScanBlock);
+    LPM_TRY(mp.scan.reserve((size_t)(n + 1) * sizeof(int32_t)));
+    LPM_TRY(mp.active.reserve((size_t)n * sizeof(int32_t)));
+    LPM_TRY(mp.blocksums.reserve((size_t)(nblocks + 1) * sizeof(int32_t)));
+    scan_count<<<nblocks, kScanBlock, 0, st>>>(n, mask_dev, mp.blocksums.as<int32_t>());
+    scan_blocksums<<<1, kScanBlock, 0, st>>>(nblocks, mp.blocksums.as<int32_t>());
+    scan_scatter<<<nblocks, kScanBlock, 0, st>>>(n, mask_dev, mp.blocksums.as<int32_t>(), nblocks,
+                                                 mp.scan.as<int32_t>(), mp.active.as<int32_t>());
+    count_launch(3);
+    LPM_CUDA(cudaGetLastError());
+    int32_t total = 0;
+    LPM_CUDA(cudaMemcpyAsync(&total, mp.scan.as<int32_t>() + n, sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+    LPM_CUDA(cudaStreamSynchronize(st));
+    mp.n = n;
+    mp.nsrc = total;
+    return LPM_OK;
+}
+
+// ---------------------------------------------------------------- launcher
+template <class K, int T, int BLOCK, int U>
+inline void launch_ds(cudaStream_t st, const typename K::Params& prm, DsGeom g, const double* src,
+                      const int32_t* scan, double* partial)
+{
+    g.ntblocks = (int32_t)((g.ntgt + BLOCK * T - 1) / (BLOCK * T));
+    const int64_t grid = (int64_t)g.ntblocks * g.nchunks;
+    ds_kernel<K, T, BLOCK, U><<<(unsigned)grid, BLOCK, 0, st>>>(prm, g, src, scan, partial);
+}
+
+// variant: 0 = automatic choice of targets-per-thread by problem size.
+template <class K>
+inline int launch_variant(int variant, cudaStream_t st, const typename K::Params& prm, const DsGeom& g,
+                          const double* src, const int32_t* scan, double* partial, int sm_count);
+
+// Packs nothing: the caller has already written the source records for this
+// evaluation into ws.sources (see the api functions).  Runs targets
+// [tbeg, tend) against all sources and writes the outputs named in prm.out.
+template <class K>
+inline int direct_sum(Device& dev, cudaStream_t st, const MaskPlan& mp, int64_t tbeg, int64_t tend,
+                      const typename K::Params& prm, int variant = 0)
+{
+    if (tend <= tbeg) return LPM_OK;
+    DsGeom g{};
+    g.tbeg = tbeg; g.tend = tend; g.ntgt = tend - tbeg;
+    g.nsrc = mp.nsrc;
+    ds_chunks(mp.nsrc, &g.nsrc_pad, &g.chunk, &g.nchunks);
+    double* partial = nullptr;
+    if (g.nchunks > 1) {
+        LPM_TRY(dev.ws.partial.reserve((size_t)g.nchunks * K::NA * g.ntgt * sizeof(double)));
+        partial = dev.ws.partial.as<double>();
+    }
+    const bool prof = rt().profiling;
+    if (prof) LPM_CUDA(cudaEventRecord(dev.ev_begin, st));
+    LPM_TRY(launch_variant<K>(variant, st, prm, g, dev.ws.sources.as<double>(), mp.scan.as<int32_t>(), partial,
+                              dev.sm_count));
+    if (prof) { LPM_CUDA(cudaEventRecord(dev.ev_end, st)); dev.timed = true; }
+    count_launch();
+    if (g.nchunks > 1) {
+        const unsigned nb = (unsigned)((g.ntgt + 255) / 256);
+        ds_finalize_kernel<K><<<nb, 256, 0, st>>>(prm, g, partial);
+        count_launch();
+    }
+    LPM_CUDA(cudaGetLastError());
+    return LPM_OK;
+}
+
+// number of source-record doubles the pack kernels must fill for this plan
+template <class K>
+inline int reserve_sources(Device& dev, const MaskPlan& mp, int32_t* nsrc_pad)
+{
+    int32_t chunk, nchunks;
+    ds_chunks(mp.nsrc, nsrc_pad, &chunk, &nchunks);
+    return dev.ws.sources.reserve((size_t)(*nsrc_pad) * K::NS * sizeof(double));
+}
+
+// Heuristic shared by all kernels: largest T that still yields >= 2 CTAs per SM.
+inline int auto_T(int64_t ntgt, int nchunks, int sm_count, int block)
+{
+    const int64_t want = 2LL * sm_count;
+    for (int T : {4, 2}) {
+        int64_t items = (ntgt + (int64_t)block * T - 1) / ((int64_t)block * T) * nchunks;
+        if (items >= want) return T;
+    }
+    return 1;
+}
+
+template <class K>
+inline int launch_variant(int variant, cudaStream_t st, const typename K::Params& prm, const DsGeom& g,
+                          const double* src, const int32_t* scan, double* partial, int sm_count)
+{
+    int T = auto_T(g.ntgt, g.nchunks, sm_count, 128);
+    (void)variant;
+    switch (T) {
+        case 4: launch_ds<K, 4, 128, 1>(st, prm, g, src, scan, partial); break;
+        case 2: launch_ds<K, 2, 128, 2>(st, prm, g, src, scan, partial); break;
+        default: launch_ds<K, 1, 128, 4>(st, prm, g, src, scan, partial); break;
+    }
+    return LPM_OK;
+}
+
+// The BVE velocity kernel (the headline path) has extra variants for tuning.
+template <>
+inline int launch_variant<BveVel>(int variant, cudaStream_t st, const BveVel::Params& prm, const DsGeom& g,
+                                  const double* src, const int32_t* scan, double* partial, int sm_count)
+{
+    using K = BveVel;
+    if (variant == 0) {
+        int T = auto_T(g.ntgt, g.nchunks, sm_count, 128);
+        variant = (T == 4) ? 1 : (T == 2) ? 5 : 6;
+    }
+    switch (variant) {
+        case 1: launch_ds<K, 4, 128, 2>(st, prm, g, src, scan, partial); break;
+        case 2: launch_ds<K, 8, 128, 1>(st, prm, g, src, scan, partial); break;
+        case 3: launch_ds<K, 4, 256, 2>(st, prm, g, src, scan, partial); break;
+        case 4: launch_ds<K, 6, 128, 2>(st, prm, g, src, scan, partial); break;
+        case 5: launch_ds<K, 2, 128, 4>(st, prm, g, src, scan, partial); break;
+        case 6: launch_ds<K, 1, 128, 4>(st, prm, g, src, scan, partial); break;
+        case 7: launch_ds<K, 4, 128, 4>(st, prm, g, src, scan, partial); break;
+        case 8: launch_ds<K, 2, 256, 4>(st, prm, g, src, scan, partial); break;
+        case 9: launch_ds<K, 4, 64, 2>(st, prm, g, src, scan, partial); break;
+        case 10: launch_ds<K, 8, 64, 2>(st, prm, g, src, scan, partial); break;
+        default: return set_error(LPM_ERR_INVALID, "unknown BVE kernel variant %d", variant);
+    }
+    return LPM_OK;
+}
+
+}  // namespace lpm

@@ -1,0 +1,597 @@
+/*
+ * lpm_oracle.c -- CPU restatement of lpm-v2's O(N^2) direct-sum hot path.
+ *
+ * TEST INFRASTRUCTURE ONLY.  Nothing in the product path (lpm_v2_b200/, the
+ * C-ABI library liblpmgpu.so) may include, link, import or call this file.
+ * It is used by tests/, by __graft_entry__.smoke() as the checker, and by
+ * bench.py's cpu_baseline / --impl reference legs.
+ *
+ * Every function restates, loop for loop and operation for operation, the
+ * Fortran routine cited above it (paths relative to the lpm-v2 source tree).
+ * Build for parity with:  gcc -O2 -ffp-contract=off -fno-fast-math
+ * (no FMA contraction, no reassociation: what gfortran -O2/-O3 emits for the
+ * reference on baseline x86-64).  The timing build (oracle/Makefile, target
+ * liblpm_oracle_fast.so) uses -O3 -march=native and the *_mt entry points.
+ *
+ * PARITY PIN STATUS
+ *   - PSE Laplacian (sphere): pinned by the reference's own regression
+ *     thresholds, tests/SpherePSEConvTest.f90:373-390 (checked in
+ *     tests/test_oracle_golden.py).
+ *   - BVE / planar / beta-plane velocity and stream-function sums:
+ *     "parity unpinned" -- the reference holds no test, golden vector or
+ *     fixture that asserts any value of these sums, and the reference cannot
+ *     be compiled in this environment (no Fortran compiler, no MPI).  They
+ *     are checked only against the analytic solutions the reference's own
+ *     examples log (solid-body rotation, examples/BVESolidBody.f90:231-243;
+ *     Rossby-Haurwitz eigenfunction) to discretisation accuracy.
+ *
+ * Index convention: all ranges are 0-based half-open [ibeg, iend); the
+ * Fortran slice indexStart(r)..indexEnd(r) is [indexStart-1, indexEnd).
+ * mask is int32 (non-zero = active), the C view of logical(klog).
+ */
+#include <math.h>
+#include <stdint.h>
+#include <stdlib.h>
+#include <string.h>
+#include <pthread.h>
+
+/* src/TypeDefs.f90:31 */
+static const double PI = 3.1415926535897932384626433832795027975;
+
+/* ------------------------------------------------------------------ */
+/* src/MPISetup.f90:132-146  LoadBalance.  Outputs are the reference's
+ * 1-based inclusive indexStart / indexEnd and messageLength.          */
+void oracle_load_balance(int32_t nItems, int32_t nProcs, int32_t *indexStart,
+                         int32_t *indexEnd, int32_t *messageLength)
+{
+    int32_t chunkSize = nItems / nProcs;
+    for (int32_t i = 0; i < nProcs; ++i) {
+        indexStart[i] = i * chunkSize + 1;
+        indexEnd[i] = (i + 1) * chunkSize;
+    }
+    indexEnd[nProcs - 1] = nItems;
+    for (int32_t i = 0; i < nProcs; ++i)
+        messageLength[i] = indexEnd[i] - indexStart[i] + 1;
+}
+
+/* Fortran pack([(j,j=1,n)], mask): the active-source index list (0-based
+ * here).  Returns the count.  This is the list the GPU compaction must
+ * reproduce bit-exactly.                                               */
+int64_t oracle_active_list(int64_t n, const int32_t *mask, int32_t *list)
+{
+    int64_t c = 0;
+    for (int64_t j = 0; j < n; ++j)
+        if (mask[j]) list[c++] = (int32_t)j;
+    return c;
+}
+
+/* ------------------------------------------------------------------ */
+/* src/SphereBVESolver.f90:377-430  BVESphereVelocity (loops :396-420).
+ * Identical arithmetic to src/SphereBVE.f90:489-531.                   */
+#define BVE_BODY                                                              \
+    if (mask[j]) {                                                            \
+        double strength = -relVort[j] * area[j] /                             \
+            (4.0 * PI * R * (R * R - x[i] * x[j] - y[i] * y[j] - z[i] * z[j])); \
+        u[i] = u[i] + (y[i] * z[j] - z[i] * y[j]) * strength;                 \
+        v[i] = v[i] + (z[i] * x[j] - x[i] * z[j]) * strength;                 \
+        w[i] = w[i] + (x[i] * y[j] - y[i] * x[j]) * strength;                 \
+    }
+
+void oracle_bve_velocity(int64_t n, const double *x, const double *y, const double *z,
+                         const double *relVort, const double *area, const int32_t *mask,
+                         double R, int64_t ibeg, int64_t iend,
+                         double *u, double *v, double *w)
+{
+    for (int64_t i = ibeg; i < iend; ++i) {
+        u[i] = 0.0; v[i] = 0.0; w[i] = 0.0;
+        for (int64_t j = 0; j < i; ++j) BVE_BODY
+        for (int64_t j = i + 1; j < n; ++j) BVE_BODY
+    }
+}
+
+/* src/SphereBVE.f90:489-531  setVelocityFromVorticity: the mesh-side twin;
+ * differs from the solver kernel only in forming sum(xi*xj) before the
+ * subtraction from R*R (:505-506).                                      */
+#define BVE_MESH_BODY                                                         \
+    if (mask[j]) {                                                            \
+        double strength = -relVort[j] * area[j] /                             \
+            (4.0 * PI * R * (R * R - (x[i] * x[j] + y[i] * y[j] + z[i] * z[j]))); \
+        u[i] = u[i] + (y[i] * z[j] - z[i] * y[j]) * strength;                 \
+        v[i] = v[i] + (z[i] * x[j] - x[i] * z[j]) * strength;                 \
+        w[i] = w[i] + (x[i] * y[j] - y[i] * x[j]) * strength;                 \
+    }
+
+void oracle_bve_velocity_mesh(int64_t n, const double *x, const double *y, const double *z,
+                              const double *relVort, const double *area, const int32_t *mask,
+                              double R, int64_t ibeg, int64_t iend,
+                              double *u, double *v, double *w)
+{
+    for (int64_t i = ibeg; i < iend; ++i) {
+        u[i] = 0.0; v[i] = 0.0; w[i] = 0.0;
+        for (int64_t j = 0; j < i; ++j) BVE_MESH_BODY
+        for (int64_t j = i + 1; j < n; ++j) BVE_MESH_BODY
+    }
+}
+
+/* Extended-precision adjudicator for the same sum (not a restatement). */
+void oracle_bve_velocity_ld(int64_t n, const double *x, const double *y, const double *z,
+                            const double *relVort, const double *area, const int32_t *mask,
+                            double R, int64_t ibeg, int64_t iend,
+                            double *u, double *v, double *w)
+{
+    const long double PIl = 3.1415926535897932384626433832795027975L;
+    for (int64_t i = ibeg; i < iend; ++i) {
+        long double su = 0, sv = 0, sw = 0;
+        long double xi = x[i], yi = y[i], zi = z[i], Rl = R;
+        for (int64_t j = 0; j < n; ++j) {
+            if (j == i || !mask[j]) continue;
+            long double xj = x[j], yj = y[j], zj = z[j];
+            long double s = -(long double)relVort[j] * (long double)area[j] /
+                (4.0L * PIl * Rl * (Rl * Rl - xi * xj - yi * yj - zi * zj));
+            su += (yi * zj - zi * yj) * s;
+            sv += (zi * xj - xi * zj) * s;
+            sw += (xi * yj - yi * xj) * s;
+        }
+        u[i] = (double)su; v[i] = (double)sv; w[i] = (double)sw;
+    }
+}
+
+/* src/SphereBVE.f90:445-485  SetStreamFunctionsOnMesh.                */
+#define BVE_STREAM_BODY                                                       \
+    if (mask[j]) {                                                            \
+        double greensKernel = -log(R * R - (x[i] * x[j] + y[i] * y[j] + z[i] * z[j])) / (4.0 * PI); \
+        relStream[i] = relStream[i] + greensKernel * relVort[j] * area[j];    \
+        absStream[i] = absStream[i] + greensKernel * absVort[j] * area[j];    \
+    }
+
+void oracle_bve_stream(int64_t n, const double *x, const double *y, const double *z,
+                       const double *relVort, const double *absVort, const double *area,
+                       const int32_t *mask, double R, int64_t ibeg, int64_t iend,
+                       double *relStream, double *absStream)
+{
+    for (int64_t i = ibeg; i < iend; ++i) {
+        relStream[i] = 0.0; absStream[i] = 0.0;
+        for (int64_t j = 0; j < i; ++j) BVE_STREAM_BODY
+        for (int64_t j = i + 1; j < n; ++j) BVE_STREAM_BODY
+    }
+}
+
+void oracle_bve_stream_ld(int64_t n, const double *x, const double *y, const double *z,
+                          const double *relVort, const double *absVort, const double *area,
+                          const int32_t *mask, double R, int64_t ibeg, int64_t iend,
+                          double *relStream, double *absStream)
+{
+    const long double PIl = 3.1415926535897932384626433832795027975L;
+    for (int64_t i = ibeg; i < iend; ++i) {
+        long double sr = 0, sa = 0, xi = x[i], yi = y[i], zi = z[i], Rl = R;
+        for (int64_t j = 0; j < n; ++j) {
+            if (j == i || !mask[j]) continue;
+            long double g = -logl(Rl * Rl - (xi * x[j] + yi * y[j] + zi * z[j])) / (4.0L * PIl);
+            sr += g * (long double)relVort[j] * (long double)area[j];
+            sa += g * (long double)absVort[j] * (long double)area[j];
+        }
+        relStream[i] = (double)sr; absStream[i] = (double)sa;
+    }
+}
+
+/* ------------------------------------------------------------------ */
+/* src/PlaneIncompressibleSolver.f90:278-316  planarIncompressibleVelocity
+ * (loops :294-307); same arithmetic as src/PlanarIncompressible.f90:426-466.
+ * Fortran (a)**2 is a*a.                                                */
+#define PLANE_BODY                                                            \
+    if (mask[j]) {                                                            \
+        double strength = vort[j] * area[j] /                                 \
+            (2.0 * PI * ((x[i] - x[j]) * (x[i] - x[j]) + (y[i] - y[j]) * (y[i] - y[j]))); \
+        u[i] = u[i] - (y[i] - y[j]) * strength;                               \
+        v[i] = v[i] + (x[i] - x[j]) * strength;                               \
+    }
+
+void oracle_plane_velocity(int64_t n, const double *x, const double *y, const double *vort,
+                           const double *area, const int32_t *mask, int64_t ibeg, int64_t iend,
+                           double *u, double *v)
+{
+    for (int64_t i = ibeg; i < iend; ++i) {
+        u[i] = 0.0; v[i] = 0.0;
+        for (int64_t j = 0; j < i; ++j) PLANE_BODY
+        for (int64_t j = i + 1; j < n; ++j) PLANE_BODY
+    }
+}
+
+void oracle_plane_velocity_ld(int64_t n, const double *x, const double *y, const double *vort,
+                              const double *area, const int32_t *mask, int64_t ibeg, int64_t iend,
+                              double *u, double *v)
+{
+    const long double PIl = 3.1415926535897932384626433832795027975L;
+    for (int64_t i = ibeg; i < iend; ++i) {
+        long double su = 0, sv = 0;
+        for (int64_t j = 0; j < n; ++j) {
+            if (j == i || !mask[j]) continue;
+            long double dx = (long double)x[i] - x[j], dy = (long double)y[i] - y[j];
+            long double s = (long double)vort[j] * (long double)area[j] / (2.0L * PIl * (dx * dx + dy * dy));
+            su -= dy * s; sv += dx * s;
+        }
+        u[i] = (double)su; v[i] = (double)sv;
+    }
+}
+
+/* src/PlanarIncompressible.f90:470-505  SetStreamFunctionOnMesh.       */
+#define PLANE_STREAM_BODY                                                     \
+    if (mask[j]) {                                                            \
+        double greensKernel = log(sqrt((x[i] - x[j]) * (x[i] - x[j]) +        \
+                                       (y[i] - y[j]) * (y[i] - y[j]))) / (2.0 * PI); \
+        psi[i] = psi[i] + greensKernel * vort[j] * area[j];                   \
+    }
+
+void oracle_plane_stream(int64_t n, const double *x, const double *y, const double *vort,
+                         const double *area, const int32_t *mask, int64_t ibeg, int64_t iend,
+                         double *psi)
+{
+    for (int64_t i = ibeg; i < iend; ++i) {
+        psi[i] = 0.0;
+        for (int64_t j = 0; j < i; ++j) PLANE_STREAM_BODY
+        for (int64_t j = i + 1; j < n; ++j) PLANE_STREAM_BODY
+    }
+}
+
+void oracle_plane_stream_ld(int64_t n, const double *x, const double *y, const double *vort,
+                            const double *area, const int32_t *mask, int64_t ibeg, int64_t iend,
+                            double *psi)
+{
+    const long double PIl = 3.1415926535897932384626433832795027975L;
+    for (int64_t i = ibeg; i < iend; ++i) {
+        long double s = 0;
+        for (int64_t j = 0; j < n; ++j) {
+            if (j == i || !mask[j]) continue;
+            long double dx = (long double)x[i] - x[j], dy = (long double)y[i] - y[j];
+            s += logl(sqrtl(dx * dx + dy * dy)) / (2.0L * PIl) * (long double)vort[j] * (long double)area[j];
+        }
+        psi[i] = (double)s;
+    }
+}
+
+/* ------------------------------------------------------------------ */
+/* src/BetaPlaneSolver.f90:227-267  BetaPlaneVelocity (loops :243-258);
+ * same arithmetic as src/BetaPlane.f90:359-397.                        */
+#define BETA_BODY                                                             \
+    if (mask[j]) {                                                            \
+        double strength = 0.5 * relVort[j] * area[j] /                        \
+            (cosh(2.0 * PI * (y[i] - y[j])) - cos(2.0 * PI * (x[i] - x[j]))); \
+        u[i] = u[i] - sinh(2.0 * PI * (y[i] - y[j])) * strength;              \
+        v[i] = v[i] + sin(2.0 * PI * (x[i] - x[j])) * strength;               \
+    }
+
+void oracle_betaplane_velocity(int64_t n, const double *x, const double *y, const double *relVort,
+                               const double *area, const int32_t *mask, int64_t ibeg, int64_t iend,
+                               double *u, double *v)
+{
+    for (int64_t i = ibeg; i < iend; ++i) {
+        u[i] = 0.0; v[i] = 0.0;
+        for (int64_t j = 0; j < i; ++j) BETA_BODY
+        for (int64_t j = i + 1; j < n; ++j) BETA_BODY
+    }
+}
+
+/* Extended-precision adjudicator.  The reference expression cosh(a)-cos(b)
+ * cancels catastrophically for near pairs ("Beta-plane kernel");
+ * here the denominator is evaluated as 2 sinh^2(a/2) + 2 sin^2(b/2).     */
+void oracle_betaplane_velocity_ld(int64_t n, const double *x, const double *y, const double *relVort,
+                                  const double *area, const int32_t *mask, int64_t ibeg, int64_t iend,
+                                  double *u, double *v)
+{
+    const long double PIl = 3.1415926535897932384626433832795027975L;
+    for (int64_t i = ibeg; i < iend; ++i) {
+        long double su = 0, sv = 0;
+        for (int64_t j = 0; j < n; ++j) {
+            if (j == i || !mask[j]) continue;
+            long double a = 2.0L * PIl * ((long double)y[i] - y[j]);
+            long double b = 2.0L * PIl * ((long double)x[i] - x[j]);
+            long double sh = sinhl(0.5L * a), sn = sinl(0.5L * b);
+            long double den = 2.0L * sh * sh + 2.0L * sn * sn;
+            long double s = 0.5L * (long double)relVort[j] * (long double)area[j] / den;
+            su -= sinhl(a) * s; sv += sinl(b) * s;
+        }
+        u[i] = (double)su; v[i] = (double)sv;
+    }
+}
+
+/* src/BetaPlane.f90:399-442  SetStreamFunctionsOnMesh.                 */
+#define BETA_STREAM_BODY                                                      \
+    if (mask[j]) {                                                            \
+        double greensKernel = log(cosh(2.0 * PI * (y[i] - y[j])) -            \
+                                  cos(2.0 * PI * (x[i] - x[j]))) / (4.0 * PI); \
+        relStream[i] = relStream[i] + greensKernel * relVort[j] * area[j];    \
+        absStream[i] = absStream[i] + greensKernel * absVort[j] * area[j];    \
+    }
+
+void oracle_betaplane_stream(int64_t n, const double *x, const double *y, const double *relVort,
+                             const double *absVort, const double *area, const int32_t *mask,
+                             int64_t ibeg, int64_t iend, double *relStream, double *absStream)
+{
+    for (int64_t i = ibeg; i < iend; ++i) {
+        absStream[i] = 0.0; relStream[i] = 0.0;
+        for (int64_t j = 0; j < i; ++j) BETA_STREAM_BODY
+        for (int64_t j = i + 1; j < n; ++j) BETA_STREAM_BODY
+    }
+}
+
+void oracle_betaplane_stream_ld(int64_t n, const double *x, const double *y, const double *relVort,
+                                const double *absVort, const double *area, const int32_t *mask,
+                                int64_t ibeg, int64_t iend, double *relStream, double *absStream)
+{
+    const long double PIl = 3.1415926535897932384626433832795027975L;
+    for (int64_t i = ibeg; i < iend; ++i) {
+        long double sr = 0, sa = 0;
+        for (int64_t j = 0; j < n; ++j) {
+            if (j == i || !mask[j]) continue;
+            long double a = 2.0L * PIl * ((long double)y[i] - y[j]);
+            long double b = 2.0L * PIl * ((long double)x[i] - x[j]);
+            long double sh = sinhl(0.5L * a), sn = sinl(0.5L * b);
+            long double g = logl(2.0L * sh * sh + 2.0L * sn * sn) / (4.0L * PIl);
+            sr += g * (long double)relVort[j] * (long double)area[j];
+            sa += g * (long double)absVort[j] * (long double)area[j];
+        }
+        relStream[i] = (double)sr; absStream[i] = (double)sa;
+    }
+}
+
+/* ------------------------------------------------------------------ */
+/* src/SphereGeometry.f90:67-73  ChordDistance                          */
+static double ChordDistance(const double a[3], const double b[3])
+{
+    return sqrt((b[0] - a[0]) * (b[0] - a[0]) + (b[1] - a[1]) * (b[1] - a[1]) +
+                (b[2] - a[2]) * (b[2] - a[2]));
+}
+
+/* src/SphereGeometry.f90:107-125  SphereDistanceVector.  sphereRadius is
+ * the module-global SphereRadius (src/TypeDefs.f90:74), passed in.      */
+static double SphereDistance(const double a[3], const double b[3], double sphereRadius)
+{
+    double cp0 = a[1] * b[2] - b[1] * a[2];
+    double cp1 = b[0] * a[2] - a[0] * b[2];
+    double cp2 = a[0] * b[1] - b[0] * a[1];
+    double crossNorm = sqrt(cp0 * cp0 + cp1 * cp1 + cp2 * cp2);
+    double dotProd = a[0] * b[0] + a[1] * b[1] + a[2] * b[2];
+    return atan2(crossNorm, dotProd) * sphereRadius;
+}
+
+/* src/PSEDirectSum.f90:622-627  bivariateLaplacianKernel8.
+ * gfortran expands r**2, r**4, r**6 to repeated products.               */
+static double bivariateLaplacianKernel8(double r)
+{
+    double r2 = r * r;
+    double r4 = r2 * r2;
+    double r6 = r4 * r2;
+    return (40.0 - 40.0 * r2 + 10.0 * r4 - 2.0 * r6 / 3.0) * exp(-r * r) / PI;
+}
+
+double oracle_pse_laplacian_kernel8(double r) { return bivariateLaplacianKernel8(r); }
+
+/* src/PSEDirectSum.f90:502-535  PSESphereLaplacianAtParticles (j = i is
+ * included; the field is zeroed, summed, then scaled by 1/eps^2, :534). */
+void oracle_pse_laplacian_sphere(int64_t n, const double *x, const double *y, const double *z,
+                                 const double *f, const double *area, const int32_t *mask,
+                                 double eps, double sphereRadius, int64_t ibeg, int64_t iend,
+                                 double *lap)
+{
+    for (int64_t i = ibeg; i < iend; ++i) {
+        double xi[3] = { x[i], y[i], z[i] };
+        lap[i] = 0.0;
+        for (int64_t j = 0; j < n; ++j) {
+            if (mask[j]) {
+                double xj[3] = { x[j], y[j], z[j] };
+                double kIn = SphereDistance(xi, xj, sphereRadius) / eps;
+                lap[i] = lap[i] + (f[j] - f[i]) * bivariateLaplacianKernel8(kIn) / (eps * eps) * area[j];
+            }
+        }
+    }
+    for (int64_t i = ibeg; i < iend; ++i) lap[i] = (1.0 / (eps * eps)) * lap[i];
+}
+
+/* src/PSEDirectSum.f90:467-500  PSEPlaneLaplacianAtParticles (z == 0,
+ * src/Particles.f90:663-670).                                           */
+void oracle_pse_laplacian_plane(int64_t n, const double *x, const double *y,
+                                const double *f, const double *area, const int32_t *mask,
+                                double eps, int64_t ibeg, int64_t iend, double *lap)
+{
+    for (int64_t i = ibeg; i < iend; ++i) {
+        double xi[3] = { x[i], y[i], 0.0 };
+        lap[i] = 0.0;
+        for (int64_t j = 0; j < n; ++j) {
+            if (mask[j]) {
+                double xj[3] = { x[j], y[j], 0.0 };
+                double kIn = ChordDistance(xi, xj) / eps;
+                lap[i] = lap[i] + (f[j] - f[i]) * bivariateLaplacianKernel8(kIn) / (eps * eps) * area[j];
+            }
+        }
+    }
+    for (int64_t i = ibeg; i < iend; ++i) lap[i] = (1.0 / (eps * eps)) * lap[i];
+}
+
+void oracle_pse_laplacian_sphere_ld(int64_t n, const double *x, const double *y, const double *z,
+                                    const double *f, const double *area, const int32_t *mask,
+                                    double eps, double sphereRadius, int64_t ibeg, int64_t iend,
+                                    double *lap)
+{
+    const long double PIl = 3.1415926535897932384626433832795027975L;
+    long double e = eps;
+    for (int64_t i = ibeg; i < iend; ++i) {
+        long double s = 0, xi = x[i], yi = y[i], zi = z[i];
+        for (int64_t j = 0; j < n; ++j) {
+            if (!mask[j]) continue;
+            long double xj = x[j], yj = y[j], zj = z[j];
+            long double c0 = yi * zj - yj * zi, c1 = xj * zi - xi * zj, c2 = xi * yj - xj * yi;
+            long double d = atan2l(sqrtl(c0 * c0 + c1 * c1 + c2 * c2), xi * xj + yi * yj + zi * zj) * sphereRadius;
+            long double k = d / e, k2 = k * k;
+            long double ker = (40.0L - 40.0L * k2 + 10.0L * k2 * k2 - 2.0L * k2 * k2 * k2 / 3.0L) * expl(-k2) / PIl;
+            s += ((long double)f[j] - f[i]) * ker / (e * e) * area[j];
+        }
+        lap[i] = (double)(s / (e * e));
+    }
+}
+
+/* ------------------------------------------------------------------ */
+/* src/SphereBVESolver.f90:219-353  timestepPrivate (BVE RK4), with the
+ * trailing SetStreamFunctionsOnMesh (:352) left to the caller.  State
+ * arrays are updated in place; u,v,w enter as the velocity at the old
+ * state and leave as the velocity at the new state (:345-350).          */
+void oracle_bve_rk4_step(int64_t n, double *x, double *y, double *z, double *relVort,
+                         double *u, double *v, double *w, const double *area,
+                         const int32_t *mask, double R, double Omega, double dt)
+{
+    size_t nb = (size_t)n * sizeof(double);
+    double *buf = (double *)malloc(nb * 20);
+    double *xIn = buf, *yIn = buf + n, *zIn = buf + 2 * n, *vIn = buf + 3 * n;
+    double *xS[4], *yS[4], *zS[4], *vS[4];
+    for (int s = 0; s < 4; ++s) {
+        xS[s] = buf + (4 + 4 * s) * n; yS[s] = xS[s] + n; zS[s] = yS[s] + n; vS[s] = zS[s] + n;
+    }
+    /* stage 1 (:239-244) */
+    for (int64_t i = 0; i < n; ++i) {
+        xS[0][i] = dt * u[i]; yS[0][i] = dt * v[i]; zS[0][i] = dt * w[i];
+        vS[0][i] = -dt * 2.0 * Omega * w[i] / R;
+    }
+    for (int s = 1; s < 4; ++s) {
+        /* stage inputs :250-255, :273-278, :296-301 */
+        for (int64_t i = 0; i < n; ++i) {
+            if (s < 3) {
+                xIn[i] = x[i] + 0.5 * xS[s - 1][i]; yIn[i] = y[i] + 0.5 * yS[s - 1][i];
+                zIn[i] = z[i] + 0.5 * zS[s - 1][i]; vIn[i] = relVort[i] + 0.5 * vS[s - 1][i];
+            } else {
+                xIn[i] = x[i] + xS[s - 1][i]; yIn[i] = y[i] + yS[s - 1][i];
+                zIn[i] = z[i] + zS[s - 1][i]; vIn[i] = relVort[i] + vS[s - 1][i];
+            }
+        }
+        oracle_bve_velocity(n, xIn, yIn, zIn, vIn, area, mask, R, 0, n, xS[s], yS[s], zS[s]);
+        for (int64_t i = 0; i < n; ++i) {   /* :262-267 */
+            vS[s][i] = -dt * 2.0 * Omega * zS[s][i] / R;
+            xS[s][i] = dt * xS[s][i]; yS[s][i] = dt * yS[s][i]; zS[s][i] = dt * zS[s][i];
+        }
+    }
+    for (int64_t i = 0; i < n; ++i) {       /* :320-329 */
+        x[i] = x[i] + xS[0][i] / 6.0 + xS[1][i] / 3.0 + xS[2][i] / 3.0 + xS[3][i] / 6.0;
+        y[i] = y[i] + yS[0][i] / 6.0 + yS[1][i] / 3.0 + yS[2][i] / 3.0 + yS[3][i] / 6.0;
+        z[i] = z[i] + zS[0][i] / 6.0 + zS[1][i] / 3.0 + zS[2][i] / 3.0 + zS[3][i] / 6.0;
+        relVort[i] = relVort[i] + vS[0][i] / 6.0 + vS[1][i] / 3.0 + vS[2][i] / 3.0 + vS[3][i] / 6.0;
+    }
+    oracle_bve_velocity(n, x, y, z, relVort, area, mask, R, 0, n, u, v, w);   /* :345-346 */
+    free(buf);
+}
+
+/* src/PlaneIncompressibleSolver.f90:171-259 (stream function :258 left
+ * to the caller).                                                       */
+void oracle_plane_rk4_step(int64_t n, double *x, double *y, const double *vort,
+                           double *u, double *v, const double *area, const int32_t *mask, double dt)
+{
+    double *buf = (double *)malloc((size_t)n * sizeof(double) * 10);
+    double *xIn = buf, *yIn = buf + n, *xS[4], *yS[4];
+    for (int s = 0; s < 4; ++s) { xS[s] = buf + (2 + 2 * s) * n; yS[s] = xS[s] + n; }
+    for (int64_t i = 0; i < n; ++i) { xS[0][i] = dt * u[i]; yS[0][i] = dt * v[i]; }
+    for (int s = 1; s < 4; ++s) {
+        for (int64_t i = 0; i < n; ++i) {
+            if (s < 3) { xIn[i] = x[i] + 0.5 * xS[s - 1][i]; yIn[i] = y[i] + 0.5 * yS[s - 1][i]; }
+            else       { xIn[i] = x[i] + xS[s - 1][i];       yIn[i] = y[i] + yS[s - 1][i]; }
+        }
+        oracle_plane_velocity(n, xIn, yIn, vort, area, mask, 0, n, xS[s], yS[s]);
+        for (int64_t i = 0; i < n; ++i) { xS[s][i] = dt * xS[s][i]; yS[s][i] = dt * yS[s][i]; }
+    }
+    for (int64_t i = 0; i < n; ++i) {
+        x[i] = x[i] + xS[0][i] / 6.0 + xS[1][i] / 3.0 + xS[2][i] / 3.0 + xS[3][i] / 6.0;
+        y[i] = y[i] + yS[0][i] / 6.0 + yS[1][i] / 3.0 + yS[2][i] / 3.0 + yS[3][i] / 6.0;
+    }
+    oracle_plane_velocity(n, x, y, vort, area, mask, 0, n, u, v);
+    free(buf);
+}
+
+/* src/BetaPlaneSolver.f90:142-219 (stream functions :218 left to the
+ * caller).  u,v enter as the mesh velocity, leave as SetVelocityOnMesh.  */
+void oracle_betaplane_rk4_step(int64_t n, double *x, double *y, double *relVort,
+                               double *u, double *v, const double *area, const int32_t *mask,
+                               double beta, double dt)
+{
+    double *buf = (double *)malloc((size_t)n * sizeof(double) * 15);
+    double *xIn = buf, *yIn = buf + n, *vIn = buf + 2 * n, *xS[4], *yS[4], *vS[4];
+    for (int s = 0; s < 4; ++s) { xS[s] = buf + (3 + 3 * s) * n; yS[s] = xS[s] + n; vS[s] = yS[s] + n; }
+    for (int64_t i = 0; i < n; ++i) {
+        xS[0][i] = dt * u[i]; yS[0][i] = dt * v[i]; vS[0][i] = -dt * beta * v[i];
+    }
+    for (int s = 1; s < 4; ++s) {
+        for (int64_t i = 0; i < n; ++i) {
+            if (s < 3) {
+                xIn[i] = x[i] + 0.5 * xS[s - 1][i]; yIn[i] = y[i] + 0.5 * yS[s - 1][i];
+                vIn[i] = relVort[i] + 0.5 * vS[s - 1][i];
+            } else {
+                xIn[i] = x[i] + xS[s - 1][i]; yIn[i] = y[i] + yS[s - 1][i];
+                vIn[i] = relVort[i] + vS[s - 1][i];
+            }
+        }
+        oracle_betaplane_velocity(n, xIn, yIn, vIn, area, mask, 0, n, xS[s], yS[s]);
+        for (int64_t i = 0; i < n; ++i) {
+            vS[s][i] = -dt * beta * yS[s][i];
+            xS[s][i] = dt * xS[s][i]; yS[s][i] = dt * yS[s][i];
+        }
+    }
+    for (int64_t i = 0; i < n; ++i) {
+        x[i] = x[i] + xS[0][i] / 6.0 + xS[1][i] / 3.0 + xS[2][i] / 3.0 + xS[3][i] / 6.0;
+        y[i] = y[i] + yS[0][i] / 6.0 + yS[1][i] / 3.0 + yS[2][i] / 3.0 + yS[3][i] / 6.0;
+        relVort[i] = relVort[i] + vS[0][i] / 6.0 + vS[1][i] / 3.0 + vS[2][i] / 3.0 + vS[3][i] / 6.0;
+    }
+    oracle_betaplane_velocity(n, x, y, relVort, area, mask, 0, n, u, v);
+    free(buf);
+}
+
+/* ------------------------------------------------------------------ */
+/* src/SphereBVE.f90:410-441  TotalKE, TotalEnstrophy.                  */
+double oracle_total_ke(int64_t n, const double *u, const double *v, const double *w,
+                       const double *area, const int32_t *mask)
+{
+    double ke = 0.0;
+    for (int64_t i = 0; i < n; ++i)
+        if (mask[i]) {
+            double magSq = u[i] * u[i] + v[i] * v[i] + w[i] * w[i];
+            ke = ke + magSq * area[i];
+        }
+    return 0.5 * ke;
+}
+
+double oracle_total_enstrophy(int64_t n, const double *relVort, const double *area, const int32_t *mask)
+{
+    double e = 0.0;
+    for (int64_t i = 0; i < n; ++i)
+        if (mask[i]) e = e + relVort[i] * relVort[i] * area[i];
+    return 0.5 * e;
+}
+
+/* ------------------------------------------------------------------ */
+/* Multi-threaded driver used only for the CPU baseline timing: the
+ * reference's replicated-data target split (LoadBalance above) with one
+ * worker thread standing in for each MPI rank (mpirun -np nthreads).    */
+typedef struct {
+    int kind; int64_t n; const double *x, *y, *z, *q, *area; const int32_t *mask;
+    double R; int64_t ibeg, iend; double *u, *v, *w;
+} mt_job;
+
+static void *mt_worker(void *arg)
+{
+    mt_job *j = (mt_job *)arg;
+    oracle_bve_velocity(j->n, j->x, j->y, j->z, j->q, j->area, j->mask, j->R, j->ibeg, j->iend, j->u, j->v, j->w);
+    return NULL;
+}
+
+/* Evaluates targets [tbeg, tend) (a bounded sample of the full target
+ * set) against all n sources, split over nthreads workers by LoadBalance. */
+void oracle_bve_velocity_mt(int nthreads, int64_t n, const double *x, const double *y, const double *z,
+                            const double *relVort, const double *area, const int32_t *mask,
+                            double R, int64_t tbeg, int64_t tend, double *u, double *v, double *w)
+{
+    pthread_t *th = (pthread_t *)malloc(sizeof(pthread_t) * nthreads);
+    mt_job *jobs = (mt_job *)malloc(sizeof(mt_job) * nthreads);
+    int64_t cnt = tend - tbeg, chunk = cnt / nthreads;
+    for (int t = 0; t < nthreads; ++t) {
+        mt_job j = { 0, n, x, y, z, relVort, area, mask, R,
+                     tbeg + t * chunk, (t == nthreads - 1) ? tend : tbeg + (t + 1) * chunk, u, v, w };
+        jobs[t] = j;
+        pthread_create(&th[t], NULL, mt_worker, &jobs[t]);
+    }
+    for (int t = 0; t < nthreads; ++t) pthread_join(th[t], NULL);
+    free(th); free(jobs);
+}
