@@ -215,6 +215,9 @@ int lpm_fp64_peak_probe(int iters, double* tflops, double* ms);
  * the launching stream), and the number of kernel launches the library has
  * issued since lpm_gpu_init / the last call with reset != 0. */
 int lpm_last_kernel_ms(double* ms);
+/* Sum of the durations (ms) and count of the direct-sum main kernels recorded on the
+ * current device since the last reset (profiling must be on). */
+int lpm_profile_summary(int reset, int64_t* nkernels, double* total_ms);
 int64_t lpm_launch_count(int reset);
 /* 1: record events around each main kernel (adds a sync at query time only). */
 int lpm_set_profiling(int enable);

@@ -175,3 +175,10 @@ def last_kernel_ms():
 
 def launch_count(reset=False):
     return int(lib.lpm_launch_count(1 if reset else 0))
+
+
+def profile_summary(reset=True):
+    """(number of direct-sum main kernels, their total duration in ms) since the last reset."""
+    k, ms = C.c_int64(0), C.c_double(0)
+    check(lib.lpm_profile_summary(1 if reset else 0, C.byref(k), C.byref(ms)))
+    return k.value, ms.value

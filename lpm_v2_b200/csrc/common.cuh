@@ -92,9 +92,22 @@ struct Device {
     int id = -1;
     int sm_count = 0;
     cudaStream_t stream = nullptr;       // library-owned stream (host API, resident solvers)
-    cudaEvent_t ev_begin = nullptr, ev_end = nullptr, ev_done = nullptr;
-    bool timed = false;                  // ev_begin/ev_end hold a measurement
+    cudaEvent_t ev_done = nullptr;       // cross-device barrier (resident solvers)
+    // profiling: one event pair per direct-sum main kernel since the last reset
+    std::vector<std::pair<cudaEvent_t, cudaEvent_t>> prof;
+    size_t prof_used = 0;
     Workspace ws;
+    int next_prof(cudaEvent_t* b, cudaEvent_t* e)
+    {
+        if (prof_used == prof.size()) {
+            cudaEvent_t x, y;
+            if (cudaEventCreate(&x) != cudaSuccess || cudaEventCreate(&y) != cudaSuccess) return LPM_ERR_CUDA;
+            prof.emplace_back(x, y);
+        }
+        *b = prof[prof_used].first; *e = prof[prof_used].second;
+        ++prof_used;
+        return LPM_OK;
+    }
 };
 
 struct Runtime {

@@ -99,7 +99,9 @@ extern "C" int lpm_gpu_finalize(void)
         cudaSetDevice(d.id);
         cudaStreamSynchronize(d.stream);
         d.ws.release();
-        cudaEventDestroy(d.ev_begin); cudaEventDestroy(d.ev_end); cudaEventDestroy(d.ev_done);
+        cudaEventDestroy(d.ev_done);
+        for (auto& pr : d.prof) { cudaEventDestroy(pr.first); cudaEventDestroy(pr.second); }
+        d.prof.clear(); d.prof_used = 0;
         cudaStreamDestroy(d.stream);
     }
     R.devs.clear();
@@ -181,11 +183,28 @@ extern "C" int lpm_last_kernel_ms(double* ms)
 {
     Device* d = nullptr;
     LPM_TRY(current_device(&d));
-    if (!d->timed) return set_error(LPM_ERR_INVALID, "no timed kernel (lpm_set_profiling(1) first)");
-    LPM_CUDA(cudaEventSynchronize(d->ev_end));
+    if (d->prof_used == 0) return set_error(LPM_ERR_INVALID, "no timed kernel (lpm_set_profiling(1) first)");
+    auto& pr = d->prof[d->prof_used - 1];
+    LPM_CUDA(cudaEventSynchronize(pr.second));
     float f = 0;
-    LPM_CUDA(cudaEventElapsedTime(&f, d->ev_begin, d->ev_end));
+    LPM_CUDA(cudaEventElapsedTime(&f, pr.first, pr.second));
     *ms = f;
+    return LPM_OK;
+}
+extern "C" int lpm_profile_summary(int reset, int64_t* nkernels, double* total_ms)
+{
+    Device* d = nullptr;
+    LPM_TRY(current_device(&d));
+    double tot = 0.0;
+    for (size_t k = 0; k < d->prof_used; ++k) {
+        LPM_CUDA(cudaEventSynchronize(d->prof[k].second));
+        float f = 0;
+        LPM_CUDA(cudaEventElapsedTime(&f, d->prof[k].first, d->prof[k].second));
+        tot += f;
+    }
+    if (nkernels) *nkernels = (int64_t)d->prof_used;
+    if (total_ms) *total_ms = tot;
+    if (reset) d->prof_used = 0;
     return LPM_OK;
 }
 

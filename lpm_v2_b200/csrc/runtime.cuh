@@ -24,8 +24,6 @@ inline int init_device(Device& d, int id)
                          prop.name, prop.major, prop.minor);
     d.sm_count = prop.multiProcessorCount;
     LPM_CUDA(cudaStreamCreateWithFlags(&d.stream, cudaStreamNonBlocking));
-    LPM_CUDA(cudaEventCreate(&d.ev_begin));
-    LPM_CUDA(cudaEventCreate(&d.ev_end));
     LPM_CUDA(cudaEventCreateWithFlags(&d.ev_done, cudaEventDisableTiming));
     return LPM_OK;
 }
@@ -188,10 +186,14 @@ inline int direct_sum(Device& dev, cudaStream_t st, const MaskPlan& mp, int64_t 
         partial = dev.ws.partial.as<double>();
     }
     const bool prof = rt().profiling;
-    if (prof) LPM_CUDA(cudaEventRecord(dev.ev_begin, st));
+    cudaEvent_t pb = nullptr, pe = nullptr;
+    if (prof) {
+        if (dev.next_prof(&pb, &pe) != LPM_OK) return set_error(LPM_ERR_CUDA, "cannot create profiling events");
+        LPM_CUDA(cudaEventRecord(pb, st));
+    }
     LPM_TRY(launch_variant<K>(variant, st, prm, g, dev.ws.sources.as<double>(), mp.scan.as<int32_t>(), partial,
                               dev.sm_count));
-    if (prof) { LPM_CUDA(cudaEventRecord(dev.ev_end, st)); dev.timed = true; }
+    if (prof) LPM_CUDA(cudaEventRecord(pe, st));
     count_launch();
     if (g.nchunks > 1) {
         const unsigned nb = (unsigned)((g.ntgt + 255) / 256);
