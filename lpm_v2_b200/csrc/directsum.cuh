@@ -36,8 +36,10 @@ struct DsGeom {
     int32_t nsrc_pad;       // padded to a multiple of kTile
     int32_t chunk;          // sources per chunk (multiple of kTile)
     int32_t nchunks;
-    int32_t ntblocks;       // target blocks = ceil((tend-tbeg) / (BLOCK*T))
+    int32_t ntblocks;       // target blocks = ceil((tend-tblk0) / (BLOCK*T))
     int64_t ntgt;           // tend - tbeg
+    int64_t tblk0;          // tbeg rounded down to a multiple of BLOCK*T
+    int64_t nall;           // all particles (launch shape depends on this, not on the slice)
 };
 
 // Source chunking depends on the number of active sources only.
@@ -104,7 +106,8 @@ __device__ __forceinline__ void tma_bulk_g2s(void* dst_smem, const void* src_gme
 //   Params            kernel-wide constants + target array pointers
 //   Tgt               per-target registers
 //   load_target(p,i)  -> Tgt
-//   pair<CHECK>(p, tgt, s[NS], acc[NA], skip)
+//   group<T,CHECK>(p, tgt[T], s[NS], acc[T][NA], j, self[T])   one source against the
+//                     thread's T targets; with CHECK, target t skips the pair when j == self[t]
 //   finalize(p, tgt, acc, i)   writes the outputs of target i
 //
 // partial layout: [(chunk*NA + a) * ntgt + local_target]
@@ -115,13 +118,21 @@ ds_kernel(const typename K::Params prm, const DsGeom g, const double* __restrict
 {
     constexpr int NS = K::NS, NA = K::NA, TS = kTile;
     constexpr uint32_t kTileBytes = TS * NS * sizeof(double);
-    __shared__ __align__(128) double tile[2][TS * NS];
-    __shared__ __align__(8) uint64_t full[2];
+    // dynamic shared memory: [2 tiles][BLOCK*T*NA running sums][2 mbarriers]
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    double(*tile)[TS * NS] = reinterpret_cast<double(*)[TS * NS]>(smem_raw);
+    double* run = reinterpret_cast<double*>(smem_raw + 2 * kTileBytes);
+    uint64_t* full = reinterpret_cast<uint64_t*>(smem_raw + 2 * kTileBytes + sizeof(double) * BLOCK * T * NA);
 
     const int tid = threadIdx.x;
     const int tb = blockIdx.x % g.ntblocks;         // chunk is the slow index: CTAs that run
     const int ck = blockIdx.x / g.ntblocks;         // together read the same sources (L2)
-    const int64_t blk0 = g.tbeg + (int64_t)tb * (BLOCK * T);
+    // Target blocks are aligned to GLOBAL particle indices (tblk0 is a multiple of BLOCK*T)
+    // and a CTA always evaluates its whole block, even the part outside [tbeg, tend): every
+    // particle is resident on every GPU, so the targets that share a thread -- and hence a
+    // batched reciprocal -- are the same whatever the partition.  Only stores are sliced.
+    const int64_t blk0 = g.tblk0 + (int64_t)tb * (BLOCK * T);
+    const int64_t blk1 = (blk0 + BLOCK * T < g.nall) ? blk0 + BLOCK * T : g.nall;
 
     typename K::Tgt tg[T];
     double acc[T][NA];
@@ -130,23 +141,24 @@ ds_kernel(const typename K::Params prm, const DsGeom g, const double* __restrict
 #pragma unroll
     for (int t = 0; t < T; ++t) {
         int64_t i = blk0 + t * BLOCK + tid;
-        live[t] = i < g.tend;
-        if (!live[t]) i = g.tend - 1;
+        live[t] = i >= g.tbeg && i < g.tend;
+        if (i >= g.nall) i = g.nall - 1;            // past the last particle: shadow it, never stored
         tg[t] = K::load_target(prm, i);
         if (K::SKIP_SELF) {
             int32_t a = scan[i], b = scan[i + 1];
-            self[t] = (b > a && live[t]) ? a : -1;
+            self[t] = (b > a) ? a : -1;
         } else {
             self[t] = -1;
         }
 #pragma unroll
-        for (int a = 0; a < NA; ++a) acc[t][a] = 0.0;
+        for (int a = 0; a < NA; ++a) {
+            acc[t][a] = 0.0;
+            run[(t * NA + a) * BLOCK + tid] = 0.0;
+        }
     }
     // compact indices of this CTA's own targets: [selflo, selfhi)
     int32_t selflo = 0, selfhi = 0;
     if (K::SKIP_SELF) {
-        int64_t blk1 = blk0 + BLOCK * T;
-        if (blk1 > g.tend) blk1 = g.tend;
         selflo = scan[blk0];
         selfhi = scan[blk1];
     }
@@ -187,8 +199,7 @@ ds_kernel(const typename K::Params prm, const DsGeom g, const double* __restrict
                     double2 v = p2[q];
                     s[2 * q] = v.x; s[2 * q + 1] = v.y;
                 }
-#pragma unroll
-                for (int t = 0; t < T; ++t) K::template pair<false>(prm, tg[t], s, acc[t], false);
+                K::template group<T, false>(prm, tg, s, acc, 0, self);
             }
         } else {
 #pragma unroll 1
@@ -200,16 +211,31 @@ ds_kernel(const typename K::Params prm, const DsGeom g, const double* __restrict
                     double2 v = p2[q];
                     s[2 * q] = v.x; s[2 * q + 1] = v.y;
                 }
-#pragma unroll
-                for (int t = 0; t < T; ++t) K::template pair<true>(prm, tg[t], s, acc[t], (j0 + j) == self[t]);
+                K::template group<T, true>(prm, tg, s, acc, j0 + j, self);
             }
         }
+        // Two-level summation: the tile's sum joins the running sum (kept in shared memory,
+        // one column per thread), so rounding error grows like sqrt(TS) + sqrt(ntiles)
+        // instead of sqrt(TS * ntiles).
+#pragma unroll
+        for (int t = 0; t < T; ++t)
+#pragma unroll
+            for (int a = 0; a < NA; ++a) {
+                double* r = &run[(t * NA + a) * BLOCK + tid];
+                *r = __dadd_rn(*r, acc[t][a]);
+                acc[t][a] = 0.0;
+            }
         __syncthreads();    // everyone is done with tile[st]
         if (tid == 0 && k + 2 < ntiles) {
             mbar_expect_tx(&full[st], kTileBytes);
             tma_bulk_g2s(tile[st], src + (size_t)(s0 + (k + 2) * TS) * NS, kTileBytes, &full[st]);
         }
     }
+
+#pragma unroll
+    for (int t = 0; t < T; ++t)
+#pragma unroll
+        for (int a = 0; a < NA; ++a) acc[t][a] = run[(t * NA + a) * BLOCK + tid];
 
     if (g.nchunks == 1) {
 #pragma unroll
@@ -224,6 +250,12 @@ ds_kernel(const typename K::Params prm, const DsGeom g, const double* __restrict
             for (int a = 0; a < NA; ++a) partial[((size_t)ck * NA + a) * g.ntgt + li] = acc[t][a];
         }
     }
+}
+
+template <class K, int T, int BLOCK>
+constexpr size_t ds_smem_bytes()
+{
+    return 2 * size_t(kTile) * K::NS * sizeof(double) + sizeof(double) * BLOCK * T * K::NA + 2 * sizeof(uint64_t);
 }
 
 // Adds the chunk partials in chunk order and writes the outputs.

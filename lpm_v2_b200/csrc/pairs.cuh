@@ -44,6 +44,54 @@ __device__ __forceinline__ double rcp_fast(double d)
     return fma(r0, t, r0);
 }
 
+
+// Reciprocals of T positive numbers behind ONE MUFU per group of (up to) four:
+// 1/d_k = (prod_{m != k} d_m) / (d_0 d_1 d_2 d_3), by a product tree.  FP64-pipe cost
+// stays 3 ops per reciprocal (12 per four), but the XU instruction -- which costs the
+// FP64 pipe dispatch slots (ncu: math-pipe throttle with the pipe 80 % busy) -- is
+// issued a quarter as often.  A few ulp, far inside the 1e-12 budget.
+template <int T>
+__device__ __forceinline__ void rcp_batch(const double (&d)[T], double (&r)[T])
+{
+    if constexpr (T == 1) {
+        r[0] = rcp_fast(d[0]);
+    } else if constexpr (T == 2) {
+        double q = rcp_fast(d[0] * d[1]);
+        r[0] = q * d[1]; r[1] = q * d[0];
+    } else if constexpr (T == 3) {
+        double p01 = d[0] * d[1];
+        double q = rcp_fast(p01 * d[2]);
+        double q01 = q * d[2];
+        r[2] = q * p01; r[0] = q01 * d[1]; r[1] = q01 * d[0];
+    } else if constexpr (T == 4) {
+        double p01 = d[0] * d[1], p23 = d[2] * d[3];
+        double q = rcp_fast(p01 * p23);
+        double q01 = q * p23, q23 = q * p01;
+        r[0] = q01 * d[1]; r[1] = q01 * d[0]; r[2] = q23 * d[3]; r[3] = q23 * d[2];
+    } else {
+        static_assert(T % 4 == 0 || T == 6, "rcp_batch: unsupported group size");
+        constexpr int H = (T == 6) ? 3 : 4;
+        double dd[H], rr[H];
+#pragma unroll
+        for (int b = 0; b < T; b += H) {
+#pragma unroll
+            for (int k = 0; k < H; ++k) dd[k] = d[b + k];
+            rcp_batch<H>(dd, rr);
+#pragma unroll
+            for (int k = 0; k < H; ++k) r[b + k] = rr[k];
+        }
+    }
+}
+
+// Default group(): one source against the thread's T targets, one pair at a time.
+#define LPM_DEFAULT_GROUP()                                                                              \
+    template <int T, bool CHECK>                                                                         \
+    __device__ static __forceinline__ void group(const Params& p, const Tgt (&t)[T], const double (&s)[NS], \
+                                                 double (&acc)[T][NA], int32_t j, const int32_t (&self)[T]) \
+    {                                                                                                    \
+        _Pragma("unroll") for (int k = 0; k < T; ++k) pair<CHECK>(p, t[k], s, acc[k], CHECK && (j == self[k])); \
+    }
+
 // =============================================================================
 // BVE velocity.  src/SphereBVESolver.f90:396-420 (== src/SphereBVE.f90:497-521):
 //   strength = -zeta_j A_j / (4 pi R (R^2 - x_i.x_j));  u_i += (x_i cross x_j) strength
@@ -51,31 +99,54 @@ __device__ __forceinline__ double rcp_fast(double d)
 // P_j = -zeta_j A_j/(4 pi R) x_j : 3 DFMA (denominator) + 3 (reciprocal) +
 // 3 (accumulate) + 1 MUFU per pair instead of the ~25 flops + divide as written.
 // Source record: x, y, z, Px, Py, Pz.
-struct BveVel {
+struct BveVelParams {
+    const double *x, *y, *z;
+    double R2;
+    Outs<3> out;
+};
+struct BveVelTgt { double x, y, z; };
+template <int RG>      // RG: reciprocals sharing one MUFU (1 = none, 2, 4)
+struct BveVelT {
     static constexpr int NS = 6, NA = 3;
     static constexpr bool SKIP_SELF = true;
-    struct Params {
-        const double *x, *y, *z;
-        double R2;
-        Outs<3> out;
-    };
-    struct Tgt { double x, y, z; };
+    using Params = BveVelParams;
+    using Tgt = BveVelTgt;
     __device__ static __forceinline__ Tgt load_target(const Params& p, int64_t i)
     {
         return Tgt{p.x[i], p.y[i], p.z[i]};
     }
-    template <bool CHECK>
-    __device__ static __forceinline__ void pair(const Params& p, const Tgt& t, const double (&s)[NS],
-                                                double (&acc)[NA], bool skip)
+    template <int T, bool CHECK>
+    __device__ static __forceinline__ void group(const Params& p, const Tgt (&t)[T], const double (&s)[NS],
+                                                 double (&acc)[T][NA], int32_t j, const int32_t (&self)[T])
     {
-        double d = fma(-t.x, s[0], p.R2);
-        d = fma(-t.y, s[1], d);
-        d = fma(-t.z, s[2], d);
-        double r = rcp_fast(d);
-        if (CHECK) r = skip ? 0.0 : r;
-        acc[0] = fma(r, s[3], acc[0]);
-        acc[1] = fma(r, s[4], acc[1]);
-        acc[2] = fma(r, s[5], acc[2]);
+        double d[T], r[T];
+#pragma unroll
+        for (int k = 0; k < T; ++k) {
+            d[k] = fma(-t[k].x, s[0], p.R2);
+            d[k] = fma(-t[k].y, s[1], d[k]);
+            d[k] = fma(-t[k].z, s[2], d[k]);
+            if (CHECK) d[k] = (j == self[k]) ? 1.0 : d[k];     // keep the self pair out of the shared product
+        }
+        if constexpr (RG >= 4 || T < 2) {
+            rcp_batch<T>(d, r);
+        } else if constexpr (RG == 2 && T % 2 == 0) {
+#pragma unroll
+            for (int k = 0; k < T; k += 2) {
+                double dd[2] = {d[k], d[k + 1]}, rr[2];
+                rcp_batch<2>(dd, rr);
+                r[k] = rr[0]; r[k + 1] = rr[1];
+            }
+        } else {
+#pragma unroll
+            for (int k = 0; k < T; ++k) r[k] = rcp_fast(d[k]);
+        }
+#pragma unroll
+        for (int k = 0; k < T; ++k) {
+            if (CHECK) r[k] = (j == self[k]) ? 0.0 : r[k];
+            acc[k][0] = fma(r[k], s[3], acc[k][0]);
+            acc[k][1] = fma(r[k], s[4], acc[k][1]);
+            acc[k][2] = fma(r[k], s[5], acc[k][2]);
+        }
     }
     __device__ static __forceinline__ void finalize(const Params& p, const Tgt& t, const double (&a)[NA], int64_t i)
     {
@@ -84,6 +155,7 @@ struct BveVel {
         p.out.store(2, i, fma(t.x, a[1], -(t.y * a[0])));
     }
 };
+using BveVel = BveVelT<4>;
 
 __global__ void pack_bve_vel(int32_t nsrc, int32_t nsrc_pad, const int32_t* __restrict__ active,
                              const double* __restrict__ x, const double* __restrict__ y,
@@ -132,6 +204,7 @@ struct BveStream {
         acc[0] = fma(l, s[3], acc[0]);
         acc[1] = fma(l, s[4], acc[1]);
     }
+    LPM_DEFAULT_GROUP()
     __device__ static __forceinline__ void finalize(const Params& p, const Tgt&, const double (&a)[NA], int64_t i)
     {
         p.out.store(0, i, a[0]);
@@ -173,16 +246,25 @@ struct PlaneVel {
     };
     struct Tgt { double x, y; };
     __device__ static __forceinline__ Tgt load_target(const Params& p, int64_t i) { return Tgt{p.x[i], p.y[i]}; }
-    template <bool CHECK>
-    __device__ static __forceinline__ void pair(const Params&, const Tgt& t, const double (&s)[NS],
-                                                double (&acc)[NA], bool skip)
+    template <int T, bool CHECK>
+    __device__ static __forceinline__ void group(const Params&, const Tgt (&t)[T], const double (&s)[NS],
+                                                 double (&acc)[T][NA], int32_t j, const int32_t (&self)[T])
     {
-        double dx = t.x - s[0], dy = t.y - s[1];
-        double r2 = fma(dx, dx, dy * dy);
-        double w = rcp_fast(r2) * s[2];
-        if (CHECK) w = skip ? 0.0 : w;
-        acc[0] = fma(-dy, w, acc[0]);
-        acc[1] = fma(dx, w, acc[1]);
+        double dx[T], dy[T], r2[T], r[T];
+#pragma unroll
+        for (int k = 0; k < T; ++k) {
+            dx[k] = t[k].x - s[0]; dy[k] = t[k].y - s[1];
+            r2[k] = fma(dx[k], dx[k], dy[k] * dy[k]);
+            if (CHECK) r2[k] = (j == self[k]) ? 1.0 : r2[k];
+        }
+        rcp_batch<T>(r2, r);
+#pragma unroll
+        for (int k = 0; k < T; ++k) {
+            double w = r[k] * s[2];
+            if (CHECK) w = (j == self[k]) ? 0.0 : w;
+            acc[k][0] = fma(-dy[k], w, acc[k][0]);
+            acc[k][1] = fma(dx[k], w, acc[k][1]);
+        }
     }
     __device__ static __forceinline__ void finalize(const Params& p, const Tgt&, const double (&a)[NA], int64_t i)
     {
@@ -191,8 +273,9 @@ struct PlaneVel {
     }
 };
 
-// Null source for the planar kernels: far away (r^2 ~ 2e300, finite) with zero strength.
-#define LPM_PLANE_FAR 1.0e150
+// Null source for the planar kernels: far away with zero strength.  r^2 ~ 2e74, so the
+// product of four of them in rcp_batch stays finite.
+#define LPM_PLANE_FAR 1.0e37
 
 __global__ void pack_plane(int32_t nsrc, int32_t nsrc_pad, const int32_t* __restrict__ active,
                            const double* __restrict__ x, const double* __restrict__ y,
@@ -231,6 +314,7 @@ struct PlaneStream {
         if (CHECK) r2 = skip ? 1.0 : r2;
         acc[0] = fma(log(r2), s[2], acc[0]);
     }
+    LPM_DEFAULT_GROUP()
     __device__ static __forceinline__ void finalize(const Params& p, const Tgt&, const double (&a)[NA], int64_t i)
     {
         p.out.store(0, i, a[0]);
@@ -264,19 +348,29 @@ struct BetaVel {
         sincospi(p.x[i], &t.sn, &t.cs);
         return t;
     }
-    template <bool CHECK>
-    __device__ static __forceinline__ void pair(const Params&, const Tgt& t, const double (&s)[NS],
-                                                double (&acc)[NA], bool skip)
+    template <int T, bool CHECK>
+    __device__ static __forceinline__ void group(const Params&, const Tgt (&t)[T], const double (&s)[NS],
+                                                 double (&acc)[T][NA], int32_t j, const int32_t (&self)[T])
     {
-        double S = fma(t.sh, s[1], -(t.ch * s[0]));
-        double C = fma(t.ch, s[1], -(t.sh * s[0]));
-        double sn = fma(t.sn, s[3], -(t.cs * s[2]));
-        double cs = fma(t.cs, s[3], t.sn * s[2]);
-        double den = fma(S, S, sn * sn);
-        double w = rcp_fast(den) * s[4];
-        if (CHECK) w = skip ? 0.0 : w;
-        acc[0] = fma(-(S * C), w, acc[0]);
-        acc[1] = fma(sn * cs, w, acc[1]);
+        double SC[T], sc[T], den[T], r[T];
+#pragma unroll
+        for (int k = 0; k < T; ++k) {
+            double S = fma(t[k].sh, s[1], -(t[k].ch * s[0]));
+            double C = fma(t[k].ch, s[1], -(t[k].sh * s[0]));
+            double sn = fma(t[k].sn, s[3], -(t[k].cs * s[2]));
+            double cs = fma(t[k].cs, s[3], t[k].sn * s[2]);
+            den[k] = fma(S, S, sn * sn);
+            if (CHECK) den[k] = (j == self[k]) ? 1.0 : den[k];
+            SC[k] = S * C; sc[k] = sn * cs;
+        }
+        rcp_batch<T>(den, r);
+#pragma unroll
+        for (int k = 0; k < T; ++k) {
+            double w = r[k] * s[4];
+            if (CHECK) w = (j == self[k]) ? 0.0 : w;
+            acc[k][0] = fma(-SC[k], w, acc[k][0]);
+            acc[k][1] = fma(sc[k], w, acc[k][1]);
+        }
     }
     __device__ static __forceinline__ void finalize(const Params& p, const Tgt&, const double (&a)[NA], int64_t i)
     {
@@ -306,6 +400,7 @@ struct BetaStream {
         acc[0] = fma(l, s[4], acc[0]);
         acc[1] = fma(l, s[5], acc[1]);
     }
+    LPM_DEFAULT_GROUP()
     __device__ static __forceinline__ void finalize(const Params& p, const Tgt&, const double (&a)[NA], int64_t i)
     {
         p.out.store(0, i, a[0]);
@@ -385,6 +480,7 @@ struct PseSphere {
         double k = atan2(cn, dot) * p.rad_over_eps;
         acc[0] = fma((s[3] - t.f) * pse_eta_pi(k * k), s[4], acc[0]);
     }
+    LPM_DEFAULT_GROUP()
     __device__ static __forceinline__ void finalize(const Params& p, const Tgt&, const double (&a)[NA], int64_t i)
     {
         p.out.store(0, i, a[0] * p.inv_eps2);
@@ -430,6 +526,7 @@ struct PsePlane {
         if (k2 > kPseCut * kPseCut) return;
         acc[0] = fma((s[2] - t.f) * pse_eta_pi(k2), s[3], acc[0]);
     }
+    LPM_DEFAULT_GROUP()
     __device__ static __forceinline__ void finalize(const Params& p, const Tgt&, const double (&a)[NA], int64_t i)
     {
         p.out.store(0, i, a[0] * p.inv_eps2);

@@ -158,9 +158,16 @@ template <class K, int T, int BLOCK, int U>
 inline void launch_ds(cudaStream_t st, const typename K::Params& prm, DsGeom g, const double* src,
                       const int32_t* scan, double* partial)
 {
-    g.ntblocks = (int32_t)((g.ntgt + BLOCK * T - 1) / (BLOCK * T));
+    g.tblk0 = g.tbeg / (BLOCK * T) * (BLOCK * T);
+    g.ntblocks = (int32_t)((g.tend - g.tblk0 + BLOCK * T - 1) / (BLOCK * T));
     const int64_t grid = (int64_t)g.ntblocks * g.nchunks;
-    ds_kernel<K, T, BLOCK, U><<<(unsigned)grid, BLOCK, 0, st>>>(prm, g, src, scan, partial);
+    constexpr size_t smem = ds_smem_bytes<K, T, BLOCK>();
+    static bool configured = false;     // per instantiation
+    if (!configured && smem > 48 * 1024) {
+        cudaFuncSetAttribute(ds_kernel<K, T, BLOCK, U>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        configured = true;
+    }
+    ds_kernel<K, T, BLOCK, U><<<(unsigned)grid, BLOCK, smem, st>>>(prm, g, src, scan, partial);
 }
 
 // variant: 0 = automatic choice of targets-per-thread by problem size.
@@ -179,6 +186,7 @@ inline int direct_sum(Device& dev, cudaStream_t st, const MaskPlan& mp, int64_t 
     DsGeom g{};
     g.tbeg = tbeg; g.tend = tend; g.ntgt = tend - tbeg;
     g.nsrc = mp.nsrc;
+    g.nall = mp.n;
     ds_chunks(mp.nsrc, &g.nsrc_pad, &g.chunk, &g.nchunks);
     double* partial = nullptr;
     if (g.nchunks > 1) {
@@ -213,7 +221,9 @@ inline int reserve_sources(Device& dev, const MaskPlan& mp, int32_t* nsrc_pad)
     return dev.ws.sources.reserve((size_t)(*nsrc_pad) * K::NS * sizeof(double));
 }
 
-// Heuristic shared by all kernels: largest T that still yields >= 2 CTAs per SM.
+// Heuristic shared by all kernels: largest T that still yields >= 2 CTAs per SM for the
+// WHOLE particle set (not the slice), so the launch shape -- and with it the grouping of
+// batched reciprocals -- is the same on 1 and on 8 GPUs.
 inline int auto_T(int64_t ntgt, int nchunks, int sm_count, int block)
 {
     const int64_t want = 2LL * sm_count;
@@ -228,7 +238,7 @@ template <class K>
 inline int launch_variant(int variant, cudaStream_t st, const typename K::Params& prm, const DsGeom& g,
                           const double* src, const int32_t* scan, double* partial, int sm_count)
 {
-    int T = auto_T(g.ntgt, g.nchunks, sm_count, 128);
+    int T = auto_T(g.nall, g.nchunks, sm_count, 128);
     (void)variant;
     switch (T) {
         case 4: launch_ds<K, 4, 128, 1>(st, prm, g, src, scan, partial); break;
@@ -245,7 +255,7 @@ inline int launch_variant<BveVel>(int variant, cudaStream_t st, const BveVel::Pa
 {
     using K = BveVel;
     if (variant == 0) {
-        int T = auto_T(g.ntgt, g.nchunks, sm_count, 128);
+        int T = auto_T(g.nall, g.nchunks, sm_count, 128);
         variant = (T == 4) ? 1 : (T == 2) ? 5 : 6;
     }
     switch (variant) {
@@ -259,6 +269,12 @@ inline int launch_variant<BveVel>(int variant, cudaStream_t st, const BveVel::Pa
         case 8: launch_ds<K, 2, 256, 4>(st, prm, g, src, scan, partial); break;
         case 9: launch_ds<K, 4, 64, 2>(st, prm, g, src, scan, partial); break;
         case 10: launch_ds<K, 8, 64, 2>(st, prm, g, src, scan, partial); break;
+        // A/B: same tiling as variant 1 with one MUFU per pair / per two pairs
+        case 11: launch_ds<BveVelT<1>, 4, 128, 2>(st, prm, g, src, scan, partial); break;
+        case 12: launch_ds<BveVelT<2>, 4, 128, 2>(st, prm, g, src, scan, partial); break;
+        case 13: launch_ds<K, 8, 128, 2>(st, prm, g, src, scan, partial); break;
+        case 14: launch_ds<K, 4, 128, 1>(st, prm, g, src, scan, partial); break;
+        case 15: launch_ds<K, 4, 192, 2>(st, prm, g, src, scan, partial); break;
         default: return set_error(LPM_ERR_INVALID, "unknown BVE kernel variant %d", variant);
     }
     return LPM_OK;
