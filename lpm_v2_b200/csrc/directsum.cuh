@@ -106,8 +106,9 @@ __device__ __forceinline__ void tma_bulk_g2s(void* dst_smem, const void* src_gme
 //   Params            kernel-wide constants + target array pointers
 //   Tgt               per-target registers
 //   load_target(p,i)  -> Tgt
-//   group<T,CHECK>(p, tgt[T], s[NS], acc[T][NA], j, self[T])   one source against the
+//   group<T,CHECK>(p, tgt[T], s[NS], acc[T][NA], j, self[T], ks)   one source against the
 //                     thread's T targets; with CHECK, target t skips the pair when j == self[t]
+//   KS, init_shared(ks, tid, nthreads)   optional per-CTA shared table (KS doubles)
 //   finalize(p, tgt, acc, i)   writes the outputs of target i
 //
 // partial layout: [(chunk*NA + a) * ntgt + local_target]
@@ -122,7 +123,8 @@ ds_kernel(const typename K::Params prm, const DsGeom g, const double* __restrict
     extern __shared__ __align__(128) unsigned char smem_raw[];
     double(*tile)[TS * NS] = reinterpret_cast<double(*)[TS * NS]>(smem_raw);
     double* run = reinterpret_cast<double*>(smem_raw + 2 * kTileBytes);
-    uint64_t* full = reinterpret_cast<uint64_t*>(smem_raw + 2 * kTileBytes + sizeof(double) * BLOCK * T * NA);
+    double* ks = run + BLOCK * T * NA;              // kernel-specific shared data (K::KS doubles)
+    uint64_t* full = reinterpret_cast<uint64_t*>(ks + K::KS);
 
     const int tid = threadIdx.x;
     const int tb = blockIdx.x % g.ntblocks;         // chunk is the slow index: CTAs that run
@@ -168,6 +170,7 @@ ds_kernel(const typename K::Params prm, const DsGeom g, const double* __restrict
     if (s1 > g.nsrc_pad) s1 = g.nsrc_pad;
     const int ntiles = (s1 - s0) / TS;
 
+    K::init_shared(ks, tid, BLOCK);
     if (tid == 0) {
         mbar_init(&full[0], 1);
         mbar_init(&full[1], 1);
@@ -199,7 +202,7 @@ ds_kernel(const typename K::Params prm, const DsGeom g, const double* __restrict
                     double2 v = p2[q];
                     s[2 * q] = v.x; s[2 * q + 1] = v.y;
                 }
-                K::template group<T, false>(prm, tg, s, acc, 0, self);
+                K::template group<T, false>(prm, tg, s, acc, 0, self, ks);
             }
         } else {
 #pragma unroll 1
@@ -211,7 +214,7 @@ ds_kernel(const typename K::Params prm, const DsGeom g, const double* __restrict
                     double2 v = p2[q];
                     s[2 * q] = v.x; s[2 * q + 1] = v.y;
                 }
-                K::template group<T, true>(prm, tg, s, acc, j0 + j, self);
+                K::template group<T, true>(prm, tg, s, acc, j0 + j, self, ks);
             }
         }
         // Two-level summation: the tile's sum joins the running sum (kept in shared memory,
@@ -255,7 +258,8 @@ ds_kernel(const typename K::Params prm, const DsGeom g, const double* __restrict
 template <class K, int T, int BLOCK>
 constexpr size_t ds_smem_bytes()
 {
-    return 2 * size_t(kTile) * K::NS * sizeof(double) + sizeof(double) * BLOCK * T * K::NA + 2 * sizeof(uint64_t);
+    return 2 * size_t(kTile) * K::NS * sizeof(double) + sizeof(double) * (BLOCK * T * K::NA + K::KS) +
+           2 * sizeof(uint64_t);
 }
 
 // Adds the chunk partials in chunk order and writes the outputs.

@@ -83,13 +83,54 @@ __device__ __forceinline__ void rcp_batch(const double (&d)[T], double (&r)[T])
     }
 }
 
+// Kernels without a per-CTA shared table.
+struct NoSharedTable {
+    static constexpr int KS = 0;
+    __device__ static __forceinline__ void init_shared(double*, int, int) {}
+};
+
+// ln(d) for finite normal d > 0 from a 128-entry table in shared memory ({1/c_k, ln c_k},
+// c_k = 1 + (k + 1/2)/128) and a degree-6 polynomial for ln(1 + r), |r| <= 2^-8:
+// 9 FP64-pipe ops and one LDS.128 instead of the ~28 FP64 ops + branches of log().
+// Absolute error ~2e-16 + 1 ulp of the result.  Anything else (d <= 0, subnormal, inf,
+// NaN) takes the library log() so the reference's -inf / NaN behaviour is kept.
+constexpr int kLogTabDoubles = 256;
+__device__ double g_log_table[kLogTabDoubles];
+
+struct LogSharedTable {
+    static constexpr int KS = kLogTabDoubles;
+    __device__ static __forceinline__ void init_shared(double* ks, int tid, int nthreads)
+    {
+        for (int q = tid; q < kLogTabDoubles; q += nthreads) ks[q] = g_log_table[q];
+    }
+};
+
+__device__ __forceinline__ double log_tab(double d, const double* tab)
+{
+    const int hi = __double2hiint(d), lo = __double2loint(d);
+    if ((unsigned)(hi - 0x00100000) >= 0x7fe00000u) return log(d);
+    const int e = (hi >> 20) - 1023;
+    const int k = (hi >> 13) & 0x7f;
+    const double m = __hiloint2double((hi & 0x000fffff) | 0x3ff00000, lo);
+    const double2 t = *reinterpret_cast<const double2*>(tab + 2 * k);
+    const double r = fma(m, t.x, -1.0);
+    const double ed = __hiloint2double(0x43300000, e ^ 0x80000000) - 4503601774854144.0;   // (double)e
+    double p = fma(r, -1.0 / 6.0, 0.2);
+    p = fma(r, p, -0.25);
+    p = fma(r, p, 1.0 / 3.0);
+    p = fma(r, p, -0.5);
+    p = fma(r, p, 1.0);
+    return fma(r, p, fma(ed, 0.693147180559945309417232121458, t.y));
+}
+
 // Default group(): one source against the thread's T targets, one pair at a time.
 #define LPM_DEFAULT_GROUP()                                                                              \
     template <int T, bool CHECK>                                                                         \
     __device__ static __forceinline__ void group(const Params& p, const Tgt (&t)[T], const double (&s)[NS], \
-                                                 double (&acc)[T][NA], int32_t j, const int32_t (&self)[T]) \
+                                                 double (&acc)[T][NA], int32_t j, const int32_t (&self)[T], \
+                                                 const double* ks)                                       \
     {                                                                                                    \
-        _Pragma("unroll") for (int k = 0; k < T; ++k) pair<CHECK>(p, t[k], s, acc[k], CHECK && (j == self[k])); \
+        _Pragma("unroll") for (int k = 0; k < T; ++k) pair<CHECK>(p, t[k], s, acc[k], CHECK && (j == self[k]), ks); \
     }
 
 // =============================================================================
@@ -106,7 +147,7 @@ struct BveVelParams {
 };
 struct BveVelTgt { double x, y, z; };
 template <int RG>      // RG: reciprocals sharing one MUFU (1 = none, 2, 4)
-struct BveVelT {
+struct BveVelT : NoSharedTable {
     static constexpr int NS = 6, NA = 3;
     static constexpr bool SKIP_SELF = true;
     using Params = BveVelParams;
@@ -117,7 +158,7 @@ struct BveVelT {
     }
     template <int T, bool CHECK>
     __device__ static __forceinline__ void group(const Params& p, const Tgt (&t)[T], const double (&s)[NS],
-                                                 double (&acc)[T][NA], int32_t j, const int32_t (&self)[T])
+                                                 double (&acc)[T][NA], int32_t j, const int32_t (&self)[T], const double*)
     {
         double d[T], r[T];
 #pragma unroll
@@ -179,7 +220,7 @@ __global__ void pack_bve_vel(int32_t nsrc, int32_t nsrc_pad, const int32_t* __re
 // BVE stream functions.  src/SphereBVE.f90:454-475:
 //   g = -log(R^2 - x_i.x_j)/(4 pi);  relStream_i += g zeta_j A_j;  absStream_i += g omega_j A_j
 // Source record: x, y, z, -zeta A/(4 pi), -omega A/(4 pi), 0.
-struct BveStream {
+struct BveStream : LogSharedTable {
     static constexpr int NS = 6, NA = 2;
     static constexpr bool SKIP_SELF = true;
     struct Params {
@@ -194,13 +235,13 @@ struct BveStream {
     }
     template <bool CHECK>
     __device__ static __forceinline__ void pair(const Params& p, const Tgt& t, const double (&s)[NS],
-                                                double (&acc)[NA], bool skip)
+                                                double (&acc)[NA], bool skip, const double* ks)
     {
         double d = fma(-t.x, s[0], p.R2);
         d = fma(-t.y, s[1], d);
         d = fma(-t.z, s[2], d);
         if (CHECK) d = skip ? 1.0 : d;      // log(1) = 0 removes the pair
-        double l = log(d);
+        double l = log_tab(d, ks);
         acc[0] = fma(l, s[3], acc[0]);
         acc[1] = fma(l, s[4], acc[1]);
     }
@@ -237,7 +278,7 @@ __global__ void pack_bve_stream(int32_t nsrc, int32_t nsrc_pad, const int32_t* _
 //   strength = omega_j A_j / (2 pi ((x_i-x_j)^2 + (y_i-y_j)^2))
 //   u_i -= (y_i-y_j) strength;  v_i += (x_i-x_j) strength
 // Source record: x, y, omega A/(2 pi), 0.
-struct PlaneVel {
+struct PlaneVel : NoSharedTable {
     static constexpr int NS = 4, NA = 2;
     static constexpr bool SKIP_SELF = true;
     struct Params {
@@ -248,7 +289,7 @@ struct PlaneVel {
     __device__ static __forceinline__ Tgt load_target(const Params& p, int64_t i) { return Tgt{p.x[i], p.y[i]}; }
     template <int T, bool CHECK>
     __device__ static __forceinline__ void group(const Params&, const Tgt (&t)[T], const double (&s)[NS],
-                                                 double (&acc)[T][NA], int32_t j, const int32_t (&self)[T])
+                                                 double (&acc)[T][NA], int32_t j, const int32_t (&self)[T], const double*)
     {
         double dx[T], dy[T], r2[T], r[T];
 #pragma unroll
@@ -296,7 +337,7 @@ __global__ void pack_plane(int32_t nsrc, int32_t nsrc_pad, const int32_t* __rest
 
 // Planar stream function.  src/PlanarIncompressible.f90:481-497:
 //   psi_i += log(sqrt(r^2))/(2 pi) omega_j A_j  ==  log(r^2) omega_j A_j/(4 pi)
-struct PlaneStream {
+struct PlaneStream : LogSharedTable {
     static constexpr int NS = 4, NA = 1;
     static constexpr bool SKIP_SELF = true;
     struct Params {
@@ -307,12 +348,12 @@ struct PlaneStream {
     __device__ static __forceinline__ Tgt load_target(const Params& p, int64_t i) { return Tgt{p.x[i], p.y[i]}; }
     template <bool CHECK>
     __device__ static __forceinline__ void pair(const Params&, const Tgt& t, const double (&s)[NS],
-                                                double (&acc)[NA], bool skip)
+                                                double (&acc)[NA], bool skip, const double* ks)
     {
         double dx = t.x - s[0], dy = t.y - s[1];
         double r2 = fma(dx, dx, dy * dy);
         if (CHECK) r2 = skip ? 1.0 : r2;
-        acc[0] = fma(log(r2), s[2], acc[0]);
+        acc[0] = fma(log_tab(r2, ks), s[2], acc[0]);
     }
     LPM_DEFAULT_GROUP()
     __device__ static __forceinline__ void finalize(const Params& p, const Tgt&, const double (&a)[NA], int64_t i)
@@ -332,7 +373,7 @@ struct PlaneStream {
 // and S, C, s, c follow from per-particle sinh/cosh(pi y), sin/cos(pi x) by
 // the addition formulas, so no transcendental is evaluated per pair.
 // Source record: sh, ch, sn, cs, zeta A / 2, 0.
-struct BetaVel {
+struct BetaVel : NoSharedTable {
     static constexpr int NS = 6, NA = 2;
     static constexpr bool SKIP_SELF = true;
     struct Params {
@@ -350,7 +391,7 @@ struct BetaVel {
     }
     template <int T, bool CHECK>
     __device__ static __forceinline__ void group(const Params&, const Tgt (&t)[T], const double (&s)[NS],
-                                                 double (&acc)[T][NA], int32_t j, const int32_t (&self)[T])
+                                                 double (&acc)[T][NA], int32_t j, const int32_t (&self)[T], const double*)
     {
         double SC[T], sc[T], den[T], r[T];
 #pragma unroll
@@ -382,7 +423,7 @@ struct BetaVel {
 // Beta-plane stream functions.  src/BetaPlane.f90:409-431:
 //   g = log(cosh(2 pi dy) - cos(2 pi dx))/(4 pi) = log(2 (S^2 + s^2))/(4 pi)
 // Source record: sh, ch, sn, cs, zeta A/(4 pi), omega A/(4 pi).
-struct BetaStream {
+struct BetaStream : LogSharedTable {
     static constexpr int NS = 6, NA = 2;
     static constexpr bool SKIP_SELF = true;
     using Params = BetaVel::Params;
@@ -390,13 +431,13 @@ struct BetaStream {
     __device__ static __forceinline__ Tgt load_target(const Params& p, int64_t i) { return BetaVel::load_target(p, i); }
     template <bool CHECK>
     __device__ static __forceinline__ void pair(const Params&, const Tgt& t, const double (&s)[NS],
-                                                double (&acc)[NA], bool skip)
+                                                double (&acc)[NA], bool skip, const double* ks)
     {
         double S = fma(t.sh, s[1], -(t.ch * s[0]));
         double sn = fma(t.sn, s[3], -(t.cs * s[2]));
         double den = 2.0 * fma(S, S, sn * sn);
         if (CHECK) den = skip ? 1.0 : den;
-        double l = log(den);
+        double l = log_tab(den, ks);
         acc[0] = fma(l, s[4], acc[0]);
         acc[1] = fma(l, s[5], acc[1]);
     }
@@ -450,7 +491,7 @@ __device__ __forceinline__ double pse_eta_pi(double k2)    // pi * eta
 
 // Sphere: d_ij = atan2(|x_i cross x_j|, x_i.x_j) * SphereRadius  (src/SphereGeometry.f90:107-125).
 // Source record: x, y, z, f, A/(pi eps^2), |x_j|.
-struct PseSphere {
+struct PseSphere : NoSharedTable {
     static constexpr int NS = 6, NA = 1;
     static constexpr bool SKIP_SELF = false;
     struct Params {
@@ -469,7 +510,7 @@ struct PseSphere {
     }
     template <bool CHECK>
     __device__ static __forceinline__ void pair(const Params& p, const Tgt& t, const double (&s)[NS],
-                                                double (&acc)[NA], bool)
+                                                double (&acc)[NA], bool, const double*)
     {
         double dot = fma(t.x, s[0], fma(t.y, s[1], t.z * s[2]));
         if (dot < t.thr * s[5]) return;           // angle beyond the cut-off
@@ -507,7 +548,7 @@ __global__ void pack_pse_sphere(int32_t nsrc, int32_t nsrc_pad, const int32_t* _
 
 // Plane: d_ij = ChordDistance with z = 0 (src/SphereGeometry.f90:67-73, src/Particles.f90:663-670).
 // Source record: x, y, f, A/(pi eps^2).
-struct PsePlane {
+struct PsePlane : NoSharedTable {
     static constexpr int NS = 4, NA = 1;
     static constexpr bool SKIP_SELF = false;
     struct Params {
@@ -519,7 +560,7 @@ struct PsePlane {
     __device__ static __forceinline__ Tgt load_target(const Params& p, int64_t i) { return Tgt{p.x[i], p.y[i], p.f[i]}; }
     template <bool CHECK>
     __device__ static __forceinline__ void pair(const Params& p, const Tgt& t, const double (&s)[NS],
-                                                double (&acc)[NA], bool)
+                                                double (&acc)[NA], bool, const double*)
     {
         double dx = s[0] - t.x, dy = s[1] - t.y;
         double k2 = fma(dx, dx, dy * dy) * p.inv_eps2;

@@ -4,6 +4,7 @@
 #include <dlfcn.h>
 
 #include <algorithm>
+#include <cmath>
 
 #include "common.cuh"
 #include "directsum.cuh"
@@ -23,6 +24,15 @@ inline int init_device(Device& d, int id)
         return set_error(LPM_ERR_NO_DEVICE, "device %d (%s) is sm_%d%d; liblpmgpu is built for sm_100a only", id,
                          prop.name, prop.major, prop.minor);
     d.sm_count = prop.multiProcessorCount;
+    {   // table for log_tab(): {1/c_k, ln c_k}, c_k = 1 + (k + 1/2)/128, rounded from long double
+        double tab[kLogTabDoubles];
+        for (int k = 0; k < kLogTabDoubles / 2; ++k) {
+            long double c = 1.0L + ((long double)k + 0.5L) / 128.0L;
+            tab[2 * k] = (double)(1.0L / c);
+            tab[2 * k + 1] = (double)logl(c);
+        }
+        LPM_CUDA(cudaMemcpyToSymbol(g_log_table, tab, sizeof(tab)));
+    }
     LPM_CUDA(cudaStreamCreateWithFlags(&d.stream, cudaStreamNonBlocking));
     LPM_CUDA(cudaEventCreateWithFlags(&d.ev_done, cudaEventDisableTiming));
     return LPM_OK;
