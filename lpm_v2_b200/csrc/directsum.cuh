@@ -85,6 +85,7 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity)
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity)
 {
     // Bounded: a lost copy traps instead of hanging the device.
+#pragma unroll 1
     for (uint32_t it = 0; it < (1u << 26); ++it)
         if (mbar_try_wait(bar, parity)) return;
     __trap();

@@ -105,10 +105,12 @@ struct LogSharedTable {
     }
 };
 
+__device__ __noinline__ double log_slow_path(double d) { return log(d); }
+
 __device__ __forceinline__ double log_tab(double d, const double* tab)
 {
     const int hi = __double2hiint(d), lo = __double2loint(d);
-    if ((unsigned)(hi - 0x00100000) >= 0x7fe00000u) return log(d);
+    if (__builtin_expect((unsigned)(hi - 0x00100000) >= 0x7fe00000u, 0)) return log_slow_path(d);
     const int e = (hi >> 20) - 1023;
     const int k = (hi >> 13) & 0x7f;
     const double m = __hiloint2double((hi & 0x000fffff) | 0x3ff00000, lo);
