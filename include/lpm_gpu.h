@@ -132,6 +132,40 @@ int lpm_pse_laplacian_plane(int64_t n, const double* x, const double* y,
                             const double* f, const double* area, const int32_t* mask,
                             double eps, double* lap);
 
+/* Remaining PSE operators.  sphere_radius as above.
+ * PSE{Sphere,Plane}InterpolateScalar, src/PSEDirectSum.f90:128-168, evaluated at m
+ * arbitrary locations (tx, ty[, tz]) -- e.g. the lat-lon grid of tests/SpherePSEConvTest.f90:188-211. */
+int lpm_pse_interpolate_sphere(int64_t n, const double* x, const double* y, const double* z,
+                               const double* f, const double* area, const int32_t* mask,
+                               double eps, double sphere_radius,
+                               int64_t m, const double* tx, const double* ty, const double* tz, double* out);
+int lpm_pse_interpolate_plane(int64_t n, const double* x, const double* y,
+                              const double* f, const double* area, const int32_t* mask, double eps,
+                              int64_t m, const double* tx, const double* ty, double* out);
+/* PSESphereGradientAtParticles :221-267 / PSEPlaneGradientAtParticles :180-218 */
+int lpm_pse_gradient_sphere(int64_t n, const double* x, const double* y, const double* z,
+                            const double* f, const double* area, const int32_t* mask,
+                            double eps, double sphere_radius, double* gx, double* gy, double* gz);
+int lpm_pse_gradient_plane(int64_t n, const double* x, const double* y,
+                           const double* f, const double* area, const int32_t* mask, double eps,
+                           double* gx, double* gy);
+/* PSEPlaneSecondPartialsAtParticles :269-320: outputs d_xx, (d_xy + d_yx)/2, d_yy */
+int lpm_pse_second_partials_plane(int64_t n, const double* x, const double* y,
+                                  const double* gx, const double* gy, const double* area,
+                                  const int32_t* mask, double eps, double* dxx, double* dxy, double* dyy);
+/* PSEPlaneDoubleDotProductAtParticles :322-365 / PSESphereDoubleDotProductAtParticles :367-420
+ * (the sphere routine's w rows add yComp(i), :408-413; kept as written) */
+int lpm_pse_double_dot_plane(int64_t n, const double* x, const double* y,
+                             const double* u, const double* v, const double* area,
+                             const int32_t* mask, double eps, double* dd);
+int lpm_pse_double_dot_sphere(int64_t n, const double* x, const double* y, const double* z,
+                              const double* u, const double* v, const double* w, const double* area,
+                              const int32_t* mask, double eps, double sphere_radius, double* dd);
+/* PSESphereDivergenceAtParticles :537-579 */
+int lpm_pse_divergence_sphere(int64_t n, const double* x, const double* y, const double* z,
+                              const double* u, const double* v, const double* w, const double* area,
+                              const int32_t* mask, double eps, double sphere_radius, double* div);
+
 /* -------------------------- direct sums, device API (one rank's slice) */
 
 int lpm_bve_velocity_dev(int64_t n, const double* x, const double* y, const double* z,

@@ -182,3 +182,78 @@ def profile_summary(reset=True):
     k, ms = C.c_int64(0), C.c_double(0)
     check(lib.lpm_profile_summary(1 if reset else 0, C.byref(k), C.byref(ms)))
     return k.value, ms.value
+
+
+# ---- remaining PSE operators (src/PSEDirectSum.f90:128-456, 537-579) ----------------
+def _mi(m):
+    return m.ctypes.data_as(_i32)
+
+
+def pse_interpolate_sphere(x, y, z, f, area, mask, eps, tx, ty, tz, sphere_radius=1.0):
+    x, y, z, f, area, tx, ty, tz = map(_f64, (x, y, z, f, area, tx, ty, tz))
+    m = _mask(mask)
+    out = np.empty(tx.size)
+    check(lib.lpm_pse_interpolate_sphere(x.size, _pd(x), _pd(y), _pd(z), _pd(f), _pd(area), _mi(m), float(eps),
+                                         float(sphere_radius), tx.size, _pd(tx), _pd(ty), _pd(tz), _pd(out)))
+    return out
+
+
+def pse_interpolate_plane(x, y, f, area, mask, eps, tx, ty):
+    x, y, f, area, tx, ty = map(_f64, (x, y, f, area, tx, ty))
+    m = _mask(mask)
+    out = np.empty(tx.size)
+    check(lib.lpm_pse_interpolate_plane(x.size, _pd(x), _pd(y), _pd(f), _pd(area), _mi(m), float(eps),
+                                        tx.size, _pd(tx), _pd(ty), _pd(out)))
+    return out
+
+
+def pse_gradient_sphere(x, y, z, f, area, mask, eps, sphere_radius=1.0):
+    x, y, z, f, area = map(_f64, (x, y, z, f, area))
+    m = _mask(mask)
+    g = [np.empty(x.size) for _ in range(3)]
+    check(lib.lpm_pse_gradient_sphere(x.size, _pd(x), _pd(y), _pd(z), _pd(f), _pd(area), _mi(m), float(eps),
+                                      float(sphere_radius), *[_pd(a) for a in g]))
+    return g
+
+
+def pse_gradient_plane(x, y, f, area, mask, eps):
+    x, y, f, area = map(_f64, (x, y, f, area))
+    m = _mask(mask)
+    g = [np.empty(x.size) for _ in range(2)]
+    check(lib.lpm_pse_gradient_plane(x.size, _pd(x), _pd(y), _pd(f), _pd(area), _mi(m), float(eps), *[_pd(a) for a in g]))
+    return g
+
+
+def pse_second_partials_plane(x, y, gx, gy, area, mask, eps):
+    x, y, gx, gy, area = map(_f64, (x, y, gx, gy, area))
+    m = _mask(mask)
+    o = [np.empty(x.size) for _ in range(3)]
+    check(lib.lpm_pse_second_partials_plane(x.size, _pd(x), _pd(y), _pd(gx), _pd(gy), _pd(area), _mi(m), float(eps),
+                                            *[_pd(a) for a in o]))
+    return o
+
+
+def pse_double_dot_plane(x, y, u, v, area, mask, eps):
+    x, y, u, v, area = map(_f64, (x, y, u, v, area))
+    m = _mask(mask)
+    dd = np.empty(x.size)
+    check(lib.lpm_pse_double_dot_plane(x.size, _pd(x), _pd(y), _pd(u), _pd(v), _pd(area), _mi(m), float(eps), _pd(dd)))
+    return dd
+
+
+def pse_double_dot_sphere(x, y, z, u, v, w, area, mask, eps, sphere_radius=1.0):
+    x, y, z, u, v, w, area = map(_f64, (x, y, z, u, v, w, area))
+    m = _mask(mask)
+    dd = np.empty(x.size)
+    check(lib.lpm_pse_double_dot_sphere(x.size, _pd(x), _pd(y), _pd(z), _pd(u), _pd(v), _pd(w), _pd(area), _mi(m),
+                                        float(eps), float(sphere_radius), _pd(dd)))
+    return dd
+
+
+def pse_divergence_sphere(x, y, z, u, v, w, area, mask, eps, sphere_radius=1.0):
+    x, y, z, u, v, w, area = map(_f64, (x, y, z, u, v, w, area))
+    m = _mask(mask)
+    div = np.empty(x.size)
+    check(lib.lpm_pse_divergence_sphere(x.size, _pd(x), _pd(y), _pd(z), _pd(u), _pd(v), _pd(w), _pd(area), _mi(m),
+                                        float(eps), float(sphere_radius), _pd(div)))
+    return div

@@ -78,7 +78,7 @@ struct Workspace {
     DevBuf active;      // int32 [nsrc]  compact -> particle index
     DevBuf sources;     // double [nsrc_pad * NS]
     DevBuf partial;     // double [nchunks * NA * ntgt]
-    DevBuf staging[12]; // host API: device copies of the caller's arrays
+    DevBuf staging[16]; // host API: device copies of the caller's arrays (0-7 in, 8 mask, 9-11 out, 12-14 targets)
     DevBuf reduce;      // small reduction scratch
     void release()
     {

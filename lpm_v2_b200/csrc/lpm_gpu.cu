@@ -313,6 +313,11 @@ int run_host(const Args& host, double* const* out_host)
         if (!out_host[k]) return set_error(LPM_ERR_INVALID, "null output array %d", k);
     if (!host.mask) return set_error(LPM_ERR_INVALID, "null mask");
     const size_t nb = (size_t)n * sizeof(double);
+    const int64_t nt = Op::NTGT ? host.m : n;       // targets: the particles, or separate locations
+    if (nt <= 0) return set_error(LPM_ERR_INVALID, "number of targets = %lld", (long long)nt);
+    for (int k = 0; k < Op::NTGT; ++k)
+        if (!host.tgt[k]) return set_error(LPM_ERR_INVALID, "null target array %d", k);
+    const size_t ntb = (size_t)nt * sizeof(double);
     const int nparts = R.rank_mode ? R.world : (int)R.devs.size();
     int rc = LPM_OK;
     static thread_local MaskPlan plans[kMaxRep];
@@ -330,9 +335,14 @@ int run_host(const Args& host, double* const* out_host)
             LPM_TRY(mbuf.reserve((size_t)n * sizeof(int32_t)));
             LPM_CUDA(cudaMemcpyAsync(mbuf.p, host.mask, (size_t)n * sizeof(int32_t), cudaMemcpyHostToDevice, dev.stream));
             a.mask = mbuf.as<int32_t>();
-            double* out[4];
+            for (int k = 0; k < Op::NTGT; ++k) {
+                LPM_TRY(dev.ws.staging[12 + k].reserve(ntb));
+                LPM_CUDA(cudaMemcpyAsync(dev.ws.staging[12 + k].p, host.tgt[k], ntb, cudaMemcpyHostToDevice, dev.stream));
+                a.tgt[k] = dev.ws.staging[12 + k].as<double>();
+            }
+            double* out[4] = {nullptr, nullptr, nullptr, nullptr};
             for (int k = 0; k < Op::NOUT; ++k) {
-                LPM_TRY(dev.ws.staging[9 + k].reserve(nb));
+                LPM_TRY(dev.ws.staging[9 + k].reserve(ntb));
                 out[k] = dev.ws.staging[9 + k].as<double>();
             }
             LPM_TRY(build_mask_plan(dev.stream, n, a.mask, plans[g]));
@@ -340,11 +350,11 @@ int run_host(const Args& host, double* const* out_host)
             typename Op::K::Params prm = Op::params(a);
             set_outs(prm.out, out);
             int64_t b, e;
-            load_balance0(n, nparts, R.rank_mode ? R.rank : (int)g, &b, &e);
-            LPM_TRY(direct_sum<typename Op::K>(dev, dev.stream, plans[g], b, e, prm, Op::variant()));
+            load_balance0(nt, nparts, R.rank_mode ? R.rank : (int)g, &b, &e);
+            LPM_TRY(direct_sum<typename Op::K>(dev, dev.stream, plans[g], b, e, prm, Op::variant(), nt));
             if (R.rank_mode) {
-                LPM_TRY(allgather_slices(Op::NOUT, out, n, dev.stream));
-                b = 0; e = n;
+                LPM_TRY(allgather_slices(Op::NOUT, out, nt, dev.stream));
+                b = 0; e = nt;
             }
             for (int k = 0; k < Op::NOUT; ++k)
                 if (e > b)
@@ -497,6 +507,85 @@ extern "C" int lpm_pse_laplacian_plane_dev(int64_t n, const double* x, const dou
     Args a{n, {x, y, f, area}, mask, {eps}};
     double* out[1] = {lap};
     return run_dev<OpPsePlane>(a, ibeg, iend, out, stream);
+}
+
+// ---- remaining PSE operators (src/PSEDirectSum.f90:128-456, 537-579) -------------
+static int check_eps(double eps, double sr)
+{
+    if (!(eps > 0.0) || !(sr > 0.0)) return set_error(LPM_ERR_INVALID, "eps and sphere_radius must be positive");
+    return LPM_OK;
+}
+extern "C" int lpm_pse_interpolate_sphere(int64_t n, const double* x, const double* y, const double* z, const double* f,
+                                          const double* area, const int32_t* mask, double eps, double sphere_radius,
+                                          int64_t m, const double* tx, const double* ty, const double* tz, double* out)
+{
+    LPM_TRY(check_eps(eps, sphere_radius));
+    Args a{n, {x, y, z, f, area}, mask, {eps, sphere_radius}};
+    a.m = m; a.tgt[0] = tx; a.tgt[1] = ty; a.tgt[2] = tz;
+    double* o[1] = {out};
+    return run_host<OpPseInterpSphere>(a, o);
+}
+extern "C" int lpm_pse_interpolate_plane(int64_t n, const double* x, const double* y, const double* f, const double* area,
+                                         const int32_t* mask, double eps, int64_t m, const double* tx, const double* ty,
+                                         double* out)
+{
+    LPM_TRY(check_eps(eps, 1.0));
+    Args a{n, {x, y, f, area}, mask, {eps}};
+    a.m = m; a.tgt[0] = tx; a.tgt[1] = ty;
+    double* o[1] = {out};
+    return run_host<OpPseInterpPlane>(a, o);
+}
+extern "C" int lpm_pse_gradient_sphere(int64_t n, const double* x, const double* y, const double* z, const double* f,
+                                       const double* area, const int32_t* mask, double eps, double sphere_radius,
+                                       double* gx, double* gy, double* gz)
+{
+    LPM_TRY(check_eps(eps, sphere_radius));
+    Args a{n, {x, y, z, f, area}, mask, {eps, sphere_radius}};
+    double* o[3] = {gx, gy, gz};
+    return run_host<OpPseGradSphere>(a, o);
+}
+extern "C" int lpm_pse_gradient_plane(int64_t n, const double* x, const double* y, const double* f, const double* area,
+                                      const int32_t* mask, double eps, double* gx, double* gy)
+{
+    LPM_TRY(check_eps(eps, 1.0));
+    Args a{n, {x, y, f, area}, mask, {eps}};
+    double* o[2] = {gx, gy};
+    return run_host<OpPseGradPlane>(a, o);
+}
+extern "C" int lpm_pse_second_partials_plane(int64_t n, const double* x, const double* y, const double* gx,
+                                             const double* gy, const double* area, const int32_t* mask, double eps,
+                                             double* dxx, double* dxy, double* dyy)
+{
+    LPM_TRY(check_eps(eps, 1.0));
+    Args a{n, {x, y, gx, gy, area}, mask, {eps}};
+    double* o[3] = {dxx, dxy, dyy};
+    return run_host<OpPseTensorPlane<0>>(a, o);
+}
+extern "C" int lpm_pse_double_dot_plane(int64_t n, const double* x, const double* y, const double* u, const double* v,
+                                        const double* area, const int32_t* mask, double eps, double* dd)
+{
+    LPM_TRY(check_eps(eps, 1.0));
+    Args a{n, {x, y, u, v, area}, mask, {eps}};
+    double* o[1] = {dd};
+    return run_host<OpPseTensorPlane<1>>(a, o);
+}
+extern "C" int lpm_pse_double_dot_sphere(int64_t n, const double* x, const double* y, const double* z, const double* u,
+                                         const double* v, const double* w, const double* area, const int32_t* mask,
+                                         double eps, double sphere_radius, double* dd)
+{
+    LPM_TRY(check_eps(eps, sphere_radius));
+    Args a{n, {x, y, z, u, v, w, area}, mask, {eps, sphere_radius}};
+    double* o[1] = {dd};
+    return run_host<OpPseDoubleDotSphere>(a, o);
+}
+extern "C" int lpm_pse_divergence_sphere(int64_t n, const double* x, const double* y, const double* z, const double* u,
+                                         const double* v, const double* w, const double* area, const int32_t* mask,
+                                         double eps, double sphere_radius, double* div)
+{
+    LPM_TRY(check_eps(eps, sphere_radius));
+    Args a{n, {x, y, z, u, v, w, area}, mask, {eps, sphere_radius}};
+    double* o[1] = {div};
+    return run_host<OpPseDivSphere>(a, o);
 }
 
 // ============================================================== resident solvers

@@ -190,13 +190,13 @@ inline int launch_variant(int variant, cudaStream_t st, const typename K::Params
 // [tbeg, tend) against all sources and writes the outputs named in prm.out.
 template <class K>
 inline int direct_sum(Device& dev, cudaStream_t st, const MaskPlan& mp, int64_t tbeg, int64_t tend,
-                      const typename K::Params& prm, int variant = 0)
+                      const typename K::Params& prm, int variant = 0, int64_t ntargets_all = -1)
 {
     if (tend <= tbeg) return LPM_OK;
     DsGeom g{};
     g.tbeg = tbeg; g.tend = tend; g.ntgt = tend - tbeg;
     g.nsrc = mp.nsrc;
-    g.nall = mp.n;
+    g.nall = ntargets_all >= 0 ? ntargets_all : mp.n;     // targets are the particles unless told otherwise
     ds_chunks(mp.nsrc, &g.nsrc_pad, &g.chunk, &g.nchunks);
     double* partial = nullptr;
     if (g.nchunks > 1) {

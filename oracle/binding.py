@@ -246,3 +246,91 @@ def bve_velocity_mt(nthreads, x, y, z, relvort, area, mask, radius, tbeg, tend):
     get(fast=True).oracle_bve_velocity_mt(nthreads, n, _p(x), _p(y), _p(z), _p(relvort), _p(area),
                                           m.ctypes.data_as(_i32), radius, tbeg, tend, _p(u), _p(v), _p(w))
     return u, v, w
+
+
+# ---- remaining PSE operators ---------------------------------------------------------
+def _declare_pse_ops(lib):
+    lib.oracle_pse_interpolate.argtypes = [C.c_int, _n, _d, _d, _d, _d, _d, _i32, _dbl, _dbl, _n, _d, _d, _d, _d]
+    lib.oracle_pse_gradient_plane.argtypes = [_n, _d, _d, _d, _d, _i32, _dbl, _n, _n, _d, _d]
+    lib.oracle_pse_gradient_sphere.argtypes = [_n, _d, _d, _d, _d, _d, _i32, _dbl, _dbl, _n, _n, _d, _d, _d]
+    lib.oracle_pse_second_partials_plane.argtypes = [_n, _d, _d, _d, _d, _d, _i32, _dbl, _n, _n, _d, _d, _d]
+    lib.oracle_pse_double_dot_plane.argtypes = [_n, _d, _d, _d, _d, _d, _i32, _dbl, _n, _n, _d]
+    lib.oracle_pse_double_dot_sphere.argtypes = [_n, _d, _d, _d, _d, _d, _d, _d, _i32, _dbl, _dbl, _n, _n, _d]
+    lib.oracle_pse_divergence_sphere.argtypes = [_n, _d, _d, _d, _d, _d, _d, _d, _i32, _dbl, _dbl, _n, _n, _d]
+    for nm in ("oracle_pse_interpolate", "oracle_pse_gradient_plane", "oracle_pse_gradient_sphere",
+               "oracle_pse_second_partials_plane", "oracle_pse_double_dot_plane", "oracle_pse_double_dot_sphere",
+               "oracle_pse_divergence_sphere"):
+        getattr(lib, nm).restype = None
+    return lib
+
+
+def _L():
+    lib = get()
+    if not getattr(lib, "_pse_ops", False):
+        _declare_pse_ops(lib)
+        lib._pse_ops = True
+    return lib
+
+
+def pse_interpolate(x, y, z, f, area, mask, eps, tx, ty, tz=None, sphere_radius=1.0):
+    sphere = tz is not None
+    x, y, f, area, tx, ty = map(_f, (x, y, f, area, tx, ty))
+    z = _f(z) if sphere else np.zeros_like(x)
+    tz = _f(tz) if sphere else np.zeros_like(tx)
+    m = _m(mask)
+    out = np.zeros(tx.size)
+    _L().oracle_pse_interpolate(1 if sphere else 0, x.size, _p(x), _p(y), _p(z), _p(f), _p(area), m.ctypes.data_as(_i32),
+                                eps, sphere_radius, tx.size, _p(tx), _p(ty), _p(tz), _p(out))
+    return out
+
+
+def pse_gradient_plane(x, y, f, area, mask, eps):
+    x, y, f, area = map(_f, (x, y, f, area))
+    m = _m(mask)
+    g = [np.zeros(x.size) for _ in range(2)]
+    _L().oracle_pse_gradient_plane(x.size, _p(x), _p(y), _p(f), _p(area), m.ctypes.data_as(_i32), eps, 0, x.size, *[_p(a) for a in g])
+    return g
+
+
+def pse_gradient_sphere(x, y, z, f, area, mask, eps, sphere_radius=1.0):
+    x, y, z, f, area = map(_f, (x, y, z, f, area))
+    m = _m(mask)
+    g = [np.zeros(x.size) for _ in range(3)]
+    _L().oracle_pse_gradient_sphere(x.size, _p(x), _p(y), _p(z), _p(f), _p(area), m.ctypes.data_as(_i32), eps,
+                                    sphere_radius, 0, x.size, *[_p(a) for a in g])
+    return g
+
+
+def pse_second_partials_plane(x, y, gx, gy, area, mask, eps):
+    x, y, gx, gy, area = map(_f, (x, y, gx, gy, area))
+    m = _m(mask)
+    o = [np.zeros(x.size) for _ in range(3)]
+    _L().oracle_pse_second_partials_plane(x.size, _p(x), _p(y), _p(gx), _p(gy), _p(area), m.ctypes.data_as(_i32), eps,
+                                          0, x.size, *[_p(a) for a in o])
+    return o
+
+
+def pse_double_dot_plane(x, y, u, v, area, mask, eps):
+    x, y, u, v, area = map(_f, (x, y, u, v, area))
+    m = _m(mask)
+    dd = np.zeros(x.size)
+    _L().oracle_pse_double_dot_plane(x.size, _p(x), _p(y), _p(u), _p(v), _p(area), m.ctypes.data_as(_i32), eps, 0, x.size, _p(dd))
+    return dd
+
+
+def pse_double_dot_sphere(x, y, z, u, v, w, area, mask, eps, sphere_radius=1.0):
+    x, y, z, u, v, w, area = map(_f, (x, y, z, u, v, w, area))
+    m = _m(mask)
+    dd = np.zeros(x.size)
+    _L().oracle_pse_double_dot_sphere(x.size, _p(x), _p(y), _p(z), _p(u), _p(v), _p(w), _p(area), m.ctypes.data_as(_i32),
+                                      eps, sphere_radius, 0, x.size, _p(dd))
+    return dd
+
+
+def pse_divergence_sphere(x, y, z, u, v, w, area, mask, eps, sphere_radius=1.0):
+    x, y, z, u, v, w, area = map(_f, (x, y, z, u, v, w, area))
+    m = _m(mask)
+    div = np.zeros(x.size)
+    _L().oracle_pse_divergence_sphere(x.size, _p(x), _p(y), _p(z), _p(u), _p(v), _p(w), _p(area), m.ctypes.data_as(_i32),
+                                      eps, sphere_radius, 0, x.size, _p(div))
+    return div

@@ -595,3 +595,204 @@ void oracle_bve_velocity_mt(int nthreads, int64_t n, const double *x, const doub
     for (int t = 0; t < nthreads; ++t) pthread_join(th[t], NULL);
     free(th); free(jobs);
 }
+
+/* ================================================================== */
+/* Remaining PSE operators.                    */
+
+/* src/PSEDirectSum.f90:611-616  bivariateDeltaKernel8                 */
+static double bivariateDeltaKernel8(double r)
+{
+    double r2 = r * r, r4 = r2 * r2, r6 = r4 * r2;
+    return (4.0 - 6.0 * r2 + 2.0 * r4 - r6 / 6.0) * exp(-r * r) / PI;
+}
+
+/* src/PSEDirectSum.f90:629-634  bivariateFirstDerivativeKernel8       */
+static double bivariateFirstDerivativeKernel8(double r)
+{
+    double r2 = r * r, r4 = r2 * r2, r6 = r4 * r2;
+    return (-20.0 + 20.0 * r2 - 5.0 * r4 + r6 / 3.0) * exp(-r * r) / PI;
+}
+
+/* src/SphereGeometry.f90:578-590  SphereProjection, applied: P g      */
+static void sphere_project(const double x[3], const double g[3], double out[3])
+{
+    double P[3][3];
+    P[0][0] = 1.0 - x[0] * x[0]; P[1][0] = -x[1] * x[0]; P[2][0] = -x[2] * x[0];
+    P[0][1] = -x[0] * x[1]; P[1][1] = 1.0 - x[1] * x[1]; P[2][1] = -x[2] * x[1];
+    P[0][2] = -x[0] * x[2]; P[1][2] = -x[1] * x[2]; P[2][2] = 1.0 - x[2] * x[2];
+    for (int r = 0; r < 3; ++r) out[r] = P[r][0] * g[0] + P[r][1] * g[1] + P[r][2] * g[2];   /* MATMUL */
+}
+
+/* src/PSEDirectSum.f90:128-168  PSE{Plane,Sphere}InterpolateScalar at m
+ * arbitrary locations (tx,ty,tz); sphere != 0 selects SphereDistance.   */
+void oracle_pse_interpolate(int sphere, int64_t n, const double *x, const double *y, const double *z,
+                            const double *f, const double *area, const int32_t *mask, double eps,
+                            double sphereRadius, int64_t m, const double *tx, const double *ty,
+                            const double *tz, double *out)
+{
+    for (int64_t i = 0; i < m; ++i) {
+        double loc[3] = { tx[i], ty[i], sphere ? tz[i] : 0.0 };
+        double s = 0.0;
+        for (int64_t j = 0; j < n; ++j) {
+            if (mask[j]) {
+                double xj[3] = { x[j], y[j], sphere ? z[j] : 0.0 };
+                double kIn = (sphere ? SphereDistance(xj, loc, sphereRadius) : ChordDistance(loc, xj)) / eps;
+                s = s + f[j] * area[j] * bivariateDeltaKernel8(kIn) / (eps * eps);
+            }
+        }
+        out[i] = s;
+    }
+}
+
+/* src/PSEDirectSum.f90:180-218  PSEPlaneGradientAtParticles            */
+void oracle_pse_gradient_plane(int64_t n, const double *x, const double *y, const double *f,
+                               const double *area, const int32_t *mask, double eps,
+                               int64_t ibeg, int64_t iend, double *gx, double *gy)
+{
+    for (int64_t i = ibeg; i < iend; ++i) {
+        double xi[3] = { x[i], y[i], 0.0 };
+        gx[i] = 0.0; gy[i] = 0.0;
+        for (int64_t j = 0; j < n; ++j) {
+            if (mask[j]) {
+                double xj[3] = { x[j], y[j], 0.0 };
+                double kIn = ChordDistance(xi, xj) / eps;
+                gx[i] = gx[i] + (f[j] + f[i]) * (xi[0] - xj[0]) * bivariateFirstDerivativeKernel8(kIn) / (eps * eps * eps) * area[j];
+                gy[i] = gy[i] + (f[j] + f[i]) * (xi[1] - xj[1]) * bivariateFirstDerivativeKernel8(kIn) / (eps * eps * eps) * area[j];
+            }
+        }
+    }
+    for (int64_t i = ibeg; i < iend; ++i) { gx[i] = (1.0 / eps) * gx[i]; gy[i] = (1.0 / eps) * gy[i]; }
+}
+
+/* src/PSEDirectSum.f90:221-267  PSESphereGradientAtParticles           */
+void oracle_pse_gradient_sphere(int64_t n, const double *x, const double *y, const double *z, const double *f,
+                                const double *area, const int32_t *mask, double eps, double sphereRadius,
+                                int64_t ibeg, int64_t iend, double *gx, double *gy, double *gz)
+{
+    for (int64_t i = ibeg; i < iend; ++i) {
+        double xi[3] = { x[i], y[i], z[i] };
+        double grad[3] = { 0.0, 0.0, 0.0 }, pg[3];
+        for (int64_t j = 0; j < n; ++j) {
+            if (mask[j]) {
+                double xj[3] = { x[j], y[j], z[j] };
+                double kIn = SphereDistance(xj, xi, sphereRadius) / eps;
+                double kOut = bivariateFirstDerivativeKernel8(kIn) / (eps * eps);
+                grad[0] = grad[0] + (f[j] + f[i]) * (xi[0] - xj[0]) * kOut * area[j];
+                grad[1] = grad[1] + (f[j] + f[i]) * (xi[1] - xj[1]) * kOut * area[j];
+                grad[2] = grad[2] + (f[j] + f[i]) * (xi[2] - xj[2]) * kOut * area[j];
+            }
+        }
+        sphere_project(xi, grad, pg);
+        gx[i] = pg[0]; gy[i] = pg[1]; gz[i] = pg[2];
+    }
+    for (int64_t i = ibeg; i < iend; ++i) {
+        gx[i] = (1.0 / (eps * eps)) * gx[i]; gy[i] = (1.0 / (eps * eps)) * gy[i]; gz[i] = (1.0 / (eps * eps)) * gz[i];
+    }
+}
+
+/* src/PSEDirectSum.f90:269-320  PSEPlaneSecondPartialsAtParticles: outputs
+ * (d_xx, (d_xy + d_yx)/2, d_yy) in xComp, yComp, zComp.                 */
+void oracle_pse_second_partials_plane(int64_t n, const double *x, const double *y, const double *gxIn,
+                                      const double *gyIn, const double *area, const int32_t *mask, double eps,
+                                      int64_t ibeg, int64_t iend, double *oxx, double *oxy, double *oyy)
+{
+    for (int64_t i = ibeg; i < iend; ++i) {
+        double xi[3] = { x[i], y[i], 0.0 };
+        double dxx = 0.0, dxy = 0.0, dyx = 0.0, dyy = 0.0;
+        for (int64_t j = 0; j < n; ++j) {
+            if (mask[j]) {
+                double xj[3] = { x[j], y[j], 0.0 };
+                double kIn = ChordDistance(xi, xj) / eps;
+                double kOut = bivariateFirstDerivativeKernel8(kIn) / (eps * eps);
+                dxx = dxx + (gxIn[j] + gxIn[i]) * (xi[0] - xj[0]) / eps * kOut * area[j];
+                dxy = dxy + (gxIn[j] + gxIn[i]) * (xi[1] - xj[1]) / eps * kOut * area[j];
+                dyx = dyx + (gyIn[j] + gyIn[i]) * (xi[0] - xj[0]) / eps * kOut * area[j];
+                dyy = dyy + (gyIn[j] + gyIn[i]) * (xi[1] - xj[1]) / eps * kOut * area[j];
+            }
+        }
+        oxx[i] = dxx; oxy[i] = 0.5 * (dxy + dyx); oyy[i] = dyy;
+    }
+    for (int64_t i = ibeg; i < iend; ++i) {
+        oxx[i] = (1.0 / eps) * oxx[i]; oxy[i] = (1.0 / eps) * oxy[i]; oyy[i] = (1.0 / eps) * oyy[i];
+    }
+}
+
+/* src/PSEDirectSum.f90:322-365  PSEPlaneDoubleDotProductAtParticles    */
+void oracle_pse_double_dot_plane(int64_t n, const double *x, const double *y, const double *u, const double *v,
+                                 const double *area, const int32_t *mask, double eps,
+                                 int64_t ibeg, int64_t iend, double *dd)
+{
+    for (int64_t i = ibeg; i < iend; ++i) {
+        double xi[3] = { x[i], y[i], 0.0 };
+        double ux = 0.0, uy = 0.0, vx = 0.0, vy = 0.0;
+        for (int64_t j = 0; j < n; ++j) {
+            if (mask[j]) {
+                double xj[3] = { x[j], y[j], 0.0 };
+                double kIn = ChordDistance(xi, xj) / eps;
+                double kOut = bivariateFirstDerivativeKernel8(kIn) / (eps * eps);
+                ux = ux + (u[j] + u[i]) * (xi[0] - xj[0]) / eps * kOut * area[j];
+                uy = uy + (u[j] + u[i]) * (xi[1] - xj[1]) / eps * kOut * area[j];
+                vx = vx + (v[j] + v[i]) * (xi[0] - xj[0]) / eps * kOut * area[j];
+                vy = vy + (v[j] + v[i]) * (xi[1] - xj[1]) / eps * kOut * area[j];
+            }
+        }
+        dd[i] = (ux * ux + 2.0 * uy * vx + vy * vy) / (eps * eps);
+    }
+}
+
+/* src/PSEDirectSum.f90:367-420  PSESphereDoubleDotProductAtParticles.
+ * The w rows add vectorField%yComp(i) (not zComp(i)) at :408-413 -- a latent
+ * reference quirk, restated as written.                                 */
+void oracle_pse_double_dot_sphere(int64_t n, const double *x, const double *y, const double *z,
+                                  const double *u, const double *v, const double *w,
+                                  const double *area, const int32_t *mask, double eps, double sphereRadius,
+                                  int64_t ibeg, int64_t iend, double *dd)
+{
+    for (int64_t i = ibeg; i < iend; ++i) {
+        double xi[3] = { x[i], y[i], z[i] };
+        double ux = 0, uy = 0, uz = 0, vx = 0, vy = 0, vz = 0, wx = 0, wy = 0, wz = 0;
+        for (int64_t j = 0; j < n; ++j) {
+            if (mask[j]) {
+                double xj[3] = { x[j], y[j], z[j] };
+                double kIn = SphereDistance(xi, xj, sphereRadius) / eps;
+                double kOut = bivariateFirstDerivativeKernel8(kIn) / (eps * eps);
+                ux = ux + (u[j] + u[i]) * (xi[0] - xj[0]) / eps * kOut * area[j];
+                uy = uy + (u[j] + u[i]) * (xi[1] - xj[1]) / eps * kOut * area[j];
+                uz = uz + (u[j] + u[i]) * (xi[2] - xj[2]) / eps * kOut * area[j];
+                vx = vx + (v[j] + v[i]) * (xi[0] - xj[0]) / eps * kOut * area[j];
+                vy = vy + (v[j] + v[i]) * (xi[1] - xj[1]) / eps * kOut * area[j];
+                vz = vz + (v[j] + v[i]) * (xi[2] - xj[2]) / eps * kOut * area[j];
+                wx = wx + (w[j] + v[i]) * (xi[0] - xj[0]) / eps * kOut * area[j];
+                wy = wy + (w[j] + v[i]) * (xi[1] - xj[1]) / eps * kOut * area[j];
+                wz = wz + (w[j] + v[i]) * (xi[2] - xj[2]) / eps * kOut * area[j];
+            }
+        }
+        dd[i] = (ux * ux + vy * vy + wz * wz + 2.0 * (uy * vx + uz * wx + vz * wy)) / (eps * eps);
+    }
+}
+
+/* src/PSEDirectSum.f90:537-579  PSESphereDivergenceAtParticles          */
+void oracle_pse_divergence_sphere(int64_t n, const double *x, const double *y, const double *z,
+                                  const double *u, const double *v, const double *w,
+                                  const double *area, const int32_t *mask, double eps, double sphereRadius,
+                                  int64_t ibeg, int64_t iend, double *div)
+{
+    double denom = eps * eps * eps;
+    for (int64_t i = ibeg; i < iend; ++i) {
+        double xi[3] = { x[i], y[i], z[i] };
+        div[i] = 0.0;
+        for (int64_t j = 0; j < n; ++j) {
+            if (mask[j]) {
+                double xj[3] = { x[j], y[j], z[j] };
+                double kIn = SphereDistance(xj, xi, sphereRadius) / eps;
+                double g[3], pg[3];
+                g[0] = (xi[0] - xj[0]) * bivariateFirstDerivativeKernel8(kIn) / denom;
+                g[1] = (xi[1] - xj[1]) * bivariateFirstDerivativeKernel8(kIn) / denom;
+                g[2] = (xi[2] - xj[2]) * bivariateFirstDerivativeKernel8(kIn) / denom;
+                sphere_project(xi, g, pg);
+                div[i] = div[i] + (pg[0] * (u[j] + u[i]) + pg[1] * (v[j] + v[i]) + pg[2] * (w[j] + w[i])) * area[j];
+            }
+        }
+    }
+    for (int64_t i = ibeg; i < iend; ++i) div[i] = (1.0 / eps) * div[i];
+}

@@ -46,6 +46,75 @@ def test_pse_laplacian_reference_thresholds(oracle, get_mesh):
     assert l2 > 0.99 * th["particlesL2HarmLap_rank0_max"]
 
 
+def _latlon_grid(n_lat, n_lon):
+    """tests/SpherePSEConvTest.f90:155-172 (radius 1)."""
+    dlam = 360.0 / n_lon
+    d2r = PI / 180.0
+    lats = -0.5 * PI + np.arange(n_lat) * dlam * d2r
+    lons = np.arange(n_lon) * dlam * d2r
+    lo, la = np.meshgrid(lons, lats)
+
+    class Grid:
+        x = (np.cos(lo) * np.cos(la)).ravel()
+        y = (np.sin(lo) * np.cos(la)).ravel()
+        z = np.sin(la).ravel()
+    return Grid
+
+
+def test_pse_interpolation_reference_thresholds(oracle, get_mesh):
+    """PSESphereInterpolateScalar (PSEDirectSum.f90:151-168) against the interpolation
+    bounds of SpherePSEConvTest.f90:379-385: at the particles (:250-251, :292, :310) and on
+    the 181 x 360 lat-lon grid (:196-197, :344)."""
+    th = json.load(open(os.path.join(HERE, "golden", "reference_thresholds.json")))
+    m = get_mesh(th["mesh"]["seed"], th["mesh"]["init_nest"])
+    eps = m.max_edge_length ** th["mesh"]["pse_power"]
+    harm = problems.spherical_harmonic54(m)
+    act = m.is_active != 0
+    hi = oracle.pse_interpolate(m.x, m.y, m.z, harm, m.area, m.is_active, eps, m.x, m.y, m.z)
+    err = np.abs(hi - harm)
+    linf = err.max() / np.abs(harm).max()
+    assert 0.99 * th["particlesLinfHarm_max"] < linf <= th["particlesLinfHarm_max"]
+    s, e, _ = oracle.load_balance(m.n, th["mesh"]["np"])
+    sl = slice(int(s[0]) - 1, int(e[0]))
+    a = act[sl]
+    l2 = np.sum(err[sl][a] ** 2 * m.area[sl][a]) / np.sum(harm[sl][a] ** 2 * m.area[sl][a])
+    assert 0.99 * th["particlesL2Harm_rank0_max"] < l2 <= th["particlesL2Harm_rank0_max"]
+    g = _latlon_grid(th["grid"]["nLat"], th["grid"]["nLon"])
+    hd = problems.spherical_harmonic54(g)
+    gi = oracle.pse_interpolate(m.x, m.y, m.z, harm, m.area, m.is_active, eps, g.x, g.y, g.z)
+    unif = np.abs(gi - hd).max() / np.abs(hd).max()
+    assert 0.99 * th["unifLinfHarm_max"] < unif <= th["unifLinfHarm_max"]
+    ci = oracle.pse_interpolate(m.x, m.y, m.z, np.full(m.n, 2.0), m.area, m.is_active, eps, m.x, m.y, m.z)
+    assert np.abs(ci - 2.0).max() / 2.0 < 2e-2           # constants reproduced to ~1 % at L3 (logged only, :290)
+
+
+def test_pse_operators_on_smooth_fields(oracle, get_mesh):
+    """Gradient / divergence / second partials / double dot restatements against analytic
+    derivatives (consistency of sign, projection and eps scaling; O(eps^8 + (h/eps)^p) error)."""
+    q = get_mesh(M.QUAD_RECT_SEED, 5, 1.0)
+    eps = q.max_edge_length ** 0.5
+    inner = (np.abs(q.x) < 0.45) & (np.abs(q.y) < 0.45)       # away from the free boundary
+    f = np.sin(2.0 * q.x) * np.cos(q.y)
+    gx, gy = oracle.pse_gradient_plane(q.x, q.y, f, q.area, q.is_active, eps)
+    ex, ey = 2.0 * np.cos(2.0 * q.x) * np.cos(q.y), -np.sin(2.0 * q.x) * np.sin(q.y)
+    assert np.abs(gx - ex)[inner].max() < 2e-2 and np.abs(gy - ey)[inner].max() < 2e-2
+    dxx, dxy, dyy = oracle.pse_second_partials_plane(q.x, q.y, ex, ey, q.area, q.is_active, eps)
+    assert np.abs(dxx + 4.0 * f)[inner].max() < 5e-2 and np.abs(dyy + f)[inner].max() < 5e-2
+    assert np.abs(dxy + 2.0 * np.cos(2.0 * q.x) * np.sin(q.y))[inner].max() < 5e-2
+    u, v = q.y ** 2, q.x * q.y                               # u_x = 0, u_y = 2y, v_x = y, v_y = x
+    dd = oracle.pse_double_dot_plane(q.x, q.y, u, v, q.area, q.is_active, eps)
+    assert np.abs(dd - (4.0 * q.y ** 2 + q.x ** 2))[inner].max() < 5e-2
+    m = get_mesh(M.ICOS_TRI_SPHERE_SEED, 4)
+    eps = m.max_edge_length ** 0.4      # at L4 the O(h/eps) quadrature error needs a wide kernel
+    g3 = oracle.pse_gradient_sphere(m.x, m.y, m.z, m.z, m.area, m.is_active, eps)      # grad z = e_z - z x
+    ez = [-m.z * m.x, -m.z * m.y, 1.0 - m.z * m.z]
+    assert max(np.abs(a - b).max() for a, b in zip(g3, ez)) < 5e-2
+    div = oracle.pse_divergence_sphere(m.x, m.y, m.z, *ez, m.area, m.is_active, eps)   # div grad z = -2 z
+    assert np.abs(div + 2.0 * m.z).max() < 5e-2
+    rot = oracle.pse_divergence_sphere(m.x, m.y, m.z, -m.y, m.x, 0 * m.x, m.area, m.is_active, eps)
+    assert np.abs(rot).max() < 5e-2                                                   # solid-body rotation is divergence free
+
+
 def test_pse_kernel_values(oracle):
     """bivariateLaplacianKernel8 (PSEDirectSum.f90:622-627) closed form."""
     k8 = oracle.get().oracle_pse_laplacian_kernel8

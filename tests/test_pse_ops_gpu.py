@@ -1,0 +1,73 @@
+"""GPU parity for the remaining PSE operators: interpolation, gradient,
+second partials, double dot product, divergence -- through the C ABI against the oracle."""
+import json
+import os
+
+import numpy as np
+import pytest
+
+from lpm_v2_b200 import mesh as M, problems
+from conftest import relerr
+from test_oracle_golden import _latlon_grid
+
+pytestmark = pytest.mark.gpu
+HERE = os.path.dirname(os.path.abspath(__file__))
+TOL = 1e-12
+
+
+@pytest.mark.parametrize("L,power", [(3, 0.6), (5, 0.75), (5, 1.4)])
+def test_sphere_operators(gpu, oracle, get_mesh, L, power):
+    m = get_mesh(M.ICOS_TRI_SPHERE_SEED, L)
+    eps = m.max_edge_length ** power          # 1.4: the far-field cut-off is active
+    f = problems.spherical_harmonic54(m)
+    u, v, w = -m.y + 0.3 * m.z * m.x, m.x * m.x, 0.5 * m.y - m.z
+    args = (m.x, m.y, m.z)
+    got = gpu.pse_gradient_sphere(*args, f, m.area, m.is_active, eps)
+    want = oracle.pse_gradient_sphere(*args, f, m.area, m.is_active, eps)
+    scale = max(np.abs(a).max() for a in want)
+    assert max(np.abs(a - b).max() for a, b in zip(got, want)) <= TOL * scale
+    assert relerr(gpu.pse_divergence_sphere(*args, u, v, w, m.area, m.is_active, eps),
+                  oracle.pse_divergence_sphere(*args, u, v, w, m.area, m.is_active, eps)) <= TOL
+    assert relerr(gpu.pse_double_dot_sphere(*args, u, v, w, m.area, m.is_active, eps),
+                  oracle.pse_double_dot_sphere(*args, u, v, w, m.area, m.is_active, eps)) <= TOL
+    rng = np.random.default_rng(L)
+    t = rng.normal(size=(3, 777))
+    t /= np.linalg.norm(t, axis=0)
+    assert relerr(gpu.pse_interpolate_sphere(*args, f, m.area, m.is_active, eps, t[0], t[1], t[2]),
+                  oracle.pse_interpolate(*args, f, m.area, m.is_active, eps, t[0], t[1], t[2])) <= TOL
+
+
+def test_sphere_interpolation_reference_thresholds_on_gpu(gpu, oracle, get_mesh):
+    """The reference's interpolation bounds (SpherePSEConvTest.f90:379-385) on GPU output:
+    1922 particle targets and the 181 x 360 lat-lon grid (65160 separate targets)."""
+    th = json.load(open(os.path.join(HERE, "golden", "reference_thresholds.json")))
+    m = get_mesh(M.ICOS_TRI_SPHERE_SEED, 3)
+    eps = m.max_edge_length ** th["mesh"]["pse_power"]
+    harm = problems.spherical_harmonic54(m)
+    hi = gpu.pse_interpolate_sphere(m.x, m.y, m.z, harm, m.area, m.is_active, eps, m.x, m.y, m.z)
+    assert np.abs(hi - harm).max() / np.abs(harm).max() <= th["particlesLinfHarm_max"]
+    g = _latlon_grid(th["grid"]["nLat"], th["grid"]["nLon"])
+    hd = problems.spherical_harmonic54(g)
+    gi = gpu.pse_interpolate_sphere(m.x, m.y, m.z, harm, m.area, m.is_active, eps, g.x, g.y, g.z)
+    assert np.abs(gi - hd).max() / np.abs(hd).max() <= th["unifLinfHarm_max"]
+    assert relerr(gi, oracle.pse_interpolate(m.x, m.y, m.z, harm, m.area, m.is_active, eps, g.x, g.y, g.z)) <= TOL
+
+
+@pytest.mark.parametrize("L,power", [(3, 0.5), (5, 0.75), (5, 1.3)])
+def test_plane_operators(gpu, oracle, get_mesh, L, power):
+    q = get_mesh(M.QUAD_RECT_SEED, L, 2.0)
+    eps = q.max_edge_length ** power
+    f = np.sin(1.3 * q.x) * np.cos(0.7 * q.y) + 0.1 * q.x * q.y
+    got = gpu.pse_gradient_plane(q.x, q.y, f, q.area, q.is_active, eps)
+    want = oracle.pse_gradient_plane(q.x, q.y, f, q.area, q.is_active, eps)
+    assert max(relerr(a, b) for a, b in zip(got, want)) <= TOL
+    got2 = gpu.pse_second_partials_plane(q.x, q.y, want[0], want[1], q.area, q.is_active, eps)
+    want2 = oracle.pse_second_partials_plane(q.x, q.y, want[0], want[1], q.area, q.is_active, eps)
+    assert max(relerr(a, b) for a, b in zip(got2, want2)) <= TOL
+    u, v = q.y ** 2 - q.x, q.x * q.y
+    assert relerr(gpu.pse_double_dot_plane(q.x, q.y, u, v, q.area, q.is_active, eps),
+                  oracle.pse_double_dot_plane(q.x, q.y, u, v, q.area, q.is_active, eps)) <= TOL
+    rng = np.random.default_rng(L)
+    tx, ty = rng.uniform(-2, 2, 501), rng.uniform(-2, 2, 501)
+    assert relerr(gpu.pse_interpolate_plane(q.x, q.y, f, q.area, q.is_active, eps, tx, ty),
+                  oracle.pse_interpolate(q.x, q.y, None, f, q.area, q.is_active, eps, tx, ty)) <= TOL
