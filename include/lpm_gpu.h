@@ -166,6 +166,14 @@ int lpm_pse_divergence_sphere(int64_t n, const double* x, const double* y, const
                               const double* u, const double* v, const double* w, const double* area,
                               const int32_t* mask, double eps, double sphere_radius, double* div);
 
+/* SWEPlaneRHSIntegrals, src/SWEPlaneSolver.f90:457-560: velocity from vorticity and divergence,
+ * the double dot product of the velocity gradient and the PSE Laplacian of the fluid surface in
+ * one pass.  surf(j) = h(j) + topoFn(x(j), y(j)), evaluated by the caller (O(N)). */
+int lpm_swe_plane_rhs_integrals(int64_t n, const double* x, const double* y, const double* vort,
+                                const double* div, const double* surf, const double* area,
+                                const int32_t* mask, double pse_eps,
+                                double* u, double* v, double* double_dot, double* lap_surf);
+
 /* -------------------------- direct sums, device API (one rank's slice) */
 
 int lpm_bve_velocity_dev(int64_t n, const double* x, const double* y, const double* z,

@@ -257,3 +257,13 @@ def pse_divergence_sphere(x, y, z, u, v, w, area, mask, eps, sphere_radius=1.0):
     check(lib.lpm_pse_divergence_sphere(x.size, _pd(x), _pd(y), _pd(z), _pd(u), _pd(v), _pd(w), _pd(area), _mi(m),
                                         float(eps), float(sphere_radius), _pd(div)))
     return div
+
+
+def swe_plane_rhs_integrals(x, y, vort, div, surf, area, mask, pse_eps):
+    """SWEPlaneRHSIntegrals (src/SWEPlaneSolver.f90:457-560): returns u, v, doubleDot, lapSurf."""
+    x, y, vort, div, surf, area = map(_f64, (x, y, vort, div, surf, area))
+    m = _mask(mask)
+    o = [np.empty(x.size) for _ in range(4)]
+    check(lib.lpm_swe_plane_rhs_integrals(x.size, _pd(x), _pd(y), _pd(vort), _pd(div), _pd(surf), _pd(area), _mi(m),
+                                          float(pse_eps), *[_pd(a) for a in o]))
+    return o

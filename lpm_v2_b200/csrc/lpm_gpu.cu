@@ -341,9 +341,11 @@ int run_host(const Args& host, double* const* out_host)
                 a.tgt[k] = dev.ws.staging[12 + k].as<double>();
             }
             double* out[4] = {nullptr, nullptr, nullptr, nullptr};
-            for (int k = 0; k < Op::NOUT; ++k) {
-                LPM_TRY(dev.ws.staging[9 + k].reserve(ntb));
-                out[k] = dev.ws.staging[9 + k].as<double>();
+            static_assert(Op::NOUT <= 4 && Op::NIN <= 8, "staging layout");
+            for (int k = 0; k < Op::NOUT; ++k) {      // outputs: staging 9-11, a 4th shares slot 15
+                DevBuf& ob = dev.ws.staging[k < 3 ? 9 + k : 15];
+                LPM_TRY(ob.reserve(ntb));
+                out[k] = ob.as<double>();
             }
             LPM_TRY(build_mask_plan(dev.stream, n, a.mask, plans[g]));
             LPM_TRY(Op::pack(dev, dev.stream, plans[g], a));
@@ -586,6 +588,18 @@ extern "C" int lpm_pse_divergence_sphere(int64_t n, const double* x, const doubl
     Args a{n, {x, y, z, u, v, w, area}, mask, {eps, sphere_radius}};
     double* o[1] = {div};
     return run_host<OpPseDivSphere>(a, o);
+}
+
+// ---- planar shallow water: SWEPlaneRHSIntegrals (src/SWEPlaneSolver.f90:457-560) ----
+extern "C" int lpm_swe_plane_rhs_integrals(int64_t n, const double* x, const double* y, const double* vort,
+                                           const double* div, const double* surf, const double* area,
+                                           const int32_t* mask, double pse_eps, double* u, double* v,
+                                           double* double_dot, double* lap_surf)
+{
+    LPM_TRY(check_eps(pse_eps, 1.0));
+    Args a{n, {x, y, vort, div, surf, area}, mask, {pse_eps}};
+    double* o[4] = {u, v, double_dot, lap_surf};
+    return run_host<OpSweRhsPlane>(a, o);
 }
 
 // ============================================================== resident solvers

@@ -5,6 +5,7 @@
 #pragma once
 #include "runtime.cuh"
 #include "pairs_pse.cuh"
+#include "pairs_swe.cuh"
 
 namespace lpm {
 
@@ -351,6 +352,29 @@ struct OpPseDivSphere {
         K::Params p{};
         p.x = a.in[0]; p.y = a.in[1]; p.z = a.in[2]; p.u = a.in[3]; p.v = a.in[4]; p.w = a.in[5];
         p.c = pse_sphere_consts(a.sc[0], a.sc[1], 1.0 / a.sc[0]);
+        return p;
+    }
+    static int variant() { return 0; }
+};
+
+// ---- planar SWE RHS integrals: in = x y vort div surf area; sc = eps; out = u v doubleDot lapSurf
+struct OpSweRhsPlane {
+    using K = SweRhsPlane;
+    static constexpr int NIN = 6, NOUT = 4, NTGT = 0;
+    static int pack(Device& dev, cudaStream_t st, const MaskPlan& mp, const Args& a)
+    {
+        int32_t pad;
+        LPM_TRY(reserve_sources<K>(dev, mp, &pad));
+        pack_swe_plane<<<pack_grid(pad), 256, 0, st>>>(mp.nsrc, pad, mp.active.as<int32_t>(), a.in[0], a.in[1], a.in[2],
+                                                       a.in[3], a.in[4], a.in[5], a.sc[0], dev.ws.sources.as<double>());
+        count_launch();
+        return LPM_OK;
+    }
+    static K::Params params(const Args& a)
+    {
+        K::Params p{};
+        p.x = a.in[0]; p.y = a.in[1]; p.surf = a.in[4];
+        p.inv_eps2 = 1.0 / (a.sc[0] * a.sc[0]);
         return p;
     }
     static int variant() { return 0; }

@@ -334,3 +334,15 @@ def pse_divergence_sphere(x, y, z, u, v, w, area, mask, eps, sphere_radius=1.0):
     _L().oracle_pse_divergence_sphere(x.size, _p(x), _p(y), _p(z), _p(u), _p(v), _p(w), _p(area), m.ctypes.data_as(_i32),
                                       eps, sphere_radius, 0, x.size, _p(div))
     return div
+
+
+def swe_plane_rhs(x, y, vort, div, surf, area, mask, pse_eps):
+    x, y, vort, div, surf, area = map(_f, (x, y, vort, div, surf, area))
+    m = _m(mask)
+    lib = get()
+    lib.oracle_swe_plane_rhs.argtypes = [_n, _d, _d, _d, _d, _d, _d, _i32, _dbl, _n, _n, _d, _d, _d, _d]
+    lib.oracle_swe_plane_rhs.restype = None
+    o = [np.zeros(x.size) for _ in range(4)]
+    lib.oracle_swe_plane_rhs(x.size, _p(x), _p(y), _p(vort), _p(div), _p(surf), _p(area), m.ctypes.data_as(_i32),
+                             pse_eps, 0, x.size, *[_p(a) for a in o])
+    return o

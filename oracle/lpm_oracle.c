@@ -796,3 +796,42 @@ void oracle_pse_divergence_sphere(int64_t n, const double *x, const double *y, c
     }
     for (int64_t i = ibeg; i < iend; ++i) div[i] = (1.0 / eps) * div[i];
 }
+
+/* ================================================================== */
+/* src/SWEPlaneSolver.f90:457-560  SWEPlaneRHSIntegrals: velocity from the
+ * vorticity and divergence, the four velocity-gradient sums behind the
+ * double dot product, and the PSE Laplacian of the fluid surface, fused
+ * in one pair loop.  surf(j) = h(j) + topoFn(x(j), y(j)) (the reference
+ * evaluates the topography function inside the loop, :483,:490).       */
+void oracle_swe_plane_rhs(int64_t n, const double *x, const double *y, const double *vort, const double *div,
+                          const double *surf, const double *area, const int32_t *mask, double pseEps,
+                          int64_t ibeg, int64_t iend, double *u, double *v, double *doubleDot, double *lapSurf)
+{
+    for (int64_t i = ibeg; i < iend; ++i) {
+        u[i] = 0.0; v[i] = 0.0; doubleDot[i] = 0.0; lapSurf[i] = 0.0;
+        double surfHeightI = surf[i];
+        double ux = 0.0, uy = 0.0, vx = 0.0, vy = 0.0;
+        for (int64_t j = 0; j < n; ++j) {
+            if (mask[j]) {
+                double surfHeightJ = surf[j];
+                double sqdist = (x[i] - x[j]) * (x[i] - x[j]) + (y[i] - y[j]) * (y[i] - y[j]);
+                double pseKin = sqrt(sqdist) / pseEps;
+                double lapKernel = bivariateLaplacianKernel8(pseKin) / (pseEps * pseEps);
+                lapSurf[i] = lapSurf[i] + lapKernel * (surfHeightJ - surfHeightI) * area[j];
+                if (i == j) continue;
+                double denom = 2.0 * PI * sqdist;
+                double denom2 = PI * sqdist * sqdist;
+                double rotStrength = vort[j] * area[j] / denom;
+                double potStrength = div[j] * area[j] / denom;
+                u[i] = u[i] - (y[i] - y[j]) * rotStrength + (x[i] - x[j]) * potStrength;
+                v[i] = v[i] + (x[i] - x[j]) * rotStrength + (y[i] - y[j]) * potStrength;
+                ux = ux + potStrength - ((x[i] - x[j]) * ((x[i] - x[j]) * div[j] - (y[i] - y[j]) * vort[j])) * area[j] / denom2;
+                uy = uy - rotStrength - ((y[i] - y[j]) * ((x[i] - x[j]) * div[j] - (y[i] - y[j]) * vort[j])) * area[j] / denom2;
+                vx = vx + rotStrength - ((x[i] - x[j]) * ((y[i] - y[j]) * div[j] + (x[i] - x[j]) * vort[j])) * area[j] / denom2;
+                vy = vy + potStrength - ((y[i] - y[j]) * ((y[i] - y[j]) * div[j] + (x[i] - x[j]) * vort[j])) * area[j] / denom2;
+            }
+        }
+        lapSurf[i] = lapSurf[i] / (pseEps * pseEps);
+        doubleDot[i] = ux * ux + 2.0 * uy * vx + vy * vy;
+    }
+}
