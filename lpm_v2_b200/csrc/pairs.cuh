@@ -89,13 +89,32 @@ struct NoSharedTable {
     __device__ static __forceinline__ void init_shared(double*, int, int) {}
 };
 
-// ln(d) for finite normal d > 0 from a 128-entry table in shared memory ({1/c_k, ln c_k},
-// c_k = 1 + (k + 1/2)/128) and a degree-6 polynomial for ln(1 + r), |r| <= 2^-8:
-// 9 FP64-pipe ops and one LDS.128 instead of the ~28 FP64 ops + branches of log().
+// ln(d) for finite normal d > 0: d = 2^e m, bin k = top 7 mantissa bits of m, q_k ~ 1/c_k from
+// MUFU.RCP64H (c_k = 1 + (k + 1/2)/128), r = m q_k - 1 with |r| <= 2^-8, then
+//   ln d = e ln2 - ln q_k + ln(1 + r)
+// with -ln q_k from a 128-entry table in shared memory and a degree-6 polynomial for ln(1 + r):
+// 9 FP64-pipe ops, one MUFU and one LDS.64 instead of the ~28 FP64 ops + branches of log().
+// (An earlier version kept {1/c_k, ln c_k} pairs in the table; its LDS.128 with a different
+// index per lane was bank-conflict bound -- 59 cycles per pair-warp measured against 28 of FP64 work.)
 // Absolute error ~2e-16 + 1 ulp of the result.  Anything else (d <= 0, subnormal, inf,
 // NaN) takes the library log() so the reference's -inf / NaN behaviour is kept.
-constexpr int kLogTabDoubles = 256;
+constexpr int kLogTabDoubles = 128;
 __device__ double g_log_table[kLogTabDoubles];
+
+// The bin-centre reciprocal used by log_tab: q_k = MUFU.RCP64H(c_k), c_k = 1 + (k + 1/2)/128.
+// It has ~20 significant bits, so m q_k - 1 is exact to an FMA rounding and |.| <= 2^-8 + 2^-20.
+__device__ __forceinline__ double log_bin_rcp(int hi_of_m)
+{
+    const double c = __hiloint2double((hi_of_m & 0x000fe000) | 0x3ff01000, 0);
+    double q;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(q) : "d"(c));
+    return q;
+}
+__global__ void log_table_seed_kernel(double* q)      // q[k] for the host to turn into -ln q[k]
+{
+    const int k = threadIdx.x;
+    if (k < kLogTabDoubles) q[k] = log_bin_rcp(0x3ff00000 | (k << 13));
+}
 
 struct LogSharedTable {
     static constexpr int KS = kLogTabDoubles;
@@ -114,15 +133,14 @@ __device__ __forceinline__ double log_tab(double d, const double* tab)
     const int e = (hi >> 20) - 1023;
     const int k = (hi >> 13) & 0x7f;
     const double m = __hiloint2double((hi & 0x000fffff) | 0x3ff00000, lo);
-    const double2 t = *reinterpret_cast<const double2*>(tab + 2 * k);
-    const double r = fma(m, t.x, -1.0);
+    const double r = fma(m, log_bin_rcp(hi), -1.0);        // m / c_k - 1
     const double ed = __hiloint2double(0x43300000, e ^ 0x80000000) - 4503601774854144.0;   // (double)e
     double p = fma(r, -1.0 / 6.0, 0.2);
     p = fma(r, p, -0.25);
     p = fma(r, p, 1.0 / 3.0);
     p = fma(r, p, -0.5);
     p = fma(r, p, 1.0);
-    return fma(r, p, fma(ed, 0.693147180559945309417232121458, t.y));
+    return fma(r, p, fma(ed, 0.693147180559945309417232121458, tab[k]));   // e ln2 - ln q_k + ln(1 + r)
 }
 
 // Default group(): one source against the thread's T targets, one pair at a time.

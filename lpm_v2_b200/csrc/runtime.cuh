@@ -24,12 +24,18 @@ inline int init_device(Device& d, int id)
         return set_error(LPM_ERR_NO_DEVICE, "device %d (%s) is sm_%d%d; liblpmgpu is built for sm_100a only", id,
                          prop.name, prop.major, prop.minor);
     d.sm_count = prop.multiProcessorCount;
-    {   // table for log_tab(): {1/c_k, ln c_k}, c_k = 1 + (k + 1/2)/128, rounded from long double
+    {   // table for log_tab(): -ln q_k, q_k = MUFU.RCP64H(c_k) read back from the device and
+        // evaluated in long double on the host
+        double* dq = nullptr;
         double tab[kLogTabDoubles];
-        for (int k = 0; k < kLogTabDoubles / 2; ++k) {
-            long double c = 1.0L + ((long double)k + 0.5L) / 128.0L;
-            tab[2 * k] = (double)(1.0L / c);
-            tab[2 * k + 1] = (double)logl(c);
+        LPM_CUDA(cudaMalloc(&dq, sizeof(tab)));
+        log_table_seed_kernel<<<1, kLogTabDoubles>>>(dq);
+        LPM_CUDA(cudaMemcpy(tab, dq, sizeof(tab), cudaMemcpyDeviceToHost));
+        LPM_CUDA(cudaFree(dq));
+        for (int k = 0; k < kLogTabDoubles; ++k) {
+            if (!(tab[k] > 0.49 && tab[k] <= 1.0))
+                return set_error(LPM_ERR_CUDA, "log table seed %d out of range (%g)", k, tab[k]);
+            tab[k] = (double)(-logl((long double)tab[k]));
         }
         LPM_CUDA(cudaMemcpyToSymbol(g_log_table, tab, sizeof(tab)));
     }
