@@ -126,10 +126,15 @@ struct LogSharedTable {
 
 __device__ __noinline__ double log_slow_path(double d) { return log(d); }
 
+__device__ __forceinline__ bool log_needs_slow_path(double d)     // d <= 0, subnormal, inf or NaN
+{
+    return (unsigned)(__double2hiint(d) - 0x00100000) >= 0x7fe00000u;
+}
+
+// Branch-free fast path (the caller has excluded the special arguments).
 __device__ __forceinline__ double log_tab(double d, const double* tab)
 {
     const int hi = __double2hiint(d), lo = __double2loint(d);
-    if (__builtin_expect((unsigned)(hi - 0x00100000) >= 0x7fe00000u, 0)) return log_slow_path(d);
     const int e = (hi >> 20) - 1023;
     const int k = (hi >> 13) & 0x7f;
     const double m = __hiloint2double((hi & 0x000fffff) | 0x3ff00000, lo);
@@ -141,6 +146,24 @@ __device__ __forceinline__ double log_tab(double d, const double* tab)
     p = fma(r, p, -0.5);
     p = fma(r, p, 1.0);
     return fma(r, p, fma(ed, 0.693147180559945309417232121458, tab[k]));   // e ln2 - ln q_k + ln(1 + r)
+}
+
+// Logs of a thread's T arguments.  ONE branch per group: the fast block is straight-line
+// code whose T dependent chains interleave (a branch per argument serialised them -- the
+// first version ran at 59 cycles per pair-warp for 28 cycles of FP64 work).
+template <int T>
+__device__ __forceinline__ void log_group(const double (&d)[T], double (&l)[T], const double* tab)
+{
+    bool slow = false;
+#pragma unroll
+    for (int k = 0; k < T; ++k) slow |= log_needs_slow_path(d[k]);
+    if (__builtin_expect(slow, 0)) {
+#pragma unroll 1
+        for (int k = 0; k < T; ++k) l[k] = log_slow_path(d[k]);
+    } else {
+#pragma unroll
+        for (int k = 0; k < T; ++k) l[k] = log_tab(d[k], tab);
+    }
 }
 
 // Default group(): one source against the thread's T targets, one pair at a time.
@@ -253,19 +276,26 @@ struct BveStream : LogSharedTable {
     {
         return Tgt{p.x[i], p.y[i], p.z[i]};
     }
-    template <bool CHECK>
-    __device__ static __forceinline__ void pair(const Params& p, const Tgt& t, const double (&s)[NS],
-                                                double (&acc)[NA], bool skip, const double* ks)
+    template <int T, bool CHECK>
+    __device__ static __forceinline__ void group(const Params& p, const Tgt (&t)[T], const double (&s)[NS],
+                                                 double (&acc)[T][NA], int32_t j, const int32_t (&self)[T],
+                                                 const double* ks)
     {
-        double d = fma(-t.x, s[0], p.R2);
-        d = fma(-t.y, s[1], d);
-        d = fma(-t.z, s[2], d);
-        if (CHECK) d = skip ? 1.0 : d;      // log(1) = 0 removes the pair
-        double l = log_tab(d, ks);
-        acc[0] = fma(l, s[3], acc[0]);
-        acc[1] = fma(l, s[4], acc[1]);
+        double d[T], l[T];
+#pragma unroll
+        for (int k = 0; k < T; ++k) {
+            d[k] = fma(-t[k].x, s[0], p.R2);
+            d[k] = fma(-t[k].y, s[1], d[k]);
+            d[k] = fma(-t[k].z, s[2], d[k]);
+            if (CHECK) d[k] = (j == self[k]) ? 1.0 : d[k];      // log(1) = 0 removes the pair
+        }
+        log_group<T>(d, l, ks);
+#pragma unroll
+        for (int k = 0; k < T; ++k) {
+            acc[k][0] = fma(l[k], s[3], acc[k][0]);
+            acc[k][1] = fma(l[k], s[4], acc[k][1]);
+        }
     }
-    LPM_DEFAULT_GROUP()
     __device__ static __forceinline__ void finalize(const Params& p, const Tgt&, const double (&a)[NA], int64_t i)
     {
         p.out.store(0, i, a[0]);
@@ -366,16 +396,22 @@ struct PlaneStream : LogSharedTable {
     };
     struct Tgt { double x, y; };
     __device__ static __forceinline__ Tgt load_target(const Params& p, int64_t i) { return Tgt{p.x[i], p.y[i]}; }
-    template <bool CHECK>
-    __device__ static __forceinline__ void pair(const Params&, const Tgt& t, const double (&s)[NS],
-                                                double (&acc)[NA], bool skip, const double* ks)
+    template <int T, bool CHECK>
+    __device__ static __forceinline__ void group(const Params&, const Tgt (&t)[T], const double (&s)[NS],
+                                                 double (&acc)[T][NA], int32_t j, const int32_t (&self)[T],
+                                                 const double* ks)
     {
-        double dx = t.x - s[0], dy = t.y - s[1];
-        double r2 = fma(dx, dx, dy * dy);
-        if (CHECK) r2 = skip ? 1.0 : r2;
-        acc[0] = fma(log_tab(r2, ks), s[2], acc[0]);
+        double r2[T], l[T];
+#pragma unroll
+        for (int k = 0; k < T; ++k) {
+            double dx = t[k].x - s[0], dy = t[k].y - s[1];
+            r2[k] = fma(dx, dx, dy * dy);
+            if (CHECK) r2[k] = (j == self[k]) ? 1.0 : r2[k];
+        }
+        log_group<T>(r2, l, ks);
+#pragma unroll
+        for (int k = 0; k < T; ++k) acc[k][0] = fma(l[k], s[2], acc[k][0]);
     }
-    LPM_DEFAULT_GROUP()
     __device__ static __forceinline__ void finalize(const Params& p, const Tgt&, const double (&a)[NA], int64_t i)
     {
         p.out.store(0, i, a[0]);
@@ -449,19 +485,26 @@ struct BetaStream : LogSharedTable {
     using Params = BetaVel::Params;
     using Tgt = BetaVel::Tgt;
     __device__ static __forceinline__ Tgt load_target(const Params& p, int64_t i) { return BetaVel::load_target(p, i); }
-    template <bool CHECK>
-    __device__ static __forceinline__ void pair(const Params&, const Tgt& t, const double (&s)[NS],
-                                                double (&acc)[NA], bool skip, const double* ks)
+    template <int T, bool CHECK>
+    __device__ static __forceinline__ void group(const Params&, const Tgt (&t)[T], const double (&s)[NS],
+                                                 double (&acc)[T][NA], int32_t j, const int32_t (&self)[T],
+                                                 const double* ks)
     {
-        double S = fma(t.sh, s[1], -(t.ch * s[0]));
-        double sn = fma(t.sn, s[3], -(t.cs * s[2]));
-        double den = 2.0 * fma(S, S, sn * sn);
-        if (CHECK) den = skip ? 1.0 : den;
-        double l = log_tab(den, ks);
-        acc[0] = fma(l, s[4], acc[0]);
-        acc[1] = fma(l, s[5], acc[1]);
+        double den[T], l[T];
+#pragma unroll
+        for (int k = 0; k < T; ++k) {
+            double S = fma(t[k].sh, s[1], -(t[k].ch * s[0]));
+            double sn = fma(t[k].sn, s[3], -(t[k].cs * s[2]));
+            den[k] = 2.0 * fma(S, S, sn * sn);
+            if (CHECK) den[k] = (j == self[k]) ? 1.0 : den[k];
+        }
+        log_group<T>(den, l, ks);
+#pragma unroll
+        for (int k = 0; k < T; ++k) {
+            acc[k][0] = fma(l[k], s[4], acc[k][0]);
+            acc[k][1] = fma(l[k], s[5], acc[k][1]);
+        }
     }
-    LPM_DEFAULT_GROUP()
     __device__ static __forceinline__ void finalize(const Params& p, const Tgt&, const double (&a)[NA], int64_t i)
     {
         p.out.store(0, i, a[0]);

@@ -14,6 +14,9 @@ public :: LpmGpuInit, LpmGpuFinalize, LpmGpuCheck, MaskToC
 public :: lpm_bve_velocity, lpm_bve_stream, lpm_plane_velocity, lpm_plane_stream
 public :: lpm_betaplane_velocity, lpm_betaplane_stream
 public :: lpm_pse_laplacian_sphere, lpm_pse_laplacian_plane
+public :: lpm_pse_interpolate_sphere, lpm_pse_gradient_sphere, lpm_pse_divergence_sphere
+public :: lpm_pse_gradient_plane, lpm_pse_second_partials_plane, lpm_pse_double_dot_plane
+public :: lpm_swe_plane_rhs_integrals
 public :: lpm_gpu_pin, lpm_gpu_unpin
 public :: lpm_bve_solver_new, lpm_bve_solver_timestep, lpm_bve_solver_get_state, lpm_bve_solver_delete
 
@@ -123,6 +126,83 @@ interface
 		integer(c_int), intent(in) :: mask(*)
 		real(c_double), value :: eps
 		real(c_double), intent(out) :: lap(*)
+	end function
+
+	!> PSESphereInterpolateScalar (PSEDirectSum.f90:151-168) at m locations
+	integer(c_int) function lpm_pse_interpolate_sphere(n, x, y, z, f, area, mask, eps, sphere_radius, &
+			m, tx, ty, tz, fOut) bind(C, name="lpm_pse_interpolate_sphere")
+		import :: c_int, c_int64_t, c_double
+		integer(c_int64_t), value :: n, m
+		real(c_double), intent(in) :: x(*), y(*), z(*), f(*), area(*), tx(*), ty(*), tz(*)
+		integer(c_int), intent(in) :: mask(*)
+		real(c_double), value :: eps, sphere_radius
+		real(c_double), intent(out) :: fOut(*)
+	end function
+
+	!> PSESphereGradientAtParticles (PSEDirectSum.f90:221-267)
+	integer(c_int) function lpm_pse_gradient_sphere(n, x, y, z, f, area, mask, eps, sphere_radius, gx, gy, gz) &
+			bind(C, name="lpm_pse_gradient_sphere")
+		import :: c_int, c_int64_t, c_double
+		integer(c_int64_t), value :: n
+		real(c_double), intent(in) :: x(*), y(*), z(*), f(*), area(*)
+		integer(c_int), intent(in) :: mask(*)
+		real(c_double), value :: eps, sphere_radius
+		real(c_double), intent(out) :: gx(*), gy(*), gz(*)
+	end function
+
+	!> PSESphereDivergenceAtParticles (PSEDirectSum.f90:537-579)
+	integer(c_int) function lpm_pse_divergence_sphere(n, x, y, z, u, v, w, area, mask, eps, sphere_radius, div) &
+			bind(C, name="lpm_pse_divergence_sphere")
+		import :: c_int, c_int64_t, c_double
+		integer(c_int64_t), value :: n
+		real(c_double), intent(in) :: x(*), y(*), z(*), u(*), v(*), w(*), area(*)
+		integer(c_int), intent(in) :: mask(*)
+		real(c_double), value :: eps, sphere_radius
+		real(c_double), intent(out) :: div(*)
+	end function
+
+	!> PSEPlaneGradientAtParticles (PSEDirectSum.f90:180-218)
+	integer(c_int) function lpm_pse_gradient_plane(n, x, y, f, area, mask, eps, gx, gy) &
+			bind(C, name="lpm_pse_gradient_plane")
+		import :: c_int, c_int64_t, c_double
+		integer(c_int64_t), value :: n
+		real(c_double), intent(in) :: x(*), y(*), f(*), area(*)
+		integer(c_int), intent(in) :: mask(*)
+		real(c_double), value :: eps
+		real(c_double), intent(out) :: gx(*), gy(*)
+	end function
+
+	!> PSEPlaneSecondPartialsAtParticles (PSEDirectSum.f90:269-320)
+	integer(c_int) function lpm_pse_second_partials_plane(n, x, y, gx, gy, area, mask, eps, dxx, dxy, dyy) &
+			bind(C, name="lpm_pse_second_partials_plane")
+		import :: c_int, c_int64_t, c_double
+		integer(c_int64_t), value :: n
+		real(c_double), intent(in) :: x(*), y(*), gx(*), gy(*), area(*)
+		integer(c_int), intent(in) :: mask(*)
+		real(c_double), value :: eps
+		real(c_double), intent(out) :: dxx(*), dxy(*), dyy(*)
+	end function
+
+	!> PSEPlaneDoubleDotProductAtParticles (PSEDirectSum.f90:322-365)
+	integer(c_int) function lpm_pse_double_dot_plane(n, x, y, u, v, area, mask, eps, dd) &
+			bind(C, name="lpm_pse_double_dot_plane")
+		import :: c_int, c_int64_t, c_double
+		integer(c_int64_t), value :: n
+		real(c_double), intent(in) :: x(*), y(*), u(*), v(*), area(*)
+		integer(c_int), intent(in) :: mask(*)
+		real(c_double), value :: eps
+		real(c_double), intent(out) :: dd(*)
+	end function
+
+	!> SWEPlaneRHSIntegrals (SWEPlaneSolver.f90:457-560); surf = h + topoFn(x, y)
+	integer(c_int) function lpm_swe_plane_rhs_integrals(n, x, y, vort, div, surf, area, mask, pse_eps, &
+			u, v, doubleDot, lapSurf) bind(C, name="lpm_swe_plane_rhs_integrals")
+		import :: c_int, c_int64_t, c_double
+		integer(c_int64_t), value :: n
+		real(c_double), intent(in) :: x(*), y(*), vort(*), div(*), surf(*), area(*)
+		integer(c_int), intent(in) :: mask(*)
+		real(c_double), value :: pse_eps
+		real(c_double), intent(out) :: u(*), v(*), doubleDot(*), lapSurf(*)
 	end function
 
 	!> device-resident BVESolver: New / Timestep / Delete (SphereBVESolver.f90:112-168, 219-353)
