@@ -126,6 +126,10 @@ struct LogSharedTable {
 
 __device__ __noinline__ double log_slow_path(double d) { return log(d); }
 
+// -1/6, 1/5, -1/4, 1/3, -1/2 (ln(1+r) = r - r^2/2 + ... - r^6/6), ln 2, 2^52 + 2^31
+__constant__ double kLogC[7] = {-1.0 / 6.0, 0.2, -0.25, 1.0 / 3.0, -0.5, 0.693147180559945309417232121458,
+                                4503601774854144.0};
+
 __device__ __forceinline__ bool log_needs_slow_path(double d)     // d <= 0, subnormal, inf or NaN
 {
     return (unsigned)(__double2hiint(d) - 0x00100000) >= 0x7fe00000u;
@@ -139,13 +143,16 @@ __device__ __forceinline__ double log_tab(double d, const double* tab)
     const int k = (hi >> 13) & 0x7f;
     const double m = __hiloint2double((hi & 0x000fffff) | 0x3ff00000, lo);
     const double r = fma(m, log_bin_rcp(hi), -1.0);        // m / c_k - 1
-    const double ed = __hiloint2double(0x43300000, e ^ 0x80000000) - 4503601774854144.0;   // (double)e
-    double p = fma(r, -1.0 / 6.0, 0.2);
-    p = fma(r, p, -0.25);
-    p = fma(r, p, 1.0 / 3.0);
-    p = fma(r, p, -0.5);
+    // Constants come from the constant bank (operands of the DFMAs themselves): as immediates
+    // ptxas rebuilt each 64-bit literal with two moves per use, and the kernel was issue-bound
+    // (ncu: 35 instructions per pair, issue 68 %, FP64 pipe 55 %).
+    const double ed = __hiloint2double(0x43300000, e ^ 0x80000000) - kLogC[6];   // (double)e
+    double p = fma(r, kLogC[0], kLogC[1]);
+    p = fma(r, p, kLogC[2]);
+    p = fma(r, p, kLogC[3]);
+    p = fma(r, p, kLogC[4]);
     p = fma(r, p, 1.0);
-    return fma(r, p, fma(ed, 0.693147180559945309417232121458, tab[k]));   // e ln2 - ln q_k + ln(1 + r)
+    return fma(r, p, fma(ed, kLogC[5], tab[k]));   // e ln2 - ln q_k + ln(1 + r)
 }
 
 // Logs of a thread's T arguments.  ONE branch per group: the fast block is straight-line
