@@ -72,17 +72,23 @@ struct DevBuf {
 };
 
 // Scratch a direct sum needs on one device.  Reused across calls.
+// Result of scanning a mask (scan.cuh): scan[n+1], active[nsrc] and the active count.
+struct MaskPlan {
+    int64_t n = 0;
+    int32_t nsrc = 0;
+    DevBuf scan, active, blocksums;
+    void release() { scan.release(); active.release(); blocksums.release(); }
+};
+
 struct Workspace {
-    DevBuf scan;        // int32 [n+1]   exclusive prefix of mask
-    DevBuf blocksums;   // int32 [nblocks+1]
-    DevBuf active;      // int32 [nsrc]  compact -> particle index
+    MaskPlan plan;      // mask scan of the one-shot entry points (rebuilt per call, buffers reused)
     DevBuf sources;     // double [nsrc_pad * NS]
     DevBuf partial;     // double [nchunks * NA * ntgt]
     DevBuf staging[16]; // host API: device copies of the caller's arrays (0-7 in, 8 mask, 9-11 out, 12-14 targets)
     DevBuf reduce;      // small reduction scratch
     void release()
     {
-        scan.release(); blocksums.release(); active.release(); sources.release(); partial.release();
+        plan.release(); sources.release(); partial.release();
         reduce.release();
         for (auto& s : staging) s.release();
     }

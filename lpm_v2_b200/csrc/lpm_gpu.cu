@@ -290,7 +290,7 @@ int run_dev(const Args& a, int64_t ibeg, int64_t iend, double* const* out, void*
     if (ibeg < 0 || iend > a.n || ibeg > iend)
         return set_error(LPM_ERR_INVALID, "target range [%lld, %lld) outside [0, %lld)", (long long)ibeg, (long long)iend, (long long)a.n);
     cudaStream_t st = (cudaStream_t)stream;
-    static thread_local MaskPlan mp;    // rebuilt per call; buffers reused
+    MaskPlan& mp = dev->ws.plan;        // rebuilt per call; buffers reused
     LPM_TRY(build_mask_plan(st, a.n, a.mask, mp));
     LPM_TRY(Op::pack(*dev, st, mp, a));
     typename Op::K::Params prm = Op::params(a);
@@ -320,7 +320,6 @@ int run_host(const Args& host, double* const* out_host)
     const size_t ntb = (size_t)nt * sizeof(double);
     const int nparts = R.rank_mode ? R.world : (int)R.devs.size();
     int rc = LPM_OK;
-    static thread_local MaskPlan plans[kMaxRep];
     for (size_t g = 0; g < R.devs.size() && rc == LPM_OK; ++g) {
         Device& dev = R.devs[g];
         auto body = [&]() -> int {
@@ -347,13 +346,13 @@ int run_host(const Args& host, double* const* out_host)
                 LPM_TRY(ob.reserve(ntb));
                 out[k] = ob.as<double>();
             }
-            LPM_TRY(build_mask_plan(dev.stream, n, a.mask, plans[g]));
-            LPM_TRY(Op::pack(dev, dev.stream, plans[g], a));
+            LPM_TRY(build_mask_plan(dev.stream, n, a.mask, dev.ws.plan));
+            LPM_TRY(Op::pack(dev, dev.stream, dev.ws.plan, a));
             typename Op::K::Params prm = Op::params(a);
             set_outs(prm.out, out);
             int64_t b, e;
             load_balance0(nt, nparts, R.rank_mode ? R.rank : (int)g, &b, &e);
-            LPM_TRY(direct_sum<typename Op::K>(dev, dev.stream, plans[g], b, e, prm, Op::variant(), nt));
+            LPM_TRY(direct_sum<typename Op::K>(dev, dev.stream, dev.ws.plan, b, e, prm, Op::variant(), nt));
             if (R.rank_mode) {
                 LPM_TRY(allgather_slices(Op::NOUT, out, nt, dev.stream));
                 b = 0; e = nt;

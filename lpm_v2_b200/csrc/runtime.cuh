@@ -140,13 +140,6 @@ inline int allgather_slices(int ncomp, double* const* bufs, int64_t n, cudaStrea
 }
 
 // ---------------------------------------------------------------- mask plan
-struct MaskPlan {
-    int64_t n = 0;
-    int32_t nsrc = 0;
-    DevBuf scan, active, blocksums;
-    void release() { scan.release(); active.release(); blocksums.release(); }
-};
-
 // Scans the device mask; synchronises `st` once to read the active count.
 inline int build_mask_plan(cudaStream_t st, int64_t n, const int32_t* mask_dev, MaskPlan& mp)
 {

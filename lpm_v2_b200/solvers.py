@@ -222,3 +222,39 @@ class PSE:
 
     def PlaneLaplacianAtParticles(self, mesh, scalar_field):                        # :467-500
         return api.pse_laplacian_plane(mesh.x, mesh.y, scalar_field, mesh.area, mesh.is_active, self.eps)
+
+    # the remaining operators of the module
+    def SphereInterpolateScalar(self, mesh, scalar_field, tx, ty, tz, sphere_radius=1.0):   # :151-168, batched
+        return api.pse_interpolate_sphere(mesh.x, mesh.y, mesh.z, scalar_field, mesh.area, mesh.is_active, self.eps,
+                                          tx, ty, tz, sphere_radius)
+
+    def PlaneInterpolateScalar(self, mesh, scalar_field, tx, ty):                           # :128-149
+        return api.pse_interpolate_plane(mesh.x, mesh.y, scalar_field, mesh.area, mesh.is_active, self.eps, tx, ty)
+
+    def SphereGradientAtParticles(self, mesh, scalar_field, sphere_radius=1.0):             # :221-267
+        return api.pse_gradient_sphere(mesh.x, mesh.y, mesh.z, scalar_field, mesh.area, mesh.is_active, self.eps,
+                                       sphere_radius)
+
+    def PlaneGradientAtParticles(self, mesh, scalar_field):                                 # :180-218
+        return api.pse_gradient_plane(mesh.x, mesh.y, scalar_field, mesh.area, mesh.is_active, self.eps)
+
+    def PlaneSecondPartialsAtParticles(self, mesh, grad_x, grad_y):                         # :269-320
+        return api.pse_second_partials_plane(mesh.x, mesh.y, grad_x, grad_y, mesh.area, mesh.is_active, self.eps)
+
+    def PlaneDoubleDotProductAtParticles(self, mesh, u, v):                                 # :322-365
+        return api.pse_double_dot_plane(mesh.x, mesh.y, u, v, mesh.area, mesh.is_active, self.eps)
+
+    def SphereDoubleDotProductAtParticles(self, mesh, u, v, w, sphere_radius=1.0):          # :367-420
+        return api.pse_double_dot_sphere(mesh.x, mesh.y, mesh.z, u, v, w, mesh.area, mesh.is_active, self.eps,
+                                         sphere_radius)
+
+    def SphereDivergenceAtParticles(self, mesh, u, v, w, sphere_radius=1.0):                # :537-579
+        return api.pse_divergence_sphere(mesh.x, mesh.y, mesh.z, u, v, w, mesh.area, mesh.is_active, self.eps,
+                                         sphere_radius)
+
+
+def SWEPlaneRHSIntegrals(mesh, vort, div, h, topo_fn, pse_eps):
+    """src/SWEPlaneSolver.f90:457-560: returns u, v, doubleDot, lapSurf.  `topo_fn(x, y)` is the
+    bottom topography function the reference passes as a procedure argument."""
+    surf = np.asarray(h, dtype=np.float64) + topo_fn(mesh.x, mesh.y)
+    return api.swe_plane_rhs_integrals(mesh.x, mesh.y, vort, div, surf, mesh.area, mesh.is_active, pse_eps)
