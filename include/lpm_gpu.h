@@ -265,6 +265,9 @@ int64_t lpm_launch_count(int reset);
 int lpm_set_profiling(int enable);
 /* Tuning knob for benchmarks: select the BVE kernel variant. */
 int lpm_set_bve_variant(int variant);
+/* A/B switch for tests and benchmarks: 0 disables the tile culling of the compactly
+ * supported PSE kernels (every tile is then visited; results are bit-identical). Default 1. */
+int lpm_set_pse_culling(int enable);
 
 /* ------------------------------------------------------ mesh (host only) */
 

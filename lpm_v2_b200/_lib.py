@@ -99,6 +99,7 @@ PROTOTYPES = {
     "lpm_launch_count": (C.c_int64, [_int]),
     "lpm_set_profiling": (_int, [_int]),
     "lpm_set_bve_variant": (_int, [_int]),
+    "lpm_set_pse_culling": (_int, [_int]),
     # mesh
     "lpm_mesh_create": (_int, [_int, _int, _dbl, C.POINTER(_vp)]),
     "lpm_mesh_destroy": (None, [_vp]),

@@ -167,6 +167,10 @@ def set_bve_variant(v):
     check(lib.lpm_set_bve_variant(int(v)))
 
 
+def set_pse_culling(on):
+    check(lib.lpm_set_pse_culling(1 if on else 0))
+
+
 def last_kernel_ms():
     ms = C.c_double(0)
     check(lib.lpm_last_kernel_ms(C.byref(ms)))

@@ -84,12 +84,14 @@ struct Workspace {
     MaskPlan plan;      // mask scan of the one-shot entry points (rebuilt per call, buffers reused)
     DevBuf sources;     // double [nsrc_pad * NS]
     DevBuf partial;     // double [nchunks * NA * ntgt]
+    DevBuf bounds;      // double [nsrc_pad / kTile][4]: bounding ball per source tile (PSE tile culling)
     DevBuf staging[16]; // host API: device copies of the caller's arrays (0-7 in, 8 mask, 9-11 out, 12-14 targets)
     DevBuf reduce;      // small reduction scratch
+    DevBuf logwin;      // int32 [2]: max |coordinate| high word, window origin of the log table (pairs.cuh)
     void release()
     {
-        plan.release(); sources.release(); partial.release();
-        reduce.release();
+        plan.release(); sources.release(); partial.release(); bounds.release();
+        reduce.release(); logwin.release();
         for (auto& s : staging) s.release();
     }
 };
@@ -97,6 +99,7 @@ struct Workspace {
 struct Device {
     int id = -1;
     int sm_count = 0;
+    const double* logtab = nullptr;      // this device's g_log_full (pairs.cuh)
     cudaStream_t stream = nullptr;       // library-owned stream (host API, resident solvers)
     cudaEvent_t ev_done = nullptr;       // cross-device barrier (resident solvers)
     // profiling: one event pair per direct-sum main kernel since the last reset
@@ -123,6 +126,7 @@ struct Runtime {
     bool profiling = false;
     int64_t launches = 0;
     int bve_variant = 0;
+    bool pse_culling = true;             // A/B switch for the PSE tile culling (lpm_set_pse_culling)
     // NCCL (rank mode)
     void* nccl_lib = nullptr;
     void* comm = nullptr;

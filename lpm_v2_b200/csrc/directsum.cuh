@@ -29,6 +29,7 @@ namespace lpm {
 constexpr int kMaxChunks = 16;      // upper bound on source chunks per evaluation
 constexpr int kChunkMin = 8192;     // do not split the source list finer than this
 constexpr int kTile = 256;          // sources per shared-memory tile (all kernels)
+constexpr int kMaxNeedWords = 256;  // tile culling: bitmap words per CTA (<= 8192 tiles per chunk)
 
 struct DsGeom {
     int64_t tbeg, tend;     // target range, global particle indices [tbeg, tend)
@@ -40,6 +41,8 @@ struct DsGeom {
     int64_t ntgt;           // tend - tbeg
     int64_t tblk0;          // tbeg rounded down to a multiple of BLOCK*T
     int64_t nall;           // all particles (launch shape depends on this, not on the slice)
+    const double* bounds;   // tile culling: (cx, cy, cz, radius) per source tile, or nullptr
+    int32_t half_bin;       // 0x800 (half a log-table bin in the high word), passed at run time
 };
 
 // Source chunking depends on the number of active sources only.
@@ -99,6 +102,14 @@ __device__ __forceinline__ void tma_bulk_g2s(void* dst_smem, const void* src_gme
         : "memory");
 }
 
+// What ds_kernel hands to group(): the functor's per-CTA shared table and one integer of
+// context that init_shared() returns (the log kernels' window origin).
+struct SharedCtx {
+    const double* ks;
+    int32_t i0;
+    int32_t i1;     // = 0x800, but opaque to the compiler (see log_bin_rcp in pairs.cuh)
+};
+
 // ---- the kernel ---------------------------------------------------------------
 //
 // K (pair functor) provides:
@@ -107,9 +118,11 @@ __device__ __forceinline__ void tma_bulk_g2s(void* dst_smem, const void* src_gme
 //   Params            kernel-wide constants + target array pointers
 //   Tgt               per-target registers
 //   load_target(p,i)  -> Tgt
-//   group<T,CHECK>(p, tgt[T], s[NS], acc[T][NA], j, self[T], ks)   one source against the
+//   group<T,CHECK>(p, tgt[T], s[NS], acc[T][NA], j, self[T], sctx)   one source against the
 //                     thread's T targets; with CHECK, target t skips the pair when j == self[t]
-//   KS, init_shared(ks, tid, nthreads)   optional per-CTA shared table (KS doubles)
+//   KS, init_shared(ks, p, tid, nthreads) -> int   optional per-CTA shared table (KS doubles)
+//                     and one integer of context, handed to group() as SharedCtx
+//   CULL, cull_dist(p), tgt_point(tgt, xyz)   tile culling for compactly supported kernels
 //   finalize(p, tgt, acc, i)   writes the outputs of target i
 //
 // partial layout: [(chunk*NA + a) * ntgt + local_target]
@@ -120,7 +133,8 @@ ds_kernel(const typename K::Params prm, const DsGeom g, const double* __restrict
 {
     constexpr int NS = K::NS, NA = K::NA, TS = kTile;
     constexpr uint32_t kTileBytes = TS * NS * sizeof(double);
-    // dynamic shared memory: [2 tiles][BLOCK*T*NA running sums][2 mbarriers]
+    // dynamic shared memory: [2 tiles][BLOCK*T*NA running sums][K::KS table][2 mbarriers]
+    // and, for culling kernels, [kMaxNeedWords bitmap][4 * BLOCK/32 reduction scratch]
     extern __shared__ __align__(128) unsigned char smem_raw[];
     double(*tile)[TS * NS] = reinterpret_cast<double(*)[TS * NS]>(smem_raw);
     double* run = reinterpret_cast<double*>(smem_raw + 2 * kTileBytes);
@@ -171,25 +185,107 @@ ds_kernel(const typename K::Params prm, const DsGeom g, const double* __restrict
     if (s1 > g.nsrc_pad) s1 = g.nsrc_pad;
     const int ntiles = (s1 - s0) / TS;
 
-    K::init_shared(ks, tid, BLOCK);
+    const SharedCtx sctx{ks, K::init_shared(ks, prm, tid, BLOCK), g.half_bin};
     if (tid == 0) {
         mbar_init(&full[0], 1);
         mbar_init(&full[1], 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    __syncthreads();
-    if (tid == 0) {
+
+    // ---- tile culling (compactly supported kernels only) ------------------------------
+    // A tile is visited only if its bounding ball can come within K::cull_dist of the ball
+    // around this CTA's targets; `need` is a bitmap over the chunk's tiles.  Skipped pairs
+    // are exactly the ones the per-pair cut-off test rejects (pairs.cuh, kPseCut), so results
+    // are unchanged bit for bit.
+    uint32_t* need = reinterpret_cast<uint32_t*>(full + 2);
+    bool cull = false;
+    if constexpr (K::CULL) {
+        const double D = K::cull_dist(prm);
+        cull = g.bounds != nullptr && D < 1.0e300 && ntiles <= 32 * kMaxNeedWords;
+        if (cull) {
+            double* red = reinterpret_cast<double*>(need + kMaxNeedWords);       // [4][BLOCK/32]
+            const int lane = tid & 31, wid = tid >> 5;
+            constexpr int NW = BLOCK / 32;
+            double px[T], py[T], pz[T], sx = 0.0, sy = 0.0, sz = 0.0;
 #pragma unroll
-        for (int s = 0; s < 2; ++s)
-            if (s < ntiles) {
-                mbar_expect_tx(&full[s], kTileBytes);
-                tma_bulk_g2s(tile[s], src + (size_t)(s0 + s * TS) * NS, kTileBytes, &full[s]);
+            for (int t = 0; t < T; ++t) {
+                double p[3];
+                K::tgt_point(tg[t], p);
+                px[t] = p[0]; py[t] = p[1]; pz[t] = p[2];
+                sx += p[0]; sy += p[1]; sz += p[2];
             }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                sx += __shfl_xor_sync(0xffffffffu, sx, o);
+                sy += __shfl_xor_sync(0xffffffffu, sy, o);
+                sz += __shfl_xor_sync(0xffffffffu, sz, o);
+            }
+            if (lane == 0) { red[wid] = sx; red[NW + wid] = sy; red[2 * NW + wid] = sz; }
+            __syncthreads();
+            double cx = 0.0, cy = 0.0, cz = 0.0;
+#pragma unroll
+            for (int w = 0; w < NW; ++w) { cx += red[w]; cy += red[NW + w]; cz += red[2 * NW + w]; }
+            cx /= BLOCK * T; cy /= BLOCK * T; cz /= BLOCK * T;
+            double r2 = 0.0;
+#pragma unroll
+            for (int t = 0; t < T; ++t) {
+                const double dx = px[t] - cx, dy = py[t] - cy, dz = pz[t] - cz;
+                r2 = fmax(r2, dx * dx + dy * dy + dz * dz);
+            }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) r2 = fmax(r2, __shfl_xor_sync(0xffffffffu, r2, o));
+            if (lane == 0) red[3 * NW + wid] = r2;
+            __syncthreads();
+            if (wid == 0) {
+                double rt2 = 0.0;
+#pragma unroll
+                for (int w = 0; w < NW; ++w) rt2 = fmax(rt2, red[3 * NW + w]);
+                const double reach = (D + sqrt(rt2)) * (1.0 + 1.0e-6) + 1.0e-14;
+                const double* b = g.bounds + (size_t)(s0 / TS) * 4;
+                for (int base = 0; base < ntiles; base += 32) {
+                    const int k = base + lane;
+                    bool nd = false;
+                    if (k < ntiles) {
+                        const double dx = b[4 * k] - cx, dy = b[4 * k + 1] - cy, dz = b[4 * k + 2] - cz;
+                        const double lim = reach + b[4 * k + 3];       // an all-padding tile has radius -1e300
+                        nd = lim > 0.0 && dx * dx + dy * dy + dz * dz <= lim * lim;
+                    }
+                    const uint32_t m = __ballot_sync(0xffffffffu, nd);
+                    if (lane == 0) need[base >> 5] = m;
+                }
+            }
+        }
+    }
+    __syncthreads();
+
+    // next tile to visit at or after `from` (ntiles if none)
+    auto next_tile = [&](int from) -> int {
+        if (!cull) return from < ntiles ? from : ntiles;
+        while (from < ntiles) {
+            const uint32_t w = need[from >> 5] >> (from & 31);
+            if (w) return from + __ffs(w) - 1;
+            from = (from | 31) + 1;
+        }
+        return ntiles;
+    };
+
+    int cur = next_tile(0);
+    int nxt = next_tile(cur + 1);
+    if (tid == 0) {
+        if (cur < ntiles) {
+            mbar_expect_tx(&full[0], kTileBytes);
+            tma_bulk_g2s(tile[0], src + (size_t)(s0 + cur * TS) * NS, kTileBytes, &full[0]);
+        }
+        if (nxt < ntiles) {
+            mbar_expect_tx(&full[1], kTileBytes);
+            tma_bulk_g2s(tile[1], src + (size_t)(s0 + nxt * TS) * NS, kTileBytes, &full[1]);
+        }
     }
 
-    for (int k = 0; k < ntiles; ++k) {
-        const int st = k & 1;
-        mbar_wait(&full[st], (k >> 1) & 1);
+    for (int it = 0; cur < ntiles; ++it) {
+        const int k = cur;
+        const int st = it & 1;
+        mbar_wait(&full[st], (it >> 1) & 1);
         const double* sm = tile[st];
         const int32_t j0 = s0 + k * TS;
         const bool check = K::SKIP_SELF && (j0 < selfhi) && (j0 + TS > selflo);
@@ -203,7 +299,7 @@ ds_kernel(const typename K::Params prm, const DsGeom g, const double* __restrict
                     double2 v = p2[q];
                     s[2 * q] = v.x; s[2 * q + 1] = v.y;
                 }
-                K::template group<T, false>(prm, tg, s, acc, 0, self, ks);
+                K::template group<T, false>(prm, tg, s, acc, 0, self, sctx);
             }
         } else {
 #pragma unroll 1
@@ -215,7 +311,7 @@ ds_kernel(const typename K::Params prm, const DsGeom g, const double* __restrict
                     double2 v = p2[q];
                     s[2 * q] = v.x; s[2 * q + 1] = v.y;
                 }
-                K::template group<T, true>(prm, tg, s, acc, j0 + j, self, ks);
+                K::template group<T, true>(prm, tg, s, acc, j0 + j, self, sctx);
             }
         }
         // Two-level summation: the tile's sum joins the running sum (kept in shared memory,
@@ -230,10 +326,13 @@ ds_kernel(const typename K::Params prm, const DsGeom g, const double* __restrict
                 acc[t][a] = 0.0;
             }
         __syncthreads();    // everyone is done with tile[st]
-        if (tid == 0 && k + 2 < ntiles) {
+        const int after = next_tile(nxt + 1);       // refill this stage with the tile after `nxt`
+        if (tid == 0 && nxt < ntiles && after < ntiles) {
             mbar_expect_tx(&full[st], kTileBytes);
-            tma_bulk_g2s(tile[st], src + (size_t)(s0 + (k + 2) * TS) * NS, kTileBytes, &full[st]);
+            tma_bulk_g2s(tile[st], src + (size_t)(s0 + after * TS) * NS, kTileBytes, &full[st]);
         }
+        cur = nxt;
+        nxt = (nxt < ntiles) ? after : ntiles;
     }
 
 #pragma unroll
@@ -260,7 +359,8 @@ template <class K, int T, int BLOCK>
 constexpr size_t ds_smem_bytes()
 {
     return 2 * size_t(kTile) * K::NS * sizeof(double) + sizeof(double) * (BLOCK * T * K::NA + K::KS) +
-           2 * sizeof(uint64_t);
+           2 * sizeof(uint64_t) +
+           (K::CULL ? kMaxNeedWords * sizeof(uint32_t) + 4 * (BLOCK / 32) * sizeof(double) : 0);
 }
 
 // Adds the chunk partials in chunk order and writes the outputs.

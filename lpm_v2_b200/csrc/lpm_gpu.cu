@@ -173,6 +173,7 @@ extern "C" int lpm_load_balance(int64_t n_items, int nprocs, int64_t* index_star
 
 extern "C" int lpm_set_profiling(int enable) { rt().profiling = enable != 0; return LPM_OK; }
 extern "C" int lpm_set_bve_variant(int variant) { rt().bve_variant = variant; return LPM_OK; }
+extern "C" int lpm_set_pse_culling(int enable) { rt().pse_culling = enable != 0; return LPM_OK; }
 extern "C" int64_t lpm_launch_count(int reset)
 {
     int64_t v = rt().launches;

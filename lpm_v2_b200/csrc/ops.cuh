@@ -61,7 +61,7 @@ struct OpBveStream {
         pack_bve_stream<<<pack_grid(pad), 256, 0, st>>>(mp.nsrc, pad, mp.active.as<int32_t>(), a.in[0], a.in[1], a.in[2],
                                                         a.in[3], a.in[4], a.in[5], a.sc[0], dev.ws.sources.as<double>());
         count_launch();
-        return LPM_OK;
+        return log_window<K>(dev, st, 0, 2.0 * a.sc[0] * a.sc[0], 0, nullptr, nullptr);     // d <= 2 R^2
     }
     static K::Params params(const Args& a)
     {
@@ -86,6 +86,7 @@ struct OpPlane {
         pack_plane<<<pack_grid(pad), 256, 0, st>>>(mp.nsrc, pad, mp.active.as<int32_t>(), a.in[0], a.in[1], a.in[2],
                                                    a.in[3], inv_norm, dev.ws.sources.as<double>());
         count_launch();
+        if constexpr (STREAM) return log_window<K>(dev, st, 1, 0.0, a.n, a.in[0], a.in[1]);
         return LPM_OK;
     }
     static typename K::Params params(const Args& a)
@@ -130,7 +131,7 @@ struct OpBetaStream {
         pack_beta<<<pack_grid(pad), 256, 0, st>>>(mp.nsrc, pad, mp.active.as<int32_t>(), a.in[0], a.in[1], a.in[2],
                                                   a.in[3], a.in[4], 1, dev.ws.sources.as<double>());
         count_launch();
-        return LPM_OK;
+        return log_window<K>(dev, st, 2, 0.0, a.n, a.in[1], nullptr);
     }
     static K::Params params(const Args& a)
     {
@@ -162,6 +163,7 @@ struct OpPseSphere {
         p.rad_over_eps = sr / eps;
         const double theta_cut = kPseCut * eps / sr;
         p.cos_cut = (theta_cut < LPM_PI) ? cos(theta_cut) : -2.0;
+        p.chord_cut = sphere_chord_cut(eps, sr);
         p.inv_eps2 = 1.0 / (eps * eps);
         return p;
     }
@@ -198,6 +200,7 @@ inline PseSphereConsts pse_sphere_consts(double eps, double sr, double scale)
     c.rad_over_eps = sr / eps;
     const double theta_cut = kPseCut * eps / sr;
     c.cos_cut = (theta_cut < LPM_PI) ? cos(theta_cut) : -2.0;
+    c.chord_cut = sphere_chord_cut(eps, sr);
     c.scale = scale;
     return c;
 }

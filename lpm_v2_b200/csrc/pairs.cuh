@@ -11,6 +11,8 @@
 
 #include <cstdint>
 
+#include "directsum.cuh"
+
 namespace lpm {
 
 // src/TypeDefs.f90:31
@@ -83,93 +85,157 @@ __device__ __forceinline__ void rcp_batch(const double (&d)[T], double (&r)[T])
     }
 }
 
-// Kernels without a per-CTA shared table.
-struct NoSharedTable {
-    static constexpr int KS = 0;
-    __device__ static __forceinline__ void init_shared(double*, int, int) {}
+// Tile culling (directsum.cuh) is for the compactly supported PSE kernels only; they
+// derive from CullSphere / CullPlane below and provide cull_dist(Params).
+struct NoCull {
+    static constexpr bool CULL = false;
+    static constexpr int CULL_GEOM = 0;
 };
 
-// ln(d) for finite normal d > 0: d = 2^e m, bin k = top 7 mantissa bits of m, q_k ~ 1/c_k from
-// MUFU.RCP64H (c_k = 1 + (k + 1/2)/128), r = m q_k - 1 with |r| <= 2^-8, then
-//   ln d = e ln2 - ln q_k + ln(1 + r)
-// with -ln q_k from a 128-entry table in shared memory and a degree-6 polynomial for ln(1 + r):
-// 9 FP64-pipe ops, one MUFU and one LDS.64 instead of the ~28 FP64 ops + branches of log().
-// (An earlier version kept {1/c_k, ln c_k} pairs in the table; its LDS.128 with a different
-// index per lane was bank-conflict bound -- 59 cycles per pair-warp measured against 28 of FP64 work.)
-// Absolute error ~2e-16 + 1 ulp of the result.  Anything else (d <= 0, subnormal, inf,
-// NaN) takes the library log() so the reference's -inf / NaN behaviour is kept.
-constexpr int kLogTabDoubles = 128;
-__device__ double g_log_table[kLogTabDoubles];
+// Kernels without a per-CTA shared table.
+struct NoSharedTable : NoCull {
+    static constexpr int KS = 0;
+    template <class Params>
+    __device__ static __forceinline__ int32_t init_shared(double*, const Params&, int, int) { return 0; }
+};
 
-// The bin-centre reciprocal used by log_tab: q_k = MUFU.RCP64H(c_k), c_k = 1 + (k + 1/2)/128.
-// It has ~20 significant bits, so m q_k - 1 is exact to an FMA rounding and |.| <= 2^-8 + 2^-20.
-__device__ __forceinline__ double log_bin_rcp(int hi_of_m)
+// ln(d) for d > 0 by table: the high word of d -- exponent and the top kLogBits mantissa bits --
+// names a bin [c - w, c + w); Q = MUFU.RCP64H(c) is a ~20-bit reciprocal of the bin centre that is
+// EXACT as a double (high word only), so r = fma(d, Q, -1) is exact to one rounding, |r| <= 2^-9 + 2^-20, and
+//   ln d = -ln Q + ln(1 + r),
+// with -ln Q from a table indexed by that same high word and a degree-5 polynomial for ln(1 + r)
+// (truncation r^6/6 < 1e-17).  No exponent extraction, no int-to-double conversion: 6 FP64-pipe
+// instructions, one MUFU and one LDS.64 per logarithm (the library log() is ~28 FP64 instructions
+// plus branches; a first table version with a 128-entry mantissa table and e ln2 added separately
+// took 9 and ran issue-bound).  Error <= 1 ulp of the result.
+//
+// The full table (every binade, 4 MB, built once per device from the device's own MUFU
+// results and long-double logarithms on the host, runtime.cuh) lives in global memory; each
+// launch copies the WINDOW of binades its arguments can fall in to shared memory.  The window
+// origin is computed on the device from a bound on d (log_window_kernel).  An argument outside
+// the window, or d <= 0 / subnormal / inf / NaN, takes the library log(), which also keeps the
+// reference's -inf / NaN behaviour.
+constexpr int kLogBits = 8;
+constexpr int kLogBin = 1 << kLogBits;                 // table entries per binade
+constexpr int kLogFull = 2048 * kLogBin;               // entries of the full table
+constexpr int kLogBinadeMin = 2, kLogBinadeMax = 2044; // biased exponents the fast path may see
+__device__ double g_log_full[kLogFull];
+
+// Q for the bin that holds a double with high word `hi`
+__device__ __forceinline__ double log_bin_rcp(int hi, int half = 0x00000800)
 {
-    const double c = __hiloint2double((hi_of_m & 0x000fe000) | 0x3ff01000, 0);
+    // (hi & 0xfffff000) | half as ONE LOP3: `half` arrives in a register (SharedCtx), because
+    // ptxas splits the expression in two when both masks are immediates
+    int chi;
+    asm("lop3.b32 %0, %1, 0xfffff000, %2, 0xEA;" : "=r"(chi) : "r"(hi), "r"(half));
+    const double c = __hiloint2double(chi, 0);
     double q;
     asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(q) : "d"(c));
     return q;
 }
-__global__ void log_table_seed_kernel(double* q)      // q[k] for the host to turn into -ln q[k]
+__global__ void log_table_seed_kernel(double* q)      // q[idx] for the host to turn into -ln q[idx]
 {
-    const int k = threadIdx.x;
-    if (k < kLogTabDoubles) q[k] = log_bin_rcp(0x3ff00000 | (k << 13));
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx < kLogFull) q[idx] = log_bin_rcp(idx << (20 - kLogBits));
 }
 
-struct LogSharedTable {
-    static constexpr int KS = kLogTabDoubles;
-    __device__ static __forceinline__ void init_shared(double* ks, int tid, int nthreads)
+// Parameters every log kernel carries (filled by direct_sum from the Device).
+struct LogParams {
+    const double* logtab;     // g_log_full of this device
+    const int32_t* win;       // window origin (entry index) written by log_window_kernel
+};
+
+template <int WB>     // WB: binades in the shared-memory window
+struct LogSharedTable : NoCull {
+    static constexpr int KS = WB * kLogBin;
+    static constexpr int WINDOW_BINADES = WB;
+    template <class Params>
+    __device__ static __forceinline__ int32_t init_shared(double* ks, const Params& p, int tid, int nthreads)
     {
-        for (int q = tid; q < kLogTabDoubles; q += nthreads) ks[q] = g_log_table[q];
+        const int32_t i0 = *p.win;
+        const double2* g = reinterpret_cast<const double2*>(p.logtab + i0);     // i0 is a multiple of 256
+        double2* s2 = reinterpret_cast<double2*>(ks);
+        for (int q = tid; q < KS / 2; q += nthreads) s2[q] = g[q];
+        return i0;
     }
 };
 
-__device__ __noinline__ double log_slow_path(double d) { return log(d); }
-
-// -1/6, 1/5, -1/4, 1/3, -1/2 (ln(1+r) = r - r^2/2 + ... - r^6/6), ln 2, 2^52 + 2^31
-__constant__ double kLogC[7] = {-1.0 / 6.0, 0.2, -0.25, 1.0 / 3.0, -0.5, 0.693147180559945309417232121458,
-                                4503601774854144.0};
-
-__device__ __forceinline__ bool log_needs_slow_path(double d)     // d <= 0, subnormal, inf or NaN
+// Window origin from an upper bound on the arguments.  mode 0: dmax = bound (BVE: 2 R^2);
+// mode 1: plane, bound = high word of max(|x|, |y|) over all particles, r^2 <= 8 m^2;
+// mode 2: beta-plane, bound = high word of max |y|, den <= 2 (4 cosh(pi y)^4 + 1).
+__global__ void log_window_kernel(int mode, double bound, const int32_t* __restrict__ maxhi, int wb, int32_t* win)
 {
-    return (unsigned)(__double2hiint(d) - 0x00100000) >= 0x7fe00000u;
+    double dmax = bound;
+    if (mode != 0) {
+        const double m = __hiloint2double(*maxhi, (int)0xffffffff);     // >= every |coordinate|
+        if (mode == 1) {
+            dmax = 8.0 * m * m;
+        } else {
+            const double c = cosh(LPM_PI * m);
+            dmax = 2.0 * (4.0 * c * c * c * c + 1.0);
+        }
+    }
+    dmax *= 1.000001;
+    int top = kLogBinadeMax;
+    if (dmax > 0.0 && dmax < CUDART_INF) top = __double2hiint(dmax) >> 20;
+    int lo = top - wb + 1;
+    if (lo > kLogBinadeMax - wb + 1) lo = kLogBinadeMax - wb + 1;
+    if (lo < kLogBinadeMin) lo = kLogBinadeMin;
+    *win = lo << kLogBits;
 }
 
-// Branch-free fast path (the caller has excluded the special arguments).
-__device__ __forceinline__ double log_tab(double d, const double* tab)
+// max over i of the high word of |a[i]| (and |b[i]|): non-negative doubles order like their high words
+__global__ void __launch_bounds__(256)
+absmax_hi_kernel(int64_t n, const double* __restrict__ a, const double* __restrict__ b, int32_t* out)
 {
-    const int hi = __double2hiint(d), lo = __double2loint(d);
-    const int e = (hi >> 20) - 1023;
-    const int k = (hi >> 13) & 0x7f;
-    const double m = __hiloint2double((hi & 0x000fffff) | 0x3ff00000, lo);
-    const double r = fma(m, log_bin_rcp(hi), -1.0);        // m / c_k - 1
-    // Constants come from the constant bank (operands of the DFMAs themselves): as immediates
-    // ptxas rebuilt each 64-bit literal with two moves per use, and the kernel was issue-bound
-    // (ncu: 35 instructions per pair, issue 68 %, FP64 pipe 55 %).
-    const double ed = __hiloint2double(0x43300000, e ^ 0x80000000) - kLogC[6];   // (double)e
+    int32_t m = 0;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        m = max(m, __double2hiint(a[i]) & 0x7fffffff);
+        if (b) m = max(m, __double2hiint(b[i]) & 0x7fffffff);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) m = max(m, __shfl_xor_sync(0xffffffffu, m, o));
+    if ((threadIdx.x & 31) == 0) atomicMax(out, m);
+}
+
+__device__ __noinline__ double log_slow_path(double d) { return log(d); }
+
+// 1/5, -1/4, 1/3, -1/2 : ln(1 + r) = r (1 + r (-1/2 + r (1/3 + r (-1/4 + r/5))))
+__constant__ double kLogC[4] = {0.2, -0.25, 1.0 / 3.0, -0.5};
+
+// Fast path; idx = (high word >> 12) - window origin, already known to be inside the window.
+// Constants come from the constant bank (operands of the DFMAs themselves): as immediates
+// ptxas rebuilt each 64-bit literal with two moves per use.
+__device__ __forceinline__ double log_tab(double d, int idx, const SharedCtx& sc)
+{
+    const double* tab = sc.ks;
+    const double r = fma(d, log_bin_rcp(__double2hiint(d), sc.i1), -1.0);
     double p = fma(r, kLogC[0], kLogC[1]);
     p = fma(r, p, kLogC[2]);
     p = fma(r, p, kLogC[3]);
-    p = fma(r, p, kLogC[4]);
     p = fma(r, p, 1.0);
-    return fma(r, p, fma(ed, kLogC[5], tab[k]));   // e ln2 - ln q_k + ln(1 + r)
+    return fma(r, p, tab[idx]);
 }
 
 // Logs of a thread's T arguments.  ONE branch per group: the fast block is straight-line
-// code whose T dependent chains interleave (a branch per argument serialised them -- the
-// first version ran at 59 cycles per pair-warp for 28 cycles of FP64 work).
-template <int T>
-__device__ __forceinline__ void log_group(const double (&d)[T], double (&l)[T], const double* tab)
+// code whose T dependent chains interleave (a branch per argument serialised them).  A
+// negative, zero, NaN or out-of-window argument has an index outside [0, KS) as unsigned.
+template <int KS, int T>
+__device__ __forceinline__ void log_group(const double (&d)[T], double (&l)[T], const SharedCtx& sc)
 {
-    bool slow = false;
+    int idx[T];
+    unsigned worst = 0;
 #pragma unroll
-    for (int k = 0; k < T; ++k) slow |= log_needs_slow_path(d[k]);
-    if (__builtin_expect(slow, 0)) {
-#pragma unroll 1
+    for (int k = 0; k < T; ++k) {
+        idx[k] = (__double2hiint(d[k]) >> (20 - kLogBits)) - sc.i0;
+        worst = max(worst, (unsigned)idx[k]);
+    }
+    if (__builtin_expect(worst >= (unsigned)KS, 0)) {
+#pragma unroll
         for (int k = 0; k < T; ++k) l[k] = log_slow_path(d[k]);
     } else {
 #pragma unroll
-        for (int k = 0; k < T; ++k) l[k] = log_tab(d[k], tab);
+        for (int k = 0; k < T; ++k) l[k] = log_tab(d[k], idx[k], sc);
     }
 }
 
@@ -178,7 +244,7 @@ __device__ __forceinline__ void log_group(const double (&d)[T], double (&l)[T], 
     template <int T, bool CHECK>                                                                         \
     __device__ static __forceinline__ void group(const Params& p, const Tgt (&t)[T], const double (&s)[NS], \
                                                  double (&acc)[T][NA], int32_t j, const int32_t (&self)[T], \
-                                                 const double* ks)                                       \
+                                                 const SharedCtx& ks)                                    \
     {                                                                                                    \
         _Pragma("unroll") for (int k = 0; k < T; ++k) pair<CHECK>(p, t[k], s, acc[k], CHECK && (j == self[k]), ks); \
     }
@@ -208,7 +274,7 @@ struct BveVelT : NoSharedTable {
     }
     template <int T, bool CHECK>
     __device__ static __forceinline__ void group(const Params& p, const Tgt (&t)[T], const double (&s)[NS],
-                                                 double (&acc)[T][NA], int32_t j, const int32_t (&self)[T], const double*)
+                                                 double (&acc)[T][NA], int32_t j, const int32_t (&self)[T], const SharedCtx&)
     {
         double d[T], r[T];
 #pragma unroll
@@ -270,10 +336,10 @@ __global__ void pack_bve_vel(int32_t nsrc, int32_t nsrc_pad, const int32_t* __re
 // BVE stream functions.  src/SphereBVE.f90:454-475:
 //   g = -log(R^2 - x_i.x_j)/(4 pi);  relStream_i += g zeta_j A_j;  absStream_i += g omega_j A_j
 // Source record: x, y, z, -zeta A/(4 pi), -omega A/(4 pi), 0.
-struct BveStream : LogSharedTable {
+struct BveStream : LogSharedTable<32> {
     static constexpr int NS = 6, NA = 2;
     static constexpr bool SKIP_SELF = true;
-    struct Params {
+    struct Params : LogParams {
         const double *x, *y, *z;
         double R2;
         Outs<2> out;
@@ -286,7 +352,7 @@ struct BveStream : LogSharedTable {
     template <int T, bool CHECK>
     __device__ static __forceinline__ void group(const Params& p, const Tgt (&t)[T], const double (&s)[NS],
                                                  double (&acc)[T][NA], int32_t j, const int32_t (&self)[T],
-                                                 const double* ks)
+                                                 const SharedCtx& sc)
     {
         double d[T], l[T];
 #pragma unroll
@@ -294,11 +360,12 @@ struct BveStream : LogSharedTable {
             d[k] = fma(-t[k].x, s[0], p.R2);
             d[k] = fma(-t[k].y, s[1], d[k]);
             d[k] = fma(-t[k].z, s[2], d[k]);
-            if (CHECK) d[k] = (j == self[k]) ? 1.0 : d[k];      // log(1) = 0 removes the pair
+            if (CHECK) d[k] = (j == self[k]) ? p.R2 : d[k];     // any in-window value; the pair is zeroed below
         }
-        log_group<T>(d, l, ks);
+        log_group<KS, T>(d, l, sc);
 #pragma unroll
         for (int k = 0; k < T; ++k) {
+            if (CHECK) l[k] = (j == self[k]) ? 0.0 : l[k];      // exactly, whatever the table gives for log(1)
             acc[k][0] = fma(l[k], s[3], acc[k][0]);
             acc[k][1] = fma(l[k], s[4], acc[k][1]);
         }
@@ -346,7 +413,7 @@ struct PlaneVel : NoSharedTable {
     __device__ static __forceinline__ Tgt load_target(const Params& p, int64_t i) { return Tgt{p.x[i], p.y[i]}; }
     template <int T, bool CHECK>
     __device__ static __forceinline__ void group(const Params&, const Tgt (&t)[T], const double (&s)[NS],
-                                                 double (&acc)[T][NA], int32_t j, const int32_t (&self)[T], const double*)
+                                                 double (&acc)[T][NA], int32_t j, const int32_t (&self)[T], const SharedCtx&)
     {
         double dx[T], dy[T], r2[T], r[T];
 #pragma unroll
@@ -394,10 +461,10 @@ __global__ void pack_plane(int32_t nsrc, int32_t nsrc_pad, const int32_t* __rest
 
 // Planar stream function.  src/PlanarIncompressible.f90:481-497:
 //   psi_i += log(sqrt(r^2))/(2 pi) omega_j A_j  ==  log(r^2) omega_j A_j/(4 pi)
-struct PlaneStream : LogSharedTable {
+struct PlaneStream : LogSharedTable<32> {
     static constexpr int NS = 4, NA = 1;
     static constexpr bool SKIP_SELF = true;
-    struct Params {
+    struct Params : LogParams {
         const double *x, *y;
         Outs<1> out;
     };
@@ -406,7 +473,7 @@ struct PlaneStream : LogSharedTable {
     template <int T, bool CHECK>
     __device__ static __forceinline__ void group(const Params&, const Tgt (&t)[T], const double (&s)[NS],
                                                  double (&acc)[T][NA], int32_t j, const int32_t (&self)[T],
-                                                 const double* ks)
+                                                 const SharedCtx& sc)
     {
         double r2[T], l[T];
 #pragma unroll
@@ -415,9 +482,12 @@ struct PlaneStream : LogSharedTable {
             r2[k] = fma(dx, dx, dy * dy);
             if (CHECK) r2[k] = (j == self[k]) ? 1.0 : r2[k];
         }
-        log_group<T>(r2, l, ks);
+        log_group<KS, T>(r2, l, sc);
 #pragma unroll
-        for (int k = 0; k < T; ++k) acc[k][0] = fma(l[k], s[2], acc[k][0]);
+        for (int k = 0; k < T; ++k) {
+            if (CHECK) l[k] = (j == self[k]) ? 0.0 : l[k];
+            acc[k][0] = fma(l[k], s[2], acc[k][0]);
+        }
     }
     __device__ static __forceinline__ void finalize(const Params& p, const Tgt&, const double (&a)[NA], int64_t i)
     {
@@ -454,7 +524,7 @@ struct BetaVel : NoSharedTable {
     }
     template <int T, bool CHECK>
     __device__ static __forceinline__ void group(const Params&, const Tgt (&t)[T], const double (&s)[NS],
-                                                 double (&acc)[T][NA], int32_t j, const int32_t (&self)[T], const double*)
+                                                 double (&acc)[T][NA], int32_t j, const int32_t (&self)[T], const SharedCtx&)
     {
         double SC[T], sc[T], den[T], r[T];
 #pragma unroll
@@ -486,16 +556,24 @@ struct BetaVel : NoSharedTable {
 // Beta-plane stream functions.  src/BetaPlane.f90:409-431:
 //   g = log(cosh(2 pi dy) - cos(2 pi dx))/(4 pi) = log(2 (S^2 + s^2))/(4 pi)
 // Source record: sh, ch, sn, cs, zeta A/(4 pi), omega A/(4 pi).
-struct BetaStream : LogSharedTable {
+struct BetaStream : LogSharedTable<40> {
     static constexpr int NS = 6, NA = 2;
     static constexpr bool SKIP_SELF = true;
-    using Params = BetaVel::Params;
+    struct Params : LogParams {
+        const double *x, *y;
+        Outs<2> out;
+    };
     using Tgt = BetaVel::Tgt;
-    __device__ static __forceinline__ Tgt load_target(const Params& p, int64_t i) { return BetaVel::load_target(p, i); }
+    __device__ static __forceinline__ Tgt load_target(const Params& p, int64_t i)
+    {
+        BetaVel::Params q{};
+        q.x = p.x; q.y = p.y;
+        return BetaVel::load_target(q, i);
+    }
     template <int T, bool CHECK>
     __device__ static __forceinline__ void group(const Params&, const Tgt (&t)[T], const double (&s)[NS],
                                                  double (&acc)[T][NA], int32_t j, const int32_t (&self)[T],
-                                                 const double* ks)
+                                                 const SharedCtx& sc)
     {
         double den[T], l[T];
 #pragma unroll
@@ -505,9 +583,10 @@ struct BetaStream : LogSharedTable {
             den[k] = 2.0 * fma(S, S, sn * sn);
             if (CHECK) den[k] = (j == self[k]) ? 1.0 : den[k];
         }
-        log_group<T>(den, l, ks);
+        log_group<KS, T>(den, l, sc);
 #pragma unroll
         for (int k = 0; k < T; ++k) {
+            if (CHECK) l[k] = (j == self[k]) ? 0.0 : l[k];
             acc[k][0] = fma(l[k], s[4], acc[k][0]);
             acc[k][1] = fma(l[k], s[5], acc[k][1]);
         }
@@ -553,6 +632,92 @@ __global__ void pack_beta(int32_t nsrc, int32_t nsrc_pad, const int32_t* __restr
 // pairs with k > kPseCut contribute < 1e-23 of eta(0) and are skipped.
 constexpr double kPseCut = 8.0;
 
+// Culling geometry.  Sphere kernels reject a pair by its ANGLE (dot < cos_cut |x_i| |x_j|), so
+// points are compared as unit vectors: an accepted pair has |u_i - u_j| <= 2 sin(theta_cut / 2)
+// whatever the particles' norms, and chords of unit vectors obey the triangle inequality.
+// Plane kernels reject by Euclidean distance > kPseCut eps.  Record fields 0..DIM-1 are the position.
+struct CullSphere : NoSharedTable {
+    static constexpr bool CULL = true;
+    static constexpr int CULL_GEOM = 3;
+    template <class Tgt>
+    __device__ static __forceinline__ void tgt_point(const Tgt& t, double (&p)[3])
+    {
+        const double inv = 1.0 / sqrt(t.x * t.x + t.y * t.y + t.z * t.z);
+        p[0] = t.x * inv; p[1] = t.y * inv; p[2] = t.z * inv;
+    }
+};
+struct CullPlane : NoSharedTable {
+    static constexpr bool CULL = true;
+    static constexpr int CULL_GEOM = 2;
+    template <class Tgt>
+    __device__ static __forceinline__ void tgt_point(const Tgt& t, double (&p)[3])
+    {
+        p[0] = t.x; p[1] = t.y; p[2] = 0.0;
+    }
+};
+// 2 sin(theta_cut / 2), or 1e301 when the cut-off reaches the antipode (no culling)
+inline double sphere_chord_cut(double eps, double sphere_radius)
+{
+    const double theta_cut = kPseCut * eps / sphere_radius;
+    return (theta_cut < LPM_PI) ? 2.0 * sin(0.5 * theta_cut) : 1.0e301;      // >= 1e300: no culling
+}
+
+// One bounding ball (centre, radius) per source tile of 256 (= kTile) records; an all-padding tile
+// gets radius -1e300 so that it is never visited.
+template <int NS, int GEOM>
+__global__ void __launch_bounds__(256)
+tile_bounds_kernel(int32_t nsrc, const double* __restrict__ src, double* __restrict__ bounds)
+{
+    __shared__ double red[4][8];
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const int32_t c = blockIdx.x * 256 + tid;
+    const bool real = c < nsrc;
+    double p[3] = {0.0, 0.0, 0.0};
+    if (real) {
+        p[0] = src[(size_t)c * NS]; p[1] = src[(size_t)c * NS + 1];
+        if (GEOM == 3) {
+            p[2] = src[(size_t)c * NS + 2];
+            const double inv = 1.0 / sqrt(p[0] * p[0] + p[1] * p[1] + p[2] * p[2]);
+            p[0] *= inv; p[1] *= inv; p[2] *= inv;
+        }
+    }
+    double s[4] = {p[0], p[1], p[2], real ? 1.0 : 0.0};
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1)
+#pragma unroll
+        for (int q = 0; q < 4; ++q) s[q] += __shfl_xor_sync(0xffffffffu, s[q], o);
+    if (lane == 0)
+#pragma unroll
+        for (int q = 0; q < 4; ++q) red[q][wid] = s[q];
+    __syncthreads();
+    double c4[4] = {0.0, 0.0, 0.0, 0.0};
+#pragma unroll
+    for (int w = 0; w < 8; ++w)
+#pragma unroll
+        for (int q = 0; q < 4; ++q) c4[q] += red[q][w];
+    const double cnt = c4[3];
+    const double inv = cnt > 0.0 ? 1.0 / cnt : 0.0;
+    const double cx = c4[0] * inv, cy = c4[1] * inv, cz = c4[2] * inv;
+    double r2 = 0.0;
+    if (real) {
+        const double dx = p[0] - cx, dy = p[1] - cy, dz = p[2] - cz;
+        r2 = dx * dx + dy * dy + dz * dz;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) r2 = fmax(r2, __shfl_xor_sync(0xffffffffu, r2, o));
+    __syncthreads();
+    if (lane == 0) red[0][wid] = r2;
+    __syncthreads();
+    if (tid == 0) {
+        double m = 0.0;
+#pragma unroll
+        for (int w = 0; w < 8; ++w) m = fmax(m, red[0][w]);
+        double* b = bounds + (size_t)blockIdx.x * 4;
+        b[0] = cx; b[1] = cy; b[2] = cz;
+        b[3] = cnt > 0.0 ? sqrt(m) * (1.0 + 1.0e-12) : -1.0e300;
+    }
+}
+
 __device__ __forceinline__ double pse_eta_pi(double k2)    // pi * eta
 {
     double poly = fma(fma(fma(-2.0 / 3.0, k2, 10.0), k2, -40.0), k2, 40.0);
@@ -561,16 +726,18 @@ __device__ __forceinline__ double pse_eta_pi(double k2)    // pi * eta
 
 // Sphere: d_ij = atan2(|x_i cross x_j|, x_i.x_j) * SphereRadius  (src/SphereGeometry.f90:107-125).
 // Source record: x, y, z, f, A/(pi eps^2), |x_j|.
-struct PseSphere : NoSharedTable {
+struct PseSphere : CullSphere {
     static constexpr int NS = 6, NA = 1;
     static constexpr bool SKIP_SELF = false;
     struct Params {
         const double *x, *y, *z, *f;
         double rad_over_eps;     // SphereRadius / eps
         double cos_cut;          // cos(kPseCut eps / SphereRadius), or -2 if the cut-off exceeds pi
+        double chord_cut;        // sphere_chord_cut(eps, SphereRadius)
         double inv_eps2;
         Outs<1> out;
     };
+    __device__ static __forceinline__ double cull_dist(const Params& p) { return p.chord_cut; }
     struct Tgt { double x, y, z, f, thr; };
     __device__ static __forceinline__ Tgt load_target(const Params& p, int64_t i)
     {
@@ -580,7 +747,7 @@ struct PseSphere : NoSharedTable {
     }
     template <bool CHECK>
     __device__ static __forceinline__ void pair(const Params& p, const Tgt& t, const double (&s)[NS],
-                                                double (&acc)[NA], bool, const double*)
+                                                double (&acc)[NA], bool, const SharedCtx&)
     {
         double dot = fma(t.x, s[0], fma(t.y, s[1], t.z * s[2]));
         if (dot < t.thr * s[5]) return;           // angle beyond the cut-off
@@ -618,7 +785,7 @@ __global__ void pack_pse_sphere(int32_t nsrc, int32_t nsrc_pad, const int32_t* _
 
 // Plane: d_ij = ChordDistance with z = 0 (src/SphereGeometry.f90:67-73, src/Particles.f90:663-670).
 // Source record: x, y, f, A/(pi eps^2).
-struct PsePlane : NoSharedTable {
+struct PsePlane : CullPlane {
     static constexpr int NS = 4, NA = 1;
     static constexpr bool SKIP_SELF = false;
     struct Params {
@@ -626,11 +793,12 @@ struct PsePlane : NoSharedTable {
         double inv_eps2;
         Outs<1> out;
     };
+    __device__ static __forceinline__ double cull_dist(const Params& p) { return kPseCut * rsqrt(p.inv_eps2); }
     struct Tgt { double x, y, f; };
     __device__ static __forceinline__ Tgt load_target(const Params& p, int64_t i) { return Tgt{p.x[i], p.y[i], p.f[i]}; }
     template <bool CHECK>
     __device__ static __forceinline__ void pair(const Params& p, const Tgt& t, const double (&s)[NS],
-                                                double (&acc)[NA], bool, const double*)
+                                                double (&acc)[NA], bool, const SharedCtx&)
     {
         double dx = s[0] - t.x, dy = s[1] - t.y;
         double k2 = fma(dx, dx, dy * dy) * p.inv_eps2;

@@ -37,12 +37,13 @@ __device__ __forceinline__ double sphere_k2(double tx, double ty, double tz, dou
 struct PseSphereConsts {
     double rad_over_eps;     // SphereRadius / eps
     double cos_cut;          // cos(kPseCut eps / SphereRadius), or -2 if the cut-off exceeds pi
+    double chord_cut;        // sphere_chord_cut(eps, SphereRadius), for tile culling
     double scale;            // post-scaling of the summed field (the trailing MultiplyFieldByScalar)
 };
 
 // ---------------------------------------------------------------- interpolation
 // Source record (sphere): x, y, z, f A/(pi eps^2), |x|, 0;  (plane): x, y, f A/(pi eps^2), 0.
-struct PseInterpSphere : NoSharedTable {
+struct PseInterpSphere : CullSphere {
     static constexpr int NS = 6, NA = 1;
     static constexpr bool SKIP_SELF = false;
     struct Params {
@@ -50,6 +51,7 @@ struct PseInterpSphere : NoSharedTable {
         PseSphereConsts c;
         Outs<1> out;
     };
+    __device__ static __forceinline__ double cull_dist(const Params& p) { return p.c.chord_cut; }
     struct Tgt { double x, y, z, thr; };
     __device__ static __forceinline__ Tgt load_target(const Params& p, int64_t i)
     {
@@ -59,7 +61,7 @@ struct PseInterpSphere : NoSharedTable {
     }
     template <bool CHECK>
     __device__ static __forceinline__ void pair(const Params& p, const Tgt& t, const double (&s)[NS],
-                                                double (&acc)[NA], bool, const double*)
+                                                double (&acc)[NA], bool, const SharedCtx&)
     {
         double dot = fma(t.x, s[0], fma(t.y, s[1], t.z * s[2]));
         if (dot < t.thr * s[4]) return;
@@ -73,7 +75,7 @@ struct PseInterpSphere : NoSharedTable {
     }
 };
 
-struct PseInterpPlane : NoSharedTable {
+struct PseInterpPlane : CullPlane {
     static constexpr int NS = 4, NA = 1;
     static constexpr bool SKIP_SELF = false;
     struct Params {
@@ -81,11 +83,12 @@ struct PseInterpPlane : NoSharedTable {
         double inv_eps2;
         Outs<1> out;
     };
+    __device__ static __forceinline__ double cull_dist(const Params& p) { return kPseCut * rsqrt(p.inv_eps2); }
     struct Tgt { double x, y; };
     __device__ static __forceinline__ Tgt load_target(const Params& p, int64_t i) { return Tgt{p.x[i], p.y[i]}; }
     template <bool CHECK>
     __device__ static __forceinline__ void pair(const Params& p, const Tgt& t, const double (&s)[NS],
-                                                double (&acc)[NA], bool, const double*)
+                                                double (&acc)[NA], bool, const SharedCtx&)
     {
         double dx = s[0] - t.x, dy = s[1] - t.y;
         double k2 = fma(dx, dx, dy * dy) * p.inv_eps2;
@@ -129,7 +132,7 @@ __global__ void pack_pse_interp(int32_t nsrc, int32_t nsrc_pad, const int32_t* _
 
 // ---------------------------------------------------------------- gradient
 // plane (:180-218): grad_i = eps^-1 sum (f_j + f_i)(x_i - x_j) phi'(k)/eps^3 A_j.  Record: x, y, f, A/(pi eps^3).
-struct PseGradPlane : NoSharedTable {
+struct PseGradPlane : CullPlane {
     static constexpr int NS = 4, NA = 2;
     static constexpr bool SKIP_SELF = false;
     struct Params {
@@ -137,11 +140,12 @@ struct PseGradPlane : NoSharedTable {
         double inv_eps2, scale;
         Outs<2> out;
     };
+    __device__ static __forceinline__ double cull_dist(const Params& p) { return kPseCut * rsqrt(p.inv_eps2); }
     struct Tgt { double x, y, f; };
     __device__ static __forceinline__ Tgt load_target(const Params& p, int64_t i) { return Tgt{p.x[i], p.y[i], p.f[i]}; }
     template <bool CHECK>
     __device__ static __forceinline__ void pair(const Params& p, const Tgt& t, const double (&s)[NS],
-                                                double (&acc)[NA], bool, const double*)
+                                                double (&acc)[NA], bool, const SharedCtx&)
     {
         double dx = t.x - s[0], dy = t.y - s[1];
         double k2 = fma(dx, dx, dy * dy) * p.inv_eps2;
@@ -160,7 +164,7 @@ struct PseGradPlane : NoSharedTable {
 
 // sphere (:221-267): grad_i = eps^-2 P_i sum (f_j + f_i)(x_i - x_j) phi'(k)/eps^2 A_j, P = I - x x^T.
 // Record: x, y, z, f, A/(pi eps^2), |x|.
-struct PseGradSphere : NoSharedTable {
+struct PseGradSphere : CullSphere {
     static constexpr int NS = 6, NA = 3;
     static constexpr bool SKIP_SELF = false;
     struct Params {
@@ -168,6 +172,7 @@ struct PseGradSphere : NoSharedTable {
         PseSphereConsts c;
         Outs<3> out;
     };
+    __device__ static __forceinline__ double cull_dist(const Params& p) { return p.c.chord_cut; }
     struct Tgt { double x, y, z, f, thr; };
     __device__ static __forceinline__ Tgt load_target(const Params& p, int64_t i)
     {
@@ -177,7 +182,7 @@ struct PseGradSphere : NoSharedTable {
     }
     template <bool CHECK>
     __device__ static __forceinline__ void pair(const Params& p, const Tgt& t, const double (&s)[NS],
-                                                double (&acc)[NA], bool, const double*)
+                                                double (&acc)[NA], bool, const SharedCtx&)
     {
         double dot = fma(t.x, s[0], fma(t.y, s[1], t.z * s[2]));
         if (dot < t.thr * s[5]) return;
@@ -202,7 +207,7 @@ struct PseGradSphere : NoSharedTable {
 // MODE 0: second partials -> (q_xx, (q_xy + q_yx)/2, q_yy)/eps;  MODE 1: double dot -> (q_xx^2 + 2 q_xy q_yx + q_yy^2)/eps^2.
 // Record: x, y, g_x, g_y, A/(pi eps^3), 0.
 template <int MODE>
-struct PseTensorPlane : NoSharedTable {
+struct PseTensorPlane : CullPlane {
     static constexpr int NS = 6, NA = 4;
     static constexpr bool SKIP_SELF = false;
     struct Params {
@@ -210,6 +215,7 @@ struct PseTensorPlane : NoSharedTable {
         double inv_eps2, inv_eps;
         Outs<3> out;
     };
+    __device__ static __forceinline__ double cull_dist(const Params& p) { return kPseCut * rsqrt(p.inv_eps2); }
     struct Tgt { double x, y, gx, gy; };
     __device__ static __forceinline__ Tgt load_target(const Params& p, int64_t i)
     {
@@ -217,7 +223,7 @@ struct PseTensorPlane : NoSharedTable {
     }
     template <bool CHECK>
     __device__ static __forceinline__ void pair(const Params& p, const Tgt& t, const double (&s)[NS],
-                                                double (&acc)[NA], bool, const double*)
+                                                double (&acc)[NA], bool, const SharedCtx&)
     {
         double dx = t.x - s[0], dy = t.y - s[1];
         double k2 = fma(dx, dx, dy * dy) * p.inv_eps2;
@@ -245,7 +251,7 @@ struct PseTensorPlane : NoSharedTable {
 // ---------------------------------------------------------------- sphere: double dot / divergence
 // Record: x, y, z, u, v, w, A/(pi eps^3), |x|.
 // Double dot (:367-420): nine sums; the w rows add yComp(i) (the reference's quirk at :408-413, kept).
-struct PseDoubleDotSphere : NoSharedTable {
+struct PseDoubleDotSphere : CullSphere {
     static constexpr int NS = 8, NA = 9;
     static constexpr bool SKIP_SELF = false;
     struct Params {
@@ -253,6 +259,7 @@ struct PseDoubleDotSphere : NoSharedTable {
         PseSphereConsts c;
         Outs<1> out;
     };
+    __device__ static __forceinline__ double cull_dist(const Params& p) { return p.c.chord_cut; }
     struct Tgt { double x, y, z, u, v, thr; };
     __device__ static __forceinline__ Tgt load_target(const Params& p, int64_t i)
     {
@@ -262,7 +269,7 @@ struct PseDoubleDotSphere : NoSharedTable {
     }
     template <bool CHECK>
     __device__ static __forceinline__ void pair(const Params& p, const Tgt& t, const double (&s)[NS],
-                                                double (&acc)[NA], bool, const double*)
+                                                double (&acc)[NA], bool, const SharedCtx&)
     {
         double dot = fma(t.x, s[0], fma(t.y, s[1], t.z * s[2]));
         if (dot < t.thr * s[7]) return;
@@ -284,7 +291,7 @@ struct PseDoubleDotSphere : NoSharedTable {
 };
 
 // Divergence (:537-579): div_i = eps^-1 sum [P_i (x_i - x_j)] . (v_j + v_i) phi'(k)/eps^3 A_j.
-struct PseDivSphere : NoSharedTable {
+struct PseDivSphere : CullSphere {
     static constexpr int NS = 8, NA = 1;
     static constexpr bool SKIP_SELF = false;
     struct Params {
@@ -292,6 +299,7 @@ struct PseDivSphere : NoSharedTable {
         PseSphereConsts c;
         Outs<1> out;
     };
+    __device__ static __forceinline__ double cull_dist(const Params& p) { return p.c.chord_cut; }
     struct Tgt { double x, y, z, u, v, w, thr; };
     __device__ static __forceinline__ Tgt load_target(const Params& p, int64_t i)
     {
@@ -301,7 +309,7 @@ struct PseDivSphere : NoSharedTable {
     }
     template <bool CHECK>
     __device__ static __forceinline__ void pair(const Params& p, const Tgt& t, const double (&s)[NS],
-                                                double (&acc)[NA], bool, const double*)
+                                                double (&acc)[NA], bool, const SharedCtx&)
     {
         double dot = fma(t.x, s[0], fma(t.y, s[1], t.z * s[2]));
         if (dot < t.thr * s[7]) return;

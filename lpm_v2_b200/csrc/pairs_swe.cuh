@@ -24,7 +24,7 @@ struct SweRhsPlane : NoSharedTable {
 
     template <int T, bool CHECK>
     __device__ static __forceinline__ void group(const Params& p, const Tgt (&t)[T], const double (&s)[NS],
-                                                 double (&acc)[T][NA], int32_t j, const int32_t (&self)[T], const double*)
+                                                 double (&acc)[T][NA], int32_t j, const int32_t (&self)[T], const SharedCtx&)
     {
         double dx[T], dy[T], r2[T], r[T];
 #pragma unroll

@@ -5,6 +5,7 @@
 
 #include <algorithm>
 #include <cmath>
+#include <vector>
 
 #include "common.cuh"
 #include "directsum.cuh"
@@ -24,20 +25,27 @@ inline int init_device(Device& d, int id)
         return set_error(LPM_ERR_NO_DEVICE, "device %d (%s) is sm_%d%d; liblpmgpu is built for sm_100a only", id,
                          prop.name, prop.major, prop.minor);
     d.sm_count = prop.multiProcessorCount;
-    {   // table for log_tab(): -ln q_k, q_k = MUFU.RCP64H(c_k) read back from the device and
-        // evaluated in long double on the host
+    {   // table for log_tab(): -ln Q for every (binade, bin), Q = MUFU.RCP64H(bin centre) read back
+        // from THIS device and evaluated in long double on the host
         double* dq = nullptr;
-        double tab[kLogTabDoubles];
-        LPM_CUDA(cudaMalloc(&dq, sizeof(tab)));
-        log_table_seed_kernel<<<1, kLogTabDoubles>>>(dq);
-        LPM_CUDA(cudaMemcpy(tab, dq, sizeof(tab), cudaMemcpyDeviceToHost));
+        std::vector<double> tab(kLogFull);
+        LPM_CUDA(cudaMalloc(&dq, sizeof(double) * kLogFull));
+        log_table_seed_kernel<<<kLogFull / 256, 256>>>(dq);
+        LPM_CUDA(cudaMemcpy(tab.data(), dq, sizeof(double) * kLogFull, cudaMemcpyDeviceToHost));
         LPM_CUDA(cudaFree(dq));
-        for (int k = 0; k < kLogTabDoubles; ++k) {
-            if (!(tab[k] > 0.49 && tab[k] <= 1.0))
-                return set_error(LPM_ERR_CUDA, "log table seed %d out of range (%g)", k, tab[k]);
-            tab[k] = (double)(-logl((long double)tab[k]));
+        for (int idx = 0; idx < kLogFull; ++idx) {
+            const int binade = idx >> kLogBits;
+            if (binade < kLogBinadeMin || binade > kLogBinadeMax) { tab[idx] = 0.0; continue; }
+            // the bin centre is c = 2^(binade-1023) (1 + (k + 1/2)/256); Q must be its reciprocal to ~2^-20
+            const double c = std::ldexp(1.0 + ((idx & (kLogBin - 1)) + 0.5) / kLogBin, binade - 1023);
+            if (!(std::fabs(tab[idx] * c - 1.0) < 1.0e-5))
+                return set_error(LPM_ERR_CUDA, "log table seed %d out of range (Q c - 1 = %g)", idx, tab[idx] * c - 1.0);
+            tab[idx] = (double)(-logl((long double)tab[idx]));
         }
-        LPM_CUDA(cudaMemcpyToSymbol(g_log_table, tab, sizeof(tab)));
+        LPM_CUDA(cudaMemcpyToSymbol(g_log_full, tab.data(), sizeof(double) * kLogFull));
+        void* sym = nullptr;
+        LPM_CUDA(cudaGetSymbolAddress(&sym, g_log_full));
+        d.logtab = (const double*)sym;
     }
     LPM_CUDA(cudaStreamCreateWithFlags(&d.stream, cudaStreamNonBlocking));
     LPM_CUDA(cudaEventCreateWithFlags(&d.ev_done, cudaEventDisableTiming));
@@ -168,13 +176,19 @@ inline void launch_ds(cudaStream_t st, const typename K::Params& prm, DsGeom g, 
                       const int32_t* scan, double* partial)
 {
     g.tblk0 = g.tbeg / (BLOCK * T) * (BLOCK * T);
+    g.half_bin = 1 << (19 - kLogBits);
     g.ntblocks = (int32_t)((g.tend - g.tblk0 + BLOCK * T - 1) / (BLOCK * T));
     const int64_t grid = (int64_t)g.ntblocks * g.nchunks;
     constexpr size_t smem = ds_smem_bytes<K, T, BLOCK>();
-    static bool configured = false;     // per instantiation
-    if (!configured && smem > 48 * 1024) {
-        cudaFuncSetAttribute(ds_kernel<K, T, BLOCK, U>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        configured = true;
+    if (smem > 48 * 1024) {
+        // the attribute is per device: remember which devices this instantiation has been configured on
+        static bool configured[64] = {};
+        int devid = 0;
+        cudaGetDevice(&devid);
+        if (devid < 0 || devid >= 64 || !configured[devid]) {
+            cudaFuncSetAttribute(ds_kernel<K, T, BLOCK, U>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            if (devid >= 0 && devid < 64) configured[devid] = true;
+        }
     }
     ds_kernel<K, T, BLOCK, U><<<(unsigned)grid, BLOCK, smem, st>>>(prm, g, src, scan, partial);
 }
@@ -202,22 +216,55 @@ inline int direct_sum(Device& dev, cudaStream_t st, const MaskPlan& mp, int64_t 
         LPM_TRY(dev.ws.partial.reserve((size_t)g.nchunks * K::NA * g.ntgt * sizeof(double)));
         partial = dev.ws.partial.as<double>();
     }
+    if constexpr (K::CULL) {
+        // bounding ball per source tile, from the records the caller has just packed
+        static_assert(kTile == 256, "tile_bounds_kernel uses one 256-thread CTA per tile");
+        const int ntiles = g.nsrc_pad / kTile;
+        LPM_TRY(dev.ws.bounds.reserve((size_t)ntiles * 4 * sizeof(double)));
+        tile_bounds_kernel<K::NS, K::CULL_GEOM><<<ntiles, 256, 0, st>>>(g.nsrc, dev.ws.sources.as<double>(),
+                                                                       dev.ws.bounds.as<double>());
+        count_launch();
+        g.bounds = rt().pse_culling ? dev.ws.bounds.as<double>() : nullptr;
+    }
+    typename K::Params prm2 = prm;
+    if constexpr (K::KS > 0) {      // log kernels: this device's table, and the window the caller's pack() computed
+        prm2.logtab = dev.logtab;
+        prm2.win = dev.ws.logwin.as<int32_t>() + 1;
+    }
     const bool prof = rt().profiling;
     cudaEvent_t pb = nullptr, pe = nullptr;
     if (prof) {
         if (dev.next_prof(&pb, &pe) != LPM_OK) return set_error(LPM_ERR_CUDA, "cannot create profiling events");
         LPM_CUDA(cudaEventRecord(pb, st));
     }
-    LPM_TRY(launch_variant<K>(variant, st, prm, g, dev.ws.sources.as<double>(), mp.scan.as<int32_t>(), partial,
+    LPM_TRY(launch_variant<K>(variant, st, prm2, g, dev.ws.sources.as<double>(), mp.scan.as<int32_t>(), partial,
                               dev.sm_count));
     if (prof) LPM_CUDA(cudaEventRecord(pe, st));
     count_launch();
     if (g.nchunks > 1) {
         const unsigned nb = (unsigned)((g.ntgt + 255) / 256);
-        ds_finalize_kernel<K><<<nb, 256, 0, st>>>(prm, g, partial);
+        ds_finalize_kernel<K><<<nb, 256, 0, st>>>(prm2, g, partial);
         count_launch();
     }
     LPM_CUDA(cudaGetLastError());
+    return LPM_OK;
+}
+
+// Log kernels: compute the table window for this evaluation on the device (pairs.cuh).
+// mode 0: bound = upper bound on the argument; mode 1 / 2: bound from max |a|, |b| over n entries.
+template <class K>
+inline int log_window(Device& dev, cudaStream_t st, int mode, double bound, int64_t n, const double* a, const double* b)
+{
+    LPM_TRY(dev.ws.logwin.reserve(2 * sizeof(int32_t)));
+    int32_t* w = dev.ws.logwin.as<int32_t>();
+    if (mode != 0) {
+        LPM_CUDA(cudaMemsetAsync(w, 0, sizeof(int32_t), st));
+        const unsigned nb = (unsigned)std::min<int64_t>((n + 255) / 256, 4 * (int64_t)dev.sm_count);
+        absmax_hi_kernel<<<nb, 256, 0, st>>>(n, a, b, w);
+        count_launch();
+    }
+    log_window_kernel<<<1, 1, 0, st>>>(mode, bound, w, K::WINDOW_BINADES, w + 1);
+    count_launch();
     return LPM_OK;
 }
 
@@ -247,12 +294,22 @@ template <class K>
 inline int launch_variant(int variant, cudaStream_t st, const typename K::Params& prm, const DsGeom& g,
                           const double* src, const int32_t* scan, double* partial, int sm_count)
 {
-    int T = auto_T(g.nall, g.nchunks, sm_count, 128);
     (void)variant;
-    switch (T) {
-        case 4: launch_ds<K, 4, 128, 1>(st, prm, g, src, scan, partial); break;
-        case 2: launch_ds<K, 2, 128, 2>(st, prm, g, src, scan, partial); break;
-        default: launch_ds<K, 1, 128, 4>(st, prm, g, src, scan, partial); break;
+    if constexpr (K::KS > 0) {
+        // log kernels carry a 64-80 KB table per CTA: 256 threads share it
+        int T = auto_T(g.nall, g.nchunks, sm_count, 256);
+        switch (T) {
+            case 4: launch_ds<K, 4, 256, 2>(st, prm, g, src, scan, partial); break;
+            case 2: launch_ds<K, 2, 256, 2>(st, prm, g, src, scan, partial); break;
+            default: launch_ds<K, 1, 256, 2>(st, prm, g, src, scan, partial); break;
+        }
+    } else {
+        int T = auto_T(g.nall, g.nchunks, sm_count, 128);
+        switch (T) {
+            case 4: launch_ds<K, 4, 128, 1>(st, prm, g, src, scan, partial); break;
+            case 2: launch_ds<K, 2, 128, 2>(st, prm, g, src, scan, partial); break;
+            default: launch_ds<K, 1, 128, 4>(st, prm, g, src, scan, partial); break;
+        }
     }
     return LPM_OK;
 }

@@ -36,6 +36,14 @@ want = O.bve_velocity(m.x, m.y, m.z, zeta, m.area, m.is_active, 1.0)
 assert max(rel(g, w) for g, w in zip(got, want)) <= 1e-12
 lap = api.pse_laplacian_sphere(m.x, m.y, m.z, zeta, m.area, m.is_active, 0.2, 1.0)
 assert rel(lap, O.pse_laplacian_sphere(m.x, m.y, m.z, zeta, m.area, m.is_active, 0.2, 1.0)) <= 1e-12
+# kernels whose shared memory exceeds 48 KB need their attribute set on every device
+dd = api.pse_double_dot_sphere(m.x, m.y, m.z, -m.y, m.x, m.z * m.x, m.area, m.is_active, 0.2, 1.0)
+assert rel(dd, O.pse_double_dot_sphere(m.x, m.y, m.z, -m.y, m.x, m.z * m.x, m.area, m.is_active, 0.2, 1.0)) <= 1e-12
+q = M.PolyMesh2d(M.QUAD_RECT_SEED, 4, 3.0)
+vq = np.exp(-2 * (q.x ** 2 + q.y ** 2))
+sw = api.swe_plane_rhs_integrals(q.x, q.y, vq, 0.1 * vq * q.x, 1 + 0.1 * vq, q.area, q.is_active, 0.3)
+so = O.swe_plane_rhs(q.x, q.y, vq, 0.1 * vq * q.x, 1 + 0.1 * vq, q.area, q.is_active, 0.3)
+assert max(rel(a, b) for a, b in zip(sw, so)) <= 1e-12
 sph = solvers.BVEMesh(m, zeta, 1.0, 2 * np.pi)
 sph.velocity = [g.copy() for g in got]
 sol = solvers.BVESolver(sph)

@@ -197,6 +197,46 @@ def test_bve_stream(gpu, oracle, get_mesh):
         assert max(relerr(g, w) for g, w in zip(got, want)) <= TOL
 
 
+@pytest.mark.parametrize("radius", [1.0, 6371.22e3, 3.0e-7])
+def test_bve_stream_any_radius(gpu, oracle, get_mesh, radius):
+    """The log table window (pairs.cuh) follows 2 R^2: Earth radius in metres and a tiny
+    sphere must be as accurate as the unit sphere."""
+    m = get_mesh(M.ICOS_TRI_SPHERE_SEED, 4)
+    zeta = problems.rossby_haurwitz54(m)
+    absv = problems.abs_vorticity(m, zeta, 2 * PI)
+    x, y, z, area = m.x * radius, m.y * radius, m.z * radius, m.area * radius * radius
+    got = gpu.bve_stream(x, y, z, zeta, absv, area, m.is_active, radius)
+    want = oracle.bve_stream(x, y, z, zeta, absv, area, m.is_active, radius)
+    assert max(relerr(g, w) for g, w in zip(got, want)) <= TOL
+
+
+def test_stream_arguments_outside_the_log_window(gpu, oracle):
+    """Pairs 1e-9 apart next to pairs 1e7 apart: r^2 spans 106 binades, far more than the
+    32-binade shared-memory window, so part of the sum takes the library log(); coincident
+    particles give log(0) = -inf as in the reference."""
+    rng = np.random.default_rng(5)
+    n = 1500
+    x = np.concatenate([rng.uniform(-1e7, 1e7, n // 3), rng.uniform(-1, 1, n // 3), 0.25 + rng.uniform(-1e-9, 1e-9, n - 2 * (n // 3))])
+    y = np.concatenate([rng.uniform(-1e7, 1e7, n // 3), rng.uniform(-1, 1, n // 3), -0.5 + rng.uniform(-1e-9, 1e-9, n - 2 * (n // 3))])
+    vort = rng.uniform(-1, 1, n)
+    area = rng.uniform(0.5, 1.5, n)
+    mask = (rng.uniform(size=n) < 0.7).astype(np.int32)
+    got = gpu.plane_stream(x, y, vort, area, mask)
+    want = oracle.plane_stream(x, y, vort, area, mask)
+    assert np.all(np.isfinite(got))
+    assert relerr(got, want) <= TOL
+    # two coincident active particles: the reference adds log(0) * w = -+inf to both
+    x[10], y[10] = x[11], y[11]
+    mask[10] = mask[11] = 1
+    vort[10] = vort[11] = 0.5
+    got = gpu.plane_stream(x, y, vort, area, mask)
+    want = oracle.plane_stream(x, y, vort, area, mask)
+    assert np.array_equal(np.isfinite(got), np.isfinite(want))
+    assert np.isneginf(got[10]) and np.isneginf(got[11]) and np.isneginf(want[10])
+    ok = np.isfinite(want)
+    assert relerr(got[ok], want[ok]) <= TOL
+
+
 # ---------------------------------------------------------------- planar
 @pytest.mark.parametrize("L", [2, 4, 5])
 def test_plane_velocity_and_stream(gpu, oracle, get_mesh, L):

@@ -91,3 +91,55 @@ def test_plane_operators(gpu, oracle, get_mesh, L, power):
     tx, ty = rng.uniform(-2, 2, 501), rng.uniform(-2, 2, 501)
     assert relerr(gpu.pse_interpolate_plane(q.x, q.y, f, q.area, q.is_active, eps, tx, ty),
                   oracle.pse_interpolate(q.x, q.y, None, f, q.area, q.is_active, eps, tx, ty)) <= TOL
+
+
+@pytest.mark.parametrize("seed,L,power", [(M.ICOS_TRI_SPHERE_SEED, 6, 0.75), (M.ICOS_TRI_SPHERE_SEED, 5, 1.5),
+                                          (M.CUBED_SPHERE_SEED, 5, 0.75)])
+def test_tile_culling_is_bit_identical_sphere(gpu, oracle, get_mesh, seed, L, power):
+    """Tile culling (directsum.cuh) only skips source tiles whose every pair the per-pair
+    cut-off rejects, so switching it off must not change a single bit; a sample of targets is
+    also checked against the oracle (which evaluates every pair, as the reference does)."""
+    m = get_mesh(seed, L)
+    eps = m.max_edge_length ** power
+    f = problems.spherical_harmonic54(m)
+    u, v, w = -m.y + 0.3 * m.z * m.x, m.x * m.x, 0.5 * m.y - m.z
+    args = (m.x, m.y, m.z)
+
+    def run():
+        return [gpu.pse_laplacian_sphere(*args, f, m.area, m.is_active, eps, 1.0),
+                *gpu.pse_gradient_sphere(*args, f, m.area, m.is_active, eps),
+                gpu.pse_divergence_sphere(*args, u, v, w, m.area, m.is_active, eps),
+                gpu.pse_interpolate_sphere(*args, f, m.area, m.is_active, eps, m.x[::7], m.y[::7], m.z[::7])]
+    try:
+        gpu.set_pse_culling(False)
+        plain = run()
+    finally:
+        gpu.set_pse_culling(True)
+    culled = run()
+    for a, b in zip(plain, culled):
+        assert np.array_equal(a, b)
+    rng = np.random.default_rng(L)
+    idx = np.concatenate([[0, 1, 12, m.n - 1], rng.integers(0, m.n, 28)])
+    lap = culled[0]
+    scale = np.abs(lap).max()
+    for i in idx:
+        want = oracle.pse_laplacian_sphere(*args, f, m.area, m.is_active, eps, 1.0, rng=(int(i), int(i) + 1))
+        assert abs(lap[i] - want[i]) <= TOL * scale
+
+
+def test_tile_culling_is_bit_identical_plane(gpu, get_mesh):
+    q = get_mesh(M.QUAD_RECT_SEED, 7, 2.0)
+    eps = q.max_edge_length ** 0.75
+    f = np.sin(1.3 * q.x) * np.cos(0.7 * q.y) + 0.1 * q.x * q.y
+
+    def run():
+        return [gpu.pse_laplacian_plane(q.x, q.y, f, q.area, q.is_active, eps),
+                *gpu.pse_gradient_plane(q.x, q.y, f, q.area, q.is_active, eps),
+                gpu.pse_double_dot_plane(q.x, q.y, q.y ** 2 - q.x, q.x * q.y, q.area, q.is_active, eps)]
+    try:
+        gpu.set_pse_culling(False)
+        plain = run()
+    finally:
+        gpu.set_pse_culling(True)
+    for a, b in zip(plain, run()):
+        assert np.array_equal(a, b)
