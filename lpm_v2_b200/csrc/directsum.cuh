@@ -126,8 +126,8 @@ struct SharedCtx {
 //   finalize(p, tgt, acc, i)   writes the outputs of target i
 //
 // partial layout: [(chunk*NA + a) * ntgt + local_target]
-template <class K, int T, int BLOCK, int U>
-__global__ void __launch_bounds__(BLOCK)
+template <class K, int T, int BLOCK, int U, int MINB = 1>
+__global__ void __launch_bounds__(BLOCK, MINB)
 ds_kernel(const typename K::Params prm, const DsGeom g, const double* __restrict__ src,
           const int32_t* __restrict__ scan, double* __restrict__ partial)
 {
@@ -260,7 +260,6 @@ ds_kernel(const typename K::Params prm, const DsGeom g, const double* __restrict
 
     // next tile to visit at or after `from` (ntiles if none)
     auto next_tile = [&](int from) -> int {
-        if (!cull) return from < ntiles ? from : ntiles;
         while (from < ntiles) {
             const uint32_t w = need[from >> 5] >> (from & 31);
             if (w) return from + __ffs(w) - 1;
@@ -269,27 +268,14 @@ ds_kernel(const typename K::Params prm, const DsGeom g, const double* __restrict
         return ntiles;
     };
 
-    int cur = next_tile(0);
-    int nxt = next_tile(cur + 1);
-    if (tid == 0) {
-        if (cur < ntiles) {
-            mbar_expect_tx(&full[0], kTileBytes);
-            tma_bulk_g2s(tile[0], src + (size_t)(s0 + cur * TS) * NS, kTileBytes, &full[0]);
-        }
-        if (nxt < ntiles) {
-            mbar_expect_tx(&full[1], kTileBytes);
-            tma_bulk_g2s(tile[1], src + (size_t)(s0 + nxt * TS) * NS, kTileBytes, &full[1]);
-        }
-    }
-
-    for (int it = 0; cur < ntiles; ++it) {
-        const int k = cur;
-        const int st = it & 1;
-        mbar_wait(&full[st], (it >> 1) & 1);
+    // One tile against the thread's targets; the tile's sums then join the running sums.
+    auto do_tile = [&](const int k, const int st) {
         const double* sm = tile[st];
         const int32_t j0 = s0 + k * TS;
         const bool check = K::SKIP_SELF && (j0 < selfhi) && (j0 + TS > selflo);
+        bool careful = check;      // run the tile through group<T, true>()
         if (!check) {
+            unsigned worst = 0;
 #pragma unroll U
             for (int j = 0; j < TS; ++j) {
                 double s[NS];
@@ -299,9 +285,22 @@ ds_kernel(const typename K::Params prm, const DsGeom g, const double* __restrict
                     double2 v = p2[q];
                     s[2 * q] = v.x; s[2 * q + 1] = v.y;
                 }
-                K::template group<T, false>(prm, tg, s, acc, 0, self, sctx);
+                if constexpr (K::RETRY) K::template group_fast<T>(prm, tg, s, acc, worst, sctx);
+                else K::template group<T, false>(prm, tg, s, acc, 0, self, sctx);
             }
-        } else {
+            if constexpr (K::RETRY) {
+                // some argument of this thread was outside the fast path's domain: drop the
+                // tile's sums and redo the tile with the general code (per thread; no barrier inside)
+                careful = K::needs_retry(worst);
+                if (careful) {
+#pragma unroll
+                    for (int t = 0; t < T; ++t)
+#pragma unroll
+                        for (int a = 0; a < NA; ++a) acc[t][a] = 0.0;
+                }
+            }
+        }
+        if (careful) {
 #pragma unroll 1
             for (int j = 0; j < TS; ++j) {
                 double s[NS];
@@ -325,14 +324,44 @@ ds_kernel(const typename K::Params prm, const DsGeom g, const double* __restrict
                 *r = __dadd_rn(*r, acc[t][a]);
                 acc[t][a] = 0.0;
             }
-        __syncthreads();    // everyone is done with tile[st]
-        const int after = next_tile(nxt + 1);       // refill this stage with the tile after `nxt`
-        if (tid == 0 && nxt < ntiles && after < ntiles) {
-            mbar_expect_tx(&full[st], kTileBytes);
-            tma_bulk_g2s(tile[st], src + (size_t)(s0 + after * TS) * NS, kTileBytes, &full[st]);
+    };
+    auto load_tile = [&](const int k, const int st) {      // thread 0 only
+        mbar_expect_tx(&full[st], kTileBytes);
+        tma_bulk_g2s(tile[st], src + (size_t)(s0 + k * TS) * NS, kTileBytes, &full[st]);
+    };
+
+    if (!cull) {
+        // every tile, in order: two-stage pipeline
+        if (tid == 0) {
+#pragma unroll
+            for (int s = 0; s < 2; ++s)
+                if (s < ntiles) load_tile(s, s);
         }
-        cur = nxt;
-        nxt = (nxt < ntiles) ? after : ntiles;
+        for (int k = 0; k < ntiles; ++k) {
+            const int st = k & 1;
+            mbar_wait(&full[st], (k >> 1) & 1);
+            do_tile(k, st);
+            __syncthreads();    // everyone is done with tile[st]
+            if (tid == 0 && k + 2 < ntiles) load_tile(k + 2, st);
+        }
+    } else {
+        // only the tiles named in `need`, same pipeline
+        int cur = next_tile(0);
+        int nxt = next_tile(cur + 1);
+        if (tid == 0) {
+            if (cur < ntiles) load_tile(cur, 0);
+            if (nxt < ntiles) load_tile(nxt, 1);
+        }
+        for (int it = 0; cur < ntiles; ++it) {
+            const int st = it & 1;
+            mbar_wait(&full[st], (it >> 1) & 1);
+            do_tile(cur, st);
+            __syncthreads();
+            const int after = next_tile(nxt + 1);       // refill this stage with the tile after `nxt`
+            if (tid == 0 && nxt < ntiles && after < ntiles) load_tile(after, st);
+            cur = nxt;
+            nxt = (nxt < ntiles) ? after : ntiles;
+        }
     }
 
 #pragma unroll

@@ -70,7 +70,7 @@ struct OpBveStream {
         p.R2 = a.sc[0] * a.sc[0];
         return p;
     }
-    static int variant() { return 0; }
+    static int variant() { return rt().bve_variant >= 100 ? rt().bve_variant : 0; }
 };
 
 // ---- planar velocity / stream: in = x y vort area

@@ -90,6 +90,7 @@ __device__ __forceinline__ void rcp_batch(const double (&d)[T], double (&r)[T])
 struct NoCull {
     static constexpr bool CULL = false;
     static constexpr int CULL_GEOM = 0;
+    static constexpr bool RETRY = false;     // no group_fast(); see LogSharedTable
 };
 
 // Kernels without a per-CTA shared table.
@@ -149,6 +150,12 @@ template <int WB>     // WB: binades in the shared-memory window
 struct LogSharedTable : NoCull {
     static constexpr int KS = WB * kLogBin;
     static constexpr int WINDOW_BINADES = WB;
+    // The unchecked tile loop calls group_fast(), which has no slow path (so no call, no
+    // branch): it records the worst table offset it saw, and ds_kernel re-runs the tile
+    // through group<T, true>() -- which has the library-log() path -- if any was outside the window.
+    static constexpr bool RETRY = true;
+    static_assert((KS & (KS - 1)) == 0, "the fast path wraps table offsets with a mask");
+    __device__ static __forceinline__ bool needs_retry(unsigned worst) { return worst >= (unsigned)(KS * 8); }
     template <class Params>
     __device__ static __forceinline__ int32_t init_shared(double* ks, const Params& p, int tid, int nthreads)
     {
@@ -239,6 +246,38 @@ __device__ __forceinline__ void log_group(const double (&d)[T], double (&l)[T], 
     }
 }
 
+// The same without the branch: `worst` collects the largest byte offset into the window
+// (as unsigned: negative, zero, NaN and out-of-window arguments all give >= 8 KS); offsets
+// are wrapped into the table so that the load is always legal, and the caller discards the
+// tile's sums when needs_retry(worst).
+template <int KS, int T>
+__device__ __forceinline__ void log_group_fast(const double (&d)[T], double (&l)[T], unsigned& worst,
+                                               const SharedCtx& sc)
+{
+    // Written "vertically" (one Horner step of all T chains, then the next) because ptxas keeps
+    // close to source order: a chain-by-chain version came out with back-to-back dependent
+    // DFMAs and stalled on their latency (ncu: `wait` the top stall, FP64 pipe 62 %).
+    double r[T], p[T], tk[T];
+#pragma unroll
+    for (int k = 0; k < T; ++k) {
+        const int hi = __double2hiint(d[k]);
+        const unsigned u = (unsigned)((hi >> (17 - kLogBits)) - sc.i0 * 8);
+        worst = max(worst, u);
+        tk[k] = *reinterpret_cast<const double*>(reinterpret_cast<const char*>(sc.ks) + (u & (KS * 8 - 8)));
+        r[k] = fma(d[k], log_bin_rcp(hi, sc.i1), -1.0);
+    }
+#pragma unroll
+    for (int k = 0; k < T; ++k) p[k] = fma(r[k], kLogC[0], kLogC[1]);
+#pragma unroll
+    for (int k = 0; k < T; ++k) p[k] = fma(r[k], p[k], kLogC[2]);
+#pragma unroll
+    for (int k = 0; k < T; ++k) p[k] = fma(r[k], p[k], kLogC[3]);
+#pragma unroll
+    for (int k = 0; k < T; ++k) p[k] = fma(r[k], p[k], 1.0);
+#pragma unroll
+    for (int k = 0; k < T; ++k) l[k] = fma(r[k], p[k], tk[k]);
+}
+
 // Default group(): one source against the thread's T targets, one pair at a time.
 #define LPM_DEFAULT_GROUP()                                                                              \
     template <int T, bool CHECK>                                                                         \
@@ -262,7 +301,40 @@ struct BveVelParams {
     Outs<3> out;
 };
 struct BveVelTgt { double x, y, z; };
-template <int RG>      // RG: reciprocals sharing one MUFU (1 = none, 2, 4)
+// Compile-time permutation of {0..3} number `idx` (0..23), factoradic.
+struct Perm4 { int v[4]; };
+__host__ __device__ constexpr Perm4 perm4(int idx)
+{
+    int pool[4] = {0, 1, 2, 3};
+    Perm4 p{};
+    int n = 4, div = 6;
+    for (int k = 0; k < 4; ++k) {
+        const int q = idx / div;
+        idx %= div;
+        p.v[k] = pool[q];
+        for (int m = q; m + 1 < n; ++m) pool[m] = pool[m + 1];
+        --n;
+        if (n > 1) div /= (n);
+        else div = 1;
+    }
+    return p;
+}
+
+// RG: reciprocals sharing one MUFU (1 = none, 2, 4).
+//
+// ORDER permutes INDEPENDENT statements of group() -- the arithmetic per pair is the same --
+// and selects how the four denominators are paired in the reciprocal's product tree.  It exists
+// because the FP64 pipe is limited by register-bank conflicts, not by the instruction count:
+// over 23 builds with identical instruction mixes, time = (FP64-bound time) + 0.5 cycle per DFMA
+// with two fresh operands in one bank + 1 cycle with three (R^2 = 0.62, intercept = the roofline;
+// tools/sass_banks.py, profiles/README.md), and ptxas' allocation changes with statement order.
+// tools/search_order.py scores orders with that model; the sweep on the GPU picks among the best.
+//   bits 0-4   target order of the denominator phase (perm4 index)
+//   bits 5-9   target order of the accumulation phase
+//   bit  10    denominator phase coordinate-major
+//   bits 11-12 accumulation phase: 0 target-major, 1 component-major, 2 target-major with components reversed
+//   bits 13-14 product-tree pairing: (0 1)(2 3), (0 2)(1 3), (0 3)(1 2)        [T = 4 only]
+template <int RG, int ORDER = 0>
 struct BveVelT : NoSharedTable {
     static constexpr int NS = 6, NA = 3;
     static constexpr bool SKIP_SELF = true;
@@ -272,19 +344,44 @@ struct BveVelT : NoSharedTable {
     {
         return Tgt{p.x[i], p.y[i], p.z[i]};
     }
+    // k-th target of a phase: permuted within each aligned group of four
+    __host__ __device__ static constexpr int pick(int pidx, int k) { return (k & ~3) | perm4(pidx).v[k & 3]; }
     template <int T, bool CHECK>
     __device__ static __forceinline__ void group(const Params& p, const Tgt (&t)[T], const double (&s)[NS],
                                                  double (&acc)[T][NA], int32_t j, const int32_t (&self)[T], const SharedCtx&)
     {
+        constexpr int PD = (T % 4 == 0) ? (ORDER & 31) % 24 : 0, PA = (T % 4 == 0) ? ((ORDER >> 5) & 31) % 24 : 0;
+        constexpr int DN = (ORDER >> 10) & 1, AN = (ORDER >> 11) & 3, PT = ((ORDER >> 13) & 3) % 3;
         double d[T], r[T];
+        if constexpr (DN == 0) {
 #pragma unroll
-        for (int k = 0; k < T; ++k) {
-            d[k] = fma(-t[k].x, s[0], p.R2);
-            d[k] = fma(-t[k].y, s[1], d[k]);
-            d[k] = fma(-t[k].z, s[2], d[k]);
-            if (CHECK) d[k] = (j == self[k]) ? 1.0 : d[k];     // keep the self pair out of the shared product
+            for (int q = 0; q < T; ++q) {
+                const int k = pick(PD, q);
+                d[k] = fma(-t[k].x, s[0], p.R2);
+                d[k] = fma(-t[k].y, s[1], d[k]);
+                d[k] = fma(-t[k].z, s[2], d[k]);
+            }
+        } else {        // coordinate by coordinate
+#pragma unroll
+            for (int q = 0; q < T; ++q) { const int k = pick(PD, q); d[k] = fma(-t[k].x, s[0], p.R2); }
+#pragma unroll
+            for (int q = 0; q < T; ++q) { const int k = pick(PD, q); d[k] = fma(-t[k].y, s[1], d[k]); }
+#pragma unroll
+            for (int q = 0; q < T; ++q) { const int k = pick(PD, q); d[k] = fma(-t[k].z, s[2], d[k]); }
         }
-        if constexpr (RG >= 4 || T < 2) {
+        if (CHECK) {
+#pragma unroll
+            for (int k = 0; k < T; ++k) d[k] = (j == self[k]) ? 1.0 : d[k];     // keep the self pair out of the shared product
+        }
+        if constexpr (RG >= 4 && T == 4) {
+            // rcp_batch<4> with the pairing chosen by PT
+            constexpr int a0 = 0, a1 = (PT == 0) ? 1 : (PT == 1) ? 2 : 3;
+            constexpr int b0 = (PT == 0) ? 2 : 1, b1 = (PT == 2) ? 2 : 3;
+            const double pa = d[a0] * d[a1], pb = d[b0] * d[b1];
+            const double q = rcp_fast(pa * pb);
+            const double qa = q * pb, qb = q * pa;
+            r[a0] = qa * d[a1]; r[a1] = qa * d[a0]; r[b0] = qb * d[b1]; r[b1] = qb * d[b0];
+        } else if constexpr (RG >= 4 || T < 2) {
             rcp_batch<T>(d, r);
         } else if constexpr (RG == 2 && T % 2 == 0) {
 #pragma unroll
@@ -297,12 +394,31 @@ struct BveVelT : NoSharedTable {
 #pragma unroll
             for (int k = 0; k < T; ++k) r[k] = rcp_fast(d[k]);
         }
+        if (CHECK) {
 #pragma unroll
-        for (int k = 0; k < T; ++k) {
-            if (CHECK) r[k] = (j == self[k]) ? 0.0 : r[k];
-            acc[k][0] = fma(r[k], s[3], acc[k][0]);
-            acc[k][1] = fma(r[k], s[4], acc[k][1]);
-            acc[k][2] = fma(r[k], s[5], acc[k][2]);
+            for (int k = 0; k < T; ++k) r[k] = (j == self[k]) ? 0.0 : r[k];
+        }
+        if constexpr (AN == 1) {      // component by component
+#pragma unroll
+            for (int a = 0; a < NA; ++a)
+#pragma unroll
+                for (int q = 0; q < T; ++q) { const int k = pick(PA, q); acc[k][a] = fma(r[k], s[3 + a], acc[k][a]); }
+        } else if constexpr (AN == 2) {
+#pragma unroll
+            for (int q = 0; q < T; ++q) {
+                const int k = pick(PA, q);
+                acc[k][2] = fma(r[k], s[5], acc[k][2]);
+                acc[k][1] = fma(r[k], s[4], acc[k][1]);
+                acc[k][0] = fma(r[k], s[3], acc[k][0]);
+            }
+        } else {
+#pragma unroll
+            for (int q = 0; q < T; ++q) {
+                const int k = pick(PA, q);
+                acc[k][0] = fma(r[k], s[3], acc[k][0]);
+                acc[k][1] = fma(r[k], s[4], acc[k][1]);
+                acc[k][2] = fma(r[k], s[5], acc[k][2]);
+            }
         }
     }
     __device__ static __forceinline__ void finalize(const Params& p, const Tgt& t, const double (&a)[NA], int64_t i)
@@ -366,6 +482,24 @@ struct BveStream : LogSharedTable<32> {
 #pragma unroll
         for (int k = 0; k < T; ++k) {
             if (CHECK) l[k] = (j == self[k]) ? 0.0 : l[k];      // exactly, whatever the table gives for log(1)
+            acc[k][0] = fma(l[k], s[3], acc[k][0]);
+            acc[k][1] = fma(l[k], s[4], acc[k][1]);
+        }
+    }
+    template <int T>
+    __device__ static __forceinline__ void group_fast(const Params& p, const Tgt (&t)[T], const double (&s)[NS],
+                                                      double (&acc)[T][NA], unsigned& worst, const SharedCtx& sc)
+    {
+        double d[T], l[T];
+#pragma unroll
+        for (int k = 0; k < T; ++k) {
+            d[k] = fma(-t[k].x, s[0], p.R2);
+            d[k] = fma(-t[k].y, s[1], d[k]);
+            d[k] = fma(-t[k].z, s[2], d[k]);
+        }
+        log_group_fast<KS, T>(d, l, worst, sc);
+#pragma unroll
+        for (int k = 0; k < T; ++k) {
             acc[k][0] = fma(l[k], s[3], acc[k][0]);
             acc[k][1] = fma(l[k], s[4], acc[k][1]);
         }
@@ -489,6 +623,20 @@ struct PlaneStream : LogSharedTable<32> {
             acc[k][0] = fma(l[k], s[2], acc[k][0]);
         }
     }
+    template <int T>
+    __device__ static __forceinline__ void group_fast(const Params&, const Tgt (&t)[T], const double (&s)[NS],
+                                                      double (&acc)[T][NA], unsigned& worst, const SharedCtx& sc)
+    {
+        double r2[T], l[T];
+#pragma unroll
+        for (int k = 0; k < T; ++k) {
+            double dx = t[k].x - s[0], dy = t[k].y - s[1];
+            r2[k] = fma(dx, dx, dy * dy);
+        }
+        log_group_fast<KS, T>(r2, l, worst, sc);
+#pragma unroll
+        for (int k = 0; k < T; ++k) acc[k][0] = fma(l[k], s[2], acc[k][0]);
+    }
     __device__ static __forceinline__ void finalize(const Params& p, const Tgt&, const double (&a)[NA], int64_t i)
     {
         p.out.store(0, i, a[0]);
@@ -556,7 +704,7 @@ struct BetaVel : NoSharedTable {
 // Beta-plane stream functions.  src/BetaPlane.f90:409-431:
 //   g = log(cosh(2 pi dy) - cos(2 pi dx))/(4 pi) = log(2 (S^2 + s^2))/(4 pi)
 // Source record: sh, ch, sn, cs, zeta A/(4 pi), omega A/(4 pi).
-struct BetaStream : LogSharedTable<40> {
+struct BetaStream : LogSharedTable<32> {
     static constexpr int NS = 6, NA = 2;
     static constexpr bool SKIP_SELF = true;
     struct Params : LogParams {
@@ -587,6 +735,24 @@ struct BetaStream : LogSharedTable<40> {
 #pragma unroll
         for (int k = 0; k < T; ++k) {
             if (CHECK) l[k] = (j == self[k]) ? 0.0 : l[k];
+            acc[k][0] = fma(l[k], s[4], acc[k][0]);
+            acc[k][1] = fma(l[k], s[5], acc[k][1]);
+        }
+    }
+    template <int T>
+    __device__ static __forceinline__ void group_fast(const Params&, const Tgt (&t)[T], const double (&s)[NS],
+                                                      double (&acc)[T][NA], unsigned& worst, const SharedCtx& sc)
+    {
+        double den[T], l[T];
+#pragma unroll
+        for (int k = 0; k < T; ++k) {
+            double S = fma(t[k].sh, s[1], -(t[k].ch * s[0]));
+            double sn = fma(t[k].sn, s[3], -(t[k].cs * s[2]));
+            den[k] = 2.0 * fma(S, S, sn * sn);
+        }
+        log_group_fast<KS, T>(den, l, worst, sc);
+#pragma unroll
+        for (int k = 0; k < T; ++k) {
             acc[k][0] = fma(l[k], s[4], acc[k][0]);
             acc[k][1] = fma(l[k], s[5], acc[k][1]);
         }

@@ -171,7 +171,7 @@ inline int build_mask_plan(cudaStream_t st, int64_t n, const int32_t* mask_dev, 
 }
 
 // ---------------------------------------------------------------- launcher
-template <class K, int T, int BLOCK, int U>
+template <class K, int T, int BLOCK, int U, int MINB = 1>
 inline void launch_ds(cudaStream_t st, const typename K::Params& prm, DsGeom g, const double* src,
                       const int32_t* scan, double* partial)
 {
@@ -186,11 +186,11 @@ inline void launch_ds(cudaStream_t st, const typename K::Params& prm, DsGeom g, 
         int devid = 0;
         cudaGetDevice(&devid);
         if (devid < 0 || devid >= 64 || !configured[devid]) {
-            cudaFuncSetAttribute(ds_kernel<K, T, BLOCK, U>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            cudaFuncSetAttribute(ds_kernel<K, T, BLOCK, U, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
             if (devid >= 0 && devid < 64) configured[devid] = true;
         }
     }
-    ds_kernel<K, T, BLOCK, U><<<(unsigned)grid, BLOCK, smem, st>>>(prm, g, src, scan, partial);
+    ds_kernel<K, T, BLOCK, U, MINB><<<(unsigned)grid, BLOCK, smem, st>>>(prm, g, src, scan, partial);
 }
 
 // variant: 0 = automatic choice of targets-per-thread by problem size.
@@ -294,14 +294,19 @@ template <class K>
 inline int launch_variant(int variant, cudaStream_t st, const typename K::Params& prm, const DsGeom& g,
                           const double* src, const int32_t* scan, double* partial, int sm_count)
 {
-    (void)variant;
     if constexpr (K::KS > 0) {
-        // log kernels carry a 64-80 KB table per CTA: 256 threads share it
+        // Log kernels carry a 64 KB table per CTA: 256 threads share it and two CTAs fit an SM.
+        // __launch_bounds__(256, 2) tells ptxas it may spend up to 128 registers; it then keeps the
+        // T x U independent log chains interleaved (>= 4 FP64 instructions between producer and
+        // consumer).  With its default target of ~80 registers it emitted each chain back to back
+        // and the kernel stalled on DFMA latency (ncu: FP64 pipe 62 %, top stall `wait`).
         int T = auto_T(g.nall, g.nchunks, sm_count, 256);
+        if (variant == 102) T = 102;
         switch (T) {
-            case 4: launch_ds<K, 4, 256, 2>(st, prm, g, src, scan, partial); break;
-            case 2: launch_ds<K, 2, 256, 2>(st, prm, g, src, scan, partial); break;
-            default: launch_ds<K, 1, 256, 2>(st, prm, g, src, scan, partial); break;
+            case 102: launch_ds<K, 4, 384, 2, 2>(st, prm, g, src, scan, partial); break;    // A/B: 24 warps, 80 registers
+            case 4: launch_ds<K, 4, 256, 2, 2>(st, prm, g, src, scan, partial); break;
+            case 2: launch_ds<K, 2, 256, 2, 2>(st, prm, g, src, scan, partial); break;
+            default: launch_ds<K, 1, 256, 2, 2>(st, prm, g, src, scan, partial); break;
         }
     } else {
         int T = auto_T(g.nall, g.nchunks, sm_count, 128);
@@ -320,9 +325,19 @@ inline int launch_variant<BveVel>(int variant, cudaStream_t st, const BveVel::Pa
                                   const double* src, const int32_t* scan, double* partial, int sm_count)
 {
     using K = BveVel;
+    if (variant >= 100) variant = 0;      // >= 100: A/B shapes of the stream-function kernels
     if (variant == 0) {
-        int T = auto_T(g.nall, g.nchunks, sm_count, 128);
-        variant = (T == 4) ? 1 : (T == 2) ? 5 : 6;
+        // 8 targets per thread (3 CTAs of 128 threads per SM) when that still leaves >= 8 waves of
+        // CTAs, else 4 (5 CTAs per SM), 2, 1.  The statement orders (BveVelT<4, ORDER>) are the
+        // ones tools/search_order.py + tools/sweep_bve.py measured fastest: at icosTri 8,
+        // T = 8 / ORDER 3680: 1412 ms;  T = 4 / ORDER 10765: 1441 ms;  T = 4 / ORDER 0: 1499 ms.
+        const int64_t items8 = (g.nall + 128 * 8 - 1) / (128 * 8) * g.nchunks;
+        if (items8 >= 8LL * 3 * sm_count) {
+            variant = 41;
+        } else {
+            int T = auto_T(g.nall, g.nchunks, sm_count, 128);
+            variant = (T == 4) ? 32 : (T == 2) ? 5 : 6;
+        }
     }
     switch (variant) {
         case 1: launch_ds<K, 4, 128, 2>(st, prm, g, src, scan, partial); break;
@@ -341,6 +356,25 @@ inline int launch_variant<BveVel>(int variant, cudaStream_t st, const BveVel::Pa
         case 13: launch_ds<K, 8, 128, 2>(st, prm, g, src, scan, partial); break;
         case 14: launch_ds<K, 4, 128, 1>(st, prm, g, src, scan, partial); break;
         case 15: launch_ds<K, 4, 192, 2>(st, prm, g, src, scan, partial); break;
+        // register budgets stated to ptxas (__launch_bounds__ min CTAs): it schedules for ILP within the budget
+        case 16: launch_ds<K, 4, 128, 2, 4>(st, prm, g, src, scan, partial); break;
+        case 17: launch_ds<K, 4, 128, 4, 4>(st, prm, g, src, scan, partial); break;
+        case 18: launch_ds<K, 4, 256, 2, 2>(st, prm, g, src, scan, partial); break;
+        case 19: launch_ds<K, 8, 128, 2, 3>(st, prm, g, src, scan, partial); break;
+        case 20: launch_ds<K, 4, 128, 2, 5>(st, prm, g, src, scan, partial); break;
+        case 21: launch_ds<K, 4, 128, 2, 6>(st, prm, g, src, scan, partial); break;
+        // statement orders short-listed by tools/search_order.py (same arithmetic; see BveVelT in pairs.cuh)
+        case 31: launch_ds<BveVelT<4, 11713>, 4, 128, 2>(st, prm, g, src, scan, partial); break;
+        case 32: launch_ds<BveVelT<4, 10765>, 4, 128, 2>(st, prm, g, src, scan, partial); break;
+        case 33: launch_ds<BveVelT<4, 2319>, 4, 128, 2>(st, prm, g, src, scan, partial); break;
+        case 34: launch_ds<BveVelT<4, 10593>, 4, 128, 2>(st, prm, g, src, scan, partial); break;
+        case 41: launch_ds<BveVelT<4, 3680>, 8, 128, 2>(st, prm, g, src, scan, partial); break;
+        case 42: launch_ds<BveVelT<4, 3310>, 8, 128, 2>(st, prm, g, src, scan, partial); break;
+        case 43: launch_ds<BveVelT<4, 3744>, 8, 128, 2>(st, prm, g, src, scan, partial); break;
+        case 44: launch_ds<BveVelT<4, 11873>, 8, 128, 2>(st, prm, g, src, scan, partial); break;
+        case 51: launch_ds<BveVelT<4, 13935>, 8, 128, 1>(st, prm, g, src, scan, partial); break;
+        case 52: launch_ds<BveVelT<4, 21167>, 8, 128, 1>(st, prm, g, src, scan, partial); break;
+        case 53: launch_ds<BveVelT<4, 20624>, 8, 128, 1>(st, prm, g, src, scan, partial); break;
         default: return set_error(LPM_ERR_INVALID, "unknown BVE kernel variant %d", variant);
     }
     return LPM_OK;

@@ -1,7 +1,7 @@
 #!/bin/bash
 # Opcode histogram of the hottest loop (the last backward-branch loop containing the most FP64 ops)
-# usage: tools/sass_loop.sh <mangled-name-substring>
-so="$(dirname "$0")/../lpm_v2_b200/liblpmgpu.so"
+# usage: tools/sass_loop.sh <mangled-name-substring> [file.so|file.cubin]
+so="${2:-$(dirname "$0")/../lpm_v2_b200/liblpmgpu.so}"
 cuobjdump -sass "$so" | awk -v pat="$1" '
 /Function :/ { on = index($0, pat) > 0 }
 on && /\/\*[0-9a-f]{4}\*\// { print }' | grep -v "^\s*/\* 0x" | sed 's#/\* 0x[0-9a-f]* \*/##' > /tmp/_fn.sass
