@@ -257,6 +257,9 @@ int lpm_fp64_peak_probe(int iters, double* tflops, double* ms);
  * the launching stream), and the number of kernel launches the library has
  * issued since lpm_gpu_init / the last call with reset != 0. */
 int lpm_last_kernel_ms(double* ms);
+/* Device time (ms) of the last one-shot direct sum as a whole on this device: source packing,
+ * the cell sort of the PSE kernels, the main kernel, finalize and scatter (no host copies). */
+int lpm_last_sum_ms(double* ms);
 /* Sum of the durations (ms) and count of the direct-sum main kernels recorded on the
  * current device since the last reset (profiling must be on). */
 int lpm_profile_summary(int reset, int64_t* nkernels, double* total_ms);
@@ -265,9 +268,12 @@ int64_t lpm_launch_count(int reset);
 int lpm_set_profiling(int enable);
 /* Tuning knob for benchmarks: select the BVE kernel variant. */
 int lpm_set_bve_variant(int variant);
-/* A/B switch for tests and benchmarks: 0 disables the tile culling of the compactly
- * supported PSE kernels (every tile is then visited; results are bit-identical). Default 1. */
-int lpm_set_pse_culling(int enable);
+/* Evaluation order of the compactly supported PSE kernels (tests and benchmarks):
+ *   0  reference order (j = 1..N over the active particles), every source tile visited;
+ *   1  sources and targets in cell (Morton) order, tiles out of reach skipped (default);
+ *   2  cell order, every tile visited -- bit-identical to mode 1.
+ * Modes 1/2 differ from mode 0 by summation order only (~1e-16 relative). */
+int lpm_set_pse_culling(int mode);
 
 /* ------------------------------------------------------ mesh (host only) */
 

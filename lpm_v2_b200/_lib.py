@@ -95,6 +95,7 @@ PROTOTYPES = {
     # measurement
     "lpm_fp64_peak_probe": (_int, [_int, _d, _d]),
     "lpm_last_kernel_ms": (_int, [_d]),
+    "lpm_last_sum_ms": (_int, [_d]),
     "lpm_profile_summary": (_int, [_int, _i64, _d]),
     "lpm_launch_count": (C.c_int64, [_int]),
     "lpm_set_profiling": (_int, [_int]),

@@ -167,13 +167,21 @@ def set_bve_variant(v):
     check(lib.lpm_set_bve_variant(int(v)))
 
 
-def set_pse_culling(on):
-    check(lib.lpm_set_pse_culling(1 if on else 0))
+def set_pse_culling(mode):
+    """0: reference order, no culling; 1 (default): cell order + tile culling; 2: cell order only."""
+    check(lib.lpm_set_pse_culling(int(mode)))
 
 
 def last_kernel_ms():
     ms = C.c_double(0)
     check(lib.lpm_last_kernel_ms(C.byref(ms)))
+    return ms.value
+
+
+def last_sum_ms():
+    """Device time of the last one-shot direct sum as a whole (pack, sort, kernels; no host copies)."""
+    ms = C.c_double(0)
+    check(lib.lpm_last_sum_ms(C.byref(ms)))
     return ms.value
 
 

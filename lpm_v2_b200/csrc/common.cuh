@@ -88,10 +88,17 @@ struct Workspace {
     DevBuf staging[16]; // host API: device copies of the caller's arrays (0-7 in, 8 mask, 9-11 out, 12-14 targets)
     DevBuf reduce;      // small reduction scratch
     DevBuf logwin;      // int32 [2]: max |coordinate| high word, window origin of the log table (pairs.cuh)
+    // spatially sorted PSE evaluation (sorted.cuh)
+    DevBuf sort_tmp, sort_keys[2], sort_vals[2], sorted_active, sorted_targets, gathered[8], sorted_out[4];
     void release()
     {
         plan.release(); sources.release(); partial.release(); bounds.release();
         reduce.release(); logwin.release();
+        sort_tmp.release(); sorted_active.release(); sorted_targets.release();
+        for (auto& s : sort_keys) s.release();
+        for (auto& s : sort_vals) s.release();
+        for (auto& s : gathered) s.release();
+        for (auto& s : sorted_out) s.release();
         for (auto& s : staging) s.release();
     }
 };
@@ -102,6 +109,7 @@ struct Device {
     const double* logtab = nullptr;      // this device's g_log_full (pairs.cuh)
     cudaStream_t stream = nullptr;       // library-owned stream (host API, resident solvers)
     cudaEvent_t ev_done = nullptr;       // cross-device barrier (resident solvers)
+    cudaEvent_t ev_sum[2] = {nullptr, nullptr};   // profiling: around the last whole direct sum (pack, sort, kernels)
     // profiling: one event pair per direct-sum main kernel since the last reset
     std::vector<std::pair<cudaEvent_t, cudaEvent_t>> prof;
     size_t prof_used = 0;
@@ -126,7 +134,7 @@ struct Runtime {
     bool profiling = false;
     int64_t launches = 0;
     int bve_variant = 0;
-    bool pse_culling = true;             // A/B switch for the PSE tile culling (lpm_set_pse_culling)
+    int pse_culling = 1;                 // PSE kernels: 0 reference order, every tile; 1 cell order + tile culling; 2 cell order only
     // NCCL (rank mode)
     void* nccl_lib = nullptr;
     void* comm = nullptr;

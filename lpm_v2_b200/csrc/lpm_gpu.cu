@@ -5,6 +5,7 @@
 // Device API: one slice on the current device / given stream (rank mode).
 #include "runtime.cuh"
 #include "ops.cuh"
+#include "sorted.cuh"
 #include "solvers.cuh"
 
 using namespace lpm;
@@ -100,6 +101,7 @@ extern "C" int lpm_gpu_finalize(void)
         cudaStreamSynchronize(d.stream);
         d.ws.release();
         cudaEventDestroy(d.ev_done);
+        for (auto& e : d.ev_sum) { if (e) cudaEventDestroy(e); e = nullptr; }
         for (auto& pr : d.prof) { cudaEventDestroy(pr.first); cudaEventDestroy(pr.second); }
         d.prof.clear(); d.prof_used = 0;
         cudaStreamDestroy(d.stream);
@@ -173,7 +175,12 @@ extern "C" int lpm_load_balance(int64_t n_items, int nprocs, int64_t* index_star
 
 extern "C" int lpm_set_profiling(int enable) { rt().profiling = enable != 0; return LPM_OK; }
 extern "C" int lpm_set_bve_variant(int variant) { rt().bve_variant = variant; return LPM_OK; }
-extern "C" int lpm_set_pse_culling(int enable) { rt().pse_culling = enable != 0; return LPM_OK; }
+extern "C" int lpm_set_pse_culling(int mode)
+{
+    if (mode < 0 || mode > 2) return set_error(LPM_ERR_INVALID, "lpm_set_pse_culling(%d): mode must be 0, 1 or 2", mode);
+    rt().pse_culling = mode;
+    return LPM_OK;
+}
 extern "C" int64_t lpm_launch_count(int reset)
 {
     int64_t v = rt().launches;
@@ -189,6 +196,17 @@ extern "C" int lpm_last_kernel_ms(double* ms)
     LPM_CUDA(cudaEventSynchronize(pr.second));
     float f = 0;
     LPM_CUDA(cudaEventElapsedTime(&f, pr.first, pr.second));
+    *ms = f;
+    return LPM_OK;
+}
+extern "C" int lpm_last_sum_ms(double* ms)
+{
+    Device* d = nullptr;
+    LPM_TRY(current_device(&d));
+    if (!d->ev_sum[1]) return set_error(LPM_ERR_INVALID, "no timed direct sum (lpm_set_profiling(1) first)");
+    LPM_CUDA(cudaEventSynchronize(d->ev_sum[1]));
+    float f = 0;
+    LPM_CUDA(cudaEventElapsedTime(&f, d->ev_sum[0], d->ev_sum[1]));
     *ms = f;
     return LPM_OK;
 }
@@ -293,10 +311,7 @@ int run_dev(const Args& a, int64_t ibeg, int64_t iend, double* const* out, void*
     cudaStream_t st = (cudaStream_t)stream;
     MaskPlan& mp = dev->ws.plan;        // rebuilt per call; buffers reused
     LPM_TRY(build_mask_plan(st, a.n, a.mask, mp));
-    LPM_TRY(Op::pack(*dev, st, mp, a));
-    typename Op::K::Params prm = Op::params(a);
-    set_outs(prm.out, out);
-    return direct_sum<typename Op::K>(*dev, st, mp, ibeg, iend, prm, Op::variant());
+    return evaluate<Op>(*dev, st, mp, a, ibeg, iend, a.n, out);
 }
 
 // Host API body: every claimed device (single-process mode) or this rank's
@@ -348,12 +363,9 @@ int run_host(const Args& host, double* const* out_host)
                 out[k] = ob.as<double>();
             }
             LPM_TRY(build_mask_plan(dev.stream, n, a.mask, dev.ws.plan));
-            LPM_TRY(Op::pack(dev, dev.stream, dev.ws.plan, a));
-            typename Op::K::Params prm = Op::params(a);
-            set_outs(prm.out, out);
             int64_t b, e;
             load_balance0(nt, nparts, R.rank_mode ? R.rank : (int)g, &b, &e);
-            LPM_TRY(direct_sum<typename Op::K>(dev, dev.stream, dev.ws.plan, b, e, prm, Op::variant(), nt));
+            LPM_TRY(evaluate<Op>(dev, dev.stream, dev.ws.plan, a, b, e, nt, out));
             if (R.rank_mode) {
                 LPM_TRY(allgather_slices(Op::NOUT, out, nt, dev.stream));
                 b = 0; e = nt;

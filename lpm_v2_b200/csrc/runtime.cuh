@@ -224,7 +224,7 @@ inline int direct_sum(Device& dev, cudaStream_t st, const MaskPlan& mp, int64_t 
         tile_bounds_kernel<K::NS, K::CULL_GEOM><<<ntiles, 256, 0, st>>>(g.nsrc, dev.ws.sources.as<double>(),
                                                                        dev.ws.bounds.as<double>());
         count_launch();
-        g.bounds = rt().pse_culling ? dev.ws.bounds.as<double>() : nullptr;
+        g.bounds = rt().pse_culling == 1 ? dev.ws.bounds.as<double>() : nullptr;
     }
     typename K::Params prm2 = prm;
     if constexpr (K::KS > 0) {      // log kernels: this device's table, and the window the caller's pack() computed

@@ -93,12 +93,27 @@ def test_plane_operators(gpu, oracle, get_mesh, L, power):
                   oracle.pse_interpolate(q.x, q.y, None, f, q.area, q.is_active, eps, tx, ty)) <= TOL
 
 
+def _three_orders(gpu, run):
+    """run() under the three evaluation modes of the PSE kernels (lpm_set_pse_culling)."""
+    res = {}
+    try:
+        for mode in (0, 2, 1):
+            gpu.set_pse_culling(mode)
+            res[mode] = run()
+    finally:
+        gpu.set_pse_culling(1)
+    return res
+
+
 @pytest.mark.parametrize("seed,L,power", [(M.ICOS_TRI_SPHERE_SEED, 6, 0.75), (M.ICOS_TRI_SPHERE_SEED, 5, 1.5),
                                           (M.CUBED_SPHERE_SEED, 5, 0.75)])
-def test_tile_culling_is_bit_identical_sphere(gpu, oracle, get_mesh, seed, L, power):
-    """Tile culling (directsum.cuh) only skips source tiles whose every pair the per-pair
-    cut-off rejects, so switching it off must not change a single bit; a sample of targets is
-    also checked against the oracle (which evaluates every pair, as the reference does)."""
+def test_cell_order_and_tile_culling_sphere(gpu, oracle, get_mesh, seed, L, power):
+    """The PSE kernels evaluate sources and targets in cell (Morton) order and skip source
+    tiles out of reach of a target block (sorted.cuh, directsum.cuh).  Culling only drops
+    tiles whose every pair the per-pair cut-off rejects: switching it off (mode 2) must not
+    change a single bit.  The reorder changes the summation order only: the reference order
+    (mode 0) agrees to ~1e-15.  A sample of targets is checked against the oracle, which
+    evaluates every pair in the reference's order."""
     m = get_mesh(seed, L)
     eps = m.max_edge_length ** power
     f = problems.spherical_harmonic54(m)
@@ -109,37 +124,35 @@ def test_tile_culling_is_bit_identical_sphere(gpu, oracle, get_mesh, seed, L, po
         return [gpu.pse_laplacian_sphere(*args, f, m.area, m.is_active, eps, 1.0),
                 *gpu.pse_gradient_sphere(*args, f, m.area, m.is_active, eps),
                 gpu.pse_divergence_sphere(*args, u, v, w, m.area, m.is_active, eps),
+                gpu.pse_double_dot_sphere(*args, u, v, w, m.area, m.is_active, eps),
                 gpu.pse_interpolate_sphere(*args, f, m.area, m.is_active, eps, m.x[::7], m.y[::7], m.z[::7])]
-    try:
-        gpu.set_pse_culling(False)
-        plain = run()
-    finally:
-        gpu.set_pse_culling(True)
-    culled = run()
-    for a, b in zip(plain, culled):
+    res = _three_orders(gpu, run)
+    for a, b, c in zip(res[2], res[1], res[0]):
         assert np.array_equal(a, b)
+        assert relerr(b, c) <= 1e-13
     rng = np.random.default_rng(L)
     idx = np.concatenate([[0, 1, 12, m.n - 1], rng.integers(0, m.n, 28)])
-    lap = culled[0]
+    lap = res[1][0]
     scale = np.abs(lap).max()
     for i in idx:
         want = oracle.pse_laplacian_sphere(*args, f, m.area, m.is_active, eps, 1.0, rng=(int(i), int(i) + 1))
         assert abs(lap[i] - want[i]) <= TOL * scale
 
 
-def test_tile_culling_is_bit_identical_plane(gpu, get_mesh):
+def test_cell_order_and_tile_culling_plane(gpu, get_mesh):
     q = get_mesh(M.QUAD_RECT_SEED, 7, 2.0)
     eps = q.max_edge_length ** 0.75
     f = np.sin(1.3 * q.x) * np.cos(0.7 * q.y) + 0.1 * q.x * q.y
+    rng = np.random.default_rng(3)
+    tx, ty = rng.uniform(-2, 2, 5001), rng.uniform(-2, 2, 5001)
 
     def run():
         return [gpu.pse_laplacian_plane(q.x, q.y, f, q.area, q.is_active, eps),
                 *gpu.pse_gradient_plane(q.x, q.y, f, q.area, q.is_active, eps),
-                gpu.pse_double_dot_plane(q.x, q.y, q.y ** 2 - q.x, q.x * q.y, q.area, q.is_active, eps)]
-    try:
-        gpu.set_pse_culling(False)
-        plain = run()
-    finally:
-        gpu.set_pse_culling(True)
-    for a, b in zip(plain, run()):
+                *gpu.pse_second_partials_plane(q.x, q.y, q.y ** 2 - q.x, q.x * q.y, q.area, q.is_active, eps),
+                gpu.pse_double_dot_plane(q.x, q.y, q.y ** 2 - q.x, q.x * q.y, q.area, q.is_active, eps),
+                gpu.pse_interpolate_plane(q.x, q.y, f, q.area, q.is_active, eps, tx, ty)]
+    res = _three_orders(gpu, run)
+    for a, b, c in zip(res[2], res[1], res[0]):
         assert np.array_equal(a, b)
+        assert relerr(b, c) <= 1e-13
