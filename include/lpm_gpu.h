@@ -77,6 +77,18 @@ int lpm_comm_rank(void);
  * lpm_load_balance; in place; ragged last slice allowed. */
 int lpm_comm_allgather_slices_dev(int ncomp, double* const* bufs, int64_t n, void* stream);
 
+/* Rank mode: device memory that every rank of the communicator can store into over NVLink
+ * (CUDA IPC mappings exchanged through the communicator).  COLLECTIVE: every rank calls with the
+ * same size, in the same order.  When ALL output arrays of a `_dev` direct sum lie inside such
+ * allocations (at the same offsets on every rank), the step that writes the results stores them
+ * into every rank's copy -- the reference's MPI_BCAST loop (e.g. src/SphereBVESolver.f90:422-429)
+ * fused into the sum as peer stores -- between two stream-ordered barriers; after the stream's
+ * work every rank holds all n results and lpm_comm_allgather_slices_dev is not needed.
+ * lpm_comm_is_shared tells whether [ptr, ptr + bytes) lies in a shared allocation (1 / 0). */
+int lpm_comm_alloc_shared(int64_t bytes, void** ptr);
+int lpm_comm_free_shared(void* ptr);
+int lpm_comm_is_shared(const void* ptr, int64_t bytes);
+
 /* Optional: page-lock host arrays the solver owns (at New), release at Delete. */
 int lpm_gpu_pin(void* ptr, int64_t bytes);
 int lpm_gpu_unpin(void* ptr);

@@ -98,6 +98,9 @@ PROTOTYPES = {
     "lpm_last_sum_ms": (_int, [_d]),
     "lpm_profile_summary": (_int, [_int, _i64, _d]),
     "lpm_launch_count": (C.c_int64, [_int]),
+    "lpm_comm_alloc_shared": (_int, [C.c_int64, C.POINTER(_vp)]),
+    "lpm_comm_free_shared": (_int, [_vp]),
+    "lpm_comm_is_shared": (_int, [_vp, C.c_int64]),
     "lpm_set_profiling": (_int, [_int]),
     "lpm_set_bve_variant": (_int, [_int]),
     "lpm_set_pse_culling": (_int, [_int]),

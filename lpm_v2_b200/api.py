@@ -61,6 +61,21 @@ def comm_init_rank(world, rank, uid):
     check(lib.lpm_comm_init_rank(int(world), int(rank), C.create_string_buffer(uid, 128)))
 
 
+def comm_alloc_shared(nbytes):
+    """COLLECTIVE (rank mode): device memory every rank can store into over NVLink; returns the address."""
+    p = C.c_void_p()
+    check(lib.lpm_comm_alloc_shared(int(nbytes), C.byref(p)))
+    return p.value
+
+
+def comm_free_shared(ptr):
+    check(lib.lpm_comm_free_shared(C.c_void_p(ptr)))
+
+
+def comm_is_shared(ptr, nbytes):
+    return bool(lib.lpm_comm_is_shared(C.c_void_p(ptr), int(nbytes)))
+
+
 def load_balance(n_items, nprocs):
     """MPISetup%indexStart/indexEnd/messageLength (1-based, inclusive)."""
     s = np.zeros(nprocs, np.int64)

@@ -80,6 +80,8 @@ struct MaskPlan {
     void release() { scan.release(); active.release(); blocksums.release(); }
 };
 
+struct SharedOut { void* p = nullptr; size_t cap = 0; };     // a shared slab used as output staging (rank mode)
+
 struct Workspace {
     MaskPlan plan;      // mask scan of the one-shot entry points (rebuilt per call, buffers reused)
     DevBuf sources;     // double [nsrc_pad * NS]
@@ -87,13 +89,16 @@ struct Workspace {
     DevBuf bounds;      // double [nsrc_pad / kTile][4]: bounding ball per source tile (PSE tile culling)
     DevBuf staging[16]; // host API: device copies of the caller's arrays (0-7 in, 8 mask, 9-11 out, 12-14 targets)
     DevBuf reduce;      // small reduction scratch
+    DevBuf barrier;     // rank-mode barrier / IPC handle exchange scratch
+    SharedOut shared_out[4];   // host API in rank mode: outputs staged where the peers can store (freed with the slabs)
     DevBuf logwin;      // int32 [2]: max |coordinate| high word, window origin of the log table (pairs.cuh)
     // spatially sorted PSE evaluation (sorted.cuh)
     DevBuf sort_tmp, sort_keys[2], sort_vals[2], sorted_active, sorted_targets, gathered[8], sorted_out[4];
     void release()
     {
         plan.release(); sources.release(); partial.release(); bounds.release();
-        reduce.release(); logwin.release();
+        reduce.release(); logwin.release(); barrier.release();
+        for (auto& so : shared_out) so = SharedOut{};      // the slabs themselves are freed by the runtime
         sort_tmp.release(); sorted_active.release(); sorted_targets.release();
         for (auto& s : sort_keys) s.release();
         for (auto& s : sort_vals) s.release();
@@ -127,6 +132,14 @@ struct Device {
     }
 };
 
+// Rank mode: a device buffer of this rank that every other rank has mapped with CUDA IPC
+// (lpm_comm_alloc_shared).  peer[r] is rank r's buffer as seen from this process; peer[rank] == local.
+struct SharedSlab {
+    char* local = nullptr;
+    size_t bytes = 0;
+    char* peer[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+};
+
 struct Runtime {
     bool initialised = false;
     bool rank_mode = false;              // one process per GPU (lpm_gpu_init_rank)
@@ -139,6 +152,7 @@ struct Runtime {
     void* nccl_lib = nullptr;
     void* comm = nullptr;
     int world = 1, rank = 0;
+    std::vector<SharedSlab> slabs;
 };
 
 inline Runtime& rt()

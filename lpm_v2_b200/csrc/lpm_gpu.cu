@@ -94,6 +94,7 @@ extern "C" int lpm_gpu_finalize(void)
 {
     Runtime& R = rt();
     if (!R.initialised) return LPM_OK;
+    while (!R.slabs.empty()) free_shared(R.slabs.back().local);
     if (R.comm && nccl().loaded) nccl().CommDestroy(R.comm);
     R.comm = nullptr;
     for (auto& d : R.devs) {
@@ -144,6 +145,21 @@ extern "C" int lpm_comm_allgather_slices_dev(int ncomp, double* const* bufs, int
 {
     LPM_TRY(require_init());
     return allgather_slices(ncomp, bufs, n, (cudaStream_t)stream);
+}
+
+extern "C" int lpm_comm_alloc_shared(int64_t bytes, void** ptr)
+{
+    if (!ptr || bytes <= 0) return set_error(LPM_ERR_INVALID, "lpm_comm_alloc_shared(%lld)", (long long)bytes);
+    return alloc_shared((size_t)bytes, ptr);
+}
+extern "C" int lpm_comm_free_shared(void* ptr)
+{
+    LPM_TRY(require_init());
+    return free_shared(ptr);
+}
+extern "C" int lpm_comm_is_shared(const void* ptr, int64_t bytes)
+{
+    return rt().initialised && ptr && bytes > 0 && find_slab(ptr, (size_t)bytes) != nullptr ? 1 : 0;
 }
 
 extern "C" int lpm_gpu_pin(void* ptr, int64_t bytes)
@@ -358,16 +374,31 @@ int run_host(const Args& host, double* const* out_host)
             double* out[4] = {nullptr, nullptr, nullptr, nullptr};
             static_assert(Op::NOUT <= 4 && Op::NIN <= 8, "staging layout");
             for (int k = 0; k < Op::NOUT; ++k) {      // outputs: staging 9-11, a 4th shares slot 15
-                DevBuf& ob = dev.ws.staging[k < 3 ? 9 + k : 15];
-                LPM_TRY(ob.reserve(ntb));
-                out[k] = ob.as<double>();
+                if (R.rank_mode && R.world > 1) {
+                    // rank mode: output staging lives in shared slabs (same sizes, same order on every
+                    // rank -- the host API is collective), so the slices are exchanged by peer stores
+                    SharedOut& so = dev.ws.shared_out[k];
+                    if (so.cap < ntb) {
+                        if (so.p) LPM_TRY(free_shared(so.p));
+                        so.p = nullptr; so.cap = 0;
+                        const size_t want = ntb + ntb / 8 + 256;
+                        LPM_TRY(alloc_shared(want, &so.p));
+                        so.cap = want;
+                    }
+                    out[k] = (double*)so.p;
+                } else {
+                    DevBuf& ob = dev.ws.staging[k < 3 ? 9 + k : 15];
+                    LPM_TRY(ob.reserve(ntb));
+                    out[k] = ob.as<double>();
+                }
             }
             LPM_TRY(build_mask_plan(dev.stream, n, a.mask, dev.ws.plan));
             int64_t b, e;
             load_balance0(nt, nparts, R.rank_mode ? R.rank : (int)g, &b, &e);
-            LPM_TRY(evaluate<Op>(dev, dev.stream, dev.ws.plan, a, b, e, nt, out));
+            bool exchanged = false;
+            LPM_TRY(evaluate<Op>(dev, dev.stream, dev.ws.plan, a, b, e, nt, out, &exchanged));
             if (R.rank_mode) {
-                LPM_TRY(allgather_slices(Op::NOUT, out, nt, dev.stream));
+                if (!exchanged) LPM_TRY(allgather_slices(Op::NOUT, out, nt, dev.stream));
                 b = 0; e = nt;
             }
             for (int k = 0; k < Op::NOUT; ++k)

@@ -80,6 +80,8 @@ struct NcclApi {
     int (*CommInitRank)(void**, int, UniqueId, int) = nullptr;
     int (*CommDestroy)(void*) = nullptr;
     int (*Broadcast)(const void*, void*, size_t, int, int, void*, cudaStream_t) = nullptr;
+    int (*AllGather)(const void*, void*, size_t, int, void*, cudaStream_t) = nullptr;
+    int (*AllReduce)(const void*, void*, size_t, int, int, void*, cudaStream_t) = nullptr;
     int (*GroupStart)() = nullptr;
     int (*GroupEnd)() = nullptr;
     const char* (*GetErrorString)(int) = nullptr;
@@ -106,6 +108,8 @@ inline int load_nccl()
     LPM_SYM(CommInitRank, "ncclCommInitRank");
     LPM_SYM(CommDestroy, "ncclCommDestroy");
     LPM_SYM(Broadcast, "ncclBroadcast");
+    LPM_SYM(AllGather, "ncclAllGather");
+    LPM_SYM(AllReduce, "ncclAllReduce");
     LPM_SYM(GroupStart, "ncclGroupStart");
     LPM_SYM(GroupEnd, "ncclGroupEnd");
     LPM_SYM(GetErrorString, "ncclGetErrorString");
@@ -145,6 +149,116 @@ inline int allgather_slices(int ncomp, double* const* bufs, int64_t n, cudaStrea
     }
     LPM_NCCL(nccl().GroupEnd());
     return LPM_OK;
+}
+
+// ---------------------------------------------------------------- shared slabs (rank mode)
+// Stream-ordered barrier across the ranks: a 4-byte all-reduce.  Work enqueued on `st` after it
+// starts only when every rank's work before its own call has finished.
+inline int comm_barrier(Device& dev, cudaStream_t st)
+{
+    Runtime& R = rt();
+    if (R.world <= 1) return LPM_OK;
+    if (!R.comm) return set_error(LPM_ERR_COMM, "world size %d but no communicator (lpm_comm_init_rank)", R.world);
+    LPM_TRY(dev.ws.barrier.reserve(64));
+    int32_t* b = dev.ws.barrier.as<int32_t>();
+    LPM_NCCL(nccl().AllReduce(b, b + 8, 1, /*ncclInt32*/ 2, /*ncclSum*/ 0, R.comm, st));
+    return LPM_OK;
+}
+
+// the slab that holds [p, p + bytes), or nullptr
+inline const SharedSlab* find_slab(const void* p, size_t bytes)
+{
+    const char* c = (const char*)p;
+    for (const auto& s : rt().slabs)
+        if (c >= s.local && c + bytes <= s.local + s.bytes) return &s;
+    return nullptr;
+}
+
+inline int alloc_shared(size_t bytes, void** out)
+{
+    Runtime& R = rt();
+    LPM_TRY(require_init());
+    if (!R.rank_mode) return set_error(LPM_ERR_INVALID, "lpm_comm_alloc_shared needs rank mode (lpm_gpu_init_rank)");
+    if (bytes == 0) return set_error(LPM_ERR_INVALID, "lpm_comm_alloc_shared(0)");
+    Device& dev = R.devs[0];
+    LPM_CUDA(cudaSetDevice(dev.id));
+    SharedSlab s;
+    s.bytes = bytes;
+    cudaError_t e = cudaMalloc((void**)&s.local, bytes);
+    if (e != cudaSuccess) return set_error(LPM_ERR_NOMEM, "cudaMalloc(%zu bytes) failed: %s", bytes, cudaGetErrorString(e));
+    s.peer[R.rank] = s.local;
+    if (R.world > 1) {
+        if (!R.comm) return set_error(LPM_ERR_COMM, "lpm_comm_alloc_shared before lpm_comm_init_rank");
+        if (R.world > 8) return set_error(LPM_ERR_INVALID, "at most 8 ranks");
+        // exchange the IPC handles with an all-gather of 64 bytes per rank
+        cudaIpcMemHandle_t mine, all[8];
+        static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+        LPM_CUDA(cudaIpcGetMemHandle(&mine, s.local));
+        LPM_TRY(dev.ws.barrier.reserve(64 + 9 * 64));
+        char* scratch = dev.ws.barrier.as<char>() + 64;
+        LPM_CUDA(cudaMemcpyAsync(scratch, &mine, 64, cudaMemcpyHostToDevice, dev.stream));
+        LPM_NCCL(nccl().AllGather(scratch, scratch + 64, 64, /*ncclInt8*/ 0, R.comm, dev.stream));
+        LPM_CUDA(cudaMemcpyAsync(all, scratch + 64, 64 * (size_t)R.world, cudaMemcpyDeviceToHost, dev.stream));
+        LPM_CUDA(cudaStreamSynchronize(dev.stream));
+        for (int r = 0; r < R.world; ++r) {
+            if (r == R.rank) continue;
+            void* p = nullptr;
+            e = cudaIpcOpenMemHandle(&p, all[r], cudaIpcMemLazyEnablePeerAccess);
+            if (e != cudaSuccess)
+                return set_error(LPM_ERR_COMM, "cudaIpcOpenMemHandle(rank %d): %s", r, cudaGetErrorString(e));
+            s.peer[r] = (char*)p;
+        }
+    }
+    R.slabs.push_back(s);
+    *out = s.local;
+    return LPM_OK;
+}
+
+inline int free_shared(void* ptr)
+{
+    Runtime& R = rt();
+    for (size_t k = 0; k < R.slabs.size(); ++k) {
+        if (R.slabs[k].local != ptr) continue;
+        SharedSlab s = R.slabs[k];
+        Device& dev = R.devs[0];
+        cudaSetDevice(dev.id);
+        cudaStreamSynchronize(dev.stream);
+        cudaDeviceSynchronize();
+        for (int r = 0; r < R.world; ++r)
+            if (r != R.rank && s.peer[r]) cudaIpcCloseMemHandle(s.peer[r]);
+        // nobody may free while a peer still has stores in flight or the mapping open
+        if (R.world > 1 && R.comm) {
+            LPM_TRY(comm_barrier(dev, dev.stream));
+            LPM_CUDA(cudaStreamSynchronize(dev.stream));
+        }
+        cudaFree(s.local);
+        R.slabs.erase(R.slabs.begin() + k);
+        return LPM_OK;
+    }
+    return set_error(LPM_ERR_INVALID, "lpm_comm_free_shared: not a shared allocation");
+}
+
+// Fill `o` so that output k goes to every rank's copy of out[k] (own copy first) when all
+// outputs of this evaluation live in shared slabs; otherwise to out[k] only.  Returns whether
+// the peer-store exchange is in effect.
+template <int NO>
+inline bool set_outs_shared(Outs<NO>& o, double* const* out, int64_t n)
+{
+    Runtime& R = rt();
+    o.nrep = 1;
+    for (int k = 0; k < NO; ++k) o.p[0][k] = out[k];
+    if (!R.rank_mode || R.world <= 1) return false;
+    const SharedSlab* sl[NO];
+    for (int k = 0; k < NO; ++k) {
+        sl[k] = find_slab(out[k], (size_t)n * sizeof(double));
+        if (!sl[k]) return false;
+    }
+    o.nrep = R.world;
+    for (int q = 0; q < R.world; ++q) {
+        const int r = (R.rank + q) % R.world;
+        for (int k = 0; k < NO; ++k) o.p[q][k] = (double*)(sl[k]->peer[r] + ((char*)out[k] - sl[k]->local));
+    }
+    return true;
 }
 
 // ---------------------------------------------------------------- mask plan
@@ -237,15 +351,22 @@ inline int direct_sum(Device& dev, cudaStream_t st, const MaskPlan& mp, int64_t 
         if (dev.next_prof(&pb, &pe) != LPM_OK) return set_error(LPM_ERR_CUDA, "cannot create profiling events");
         LPM_CUDA(cudaEventRecord(pb, st));
     }
+    // Rank mode with outputs in shared slabs: the storing kernel writes every rank's copy over
+    // NVLink.  A barrier BEFORE it (every rank has finished reading the previous contents of its
+    // copy) and one AFTER it (every rank's stores have landed) replace the NCCL exchange.
+    const bool peer_exchange = rt().rank_mode && prm2.out.nrep > 1;
+    if (peer_exchange && g.nchunks == 1) LPM_TRY(comm_barrier(dev, st));
     LPM_TRY(launch_variant<K>(variant, st, prm2, g, dev.ws.sources.as<double>(), mp.scan.as<int32_t>(), partial,
                               dev.sm_count));
     if (prof) LPM_CUDA(cudaEventRecord(pe, st));
     count_launch();
     if (g.nchunks > 1) {
+        if (peer_exchange) LPM_TRY(comm_barrier(dev, st));
         const unsigned nb = (unsigned)((g.ntgt + 255) / 256);
         ds_finalize_kernel<K><<<nb, 256, 0, st>>>(prm2, g, partial);
         count_launch();
     }
+    if (peer_exchange) LPM_TRY(comm_barrier(dev, st));
     LPM_CUDA(cudaGetLastError());
     return LPM_OK;
 }

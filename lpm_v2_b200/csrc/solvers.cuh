@@ -14,7 +14,9 @@
 // device's LoadBalance slice only; the results reach the other replicas
 //   - single-process mode: by peer stores from the finalize step (Outs::nrep
 //     replicas over NVLink), followed by an event barrier between the streams;
-//   - rank mode: by the grouped NCCL broadcast in allgather_slices().
+//   - rank mode: the arrays of every rank live in one CUDA-IPC shared slab each, and the
+//     finalize step stores to all of them over NVLink between two stream-ordered barriers
+//     (runtime.cuh); the grouped NCCL broadcast of allgather_slices() is the fallback.
 // The O(N) stage arithmetic is then repeated identically on every replica.
 #pragma once
 #include <memory>
@@ -124,6 +126,7 @@ struct Replica {
 struct SolverBase {
     int64_t n = 0;
     std::vector<Replica> reps;
+    void* slab = nullptr;         // rank mode: all arrays live in one shared slab (peer-store exchange)
 
     int alloc(int64_t n_, int narr, const int32_t* mask_host)
     {
@@ -138,9 +141,17 @@ struct SolverBase {
             r.dev = &R.devs[g];
             LPM_CUDA(cudaSetDevice(r.dev->id));
             r.a.resize(narr);
-            for (auto& b : r.a) {
-                LPM_TRY(b.reserve((size_t)n * sizeof(double)));
-                LPM_CUDA(cudaMemsetAsync(b.p, 0, (size_t)n * sizeof(double), r.dev->stream));
+            if (R.rank_mode && R.world > 1) {
+                // one slab every rank can store into (COLLECTIVE: solvers are created by all ranks together)
+                const size_t stride = ((size_t)n * sizeof(double) + 255) / 256 * 256;
+                LPM_TRY(alloc_shared(stride * narr, &slab));
+                LPM_CUDA(cudaMemsetAsync(slab, 0, stride * narr, r.dev->stream));
+                for (int k = 0; k < narr; ++k) { r.a[k].p = (char*)slab + stride * k; r.a[k].cap = 0; }
+            } else {
+                for (auto& b : r.a) {
+                    LPM_TRY(b.reserve((size_t)n * sizeof(double)));
+                    LPM_CUDA(cudaMemsetAsync(b.p, 0, (size_t)n * sizeof(double), r.dev->stream));
+                }
             }
             LPM_TRY(r.mask.reserve((size_t)n * sizeof(int32_t)));
             LPM_CUDA(cudaMemcpyAsync(r.mask.p, mask_host, (size_t)n * sizeof(int32_t), cudaMemcpyHostToDevice, r.dev->stream));
@@ -182,11 +193,14 @@ struct SolverBase {
         for (auto& r : reps) {
             cudaSetDevice(r.dev->id);
             cudaStreamSynchronize(r.dev->stream);
+            if (slab)
+                for (auto& b : r.a) b.p = nullptr;      // views into the slab
             for (auto& b : r.a) b.release();
             r.mask.release();
             r.mp.release();
         }
         reps.clear();
+        if (slab) { free_shared(slab); slab = nullptr; }
     }
 
     // One direct sum over all replicas: inputs are array indices `in` (Op order),
@@ -196,6 +210,7 @@ struct SolverBase {
     {
         Runtime& R = rt();
         const int nrep = (int)reps.size();
+        bool exchanged = false;
         for (int g = 0; g < nrep; ++g) {
             Replica& r = reps[g];
             LPM_CUDA(cudaSetDevice(r.dev->id));
@@ -206,9 +221,19 @@ struct SolverBase {
             for (int k = 0; k < 3; ++k) a.sc[k] = sc ? sc[k] : 0.0;
             LPM_TRY(Op::pack(*r.dev, r.dev->stream, r.mp, a));
             typename Op::K::Params prm = Op::params(a);
-            prm.out.nrep = nrep;
-            for (int q = 0; q < nrep; ++q)       // own replica first, then the peers
-                for (int k = 0; k < Op::NOUT; ++k) prm.out.p[q][k] = reps[(g + q) % nrep].A(out[k]);
+            if (R.rank_mode) {                   // one replica per process: the peers' copies through the shared slab
+                double* o[4];
+                for (int k = 0; k < Op::NOUT; ++k) o[k] = r.A(out[k]);
+                exchanged = set_outs_shared(prm.out, o, n);
+                if (exchanged && r.se <= r.sb) {
+                    LPM_TRY(comm_barrier(*r.dev, r.dev->stream));
+                    LPM_TRY(comm_barrier(*r.dev, r.dev->stream));
+                }
+            } else {
+                prm.out.nrep = nrep;
+                for (int q = 0; q < nrep; ++q)       // own replica first, then the peers
+                    for (int k = 0; k < Op::NOUT; ++k) prm.out.p[q][k] = reps[(g + q) % nrep].A(out[k]);
+            }
             LPM_TRY(direct_sum<typename Op::K>(*r.dev, r.dev->stream, r.mp, r.sb, r.se, prm, variant));
         }
         if (nrep > 1) {
@@ -219,7 +244,7 @@ struct SolverBase {
             for (int g = 0; g < nrep; ++g)
                 for (int h = 0; h < nrep; ++h)
                     if (h != g) LPM_CUDA(cudaStreamWaitEvent(reps[g].dev->stream, reps[h].dev->ev_done, 0));
-        } else if (R.rank_mode && R.world > 1) {
+        } else if (R.rank_mode && R.world > 1 && !exchanged) {
             double* bufs[4];
             for (int k = 0; k < Op::NOUT; ++k) bufs[k] = reps[0].A(out[k]);
             LPM_TRY(allgather_slices(Op::NOUT, bufs, n, reps[0].dev->stream));

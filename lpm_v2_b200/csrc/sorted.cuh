@@ -107,29 +107,34 @@ inline int sort_by_cell(Device& dev, cudaStream_t st, int64_t count, int bits, u
 }
 
 // Evaluate Op for targets [tbeg, tend) of nt into out[k][i] (device arrays in particle / target
-// order).  Plain path: reference order.  Sorted path: see above.
+// order).  Plain path: reference order.  Sorted path: see above.  In rank mode, when every
+// out[k] lies in a shared slab (lpm_comm_alloc_shared), the results are stored into every
+// rank's copy over NVLink, bracketed by barriers (runtime.cuh), and *exchanged is set: the
+// caller then skips the NCCL slice exchange.
 template <class Op>
 inline int evaluate_impl(Device& dev, cudaStream_t st, MaskPlan& mp, const Args& a, int64_t tbeg, int64_t tend, int64_t nt,
-                         double* const* out);
+                         double* const* out, bool* exchanged);
 
 template <class Op>
 inline int evaluate(Device& dev, cudaStream_t st, MaskPlan& mp, const Args& a, int64_t tbeg, int64_t tend, int64_t nt,
-                    double* const* out)
+                    double* const* out, bool* exchanged = nullptr)
 {
+    bool ex = false;
+    if (!exchanged) exchanged = &ex;
     const bool prof = rt().profiling;
     if (prof) {
         for (auto& e : dev.ev_sum)
             if (!e) LPM_CUDA(cudaEventCreate(&e));
         LPM_CUDA(cudaEventRecord(dev.ev_sum[0], st));
     }
-    LPM_TRY(evaluate_impl<Op>(dev, st, mp, a, tbeg, tend, nt, out));
+    LPM_TRY(evaluate_impl<Op>(dev, st, mp, a, tbeg, tend, nt, out, exchanged));
     if (prof) LPM_CUDA(cudaEventRecord(dev.ev_sum[1], st));
     return LPM_OK;
 }
 
 template <class Op>
 inline int evaluate_impl(Device& dev, cudaStream_t st, MaskPlan& mp, const Args& a, int64_t tbeg, int64_t tend, int64_t nt,
-                         double* const* out)
+                         double* const* out, bool* exchanged)
 {
     using K = typename Op::K;
     const int mode = rt().pse_culling;      // 0 plain, 1 sort + cull, 2 sort only
@@ -138,7 +143,11 @@ inline int evaluate_impl(Device& dev, cudaStream_t st, MaskPlan& mp, const Args&
     if (!sorted) {
         LPM_TRY(Op::pack(dev, st, mp, a));
         typename K::Params prm = Op::params(a);
-        set_outs(prm.out, out);
+        *exchanged = set_outs_shared(prm.out, out, nt);
+        if (tend <= tbeg && *exchanged) {      // empty slice: still take part in the barriers
+            LPM_TRY(comm_barrier(dev, st));
+            LPM_TRY(comm_barrier(dev, st));
+        }
         return direct_sum<K>(dev, st, mp, tbeg, tend, prm, Op::variant(), nt);
     }
     if constexpr (K::CULL) {
@@ -198,13 +207,17 @@ inline int evaluate_impl(Device& dev, cudaStream_t st, MaskPlan& mp, const Args&
             prm.out.p[0][k] = ws.sorted_out[k].as<double>();
         }
         LPM_TRY(direct_sum<K>(dev, st, mps, 0, ns, prm, Op::variant(), ns));
+        Outs<Op::NOUT> o{};
+        *exchanged = set_outs_shared(o, out, nt);      // the scatter is the storing kernel here
+        if (*exchanged) LPM_TRY(comm_barrier(dev, st));
         for (int k = 0; k < Op::NOUT; ++k) {
             ScatterDst dst{};
-            dst.nrep = 1;
-            dst.p[0] = out[k];
+            dst.nrep = o.nrep;
+            for (int r = 0; r < o.nrep; ++r) dst.p[r] = o.p[r][k];
             scatter_kernel<<<(unsigned)((ns + 255) / 256), 256, 0, st>>>(ns, tperm, ws.sorted_out[k].as<double>(), dst);
         }
         count_launch(Op::NOUT);
+        if (*exchanged) LPM_TRY(comm_barrier(dev, st));
         LPM_CUDA(cudaGetLastError());
     }
     return LPM_OK;

@@ -45,6 +45,29 @@ def pse_laplacian_sphere_dev(x, y, z, f, area, mask, eps, sphere_radius, ibeg, i
                                            _stream(stream)))
 
 
+class _SharedArray:
+    """__cuda_array_interface__ view of library-owned device memory (a shared slab)."""
+
+    def __init__(self, ptr, shape, typestr="<f8"):
+        self.__cuda_array_interface__ = {"shape": tuple(shape), "typestr": typestr, "data": (int(ptr), False),
+                                         "version": 3, "strides": None}
+
+
+def shared_tensors(count, n, device):
+    """COLLECTIVE (rank mode): `count` float64 tensors of n entries carved from ONE shared slab
+    (lpm_comm_alloc_shared).  Direct sums whose outputs are these tensors deliver every rank's
+    slice to every rank by NVLink peer stores: no allgather_slices_dev afterwards.  Returns
+    (tensors, slab address); free with api.comm_free_shared(address) once the tensors are dropped."""
+    from . import api
+    stride = (n * 8 + 255) // 256 * 256
+    base = api.comm_alloc_shared(stride * count)
+    ts = [torch.as_tensor(_SharedArray(base + k * stride, (n,)), device=device) for k in range(count)]
+    for k, t in enumerate(ts):
+        assert t.data_ptr() == base + k * stride
+        t.zero_()
+    return ts, base
+
+
 def allgather_slices_dev(tensors, stream=None):
     """The reference's MPI_BCAST loop (src/SphereBVESolver.f90:422-429) over NCCL, in place."""
     n = tensors[0].numel()

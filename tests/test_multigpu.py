@@ -1,6 +1,6 @@
 """Multi-GPU paths (skipped on a 1-GPU box): single-process mode (all devices of the
 box, peer stores + event barrier) in a subprocess, and rank mode (torchrun, NCCL
-slice exchange inside liblpmgpu)."""
+slice exchange inside liblpmgpu, and the peer-store exchange through CUDA-IPC shared slabs)."""
 import os
 import subprocess
 import sys
@@ -85,6 +85,26 @@ torch_api.allgather_slices_dev(out)
 torch.cuda.synchronize()
 for o, g in zip(out, got):
     assert np.array_equal(o.cpu().numpy(), g)
+# device API with the outputs in a shared slab: the finalize step stores every slice to every
+# rank over NVLink (no NCCL exchange); bit-identical to the NCCL path
+sh, slab = torch_api.shared_tensors(3, m.n, dev)
+assert api.comm_is_shared(sh[0].data_ptr(), m.n * 8) and not api.comm_is_shared(out[0].data_ptr(), m.n * 8)
+for rep in range(3):
+    for s_ in sh:
+        s_.fill_(float(rep))
+    torch_api.bve_velocity_dev(*t, mask, 1.0, b, e, *sh)
+    torch.cuda.synchronize()
+    for s_, g in zip(sh, got):
+        assert np.array_equal(s_.cpu().numpy(), g), rep
+# a PSE sum (cell-ordered targets: the scatter kernel does the peer stores)
+lap_sh, slab2 = torch_api.shared_tensors(1, m.n, dev)
+f_t = torch.from_numpy(problems.spherical_harmonic54(m)).to(dev)
+torch_api.pse_laplacian_sphere_dev(t[0], t[1], t[2], f_t, t[4], mask, 0.1, 1.0, b, e, lap_sh[0])
+torch.cuda.synchronize()
+lap_host = api.pse_laplacian_sphere(m.x, m.y, m.z, problems.spherical_harmonic54(m), m.area, m.is_active, 0.1, 1.0)
+assert np.array_equal(lap_sh[0].cpu().numpy(), lap_host)
+del sh, lap_sh
+api.comm_free_shared(slab); api.comm_free_shared(slab2)
 # all ranks hold identical results
 chk = torch.stack([o.sum() for o in out])
 lo, hi = chk.clone(), chk.clone()
