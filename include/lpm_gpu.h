@@ -286,6 +286,10 @@ int lpm_set_bve_variant(int variant);
  *   2  cell order, every tile visited -- bit-identical to mode 1.
  * Modes 1/2 differ from mode 0 by summation order only (~1e-16 relative). */
 int lpm_set_pse_culling(int mode);
+/* Sphere PSE kernels: 1 (default) evaluates (d_ij / eps)^2 inside the cut-off from
+ * tan^2(theta / 2) = |x_i cross x_j|^2 / (|x_i| |x_j| + x_i . x_j)^2 and a short series for
+ * atan^2; 0 always calls sqrt + atan2 as the reference writes it.  Same value to ~1e-15. */
+int lpm_set_pse_series(int enable);
 
 /* ------------------------------------------------------ mesh (host only) */
 

@@ -104,6 +104,7 @@ PROTOTYPES = {
     "lpm_set_profiling": (_int, [_int]),
     "lpm_set_bve_variant": (_int, [_int]),
     "lpm_set_pse_culling": (_int, [_int]),
+    "lpm_set_pse_series": (_int, [_int]),
     # mesh
     "lpm_mesh_create": (_int, [_int, _int, _dbl, C.POINTER(_vp)]),
     "lpm_mesh_destroy": (None, [_vp]),

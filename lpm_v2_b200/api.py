@@ -187,6 +187,11 @@ def set_pse_culling(mode):
     check(lib.lpm_set_pse_culling(int(mode)))
 
 
+def set_pse_series(on):
+    """Sphere PSE kernels: series for theta^2 inside the cut-off (default) or atan2 always."""
+    check(lib.lpm_set_pse_series(1 if on else 0))
+
+
 def last_kernel_ms():
     ms = C.c_double(0)
     check(lib.lpm_last_kernel_ms(C.byref(ms)))

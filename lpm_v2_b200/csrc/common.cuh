@@ -147,6 +147,7 @@ struct Runtime {
     bool profiling = false;
     int64_t launches = 0;
     int bve_variant = 0;
+    bool pse_series = true;              // sphere PSE kernels: theta^2 by series inside the cut-off (false: atan2 always)
     int pse_culling = 1;                 // PSE kernels: 0 reference order, every tile; 1 cell order + tile culling; 2 cell order only
     // NCCL (rank mode)
     void* nccl_lib = nullptr;

@@ -155,18 +155,7 @@ struct OpPseSphere {
         count_launch();
         return LPM_OK;
     }
-    static K::Params params(const Args& a)
-    {
-        K::Params p{};
-        p.x = a.in[0]; p.y = a.in[1]; p.z = a.in[2]; p.f = a.in[3];
-        const double eps = a.sc[0], sr = a.sc[1];
-        p.rad_over_eps = sr / eps;
-        const double theta_cut = kPseCut * eps / sr;
-        p.cos_cut = (theta_cut < LPM_PI) ? cos(theta_cut) : -2.0;
-        p.chord_cut = sphere_chord_cut(eps, sr);
-        p.inv_eps2 = 1.0 / (eps * eps);
-        return p;
-    }
+    static K::Params params(const Args& a);
     static int variant() { return 0; }
 };
 
@@ -202,7 +191,16 @@ inline PseSphereConsts pse_sphere_consts(double eps, double sr, double scale)
     c.cos_cut = (theta_cut < LPM_PI) ? cos(theta_cut) : -2.0;
     c.chord_cut = sphere_chord_cut(eps, sr);
     c.scale = scale;
+    c.k2_scale = 4.0 * c.rad_over_eps * c.rad_over_eps;
+    c.nterms = rt().pse_series ? atan_sq_terms(theta_cut) : 0;
     return c;
+}
+inline OpPseSphere::K::Params OpPseSphere::params(const Args& a)
+{
+    K::Params p{};
+    p.x = a.in[0]; p.y = a.in[1]; p.z = a.in[2]; p.f = a.in[3];
+    p.c = pse_sphere_consts(a.sc[0], a.sc[1], 1.0 / (a.sc[0] * a.sc[0]));
+    return p;
 }
 
 // ---- interpolation (sphere): in = x y z f area; sc = eps, sphere_radius; targets tgt[0..2] (m of them)

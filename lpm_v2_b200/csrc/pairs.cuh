@@ -266,12 +266,15 @@ __device__ __forceinline__ void log_group_fast(const double (&d)[T], double (&l)
         tk[k] = *reinterpret_cast<const double*>(reinterpret_cast<const char*>(sc.ks) + (u & (KS * 8 - 8)));
         r[k] = fma(d[k], log_bin_rcp(hi, sc.i1), -1.0);
     }
+    // -1/4 and -1/2 are written as literals: their low words are zero, so they fit the DFMA's
+    // 32-bit immediate and the first Horner step reads r and one constant register instead of two
+    // (the kernel is bound by register operand delivery, see BveVelT).
 #pragma unroll
-    for (int k = 0; k < T; ++k) p[k] = fma(r[k], kLogC[0], kLogC[1]);
+    for (int k = 0; k < T; ++k) p[k] = fma(r[k], kLogC[0], -0.25);
 #pragma unroll
     for (int k = 0; k < T; ++k) p[k] = fma(r[k], p[k], kLogC[2]);
 #pragma unroll
-    for (int k = 0; k < T; ++k) p[k] = fma(r[k], p[k], kLogC[3]);
+    for (int k = 0; k < T; ++k) p[k] = fma(r[k], p[k], -0.5);
 #pragma unroll
     for (int k = 0; k < T; ++k) p[k] = fma(r[k], p[k], 1.0);
 #pragma unroll
@@ -890,6 +893,56 @@ __device__ __forceinline__ double pse_eta_pi(double k2)    // pi * eta
     return poly * exp(-k2);
 }
 
+// (d_ij / eps)^2 on the sphere.  The reference evaluates d_ij = R atan2(|x_i cross x_j|, x_i . x_j)
+// (src/SphereGeometry.f90:107-125).  Inside the cut-off the angle is small, and
+//   theta^2 = 4 atan^2(tan(theta / 2)),  tan^2(theta / 2) = |x_i cross x_j|^2 / (|x_i| |x_j| + x_i . x_j)^2 =: t
+// has no cancellation (the cross product carries the small angle), so theta^2 = 4 t A(t) with
+// A(t) = atan^2(sqrt t) / t = sum_k (-1)^(k-1) / k (1 + 1/3 + ... + 1/(2k-1)) t^(k-1): one reciprocal and
+// a short polynomial (nterms from the cut-off angle, relative truncation < 1e-17) instead of the
+// library sqrt + atan2 (~75 FP64 instructions).  nterms == 0 (cut-off angle > 0.9 rad) keeps atan2.
+constexpr int kAtanSqMaxTerms = 28;
+__constant__ double kAtanSq[kAtanSqMaxTerms] = {1.0, -0.6666666666666666, 0.5111111111111111, -0.41904761904761906, 0.3574603174603175, -0.31303511303511306, 0.279304822161965, -0.25272505272505275, 0.23118043902357627, -0.2133255530159555, 0.19826132525260023, -0.18536273655401397, 0.1741809875883206, -0.16438499112037178, 0.15572484228705963, -0.14800816867637648, 0.1410843370073561, -0.1348336198720268, 0.12915958866965838, -0.12398366051822675, 0.1192411168698559, -0.11487814855547557, 0.11084963001924716, -0.10711742025780689, 0.10364904997810687, -0.10041669586884333, 0.09739637100437883, -0.09456727983214452};
+
+struct PseSphereConsts {
+    double rad_over_eps;     // SphereRadius / eps
+    double cos_cut;          // cos(kPseCut eps / SphereRadius), or -2 if the cut-off exceeds pi
+    double chord_cut;        // sphere_chord_cut(eps, SphereRadius), for tile culling
+    double scale;            // post-scaling of the summed field (the trailing MultiplyFieldByScalar)
+    double k2_scale;         // 4 (SphereRadius / eps)^2
+    int nterms;              // terms of A(t); 0: use atan2
+};
+
+// nn = |x_i| |x_j|
+__device__ __forceinline__ double sphere_k2(double tx, double ty, double tz, double sx, double sy, double sz,
+                                            double dot, double nn, const PseSphereConsts& c)
+{
+    double c0 = fma(ty, sz, -(sy * tz));
+    double c1 = fma(sx, tz, -(tx * sz));
+    double c2 = fma(tx, sy, -(sx * ty));
+    double s2 = fma(c0, c0, fma(c1, c1, c2 * c2));
+    if (c.nterms == 0) {
+        double k = atan2(sqrt(s2), dot) * c.rad_over_eps;
+        return k * k;
+    }
+    const double den = nn + dot;
+    const double t = s2 * rcp_fast(den * den);
+    double a = kAtanSq[c.nterms - 1];
+#pragma unroll 1
+    for (int n = c.nterms - 2; n >= 0; --n) a = fma(a, t, kAtanSq[n]);
+    return c.k2_scale * (t * a);
+}
+
+// host: number of terms of A(t) for a cut-off angle, 0 if atan2 is the better choice
+inline int atan_sq_terms(double theta_cut)
+{
+    if (!(theta_cut < 0.9)) return 0;
+    const double t = tan(0.5 * theta_cut) * tan(0.5 * theta_cut) * 1.02;       // margin for the cut-off's rounding
+    int n = 2;
+    double tn = t;                      // t^(n-1)
+    while (n < kAtanSqMaxTerms && tn * t > 1.0e-18) { tn *= t; ++n; }
+    return tn * t > 1.0e-18 ? 0 : n;
+}
+
 // Sphere: d_ij = atan2(|x_i cross x_j|, x_i.x_j) * SphereRadius  (src/SphereGeometry.f90:107-125).
 // Source record: x, y, z, f, A/(pi eps^2), |x_j|.
 struct PseSphere : CullSphere {
@@ -897,18 +950,16 @@ struct PseSphere : CullSphere {
     static constexpr bool SKIP_SELF = false;
     struct Params {
         const double *x, *y, *z, *f;
-        double rad_over_eps;     // SphereRadius / eps
-        double cos_cut;          // cos(kPseCut eps / SphereRadius), or -2 if the cut-off exceeds pi
-        double chord_cut;        // sphere_chord_cut(eps, SphereRadius)
-        double inv_eps2;
+        PseSphereConsts c;       // c.scale = 1 / eps^2
         Outs<1> out;
     };
-    __device__ static __forceinline__ double cull_dist(const Params& p) { return p.chord_cut; }
-    struct Tgt { double x, y, z, f, thr; };
+    __device__ static __forceinline__ double cull_dist(const Params& p) { return p.c.chord_cut; }
+    struct Tgt { double x, y, z, f, nrm, thr; };
     __device__ static __forceinline__ Tgt load_target(const Params& p, int64_t i)
     {
-        Tgt t{p.x[i], p.y[i], p.z[i], p.f[i], 0.0};
-        t.thr = p.cos_cut * sqrt(t.x * t.x + t.y * t.y + t.z * t.z);
+        Tgt t{p.x[i], p.y[i], p.z[i], p.f[i], 0.0, 0.0};
+        t.nrm = sqrt(t.x * t.x + t.y * t.y + t.z * t.z);
+        t.thr = p.c.cos_cut * t.nrm;
         return t;
     }
     template <bool CHECK>
@@ -917,17 +968,13 @@ struct PseSphere : CullSphere {
     {
         double dot = fma(t.x, s[0], fma(t.y, s[1], t.z * s[2]));
         if (dot < t.thr * s[5]) return;           // angle beyond the cut-off
-        double c0 = fma(t.y, s[2], -(s[1] * t.z));
-        double c1 = fma(s[0], t.z, -(t.x * s[2]));
-        double c2 = fma(t.x, s[1], -(s[0] * t.y));
-        double cn = sqrt(fma(c0, c0, fma(c1, c1, c2 * c2)));
-        double k = atan2(cn, dot) * p.rad_over_eps;
-        acc[0] = fma((s[3] - t.f) * pse_eta_pi(k * k), s[4], acc[0]);
+        const double k2 = sphere_k2(t.x, t.y, t.z, s[0], s[1], s[2], dot, t.nrm * s[5], p.c);
+        acc[0] = fma((s[3] - t.f) * pse_eta_pi(k2), s[4], acc[0]);
     }
     LPM_DEFAULT_GROUP()
     __device__ static __forceinline__ void finalize(const Params& p, const Tgt&, const double (&a)[NA], int64_t i)
     {
-        p.out.store(0, i, a[0] * p.inv_eps2);
+        p.out.store(0, i, a[0] * p.c.scale);
     }
 };
 

@@ -22,25 +22,6 @@ __device__ __forceinline__ double pse_dphi_pi(double k2)
     return fma(fma(fma(1.0 / 3.0, k2, -5.0), k2, 20.0), k2, -20.0) * exp(-k2);
 }
 
-// (d_ij / eps)^2 on the sphere from the reference's atan2 form (SphereGeometry.f90:107-125)
-__device__ __forceinline__ double sphere_k2(double tx, double ty, double tz, double sx, double sy, double sz,
-                                            double dot, double rad_over_eps)
-{
-    double c0 = fma(ty, sz, -(sy * tz));
-    double c1 = fma(sx, tz, -(tx * sz));
-    double c2 = fma(tx, sy, -(sx * ty));
-    double cn = sqrt(fma(c0, c0, fma(c1, c1, c2 * c2)));
-    double k = atan2(cn, dot) * rad_over_eps;
-    return k * k;
-}
-
-struct PseSphereConsts {
-    double rad_over_eps;     // SphereRadius / eps
-    double cos_cut;          // cos(kPseCut eps / SphereRadius), or -2 if the cut-off exceeds pi
-    double chord_cut;        // sphere_chord_cut(eps, SphereRadius), for tile culling
-    double scale;            // post-scaling of the summed field (the trailing MultiplyFieldByScalar)
-};
-
 // ---------------------------------------------------------------- interpolation
 // Source record (sphere): x, y, z, f A/(pi eps^2), |x|, 0;  (plane): x, y, f A/(pi eps^2), 0.
 struct PseInterpSphere : CullSphere {
@@ -52,11 +33,12 @@ struct PseInterpSphere : CullSphere {
         Outs<1> out;
     };
     __device__ static __forceinline__ double cull_dist(const Params& p) { return p.c.chord_cut; }
-    struct Tgt { double x, y, z, thr; };
+    struct Tgt { double x, y, z, nrm, thr; };
     __device__ static __forceinline__ Tgt load_target(const Params& p, int64_t i)
     {
-        Tgt t{p.x[i], p.y[i], p.z[i], 0.0};
-        t.thr = p.c.cos_cut * sqrt(t.x * t.x + t.y * t.y + t.z * t.z);
+        Tgt t{p.x[i], p.y[i], p.z[i], 0.0, 0.0};
+        t.nrm = sqrt(t.x * t.x + t.y * t.y + t.z * t.z);
+        t.thr = p.c.cos_cut * t.nrm;
         return t;
     }
     template <bool CHECK>
@@ -65,7 +47,7 @@ struct PseInterpSphere : CullSphere {
     {
         double dot = fma(t.x, s[0], fma(t.y, s[1], t.z * s[2]));
         if (dot < t.thr * s[4]) return;
-        double k2 = sphere_k2(t.x, t.y, t.z, s[0], s[1], s[2], dot, p.c.rad_over_eps);
+        double k2 = sphere_k2(t.x, t.y, t.z, s[0], s[1], s[2], dot, t.nrm * s[4], p.c);
         acc[0] = fma(pse_delta_pi(k2), s[3], acc[0]);
     }
     LPM_DEFAULT_GROUP()
@@ -173,11 +155,12 @@ struct PseGradSphere : CullSphere {
         Outs<3> out;
     };
     __device__ static __forceinline__ double cull_dist(const Params& p) { return p.c.chord_cut; }
-    struct Tgt { double x, y, z, f, thr; };
+    struct Tgt { double x, y, z, f, nrm, thr; };
     __device__ static __forceinline__ Tgt load_target(const Params& p, int64_t i)
     {
-        Tgt t{p.x[i], p.y[i], p.z[i], p.f[i], 0.0};
-        t.thr = p.c.cos_cut * sqrt(t.x * t.x + t.y * t.y + t.z * t.z);
+        Tgt t{p.x[i], p.y[i], p.z[i], p.f[i], 0.0, 0.0};
+        t.nrm = sqrt(t.x * t.x + t.y * t.y + t.z * t.z);
+        t.thr = p.c.cos_cut * t.nrm;
         return t;
     }
     template <bool CHECK>
@@ -186,7 +169,7 @@ struct PseGradSphere : CullSphere {
     {
         double dot = fma(t.x, s[0], fma(t.y, s[1], t.z * s[2]));
         if (dot < t.thr * s[5]) return;
-        double k2 = sphere_k2(t.x, t.y, t.z, s[0], s[1], s[2], dot, p.c.rad_over_eps);
+        double k2 = sphere_k2(t.x, t.y, t.z, s[0], s[1], s[2], dot, t.nrm * s[5], p.c);
         double c = (s[3] + t.f) * pse_dphi_pi(k2) * s[4];
         acc[0] = fma(t.x - s[0], c, acc[0]);
         acc[1] = fma(t.y - s[1], c, acc[1]);
@@ -260,11 +243,12 @@ struct PseDoubleDotSphere : CullSphere {
         Outs<1> out;
     };
     __device__ static __forceinline__ double cull_dist(const Params& p) { return p.c.chord_cut; }
-    struct Tgt { double x, y, z, u, v, thr; };
+    struct Tgt { double x, y, z, u, v, nrm, thr; };
     __device__ static __forceinline__ Tgt load_target(const Params& p, int64_t i)
     {
-        Tgt t{p.x[i], p.y[i], p.z[i], p.u[i], p.v[i], 0.0};
-        t.thr = p.c.cos_cut * sqrt(t.x * t.x + t.y * t.y + t.z * t.z);
+        Tgt t{p.x[i], p.y[i], p.z[i], p.u[i], p.v[i], 0.0, 0.0};
+        t.nrm = sqrt(t.x * t.x + t.y * t.y + t.z * t.z);
+        t.thr = p.c.cos_cut * t.nrm;
         return t;
     }
     template <bool CHECK>
@@ -273,7 +257,7 @@ struct PseDoubleDotSphere : CullSphere {
     {
         double dot = fma(t.x, s[0], fma(t.y, s[1], t.z * s[2]));
         if (dot < t.thr * s[7]) return;
-        double k2 = sphere_k2(t.x, t.y, t.z, s[0], s[1], s[2], dot, p.c.rad_over_eps);
+        double k2 = sphere_k2(t.x, t.y, t.z, s[0], s[1], s[2], dot, t.nrm * s[7], p.c);
         double c = pse_dphi_pi(k2) * s[6];
         double dx = t.x - s[0], dy = t.y - s[1], dz = t.z - s[2];
         double a = (s[3] + t.u) * c, b = (s[4] + t.v) * c, e = (s[5] + t.v) * c;
@@ -300,11 +284,12 @@ struct PseDivSphere : CullSphere {
         Outs<1> out;
     };
     __device__ static __forceinline__ double cull_dist(const Params& p) { return p.c.chord_cut; }
-    struct Tgt { double x, y, z, u, v, w, thr; };
+    struct Tgt { double x, y, z, u, v, w, nrm, thr; };
     __device__ static __forceinline__ Tgt load_target(const Params& p, int64_t i)
     {
-        Tgt t{p.x[i], p.y[i], p.z[i], p.u[i], p.v[i], p.w[i], 0.0};
-        t.thr = p.c.cos_cut * sqrt(t.x * t.x + t.y * t.y + t.z * t.z);
+        Tgt t{p.x[i], p.y[i], p.z[i], p.u[i], p.v[i], p.w[i], 0.0, 0.0};
+        t.nrm = sqrt(t.x * t.x + t.y * t.y + t.z * t.z);
+        t.thr = p.c.cos_cut * t.nrm;
         return t;
     }
     template <bool CHECK>
@@ -313,7 +298,7 @@ struct PseDivSphere : CullSphere {
     {
         double dot = fma(t.x, s[0], fma(t.y, s[1], t.z * s[2]));
         if (dot < t.thr * s[7]) return;
-        double k2 = sphere_k2(t.x, t.y, t.z, s[0], s[1], s[2], dot, p.c.rad_over_eps);
+        double k2 = sphere_k2(t.x, t.y, t.z, s[0], s[1], s[2], dot, t.nrm * s[7], p.c);
         double c = pse_dphi_pi(k2) * s[6];
         double dx = t.x - s[0], dy = t.y - s[1], dz = t.z - s[2];
         double wu = s[3] + t.u, wv = s[4] + t.v, ww = s[5] + t.w;

@@ -156,3 +156,30 @@ def test_cell_order_and_tile_culling_plane(gpu, get_mesh):
     for a, b, c in zip(res[2], res[1], res[0]):
         assert np.array_equal(a, b)
         assert relerr(b, c) <= 1e-13
+
+
+@pytest.mark.parametrize("L,power", [(5, 0.75), (4, 0.9), (6, 1.2)])
+def test_sphere_distance_series_matches_atan2(gpu, oracle, get_mesh, L, power):
+    """Inside the cut-off the sphere kernels get (d/eps)^2 from tan^2(theta/2) and a series for
+    atan^2 (pairs.cuh, sphere_k2) instead of the reference's sqrt + atan2: same sums to 1e-13,
+    and both within 1e-12 of the oracle (which calls atan2 like SphereGeometry.f90:107-125)."""
+    m = get_mesh(M.ICOS_TRI_SPHERE_SEED, L)
+    eps = m.max_edge_length ** power
+    f = problems.spherical_harmonic54(m)
+    u, v, w = -m.y + 0.3 * m.z * m.x, m.x * m.x, 0.5 * m.y - m.z
+    args = (m.x, m.y, m.z)
+
+    def run():
+        return [gpu.pse_laplacian_sphere(*args, f, m.area, m.is_active, eps, 1.0),
+                *gpu.pse_gradient_sphere(*args, f, m.area, m.is_active, eps),
+                gpu.pse_divergence_sphere(*args, u, v, w, m.area, m.is_active, eps)]
+    try:
+        gpu.set_pse_series(False)
+        plain = run()
+    finally:
+        gpu.set_pse_series(True)
+    series = run()
+    for a, b in zip(series, plain):
+        assert relerr(a, b) <= 1e-13
+    if L <= 5:
+        assert relerr(series[0], oracle.pse_laplacian_sphere(*args, f, m.area, m.is_active, eps, 1.0)) <= TOL
