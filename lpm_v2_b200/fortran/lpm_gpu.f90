@@ -46,6 +46,46 @@ interface
 		type(c_ptr), value :: ptr
 	end function
 
+	!> one MPI rank per GPU: claim one device, then join the communicator (id from rank 0 via MPI_BCAST)
+	integer(c_int) function lpm_gpu_init_rank(device) bind(C, name="lpm_gpu_init_rank")
+		import :: c_int
+		integer(c_int), value :: device
+	end function
+
+	integer(c_int) function lpm_comm_unique_id(id) bind(C, name="lpm_comm_unique_id")
+		import :: c_int, c_char
+		character(kind=c_char), intent(out) :: id(128)
+	end function
+
+	integer(c_int) function lpm_comm_init_rank(world_size, rank, id) bind(C, name="lpm_comm_init_rank")
+		import :: c_int, c_char
+		integer(c_int), value :: world_size, rank
+		character(kind=c_char), intent(in) :: id(128)
+	end function
+
+	!> collective: device memory every rank can store into over NVLink; a _dev sum whose outputs
+	!> lie in such buffers delivers every slice to every rank (replaces the MPI_BCAST loop)
+	integer(c_int) function lpm_comm_alloc_shared(bytes, ptr) bind(C, name="lpm_comm_alloc_shared")
+		import :: c_int, c_int64_t, c_ptr
+		integer(c_int64_t), value :: bytes
+		type(c_ptr), intent(out) :: ptr
+	end function
+
+	integer(c_int) function lpm_comm_free_shared(ptr) bind(C, name="lpm_comm_free_shared")
+		import :: c_int, c_ptr
+		type(c_ptr), value :: ptr
+	end function
+
+	!> BVESphereVelocity on device-resident arrays: targets [ibeg, iend) (0-based, half open) =
+	!> [indexStart(procRank) - 1, indexEnd(procRank)) of src/MPISetup.f90:138-144
+	integer(c_int) function lpm_bve_velocity_dev(n, x, y, z, relvort, area, mask, radius, ibeg, iend, u, v, w, stream) &
+			bind(C, name="lpm_bve_velocity_dev")
+		import :: c_int, c_int64_t, c_double, c_ptr
+		integer(c_int64_t), value :: n, ibeg, iend
+		type(c_ptr), value :: x, y, z, relvort, area, mask, u, v, w, stream
+		real(c_double), value :: radius
+	end function
+
 	!> replaces the loop nest + MPI_BCAST loop of BVESphereVelocity (SphereBVESolver.f90:395-429)
 	integer(c_int) function lpm_bve_velocity(n, x, y, z, relvort, area, mask, radius, u, v, w) &
 			bind(C, name="lpm_bve_velocity")
