@@ -3,7 +3,7 @@
 Compiles the BVE velocity kernel alone (a one-instantiation translation unit, ~1.5 s) for many
 ORDER seeds, scores each hot loop with the bank model of tools/sass_banks.py
 (fresh operand reads + bank conflicts -> predicted ms at icosTri 7) and prints the best; the GPU sweep
-(tools/sweep_bve.py) then measures the short list.   usage: search_order.py [n_random] [T] [U]"""
+(tools/sweep_bve.py) then measures the short list.   usage: search_order.py [n_random] [T] [U] [min CTAs per SM]"""
 import concurrent.futures as cf
 import os, random, subprocess, sys, tempfile
 
@@ -15,14 +15,14 @@ TU = r'''
 #include "directsum.cuh"
 #include "pairs.cuh"
 using namespace lpm;
-template __global__ void lpm::ds_kernel<BveVelT<4, ORD_SEED>, TT, 128, UU>(const BveVelParams, const DsGeom, const double*, const int32_t*, double*);
+template __global__ void lpm::ds_kernel<BveVelT<4, ORD_SEED>, TT, 128, UU, LB_MIN>(const BveVelParams, const DsGeom, const double*, const int32_t*, double*);
 '''
 
-def score(seed, T, U, work):
+def score(seed, T, U, work, minb=1):
     cu = os.path.join(work, "tu.cu")
-    out = os.path.join(work, f"o{seed}_{T}_{U}.cubin")
+    out = os.path.join(work, f"o{seed}_{T}_{U}_{minb}.cubin")
     r = subprocess.run(["nvcc", "-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
-                        f"-I{ROOT}/include", f"-I{ROOT}/lpm_v2_b200/csrc", f"-DORD_SEED={seed}", f"-DTT={T}", f"-DUU={U}",
+                        f"-I{ROOT}/include", f"-I{ROOT}/lpm_v2_b200/csrc", f"-DORD_SEED={seed}", f"-DTT={T}", f"-DUU={U}", f"-DLB_MIN={minb}",
                         "-cubin", "-o", out, cu], capture_output=True, text=True)
     if r.returncode != 0:
         return seed, None
@@ -42,6 +42,7 @@ if __name__ == "__main__":
     n = int(sys.argv[1]) if len(sys.argv) > 1 else 64
     T = int(sys.argv[2]) if len(sys.argv) > 2 else 4
     U = int(sys.argv[3]) if len(sys.argv) > 3 else 2
+    MINB = int(sys.argv[4]) if len(sys.argv) > 4 else 1      # __launch_bounds__ min CTAs per SM (register cap)
     rng = random.Random(2024)
     seeds = {0}
     while len(seeds) < n:
@@ -50,7 +51,7 @@ if __name__ == "__main__":
     open(os.path.join(work, "tu.cu"), "w").write(TU)
     res = []
     with cf.ThreadPoolExecutor(max_workers=os.cpu_count() or 4) as ex:
-        for seed, sc in ex.map(lambda s: score(s, T, U, work), sorted(seeds)):
+        for seed, sc in ex.map(lambda s: score(s, T, U, work, MINB), sorted(seeds)):
             if sc:
                 res.append((sc["cost"], seed, sc))
     res.sort()
