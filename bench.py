@@ -39,6 +39,7 @@ def parse():
     ap.add_argument("--no-rk4", action="store_true", help="skip the RK4 step-time measurement")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--variant", type=int, default=0)
+    ap.add_argument("--max-chunks", type=int, default=0, help="tuning: upper bound on source chunks (0 = library default)")
     return ap.parse_args()
 
 
@@ -172,6 +173,8 @@ def run_b200(args):
         uid = D.broadcast_unique_id(api.comm_unique_id() if rank == 0 else None)
         api.comm_init_rank(world, rank, uid)
     api.set_bve_variant(args.variant)
+    if args.max_chunks:
+        api.set_max_chunks(args.max_chunks)
 
     m, zeta = workload(args.level)
     n, F = m.n, m.n_active

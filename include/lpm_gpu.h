@@ -280,6 +280,10 @@ int64_t lpm_launch_count(int reset);
 int lpm_set_profiling(int enable);
 /* Tuning knob for benchmarks: select the BVE kernel variant. */
 int lpm_set_bve_variant(int variant);
+/* Upper bound on the number of source chunks an evaluation is split into (work items = target
+ * blocks x chunks).  More chunks = shorter CTAs = a smaller tail when few waves of CTAs fit a
+ * GPU's slice; every rank must use the same value (the chunking is part of the summation order). */
+int lpm_set_max_chunks(int chunks);
 /* Evaluation order of the compactly supported PSE kernels (tests and benchmarks):
  *   0  reference order (j = 1..N over the active particles), every source tile visited;
  *   1  sources and targets in cell (Morton) order, tiles out of reach skipped (default);

@@ -103,6 +103,7 @@ PROTOTYPES = {
     "lpm_comm_is_shared": (_int, [_vp, C.c_int64]),
     "lpm_set_profiling": (_int, [_int]),
     "lpm_set_bve_variant": (_int, [_int]),
+    "lpm_set_max_chunks": (_int, [_int]),
     "lpm_set_pse_culling": (_int, [_int]),
     "lpm_set_pse_series": (_int, [_int]),
     # mesh

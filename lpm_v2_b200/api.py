@@ -178,6 +178,10 @@ def set_profiling(on):
     check(lib.lpm_set_profiling(1 if on else 0))
 
 
+def set_max_chunks(c):
+    check(lib.lpm_set_max_chunks(int(c)))
+
+
 def set_bve_variant(v):
     check(lib.lpm_set_bve_variant(int(v)))
 

@@ -26,7 +26,15 @@
 
 namespace lpm {
 
-constexpr int kMaxChunks = 16;      // upper bound on source chunks per evaluation
+// Upper bound on source chunks per evaluation (lpm_set_max_chunks).  64 rather than 16: at icosTri 8
+// on 8 GPUs a rank's slice is only ~9 waves of CTAs with 16 chunks and the tail costs 3 %
+// (184.1 -> 178.7 ms per evaluation); the price is partial-sum traffic (3 GB at level 8, < 1 ms).
+constexpr int kMaxChunksDefault = 64;
+inline int& max_chunks_ref()
+{
+    static int v = kMaxChunksDefault;
+    return v;
+}
 constexpr int kChunkMin = 8192;     // do not split the source list finer than this
 constexpr int kTile = 256;          // sources per shared-memory tile (all kernels)
 constexpr int kMaxNeedWords = 256;  // tile culling: bitmap words per CTA (<= 8192 tiles per chunk)
@@ -46,12 +54,16 @@ struct DsGeom {
 };
 
 // Source chunking depends on the number of active sources only.
-inline void ds_chunks(int64_t nsrc, int32_t* nsrc_pad, int32_t* chunk, int32_t* nchunks)
+// `nall` (all targets of the evaluation, NOT the slice) caps the partial-sum scratch for very large runs.
+inline void ds_chunks(int64_t nsrc, int32_t* nsrc_pad, int32_t* chunk, int32_t* nchunks, int64_t nall = 0)
 {
     int64_t pad = (nsrc + kTile - 1) / kTile * kTile;
     if (pad == 0) pad = kTile;
     int64_t nc = (pad + kChunkMin - 1) / kChunkMin;
-    if (nc > kMaxChunks) nc = kMaxChunks;
+    int cap = max_chunks_ref();
+    if (nall > (16LL << 20)) cap = cap < 16 ? cap : 16;
+    else if (nall > (8LL << 20)) cap = cap < 32 ? cap : 32;
+    if (nc > cap) nc = cap;
     if (nc < 1) nc = 1;
     int64_t ch = (pad + nc - 1) / nc;
     ch = (ch + kTile - 1) / kTile * kTile;

@@ -191,6 +191,12 @@ extern "C" int lpm_load_balance(int64_t n_items, int nprocs, int64_t* index_star
 
 extern "C" int lpm_set_profiling(int enable) { rt().profiling = enable != 0; return LPM_OK; }
 extern "C" int lpm_set_bve_variant(int variant) { rt().bve_variant = variant; return LPM_OK; }
+extern "C" int lpm_set_max_chunks(int chunks)
+{
+    if (chunks < 1 || chunks > 256) return set_error(LPM_ERR_INVALID, "lpm_set_max_chunks(%d): 1..256", chunks);
+    max_chunks_ref() = chunks;
+    return LPM_OK;
+}
 extern "C" int lpm_set_pse_series(int enable) { rt().pse_series = enable != 0; return LPM_OK; }
 extern "C" int lpm_set_pse_culling(int mode)
 {

@@ -324,7 +324,7 @@ inline int direct_sum(Device& dev, cudaStream_t st, const MaskPlan& mp, int64_t 
     g.tbeg = tbeg; g.tend = tend; g.ntgt = tend - tbeg;
     g.nsrc = mp.nsrc;
     g.nall = ntargets_all >= 0 ? ntargets_all : mp.n;     // targets are the particles unless told otherwise
-    ds_chunks(mp.nsrc, &g.nsrc_pad, &g.chunk, &g.nchunks);
+    ds_chunks(mp.nsrc, &g.nsrc_pad, &g.chunk, &g.nchunks, g.nall);
     double* partial = nullptr;
     if (g.nchunks > 1) {
         LPM_TRY(dev.ws.partial.reserve((size_t)g.nchunks * K::NA * g.ntgt * sizeof(double)));
@@ -493,6 +493,13 @@ inline int launch_variant<BveVel>(int variant, cudaStream_t st, const BveVel::Pa
         case 42: launch_ds<BveVelT<4, 3310>, 8, 128, 2>(st, prm, g, src, scan, partial); break;
         case 43: launch_ds<BveVelT<4, 3744>, 8, 128, 2>(st, prm, g, src, scan, partial); break;
         case 44: launch_ds<BveVelT<4, 11873>, 8, 128, 2>(st, prm, g, src, scan, partial); break;
+        // with a register cap (min CTAs per SM): more warps to cover the dependent chains
+        case 61: launch_ds<BveVelT<4, 2102>, 8, 128, 2, 3>(st, prm, g, src, scan, partial); break;
+        case 62: launch_ds<BveVelT<4, 10313>, 8, 128, 2, 3>(st, prm, g, src, scan, partial); break;
+        case 63: launch_ds<BveVelT<4, 3680>, 8, 128, 2, 3>(st, prm, g, src, scan, partial); break;
+        case 71: launch_ds<BveVelT<4, 10737>, 4, 128, 2, 6>(st, prm, g, src, scan, partial); break;
+        case 72: launch_ds<BveVelT<4, 3680>, 4, 128, 2, 6>(st, prm, g, src, scan, partial); break;
+        case 73: launch_ds<BveVelT<4, 19845>, 4, 128, 2, 6>(st, prm, g, src, scan, partial); break;
         case 51: launch_ds<BveVelT<4, 13935>, 8, 128, 1>(st, prm, g, src, scan, partial); break;
         case 52: launch_ds<BveVelT<4, 21167>, 8, 128, 1>(st, prm, g, src, scan, partial); break;
         case 53: launch_ds<BveVelT<4, 20624>, 8, 128, 1>(st, prm, g, src, scan, partial); break;
