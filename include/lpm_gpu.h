@@ -186,6 +186,21 @@ int lpm_swe_plane_rhs_integrals(int64_t n, const double* x, const double* y, con
                                 const int32_t* mask, double pse_eps,
                                 double* u, double* v, double* double_dot, double* lap_surf);
 
+/* SetVelocityFromFieldData, src/PlanarSWE.f90:469-494 (== SWEComputeVelocity :261-290): planar
+ * velocity from relative vorticity and divergence, j /= i, active sources. */
+int lpm_swe_plane_velocity(int64_t n, const double* x, const double* y, const double* vort, const double* div,
+                           const double* area, const int32_t* mask, double* u, double* v);
+
+/* SWESphereRHSIntegrals, src/SphereSWESolver.f90:296-375, as written: velocity from vorticity and
+ * divergence on the sphere and the PSE Laplacian of the fluid surface `surf` = h + topography
+ * (evaluated by the caller).  The reference routine is unfinished: double_dot is zeroed and never
+ * accumulated, and lap_surf gets no trailing 1/eps^2 (the plane routine applies one); both are
+ * reproduced.  SphereDistance's module-global SphereRadius is taken to be `radius`. */
+int lpm_swe_sphere_rhs_integrals(int64_t n, const double* x, const double* y, const double* z, const double* vort,
+                                 const double* div, const double* surf, const double* area, const int32_t* mask,
+                                 double radius, double pse_eps, double* u, double* v, double* w, double* double_dot,
+                                 double* lap_surf);
+
 /* -------------------------- direct sums, device API (one rank's slice) */
 
 int lpm_bve_velocity_dev(int64_t n, const double* x, const double* y, const double* z,

@@ -69,6 +69,8 @@ PROTOTYPES = {
     "lpm_pse_double_dot_sphere": (_int, [_n, _d, _d, _d, _d, _d, _d, _d, _i32, _dbl, _dbl, _d]),
     "lpm_pse_divergence_sphere": (_int, [_n, _d, _d, _d, _d, _d, _d, _d, _i32, _dbl, _dbl, _d]),
     "lpm_swe_plane_rhs_integrals": (_int, [_n, _d, _d, _d, _d, _d, _d, _i32, _dbl, _d, _d, _d, _d]),
+    "lpm_swe_plane_velocity": (_int, [_n, _d, _d, _d, _d, _d, _i32, _d, _d]),
+    "lpm_swe_sphere_rhs_integrals": (_int, [_n, _d, _d, _d, _d, _d, _d, _d, _i32, _dbl, _dbl, _d, _d, _d, _d, _d]),
     # device API (device pointers passed as integers)
     "lpm_bve_velocity_dev": (_int, [_n, _vp, _vp, _vp, _vp, _vp, _vp, _dbl, _n, _n, _vp, _vp, _vp, _vp]),
     "lpm_bve_stream_dev": (_int, [_n, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _dbl, _n, _n, _vp, _vp, _vp]),

@@ -303,3 +303,22 @@ def swe_plane_rhs_integrals(x, y, vort, div, surf, area, mask, pse_eps):
     check(lib.lpm_swe_plane_rhs_integrals(x.size, _pd(x), _pd(y), _pd(vort), _pd(div), _pd(surf), _pd(area), _mi(m),
                                           float(pse_eps), *[_pd(a) for a in o]))
     return o
+
+
+def swe_plane_velocity(x, y, vort, div, area, mask):
+    """SetVelocityFromFieldData (src/PlanarSWE.f90:469-494): returns u, v."""
+    x, y, vort, div, area = map(_f64, (x, y, vort, div, area))
+    m = _mask(mask)
+    o = [np.empty(x.size) for _ in range(2)]
+    check(lib.lpm_swe_plane_velocity(x.size, _pd(x), _pd(y), _pd(vort), _pd(div), _pd(area), _mi(m), *[_pd(a) for a in o]))
+    return o
+
+
+def swe_sphere_rhs_integrals(x, y, z, vort, div, surf, area, mask, radius, pse_eps):
+    """SWESphereRHSIntegrals (src/SphereSWESolver.f90:296-375), as written: returns u, v, w, doubleDot (zero), lapSurf."""
+    x, y, z, vort, div, surf, area = map(_f64, (x, y, z, vort, div, surf, area))
+    m = _mask(mask)
+    o = [np.empty(x.size) for _ in range(5)]
+    check(lib.lpm_swe_sphere_rhs_integrals(x.size, _pd(x), _pd(y), _pd(z), _pd(vort), _pd(div), _pd(surf), _pd(area),
+                                           _mi(m), float(radius), float(pse_eps), *[_pd(a) for a in o]))
+    return o

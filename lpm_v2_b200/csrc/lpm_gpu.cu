@@ -652,5 +652,29 @@ extern "C" int lpm_swe_plane_rhs_integrals(int64_t n, const double* x, const dou
     return run_host<OpSweRhsPlane>(a, o);
 }
 
+// ---- planar SWE velocity: SetVelocityFromFieldData (src/PlanarSWE.f90:469-494) ----
+extern "C" int lpm_swe_plane_velocity(int64_t n, const double* x, const double* y, const double* vort, const double* div,
+                                      const double* area, const int32_t* mask, double* u, double* v)
+{
+    Args a{n, {x, y, vort, div, area}, mask, {}};
+    double* o[2] = {u, v};
+    return run_host<OpSwePlaneVel>(a, o);
+}
+
+// ---- spherical shallow water: SWESphereRHSIntegrals (src/SphereSWESolver.f90:296-375), as written ----
+extern "C" int lpm_swe_sphere_rhs_integrals(int64_t n, const double* x, const double* y, const double* z,
+                                            const double* vort, const double* div, const double* surf,
+                                            const double* area, const int32_t* mask, double radius, double pse_eps,
+                                            double* u, double* v, double* w, double* double_dot, double* lap_surf)
+{
+    LPM_TRY(check_eps(pse_eps, radius));
+    if (!double_dot) return set_error(LPM_ERR_INVALID, "null output array 3");
+    Args a{n, {x, y, z, vort, div, surf, area}, mask, {radius, pse_eps}};
+    double* o[4] = {u, v, w, lap_surf};
+    LPM_TRY(run_host<OpSweRhsSphere>(a, o));
+    memset(double_dot, 0, (size_t)n * sizeof(double));      // the reference zeroes it and never accumulates it (:328)
+    return LPM_OK;
+}
+
 // ============================================================== resident solvers
 #include "solvers_api.inc"

@@ -381,4 +381,52 @@ struct OpSweRhsPlane {
     static int variant() { return 0; }
 };
 
+// ---- planar SWE velocity (PlanarSWE.f90:469-494): in = x y vort div area; out = u v
+struct OpSwePlaneVel {
+    using K = SwePlaneVel;
+    static constexpr int NIN = 5, NOUT = 2, NTGT = 0;
+    static int pack(Device& dev, cudaStream_t st, const MaskPlan& mp, const Args& a)
+    {
+        int32_t pad;
+        LPM_TRY(reserve_sources<K>(dev, mp, &pad));
+        pack_swe_plane_vel<<<pack_grid(pad), 256, 0, st>>>(mp.nsrc, pad, mp.active.as<int32_t>(), a.in[0], a.in[1], a.in[2],
+                                                           a.in[3], a.in[4], dev.ws.sources.as<double>());
+        count_launch();
+        return LPM_OK;
+    }
+    static K::Params params(const Args& a)
+    {
+        K::Params p{};
+        p.x = a.in[0]; p.y = a.in[1];
+        return p;
+    }
+    static int variant() { return 0; }
+};
+
+// ---- spherical SWE RHS integrals (SphereSWESolver.f90:296-375): in = x y z vort div surf area;
+//      sc = radius, eps; out = u v w lapSurf
+struct OpSweRhsSphere {
+    using K = SweRhsSphere;
+    static constexpr int NIN = 7, NOUT = 4, NTGT = 0;
+    static int pack(Device& dev, cudaStream_t st, const MaskPlan& mp, const Args& a)
+    {
+        int32_t pad;
+        LPM_TRY(reserve_sources<K>(dev, mp, &pad));
+        pack_swe_sphere<<<pack_grid(pad), 256, 0, st>>>(mp.nsrc, pad, mp.active.as<int32_t>(), a.in[0], a.in[1], a.in[2],
+                                                        a.in[3], a.in[4], a.in[5], a.in[6], a.sc[0], a.sc[1],
+                                                        dev.ws.sources.as<double>());
+        count_launch();
+        return LPM_OK;
+    }
+    static K::Params params(const Args& a)
+    {
+        K::Params p{};
+        p.x = a.in[0]; p.y = a.in[1]; p.z = a.in[2]; p.surf = a.in[5];
+        p.R2 = a.sc[0] * a.sc[0];
+        p.c = pse_sphere_consts(a.sc[1], a.sc[0], 1.0);      // SphereDistance uses the sphere's radius
+        return p;
+    }
+    static int variant() { return 0; }
+};
+
 }  // namespace lpm

@@ -800,6 +800,7 @@ __global__ void pack_beta(int32_t nsrc, int32_t nsrc_pad, const int32_t* __restr
 // j == i is included (the term is exactly zero).  eta decays like exp(-k^2):
 // pairs with k > kPseCut contribute < 1e-23 of eta(0) and are skipped.
 constexpr double kPseCut = 8.0;
+constexpr double kNullNorm = 1.0e300;     // |x| of a padding source in the sphere PSE records
 
 // Culling geometry.  Sphere kernels reject a pair by its ANGLE (dot < cos_cut |x_i| |x_j|), so
 // points are compared as unit vectors: an accepted pair has |u_i - u_j| <= 2 sin(theta_cut / 2)
@@ -985,7 +986,9 @@ __global__ void pack_pse_sphere(int32_t nsrc, int32_t nsrc_pad, const int32_t* _
 {
     int32_t c = blockIdx.x * blockDim.x + threadIdx.x;
     if (c >= nsrc_pad) return;
-    double r[6] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0};     // null source: zero area
+    // null source: zero area, and a norm so large that the cut-off test (dot < thr |x_j|) rejects it
+    // before the distance is evaluated (0 / 0 in the series form of sphere_k2)
+    double r[6] = {0.0, 0.0, 0.0, 0.0, 0.0, kNullNorm};
     if (c < nsrc) {
         int32_t j = active[c];
         r[0] = x[j]; r[1] = y[j]; r[2] = z[j]; r[3] = f[j];

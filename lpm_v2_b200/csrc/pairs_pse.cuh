@@ -92,7 +92,7 @@ __global__ void pack_pse_interp(int32_t nsrc, int32_t nsrc_pad, const int32_t* _
 {
     int32_t c = blockIdx.x * blockDim.x + threadIdx.x;
     if (c >= nsrc_pad) return;
-    double r[6] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
+    double r[6] = {0.0, 0.0, 0.0, 0.0, sphere ? kNullNorm : 0.0, 0.0};      // null source (see pack_pse_sphere)
     if (c < nsrc) {
         int32_t j = active[c];
         double w = f[j] * area[j] / (LPM_PI * eps * eps);
@@ -329,6 +329,8 @@ __global__ void pack_pse_generic(int32_t nsrc, int32_t nsrc_pad, const int32_t* 
     if (c >= nsrc_pad) return;
     double r[8] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
     const int ns = (layout == 0) ? 4 : (layout == 3) ? 8 : 6;
+    if (layout == 1) r[5] = kNullNorm;           // null source of the sphere layouts (see pack_pse_sphere)
+    if (layout == 3) r[7] = kNullNorm;
     if (c < nsrc) {
         int32_t j = active[c];
         double w = area[j] * wscale;

@@ -477,32 +477,14 @@ inline int launch_variant<BveVel>(int variant, cudaStream_t st, const BveVel::Pa
         case 13: launch_ds<K, 8, 128, 2>(st, prm, g, src, scan, partial); break;
         case 14: launch_ds<K, 4, 128, 1>(st, prm, g, src, scan, partial); break;
         case 15: launch_ds<K, 4, 192, 2>(st, prm, g, src, scan, partial); break;
-        // register budgets stated to ptxas (__launch_bounds__ min CTAs): it schedules for ILP within the budget
-        case 16: launch_ds<K, 4, 128, 2, 4>(st, prm, g, src, scan, partial); break;
-        case 17: launch_ds<K, 4, 128, 4, 4>(st, prm, g, src, scan, partial); break;
-        case 18: launch_ds<K, 4, 256, 2, 2>(st, prm, g, src, scan, partial); break;
-        case 19: launch_ds<K, 8, 128, 2, 3>(st, prm, g, src, scan, partial); break;
-        case 20: launch_ds<K, 4, 128, 2, 5>(st, prm, g, src, scan, partial); break;
-        case 21: launch_ds<K, 4, 128, 2, 6>(st, prm, g, src, scan, partial); break;
-        // statement orders short-listed by tools/search_order.py (same arithmetic; see BveVelT in pairs.cuh)
+        // Statement orders short-listed by tools/search_order.py (same arithmetic; see BveVelT in pairs.cuh)
+        // and measured by tools/sweep_bve.py (profiles/r01b_sweep_L{7,8}_orders.log).  Shapes that lost the
+        // sweeps -- register caps of 80 / 96 / 128 / 168 per thread, U = 1 with 8 targets, other orders --
+        // are no longer instantiated (profiles/r01c_sweep_L7_caps.log).
         case 31: launch_ds<BveVelT<4, 11713>, 4, 128, 2>(st, prm, g, src, scan, partial); break;
         case 32: launch_ds<BveVelT<4, 10765>, 4, 128, 2>(st, prm, g, src, scan, partial); break;
-        case 33: launch_ds<BveVelT<4, 2319>, 4, 128, 2>(st, prm, g, src, scan, partial); break;
-        case 34: launch_ds<BveVelT<4, 10593>, 4, 128, 2>(st, prm, g, src, scan, partial); break;
         case 41: launch_ds<BveVelT<4, 3680>, 8, 128, 2>(st, prm, g, src, scan, partial); break;
-        case 42: launch_ds<BveVelT<4, 3310>, 8, 128, 2>(st, prm, g, src, scan, partial); break;
         case 43: launch_ds<BveVelT<4, 3744>, 8, 128, 2>(st, prm, g, src, scan, partial); break;
-        case 44: launch_ds<BveVelT<4, 11873>, 8, 128, 2>(st, prm, g, src, scan, partial); break;
-        // with a register cap (min CTAs per SM): more warps to cover the dependent chains
-        case 61: launch_ds<BveVelT<4, 2102>, 8, 128, 2, 3>(st, prm, g, src, scan, partial); break;
-        case 62: launch_ds<BveVelT<4, 10313>, 8, 128, 2, 3>(st, prm, g, src, scan, partial); break;
-        case 63: launch_ds<BveVelT<4, 3680>, 8, 128, 2, 3>(st, prm, g, src, scan, partial); break;
-        case 71: launch_ds<BveVelT<4, 10737>, 4, 128, 2, 6>(st, prm, g, src, scan, partial); break;
-        case 72: launch_ds<BveVelT<4, 3680>, 4, 128, 2, 6>(st, prm, g, src, scan, partial); break;
-        case 73: launch_ds<BveVelT<4, 19845>, 4, 128, 2, 6>(st, prm, g, src, scan, partial); break;
-        case 51: launch_ds<BveVelT<4, 13935>, 8, 128, 1>(st, prm, g, src, scan, partial); break;
-        case 52: launch_ds<BveVelT<4, 21167>, 8, 128, 1>(st, prm, g, src, scan, partial); break;
-        case 53: launch_ds<BveVelT<4, 20624>, 8, 128, 1>(st, prm, g, src, scan, partial); break;
         default: return set_error(LPM_ERR_INVALID, "unknown BVE kernel variant %d", variant);
     }
     return LPM_OK;

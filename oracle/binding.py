@@ -346,3 +346,27 @@ def swe_plane_rhs(x, y, vort, div, surf, area, mask, pse_eps):
     lib.oracle_swe_plane_rhs(x.size, _p(x), _p(y), _p(vort), _p(div), _p(surf), _p(area), m.ctypes.data_as(_i32),
                              pse_eps, 0, x.size, *[_p(a) for a in o])
     return o
+
+
+def swe_plane_velocity(x, y, vort, div, area, mask):
+    x, y, vort, div, area = map(_f, (x, y, vort, div, area))
+    m = _m(mask)
+    lib = get()
+    lib.oracle_swe_plane_velocity.argtypes = [_n, _d, _d, _d, _d, _d, _i32, _n, _n, _d, _d]
+    lib.oracle_swe_plane_velocity.restype = None
+    o = [np.zeros(x.size) for _ in range(2)]
+    lib.oracle_swe_plane_velocity(x.size, _p(x), _p(y), _p(vort), _p(div), _p(area), m.ctypes.data_as(_i32), 0, x.size,
+                                  *[_p(a) for a in o])
+    return o
+
+
+def swe_sphere_rhs(x, y, z, vort, div, surf, area, mask, radius, pse_eps):
+    x, y, z, vort, div, surf, area = map(_f, (x, y, z, vort, div, surf, area))
+    m = _m(mask)
+    lib = get()
+    lib.oracle_swe_sphere_rhs.argtypes = [_n, _d, _d, _d, _d, _d, _d, _d, _i32, _dbl, _dbl, _n, _n, _d, _d, _d, _d, _d]
+    lib.oracle_swe_sphere_rhs.restype = None
+    o = [np.zeros(x.size) for _ in range(5)]
+    lib.oracle_swe_sphere_rhs(x.size, _p(x), _p(y), _p(z), _p(vort), _p(div), _p(surf), _p(area), m.ctypes.data_as(_i32),
+                              radius, pse_eps, 0, x.size, *[_p(a) for a in o])
+    return o

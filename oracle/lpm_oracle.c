@@ -835,3 +835,60 @@ void oracle_swe_plane_rhs(int64_t n, const double *x, const double *y, const dou
         doubleDot[i] = ux * ux + 2.0 * uy * vx + vy * vy;
     }
 }
+
+/* src/PlanarSWE.f90:469-494  SetVelocityFromFieldData (private body; SWEComputeVelocity :261-290
+ * is the same sum): planar velocity from relative vorticity and divergence,
+ *   u_i = sum_{j /= i, active} [ -(y_i - y_j) rot + (x_i - x_j) pot ],  v_i = sum [ (x_i - x_j) rot + (y_i - y_j) pot ],
+ *   rot = zeta_j A_j / (2 pi r^2), pot = delta_j A_j / (2 pi r^2). */
+void oracle_swe_plane_velocity(int64_t n, const double *x, const double *y, const double *vort, const double *div,
+                               const double *area, const int32_t *mask, int64_t ibeg, int64_t iend, double *u, double *v)
+{
+    for (int64_t i = ibeg; i < iend; ++i) {
+        u[i] = 0.0; v[i] = 0.0;
+        for (int64_t j = 0; j < n; ++j) {
+            if (i != j && mask[j]) {
+                double sqDist = (x[i] - x[j]) * (x[i] - x[j]) + (y[i] - y[j]) * (y[i] - y[j]);
+                double denom = 2.0 * PI * sqDist;
+                double rotStrength = vort[j] * area[j] / denom;
+                double potStrength = div[j] * area[j] / denom;
+                u[i] = u[i] - (y[i] - y[j]) * rotStrength + (x[i] - x[j]) * potStrength;
+                v[i] = v[i] + (x[i] - x[j]) * rotStrength + (y[i] - y[j]) * potStrength;
+            }
+        }
+    }
+}
+
+/* src/SphereSWESolver.f90:296-375  SWESphereRHSIntegrals, as written: velocity from vorticity
+ * and divergence on the sphere and the PSE Laplacian of the fluid surface (surf = h + topography,
+ * evaluated by the caller).  The reference routine is unfinished: doubleDot is zeroed and never
+ * accumulated (:328, the ux.. sums are dropped) and nothing is broadcast; this restates what
+ * it does compute.  The Laplacian is NOT post-scaled by 1/eps^2 here (the plane twin does it
+ * at SWEPlaneSolver.f90:556; the sphere routine has no such line). */
+void oracle_swe_sphere_rhs(int64_t n, const double *x, const double *y, const double *z, const double *relVort,
+                           const double *div, const double *surf, const double *area, const int32_t *mask,
+                           double radius, double pseEps, int64_t ibeg, int64_t iend, double *u, double *v, double *w,
+                           double *doubleDot, double *lapSurf)
+{
+    const double fourPiRsq = 4.0 * PI * radius * radius;
+    for (int64_t i = ibeg; i < iend; ++i) {
+        u[i] = 0.0; v[i] = 0.0; w[i] = 0.0; doubleDot[i] = 0.0; lapSurf[i] = 0.0;
+        const double surfHeightI = surf[i];
+        for (int64_t j = 0; j < n; ++j) {
+            if (mask[j]) {
+                const double surfHeightJ = surf[j];
+                const double xi[3] = {x[i], y[i], z[i]}, xj[3] = {x[j], y[j], z[j]};
+                const double pseKin = SphereDistance(xi, xj, radius) / pseEps;
+                const double lapKernel = bivariateLaplacianKernel8(pseKin) / (pseEps * pseEps);
+                lapSurf[i] = lapSurf[i] + lapKernel * (surfHeightJ - surfHeightI) * area[j];
+                if (i == j) continue;
+                const double dotProd = x[i] * x[j] + y[i] * y[j] + z[i] * z[j];
+                const double denom = fourPiRsq * (radius * radius - dotProd);
+                const double rotStrength = relVort[j] * area[j] / denom;
+                const double potStrength = radius * div[j] * area[j] / denom;
+                u[i] = u[i] - (y[i] * z[j] - z[i] * y[j]) * rotStrength - x[j] * potStrength;
+                v[i] = v[i] - (z[i] * x[j] - x[i] * z[j]) * rotStrength - y[j] * potStrength;
+                w[i] = w[i] - (x[i] * y[j] - y[i] * x[j]) * rotStrength - z[j] * potStrength;
+            }
+        }
+    }
+}

@@ -126,7 +126,7 @@ def test_bve_all_active_self_exclusion(gpu, oracle):
     assert max(relerr(g, w) for g, w in zip(got, want)) <= TOL
 
 
-@pytest.mark.parametrize("variant", list(range(1, 16)))
+@pytest.mark.parametrize("variant", list(range(1, 16)) + [31, 32, 41, 43])
 def test_bve_kernel_variants(gpu, oracle, get_mesh, variant):
     """Every tuning variant (targets per thread, block size, reciprocal batching) is a
     correct kernel: each meets the parity tolerance on its own.  (They differ from each

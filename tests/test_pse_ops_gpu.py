@@ -183,3 +183,31 @@ def test_sphere_distance_series_matches_atan2(gpu, oracle, get_mesh, L, power):
         assert relerr(a, b) <= 1e-13
     if L <= 5:
         assert relerr(series[0], oracle.pse_laplacian_sphere(*args, f, m.area, m.is_active, eps, 1.0)) <= TOL
+
+
+@pytest.mark.parametrize("L,power", [(2, 0.9), (4, 0.75)])
+def test_sphere_padding_sources(gpu, oracle, get_mesh, L, power):
+    """Active counts that are not a multiple of the 256-source tile: the padding records must
+    not reach the distance evaluation (0/0 in its series form).  L2 has 320 sources; at L4 a
+    ragged mask leaves 5120 - 173."""
+    m = get_mesh(M.ICOS_TRI_SPHERE_SEED, L)
+    mask = m.is_active.copy()
+    if L == 4:
+        act = np.nonzero(mask)[0]
+        mask[act[::30][:173]] = 0
+    assert int(mask.sum()) % 256 != 0
+    eps = m.max_edge_length ** power
+    f = problems.spherical_harmonic54(m)
+    u, v, w = -m.y + 0.3 * m.z * m.x, m.x * m.x, 0.5 * m.y - m.z
+    args = (m.x, m.y, m.z)
+    lap = gpu.pse_laplacian_sphere(*args, f, m.area, mask, eps, 1.0)
+    assert np.all(np.isfinite(lap))
+    assert relerr(lap, oracle.pse_laplacian_sphere(*args, f, m.area, mask, eps, 1.0)) <= TOL
+    g = gpu.pse_gradient_sphere(*args, f, m.area, mask, eps)
+    want = oracle.pse_gradient_sphere(*args, f, m.area, mask, eps)
+    scale = max(np.abs(a).max() for a in want)
+    assert max(np.abs(a - b).max() for a, b in zip(g, want)) <= TOL * scale
+    assert relerr(gpu.pse_divergence_sphere(*args, u, v, w, m.area, mask, eps),
+                  oracle.pse_divergence_sphere(*args, u, v, w, m.area, mask, eps)) <= TOL
+    assert relerr(gpu.pse_interpolate_sphere(*args, f, m.area, mask, eps, m.x[::3], m.y[::3], m.z[::3]),
+                  oracle.pse_interpolate(*args, f, m.area, mask, eps, m.x[::3], m.y[::3], m.z[::3])) <= TOL
