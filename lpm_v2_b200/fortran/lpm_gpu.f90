@@ -16,8 +16,10 @@ public :: lpm_betaplane_velocity, lpm_betaplane_stream
 public :: lpm_pse_laplacian_sphere, lpm_pse_laplacian_plane
 public :: lpm_pse_interpolate_sphere, lpm_pse_gradient_sphere, lpm_pse_divergence_sphere
 public :: lpm_pse_gradient_plane, lpm_pse_second_partials_plane, lpm_pse_double_dot_plane
-public :: lpm_swe_plane_rhs_integrals
+public :: lpm_swe_plane_rhs_integrals, lpm_swe_plane_velocity, lpm_swe_sphere_rhs_integrals
 public :: lpm_gpu_pin, lpm_gpu_unpin
+public :: lpm_gpu_init_rank, lpm_comm_unique_id, lpm_comm_init_rank, lpm_comm_alloc_shared, lpm_comm_free_shared
+public :: lpm_bve_velocity_dev
 public :: lpm_bve_solver_new, lpm_bve_solver_timestep, lpm_bve_solver_get_state, lpm_bve_solver_delete
 
 interface
@@ -243,6 +245,27 @@ interface
 		integer(c_int), intent(in) :: mask(*)
 		real(c_double), value :: pse_eps
 		real(c_double), intent(out) :: u(*), v(*), doubleDot(*), lapSurf(*)
+	end function
+
+	!> SetVelocityFromFieldData (PlanarSWE.f90:469-494)
+	integer(c_int) function lpm_swe_plane_velocity(n, x, y, vort, div, area, mask, u, v) &
+			bind(C, name="lpm_swe_plane_velocity")
+		import :: c_int, c_int64_t, c_double
+		integer(c_int64_t), value :: n
+		real(c_double), intent(in) :: x(*), y(*), vort(*), div(*), area(*)
+		integer(c_int), intent(in) :: mask(*)
+		real(c_double), intent(out) :: u(*), v(*)
+	end function
+
+	!> SWESphereRHSIntegrals (SphereSWESolver.f90:296-375); surf = h + topoFn(x, y, z)
+	integer(c_int) function lpm_swe_sphere_rhs_integrals(n, x, y, z, vort, div, surf, area, mask, radius, pse_eps, &
+			u, v, w, doubleDot, lapSurf) bind(C, name="lpm_swe_sphere_rhs_integrals")
+		import :: c_int, c_int64_t, c_double
+		integer(c_int64_t), value :: n
+		real(c_double), intent(in) :: x(*), y(*), z(*), vort(*), div(*), surf(*), area(*)
+		integer(c_int), intent(in) :: mask(*)
+		real(c_double), value :: radius, pse_eps
+		real(c_double), intent(out) :: u(*), v(*), w(*), doubleDot(*), lapSurf(*)
 	end function
 
 	!> device-resident BVESolver: New / Timestep / Delete (SphereBVESolver.f90:112-168, 219-353)
