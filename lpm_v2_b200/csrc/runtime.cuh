@@ -180,6 +180,8 @@ inline int alloc_shared(size_t bytes, void** out)
     LPM_TRY(require_init());
     if (!R.rank_mode) return set_error(LPM_ERR_INVALID, "lpm_comm_alloc_shared needs rank mode (lpm_gpu_init_rank)");
     if (bytes == 0) return set_error(LPM_ERR_INVALID, "lpm_comm_alloc_shared(0)");
+    if (R.world > 8) return set_error(LPM_ERR_INVALID, "at most 8 ranks");
+    if (R.world > 1 && !R.comm) return set_error(LPM_ERR_COMM, "lpm_comm_alloc_shared before lpm_comm_init_rank");
     Device& dev = R.devs[0];
     LPM_CUDA(cudaSetDevice(dev.id));
     SharedSlab s;
@@ -187,9 +189,9 @@ inline int alloc_shared(size_t bytes, void** out)
     cudaError_t e = cudaMalloc((void**)&s.local, bytes);
     if (e != cudaSuccess) return set_error(LPM_ERR_NOMEM, "cudaMalloc(%zu bytes) failed: %s", bytes, cudaGetErrorString(e));
     s.peer[R.rank] = s.local;
-    if (R.world > 1) {
-        if (!R.comm) return set_error(LPM_ERR_COMM, "lpm_comm_alloc_shared before lpm_comm_init_rank");
-        if (R.world > 8) return set_error(LPM_ERR_INVALID, "at most 8 ranks");
+    // on any failure below: close what was opened, free the buffer (the other ranks fail the same call)
+    auto body = [&]() -> int {
+        if (R.world <= 1) return LPM_OK;
         // exchange the IPC handles with an all-gather of 64 bytes per rank
         cudaIpcMemHandle_t mine, all[8];
         static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
@@ -203,11 +205,20 @@ inline int alloc_shared(size_t bytes, void** out)
         for (int r = 0; r < R.world; ++r) {
             if (r == R.rank) continue;
             void* p = nullptr;
-            e = cudaIpcOpenMemHandle(&p, all[r], cudaIpcMemLazyEnablePeerAccess);
-            if (e != cudaSuccess)
-                return set_error(LPM_ERR_COMM, "cudaIpcOpenMemHandle(rank %d): %s", r, cudaGetErrorString(e));
+            cudaError_t oe = cudaIpcOpenMemHandle(&p, all[r], cudaIpcMemLazyEnablePeerAccess);
+            if (oe != cudaSuccess)
+                return set_error(LPM_ERR_COMM, "cudaIpcOpenMemHandle(rank %d): %s", r, cudaGetErrorString(oe));
             s.peer[r] = (char*)p;
         }
+        return LPM_OK;
+    };
+    const int rc = body();
+    if (rc != LPM_OK) {
+        for (int r = 0; r < R.world; ++r)
+            if (r != R.rank && s.peer[r]) cudaIpcCloseMemHandle(s.peer[r]);
+        cudaFree(s.local);
+        cudaGetLastError();
+        return rc;
     }
     R.slabs.push_back(s);
     *out = s.local;
