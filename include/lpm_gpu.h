@@ -325,6 +325,14 @@ int64_t lpm_mesh_num_leaf_edges(const lpm_mesh* m);
 double lpm_mesh_max_edge_length(const lpm_mesh* m);   /* src/Edges.f90:260-275 */
 int lpm_mesh_get_particles(const lpm_mesh* m, double* x, double* y, double* z, double* area, int32_t* is_active);
 int lpm_mesh_get_leaf_faces(const lpm_mesh* m, int32_t* verts, int32_t* center);
+/* Legacy ASCII .vtk PolyData file of the mesh and `nfields` point fields, in the layout of
+ * OutputToVTK (src/SphereBVE.f90:283-328): POINTS, POLYGONS (each leaf face as triangles around
+ * its centre particle), POINT_DATA (lagParam, then the fields: names[f] = "name_units", ndim[f] in
+ * 1..3, data[f] = ndim[f] component arrays of N doubles stored one after the other), CELL_DATA
+ * faceArea.  x, y, z: current particle positions, or NULL for the mesh's own. */
+int lpm_mesh_write_vtk(const lpm_mesh* m, const char* filename, const char* title, const double* x, const double* y,
+                       const double* z, int nfields, const char* const* names, const int* ndim,
+                       const double* const* data);
 
 #ifdef __cplusplus
 }

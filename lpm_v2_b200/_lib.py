@@ -119,6 +119,8 @@ PROTOTYPES = {
     "lpm_mesh_max_edge_length": (_dbl, [_vp]),
     "lpm_mesh_get_particles": (_int, [_vp, _d, _d, _d, _d, _i32]),
     "lpm_mesh_get_leaf_faces": (_int, [_vp, _i32, _i32]),
+    "lpm_mesh_write_vtk": (_int, [_vp, C.c_char_p, C.c_char_p, _d, _d, _d, _int, C.POINTER(C.c_char_p), C.POINTER(_int),
+                                  C.POINTER(_d)]),
 }
 
 for _name, (_res, _args) in PROTOTYPES.items():

@@ -24,6 +24,7 @@
 // reference Fortran (out of scope).
 #include <cmath>
 #include <cstdint>
+#include <cstdio>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -377,6 +378,70 @@ int lpm_mesh_get_leaf_faces(const lpm_mesh* h, int32_t* verts, int32_t* center)
         ++c;
     }
     return LPM_OK;
+}
+
+// Legacy-format ASCII .vtk PolyData output of a mesh and point fields, the layout of the
+// reference's outputVTKPrivate (src/SphereBVE.f90:283-328): header (src/OutputWriter.f90:272-283),
+// POINTS (src/Particles.f90:368-390), POLYGONS -- every leaf face as vertsPerFace triangles
+// (vertex j, vertex j+1, centre particle), 0-based (src/Faces.f90:388-408), POINT_DATA with
+// lagParam (src/Particles.f90:419-436; the uniform meshes here have x0 == x at creation, so the
+// mesh's own coordinates are the Lagrangian parameter) and the caller's fields
+// (src/Field.f90:285-311: "SCALARS name  double nDim", scalars below ZERO_TOL = 1e-14 written as 0),
+// CELL_DATA faceArea (src/Faces.f90:418-440).  Positions x, y, z may be NULL (the mesh's own);
+// field f has ndim[f] components stored one after the other in data[f] (ndim[f] * N doubles).
+// Numbers are written with 17 significant digits (the reference's list-directed output is
+// compiler dependent; any VTK reader accepts both).
+int lpm_mesh_write_vtk(const lpm_mesh* h, const char* filename, const char* title, const double* x, const double* y,
+                       const double* z, int nfields, const char* const* names, const int* ndim,
+                       const double* const* data)
+{
+    if (!h || !filename || nfields < 0 || (nfields > 0 && (!names || !ndim || !data))) return LPM_ERR_INVALID;
+    const Mesh& m = h->m;
+    const int64_t n = m.nParticles();
+    for (int f = 0; f < nfields; ++f)
+        if (!names[f] || !data[f] || ndim[f] < 1 || ndim[f] > 3) return LPM_ERR_INVALID;
+    FILE* fp = std::fopen(filename, "w");
+    if (!fp) return LPM_ERR_INVALID;
+    const double* px = x ? x : m.x.data();
+    const double* py = y ? y : m.y.data();
+    const double* pz = z ? z : m.z.data();
+    const bool planar = !m.sphere;
+    std::fprintf(fp, "# vtk DataFile Version 2.0\n%s\nASCII\nDATASET POLYDATA\n", (title && *title) ? title : " ");
+    std::fprintf(fp, "POINTS %8lld double \n", (long long)n);
+    for (int64_t j = 0; j < n; ++j) std::fprintf(fp, "%.17g %.17g %.17g\n", px[j], py[j], planar ? 0.0 : pz[j]);
+    int64_t nleaf = 0;
+    for (uint8_t k : m.fHasKids) nleaf += !k;
+    const int64_t ncells = (int64_t)m.vpf * nleaf;
+    std::fprintf(fp, "POLYGONS %8lld   %8lld\n", (long long)ncells, (long long)(4 * ncells));
+    for (int64_t f = 0; f < m.nFaces(); ++f) {
+        if (m.fHasKids[f]) continue;
+        for (int j = 0; j < m.vpf; ++j)
+            std::fprintf(fp, "%10d%10d%10d%10d\n", 3, m.fVerts[f * m.vpf + j], m.fVerts[f * m.vpf + (j + 1) % m.vpf],
+                         m.fCenter[f]);
+    }
+    std::fprintf(fp, "POINT_DATA %8lld\n", (long long)n);
+    std::fprintf(fp, "SCALARS lagParam double 3\nLOOKUP_TABLE default\n");
+    for (int64_t j = 0; j < n; ++j) std::fprintf(fp, "%.17g %.17g %.17g\n", m.x[j], m.y[j], planar ? 0.0 : m.z[j]);
+    for (int f = 0; f < nfields; ++f) {
+        std::fprintf(fp, "SCALARS %s  double %4d\nLOOKUP_TABLE default\n", names[f], ndim[f]);
+        const double* d = data[f];
+        for (int64_t j = 0; j < n; ++j) {
+            if (ndim[f] == 1) {
+                std::fprintf(fp, "%.17g\n", std::fabs(d[j]) < 1.0e-14 ? 0.0 : d[j]);
+            } else if (ndim[f] == 2) {
+                std::fprintf(fp, "%.17g %.17g\n", d[j], d[n + j]);
+            } else {
+                std::fprintf(fp, "%.17g %.17g %.17g\n", d[j], d[n + j], d[2 * n + j]);
+            }
+        }
+    }
+    std::fprintf(fp, "CELL_DATA %8lld\nSCALARS faceArea double 1\nLOOKUP_TABLE default\n", (long long)ncells);
+    for (int64_t f = 0; f < m.nFaces(); ++f) {
+        if (m.fHasKids[f]) continue;
+        for (int j = 0; j < m.vpf; ++j) std::fprintf(fp, "%.17g\n", m.area[m.fCenter[f]]);
+    }
+    const bool ok = std::ferror(fp) == 0;
+    return (std::fclose(fp) == 0 && ok) ? LPM_OK : LPM_ERR_INVALID;
 }
 
 }  // extern "C"

@@ -33,6 +33,7 @@ class PolyMesh2d:
         try:
             self.seed = seed
             self.init_nest = init_nest
+            self._amp = amp_factor
             n = lib.lpm_mesh_num_particles(h)
             self.n = int(n)
             self.n_faces_total = int(lib.lpm_mesh_num_faces(h))
@@ -56,3 +57,31 @@ class PolyMesh2d:
     @property
     def n_active(self):
         return int(self.is_active.sum())
+
+    def write_vtk(self, filename, fields=(), title="", positions=None):
+        """OutputToVTK (src/SphereBVE.f90:283-328): legacy ASCII .vtk PolyData of the mesh and point
+        fields.  `fields` = [(name_units, array or tuple of 2-3 component arrays), ...];
+        `positions` = current (x, y, z) of the particles, default the mesh's own."""
+        h = C.c_void_p()
+        check(lib.lpm_mesh_create(int(self.seed), int(self.init_nest), float(self._amp), C.byref(h)))
+        try:
+            names, ndim, blobs = [], [], []
+            for name, val in fields:
+                comps = [val] if isinstance(val, np.ndarray) else list(val)
+                blob = np.ascontiguousarray(np.concatenate([np.asarray(c, np.float64).ravel() for c in comps]))
+                assert blob.size == len(comps) * self.n, name
+                names.append(name.encode()); ndim.append(len(comps)); blobs.append(blob)
+            k = len(names)
+            c_names = (C.c_char_p * max(k, 1))(*names)
+            c_ndim = (C.c_int * max(k, 1))(*ndim)
+            c_data = (_d * max(k, 1))(*[b.ctypes.data_as(_d) for b in blobs])
+            pos = [None, None, None]
+            if positions is not None:
+                pos = [np.ascontiguousarray(p, np.float64) for p in positions]
+                while len(pos) < 3:
+                    pos.append(None)
+            pp = [p.ctypes.data_as(_d) if p is not None else None for p in pos]
+            check(lib.lpm_mesh_write_vtk(h, str(filename).encode(), title.encode(), pp[0], pp[1], pp[2], k, c_names,
+                                         c_ndim, c_data))
+        finally:
+            lib.lpm_mesh_destroy(h)

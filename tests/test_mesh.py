@@ -81,3 +81,76 @@ def test_max_edge_length(get_mesh):
     assert abs(h[0] - np.arctan(2.0)) < 1e-14          # icosahedron edge angle
     for a, b in zip(h, h[1:]):
         assert 1.7 < a / b < 2.05
+
+
+def _parse_vtk(path):
+    toks = open(path).read().split("\n")
+    assert toks[0] == "# vtk DataFile Version 2.0" and toks[2] == "ASCII" and toks[3] == "DATASET POLYDATA"
+    out = {"title": toks[1], "fields": {}}
+    i = 4
+    while i < len(toks):
+        ln = toks[i].split()
+        if not ln:
+            i += 1
+            continue
+        if ln[0] == "POINTS":
+            n = int(ln[1])
+            out["points"] = np.array([[float(v) for v in toks[i + 1 + k].split()] for k in range(n)])
+            i += 1 + n
+        elif ln[0] == "POLYGONS":
+            nc, size = int(ln[1]), int(ln[2])
+            out["polys"] = np.array([[int(v) for v in toks[i + 1 + k].split()] for k in range(nc)])
+            assert size == 4 * nc
+            i += 1 + nc
+        elif ln[0] in ("POINT_DATA", "CELL_DATA"):
+            section, count = ln[0], int(ln[1])
+            i += 1
+        elif ln[0] == "SCALARS":
+            name, nd = ln[1], int(ln[3])
+            assert toks[i + 1] == "LOOKUP_TABLE default"
+            vals = np.array([[float(v) for v in toks[i + 2 + k].split()] for k in range(count)])
+            assert vals.shape == (count, nd)
+            out["fields"][(section, name)] = vals
+            i += 2 + count
+        else:
+            raise AssertionError(f"unexpected line {i}: {toks[i]!r}")
+    return out
+
+
+@pytest.mark.parametrize("seed,L", [(M.ICOS_TRI_SPHERE_SEED, 2), (M.CUBED_SPHERE_SEED, 1), (M.QUAD_RECT_SEED, 2)])
+def test_write_vtk_layout(tmp_path, seed, L):
+    """OutputToVTK (src/SphereBVE.f90:283-328): POINTS, POLYGONS (leaf faces as triangles around their
+    centre particle, 0-based), POINT_DATA lagParam + fields, CELL_DATA faceArea; exact round trip."""
+    m = M.PolyMesh2d(seed, L, 2.0 if seed == M.QUAD_RECT_SEED else 1.0)
+    sphere = seed != M.QUAD_RECT_SEED
+    zeta = np.cos(3 * m.x) + m.y
+    zeta[5] = 3e-15                                    # below ZERO_TOL: written as 0 (Field.f90:299-303)
+    vel = (-m.y, m.x, 0.1 * m.z) if sphere else (-m.y, m.x)
+    moved = (m.x + 0.01, m.y - 0.02, m.z)
+    path = tmp_path / "mesh.vtk"
+    m.write_vtk(path, [("relVort_1/s", zeta), ("velocity_m/s", vel)], title="unit test", positions=moved)
+    v = _parse_vtk(path)
+    assert v["title"] == "unit test"
+    pts = np.stack([moved[0], moved[1], moved[2] if sphere else 0 * m.x], 1)
+    assert np.array_equal(v["points"], pts)
+    vpf = m.face_verts.shape[1]
+    assert v["polys"].shape == (vpf * m.n_leaf_faces, 4) and np.all(v["polys"][:, 0] == 3)
+    for f in range(m.n_leaf_faces):
+        for j in range(vpf):
+            row = v["polys"][f * vpf + j]
+            assert row[1] == m.face_verts[f, j] and row[2] == m.face_verts[f, (j + 1) % vpf] and row[3] == m.face_center[f]
+    lag = np.stack([m.x, m.y, m.z if sphere else 0 * m.x], 1)
+    assert np.array_equal(v["fields"][("POINT_DATA", "lagParam")], lag)
+    z0 = zeta.copy()
+    z0[5] = 0.0
+    assert np.array_equal(v["fields"][("POINT_DATA", "relVort_1/s")][:, 0], z0)
+    assert np.array_equal(v["fields"][("POINT_DATA", "velocity_m/s")], np.stack(vel, 1))
+    area = v["fields"][("CELL_DATA", "faceArea")][:, 0]
+    assert np.array_equal(area, np.repeat(m.area[m.face_center], vpf))
+    # the sub-triangles tile the mesh: their flat areas approach the panel areas
+    if not sphere:
+        p = v["points"]
+        tri = v["polys"][:, 1:]
+        a = 0.5 * np.abs((p[tri[:, 1], 0] - p[tri[:, 0], 0]) * (p[tri[:, 2], 1] - p[tri[:, 0], 1]) -
+                         (p[tri[:, 2], 0] - p[tri[:, 0], 0]) * (p[tri[:, 1], 1] - p[tri[:, 0], 1]))
+        assert abs(a.sum() - m.area[m.is_active != 0].sum()) <= 1e-12 * a.sum()
