@@ -108,7 +108,7 @@ struct NoSharedTable : NoCull {
 // (truncation r^6/6 < 1e-17).  No exponent extraction, no int-to-double conversion: 6 FP64-pipe
 // instructions, one MUFU and one LDS.64 per logarithm (the library log() is ~28 FP64 instructions
 // plus branches; a first table version with a 128-entry mantissa table and e ln2 added separately
-// took 9 and ran issue-bound).  Error <= 1 ulp of the result.
+// took 9 and ran issue-bound).  Absolute error <= 1.5 ulp of max(|ln d|, 1/2) (tests/test_kernel_math.py).
 //
 // The full table (every binade, 4 MB, built once per device from the device's own MUFU
 // results and long-double logarithms on the host, runtime.cuh) lives in global memory; each
