@@ -55,9 +55,9 @@ def config_dict(level, m, world):
         "workload": f"RossbyHaurwitz54 BVE direct sum, icosTri level {level} (faceKind=3, initNest={level}): "
                     f"{m.n} targets x {m.n_active} active panels, RH54 vorticity (examples/rh54.namelist), R=1",
         "interactions_per_step": int(m.n) * int(m.n_active) - int(m.n_active),
-        "partition": f"LoadBalance target slices over {world} GPU(s), sources replicated; slices exchanged by NVLink "
-                     "peer stores from the sum's finalize step into CUDA-IPC shared output buffers, between two "
-                     "4-byte NCCL all-reduce barriers",
+        "partition": (f"LoadBalance target slices over {world} GPUs, sources replicated; slices exchanged by NVLink "
+                      "peer stores from the sum's finalize step into CUDA-IPC shared output buffers, between two "
+                      "4-byte NCCL all-reduce barriers") if world > 1 else "all targets on 1 GPU (no exchange)",
         "l2": "256 MiB memset between timed steps (time included); sources (63 MB) are meant to live in L2",
     }
 
