@@ -5,7 +5,7 @@ ORDER seeds, scores each hot loop with the bank model of tools/sass_banks.py
 (fresh operand reads + bank conflicts -> predicted ms at icosTri 7) and prints the best; the GPU sweep
 (tools/sweep_bve.py) then measures the short list.   usage: search_order.py [n_random] [T] [U] [min CTAs per SM]"""
 import concurrent.futures as cf
-import os, random, subprocess, sys, tempfile
+import os, random, shutil, subprocess, sys, tempfile
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, os.path.join(ROOT, "tools"))
@@ -54,6 +54,7 @@ if __name__ == "__main__":
         for seed, sc in ex.map(lambda s: score(s, T, U, work, MINB), sorted(seeds)):
             if sc:
                 res.append((sc["cost"], seed, sc))
+    shutil.rmtree(work, ignore_errors=True)
     res.sort()
     for cost, seed, sc in res[:16]:
         print(f"ORDER {seed:6d} {decode(seed)}  model {cost:.2f} ms  fresh {sc['fresh']:.2f} same2 {sc['same2']:.2f} same3 {sc['same3']:.2f} instr {sc['instr']:.2f}")
