@@ -370,3 +370,15 @@ def swe_sphere_rhs(x, y, z, vort, div, surf, area, mask, radius, pse_eps):
     lib.oracle_swe_sphere_rhs(x.size, _p(x), _p(y), _p(z), _p(vort), _p(div), _p(surf), _p(area), m.ctypes.data_as(_i32),
                               radius, pse_eps, 0, x.size, *[_p(a) for a in o])
     return o
+
+
+def pse_laplacian_sphere_at_points(x, y, z, f, area, mask, eps, tx, ty, tz, ftarget, sphere_radius=1.0):
+    x, y, z, f, area, tx, ty, tz, ftarget = map(_f, (x, y, z, f, area, tx, ty, tz, ftarget))
+    m = _m(mask)
+    lib = get()
+    lib.oracle_pse_laplacian_sphere_at_points.argtypes = [_n, _d, _d, _d, _d, _d, _i32, _dbl, _dbl, _n, _d, _d, _d, _d, _d]
+    lib.oracle_pse_laplacian_sphere_at_points.restype = None
+    out = np.zeros(tx.size)
+    lib.oracle_pse_laplacian_sphere_at_points(x.size, _p(x), _p(y), _p(z), _p(f), _p(area), m.ctypes.data_as(_i32),
+                                              eps, sphere_radius, tx.size, _p(tx), _p(ty), _p(tz), _p(ftarget), _p(out))
+    return out

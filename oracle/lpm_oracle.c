@@ -892,3 +892,27 @@ void oracle_swe_sphere_rhs(int64_t n, const double *x, const double *y, const do
         }
     }
 }
+
+/* tests/SpherePSEConvTest.f90:196-207: the PSE Laplacian evaluated at arbitrary points of the
+ * sphere (the test's 181 x 360 lat-lon grid), f_target = the field's exact value there:
+ *   lap(t) = sum_{k active} eta(d(x_k, t)/eps)/eps^2 (f_k - f_target(t)) A_k / eps^2 .
+ * Pins bivariateLaplacianKernel8 + SphereDistance at non-particle targets (unifLinfHarmLap). */
+void oracle_pse_laplacian_sphere_at_points(int64_t n, const double *x, const double *y, const double *z,
+                                           const double *f, const double *area, const int32_t *mask, double eps,
+                                           double sphereRadius, int64_t m, const double *tx, const double *ty,
+                                           const double *tz, const double *ftarget, double *lap)
+{
+    for (int64_t t = 0; t < m; ++t) {
+        const double xt[3] = {tx[t], ty[t], tz[t]};
+        double acc = 0.0;
+        for (int64_t k = 0; k < n; ++k) {
+            if (mask[k]) {
+                const double xk[3] = {x[k], y[k], z[k]};
+                double pseKin = SphereDistance(xk, xt, sphereRadius) / eps;
+                double lapKernel = bivariateLaplacianKernel8(pseKin) / (eps * eps);
+                acc = acc + lapKernel * (f[k] - ftarget[t]) * area[k] / (eps * eps);
+            }
+        }
+        lap[t] = acc;
+    }
+}
