@@ -293,7 +293,10 @@ int lpm_profile_summary(int reset, int64_t* nkernels, double* total_ms);
 int64_t lpm_launch_count(int reset);
 /* 1: record events around each main kernel (adds a sync at query time only). */
 int lpm_set_profiling(int enable);
-/* Tuning knob for benchmarks: select the BVE kernel variant. */
+/* Tuning knob for benchmarks: select the BVE kernel variant.  0 = default.
+ * 1-99: tilings / statement orders of the one-sided kernel; 102: a shape of the stream-function kernels;
+ * 200, 201: EXPERIMENTAL pair-symmetric evaluation of the velocity sum (csrc/symmetric.cuh; opt-in, results
+ * reproducible to rounding but not bit for bit; in rank mode every rank must set the same value). */
 int lpm_set_bve_variant(int variant);
 /* Upper bound on the number of source chunks an evaluation is split into (work items = target
  * blocks x chunks).  More chunks = shorter CTAs = a smaller tail when few waves of CTAs fit a

@@ -219,6 +219,16 @@ struct SolverBase {
             for (int k = 0; k < Op::NIN; ++k) a.in[k] = r.A(in[k]);
             a.mask = r.mask.as<int32_t>();
             for (int k = 0; k < 3; ++k) a.sc[k] = sc ? sc[k] : 0.0;
+            if constexpr (std::is_same<Op, OpBveVel>::value) {
+                if (sym_applicable(variant, r.sb, r.se, n, r.mp, nrep)) {      // opt-in experiment (symmetric.cuh)
+                    Outs<3> o{};
+                    o.nrep = 1;
+                    for (int k = 0; k < 3; ++k) o.p[0][k] = r.A(out[k]);
+                    LPM_TRY(bve_velocity_sym(*r.dev, r.dev->stream, r.mp, a, o, variant));
+                    exchanged = true;       // rank mode: every rank already holds all n results
+                    continue;
+                }
+            }
             LPM_TRY(Op::pack(*r.dev, r.dev->stream, r.mp, a));
             typename Op::K::Params prm = Op::params(a);
             if (R.rank_mode) {                   // one replica per process: the peers' copies through the shared slab

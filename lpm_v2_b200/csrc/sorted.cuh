@@ -20,6 +20,8 @@
 #pragma once
 #include <cub/device/device_radix_sort.cuh>
 
+#include <type_traits>
+
 #include "ops.cuh"
 
 namespace lpm {
@@ -93,6 +95,10 @@ __global__ void scatter_kernel(int64_t count, const int32_t* __restrict__ perm, 
     for (int r = 0; r < dst.nrep; ++r) dst.p[r][i] = v;
 }
 
+// experimental pair-symmetric BVE velocity (symmetric.cuh, included at the end of this file)
+inline int bve_velocity_sym(Device& dev, cudaStream_t st, MaskPlan& mp, const Args& a, const Outs<3>& out, int variant);
+inline bool sym_applicable(int variant, int64_t tbeg, int64_t tend, int64_t nt, const MaskPlan& mp, int nrep);
+
 // (key, value) pairs sorted by key into ws.sort_vals[1]; returns that pointer
 inline int sort_by_cell(Device& dev, cudaStream_t st, int64_t count, int bits, uint32_t* keys_in, int32_t* vals_in,
                         uint32_t* keys_out, int32_t* vals_out)
@@ -141,6 +147,14 @@ inline int evaluate_impl(Device& dev, cudaStream_t st, MaskPlan& mp, const Args&
     bool sorted = false;
     if constexpr (K::CULL) sorted = mode != 0 && mp.nsrc > 2 * kTile && tend - tbeg > 0;
     if (!sorted) {
+        if constexpr (std::is_same<Op, OpBveVel>::value) {
+            if (sym_applicable(Op::variant(), tbeg, tend, nt, mp, 1)) {     // opt-in experiment, one device only
+                Outs<3> o{};
+                set_outs(o, out);
+                *exchanged = rt().rank_mode && rt().world > 1;      // every rank ends up with all n results
+                return bve_velocity_sym(dev, st, mp, a, o, Op::variant());
+            }
+        }
         LPM_TRY(Op::pack(dev, st, mp, a));
         typename K::Params prm = Op::params(a);
         *exchanged = set_outs_shared(prm.out, out, nt);
@@ -224,3 +238,5 @@ inline int evaluate_impl(Device& dev, cudaStream_t st, MaskPlan& mp, const Args&
 }
 
 }  // namespace lpm
+
+#include "symmetric.cuh"

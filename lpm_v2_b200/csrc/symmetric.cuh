@@ -1,0 +1,156 @@
+// symmetric.cuh -- EXPERIMENTAL, opt-in (lpm_set_bve_variant(200)); NOT the default path and not
+// yet measured on a GPU.  Pair-symmetric evaluation of the BVE velocity sum.
+//
+// The reference (src/SphereBVESolver.f90:396-420) visits every ordered pair (i, j): for the
+// factored form used here, a_i = sum_j P_j / d_ij with d_ij = R^2 - x_i.x_j = d_ji.  Active
+// particles are both targets and sources, so for two active particles c < c' the denominator --
+// 3 DFMA -- and its reciprocal -- 3 more -- serve both a_c += P_c' / d and a_c' += P_c / d:
+// 12 FP64 instructions for two interactions instead of 18.  At icosTri 8 two thirds of all
+// interactions are active-active (1 310 720^2 of 2.577e12).
+//
+//   * passive targets (vertices) x all active sources: the one-sided engine (directsum.cuh) on the
+//     gathered passive particles;
+//   * active x active, on COMPACT indices (the packed source records are also the targets): a CTA
+//     owns a block of BLOCK*T compact targets (registers) and a chunk of source tiles at or
+//     above its own ("upper triangle").  Diagonal tiles (the block against itself) are
+//     evaluated one-sided with the self pair excluded; for every tile above the diagonal each
+//     pair is evaluated once: the thread adds P_j / d to its targets' sums and, per source, sums
+//     P_t / d over its T targets.  Those per-source sums are reduced across the warp by
+//     recursive halving over batches of SB sources (SB (2 SHFL + DADD) per level instead of a full
+//     butterfly per source: ~3.4 DADD per source per thread against 12 T of pair work) and added
+//     to the source's accumulator in global memory with RED.ADD.F64 -- one per (warp, source,
+//     component).  A CTA's own sums join the same accumulators when it ends.
+//   * u_i = x_i cross a_i in a finalize kernel.
+//
+// The accumulation order of the atomics is not fixed, so results are reproducible to rounding
+// (~1e-16 relative), not bit for bit; the default path keeps its bitwise guarantees.
+#pragma once
+#include "ops.cuh"
+#include "sym_kernels.cuh"
+
+namespace lpm {
+
+constexpr int kSymVariant = 200;        // lpm_set_bve_variant: symmetric path, 4 targets per thread
+constexpr int kSymVariant8 = 201;       //                      8 targets per thread, batches of 4 sources
+
+template <int T, int BLOCK, int SB, int MINB>
+inline int launch_sym(cudaStream_t st, SymGeom g, const double* src, double* acc)
+{
+    constexpr int TB = BLOCK * T;
+    g.nblocks = (g.nsrc_pad + TB - 1) / TB;
+    constexpr size_t smem = 2 * size_t(kTile) * 6 * sizeof(double) + 2 * sizeof(uint64_t);
+    const int64_t grid = (int64_t)g.nblocks * g.nchunks;
+    if (grid <= 0 || grid > 0x7fffffffLL) return set_error(LPM_ERR_INVALID, "symmetric BVE grid %lld", (long long)grid);
+    sym_bve_kernel<T, BLOCK, SB, MINB><<<(unsigned)grid, BLOCK, smem, st>>>(g, src, acc);
+    return LPM_OK;
+}
+
+// Whole evaluation: one device, or -- rank mode -- collectively on every rank (each must call with its
+// LoadBalance slice, sym_applicable() checks that): target blocks of the active x active part are dealt
+// round-robin to the ranks and the accumulators summed with one ncclAllReduce (3 F doubles); the passive
+// targets are sliced by LoadBalance and exchanged with the grouped broadcast of allgather_slices().
+// Every rank then writes ALL n results into its own `out` (no peer stores), so the caller has nothing
+// left to exchange.  a: the OpBveVel arguments; out: where u, v, w go (replica 0 only is used).
+inline int bve_velocity_sym(Device& dev, cudaStream_t st, MaskPlan& mp, const Args& a, const Outs<3>& out, int variant)
+{
+    using K = BveVel;
+    Runtime& R = rt();
+    Workspace& ws = dev.ws;
+    const bool prof = R.profiling;
+    cudaEvent_t pb = nullptr, pe = nullptr;
+    if (prof) {
+        if (dev.next_prof(&pb, &pe) != LPM_OK) return set_error(LPM_ERR_CUDA, "cannot create profiling events");
+        LPM_CUDA(cudaEventRecord(pb, st));
+        R.profiling = false;        // one event pair around both kernels
+    }
+    auto body = [&]() -> int {
+        LPM_TRY(OpBveVel::pack(dev, st, mp, a));
+        const double* src = ws.sources.as<double>();
+        SymGeom g{};
+        int32_t chunk = 0;
+        ds_chunks(mp.nsrc, &g.nsrc_pad, &chunk, &g.nchunks, mp.n);
+        g.nsrc = mp.nsrc;
+        g.ntiles = g.nsrc_pad / kTile;
+        g.chunk_tiles = chunk / kTile;
+        g.world = R.rank_mode ? R.world : 1;
+        g.rank = R.rank_mode ? R.rank : 0;
+        g.R2 = a.sc[0] * a.sc[0];
+        // ---- active x active
+        if (mp.nsrc > 0) {
+            LPM_TRY(ws.sym_acc.reserve((size_t)g.nsrc_pad * 3 * sizeof(double)));
+            LPM_CUDA(cudaMemsetAsync(ws.sym_acc.p, 0, (size_t)g.nsrc_pad * 3 * sizeof(double), st));
+            if (variant == kSymVariant8) LPM_TRY((launch_sym<8, 128, 4, 1>(st, g, src, ws.sym_acc.as<double>())));
+            else LPM_TRY((launch_sym<4, 128, 8, 2>(st, g, src, ws.sym_acc.as<double>())));
+            if (g.world > 1) {
+                if (!R.comm) return set_error(LPM_ERR_COMM, "world size %d but no communicator (lpm_comm_init_rank)", R.world);
+                LPM_NCCL(nccl().AllReduce(ws.sym_acc.p, ws.sym_acc.p, (size_t)g.nsrc_pad * 3, /*ncclDouble*/ 8, /*ncclSum*/ 0,
+                                          R.comm, st));
+            }
+            sym_bve_finalize<<<(unsigned)((mp.nsrc + 255) / 256), 256, 0, st>>>(mp.nsrc, mp.active.as<int32_t>(), src,
+                                                                                ws.sym_acc.as<double>(), out);
+            count_launch(2);
+        }
+        // ---- passive targets x all active sources: the one-sided engine on the gathered passive particles
+        const int64_t nv = mp.n - mp.nsrc;
+        if (nv > 0) {
+            LPM_TRY(ws.sorted_targets.reserve((size_t)nv * sizeof(int32_t)));
+            int32_t* perm = ws.sorted_targets.as<int32_t>();
+            passive_list_kernel<<<(unsigned)((mp.n + 255) / 256), 256, 0, st>>>(mp.n, mp.scan.as<int32_t>(), perm);
+            LPM_TRY(ws.sort_vals[0].reserve((size_t)(nv + 1) * sizeof(int32_t)));       // "scan" of a list with no source in it
+            LPM_CUDA(cudaMemsetAsync(ws.sort_vals[0].p, 0, (size_t)(nv + 1) * sizeof(int32_t), st));
+            const unsigned gb = (unsigned)((nv + 255) / 256);
+            for (int k = 0; k < 3; ++k) {
+                LPM_TRY(ws.gathered[k].reserve((size_t)nv * sizeof(double)));
+                LPM_TRY(ws.sorted_out[k].reserve((size_t)nv * sizeof(double)));
+                gather_kernel<<<gb, 256, 0, st>>>(nv, perm, a.in[k], ws.gathered[k].as<double>());
+            }
+            count_launch(4);
+            K::Params prm{};
+            prm.x = ws.gathered[0].as<double>(); prm.y = ws.gathered[1].as<double>(); prm.z = ws.gathered[2].as<double>();
+            prm.R2 = g.R2;
+            prm.out.nrep = 1;
+            for (int k = 0; k < 3; ++k) prm.out.p[0][k] = ws.sorted_out[k].as<double>();
+            MaskPlan view;                          // not owned: the sources of mp, no self pairs
+            view.n = nv; view.nsrc = mp.nsrc;
+            view.scan.p = ws.sort_vals[0].p; view.scan.cap = ws.sort_vals[0].cap;
+            view.active.p = mp.active.p; view.active.cap = mp.active.cap;
+            int64_t vb = 0, ve = nv;
+            if (g.world > 1) load_balance0(nv, g.world, g.rank, &vb, &ve);
+            const int rc = direct_sum<K>(dev, st, view, vb, ve, prm, 0, nv);
+            view.scan = DevBuf{}; view.active = DevBuf{};
+            LPM_TRY(rc);
+            if (g.world > 1) {
+                double* bufs[3] = {ws.sorted_out[0].as<double>(), ws.sorted_out[1].as<double>(), ws.sorted_out[2].as<double>()};
+                LPM_TRY(allgather_slices(3, bufs, nv, st));
+            }
+            for (int k = 0; k < 3; ++k) {
+                ScatterDst dst{};
+                dst.nrep = 1;
+                dst.p[0] = out.p[0][k];
+                scatter_kernel<<<gb, 256, 0, st>>>(nv, perm, ws.sorted_out[k].as<double>(), dst);
+            }
+            count_launch(3);
+        }
+        LPM_CUDA(cudaGetLastError());
+        return LPM_OK;
+    };
+    const int rc = body();
+    if (prof) {
+        R.profiling = true;
+        if (rc == LPM_OK) LPM_CUDA(cudaEventRecord(pe, st));
+    }
+    return rc;
+}
+
+// May this evaluation take the symmetric path?  One device driving every target, or rank mode with this
+// rank's LoadBalance slice (then every rank reaches the same answer and the collectives inside match up).
+inline bool sym_applicable(int variant, int64_t tbeg, int64_t tend, int64_t nt, const MaskPlan& mp, int nrep)
+{
+    const Runtime& R = rt();
+    if ((variant != kSymVariant && variant != kSymVariant8) || nt != mp.n || nrep != 1 || R.devs.size() != 1) return false;
+    int64_t b = 0, e = nt;
+    if (R.rank_mode && R.world > 1) load_balance0(nt, R.world, R.rank, &b, &e);
+    return tbeg == b && tend == e;
+}
+
+}  // namespace lpm

@@ -1,0 +1,88 @@
+"""GPU parity of the EXPERIMENTAL pair-symmetric BVE velocity path (lpm_set_bve_variant(200 / 201),
+lpm_v2_b200/csrc/symmetric.cuh).
+
+The path was written at the end of round 1 without GPU time left, so it has not run yet: these tests
+are skipped unless LPM_EXPERIMENTAL=1, and the default path does not depend on them.  First thing to
+run on a B200 in the next round:
+
+    LPM_EXPERIMENTAL=1 python -m pytest tests/test_sym_gpu.py -m gpu -x -q
+    python tools/ab_sym.py 7            # default vs symmetric timings, one box
+"""
+import os
+
+import numpy as np
+import pytest
+
+from lpm_v2_b200 import mesh as M, problems, solvers
+from conftest import relerr
+from test_parity_gpu import _rand_sphere
+
+pytestmark = [pytest.mark.gpu,
+              pytest.mark.skipif(os.environ.get("LPM_EXPERIMENTAL") != "1",
+                                 reason="experimental symmetric path: set LPM_EXPERIMENTAL=1")]
+TOL = 1e-12
+
+
+@pytest.fixture
+def sym(gpu, request):
+    gpu.set_bve_variant(request.param)
+    yield gpu
+    gpu.set_bve_variant(0)
+
+
+@pytest.mark.parametrize("sym", [200, 201], indirect=True)
+@pytest.mark.parametrize("seed,L", [(M.ICOS_TRI_SPHERE_SEED, 2), (M.ICOS_TRI_SPHERE_SEED, 5), (M.CUBED_SPHERE_SEED, 5),
+                                    (M.ICOS_TRI_SPHERE_SEED, 6)])
+def test_sym_bve_velocity_meshes(sym, oracle, get_mesh, seed, L):
+    m = get_mesh(seed, L)
+    zeta = problems.rossby_haurwitz54(m)
+    got = sym.bve_velocity(m.x, m.y, m.z, zeta, m.area, m.is_active, 1.0)
+    want = oracle.bve_velocity(m.x, m.y, m.z, zeta, m.area, m.is_active, 1.0)
+    scale = max(np.abs(w).max() for w in want)
+    assert max(np.abs(g - w).max() for g, w in zip(got, want)) <= TOL * scale
+
+
+@pytest.mark.parametrize("sym", [200, 201], indirect=True)
+@pytest.mark.parametrize("n,frac,seed", [(1, 1.0, 1), (2, 1.0, 2), (3, 0.5, 3), (127, 0.3, 4), (513, 0.9, 5),
+                                         (1025, 0.05, 6), (4099, 0.6, 12345), (20011, 0.55, 7), (20011, 1.0, 8),
+                                         (3000, 0.0, 9)])
+def test_sym_bve_velocity_random_ragged(sym, oracle, n, frac, seed):
+    """Ragged sizes (active counts that are not multiples of a tile or a block), all-active and
+    all-passive masks, radius != 1."""
+    x, y, z, zeta, area, mask = _rand_sphere(n, seed, frac)
+    R = 1.7
+    x, y, z = R * x, R * y, R * z
+    got = sym.bve_velocity(x, y, z, zeta, area, mask, R)
+    want = oracle.bve_velocity(x, y, z, zeta, area, mask, R)
+    for g, w in zip(got, want):
+        assert relerr(g, w) <= TOL
+
+
+@pytest.mark.parametrize("sym", [200], indirect=True)
+def test_sym_matches_default_path(sym, get_mesh):
+    """Same sum, other order: within a few ulp of the default kernel at icosTri 6."""
+    m = get_mesh(M.ICOS_TRI_SPHERE_SEED, 6)
+    zeta = problems.gaussian_vortex(m)
+    a = sym.bve_velocity(m.x, m.y, m.z, zeta, m.area, m.is_active, 1.0)
+    sym.set_bve_variant(0)
+    b = sym.bve_velocity(m.x, m.y, m.z, zeta, m.area, m.is_active, 1.0)
+    for g, w in zip(a, b):
+        assert relerr(g, w) <= 1e-13
+
+
+@pytest.mark.parametrize("sym", [200], indirect=True)
+def test_sym_rk4_step(sym, oracle, get_mesh):
+    """The resident solver takes the symmetric path for its four velocity sums."""
+    m = get_mesh(M.ICOS_TRI_SPHERE_SEED, 4)
+    zeta = problems.gaussian_vortex(m)
+    omega = 2.0 * np.pi
+    u, v, w = oracle.bve_velocity(m.x, m.y, m.z, zeta, m.area, m.is_active, 1.0)
+    sph = solvers.BVEMesh(m, zeta, 1.0, omega)
+    sph.velocity = [u.copy(), v.copy(), w.copy()]
+    sol = solvers.BVESolver(sph)
+    sol.Timestep(sph, 0.01, with_stream=False)
+    sol.Delete()
+    ref = oracle.bve_rk4_step(m.x, m.y, m.z, zeta, u, v, w, m.area, m.is_active, 1.0, omega, 0.01)
+    got = [sph.x, sph.y, sph.z, sph.relVort] + sph.velocity
+    for a, b in zip(got, ref):
+        assert relerr(a, b) <= TOL

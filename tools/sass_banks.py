@@ -28,7 +28,12 @@ def hot_loop(ins):
             if m and int(m.group(1), 16) < a:
                 t = int(m.group(1), 16)
                 body = [x for x in ins if t <= x[0] <= a]
-                if sum(o.startswith('BRA') for _, o, _ in body) > 1:
+                # innermost loops only: no other BACKWARD branch inside (forward branches, e.g. around a
+                # predicated atomic, are fine)
+                def backward(x):
+                    mm = re.search(r'0x([0-9a-f]+)', x[2])
+                    return x[1].startswith('BRA') and mm and int(mm.group(1), 16) < x[0]
+                if sum(1 for x in body if backward(x)) > 1:
                     continue
                 n = sum(o.startswith(('DFMA', 'DMUL', 'DADD')) for _, o, _ in body)
                 if best is None or n > best[0]:
