@@ -229,6 +229,16 @@ struct SolverBase {
                     continue;
                 }
             }
+            if constexpr (std::is_same<Op, OpBveStream>::value) {
+                if (sym_applicable(variant, r.sb, r.se, n, r.mp, nrep)) {
+                    Outs<2> o{};
+                    o.nrep = 1;
+                    for (int k = 0; k < 2; ++k) o.p[0][k] = r.A(out[k]);
+                    LPM_TRY(bve_stream_sym(*r.dev, r.dev->stream, r.mp, a, o, variant));
+                    exchanged = true;
+                    continue;
+                }
+            }
             LPM_TRY(Op::pack(*r.dev, r.dev->stream, r.mp, a));
             typename Op::K::Params prm = Op::params(a);
             if (R.rank_mode) {                   // one replica per process: the peers' copies through the shared slab
@@ -337,7 +347,7 @@ struct BveSolver : SolverBase {
         const int in[6] = {X, Y, Z, ZETA, ABSV, AREA};
         const int out[2] = {RELS, ABSS};
         const double sc[3] = {R, 0, 0};
-        return eval<OpBveStream>(in, out, sc, 0);
+        return eval<OpBveStream>(in, out, sc, OpBveStream::variant());
     }
 
     int diagnostics(double* ke, double* ens)

@@ -1,5 +1,5 @@
-// sym_kernels.cuh -- device code of the EXPERIMENTAL pair-symmetric BVE velocity path (see symmetric.cuh
-// for the design and the host side).  Kept apart so that tools/sym_score.py can compile the kernel alone.
+// sym_kernels.cuh -- device code of the EXPERIMENTAL pair-symmetric paths (see symmetric.cuh for the
+// design and the host side).  Kept apart so that tools/sym_score.py can compile a kernel alone.
 #pragma once
 #include "directsum.cuh"
 #include "pairs.cuh"
@@ -14,27 +14,33 @@ struct SymGeom {
     int32_t chunk_tiles;    // source tiles per chunk
     int32_t nchunks;
     int32_t world, rank;    // target blocks are dealt round-robin to ranks (sums joined by the caller)
+    int32_t half_bin;       // as DsGeom::half_bin (log kernels)
+};
+
+// kernel-wide constants of the symmetric functors
+struct SymParams : LogParams {
     double R2;
 };
 
-// Warp reduction of cb[s][a] (thread-local sums for SB sources, 3 components) by recursive
+// Warp reduction of cb[s][a] (thread-local sums for SB sources, NC <= 3 components) by recursive
 // halving, then one RED per (source, component) from the lane that ends up owning it.
 // After the halving levels lane l holds source ((l >> (5 - LV)) & (SB - 1)) summed over the lanes
 // that differ from it in the high LV bits; a butterfly over the remaining low bits finishes the sum.
-template <int SB>
-__device__ __forceinline__ void sym_reduce_red(double (&cb)[SB][3], int lane, double* __restrict__ accj)
+template <int SB, int NC>
+__device__ __forceinline__ void sym_reduce_red(double (&cb)[SB][NC], int lane, double* __restrict__ accj)
 {
     static_assert(SB == 8 || SB == 4, "source batch");
+    static_assert(NC >= 1 && NC <= 3, "components per source");
     constexpr unsigned FULL = 0xffffffffu;
-    double v[3];
+    double v[NC];
     int sidx;
     if constexpr (SB == 8) {
         const bool b4 = (lane & 16) != 0, b3 = (lane & 8) != 0, b2 = (lane & 4) != 0;
-        double v4[4][3], v2[2][3];
+        double v4[4][NC], v2[2][NC];
 #pragma unroll
         for (int k = 0; k < 4; ++k)
 #pragma unroll
-            for (int a = 0; a < 3; ++a) {
+            for (int a = 0; a < NC; ++a) {
                 const double lo = cb[k][a], hi = cb[k + 4][a];
                 const double keep = b4 ? hi : lo, send = b4 ? lo : hi;
                 v4[k][a] = keep + __shfl_xor_sync(FULL, send, 16);
@@ -42,56 +48,65 @@ __device__ __forceinline__ void sym_reduce_red(double (&cb)[SB][3], int lane, do
 #pragma unroll
         for (int k = 0; k < 2; ++k)
 #pragma unroll
-            for (int a = 0; a < 3; ++a) {
+            for (int a = 0; a < NC; ++a) {
                 const double lo = v4[k][a], hi = v4[k + 2][a];
                 const double keep = b3 ? hi : lo, send = b3 ? lo : hi;
                 v2[k][a] = keep + __shfl_xor_sync(FULL, send, 8);
             }
 #pragma unroll
-        for (int a = 0; a < 3; ++a) {
+        for (int a = 0; a < NC; ++a) {
             const double lo = v2[0][a], hi = v2[1][a];
             const double keep = b2 ? hi : lo, send = b2 ? lo : hi;
             v[a] = keep + __shfl_xor_sync(FULL, send, 4);
         }
 #pragma unroll
-        for (int a = 0; a < 3; ++a) {
+        for (int a = 0; a < NC; ++a) {
             v[a] += __shfl_xor_sync(FULL, v[a], 2);
             v[a] += __shfl_xor_sync(FULL, v[a], 1);
         }
         sidx = (lane >> 2) & 7;
         const int q = lane & 3;
-        if (q < 3) atomicAdd(accj + sidx * 3 + q, q == 0 ? v[0] : (q == 1 ? v[1] : v[2]));
+        if (q < NC) atomicAdd(accj + sidx * NC + q, q == 0 ? v[0] : (q == 1 ? v[NC > 1 ? 1 : 0] : v[NC > 2 ? 2 : 0]));
     } else {
         const bool b4 = (lane & 16) != 0, b3 = (lane & 8) != 0;
-        double v2[2][3];
+        double v2[2][NC];
 #pragma unroll
         for (int k = 0; k < 2; ++k)
 #pragma unroll
-            for (int a = 0; a < 3; ++a) {
+            for (int a = 0; a < NC; ++a) {
                 const double lo = cb[k][a], hi = cb[k + 2][a];
                 const double keep = b4 ? hi : lo, send = b4 ? lo : hi;
                 v2[k][a] = keep + __shfl_xor_sync(FULL, send, 16);
             }
 #pragma unroll
-        for (int a = 0; a < 3; ++a) {
+        for (int a = 0; a < NC; ++a) {
             const double lo = v2[0][a], hi = v2[1][a];
             const double keep = b3 ? hi : lo, send = b3 ? lo : hi;
             v[a] = keep + __shfl_xor_sync(FULL, send, 8);
         }
 #pragma unroll
-        for (int a = 0; a < 3; ++a) {
+        for (int a = 0; a < NC; ++a) {
             v[a] += __shfl_xor_sync(FULL, v[a], 4);
             v[a] += __shfl_xor_sync(FULL, v[a], 2);
             v[a] += __shfl_xor_sync(FULL, v[a], 1);
         }
         sidx = (lane >> 3) & 3;
         const int q = lane & 7;
-        if (q < 3) atomicAdd(accj + sidx * 3 + q, q == 0 ? v[0] : (q == 1 ? v[1] : v[2]));
+        if (q < NC) atomicAdd(accj + sidx * NC + q, q == 0 ? v[0] : (q == 1 ? v[NC > 1 ? 1 : 0] : v[NC > 2 ? 2 : 0]));
     }
 }
 
-// SB sources of a tile above the diagonal against the thread's T targets, both directions:
-// a[t] += P_j / d (the targets' sums) and cb[u] = sum_t P_t / d (this thread's share of source u's sum).
+// =============================================================================
+// Functors of the symmetric kernels.  K provides
+//   NS, NA, NC        doubles per record / sums per target / sums per source (the transposed direction)
+//   KS                per-CTA shared table (doubles), init_shared() as in directsum.cuh
+//   Tgt, from_record  what a thread keeps of a target (read from its packed record), null()
+//   batch<T,SB,ORDER> SB sources of a tile above the diagonal against the thread's T targets, both
+//                     directions: a[t] += (source's weight) g(d) and cb[u] = sum_t (target's weight) g(d)
+//   diag<T>           one source of a diagonal tile, one-sided, pair skipped where isself[t]
+// =============================================================================
+
+// BVE velocity (BveVelT in pairs.cuh): a_i = sum_j P_j / (R^2 - x_i.x_j); record x, y, z, Px, Py, Pz.
 // ORDER permutes INDEPENDENT statements only (as BveVelT's ORDER does): the kernel is bound by register
 // operand delivery, and what ptxas allocates and where it can set .reuse follows the statement order.
 //   bit 0     denominators coordinate by coordinate (else target by target)
@@ -99,112 +114,235 @@ __device__ __forceinline__ void sym_reduce_red(double (&cb)[SB][3], int lane, do
 //   bits 2-3  sources handled together, phase by phase: 1, 2, 4, SB
 //   bit 4     cb-phase nest (target, component, source) -- P_t stays in the reuse cache -- else
 //             (source, target, component) -- 1/d stays
-template <int T, int SB, int ORDER>
-__device__ __forceinline__ void sym_batch(const double (&tx)[T], const double (&ty)[T], const double (&tz)[T],
-                                          const double (&px)[T], const double (&py)[T], const double (&pz)[T],
-                                          double (&a)[T][3], const double* __restrict__ sm, double R2, double (&cb)[SB][3])
-{
-    constexpr int NS = 6;
-    constexpr int DN = ORDER & 1, AN = (ORDER >> 1) & 1, GS = (ORDER >> 2) & 3, CU = (ORDER >> 4) & 1;
-    constexpr int G = GS == 0 ? 1 : GS == 1 ? 2 : GS == 2 ? 4 : SB;
-    static_assert(SB % G == 0, "source group");
+struct SymBveVel : NoSharedTable {
+    static constexpr int NS = 6, NA = 3, NC = 3;
+    struct Tgt { double x, y, z, px, py, pz; };
+    __device__ static __forceinline__ Tgt null() { return Tgt{0.0, 0.0, 0.0, 0.0, 0.0, 0.0}; }
+    __device__ static __forceinline__ Tgt from_record(const double2 v0, const double2 v1, const double2 v2)
+    {
+        return Tgt{v0.x, v0.y, v1.x, v1.y, v2.x, v2.y};
+    }
+    template <int T, int SB, int ORDER>
+    __device__ static __forceinline__ void batch(const SymParams& p, const Tgt (&tg)[T], double (&a)[T][NA],
+                                                 const double* __restrict__ sm, double (&cb)[SB][NC], const SharedCtx&)
+    {
+        constexpr int DN = ORDER & 1, AN = (ORDER >> 1) & 1, GS = (ORDER >> 2) & 3, CU = (ORDER >> 4) & 1;
+        constexpr int G = GS == 0 ? 1 : GS == 1 ? 2 : GS == 2 ? 4 : SB;
+        static_assert(SB % G == 0, "source group");
 #pragma unroll
-    for (int g0 = 0; g0 < SB; g0 += G) {
-        double s[G][NS], d[G][T], r[G][T];
+        for (int g0 = 0; g0 < SB; g0 += G) {
+            double s[G][NS], d[G][T], r[G][T];
 #pragma unroll
-        for (int u = 0; u < G; ++u) {
-            const double2* p2 = reinterpret_cast<const double2*>(sm + (g0 + u) * NS);
+            for (int u = 0; u < G; ++u) {
+                const double2* p2 = reinterpret_cast<const double2*>(sm + (g0 + u) * NS);
 #pragma unroll
-            for (int q = 0; q < NS / 2; ++q) {
-                const double2 v = p2[q];
-                s[u][2 * q] = v.x; s[u][2 * q + 1] = v.y;
+                for (int q = 0; q < NS / 2; ++q) {
+                    const double2 v = p2[q];
+                    s[u][2 * q] = v.x; s[u][2 * q + 1] = v.y;
+                }
             }
-        }
-        if constexpr (DN == 0) {
-#pragma unroll
-            for (int u = 0; u < G; ++u)
-#pragma unroll
-                for (int t = 0; t < T; ++t) {
-                    d[u][t] = fma(-tx[t], s[u][0], R2);
-                    d[u][t] = fma(-ty[t], s[u][1], d[u][t]);
-                    d[u][t] = fma(-tz[t], s[u][2], d[u][t]);
-                }
-        } else {
-#pragma unroll
-            for (int u = 0; u < G; ++u)
-#pragma unroll
-                for (int t = 0; t < T; ++t) d[u][t] = fma(-tx[t], s[u][0], R2);
-#pragma unroll
-            for (int u = 0; u < G; ++u)
-#pragma unroll
-                for (int t = 0; t < T; ++t) d[u][t] = fma(-ty[t], s[u][1], d[u][t]);
-#pragma unroll
-            for (int u = 0; u < G; ++u)
-#pragma unroll
-                for (int t = 0; t < T; ++t) d[u][t] = fma(-tz[t], s[u][2], d[u][t]);
-        }
-#pragma unroll
-        for (int u = 0; u < G; ++u) rcp_batch<T>(d[u], r[u]);
-        if constexpr (AN == 0) {
-#pragma unroll
-            for (int u = 0; u < G; ++u)
-#pragma unroll
-                for (int t = 0; t < T; ++t) {
-                    a[t][0] = fma(r[u][t], s[u][3], a[t][0]);
-                    a[t][1] = fma(r[u][t], s[u][4], a[t][1]);
-                    a[t][2] = fma(r[u][t], s[u][5], a[t][2]);
-                }
-        } else {
-#pragma unroll
-            for (int c = 0; c < 3; ++c)
+            if constexpr (DN == 0) {
 #pragma unroll
                 for (int u = 0; u < G; ++u)
 #pragma unroll
-                    for (int t = 0; t < T; ++t) a[t][c] = fma(r[u][t], s[u][3 + c], a[t][c]);
-        }
-        if constexpr (CU == 0) {
+                    for (int t = 0; t < T; ++t) {
+                        d[u][t] = fma(-tg[t].x, s[u][0], p.R2);
+                        d[u][t] = fma(-tg[t].y, s[u][1], d[u][t]);
+                        d[u][t] = fma(-tg[t].z, s[u][2], d[u][t]);
+                    }
+            } else {
 #pragma unroll
-            for (int u = 0; u < G; ++u) {
-                cb[g0 + u][0] = r[u][0] * px[0]; cb[g0 + u][1] = r[u][0] * py[0]; cb[g0 + u][2] = r[u][0] * pz[0];
+                for (int u = 0; u < G; ++u)
+#pragma unroll
+                    for (int t = 0; t < T; ++t) d[u][t] = fma(-tg[t].x, s[u][0], p.R2);
+#pragma unroll
+                for (int u = 0; u < G; ++u)
+#pragma unroll
+                    for (int t = 0; t < T; ++t) d[u][t] = fma(-tg[t].y, s[u][1], d[u][t]);
+#pragma unroll
+                for (int u = 0; u < G; ++u)
+#pragma unroll
+                    for (int t = 0; t < T; ++t) d[u][t] = fma(-tg[t].z, s[u][2], d[u][t]);
+            }
+#pragma unroll
+            for (int u = 0; u < G; ++u) rcp_batch<T>(d[u], r[u]);
+            if constexpr (AN == 0) {
+#pragma unroll
+                for (int u = 0; u < G; ++u)
+#pragma unroll
+                    for (int t = 0; t < T; ++t) {
+                        a[t][0] = fma(r[u][t], s[u][3], a[t][0]);
+                        a[t][1] = fma(r[u][t], s[u][4], a[t][1]);
+                        a[t][2] = fma(r[u][t], s[u][5], a[t][2]);
+                    }
+            } else {
+#pragma unroll
+                for (int c = 0; c < 3; ++c)
+#pragma unroll
+                    for (int u = 0; u < G; ++u)
+#pragma unroll
+                        for (int t = 0; t < T; ++t) a[t][c] = fma(r[u][t], s[u][3 + c], a[t][c]);
+            }
+            if constexpr (CU == 0) {
+#pragma unroll
+                for (int u = 0; u < G; ++u) {
+                    cb[g0 + u][0] = r[u][0] * tg[0].px; cb[g0 + u][1] = r[u][0] * tg[0].py; cb[g0 + u][2] = r[u][0] * tg[0].pz;
+#pragma unroll
+                    for (int t = 1; t < T; ++t) {
+                        cb[g0 + u][0] = fma(r[u][t], tg[t].px, cb[g0 + u][0]);
+                        cb[g0 + u][1] = fma(r[u][t], tg[t].py, cb[g0 + u][1]);
+                        cb[g0 + u][2] = fma(r[u][t], tg[t].pz, cb[g0 + u][2]);
+                    }
+                }
+            } else {
+#pragma unroll
+                for (int u = 0; u < G; ++u) cb[g0 + u][0] = r[u][0] * tg[0].px;
+#pragma unroll
+                for (int u = 0; u < G; ++u) cb[g0 + u][1] = r[u][0] * tg[0].py;
+#pragma unroll
+                for (int u = 0; u < G; ++u) cb[g0 + u][2] = r[u][0] * tg[0].pz;
 #pragma unroll
                 for (int t = 1; t < T; ++t) {
-                    cb[g0 + u][0] = fma(r[u][t], px[t], cb[g0 + u][0]);
-                    cb[g0 + u][1] = fma(r[u][t], py[t], cb[g0 + u][1]);
-                    cb[g0 + u][2] = fma(r[u][t], pz[t], cb[g0 + u][2]);
+#pragma unroll
+                    for (int u = 0; u < G; ++u) cb[g0 + u][0] = fma(r[u][t], tg[t].px, cb[g0 + u][0]);
+#pragma unroll
+                    for (int u = 0; u < G; ++u) cb[g0 + u][1] = fma(r[u][t], tg[t].py, cb[g0 + u][1]);
+#pragma unroll
+                    for (int u = 0; u < G; ++u) cb[g0 + u][2] = fma(r[u][t], tg[t].pz, cb[g0 + u][2]);
                 }
-            }
-        } else {
-#pragma unroll
-            for (int u = 0; u < G; ++u) cb[g0 + u][0] = r[u][0] * px[0];
-#pragma unroll
-            for (int u = 0; u < G; ++u) cb[g0 + u][1] = r[u][0] * py[0];
-#pragma unroll
-            for (int u = 0; u < G; ++u) cb[g0 + u][2] = r[u][0] * pz[0];
-#pragma unroll
-            for (int t = 1; t < T; ++t) {
-#pragma unroll
-                for (int u = 0; u < G; ++u) cb[g0 + u][0] = fma(r[u][t], px[t], cb[g0 + u][0]);
-#pragma unroll
-                for (int u = 0; u < G; ++u) cb[g0 + u][1] = fma(r[u][t], py[t], cb[g0 + u][1]);
-#pragma unroll
-                for (int u = 0; u < G; ++u) cb[g0 + u][2] = fma(r[u][t], pz[t], cb[g0 + u][2]);
             }
         }
     }
-}
+    // as BveVelT::group<T, true>
+    template <int T>
+    __device__ static __forceinline__ void diag(const SymParams& p, const Tgt (&tg)[T], double (&a)[T][NA],
+                                                const double (&s)[NS], const bool (&isself)[T], const SharedCtx&)
+    {
+        double d[T], r[T];
+#pragma unroll
+        for (int t = 0; t < T; ++t) {
+            d[t] = fma(-tg[t].x, s[0], p.R2);
+            d[t] = fma(-tg[t].y, s[1], d[t]);
+            d[t] = fma(-tg[t].z, s[2], d[t]);
+            d[t] = isself[t] ? 1.0 : d[t];          // keep the self pair out of the shared product
+        }
+        rcp_batch<T>(d, r);
+#pragma unroll
+        for (int t = 0; t < T; ++t) {
+            r[t] = isself[t] ? 0.0 : r[t];
+            a[t][0] = fma(r[t], s[3], a[t][0]);
+            a[t][1] = fma(r[t], s[4], a[t][1]);
+            a[t][2] = fma(r[t], s[5], a[t][2]);
+        }
+    }
+};
 
-// acc: [nsrc_pad][3] doubles, zeroed by the caller.
-template <int T, int BLOCK, int SB, int MINB, int ORDER = 0>
+// BVE stream functions (BveStream in pairs.cuh): psi_i = sum_j w_j ln(R^2 - x_i.x_j) for two weights;
+// record x, y, z, w_rel, w_abs, 0.  One dot product and ONE logarithm serve both directions of a pair:
+// 3 + 6 + 2 + 2 = 13 FP64 instructions for two interactions instead of 22.
+// The branch-free table logarithm (log_group_fast) is evaluated for the whole batch first; if any
+// argument of this thread was outside the table window the batch's logarithms are recomputed with
+// the library log() before anything is accumulated (the one-sided kernel redoes a whole tile instead).
+struct SymBveStream : LogSharedTable<32> {
+    static constexpr int NS = 6, NA = 2, NC = 2;
+    struct Tgt { double x, y, z, w0, w1; };
+    __device__ static __forceinline__ Tgt null() { return Tgt{0.0, 0.0, 0.0, 0.0, 0.0}; }
+    __device__ static __forceinline__ Tgt from_record(const double2 v0, const double2 v1, const double2 v2)
+    {
+        return Tgt{v0.x, v0.y, v1.x, v1.y, v2.x};
+    }
+    template <int T, int SB, int ORDER>
+    __device__ static __forceinline__ void batch(const SymParams& p, const Tgt (&tg)[T], double (&a)[T][NA],
+                                                 const double* __restrict__ sm, double (&cb)[SB][NC], const SharedCtx& sc)
+    {
+        double w[SB][2], l[SB][T];
+        unsigned worst = 0;
+#pragma unroll
+        for (int u = 0; u < SB; ++u) {
+            const double2* p2 = reinterpret_cast<const double2*>(sm + u * NS);
+            const double2 v0 = p2[0], v1 = p2[1], v2 = p2[2];
+            w[u][0] = v1.y; w[u][1] = v2.x;
+            double d[T];
+#pragma unroll
+            for (int t = 0; t < T; ++t) {
+                d[t] = fma(-tg[t].x, v0.x, p.R2);
+                d[t] = fma(-tg[t].y, v0.y, d[t]);
+                d[t] = fma(-tg[t].z, v1.x, d[t]);
+            }
+            log_group_fast<KS, T>(d, l[u], worst, sc);
+        }
+        if (__builtin_expect(needs_retry(worst), 0)) {
+#pragma unroll 1
+            for (int u = 0; u < SB; ++u) {
+                const double2* p2 = reinterpret_cast<const double2*>(sm + u * NS);
+                const double2 v0 = p2[0], v1 = p2[1];
+#pragma unroll
+                for (int t = 0; t < T; ++t) {
+                    double d = fma(-tg[t].x, v0.x, p.R2);
+                    d = fma(-tg[t].y, v0.y, d);
+                    d = fma(-tg[t].z, v1.x, d);
+                    const double lv = log_slow_path(d);
+#pragma unroll
+                    for (int uu = 0; uu < SB; ++uu)         // static indexing keeps l in registers
+                        if (uu == u) l[uu][t] = lv;
+                }
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < SB; ++u) {
+#pragma unroll
+            for (int t = 0; t < T; ++t) {
+                a[t][0] = fma(l[u][t], w[u][0], a[t][0]);
+                a[t][1] = fma(l[u][t], w[u][1], a[t][1]);
+            }
+            cb[u][0] = l[u][0] * tg[0].w0; cb[u][1] = l[u][0] * tg[0].w1;
+#pragma unroll
+            for (int t = 1; t < T; ++t) {
+                cb[u][0] = fma(l[u][t], tg[t].w0, cb[u][0]);
+                cb[u][1] = fma(l[u][t], tg[t].w1, cb[u][1]);
+            }
+        }
+    }
+    // as BveStream::group<T, true>
+    template <int T>
+    __device__ static __forceinline__ void diag(const SymParams& p, const Tgt (&tg)[T], double (&a)[T][NA],
+                                                const double (&s)[NS], const bool (&isself)[T], const SharedCtx& sc)
+    {
+        double d[T], l[T];
+#pragma unroll
+        for (int t = 0; t < T; ++t) {
+            d[t] = fma(-tg[t].x, s[0], p.R2);
+            d[t] = fma(-tg[t].y, s[1], d[t]);
+            d[t] = fma(-tg[t].z, s[2], d[t]);
+            d[t] = isself[t] ? p.R2 : d[t];         // any in-window value; the pair is zeroed below
+        }
+        log_group<KS, T>(d, l, sc);
+#pragma unroll
+        for (int t = 0; t < T; ++t) {
+            l[t] = isself[t] ? 0.0 : l[t];
+            a[t][0] = fma(l[t], s[3], a[t][0]);
+            a[t][1] = fma(l[t], s[4], a[t][1]);
+        }
+    }
+};
+
+// ---- the kernel ---------------------------------------------------------------
+// acc: [nsrc_pad][NC] doubles, zeroed by the caller (NA == NC: both directions feed the same sums).
+// dynamic shared memory: [2 tiles][K::KS table][2 mbarriers]
+template <class K, int T, int BLOCK, int SB, int MINB, int ORDER = 0>
 __global__ void __launch_bounds__(BLOCK, MINB)
-sym_bve_kernel(const SymGeom g, const double* __restrict__ src, double* __restrict__ acc)
+sym_kernel(const SymParams prm, const SymGeom g, const double* __restrict__ src, double* __restrict__ acc)
 {
-    constexpr int NS = 6, TS = kTile, TB = BLOCK * T, DT = TB / TS;
+    constexpr int NS = K::NS, NA = K::NA, NC = K::NC, TS = kTile, TB = BLOCK * T, DT = TB / TS;
+    static_assert(NS == 6, "records are three double2");
+    static_assert(NA == NC, "one accumulator array for both directions");
     static_assert(TB % TS == 0, "a target block must be whole source tiles");
     static_assert(TS % SB == 0, "source batch");
     constexpr uint32_t kTileBytes = TS * NS * sizeof(double);
     extern __shared__ __align__(128) unsigned char smem_raw[];
     double(*tile)[TS * NS] = reinterpret_cast<double(*)[TS * NS]>(smem_raw);
-    uint64_t* full = reinterpret_cast<uint64_t*>(smem_raw + 2 * kTileBytes);
+    double* ks = reinterpret_cast<double*>(smem_raw + 2 * kTileBytes);
+    uint64_t* full = reinterpret_cast<uint64_t*>(ks + K::KS);
 
     const int tid = threadIdx.x, lane = tid & 31;
     const int I = blockIdx.x % g.nblocks;           // chunk is the slow index, as in ds_kernel
@@ -216,20 +354,22 @@ sym_bve_kernel(const SymGeom g, const double* __restrict__ src, double* __restri
     if (k0 < kdiag) k0 = kdiag;
     if (k0 >= k1) return;                            // chunk entirely below the diagonal (whole CTA)
 
-    double tx[T], ty[T], tz[T], px[T], py[T], pz[T], a[T][3];
+    typename K::Tgt tg[T];
+    double a[T][NA];
     int32_t cidx[T];
 #pragma unroll
     for (int t = 0; t < T; ++t) {
         const int32_t c = I * TB + t * BLOCK + tid;
         cidx[t] = c;
-        tx[t] = ty[t] = tz[t] = px[t] = py[t] = pz[t] = 0.0;     // past the padded list: a null particle
+        tg[t] = K::null();                           // past the padded list: a null particle
         if (c < g.nsrc_pad) {
             const double2* p2 = reinterpret_cast<const double2*>(src + (size_t)c * NS);
-            const double2 v0 = p2[0], v1 = p2[1], v2 = p2[2];
-            tx[t] = v0.x; ty[t] = v0.y; tz[t] = v1.x; px[t] = v1.y; py[t] = v2.x; pz[t] = v2.y;
+            tg[t] = K::from_record(p2[0], p2[1], p2[2]);
         }
-        a[t][0] = a[t][1] = a[t][2] = 0.0;
+#pragma unroll
+        for (int q = 0; q < NA; ++q) a[t][q] = 0.0;
     }
+    const SharedCtx sctx{ks, K::init_shared(ks, prm, tid, BLOCK), g.half_bin};
     if (tid == 0) {
         mbar_init(&full[0], 1);
         mbar_init(&full[1], 1);
@@ -241,48 +381,34 @@ sym_bve_kernel(const SymGeom g, const double* __restrict__ src, double* __restri
         mbar_expect_tx(&full[st], kTileBytes);
         tma_bulk_g2s(tile[st], src + (size_t)k * TS * NS, kTileBytes, &full[st]);
     };
-    auto load_source = [&](const double* sm, int j, double (&s)[NS]) {
-        const double2* p2 = reinterpret_cast<const double2*>(sm + j * NS);
-#pragma unroll
-        for (int q = 0; q < NS / 2; ++q) {
-            const double2 v = p2[q];
-            s[2 * q] = v.x; s[2 * q + 1] = v.y;
-        }
-    };
-    // the block against itself: one-sided, self pair excluded (as BveVelT::group<T, true>)
+    // the block against itself: one-sided, self pair excluded
     auto diag_tile = [&](const int k, const int st) {
         const double* sm = tile[st];
         const int32_t j0 = k * TS;
 #pragma unroll 1
         for (int j = 0; j < TS; ++j) {
-            double s[NS], d[T], r[T];
-            load_source(sm, j, s);
+            double s[NS];
+            const double2* p2 = reinterpret_cast<const double2*>(sm + j * NS);
 #pragma unroll
-            for (int t = 0; t < T; ++t) {
-                d[t] = fma(-tx[t], s[0], g.R2);
-                d[t] = fma(-ty[t], s[1], d[t]);
-                d[t] = fma(-tz[t], s[2], d[t]);
-                d[t] = (j0 + j == cidx[t]) ? 1.0 : d[t];
+            for (int q = 0; q < NS / 2; ++q) {
+                const double2 v = p2[q];
+                s[2 * q] = v.x; s[2 * q + 1] = v.y;
             }
-            rcp_batch<T>(d, r);
+            bool isself[T];
 #pragma unroll
-            for (int t = 0; t < T; ++t) {
-                r[t] = (j0 + j == cidx[t]) ? 0.0 : r[t];
-                a[t][0] = fma(r[t], s[3], a[t][0]);
-                a[t][1] = fma(r[t], s[4], a[t][1]);
-                a[t][2] = fma(r[t], s[5], a[t][2]);
-            }
+            for (int t = 0; t < T; ++t) isself[t] = (j0 + j == cidx[t]);
+            K::template diag<T>(prm, tg, a, s, isself, sctx);
         }
     };
     // a tile above the diagonal: every pair once, both directions
     auto sym_tile = [&](const int k, const int st) {
         const double* sm = tile[st];
-        double* accj = acc + (size_t)k * TS * 3;
+        double* accj = acc + (size_t)k * TS * NC;
 #pragma unroll 1
         for (int jb = 0; jb < TS; jb += SB) {
-            double cb[SB][3];
-            sym_batch<T, SB, ORDER>(tx, ty, tz, px, py, pz, a, sm + jb * NS, g.R2, cb);
-            sym_reduce_red<SB>(cb, lane, accj + jb * 3);
+            double cb[SB][NC];
+            K::template batch<T, SB, ORDER>(prm, tg, a, sm + jb * NS, cb, sctx);
+            sym_reduce_red<SB, NC>(cb, lane, accj + jb * NC);
         }
     };
 
@@ -303,10 +429,15 @@ sym_bve_kernel(const SymGeom g, const double* __restrict__ src, double* __restri
 #pragma unroll
     for (int t = 0; t < T; ++t)
         if (cidx[t] < g.nsrc) {
-            atomicAdd(acc + (size_t)cidx[t] * 3 + 0, a[t][0]);
-            atomicAdd(acc + (size_t)cidx[t] * 3 + 1, a[t][1]);
-            atomicAdd(acc + (size_t)cidx[t] * 3 + 2, a[t][2]);
+#pragma unroll
+            for (int q = 0; q < NA; ++q) atomicAdd(acc + (size_t)cidx[t] * NA + q, a[t][q]);
         }
+}
+
+template <class K, int T, int BLOCK>
+constexpr size_t sym_smem_bytes()
+{
+    return 2 * size_t(kTile) * K::NS * sizeof(double) + sizeof(double) * K::KS + 2 * sizeof(uint64_t);
 }
 
 // u_i = x_i cross a_i for the active particles (BveVelT::finalize)
@@ -322,6 +453,17 @@ sym_bve_finalize(int32_t nsrc, const int32_t* __restrict__ active, const double*
     out.store(0, i, fma(y, a2, -(z * a1)));
     out.store(1, i, fma(z, a0, -(x * a2)));
     out.store(2, i, fma(x, a1, -(y * a0)));
+}
+
+// the two stream functions of the active particles (BveStream::finalize)
+__global__ void __launch_bounds__(256)
+sym_stream_finalize(int32_t nsrc, const int32_t* __restrict__ active, const double* __restrict__ acc, Outs<2> out)
+{
+    const int32_t c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= nsrc) return;
+    const int64_t i = active[c];
+    out.store(0, i, acc[(size_t)c * 2]);
+    out.store(1, i, acc[(size_t)c * 2 + 1]);
 }
 
 // passive[i - scan[i]] = i for every particle with mask 0 (stable, like the active list)

@@ -33,27 +33,74 @@ namespace lpm {
 constexpr int kSymVariant = 200;        // lpm_set_bve_variant: symmetric path, 4 targets per thread
 constexpr int kSymVariant8 = 201;       //                      8 targets per thread, batches of 4 sources
 
-template <int T, int BLOCK, int SB, int MINB>
-inline int launch_sym(cudaStream_t st, SymGeom g, const double* src, double* acc)
+template <class K, int T, int BLOCK, int SB, int MINB, int ORDER = 0>
+inline int launch_sym(cudaStream_t st, const SymParams& prm, SymGeom g, const double* src, double* acc)
 {
     constexpr int TB = BLOCK * T;
     g.nblocks = (g.nsrc_pad + TB - 1) / TB;
-    constexpr size_t smem = 2 * size_t(kTile) * 6 * sizeof(double) + 2 * sizeof(uint64_t);
+    g.half_bin = 1 << (19 - kLogBits);
+    constexpr size_t smem = sym_smem_bytes<K, T, BLOCK>();
     const int64_t grid = (int64_t)g.nblocks * g.nchunks;
-    if (grid <= 0 || grid > 0x7fffffffLL) return set_error(LPM_ERR_INVALID, "symmetric BVE grid %lld", (long long)grid);
-    sym_bve_kernel<T, BLOCK, SB, MINB><<<(unsigned)grid, BLOCK, smem, st>>>(g, src, acc);
+    if (grid <= 0 || grid > 0x7fffffffLL) return set_error(LPM_ERR_INVALID, "symmetric kernel grid %lld", (long long)grid);
+    if (smem > 48 * 1024) {     // per device, as in launch_ds
+        static bool configured[64] = {};
+        int devid = 0;
+        cudaGetDevice(&devid);
+        if (devid < 0 || devid >= 64 || !configured[devid]) {
+            LPM_CUDA(cudaFuncSetAttribute(sym_kernel<K, T, BLOCK, SB, MINB, ORDER>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            if (devid >= 0 && devid < 64) configured[devid] = true;
+        }
+    }
+    sym_kernel<K, T, BLOCK, SB, MINB, ORDER><<<(unsigned)grid, BLOCK, smem, st>>>(prm, g, src, acc);
     return LPM_OK;
 }
 
+// What differs between the two symmetric sums.
+struct SymVel {
+    using Op = OpBveVel;
+    using SK = SymBveVel;
+    static int launch(int variant, cudaStream_t st, const SymParams& prm, const SymGeom& g, const double* src, double* acc)
+    {
+        // statement order 27: the best of the 32 under the operand-delivery model (tools/sym_score.py)
+        if (variant == kSymVariant8) return launch_sym<SK, 8, 128, 4, 1, 27>(st, prm, g, src, acc);
+        return launch_sym<SK, 4, 128, 8, 2, 27>(st, prm, g, src, acc);
+    }
+    static void finalize(cudaStream_t st, const MaskPlan& mp, const double* src, const double* acc, const Outs<3>& out)
+    {
+        sym_bve_finalize<<<(unsigned)((mp.nsrc + 255) / 256), 256, 0, st>>>(mp.nsrc, mp.active.as<int32_t>(), src, acc, out);
+    }
+};
+struct SymStream {
+    using Op = OpBveStream;
+    using SK = SymBveStream;
+    static int launch(int variant, cudaStream_t st, const SymParams& prm, const SymGeom& g, const double* src, double* acc)
+    {
+        // 64 KB table per CTA, so two CTAs per SM either way: 256 threads under a 128-register cap (ptxas spills
+        // 24 bytes) or 128 threads with ~165 registers
+        if (variant == kSymVariant8) return launch_sym<SK, 4, 128, 4, 2>(st, prm, g, src, acc);
+        return launch_sym<SK, 4, 256, 4, 2>(st, prm, g, src, acc);
+    }
+    static void finalize(cudaStream_t st, const MaskPlan& mp, const double*, const double* acc, const Outs<2>& out)
+    {
+        sym_stream_finalize<<<(unsigned)((mp.nsrc + 255) / 256), 256, 0, st>>>(mp.nsrc, mp.active.as<int32_t>(), acc, out);
+    }
+};
+
 // Whole evaluation: one device, or -- rank mode -- collectively on every rank (each must call with its
 // LoadBalance slice, sym_applicable() checks that): target blocks of the active x active part are dealt
-// round-robin to the ranks and the accumulators summed with one ncclAllReduce (3 F doubles); the passive
+// round-robin to the ranks and the accumulators summed with one ncclAllReduce (NC F doubles); the passive
 // targets are sliced by LoadBalance and exchanged with the grouped broadcast of allgather_slices().
 // Every rank then writes ALL n results into its own `out` (no peer stores), so the caller has nothing
-// left to exchange.  a: the OpBveVel arguments; out: where u, v, w go (replica 0 only is used).
-inline int bve_velocity_sym(Device& dev, cudaStream_t st, MaskPlan& mp, const Args& a, const Outs<3>& out, int variant)
+// left to exchange.  a: the Op's arguments; out: where the results go (replica 0 only is used).
+template <class S>
+inline int sym_evaluate(Device& dev, cudaStream_t st, MaskPlan& mp, const Args& a,
+                        const Outs<S::Op::NOUT>& out, int variant)
 {
-    using K = BveVel;
+    using Op = typename S::Op;
+    using K = typename Op::K;
+    using SK = typename S::SK;
+    constexpr int NOUT = Op::NOUT;
+    static_assert(SK::NC == NOUT && K::NS == SK::NS, "the symmetric functor reads the one-sided kernel's records");
     Runtime& R = rt();
     Workspace& ws = dev.ws;
     const bool prof = R.profiling;
@@ -64,7 +111,7 @@ inline int bve_velocity_sym(Device& dev, cudaStream_t st, MaskPlan& mp, const Ar
         R.profiling = false;        // one event pair around both kernels
     }
     auto body = [&]() -> int {
-        LPM_TRY(OpBveVel::pack(dev, st, mp, a));
+        LPM_TRY(Op::pack(dev, st, mp, a));          // records, and the log window for the stream functions
         const double* src = ws.sources.as<double>();
         SymGeom g{};
         int32_t chunk = 0;
@@ -74,20 +121,23 @@ inline int bve_velocity_sym(Device& dev, cudaStream_t st, MaskPlan& mp, const Ar
         g.chunk_tiles = chunk / kTile;
         g.world = R.rank_mode ? R.world : 1;
         g.rank = R.rank_mode ? R.rank : 0;
-        g.R2 = a.sc[0] * a.sc[0];
+        SymParams prm{};
+        prm.R2 = a.sc[0] * a.sc[0];
+        if constexpr (SK::KS > 0) {
+            prm.logtab = dev.logtab;
+            prm.win = ws.logwin.as<int32_t>() + 1;
+        }
         // ---- active x active
         if (mp.nsrc > 0) {
-            LPM_TRY(ws.sym_acc.reserve((size_t)g.nsrc_pad * 3 * sizeof(double)));
-            LPM_CUDA(cudaMemsetAsync(ws.sym_acc.p, 0, (size_t)g.nsrc_pad * 3 * sizeof(double), st));
-            if (variant == kSymVariant8) LPM_TRY((launch_sym<8, 128, 4, 1>(st, g, src, ws.sym_acc.as<double>())));
-            else LPM_TRY((launch_sym<4, 128, 8, 2>(st, g, src, ws.sym_acc.as<double>())));
+            const size_t nacc = (size_t)g.nsrc_pad * SK::NC;
+            LPM_TRY(ws.sym_acc.reserve(nacc * sizeof(double)));
+            LPM_CUDA(cudaMemsetAsync(ws.sym_acc.p, 0, nacc * sizeof(double), st));
+            LPM_TRY(S::launch(variant, st, prm, g, src, ws.sym_acc.as<double>()));
             if (g.world > 1) {
                 if (!R.comm) return set_error(LPM_ERR_COMM, "world size %d but no communicator (lpm_comm_init_rank)", R.world);
-                LPM_NCCL(nccl().AllReduce(ws.sym_acc.p, ws.sym_acc.p, (size_t)g.nsrc_pad * 3, /*ncclDouble*/ 8, /*ncclSum*/ 0,
-                                          R.comm, st));
+                LPM_NCCL(nccl().AllReduce(ws.sym_acc.p, ws.sym_acc.p, nacc, /*ncclDouble*/ 8, /*ncclSum*/ 0, R.comm, st));
             }
-            sym_bve_finalize<<<(unsigned)((mp.nsrc + 255) / 256), 256, 0, st>>>(mp.nsrc, mp.active.as<int32_t>(), src,
-                                                                                ws.sym_acc.as<double>(), out);
+            S::finalize(st, mp, src, ws.sym_acc.as<double>(), out);
             count_launch(2);
         }
         // ---- passive targets x all active sources: the one-sided engine on the gathered passive particles
@@ -101,35 +151,36 @@ inline int bve_velocity_sym(Device& dev, cudaStream_t st, MaskPlan& mp, const Ar
             const unsigned gb = (unsigned)((nv + 255) / 256);
             for (int k = 0; k < 3; ++k) {
                 LPM_TRY(ws.gathered[k].reserve((size_t)nv * sizeof(double)));
-                LPM_TRY(ws.sorted_out[k].reserve((size_t)nv * sizeof(double)));
                 gather_kernel<<<gb, 256, 0, st>>>(nv, perm, a.in[k], ws.gathered[k].as<double>());
             }
             count_launch(4);
-            K::Params prm{};
-            prm.x = ws.gathered[0].as<double>(); prm.y = ws.gathered[1].as<double>(); prm.z = ws.gathered[2].as<double>();
-            prm.R2 = g.R2;
-            prm.out.nrep = 1;
-            for (int k = 0; k < 3; ++k) prm.out.p[0][k] = ws.sorted_out[k].as<double>();
+            typename K::Params prm1{};
+            prm1.x = ws.gathered[0].as<double>(); prm1.y = ws.gathered[1].as<double>(); prm1.z = ws.gathered[2].as<double>();
+            prm1.R2 = prm.R2;
+            prm1.out.nrep = 1;
+            double* bufs[NOUT];
+            for (int k = 0; k < NOUT; ++k) {
+                LPM_TRY(ws.sorted_out[k].reserve((size_t)nv * sizeof(double)));
+                bufs[k] = ws.sorted_out[k].as<double>();
+                prm1.out.p[0][k] = bufs[k];
+            }
             MaskPlan view;                          // not owned: the sources of mp, no self pairs
             view.n = nv; view.nsrc = mp.nsrc;
             view.scan.p = ws.sort_vals[0].p; view.scan.cap = ws.sort_vals[0].cap;
             view.active.p = mp.active.p; view.active.cap = mp.active.cap;
             int64_t vb = 0, ve = nv;
             if (g.world > 1) load_balance0(nv, g.world, g.rank, &vb, &ve);
-            const int rc = direct_sum<K>(dev, st, view, vb, ve, prm, 0, nv);
+            const int rc = direct_sum<K>(dev, st, view, vb, ve, prm1, 0, nv);
             view.scan = DevBuf{}; view.active = DevBuf{};
             LPM_TRY(rc);
-            if (g.world > 1) {
-                double* bufs[3] = {ws.sorted_out[0].as<double>(), ws.sorted_out[1].as<double>(), ws.sorted_out[2].as<double>()};
-                LPM_TRY(allgather_slices(3, bufs, nv, st));
-            }
-            for (int k = 0; k < 3; ++k) {
+            if (g.world > 1) LPM_TRY(allgather_slices(NOUT, bufs, nv, st));
+            for (int k = 0; k < NOUT; ++k) {
                 ScatterDst dst{};
                 dst.nrep = 1;
                 dst.p[0] = out.p[0][k];
-                scatter_kernel<<<gb, 256, 0, st>>>(nv, perm, ws.sorted_out[k].as<double>(), dst);
+                scatter_kernel<<<gb, 256, 0, st>>>(nv, perm, bufs[k], dst);
             }
-            count_launch(3);
+            count_launch(NOUT);
         }
         LPM_CUDA(cudaGetLastError());
         return LPM_OK;
@@ -140,6 +191,15 @@ inline int bve_velocity_sym(Device& dev, cudaStream_t st, MaskPlan& mp, const Ar
         if (rc == LPM_OK) LPM_CUDA(cudaEventRecord(pe, st));
     }
     return rc;
+}
+
+inline int bve_velocity_sym(Device& dev, cudaStream_t st, MaskPlan& mp, const Args& a, const Outs<3>& out, int variant)
+{
+    return sym_evaluate<SymVel>(dev, st, mp, a, out, variant);
+}
+inline int bve_stream_sym(Device& dev, cudaStream_t st, MaskPlan& mp, const Args& a, const Outs<2>& out, int variant)
+{
+    return sym_evaluate<SymStream>(dev, st, mp, a, out, variant);
 }
 
 // May this evaluation take the symmetric path?  One device driving every target, or rank mode with this

@@ -58,6 +58,32 @@ def test_sym_bve_velocity_random_ragged(sym, oracle, n, frac, seed):
         assert relerr(g, w) <= TOL
 
 
+@pytest.mark.parametrize("sym", [200, 201], indirect=True)
+@pytest.mark.parametrize("seed,L", [(M.ICOS_TRI_SPHERE_SEED, 2), (M.ICOS_TRI_SPHERE_SEED, 5), (M.CUBED_SPHERE_SEED, 5)])
+def test_sym_bve_stream_meshes(sym, oracle, get_mesh, seed, L):
+    m = get_mesh(seed, L)
+    zeta = problems.rossby_haurwitz54(m)
+    av = problems.abs_vorticity(m, zeta, 2.0 * np.pi)
+    got = sym.bve_stream(m.x, m.y, m.z, zeta, av, m.area, m.is_active, 1.0)
+    want = oracle.bve_stream(m.x, m.y, m.z, zeta, av, m.area, m.is_active, 1.0)
+    for g, w in zip(got, want):
+        assert relerr(g, w) <= TOL
+
+
+@pytest.mark.parametrize("sym", [200, 201], indirect=True)
+@pytest.mark.parametrize("n,frac,seed,R", [(3, 0.5, 3, 1.0), (513, 0.9, 5, 1.0), (4099, 0.6, 12345, 1.7),
+                                           (20011, 0.55, 7, 6.371e6), (6000, 1.0, 8, 3.0e-7), (3000, 0.0, 9, 1.0)])
+def test_sym_bve_stream_random_ragged(sym, oracle, n, frac, seed, R):
+    """Ragged sizes and radii whose arguments fall in very different binades of the log table."""
+    x, y, z, zeta, area, mask = _rand_sphere(n, seed, frac)
+    x, y, z = R * x, R * y, R * z
+    av = zeta + 0.3 * z / R
+    got = sym.bve_stream(x, y, z, zeta, av, area, mask, R)
+    want = oracle.bve_stream(x, y, z, zeta, av, area, mask, R)
+    for g, w in zip(got, want):
+        assert relerr(g, w) <= TOL
+
+
 @pytest.mark.parametrize("sym", [200], indirect=True)
 def test_sym_matches_default_path(sym, get_mesh):
     """Same sum, other order: within a few ulp of the default kernel at icosTri 6."""
@@ -80,7 +106,7 @@ def test_sym_rk4_step(sym, oracle, get_mesh):
     sph = solvers.BVEMesh(m, zeta, 1.0, omega)
     sph.velocity = [u.copy(), v.copy(), w.copy()]
     sol = solvers.BVESolver(sph)
-    sol.Timestep(sph, 0.01, with_stream=False)
+    sol.Timestep(sph, 0.01, with_stream=True)
     sol.Delete()
     ref = oracle.bve_rk4_step(m.x, m.y, m.z, zeta, u, v, w, m.area, m.is_active, 1.0, omega, 0.01)
     got = [sph.x, sph.y, sph.z, sph.relVort] + sph.velocity

@@ -74,8 +74,8 @@ def shfl_xor(v, off):
 
 
 def reduce_red(cb):
-    """sym_reduce_red<SB>: cb[lane, s, a] -> list of (lane, source, component, value) REDs."""
-    SB = cb.shape[1]
+    """sym_reduce_red<SB, NC>: cb[lane, s, a] -> list of (lane, source, component, value) REDs."""
+    SB, NC = cb.shape[1], cb.shape[2]
     lane = np.arange(32)
     if SB == 8:
         levels, low = [(16, 4), (8, 2), (4, 1)], [2, 1]
@@ -84,9 +84,9 @@ def reduce_red(cb):
     v = cb.copy()
     for off, half in levels:
         bit = (lane & off) != 0
-        nxt = np.empty((32, half, 3))
+        nxt = np.empty((32, half, NC))
         for k in range(half):
-            for a in range(3):
+            for a in range(NC):
                 lo, hi = v[:, k, a], v[:, k + half, a]
                 keep = np.where(bit, hi, lo)
                 send = np.where(bit, lo, hi)
@@ -94,24 +94,24 @@ def reduce_red(cb):
         v = nxt
     v = v[:, 0, :]
     for off in low:
-        v = v + np.stack([shfl_xor(v[:, a], off) for a in range(3)], axis=1)
+        v = v + np.stack([shfl_xor(v[:, a], off) for a in range(NC)], axis=1)
     if SB == 8:
         sidx, q = (lane >> 2) & 7, lane & 3
     else:
         sidx, q = (lane >> 3) & 3, lane & 7
-    return [(l, int(sidx[l]), int(q[l]), v[l, q[l]]) for l in range(32) if q[l] < 3]
+    return [(l, int(sidx[l]), int(q[l]), v[l, q[l]]) for l in range(32) if q[l] < NC]
 
 
-@pytest.mark.parametrize("SB", [8, 4])
-def test_recursive_halving_reduction(SB):
+@pytest.mark.parametrize("SB,NC", [(8, 3), (4, 3), (4, 2), (8, 2), (4, 1)])
+def test_recursive_halving_reduction(SB, NC):
     rng = np.random.default_rng(7)
-    cb = rng.integers(-1000, 1000, size=(32, SB, 3)).astype(np.float64)      # integers: sums are exact
+    cb = rng.integers(-1000, 1000, size=(32, SB, NC)).astype(np.float64)      # integers: sums are exact
     reds = reduce_red(cb)
     seen = {}
     for _, s, a, val in reds:
         assert (s, a) not in seen, "one RED per (source, component)"
         seen[(s, a)] = val
-    assert len(seen) == SB * 3
+    assert len(seen) == SB * NC
     total = cb.sum(axis=0)
     for (s, a), val in seen.items():
         assert val == total[s, a]

@@ -1,4 +1,4 @@
-"""A/B on one box (run under gpurun): the default BVE velocity path against the EXPERIMENTAL pair-symmetric one
+"""A/B on one box (run under gpurun): the default BVE velocity / stream-function paths against the EXPERIMENTAL pair-symmetric ones
 (lpm_set_bve_variant(200 / 201), csrc/symmetric.cuh) at icosTri levels argv[1] (default "6,7").
 Prints, per variant, the whole-sum time (pack, kernels, finalize / gather / scatter), the interactions/s, and the
 largest difference from the default path's result relative to the field scale.
@@ -16,17 +16,20 @@ for L in levels:
     m = mesh.PolyMesh2d(mesh.ICOS_TRI_SPHERE_SEED, L)
     z = problems.rossby_haurwitz54(m)
     pairs = m.n * m.n_active - m.n_active
-    ref = None
-    for var in variants:
-        api.set_bve_variant(var)
-        ts = []
-        for _ in range(3 if L < 8 else 2):
-            out = api.bve_velocity(m.x, m.y, m.z, z, m.area, m.is_active, 1.0)
-            ts.append(api.last_sum_ms())
-        if ref is None:
-            ref = out
-        scale = max(np.abs(r).max() for r in ref)
-        diff = max(np.abs(a - b).max() for a, b in zip(out, ref)) / scale
-        print(f"L{L} variant {var}: sum ms " + " ".join(f"{t:.3f}" for t in ts) +
-              f"  -> {pairs / min(ts) / 1e9:.1f} G interactions/s, max diff from variant {variants[0]}: {diff:.2e}", flush=True)
+    av = problems.abs_vorticity(m, z, 2 * np.pi)
+    for name, fn in (("bve_velocity", lambda: api.bve_velocity(m.x, m.y, m.z, z, m.area, m.is_active, 1.0)),
+                     ("bve_stream", lambda: api.bve_stream(m.x, m.y, m.z, z, av, m.area, m.is_active, 1.0))):
+        ref = None
+        for var in variants:
+            api.set_bve_variant(var)
+            ts = []
+            for _ in range(3 if L < 8 else 2):
+                out = fn()
+                ts.append(api.last_sum_ms())
+            if ref is None:
+                ref = out
+            scale = max(np.abs(r).max() for r in ref)
+            diff = max(np.abs(a - b).max() for a, b in zip(out, ref)) / scale
+            print(f"L{L} {name} variant {var}: sum ms " + " ".join(f"{t:.3f}" for t in ts) +
+                  f"  -> {pairs / min(ts) / 1e9:.1f} G interactions/s, max diff from variant {variants[0]}: {diff:.2e}", flush=True)
 api.set_bve_variant(0)

@@ -20,24 +20,31 @@ def function_sass(pattern, path):
                 ins.append((int(m.group(1), 16), m.group(3), m.group(4)))
     return ins
 
-def hot_loop(ins):
+def hot_loop(ins, allow_inner=False):
+    """The backward-branch loop with the most FP64 instructions that has no loop inside.  With
+    allow_inner, loops inside are tolerated (and cut out of the body) when they hold < 25 % of the
+    body's FP64 instructions -- a rarely taken slow path, e.g. the library-log() retry of the log kernels."""
+    def target(x):
+        mm = re.search(r'0x([0-9a-f]+)', x[2])
+        return int(mm.group(1), 16) if (x[1].startswith('BRA') and mm) else None
+    fp = lambda body: sum(o.startswith(('DFMA', 'DMUL', 'DADD')) for _, o, _ in body)
     best = None
-    for a, op, rest in ins:
-        if op.startswith('BRA'):
-            m = re.search(r'0x([0-9a-f]+)', rest)
-            if m and int(m.group(1), 16) < a:
-                t = int(m.group(1), 16)
-                body = [x for x in ins if t <= x[0] <= a]
-                # innermost loops only: no other BACKWARD branch inside (forward branches, e.g. around a
-                # predicated atomic, are fine)
-                def backward(x):
-                    mm = re.search(r'0x([0-9a-f]+)', x[2])
-                    return x[1].startswith('BRA') and mm and int(mm.group(1), 16) < x[0]
-                if sum(1 for x in body if backward(x)) > 1:
-                    continue
-                n = sum(o.startswith(('DFMA', 'DMUL', 'DADD')) for _, o, _ in body)
-                if best is None or n > best[0]:
-                    best = (n, body)
+    for x in ins:
+        t = target(x)
+        if t is None or t >= x[0]:
+            continue
+        body = [y for y in ins if t <= y[0] <= x[0]]
+        inner = [(target(y), y[0]) for y in body[:-1] if target(y) is not None and target(y) < y[0]]
+        if inner:
+            if not allow_inner:
+                continue
+            cut = [y for y in body if any(a <= y[0] <= b for a, b in inner)]
+            if fp(cut) >= 0.25 * fp(body):
+                continue
+            body = [y for y in body if y not in cut]
+        n = fp(body)
+        if best is None or n > best[0]:
+            best = (n, body)
     return best[1] if best else []
 
 def bank_stats(body, bank=lambda r: (r // 2) % 2):

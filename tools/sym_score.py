@@ -6,7 +6,8 @@ pair is two interactions) with the cycle model that matches the two measured ker
 (BVE velocity: model 20.8 / measured 20.3 cycles per interaction per SM sub-partition; BVE stream
 functions: 29.6 / 32.3):   cycles = max(2 * FP64 instructions, fresh + 0.5 same2 + same3).
 
-usage: sym_score.py [T] [SB] [MINB] [order ...]        (orders default to 0)"""
+usage: sym_score.py [T] [SB] [MINB] [order ...]        (orders default to 0)
+       SYM_KERNEL=SymBveStream SYM_BLOCK=256 sym_score.py 4 4 2"""
 import concurrent.futures as cf
 import os, shutil, subprocess, sys, tempfile
 
@@ -17,26 +18,28 @@ from sass_banks import bank_stats, function_sass, hot_loop
 TU = r'''
 #include "sym_kernels.cuh"
 using namespace lpm;
-template __global__ void lpm::sym_bve_kernel<TT, 128, SBB, LB_MIN, ORD>(const SymGeom, const double*, double*);
+template __global__ void lpm::sym_kernel<KK, TT, BLK, SBB, LB_MIN, ORD>(const SymParams, const SymGeom, const double*, double*);
 '''
 
 def cycles(st):
     return max(2.0 * st["fp64"], st["fresh"] + 0.5 * st["same2"] + st["same3"])
 
-def score(order, T, SB, minb, work):
-    out = os.path.join(work, f"o{order}_{T}_{SB}_{minb}.cubin")
+def score(order, T, SB, minb, work, kern="SymBveVel", block=128):
+    out = os.path.join(work, f"o{order}_{T}_{SB}_{minb}_{kern}_{block}.cubin")
     r = subprocess.run(["nvcc", "-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
                         f"-I{ROOT}/include", f"-I{ROOT}/lpm_v2_b200/csrc", f"-DORD={order}", f"-DTT={T}", f"-DSBB={SB}",
-                        f"-DLB_MIN={minb}", "-Xptxas", "-v", "-cubin", "-o", out, os.path.join(work, "tu.cu")],
+                        f"-DLB_MIN={minb}", f"-DKK={kern}", f"-DBLK={block}", "-Xptxas", "-v", "-cubin", "-o", out, os.path.join(work, "tu.cu")],
                        capture_output=True, text=True)
     if r.returncode != 0:
         return order, None, r.stderr[-400:]
-    regs = [l for l in r.stderr.splitlines() if "registers" in l]
-    spill = [l for l in r.stderr.splitlines() if "spill" in l]
-    st = bank_stats(hot_loop(function_sass("sym_bve_kernel", out)))
+    lines = r.stderr.splitlines()
+    at = max((i for i, l in enumerate(lines) if "Compiling entry function" in l and "sym_kernel" in l), default=0)
+    regs = [l.split("Used")[1].split(",")[0].strip() for l in lines[at:at + 4] if "registers" in l]
+    spill = [l.strip() for l in lines[at:at + 4] if "spill" in l]
+    st = bank_stats(hot_loop(function_sass("sym_kernel", out), allow_inner=True))
     os.remove(out)
     inter = 2.0 * T * SB
-    return order, {k: v / inter for k, v in st.items()} | {"cycles": cycles(st) / inter}, (regs[-1].strip() if regs else "") + " | " + (spill[-1].strip() if spill else "")
+    return order, {k: v / inter for k, v in st.items()} | {"cycles": cycles(st) / inter}, (regs[0] if regs else "?") + " | " + (spill[0] if spill else "")
 
 if __name__ == "__main__":
     T = int(sys.argv[1]) if len(sys.argv) > 1 else 4
@@ -46,7 +49,8 @@ if __name__ == "__main__":
     work = tempfile.mkdtemp(prefix="sym_score_")
     open(os.path.join(work, "tu.cu"), "w").write(TU)
     with cf.ThreadPoolExecutor(max_workers=os.cpu_count() or 4) as ex:
-        res = list(ex.map(lambda o: score(o, T, SB, MINB, work), orders))
+        res = list(ex.map(lambda o: score(o, T, SB, MINB, work, os.environ.get('SYM_KERNEL', 'SymBveVel'),
+                                          int(os.environ.get('SYM_BLOCK', '128'))), orders))
     shutil.rmtree(work, ignore_errors=True)
     for order, sc, info in sorted(res, key=lambda r: (r[1] or {}).get("cycles", 1e9)):
         if sc is None:
