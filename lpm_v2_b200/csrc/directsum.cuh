@@ -71,7 +71,13 @@ inline void ds_chunks(int64_t nsrc, int32_t* nsrc_pad, int32_t* chunk, int32_t* 
     *nsrc_pad = (int32_t)pad; *chunk = (int32_t)ch; *nchunks = (int32_t)nc;
 }
 
-// ---- mbarrier / TMA bulk copy (PTX) ------------------------------------------
+// ---- mbarrier / TMA bulk copy / MUFU (PTX) ------------------------------------
+// LPM_CUDA_EMU is defined only by tests/cuda_emu, which compiles these kernel sources with g++ to
+// run them on CPU threads (a test of the kernels' logic, never part of liblpmgpu.so); it supplies
+// its own versions of the few primitives that are inline PTX here.
+#ifdef LPM_CUDA_EMU
+#include "emu_primitives.h"
+#else
 __device__ __forceinline__ uint32_t smem_u32(const void* p)
 {
     return (uint32_t)__cvta_generic_to_shared(p);
@@ -79,6 +85,10 @@ __device__ __forceinline__ uint32_t smem_u32(const void* p)
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count)
 {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_fence_init()
+{
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
 }
 __device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes)
 {
@@ -97,14 +107,6 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity)
         : "memory");
     return ok != 0;
 }
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity)
-{
-    // Bounded: a lost copy traps instead of hanging the device.
-#pragma unroll 1
-    for (uint32_t it = 0; it < (1u << 26); ++it)
-        if (mbar_try_wait(bar, parity)) return;
-    __trap();
-}
 __device__ __forceinline__ void tma_bulk_g2s(void* dst_smem, const void* src_gmem, uint32_t bytes, uint64_t* bar)
 {
     asm volatile(
@@ -112,6 +114,29 @@ __device__ __forceinline__ void tma_bulk_g2s(void* dst_smem, const void* src_gme
             smem_u32(dst_smem)),
         "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
         : "memory");
+}
+// MUFU.RCP64H: a >= 20-bit reciprocal whose low word is zero
+__device__ __forceinline__ double rcp_approx_f64(double d)
+{
+    double r;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(d));
+    return r;
+}
+// (hi & 0xfffff000) | half as ONE LOP3 (pairs.cuh, log_bin_rcp)
+__device__ __forceinline__ int lop3_and_or(int hi, int half)
+{
+    int r;
+    asm("lop3.b32 %0, %1, 0xfffff000, %2, 0xEA;" : "=r"(r) : "r"(hi), "r"(half));
+    return r;
+}
+#endif
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity)
+{
+    // Bounded: a lost copy traps instead of hanging the device.
+#pragma unroll 1
+    for (uint32_t it = 0; it < (1u << 26); ++it)
+        if (mbar_try_wait(bar, parity)) return;
+    __trap();
 }
 
 // What ds_kernel hands to group(): the functor's per-CTA shared table and one integer of
@@ -201,7 +226,7 @@ ds_kernel(const typename K::Params prm, const DsGeom g, const double* __restrict
     if (tid == 0) {
         mbar_init(&full[0], 1);
         mbar_init(&full[1], 1);
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        mbar_fence_init();
     }
 
     // ---- tile culling (compactly supported kernels only) ------------------------------

@@ -39,8 +39,7 @@ struct Outs {
 // e^3 < 2^-57 before rounding.  (An IEEE divide costs ~10 DFMA-pipe slots.)
 __device__ __forceinline__ double rcp_fast(double d)
 {
-    double r0;
-    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r0) : "d"(d));
+    const double r0 = rcp_approx_f64(d);
     double e = fma(-d, r0, 1.0);
     double t = fma(e, e, e);
     return fma(r0, t, r0);
@@ -127,12 +126,8 @@ __device__ __forceinline__ double log_bin_rcp(int hi, int half = 0x00000800)
 {
     // (hi & 0xfffff000) | half as ONE LOP3: `half` arrives in a register (SharedCtx), because
     // ptxas splits the expression in two when both masks are immediates
-    int chi;
-    asm("lop3.b32 %0, %1, 0xfffff000, %2, 0xEA;" : "=r"(chi) : "r"(hi), "r"(half));
-    const double c = __hiloint2double(chi, 0);
-    double q;
-    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(q) : "d"(c));
-    return q;
+    const double c = __hiloint2double(lop3_and_or(hi, half), 0);
+    return rcp_approx_f64(c);
 }
 __global__ void log_table_seed_kernel(double* q)      // q[idx] for the host to turn into -ln q[idx]
 {

@@ -373,7 +373,7 @@ sym_kernel(const SymParams prm, const SymGeom g, const double* __restrict__ src,
     if (tid == 0) {
         mbar_init(&full[0], 1);
         mbar_init(&full[1], 1);
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        mbar_fence_init();
     }
     __syncthreads();
 

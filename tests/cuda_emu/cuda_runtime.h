@@ -1,0 +1,3 @@
+// stub of <cuda_runtime.h> for tests/cuda_emu (see emu_core.h)
+#pragma once
+#include "emu_core.h"

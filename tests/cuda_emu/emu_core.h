@@ -1,0 +1,173 @@
+// emu_core.h -- TEST INFRASTRUCTURE ONLY.  A minimal SIMT emulator: enough of the CUDA device
+// vocabulary to compile lpm_v2_b200/csrc/{directsum,pairs,sym_kernels}.cuh with g++ and run their
+// kernels on CPU threads -- one OS thread per CUDA thread, one CTA at a time, pthread barriers for
+// __syncthreads() and for the warp shuffles.  It checks the LOGIC of kernel source that has not run on
+// a GPU yet (indexing, pipelines, warp reductions, retry paths); it says nothing about speed, and
+// nothing in liblpmgpu.so uses it.
+#pragma once
+#include <pthread.h>
+#include <sched.h>
+
+#include <atomic>
+#include <cmath>
+#include <cstdint>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <functional>
+#include <thread>
+#include <vector>
+
+#define __global__
+#define __device__
+#define __host__
+#define __forceinline__ inline __attribute__((always_inline))
+#define __noinline__ __attribute__((noinline))
+#define __restrict__ __restrict
+#define __launch_bounds__(...)
+#define __shared__
+#define __constant__
+#define __align__(n)
+
+struct EmuDim3 { unsigned x = 1, y = 1, z = 1; };
+inline thread_local EmuDim3 threadIdx, blockIdx, blockDim, gridDim;
+
+struct double2 { double x, y; };
+inline double2 make_double2(double x, double y) { return double2{x, y}; }
+
+using cudaStream_t = void*;
+
+// ---- one CTA at a time -------------------------------------------------------------------------
+struct EmuCta {
+    int nthreads = 0;
+    pthread_barrier_t cta_bar;
+    std::vector<pthread_barrier_t> warp_bar;
+    std::vector<uint64_t> xchg;          // [warp][32]
+};
+inline EmuCta* g_emu_cta = nullptr;
+
+inline void __syncthreads() { pthread_barrier_wait(&g_emu_cta->cta_bar); }
+[[noreturn]] inline void __trap()
+{
+    std::fprintf(stderr, "cuda_emu: __trap() in block %u thread %u\n", blockIdx.x, threadIdx.x);
+    std::abort();
+}
+
+template <class T>
+inline T emu_warp_exchange(T v, int src_lane)
+{
+    static_assert(sizeof(T) <= 8, "shuffle of at most 64 bits");
+    const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    uint64_t bits = 0;
+    std::memcpy(&bits, &v, sizeof(T));
+    g_emu_cta->xchg[w * 32 + lane] = bits;
+    pthread_barrier_wait(&g_emu_cta->warp_bar[w]);
+    const uint64_t got = g_emu_cta->xchg[w * 32 + (src_lane & 31)];
+    pthread_barrier_wait(&g_emu_cta->warp_bar[w]);
+    T r;
+    std::memcpy(&r, &got, sizeof(T));
+    return r;
+}
+template <class T> inline T __shfl_xor_sync(unsigned, T v, int off) { return emu_warp_exchange(v, (threadIdx.x & 31) ^ off); }
+template <class T> inline T __shfl_up_sync(unsigned, T v, int d)
+{
+    const int lane = threadIdx.x & 31;
+    return emu_warp_exchange(v, lane >= d ? lane - d : lane);
+}
+inline unsigned __ballot_sync(unsigned, bool p)
+{
+    unsigned m = 0;
+    for (int l = 0; l < 32; ++l) m |= (emu_warp_exchange<unsigned>(p ? 1u : 0u, l) << l);
+    return m;
+}
+inline int __ffs(unsigned v) { return __builtin_ffs((int)v); }
+
+// ---- atomics (the threads of a CTA run concurrently) -------------------------------------------
+inline double atomicAdd(double* p, double v)
+{
+    uint64_t* u = reinterpret_cast<uint64_t*>(p);
+    uint64_t old = __atomic_load_n(u, __ATOMIC_RELAXED);
+    for (;;) {
+        double o;
+        std::memcpy(&o, &old, 8);
+        const double nv = o + v;
+        uint64_t nb;
+        std::memcpy(&nb, &nv, 8);
+        if (__atomic_compare_exchange_n(u, &old, nb, false, __ATOMIC_ACQ_REL, __ATOMIC_RELAXED)) return o;
+    }
+}
+inline int atomicMax(int* p, int v)
+{
+    int old = __atomic_load_n(p, __ATOMIC_RELAXED);
+    while (old < v && !__atomic_compare_exchange_n(p, &old, v, false, __ATOMIC_ACQ_REL, __ATOMIC_RELAXED)) {}
+    return old;
+}
+
+// ---- device math intrinsics --------------------------------------------------------------------
+using std::fma;
+using std::fmax;
+using std::sqrt;
+using std::cosh;
+using std::log;
+using std::floor;
+using std::sinh;
+using std::sin;
+using std::cos;
+using std::exp;
+using std::atan2;
+using std::fabs;
+inline double rsqrt(double v) { return 1.0 / std::sqrt(v); }
+inline void sincospi(double v, double* s, double* c) { *s = std::sin(M_PI * v); *c = std::cos(M_PI * v); }
+inline double __dadd_rn(double a, double b) { return a + b; }
+inline double __hiloint2double(int hi, int lo)
+{
+    const uint64_t b = ((uint64_t)(uint32_t)hi << 32) | (uint32_t)lo;
+    double d;
+    std::memcpy(&d, &b, 8);
+    return d;
+}
+inline int __double2hiint(double d)
+{
+    uint64_t b;
+    std::memcpy(&b, &d, 8);
+    return (int)(b >> 32);
+}
+inline int max(int a, int b) { return a > b ? a : b; }
+inline unsigned max(unsigned a, unsigned b) { return a > b ? a : b; }
+inline int min(int a, int b) { return a < b ? a : b; }
+
+// ---- launchers ---------------------------------------------------------------------------------
+// kernels with barriers / shuffles: one OS thread per CUDA thread, CTAs one after the other
+inline void emu_launch(unsigned grid, unsigned block, const std::function<void()>& kernel)
+{
+    if (block % 32 != 0) { std::fprintf(stderr, "cuda_emu: block size %u\n", block); std::abort(); }
+    for (unsigned b = 0; b < grid; ++b) {
+        EmuCta cta;
+        cta.nthreads = (int)block;
+        pthread_barrier_init(&cta.cta_bar, nullptr, block);
+        cta.warp_bar.resize(block / 32);
+        for (auto& wb : cta.warp_bar) pthread_barrier_init(&wb, nullptr, 32);
+        cta.xchg.assign(block, 0);
+        g_emu_cta = &cta;
+        std::vector<std::thread> th;
+        th.reserve(block);
+        for (unsigned t = 0; t < block; ++t)
+            th.emplace_back([&, t]() {
+                threadIdx.x = t; blockIdx.x = b; blockDim.x = block; gridDim.x = grid;
+                kernel();
+            });
+        for (auto& x : th) x.join();
+        pthread_barrier_destroy(&cta.cta_bar);
+        for (auto& wb : cta.warp_bar) pthread_barrier_destroy(&wb);
+        g_emu_cta = nullptr;
+    }
+}
+// kernels whose threads never talk to each other: a plain loop
+inline void emu_launch_seq(unsigned grid, unsigned block, const std::function<void()>& kernel)
+{
+    for (unsigned b = 0; b < grid; ++b)
+        for (unsigned t = 0; t < block; ++t) {
+            threadIdx.x = t; blockIdx.x = b; blockDim.x = block; gridDim.x = grid;
+            kernel();
+        }
+}
