@@ -1,0 +1,20 @@
+#!/bin/bash
+# The first gpurun call of the next round, in one script (everything below was prepared without GPU time):
+#   /usr/local/graft/bin/gpurun --timeout 1500 -- 'bash tools/round2_first_call.sh'
+# Before calling: python __graft_entry__.py (build), and optionally `bash tools/build_renamed.sh` for step 4.
+# Every step writes its log under gpurun_out/; a failing step does not stop the rest.
+mkdir -p gpurun_out
+echo "== 1. GPU parity tests of the default paths"
+timeout 600 python -m pytest tests -m gpu -x -q > gpurun_out/r02_pytest_gpu.log 2>&1; tail -3 gpurun_out/r02_pytest_gpu.log
+echo "== 2. experimental pair-symmetric paths: parity (tests/test_sym_gpu.py)"
+LPM_EXPERIMENTAL=1 timeout 600 python -m pytest tests/test_sym_gpu.py -m gpu -q > gpurun_out/r02_pytest_sym.log 2>&1; tail -5 gpurun_out/r02_pytest_sym.log
+echo "== 3. default vs symmetric, icosTri 7 and 8, one box"
+timeout 600 python tools/ab_sym.py 7,8 0,200,201 > gpurun_out/r02_ab_sym.log 2>&1; cat gpurun_out/r02_ab_sym.log
+if [ -f build/renamed/lpm_v2_b200/liblpmgpu.so ]; then
+  echo "== 4. register-renamed BVE kernel (tools/build_renamed.sh) against the product build"
+  { timeout 300 python tools/ab_bve.py . 7; timeout 300 python tools/ab_bve.py build/renamed 7; timeout 300 python tools/ab_bve.py . 7; } > gpurun_out/r02_ab_renamed.log 2>&1
+  cat gpurun_out/r02_ab_renamed.log
+fi
+echo "== 5. bench line (default) and with the symmetric velocity sum"
+timeout 600 python bench.py --steps 5 --warmup 3 > gpurun_out/r02_bench_default.json 2> gpurun_out/r02_bench_default.err; tail -c 600 gpurun_out/r02_bench_default.json
+timeout 600 python bench.py --steps 5 --warmup 3 --variant 200 --no-cpu > gpurun_out/r02_bench_sym.json 2> gpurun_out/r02_bench_sym.err; tail -c 600 gpurun_out/r02_bench_sym.json
