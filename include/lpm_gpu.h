@@ -295,7 +295,7 @@ int64_t lpm_launch_count(int reset);
 int lpm_set_profiling(int enable);
 /* Tuning knob for benchmarks: select the BVE kernel variant.  0 = default.
  * 1-99: tilings / statement orders of the one-sided kernel; 102: a shape of the stream-function kernels;
- * 200, 201: EXPERIMENTAL pair-symmetric evaluation of the velocity sum (csrc/symmetric.cuh; opt-in, results
+ * 200-203: EXPERIMENTAL pair-symmetric evaluation of the velocity sum (csrc/symmetric.cuh; opt-in, results
  * reproducible to rounding but not bit for bit; in rank mode every rank must set the same value). */
 int lpm_set_bve_variant(int variant);
 /* Upper bound on the number of source chunks an evaluation is split into (work items = target

@@ -114,6 +114,15 @@ __device__ __forceinline__ void sym_reduce_red(double (&cb)[SB][NC], int lane, d
 //   bits 2-3  sources handled together, phase by phase: 1, 2, 4, SB
 //   bit 4     cb-phase nest (target, component, source) -- P_t stays in the reuse cache -- else
 //             (source, target, component) -- 1/d stays
+//   bit 5     a scheduling fence after every source group (sched_fence below)
+// A never-taken branch on loaded data: it ends the basic block, so ptxas schedules the source groups one
+// after the other instead of interleaving a whole batch (which loses the operand reuse between
+// neighbouring instructions of a phase).  The payload is a signalling-NaN pattern no coordinate carries.
+__device__ __forceinline__ void sched_fence(double v)
+{
+    if (__builtin_expect(__double2hiint(v) == 0x7ff4dead, 0)) __trap();
+}
+
 struct SymBveVel : NoSharedTable {
     static constexpr int NS = 6, NA = 3, NC = 3;
     struct Tgt { double x, y, z, px, py, pz; };
@@ -126,7 +135,7 @@ struct SymBveVel : NoSharedTable {
     __device__ static __forceinline__ void batch(const SymParams& p, const Tgt (&tg)[T], double (&a)[T][NA],
                                                  const double* __restrict__ sm, double (&cb)[SB][NC], const SharedCtx&)
     {
-        constexpr int DN = ORDER & 1, AN = (ORDER >> 1) & 1, GS = (ORDER >> 2) & 3, CU = (ORDER >> 4) & 1;
+        constexpr int DN = ORDER & 1, AN = (ORDER >> 1) & 1, GS = (ORDER >> 2) & 3, CU = (ORDER >> 4) & 1, FENCE = (ORDER >> 5) & 1;
         constexpr int G = GS == 0 ? 1 : GS == 1 ? 2 : GS == 2 ? 4 : SB;
         static_assert(SB % G == 0, "source group");
 #pragma unroll
@@ -211,6 +220,7 @@ struct SymBveVel : NoSharedTable {
                     for (int u = 0; u < G; ++u) cb[g0 + u][2] = fma(r[u][t], tg[t].pz, cb[g0 + u][2]);
                 }
             }
+            if constexpr (FENCE != 0) sched_fence(s[0][0]);
         }
     }
     // as BveVelT::group<T, true>
@@ -251,10 +261,44 @@ struct SymBveStream : LogSharedTable<32> {
     {
         return Tgt{v0.x, v0.y, v1.x, v1.y, v2.x};
     }
+    // ORDER bit 0: retry per source instead of per batch -- a branch after every source's logarithms, which also
+    // keeps ptxas from interleaving the whole batch (see sched_fence)
     template <int T, int SB, int ORDER>
     __device__ static __forceinline__ void batch(const SymParams& p, const Tgt (&tg)[T], double (&a)[T][NA],
                                                  const double* __restrict__ sm, double (&cb)[SB][NC], const SharedCtx& sc)
     {
+        if constexpr ((ORDER & 1) != 0) {
+#pragma unroll
+            for (int u = 0; u < SB; ++u) {
+                const double2* p2 = reinterpret_cast<const double2*>(sm + u * NS);
+                const double2 v0 = p2[0], v1 = p2[1], v2 = p2[2];
+                double d[T], l[T];
+                unsigned worst = 0;
+#pragma unroll
+                for (int t = 0; t < T; ++t) {
+                    d[t] = fma(-tg[t].x, v0.x, p.R2);
+                    d[t] = fma(-tg[t].y, v0.y, d[t]);
+                    d[t] = fma(-tg[t].z, v1.x, d[t]);
+                }
+                log_group_fast<KS, T>(d, l, worst, sc);
+                if (__builtin_expect(needs_retry(worst), 0)) {
+#pragma unroll
+                    for (int t = 0; t < T; ++t) l[t] = log_slow_path(d[t]);
+                }
+#pragma unroll
+                for (int t = 0; t < T; ++t) {
+                    a[t][0] = fma(l[t], v1.y, a[t][0]);
+                    a[t][1] = fma(l[t], v2.x, a[t][1]);
+                }
+                cb[u][0] = l[0] * tg[0].w0; cb[u][1] = l[0] * tg[0].w1;
+#pragma unroll
+                for (int t = 1; t < T; ++t) {
+                    cb[u][0] = fma(l[t], tg[t].w0, cb[u][0]);
+                    cb[u][1] = fma(l[t], tg[t].w1, cb[u][1]);
+                }
+            }
+            return;
+        }
         double w[SB][2], l[SB][T];
         unsigned worst = 0;
 #pragma unroll

@@ -1,4 +1,4 @@
-// symmetric.cuh -- EXPERIMENTAL, opt-in (lpm_set_bve_variant(200)); NOT the default path and not
+// symmetric.cuh -- EXPERIMENTAL, opt-in (lpm_set_bve_variant(200 .. 203)); NOT the default path and not
 // yet measured on a GPU.  Pair-symmetric evaluation of the BVE velocity sum.
 //
 // The reference (src/SphereBVESolver.f90:396-420) visits every ordered pair (i, j): for the
@@ -30,8 +30,13 @@
 
 namespace lpm {
 
-constexpr int kSymVariant = 200;        // lpm_set_bve_variant: symmetric path, 4 targets per thread
-constexpr int kSymVariant8 = 201;       //                      8 targets per thread, batches of 4 sources
+// lpm_set_bve_variant values that select the symmetric paths (shape = variant - 200):
+//   velocity          200: 4 targets per thread, batches of 8 sources, a scheduling fence per source (ORDER 35)
+//                     201: 8 targets per thread, batches of 4, fenced        202 / 203: the same two without fences (ORDER 27)
+//   stream functions  200: 256 threads, retry branch per source (ORDER 1)    201: 128 threads, retry per batch (ORDER 0)
+//                     202: 256 threads, retry per batch                      203: 128 threads, retry per source
+constexpr int kSymVariant = 200;
+constexpr int kSymVariantLast = 203;
 
 template <class K, int T, int BLOCK, int SB, int MINB, int ORDER = 0>
 inline int launch_sym(cudaStream_t st, const SymParams& prm, SymGeom g, const double* src, double* acc)
@@ -61,9 +66,14 @@ struct SymVel {
     using SK = SymBveVel;
     static int launch(int variant, cudaStream_t st, const SymParams& prm, const SymGeom& g, const double* src, double* acc)
     {
-        // statement order 27: the best of the 32 under the operand-delivery model (tools/sym_score.py)
-        if (variant == kSymVariant8) return launch_sym<SK, 8, 128, 4, 1, 27>(st, prm, g, src, acc);
-        return launch_sym<SK, 4, 128, 8, 2, 27>(st, prm, g, src, acc);
+        // orders picked with the operand-delivery model (tools/sym_score.py): modelled 15.9 / 15.1 / 17.1 / 16.7
+        // cycles per interaction per SM sub-partition (the default one-sided kernel: 20.8 modelled, 20.3 measured)
+        switch (variant - kSymVariant) {
+            case 1: return launch_sym<SK, 8, 128, 4, 1, 35>(st, prm, g, src, acc);
+            case 2: return launch_sym<SK, 4, 128, 8, 2, 27>(st, prm, g, src, acc);
+            case 3: return launch_sym<SK, 8, 128, 4, 1, 27>(st, prm, g, src, acc);
+            default: return launch_sym<SK, 4, 128, 8, 2, 35>(st, prm, g, src, acc);
+        }
     }
     static void finalize(cudaStream_t st, const MaskPlan& mp, const double* src, const double* acc, const Outs<3>& out)
     {
@@ -75,10 +85,15 @@ struct SymStream {
     using SK = SymBveStream;
     static int launch(int variant, cudaStream_t st, const SymParams& prm, const SymGeom& g, const double* src, double* acc)
     {
-        // 64 KB table per CTA, so two CTAs per SM either way: 256 threads under a 128-register cap (ptxas spills
-        // 24 bytes) or 128 threads with ~165 registers
-        if (variant == kSymVariant8) return launch_sym<SK, 4, 128, 4, 2>(st, prm, g, src, acc);
-        return launch_sym<SK, 4, 256, 4, 2>(st, prm, g, src, acc);
+        // 64 KB table per CTA, so two CTAs per SM either way: 256 threads under a 128-register cap (121 registers
+        // with the per-source retry; the per-batch retry spills 24 bytes there) or 128 threads with ~155.
+        // Modelled 17.7 / 18.9 / 18.9 / 18.4 cycles per interaction (the one-sided kernel: 29.6 modelled, 32.3 measured).
+        switch (variant - kSymVariant) {
+            case 1: return launch_sym<SK, 4, 128, 4, 2, 0>(st, prm, g, src, acc);
+            case 2: return launch_sym<SK, 4, 256, 4, 2, 0>(st, prm, g, src, acc);
+            case 3: return launch_sym<SK, 4, 128, 4, 2, 1>(st, prm, g, src, acc);
+            default: return launch_sym<SK, 4, 256, 4, 2, 1>(st, prm, g, src, acc);
+        }
     }
     static void finalize(cudaStream_t st, const MaskPlan& mp, const double*, const double* acc, const Outs<2>& out)
     {
@@ -207,7 +222,7 @@ inline int bve_stream_sym(Device& dev, cudaStream_t st, MaskPlan& mp, const Args
 inline bool sym_applicable(int variant, int64_t tbeg, int64_t tend, int64_t nt, const MaskPlan& mp, int nrep)
 {
     const Runtime& R = rt();
-    if ((variant != kSymVariant && variant != kSymVariant8) || nt != mp.n || nrep != 1 || R.devs.size() != 1) return false;
+    if (variant < kSymVariant || variant > kSymVariantLast || nt != mp.n || nrep != 1 || R.devs.size() != 1) return false;
     int64_t b = 0, e = nt;
     if (R.rank_mode && R.world > 1) load_balance0(nt, R.world, R.rank, &b, &e);
     return tbeg == b && tend == e;

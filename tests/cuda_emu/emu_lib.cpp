@@ -77,7 +77,7 @@ void run_one_sided(typename K::Params prm, int64_t nv, int32_t nsrc, int32_t nsr
 
 }  // namespace
 
-// shape: 0 -> T = 4, batches of 8 (variant 200); 1 -> T = 8, batches of 4 (variant 201)
+// shape = lpm_set_bve_variant value - 200 (csrc/symmetric.cuh)
 extern "C" __attribute__((visibility("default"))) int emu_sym_bve_velocity(int64_t n, const double* x, const double* y, const double* z, const double* zeta,
                                     const double* area, const int32_t* mask, double R, int shape, int chunk_tiles,
                                     int world, double* u, double* v, double* w)
@@ -101,8 +101,12 @@ extern "C" __attribute__((visibility("default"))) int emu_sym_bve_velocity(int64
     out.p[0][0] = u; out.p[0][1] = v; out.p[0][2] = w;
     if (nsrc > 0) {
         std::vector<double> acc((size_t)pad * 3, 0.0);
-        if (shape == 1) run_sym<SymBveVel, 8, 128, 4, 27>(prm, g, src.data(), acc.data());
-        else run_sym<SymBveVel, 4, 128, 8, 27>(prm, g, src.data(), acc.data());
+        switch (shape) {        // as SymVel::launch in csrc/symmetric.cuh
+            case 1: run_sym<SymBveVel, 8, 128, 4, 35>(prm, g, src.data(), acc.data()); break;
+            case 2: run_sym<SymBveVel, 4, 128, 8, 27>(prm, g, src.data(), acc.data()); break;
+            case 3: run_sym<SymBveVel, 8, 128, 4, 27>(prm, g, src.data(), acc.data()); break;
+            default: run_sym<SymBveVel, 4, 128, 8, 35>(prm, g, src.data(), acc.data()); break;
+        }
         emu_launch_seq((unsigned)((nsrc + 255) / 256), 256,
                        [&]() { sym_bve_finalize(nsrc, pl.active.data(), src.data(), acc.data(), out); });
     }
@@ -121,7 +125,7 @@ extern "C" __attribute__((visibility("default"))) int emu_sym_bve_velocity(int64
     return 0;
 }
 
-// shape: 0 -> 256 threads (variant 200); 1 -> 128 threads (variant 201)
+// shape = lpm_set_bve_variant value - 200
 extern "C" __attribute__((visibility("default"))) int emu_sym_bve_stream(int64_t n, const double* x, const double* y, const double* z, const double* zeta,
                                   const double* omega, const double* area, const int32_t* mask, double R, int shape,
                                   int chunk_tiles, int world, double* rel, double* abs_)
@@ -150,8 +154,12 @@ extern "C" __attribute__((visibility("default"))) int emu_sym_bve_stream(int64_t
     out.p[0][0] = rel; out.p[0][1] = abs_;
     if (nsrc > 0) {
         std::vector<double> acc((size_t)pad * 2, 0.0);
-        if (shape == 1) run_sym<SymBveStream, 4, 128, 4, 0>(prm, g, src.data(), acc.data());
-        else run_sym<SymBveStream, 4, 256, 4, 0>(prm, g, src.data(), acc.data());
+        switch (shape) {        // as SymStream::launch in csrc/symmetric.cuh
+            case 1: run_sym<SymBveStream, 4, 128, 4, 0>(prm, g, src.data(), acc.data()); break;
+            case 2: run_sym<SymBveStream, 4, 256, 4, 0>(prm, g, src.data(), acc.data()); break;
+            case 3: run_sym<SymBveStream, 4, 128, 4, 1>(prm, g, src.data(), acc.data()); break;
+            default: run_sym<SymBveStream, 4, 256, 4, 1>(prm, g, src.data(), acc.data()); break;
+        }
         emu_launch_seq((unsigned)((nsrc + 255) / 256), 256,
                        [&]() { sym_stream_finalize(nsrc, pl.active.data(), acc.data(), out); });
     }

@@ -1,4 +1,4 @@
-"""GPU parity of the EXPERIMENTAL pair-symmetric BVE velocity path (lpm_set_bve_variant(200 / 201),
+"""GPU parity of the EXPERIMENTAL pair-symmetric BVE velocity path (lpm_set_bve_variant(200 .. 203),
 lpm_v2_b200/csrc/symmetric.cuh).
 
 The path was written at the end of round 1 without GPU time left, so it has not run yet: these tests
@@ -40,7 +40,7 @@ def sym(gpu, request):
     gpu.set_bve_variant(0)
 
 
-@pytest.mark.parametrize("sym", [200, 201], indirect=True)
+@pytest.mark.parametrize("sym", [200, 201, 202, 203], indirect=True)
 @pytest.mark.parametrize("seed,L", [(M.ICOS_TRI_SPHERE_SEED, 2), (M.ICOS_TRI_SPHERE_SEED, 5), (M.CUBED_SPHERE_SEED, 5),
                                     (M.ICOS_TRI_SPHERE_SEED, 6)])
 def test_sym_bve_velocity_meshes(sym, oracle, get_mesh, seed, L):
@@ -52,7 +52,7 @@ def test_sym_bve_velocity_meshes(sym, oracle, get_mesh, seed, L):
     assert max(np.abs(g - w).max() for g, w in zip(got, want)) <= TOL * scale
 
 
-@pytest.mark.parametrize("sym", [200, 201], indirect=True)
+@pytest.mark.parametrize("sym", [200, 201, 202, 203], indirect=True)
 @pytest.mark.parametrize("n,frac,seed", [(1, 1.0, 1), (2, 1.0, 2), (3, 0.5, 3), (127, 0.3, 4), (513, 0.9, 5),
                                          (1025, 0.05, 6), (4099, 0.6, 12345), (20011, 0.55, 7), (20011, 1.0, 8),
                                          (3000, 0.0, 9)])
@@ -68,7 +68,7 @@ def test_sym_bve_velocity_random_ragged(sym, oracle, n, frac, seed):
     _check(got, want, ld)
 
 
-@pytest.mark.parametrize("sym", [200, 201], indirect=True)
+@pytest.mark.parametrize("sym", [200, 201, 202, 203], indirect=True)
 @pytest.mark.parametrize("seed,L", [(M.ICOS_TRI_SPHERE_SEED, 2), (M.ICOS_TRI_SPHERE_SEED, 5), (M.CUBED_SPHERE_SEED, 5)])
 def test_sym_bve_stream_meshes(sym, oracle, get_mesh, seed, L):
     m = get_mesh(seed, L)
@@ -80,7 +80,7 @@ def test_sym_bve_stream_meshes(sym, oracle, get_mesh, seed, L):
         assert relerr(g, w) <= TOL
 
 
-@pytest.mark.parametrize("sym", [200, 201], indirect=True)
+@pytest.mark.parametrize("sym", [200, 201, 202, 203], indirect=True)
 @pytest.mark.parametrize("n,frac,seed,R", [(3, 0.5, 3, 1.0), (513, 0.9, 5, 1.0), (4099, 0.6, 12345, 1.7),
                                            (20011, 0.55, 7, 6.371e6), (6000, 1.0, 8, 3.0e-7), (3000, 0.0, 9, 1.0)])
 def test_sym_bve_stream_random_ragged(sym, oracle, n, frac, seed, R):

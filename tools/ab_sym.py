@@ -1,5 +1,5 @@
 """A/B on one box (run under gpurun): the default BVE velocity / stream-function paths against the EXPERIMENTAL pair-symmetric ones
-(lpm_set_bve_variant(200 / 201), csrc/symmetric.cuh) at icosTri levels argv[1] (default "6,7").
+(lpm_set_bve_variant(200 .. 203), csrc/symmetric.cuh) at icosTri levels argv[1] (default "6,7").
 Prints, per variant, the whole-sum time (pack, kernels, finalize / gather / scatter), the interactions/s, and the
 largest difference from the default path's result relative to the field scale.
     python tools/ab_sym.py 7,8"""
@@ -9,7 +9,7 @@ import numpy as np
 from lpm_v2_b200 import api, mesh, problems
 
 levels = [int(a) for a in sys.argv[1].split(",")] if len(sys.argv) > 1 else [6, 7]
-variants = [int(a) for a in sys.argv[2].split(",")] if len(sys.argv) > 2 else [0, 200, 201]
+variants = [int(a) for a in sys.argv[2].split(",")] if len(sys.argv) > 2 else [0, 200, 201, 202, 203]
 api.init(1)
 api.set_profiling(True)
 for L in levels:
