@@ -15,6 +15,9 @@ if [ -f build/renamed/lpm_v2_b200/liblpmgpu.so ]; then
   { timeout 300 python tools/ab_bve.py . 7; timeout 300 python tools/ab_bve.py build/renamed 7; timeout 300 python tools/ab_bve.py . 7; } > gpurun_out/r02_ab_renamed.log 2>&1
   cat gpurun_out/r02_ab_renamed.log
 fi
+echo "== 4b. ncu of the symmetric velocity kernel at icosTri 6 (stall reasons, FP64 pipe, L2 atomics); read with ncu -i ... --page raw --csv"
+timeout 600 ncu --set full --clock-control none --import-source on -k regex:sym_kernel -c 1 -f -o gpurun_out/r02_sym_vel_L6 \
+    python tools/profile_bve.py 6 1 201 > gpurun_out/r02_ncu_sym.log 2>&1; tail -2 gpurun_out/r02_ncu_sym.log
 echo "== 5. bench line (default) and with the symmetric velocity sum"
 timeout 600 python bench.py --steps 5 --warmup 3 > gpurun_out/r02_bench_default.json 2> gpurun_out/r02_bench_default.err; tail -c 600 gpurun_out/r02_bench_default.json
 timeout 600 python bench.py --steps 5 --warmup 3 --variant 200 --no-cpu > gpurun_out/r02_bench_sym.json 2> gpurun_out/r02_bench_sym.err; tail -c 600 gpurun_out/r02_bench_sym.json
