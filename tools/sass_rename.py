@@ -99,18 +99,32 @@ def find_fields(blob, text_off, kernel, base, tmp):
 
 
 def hot_loop(ins):
+    """Indices of the backward-branch loop with the most FP64 instructions; loops inside it are tolerated
+    (and left out) when they hold < 25 % of its FP64 instructions -- a slow path -- as in tools/sass_banks.py."""
+    def opname(text):
+        return text.lstrip('@!UP0123456789 ').split()[0]
+    def target(j):
+        a, text = ins[j]
+        if not opname(text).startswith('BRA'):
+            return None
+        m = re.search(r'0x([0-9a-f]+)', text)
+        return int(m.group(1), 16) if m else None
+    fp = lambda body: sum(opname(ins[j][1]).startswith(('DFMA', 'DMUL', 'DADD')) for j in body)
     best = None
     for idx, (a, text) in enumerate(ins):
-        if text.split()[0].startswith('BRA') or (text.startswith('@') and 'BRA' in text.split()[1]):
-            m = re.search(r'0x([0-9a-f]+)', text)
-            if m and int(m.group(1), 16) < a:
-                t = int(m.group(1), 16)
-                body = [j for j, (aa, _) in enumerate(ins) if t <= aa <= a]
-                if sum('BRA' in ins[j][1] for j in body) > 1:
-                    continue
-                n = sum(ins[j][1].lstrip('@!UP0123456789 ').startswith(('DFMA', 'DMUL', 'DADD')) for j in body)
-                if best is None or n > best[0]:
-                    best = (n, body)
+        t = target(idx)
+        if t is None or t >= a:
+            continue
+        body = [j for j, (aa, _) in enumerate(ins) if t <= aa <= a]
+        inner = [(target(j), ins[j][0]) for j in body[:-1] if target(j) is not None and target(j) < ins[j][0]]
+        if inner:
+            cut = [j for j in body if any(lo <= ins[j][0] <= hi for lo, hi in inner)]
+            if fp(cut) >= 0.25 * fp(body):
+                continue
+            body = [j for j in body if j not in cut]
+        n = fp(body)
+        if best is None or n > best[0]:
+            best = (n, body)
     return best[1]
 
 
