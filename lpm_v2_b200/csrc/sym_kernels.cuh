@@ -127,8 +127,9 @@ struct SymBveVel : NoSharedTable {
     static constexpr int NS = 6, NA = 3, NC = 3;
     struct Tgt { double x, y, z, px, py, pz; };
     __device__ static __forceinline__ Tgt null() { return Tgt{0.0, 0.0, 0.0, 0.0, 0.0, 0.0}; }
-    __device__ static __forceinline__ Tgt from_record(const double2 v0, const double2 v1, const double2 v2)
+    __device__ static __forceinline__ Tgt from_record(const double2* p2)
     {
+        const double2 v0 = p2[0], v1 = p2[1], v2 = p2[2];
         return Tgt{v0.x, v0.y, v1.x, v1.y, v2.x, v2.y};
     }
     template <int T, int SB, int ORDER>
@@ -257,8 +258,9 @@ struct SymBveStream : LogSharedTable<32> {
     static constexpr int NS = 6, NA = 2, NC = 2;
     struct Tgt { double x, y, z, w0, w1; };
     __device__ static __forceinline__ Tgt null() { return Tgt{0.0, 0.0, 0.0, 0.0, 0.0}; }
-    __device__ static __forceinline__ Tgt from_record(const double2 v0, const double2 v1, const double2 v2)
+    __device__ static __forceinline__ Tgt from_record(const double2* p2)
     {
+        const double2 v0 = p2[0], v1 = p2[1], v2 = p2[2];
         return Tgt{v0.x, v0.y, v1.x, v1.y, v2.x};
     }
     // ORDER bit 0: retry per source instead of per batch -- a branch after every source's logarithms, which also
@@ -370,6 +372,79 @@ struct SymBveStream : LogSharedTable<32> {
     }
 };
 
+// Planar Biot-Savart (PlaneVel in pairs.cuh): u_i -= dy s_j / r^2, v_i += dx s_j / r^2 with dx = x_i - x_j,
+// dy = y_i - y_j, s_j = omega_j A_j / (2 pi); record x, y, s, 0.  The pair shares dx, dy, r^2 and 1 / r^2:
+// 2 + 2 + 3 + (1 + 2) + (1 + 2) = 13 FP64 instructions for two interactions instead of 20.  The transposed
+// direction sees -dx, -dy:  u_j += dy s_i / r^2,  v_j -= dx s_i / r^2.
+// Null SOURCE records sit at (+1e37, +1e37) (pack_plane); a null TARGET is put at (-1e37, -1e37), so that no pair
+// has r^2 = 0 -- a zero would poison the reciprocal the four targets of a thread share.
+//   ORDER bit 0: a scheduling fence after every source (sched_fence)
+struct SymPlaneVel : NoSharedTable {
+    static constexpr int NS = 4, NA = 2, NC = 2;
+    struct Tgt { double x, y, s; };
+    __device__ static __forceinline__ Tgt null() { return Tgt{-LPM_PLANE_FAR, -LPM_PLANE_FAR, 0.0}; }
+    __device__ static __forceinline__ Tgt from_record(const double2* p2)
+    {
+        const double2 v0 = p2[0], v1 = p2[1];
+        return Tgt{v0.x, v0.y, v1.x};
+    }
+    template <int T, int SB, int ORDER>
+    __device__ static __forceinline__ void batch(const SymParams&, const Tgt (&tg)[T], double (&a)[T][NA],
+                                                 const double* __restrict__ sm, double (&cb)[SB][NC], const SharedCtx&)
+    {
+#pragma unroll
+        for (int u = 0; u < SB; ++u) {
+            const double2* p2 = reinterpret_cast<const double2*>(sm + u * NS);
+            const double2 v0 = p2[0], v1 = p2[1];
+            double dx[T], dy[T], r2[T], r[T];
+#pragma unroll
+            for (int t = 0; t < T; ++t) {
+                dx[t] = tg[t].x - v0.x; dy[t] = tg[t].y - v0.y;
+                r2[t] = fma(dx[t], dx[t], dy[t] * dy[t]);
+            }
+            rcp_batch<T>(r2, r);
+#pragma unroll
+            for (int t = 0; t < T; ++t) {
+                const double w = r[t] * v1.x;
+                a[t][0] = fma(-dy[t], w, a[t][0]);
+                a[t][1] = fma(dx[t], w, a[t][1]);
+            }
+            {
+                const double w = r[0] * tg[0].s;
+                cb[u][0] = dy[0] * w; cb[u][1] = -dx[0] * w;
+            }
+#pragma unroll
+            for (int t = 1; t < T; ++t) {
+                const double w = r[t] * tg[t].s;
+                cb[u][0] = fma(dy[t], w, cb[u][0]);
+                cb[u][1] = fma(-dx[t], w, cb[u][1]);
+            }
+            if constexpr ((ORDER & 1) != 0) sched_fence(v0.x);
+        }
+    }
+    // as PlaneVel::group<T, true>
+    template <int T>
+    __device__ static __forceinline__ void diag(const SymParams&, const Tgt (&tg)[T], double (&a)[T][NA],
+                                                const double (&s)[NS], const bool (&isself)[T], const SharedCtx&)
+    {
+        double dx[T], dy[T], r2[T], r[T];
+#pragma unroll
+        for (int t = 0; t < T; ++t) {
+            dx[t] = tg[t].x - s[0]; dy[t] = tg[t].y - s[1];
+            r2[t] = fma(dx[t], dx[t], dy[t] * dy[t]);
+            r2[t] = isself[t] ? 1.0 : r2[t];
+        }
+        rcp_batch<T>(r2, r);
+#pragma unroll
+        for (int t = 0; t < T; ++t) {
+            double w = r[t] * s[2];
+            w = isself[t] ? 0.0 : w;
+            a[t][0] = fma(-dy[t], w, a[t][0]);
+            a[t][1] = fma(dx[t], w, a[t][1]);
+        }
+    }
+};
+
 // ---- the kernel ---------------------------------------------------------------
 // acc: [nsrc_pad][NC] doubles, zeroed by the caller (NA == NC: both directions feed the same sums).
 // dynamic shared memory: [2 tiles][K::KS table][2 mbarriers]
@@ -378,7 +453,7 @@ __global__ void __launch_bounds__(BLOCK, MINB)
 sym_kernel(const SymParams prm, const SymGeom g, const double* __restrict__ src, double* __restrict__ acc)
 {
     constexpr int NS = K::NS, NA = K::NA, NC = K::NC, TS = kTile, TB = BLOCK * T, DT = TB / TS;
-    static_assert(NS == 6, "records are three double2");
+    static_assert(NS % 2 == 0, "records are read as double2");
     static_assert(NA == NC, "one accumulator array for both directions");
     static_assert(TB % TS == 0, "a target block must be whole source tiles");
     static_assert(TS % SB == 0, "source batch");
@@ -405,11 +480,9 @@ sym_kernel(const SymParams prm, const SymGeom g, const double* __restrict__ src,
     for (int t = 0; t < T; ++t) {
         const int32_t c = I * TB + t * BLOCK + tid;
         cidx[t] = c;
-        tg[t] = K::null();                           // past the padded list: a null particle
-        if (c < g.nsrc_pad) {
-            const double2* p2 = reinterpret_cast<const double2*>(src + (size_t)c * NS);
-            tg[t] = K::from_record(p2[0], p2[1], p2[2]);
-        }
+        tg[t] = K::null();                           // past the active list: a null TARGET (K::null() never coincides
+        if (c < g.nsrc)                              // with a null source record, see SymPlaneVel)
+            tg[t] = K::from_record(reinterpret_cast<const double2*>(src + (size_t)c * NS));
 #pragma unroll
         for (int q = 0; q < NA; ++q) a[t][q] = 0.0;
     }
@@ -499,7 +572,7 @@ sym_bve_finalize(int32_t nsrc, const int32_t* __restrict__ active, const double*
     out.store(2, i, fma(x, a1, -(y * a0)));
 }
 
-// the two stream functions of the active particles (BveStream::finalize)
+// two sums per active particle, copied out (BveStream::finalize, PlaneVel::finalize)
 __global__ void __launch_bounds__(256)
 sym_stream_finalize(int32_t nsrc, const int32_t* __restrict__ active, const double* __restrict__ acc, Outs<2> out)
 {

@@ -64,6 +64,13 @@ inline int launch_sym(cudaStream_t st, const SymParams& prm, SymGeom g, const do
 struct SymVel {
     using Op = OpBveVel;
     using SK = SymBveVel;
+    static constexpr int NCOORD = 3;
+    static void sym_params(SymParams& p, const Args& a) { p.R2 = a.sc[0] * a.sc[0]; }
+    static void passive_params(BveVel::Params& p, const double* const* xyz, const Args& a)
+    {
+        p.x = xyz[0]; p.y = xyz[1]; p.z = xyz[2];
+        p.R2 = a.sc[0] * a.sc[0];
+    }
     static int launch(int variant, cudaStream_t st, const SymParams& prm, const SymGeom& g, const double* src, double* acc)
     {
         // orders picked with the operand-delivery model (tools/sym_score.py): modelled 15.9 / 15.1 / 17.1 / 16.7
@@ -83,6 +90,13 @@ struct SymVel {
 struct SymStream {
     using Op = OpBveStream;
     using SK = SymBveStream;
+    static constexpr int NCOORD = 3;
+    static void sym_params(SymParams& p, const Args& a) { p.R2 = a.sc[0] * a.sc[0]; }
+    static void passive_params(BveStream::Params& p, const double* const* xyz, const Args& a)
+    {
+        p.x = xyz[0]; p.y = xyz[1]; p.z = xyz[2];
+        p.R2 = a.sc[0] * a.sc[0];
+    }
     static int launch(int variant, cudaStream_t st, const SymParams& prm, const SymGeom& g, const double* src, double* acc)
     {
         // 64 KB table per CTA, so two CTAs per SM either way: 256 threads under a 128-register cap (121 registers
@@ -93,6 +107,28 @@ struct SymStream {
             case 2: return launch_sym<SK, 4, 256, 4, 2, 0>(st, prm, g, src, acc);
             case 3: return launch_sym<SK, 4, 128, 4, 2, 1>(st, prm, g, src, acc);
             default: return launch_sym<SK, 4, 256, 4, 2, 1>(st, prm, g, src, acc);
+        }
+    }
+    static void finalize(cudaStream_t st, const MaskPlan& mp, const double*, const double* acc, const Outs<2>& out)
+    {
+        sym_stream_finalize<<<(unsigned)((mp.nsrc + 255) / 256), 256, 0, st>>>(mp.nsrc, mp.active.as<int32_t>(), acc, out);
+    }
+};
+
+// Planar Biot-Savart (variants as for the BVE velocity: 200 / 201 fenced, 202 / 203 not)
+struct SymPlane {
+    using Op = OpPlaneVel;
+    using SK = SymPlaneVel;
+    static constexpr int NCOORD = 2;
+    static void sym_params(SymParams&, const Args&) {}
+    static void passive_params(PlaneVel::Params& p, const double* const* xy, const Args&) { p.x = xy[0]; p.y = xy[1]; }
+    static int launch(int variant, cudaStream_t st, const SymParams& prm, const SymGeom& g, const double* src, double* acc)
+    {
+        switch (variant - kSymVariant) {
+            case 1: return launch_sym<SK, 8, 128, 4, 1, 1>(st, prm, g, src, acc);
+            case 2: return launch_sym<SK, 4, 128, 8, 2, 0>(st, prm, g, src, acc);
+            case 3: return launch_sym<SK, 8, 128, 4, 1, 0>(st, prm, g, src, acc);
+            default: return launch_sym<SK, 4, 128, 8, 2, 1>(st, prm, g, src, acc);
         }
     }
     static void finalize(cudaStream_t st, const MaskPlan& mp, const double*, const double* acc, const Outs<2>& out)
@@ -115,7 +151,7 @@ inline int sym_evaluate(Device& dev, cudaStream_t st, MaskPlan& mp, const Args& 
     using K = typename Op::K;
     using SK = typename S::SK;
     constexpr int NOUT = Op::NOUT;
-    static_assert(SK::NC == NOUT && K::NS == SK::NS, "the symmetric functor reads the one-sided kernel's records");
+    static_assert(SK::NC == NOUT && (int)K::NS == (int)SK::NS, "the symmetric functor reads the one-sided kernel's records");
     Runtime& R = rt();
     Workspace& ws = dev.ws;
     const bool prof = R.profiling;
@@ -137,7 +173,7 @@ inline int sym_evaluate(Device& dev, cudaStream_t st, MaskPlan& mp, const Args& 
         g.world = R.rank_mode ? R.world : 1;
         g.rank = R.rank_mode ? R.rank : 0;
         SymParams prm{};
-        prm.R2 = a.sc[0] * a.sc[0];
+        S::sym_params(prm, a);
         if constexpr (SK::KS > 0) {
             prm.logtab = dev.logtab;
             prm.win = ws.logwin.as<int32_t>() + 1;
@@ -164,14 +200,15 @@ inline int sym_evaluate(Device& dev, cudaStream_t st, MaskPlan& mp, const Args& 
             LPM_TRY(ws.sort_vals[0].reserve((size_t)(nv + 1) * sizeof(int32_t)));       // "scan" of a list with no source in it
             LPM_CUDA(cudaMemsetAsync(ws.sort_vals[0].p, 0, (size_t)(nv + 1) * sizeof(int32_t), st));
             const unsigned gb = (unsigned)((nv + 255) / 256);
-            for (int k = 0; k < 3; ++k) {
+            const double* coords[3] = {nullptr, nullptr, nullptr};
+            for (int k = 0; k < S::NCOORD; ++k) {       // the coordinates are the first NCOORD input arrays of every Op here
                 LPM_TRY(ws.gathered[k].reserve((size_t)nv * sizeof(double)));
                 gather_kernel<<<gb, 256, 0, st>>>(nv, perm, a.in[k], ws.gathered[k].as<double>());
+                coords[k] = ws.gathered[k].as<double>();
             }
-            count_launch(4);
+            count_launch(1 + S::NCOORD);
             typename K::Params prm1{};
-            prm1.x = ws.gathered[0].as<double>(); prm1.y = ws.gathered[1].as<double>(); prm1.z = ws.gathered[2].as<double>();
-            prm1.R2 = prm.R2;
+            S::passive_params(prm1, coords, a);
             prm1.out.nrep = 1;
             double* bufs[NOUT];
             for (int k = 0; k < NOUT; ++k) {
@@ -215,6 +252,10 @@ inline int bve_velocity_sym(Device& dev, cudaStream_t st, MaskPlan& mp, const Ar
 inline int bve_stream_sym(Device& dev, cudaStream_t st, MaskPlan& mp, const Args& a, const Outs<2>& out, int variant)
 {
     return sym_evaluate<SymStream>(dev, st, mp, a, out, variant);
+}
+inline int plane_velocity_sym(Device& dev, cudaStream_t st, MaskPlan& mp, const Args& a, const Outs<2>& out, int variant)
+{
+    return sym_evaluate<SymPlane>(dev, st, mp, a, out, variant);
 }
 
 // May this evaluation take the symmetric path?  One device driving every target, or rank mode with this

@@ -206,3 +206,50 @@ extern "C" __attribute__((visibility("default"))) int emu_default_bve_velocity(i
     emu_launch((unsigned)g.ntblocks, BLOCK, [&]() { ds_kernel<BveVel, T, BLOCK, 2, 1>(p1, g, src.data(), pl.scan.data(), nullptr); });
     return 0;
 }
+
+// shape = lpm_set_bve_variant value - 200 (SymPlane::launch in csrc/symmetric.cuh)
+extern "C" __attribute__((visibility("default"))) int emu_sym_plane_velocity(int64_t n, const double* x, const double* y, const double* vort,
+                                      const double* area, const int32_t* mask, int shape, int chunk_tiles, int world,
+                                      double* u, double* v)
+{
+    Plan pl = make_plan(n, mask);
+    const int32_t nsrc = (int32_t)pl.active.size();
+    int32_t pad = (nsrc + kTile - 1) / kTile * kTile;
+    if (pad == 0) pad = kTile;
+    std::vector<double> src((size_t)pad * 4);
+    const double inv_norm = 1.0 / (2.0 * LPM_PI);
+    emu_launch_seq((unsigned)((pad + 255) / 256), 256,
+                   [&]() { pack_plane(nsrc, pad, pl.active.data(), x, y, vort, area, inv_norm, src.data()); });
+    SymGeom g{};
+    g.nsrc = nsrc; g.nsrc_pad = pad; g.ntiles = pad / kTile;
+    g.chunk_tiles = chunk_tiles;
+    g.nchunks = (g.ntiles + chunk_tiles - 1) / chunk_tiles;
+    g.world = world;
+    SymParams prm{};
+    Outs<2> out{};
+    out.nrep = 1;
+    out.p[0][0] = u; out.p[0][1] = v;
+    if (nsrc > 0) {
+        std::vector<double> acc((size_t)pad * 2, 0.0);
+        switch (shape) {
+            case 1: run_sym<SymPlaneVel, 8, 128, 4, 1>(prm, g, src.data(), acc.data()); break;
+            case 2: run_sym<SymPlaneVel, 4, 128, 8, 0>(prm, g, src.data(), acc.data()); break;
+            case 3: run_sym<SymPlaneVel, 8, 128, 4, 0>(prm, g, src.data(), acc.data()); break;
+            default: run_sym<SymPlaneVel, 4, 128, 8, 1>(prm, g, src.data(), acc.data()); break;
+        }
+        emu_launch_seq((unsigned)((nsrc + 255) / 256), 256,
+                       [&]() { sym_stream_finalize(nsrc, pl.active.data(), acc.data(), out); });
+    }
+    const int64_t nv = n - nsrc;
+    if (nv > 0) {
+        std::vector<double> gx(nv), gy(nv), o0(nv), o1(nv);
+        for (int64_t c = 0; c < nv; ++c) { gx[c] = x[pl.passive[c]]; gy[c] = y[pl.passive[c]]; }
+        PlaneVel::Params p1{};
+        p1.x = gx.data(); p1.y = gy.data();
+        p1.out.nrep = 1;
+        p1.out.p[0][0] = o0.data(); p1.out.p[0][1] = o1.data();
+        run_one_sided<PlaneVel, 4, 128, 1>(p1, nv, nsrc, pad, src.data());
+        for (int64_t c = 0; c < nv; ++c) { u[pl.passive[c]] = o0[c]; v[pl.passive[c]] = o1[c]; }
+    }
+    return 0;
+}

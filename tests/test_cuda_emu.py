@@ -42,6 +42,7 @@ def emu():
     i32 = np.ctypeslib.ndpointer(np.int32, flags="C")
     lib.emu_sym_bve_velocity.argtypes = [C.c_int64, d, d, d, d, d, i32, C.c_double, C.c_int, C.c_int, C.c_int, d, d, d]
     lib.emu_default_bve_velocity.argtypes = [C.c_int64, d, d, d, d, d, i32, C.c_double, d, d, d]
+    lib.emu_sym_plane_velocity.argtypes = [C.c_int64, d, d, d, d, i32, C.c_int, C.c_int, C.c_int, d, d]
     lib.emu_sym_bve_stream.argtypes = [C.c_int64, d, d, d, d, d, d, i32, C.c_double, C.c_int, C.c_int, C.c_int, d, d]
     return lib
 
@@ -106,4 +107,34 @@ def test_emulated_symmetric_stream(emu, oracle, n, frac, R, shape, chunk_tiles, 
     assert emu.emu_sym_bve_stream(n, x, y, z, zeta, av, area, mask, R, shape, chunk_tiles, world, *got) == 0
     want = oracle.bve_stream(x, y, z, zeta, av, area, mask, R)
     ld = oracle.bve_stream(x, y, z, zeta, av, area, mask, R, variant="_ld")
+    _check(got, want, ld)
+
+
+def _rand_plane(n, seed, frac):
+    """Jittered lattice in [-7, 7]^2 (order shuffled), random mask and vorticity (as tests/test_parity_gpu.py)."""
+    rng = np.random.default_rng(seed)
+    m = int(np.ceil(np.sqrt(n)))
+    gx, gy = np.meshgrid(np.arange(m), np.arange(m))
+    p = np.stack([gx.ravel(), gy.ravel()]).astype(np.float64)[:, :n]
+    h = 14.0 / m
+    p = -7.0 + h * (p + 0.5) + 0.2 * h * rng.normal(size=(2, n))
+    p = p[:, rng.permutation(n)]
+    mask = (rng.random(n) < frac).astype(np.int32)
+    area = np.where(mask != 0, h * h, 0.0)
+    vort = rng.uniform(-1.0, 1.0, n)
+    return p[0].copy(), p[1].copy(), vort, area, mask
+
+
+@pytest.mark.parametrize("n,frac,shape,chunk_tiles,world", [
+    (2500, 0.5, 0, 2, 1),       # quadRect-like: half of the particles active; ragged last block and tile
+    (2100, 1.0, 1, 3, 2),
+    (1500, 0.7, 2, 1, 1),
+    (1500, 0.7, 3, 5, 3),
+])
+def test_emulated_symmetric_plane_velocity(emu, oracle, n, frac, shape, chunk_tiles, world):
+    x, y, vort, area, mask = _rand_plane(n, 3, frac)
+    got = [np.full(n, np.nan) for _ in range(2)]
+    assert emu.emu_sym_plane_velocity(n, x, y, vort, area, mask, shape, chunk_tiles, world, *got) == 0
+    want = oracle.plane_velocity(x, y, vort, area, mask)
+    ld = oracle.plane_velocity(x, y, vort, area, mask, variant="_ld")
     _check(got, want, ld)

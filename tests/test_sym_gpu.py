@@ -94,6 +94,29 @@ def test_sym_bve_stream_random_ragged(sym, oracle, n, frac, seed, R):
     _check(got, want, ld)
 
 
+@pytest.mark.parametrize("sym", [200, 201, 202, 203], indirect=True)
+@pytest.mark.parametrize("L", [3, 5])
+def test_sym_plane_velocity_mesh(sym, oracle, get_mesh, L):
+    """Config 2 (colliding dipoles on quadRect): the planar Biot-Savart sum through the symmetric path."""
+    q = get_mesh(M.QUAD_RECT_SEED, L, 7.0)
+    vort = problems.colliding_dipoles(q)
+    got = sym.plane_velocity(q.x, q.y, vort, q.area, q.is_active)
+    want = oracle.plane_velocity(q.x, q.y, vort, q.area, q.is_active)
+    ld = oracle.plane_velocity(q.x, q.y, vort, q.area, q.is_active, variant="_ld")
+    _check(got, want, ld)
+
+
+@pytest.mark.parametrize("sym", [200, 201], indirect=True)
+@pytest.mark.parametrize("n,frac,seed", [(2, 1.0, 2), (513, 0.9, 5), (4099, 0.6, 12345), (20011, 0.5, 7), (3000, 0.0, 9)])
+def test_sym_plane_velocity_random_ragged(sym, oracle, n, frac, seed):
+    from test_cuda_emu import _rand_plane
+    x, y, vort, area, mask = _rand_plane(n, seed, frac)
+    got = sym.plane_velocity(x, y, vort, area, mask)
+    want = oracle.plane_velocity(x, y, vort, area, mask)
+    ld = oracle.plane_velocity(x, y, vort, area, mask, variant="_ld")
+    _check(got, want, ld)
+
+
 @pytest.mark.parametrize("sym", [200], indirect=True)
 def test_sym_matches_default_path(sym, get_mesh):
     """Same sum, other order: within a few ulp of the default kernel at icosTri 6."""

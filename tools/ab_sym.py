@@ -32,4 +32,21 @@ for L in levels:
             diff = max(np.abs(a - b).max() for a, b in zip(out, ref)) / scale
             print(f"L{L} {name} variant {var}: sum ms " + " ".join(f"{t:.3f}" for t in ts) +
                   f"  -> {pairs / min(ts) / 1e9:.1f} G interactions/s, max diff from variant {variants[0]}: {diff:.2e}", flush=True)
+for L in levels:
+    q = mesh.PolyMesh2d(mesh.QUAD_RECT_SEED, L + 1, 7.0)
+    vort = problems.colliding_dipoles(q)
+    pairs = q.n * q.n_active - q.n_active
+    ref = None
+    for var in variants:
+        api.set_bve_variant(var)
+        ts = []
+        for _ in range(3):
+            out = api.plane_velocity(q.x, q.y, vort, q.area, q.is_active)
+            ts.append(api.last_sum_ms())
+        if ref is None:
+            ref = out
+        scale = max(np.abs(r).max() for r in ref)
+        diff = max(np.abs(a - b).max() for a, b in zip(out, ref)) / scale
+        print(f"quadRect L{L + 1} plane_velocity variant {var}: sum ms " + " ".join(f"{t:.3f}" for t in ts) +
+              f"  -> {pairs / min(ts) / 1e9:.1f} G interactions/s, max diff from variant {variants[0]}: {diff:.2e}", flush=True)
 api.set_bve_variant(0)
