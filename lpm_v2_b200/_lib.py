@@ -9,7 +9,9 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "liblpmgpu.so")
+# LPM_GPU_LIBRARY: load the library from another path (a build under test, e.g. tools/build_renamed.sh, or the
+# emulator build of tests/cuda_emu).  It replaces the path only: a missing file still raises.
+LIB_PATH = os.environ.get("LPM_GPU_LIBRARY") or os.path.join(_HERE, "liblpmgpu.so")
 
 
 class LpmError(RuntimeError):

@@ -22,10 +22,9 @@
 #define __device__
 #define __host__
 #define __forceinline__ inline __attribute__((always_inline))
-#define __noinline__ __attribute__((noinline))
+// (__noinline__ is rewritten by convert.py: libstdc++ spells the attribute that way itself)
 #define __restrict__ __restrict
 #define __launch_bounds__(...)
-#define __shared__
 #define __constant__
 #define __align__(n)
 
@@ -35,7 +34,6 @@ inline thread_local EmuDim3 threadIdx, blockIdx, blockDim, gridDim;
 struct double2 { double x, y; };
 inline double2 make_double2(double x, double y) { return double2{x, y}; }
 
-using cudaStream_t = void*;
 
 // ---- one CTA at a time -------------------------------------------------------------------------
 struct EmuCta {
@@ -116,9 +114,14 @@ using std::cos;
 using std::exp;
 using std::atan2;
 using std::fabs;
+using std::tan;
+using std::ceil;
+using std::ldexp;
 inline double rsqrt(double v) { return 1.0 / std::sqrt(v); }
 inline void sincospi(double v, double* s, double* c) { *s = std::sin(M_PI * v); *c = std::cos(M_PI * v); }
 inline double __dadd_rn(double a, double b) { return a + b; }
+inline double __dmul_rn(double a, double b) { return a * b; }
+inline double __ddiv_rn(double a, double b) { return a / b; }
 inline double __hiloint2double(int hi, int lo)
 {
     const uint64_t b = ((uint64_t)(uint32_t)hi << 32) | (uint32_t)lo;
@@ -136,31 +139,71 @@ inline int max(int a, int b) { return a > b ? a : b; }
 inline unsigned max(unsigned a, unsigned b) { return a > b ? a : b; }
 inline int min(int a, int b) { return a < b ? a : b; }
 
-// ---- launchers ---------------------------------------------------------------------------------
-// kernels with barriers / shuffles: one OS thread per CUDA thread, CTAs one after the other
-inline void emu_launch(unsigned grid, unsigned block, const std::function<void()>& kernel)
+// ---- dynamic shared memory: one CTA runs at a time ---------------------------------------------
+inline unsigned char* emu_dynamic_smem()
 {
-    if (block % 32 != 0) { std::fprintf(stderr, "cuda_emu: block size %u\n", block); std::abort(); }
-    for (unsigned b = 0; b < grid; ++b) {
-        EmuCta cta;
-        cta.nthreads = (int)block;
-        pthread_barrier_init(&cta.cta_bar, nullptr, block);
-        cta.warp_bar.resize(block / 32);
+    alignas(128) static unsigned char buf[232 * 1024];
+    return buf;
+}
+
+// ---- launchers ---------------------------------------------------------------------------------
+// Kernels with barriers / shuffles: one OS thread per CUDA thread, CTAs one after the other.  The threads
+// of a block size are created once and parked between CTAs (a 256-thread spawn per CTA costs milliseconds).
+struct EmuPool {
+    unsigned block = 0;
+    std::vector<std::thread> threads;
+    pthread_barrier_t start, done;
+    EmuCta cta;
+    const std::function<void()>* kernel = nullptr;
+    unsigned bid = 0, grid = 0;
+    bool quit = false;
+    explicit EmuPool(unsigned b) : block(b)
+    {
+        pthread_barrier_init(&start, nullptr, b + 1);
+        pthread_barrier_init(&done, nullptr, b + 1);
+        cta.nthreads = (int)b;
+        pthread_barrier_init(&cta.cta_bar, nullptr, b);
+        cta.warp_bar.resize(b / 32);
         for (auto& wb : cta.warp_bar) pthread_barrier_init(&wb, nullptr, 32);
-        cta.xchg.assign(block, 0);
-        g_emu_cta = &cta;
-        std::vector<std::thread> th;
-        th.reserve(block);
-        for (unsigned t = 0; t < block; ++t)
-            th.emplace_back([&, t]() {
-                threadIdx.x = t; blockIdx.x = b; blockDim.x = block; gridDim.x = grid;
-                kernel();
+        cta.xchg.assign(b, 0);
+        for (unsigned t = 0; t < b; ++t)
+            threads.emplace_back([this, t]() {
+                for (;;) {
+                    pthread_barrier_wait(&start);
+                    if (quit) return;
+                    threadIdx.x = t; blockIdx.x = bid; blockDim.x = block; gridDim.x = grid;
+                    (*kernel)();
+                    pthread_barrier_wait(&done);
+                }
             });
-        for (auto& x : th) x.join();
-        pthread_barrier_destroy(&cta.cta_bar);
-        for (auto& wb : cta.warp_bar) pthread_barrier_destroy(&wb);
+    }
+    void run(unsigned g, const std::function<void()>& k)
+    {
+        kernel = &k; grid = g;
+        g_emu_cta = &cta;
+        for (unsigned b = 0; b < g; ++b) {
+            bid = b;
+            pthread_barrier_wait(&start);
+            pthread_barrier_wait(&done);
+        }
         g_emu_cta = nullptr;
     }
+    ~EmuPool()
+    {
+        quit = true;
+        pthread_barrier_wait(&start);
+        for (auto& t : threads) t.join();
+    }
+};
+inline void emu_launch(unsigned grid, unsigned block, const std::function<void()>& kernel)
+{
+    if (block % 32 != 0 || block == 0) { std::fprintf(stderr, "cuda_emu: block size %u\n", block); std::abort(); }
+    static std::vector<EmuPool*> pools;          // never destroyed: the threads die with the process
+    EmuPool* p = nullptr;
+    for (auto* q : pools)
+        if (q->block == block) p = q;
+    if (!p) { p = new EmuPool(block); pools.push_back(p); }
+    p->run(grid, kernel);
 }
 // kernels whose threads never talk to each other: a plain loop
 inline void emu_launch_seq(unsigned grid, unsigned block, const std::function<void()>& kernel)

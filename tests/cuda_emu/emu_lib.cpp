@@ -4,14 +4,13 @@
 // (sym_evaluate): pack, zero the accumulators, symmetric kernel (once per emulated rank, into the same
 // accumulators = the all-reduce), finalize, passive list, gather, one-sided kernel on a "view" whose
 // scan is all zero, scatter.
+#ifndef LPM_CUDA_EMU
 #define LPM_CUDA_EMU 1
+#endif
 #include "cuda_runtime.h"
 
 #include "sym_kernels.cuh"
 
-namespace lpm {
-alignas(128) unsigned char smem_raw[232 * 1024];      // the `extern __shared__` array of the kernels
-}
 using namespace lpm;
 
 namespace {

@@ -1,0 +1,86 @@
+// emu_runtime.h -- TEST INFRASTRUCTURE ONLY: the slice of the CUDA runtime API that lpm_v2_b200/csrc uses,
+// for the SIMT emulator.  "Device" memory is host memory, streams are synchronous (every operation has
+// completed when the call returns), events are wall-clock stamps.  LPM_EMU_DEVICES (default 1) emulated
+// devices share that memory, so peer stores simply work.
+#pragma once
+#include <chrono>
+
+enum cudaError_t { cudaSuccess = 0, cudaErrorInvalidValue = 1, cudaErrorMemoryAllocation = 2, cudaErrorNotSupported = 801,
+                   cudaErrorPeerAccessAlreadyEnabled = 704 };
+inline const char* cudaGetErrorString(cudaError_t e)
+{
+    switch (e) {
+        case cudaSuccess: return "no error";
+        case cudaErrorMemoryAllocation: return "out of memory (emulated)";
+        case cudaErrorNotSupported: return "not supported by the emulator";
+        default: return "emulated CUDA error";
+    }
+}
+inline cudaError_t cudaGetLastError() { return cudaSuccess; }
+
+struct EmuStream { int id; };
+using cudaStream_t = EmuStream*;
+struct EmuEvent { std::chrono::steady_clock::time_point t; };
+using cudaEvent_t = EmuEvent*;
+enum { cudaStreamNonBlocking = 1, cudaEventDisableTiming = 2, cudaHostRegisterPortable = 1, cudaIpcMemLazyEnablePeerAccess = 1 };
+enum cudaMemcpyKind { cudaMemcpyHostToDevice = 1, cudaMemcpyDeviceToHost = 2, cudaMemcpyDeviceToDevice = 3 };
+enum cudaFuncAttribute { cudaFuncAttributeMaxDynamicSharedMemorySize = 8 };
+struct cudaDeviceProp { char name[256]; int major, minor, multiProcessorCount; };
+struct cudaIpcMemHandle_t { char reserved[64]; };
+
+inline int& emu_current_device() { static thread_local int d = 0; return d; }
+inline int emu_device_count()
+{
+    const char* e = std::getenv("LPM_EMU_DEVICES");
+    const int n = e ? std::atoi(e) : 1;
+    return n < 1 ? 1 : (n > 8 ? 8 : n);
+}
+inline cudaError_t cudaGetDeviceCount(int* n) { *n = emu_device_count(); return cudaSuccess; }
+inline cudaError_t cudaSetDevice(int d) { emu_current_device() = d; return cudaSuccess; }
+inline cudaError_t cudaGetDevice(int* d) { *d = emu_current_device(); return cudaSuccess; }
+inline cudaError_t cudaGetDeviceProperties(cudaDeviceProp* p, int)
+{
+    std::snprintf(p->name, sizeof(p->name), "emulated sm_100a (tests/cuda_emu)");
+    p->major = 10; p->minor = 0; p->multiProcessorCount = 2;
+    return cudaSuccess;
+}
+inline cudaError_t cudaDeviceCanAccessPeer(int* can, int, int) { *can = 1; return cudaSuccess; }
+inline cudaError_t cudaDeviceEnablePeerAccess(int, unsigned) { return cudaSuccess; }
+inline cudaError_t cudaDeviceSynchronize() { return cudaSuccess; }
+
+template <class T> inline cudaError_t cudaMalloc(T** p, size_t bytes)
+{
+    void* q = nullptr;
+    if (posix_memalign(&q, 256, bytes ? bytes : 1) != 0) { *p = nullptr; return cudaErrorMemoryAllocation; }
+    std::memset(q, 0xdb, bytes);        // poison: nothing may rely on fresh device memory being zero
+    *p = (T*)q;
+    return cudaSuccess;
+}
+inline cudaError_t cudaFree(void* p) { std::free(p); return cudaSuccess; }
+inline cudaError_t cudaMemcpy(void* d, const void* s, size_t n, cudaMemcpyKind) { std::memmove(d, s, n); return cudaSuccess; }
+inline cudaError_t cudaMemcpyAsync(void* d, const void* s, size_t n, cudaMemcpyKind, cudaStream_t = nullptr) { std::memmove(d, s, n); return cudaSuccess; }
+inline cudaError_t cudaMemsetAsync(void* d, int v, size_t n, cudaStream_t = nullptr) { std::memset(d, v, n); return cudaSuccess; }
+template <class T> inline cudaError_t cudaMemcpyToSymbol(T& sym, const void* s, size_t n) { std::memcpy(&sym, s, n); return cudaSuccess; }
+template <class T> inline cudaError_t cudaGetSymbolAddress(void** p, T& sym) { *p = (void*)&sym; return cudaSuccess; }
+inline cudaError_t cudaHostRegister(void*, size_t, unsigned) { return cudaSuccess; }
+inline cudaError_t cudaHostUnregister(void*) { return cudaSuccess; }
+
+inline cudaError_t cudaStreamCreateWithFlags(cudaStream_t* s, unsigned) { *s = new EmuStream{0}; return cudaSuccess; }
+inline cudaError_t cudaStreamDestroy(cudaStream_t s) { delete s; return cudaSuccess; }
+inline cudaError_t cudaStreamSynchronize(cudaStream_t) { return cudaSuccess; }
+inline cudaError_t cudaEventCreate(cudaEvent_t* e) { *e = new EmuEvent{std::chrono::steady_clock::now()}; return cudaSuccess; }
+inline cudaError_t cudaEventCreateWithFlags(cudaEvent_t* e, unsigned) { return cudaEventCreate(e); }
+inline cudaError_t cudaEventDestroy(cudaEvent_t e) { delete e; return cudaSuccess; }
+inline cudaError_t cudaEventRecord(cudaEvent_t e, cudaStream_t = nullptr) { e->t = std::chrono::steady_clock::now(); return cudaSuccess; }
+inline cudaError_t cudaEventSynchronize(cudaEvent_t) { return cudaSuccess; }
+inline cudaError_t cudaStreamWaitEvent(cudaStream_t, cudaEvent_t, unsigned) { return cudaSuccess; }
+inline cudaError_t cudaEventElapsedTime(float* ms, cudaEvent_t a, cudaEvent_t b)
+{
+    *ms = std::chrono::duration<float, std::milli>(b->t - a->t).count();
+    if (!(*ms > 1e-6f)) *ms = 1e-6f;
+    return cudaSuccess;
+}
+template <class F> inline cudaError_t cudaFuncSetAttribute(F, cudaFuncAttribute, int) { return cudaSuccess; }
+inline cudaError_t cudaIpcGetMemHandle(cudaIpcMemHandle_t*, void*) { return cudaErrorNotSupported; }
+inline cudaError_t cudaIpcOpenMemHandle(void**, cudaIpcMemHandle_t, unsigned) { return cudaErrorNotSupported; }
+inline cudaError_t cudaIpcCloseMemHandle(void*) { return cudaErrorNotSupported; }

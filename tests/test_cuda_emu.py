@@ -30,13 +30,7 @@ TOL = 1e-12
 @pytest.fixture(scope="module")
 def emu():
     so = os.path.join(EMU, "libcuda_emu.so")
-    srcs = [os.path.join(EMU, f) for f in os.listdir(EMU) if f.endswith((".h", ".cpp"))]
-    srcs += [os.path.join(ROOT, "lpm_v2_b200", "csrc", f) for f in ("directsum.cuh", "pairs.cuh", "sym_kernels.cuh")]
-    if not os.path.exists(so) or os.path.getmtime(so) < max(os.path.getmtime(s) for s in srcs):
-        # hidden visibility + -Bsymbolic: liblpmgpu.so exports host stubs with the kernels' names
-        subprocess.check_call(["g++", "-std=c++20", "-O1", "-fPIC", "-shared", "-pthread", "-fvisibility=hidden",
-                               "-Wl,-Bsymbolic", f"-I{EMU}", f"-I{ROOT}/lpm_v2_b200/csrc", f"-I{ROOT}/include",
-                               "-o", so, os.path.join(EMU, "emu_lib.cpp")])
+    subprocess.check_call(["bash", os.path.join(EMU, "build_emu.sh")])      # also converts csrc for g++ (convert.py)
     lib = C.CDLL(so)
     d = np.ctypeslib.ndpointer(np.float64, flags="C")
     i32 = np.ctypeslib.ndpointer(np.int32, flags="C")

@@ -1,0 +1,54 @@
+"""The whole C ABI on the SIMT emulator (CPU tier).
+
+tests/cuda_emu/build_emu.sh compiles lpm_v2_b200/csrc -- kernels AND host code -- with g++ against the emulator
+(convert.py rewrites the <<<>>> launches; emu_runtime.h stands in for the CUDA runtime, device memory = host memory)
+into tests/cuda_emu/liblpmgpu_emu.so, which exports the same symbols as liblpmgpu.so.  A subprocess then runs a
+subset of the GPU parity tests against it (LPM_GPU_LIBRARY): the tests that finish within seconds under emulation
+(tests/cuda_emu/emu_subset.txt: 60-odd of tests/test_parity_gpu.py, test_pse_ops_gpu.py, test_swe_gpu.py) and the small
+cases of the experimental pair-symmetric paths (tests/test_sym_gpu.py).
+
+What this buys: kernel and host logic (indexing, pipelines, culling, retry paths, chunking, the symmetric schedule
+and its gather / scatter plumbing) is exercised on every CPU run, before any GPU time is spent.  What it is not: a
+CPU path of the product -- liblpmgpu.so has none (tests/test_abi.py::test_no_cpu_fallback), nothing under
+lpm_v2_b200/ refers to the emulator, and timings under it mean nothing.
+"""
+import os
+import subprocess
+import sys
+
+import pytest
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(HERE)
+EMU = os.path.join(HERE, "cuda_emu")
+
+
+@pytest.fixture(scope="module")
+def emu_env():
+    subprocess.check_call(["bash", os.path.join(EMU, "build_emu.sh")])
+    env = dict(os.environ)
+    env["LPM_GPU_LIBRARY"] = os.path.join(EMU, "liblpmgpu_emu.so")
+    env["LPM_EXPERIMENTAL"] = "1"
+    return env
+
+
+def _run(env, args, timeout):
+    r = subprocess.run([sys.executable, "-m", "pytest", "-m", "gpu", "-q", "-x", "-p", "no:cacheprovider"] + args,
+                       cwd=ROOT, env=env, capture_output=True, text=True, timeout=timeout)
+    tail = "\n".join((r.stdout + r.stderr).splitlines()[-25:])
+    assert r.returncode == 0, tail
+    return tail
+
+
+def test_default_paths_on_emulator(emu_env):
+    ids = [l.strip() for l in open(os.path.join(EMU, "emu_subset.txt")) if l.strip()]
+    tail = _run(emu_env, ids, 900)
+    assert f"{len(ids)} passed" in tail, tail
+
+
+def test_symmetric_paths_on_emulator(emu_env):
+    """lpm_set_bve_variant(200..203) through the real host code: velocity, stream functions, planar velocity."""
+    tail = _run(emu_env, ["tests/test_sym_gpu.py", "-k",
+                          "(random_ragged and not 20011 and not 4099 and not 6000) or plane_velocity_mesh and 3-20 "
+                          "or (4099 and (200 or 201) and velocity_random)"], 900)
+    assert " passed" in tail and "failed" not in tail, tail
