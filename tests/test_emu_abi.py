@@ -52,3 +52,20 @@ def test_symmetric_paths_on_emulator(emu_env):
                           "(random_ragged and not 20011 and not 4099 and not 6000) or plane_velocity_mesh and 3-20 "
                           "or (4099 and (200 or 201) and velocity_random)"], 900)
     assert " passed" in tail and "failed" not in tail, tail
+
+
+def test_single_process_multi_device_on_emulator(emu_env, tmp_path):
+    """The single-process mode of tests/test_multigpu.py (every device evaluates its LoadBalance slice and stores it
+    to all replicas, event barrier, RK4 steps on every replica) on three emulated devices, one level smaller."""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("_tm", os.path.join(HERE, "test_multigpu.py"))
+    tm = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(tm)
+    text = (tm.SINGLE_PROCESS % {"root": ROOT}).replace("ICOS_TRI_SPHERE_SEED, 4)", "ICOS_TRI_SPHERE_SEED, 3)")
+    text = text.replace("QUAD_RECT_SEED, 4, 3.0)", "QUAD_RECT_SEED, 3, 3.0)")
+    assert "SEED, 3)" in text and "SEED, 3, 3.0)" in text
+    script = tmp_path / "sp.py"
+    script.write_text(text)
+    env = dict(emu_env, LPM_EMU_DEVICES="3")
+    r = subprocess.run([sys.executable, str(script)], capture_output=True, text=True, timeout=600, env=env)
+    assert r.returncode == 0 and "OK 3" in r.stdout, r.stdout[-2000:] + r.stderr[-4000:]
