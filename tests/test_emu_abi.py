@@ -69,3 +69,13 @@ def test_single_process_multi_device_on_emulator(emu_env, tmp_path):
     env = dict(emu_env, LPM_EMU_DEVICES="3")
     r = subprocess.run([sys.executable, str(script)], capture_output=True, text=True, timeout=600, env=env)
     assert r.returncode == 0 and "OK 3" in r.stdout, r.stdout[-2000:] + r.stderr[-4000:]
+
+
+@pytest.mark.skipif(os.environ.get("LPM_RACE_CHECK") != "1", reason="2 minutes: set LPM_RACE_CHECK=1")
+def test_kernels_are_race_free_under_thread_sanitizer(tmp_path):
+    """tests/cuda_emu/race_check.sh: every kernel family once through the ThreadSanitizer build of the emulated
+    library; a shared-memory protocol error in a kernel is a data race between the threads that stand for a CTA."""
+    log = tmp_path / "race.log"
+    r = subprocess.run(["bash", os.path.join(EMU, "race_check.sh"), str(log)], capture_output=True, text=True, timeout=1800)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert "workloads completed: 2" in r.stdout and "ThreadSanitizer reports: 0" in r.stdout, r.stdout + log.read_text()[-4000:]
