@@ -3,7 +3,15 @@
 // completed when the call returns), events are wall-clock stamps.  LPM_EMU_DEVICES (default 1) emulated
 // devices share that memory, so peer stores simply work.
 #pragma once
+#include <fcntl.h>
+#include <sys/mman.h>
+#include <sys/stat.h>
+#include <unistd.h>
+
 #include <chrono>
+#include <map>
+#include <mutex>
+#include <string>
 
 enum cudaError_t { cudaSuccess = 0, cudaErrorInvalidValue = 1, cudaErrorMemoryAllocation = 2, cudaErrorNotSupported = 801,
                    cudaErrorPeerAccessAlreadyEnabled = 704 };
@@ -48,15 +56,42 @@ inline cudaError_t cudaDeviceCanAccessPeer(int* can, int, int) { *can = 1; retur
 inline cudaError_t cudaDeviceEnablePeerAccess(int, unsigned) { return cudaSuccess; }
 inline cudaError_t cudaDeviceSynchronize() { return cudaSuccess; }
 
-template <class T> inline cudaError_t cudaMalloc(T** p, size_t bytes)
+// Device allocations are POSIX shared-memory segments, so that cudaIpcGetMemHandle / cudaIpcOpenMemHandle can map
+// one process's "device" buffer into another (rank mode: the shared slabs the ranks store their slices into).
+struct EmuAlloc { std::string name; size_t bytes; };
+inline std::map<void*, EmuAlloc>& emu_allocs() { static std::map<void*, EmuAlloc> m; return m; }
+inline std::map<void*, size_t>& emu_ipc_maps() { static std::map<void*, size_t> m; return m; }
+inline std::mutex& emu_alloc_mutex() { static std::mutex m; return m; }
+inline cudaError_t emu_malloc(void** p, size_t bytes)
 {
-    void* q = nullptr;
-    if (posix_memalign(&q, 256, bytes ? bytes : 1) != 0) { *p = nullptr; return cudaErrorMemoryAllocation; }
+    static int counter = 0;
+    std::lock_guard<std::mutex> lock(emu_alloc_mutex());
+    if (bytes == 0) bytes = 1;
+    char name[64];
+    std::snprintf(name, sizeof(name), "/lpmemu_%d_%d", (int)getpid(), counter++);
+    const int fd = shm_open(name, O_CREAT | O_EXCL | O_RDWR, 0600);
+    if (fd < 0) { *p = nullptr; return cudaErrorMemoryAllocation; }
+    if (ftruncate(fd, (off_t)bytes) != 0) { close(fd); shm_unlink(name); *p = nullptr; return cudaErrorMemoryAllocation; }
+    void* q = mmap(nullptr, bytes, PROT_READ | PROT_WRITE, MAP_SHARED, fd, 0);
+    close(fd);
+    if (q == MAP_FAILED) { shm_unlink(name); *p = nullptr; return cudaErrorMemoryAllocation; }
     std::memset(q, 0xdb, bytes);        // poison: nothing may rely on fresh device memory being zero
-    *p = (T*)q;
+    emu_allocs()[q] = EmuAlloc{name, bytes};
+    *p = q;
     return cudaSuccess;
 }
-inline cudaError_t cudaFree(void* p) { std::free(p); return cudaSuccess; }
+template <class T> inline cudaError_t cudaMalloc(T** p, size_t bytes) { return emu_malloc((void**)p, bytes); }
+inline cudaError_t cudaFree(void* p)
+{
+    if (!p) return cudaSuccess;
+    std::lock_guard<std::mutex> lock(emu_alloc_mutex());
+    auto it = emu_allocs().find(p);
+    if (it == emu_allocs().end()) return cudaErrorInvalidValue;
+    munmap(p, it->second.bytes);
+    shm_unlink(it->second.name.c_str());
+    emu_allocs().erase(it);
+    return cudaSuccess;
+}
 inline cudaError_t cudaMemcpy(void* d, const void* s, size_t n, cudaMemcpyKind) { std::memmove(d, s, n); return cudaSuccess; }
 inline cudaError_t cudaMemcpyAsync(void* d, const void* s, size_t n, cudaMemcpyKind, cudaStream_t = nullptr) { std::memmove(d, s, n); return cudaSuccess; }
 inline cudaError_t cudaMemsetAsync(void* d, int v, size_t n, cudaStream_t = nullptr) { std::memset(d, v, n); return cudaSuccess; }
@@ -81,6 +116,37 @@ inline cudaError_t cudaEventElapsedTime(float* ms, cudaEvent_t a, cudaEvent_t b)
     return cudaSuccess;
 }
 template <class F> inline cudaError_t cudaFuncSetAttribute(F, cudaFuncAttribute, int) { return cudaSuccess; }
-inline cudaError_t cudaIpcGetMemHandle(cudaIpcMemHandle_t*, void*) { return cudaErrorNotSupported; }
-inline cudaError_t cudaIpcOpenMemHandle(void**, cudaIpcMemHandle_t, unsigned) { return cudaErrorNotSupported; }
-inline cudaError_t cudaIpcCloseMemHandle(void*) { return cudaErrorNotSupported; }
+inline cudaError_t cudaIpcGetMemHandle(cudaIpcMemHandle_t* h, void* p)
+{
+    std::lock_guard<std::mutex> lock(emu_alloc_mutex());
+    auto it = emu_allocs().find(p);
+    if (it == emu_allocs().end()) return cudaErrorInvalidValue;
+    std::memset(h, 0, sizeof(*h));
+    std::snprintf(h->reserved, 48, "%s", it->second.name.c_str());
+    const uint64_t bytes = it->second.bytes;
+    std::memcpy(h->reserved + 48, &bytes, 8);
+    return cudaSuccess;
+}
+inline cudaError_t cudaIpcOpenMemHandle(void** p, cudaIpcMemHandle_t h, unsigned)
+{
+    uint64_t bytes = 0;
+    std::memcpy(&bytes, h.reserved + 48, 8);
+    const int fd = shm_open(h.reserved, O_RDWR, 0600);
+    if (fd < 0) return cudaErrorInvalidValue;
+    void* q = mmap(nullptr, bytes, PROT_READ | PROT_WRITE, MAP_SHARED, fd, 0);
+    close(fd);
+    if (q == MAP_FAILED) return cudaErrorInvalidValue;
+    std::lock_guard<std::mutex> lock(emu_alloc_mutex());
+    emu_ipc_maps()[q] = bytes;
+    *p = q;
+    return cudaSuccess;
+}
+inline cudaError_t cudaIpcCloseMemHandle(void* p)
+{
+    std::lock_guard<std::mutex> lock(emu_alloc_mutex());
+    auto it = emu_ipc_maps().find(p);
+    if (it == emu_ipc_maps().end()) return cudaErrorInvalidValue;
+    munmap(p, it->second);
+    emu_ipc_maps().erase(it);
+    return cudaSuccess;
+}

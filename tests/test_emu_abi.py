@@ -71,6 +71,30 @@ def test_single_process_multi_device_on_emulator(emu_env, tmp_path):
     assert r.returncode == 0 and "OK 3" in r.stdout, r.stdout[-2000:] + r.stderr[-4000:]
 
 
+def test_rank_mode_on_emulator(emu_env, tmp_path):
+    """One process per "GPU", three ranks (a ragged LoadBalance split): tests/cuda_emu/rank_mode.py.  The NCCL calls
+    go to tests/cuda_emu/fake_nccl (shared memory + a process-shared barrier); "device" allocations are shared-memory
+    segments, so the CUDA-IPC slabs and the peer stores into them are real cross-process stores.  Covers the fused
+    peer-store exchange with its barriers, the resident solver in a shared slab, the scatter exchange of the
+    cell-ordered PSE path, and the all-reduce + grouped broadcast of the pair-symmetric variants."""
+    world = 3
+    env = dict(emu_env)
+    env["LD_LIBRARY_PATH"] = os.path.join(EMU, "fake_nccl") + os.pathsep + env.get("LD_LIBRARY_PATH", "")
+    idfile = str(tmp_path / "uid")
+    procs = [subprocess.Popen([sys.executable, os.path.join(EMU, "rank_mode.py"), str(world), str(r), idfile],
+                              env=env, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True) for r in range(world)]
+    outs = []
+    for p in procs:
+        try:
+            outs.append(p.communicate(timeout=600)[0])
+        except subprocess.TimeoutExpired:
+            for q in procs:
+                q.kill()
+            raise
+    for r, (p, out) in enumerate(zip(procs, outs)):
+        assert p.returncode == 0 and f"OK rank {r} of {world}" in out, out[-3000:]
+
+
 @pytest.mark.skipif(os.environ.get("LPM_RACE_CHECK") != "1", reason="2 minutes: set LPM_RACE_CHECK=1")
 def test_kernels_are_race_free_under_thread_sanitizer(tmp_path):
     """tests/cuda_emu/race_check.sh: every kernel family once through the ThreadSanitizer build of the emulated
