@@ -433,9 +433,11 @@ inline int launch_variant(int variant, cudaStream_t st, const typename K::Params
         // consumer).  With its default target of ~80 registers it emitted each chain back to back
         // and the kernel stalled on DFMA latency (ncu: FP64 pipe 62 %, top stall `wait`).
         int T = auto_T(g.nall, g.nchunks, sm_count, 256);
-        if (variant == 102) T = 102;
+        if (variant == 102 || variant == 103) T = variant;
         switch (T) {
             case 102: launch_ds<K, 4, 384, 2, 2>(st, prm, g, src, scan, partial); break;    // A/B: 24 warps, 80 registers
+            // A/B (not measured yet): a scheduling fence after every source; modelled 27.7 instead of 29.6 cycles per pair
+            case 103: launch_ds<Fenced<K>, 4, 256, 2, 2>(st, prm, g, src, scan, partial); break;
             case 4: launch_ds<K, 4, 256, 2, 2>(st, prm, g, src, scan, partial); break;
             case 2: launch_ds<K, 2, 256, 2, 2>(st, prm, g, src, scan, partial); break;
             default: launch_ds<K, 1, 256, 2, 2>(st, prm, g, src, scan, partial); break;
@@ -496,6 +498,9 @@ inline int launch_variant<BveVel>(int variant, cudaStream_t st, const BveVel::Pa
         case 32: launch_ds<BveVelT<4, 10765>, 4, 128, 2>(st, prm, g, src, scan, partial); break;
         case 41: launch_ds<BveVelT<4, 3680>, 8, 128, 2>(st, prm, g, src, scan, partial); break;
         case 43: launch_ds<BveVelT<4, 3744>, 8, 128, 2>(st, prm, g, src, scan, partial); break;
+        // A/B (not measured yet): variant 41 with a scheduling fence after every source (directsum.cuh, sched_fence);
+        // modelled 20.3 instead of 20.8 cycles per pair, 164 registers
+        case 44: launch_ds<Fenced<BveVelT<4, 3680>>, 8, 128, 2>(st, prm, g, src, scan, partial); break;
         default: return set_error(LPM_ERR_INVALID, "unknown BVE kernel variant %d", variant);
     }
     return LPM_OK;

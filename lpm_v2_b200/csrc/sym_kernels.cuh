@@ -115,14 +115,6 @@ __device__ __forceinline__ void sym_reduce_red(double (&cb)[SB][NC], int lane, d
 //   bit 4     cb-phase nest (target, component, source) -- P_t stays in the reuse cache -- else
 //             (source, target, component) -- 1/d stays
 //   bit 5     a scheduling fence after every source group (sched_fence below)
-// A never-taken branch on loaded data: it ends the basic block, so ptxas schedules the source groups one
-// after the other instead of interleaving a whole batch (which loses the operand reuse between
-// neighbouring instructions of a phase).  The payload is a signalling-NaN pattern no coordinate carries.
-__device__ __forceinline__ void sched_fence(double v)
-{
-    if (__builtin_expect(__double2hiint(v) == 0x7ff4dead, 0)) __trap();
-}
-
 struct SymBveVel : NoSharedTable {
     static constexpr int NS = 6, NA = 3, NC = 3;
     struct Tgt { double x, y, z, px, py, pz; };

@@ -145,3 +145,23 @@ def test_sym_rk4_step(sym, oracle, get_mesh):
     got = [sph.x, sph.y, sph.z, sph.relVort] + sph.velocity
     for a, b in zip(got, ref):
         assert relerr(a, b) <= TOL
+
+
+@pytest.mark.parametrize("sym", [44, 103], indirect=True)
+def test_fenced_one_sided_variants(sym, oracle, get_mesh):
+    """The one-sided kernels with a scheduling fence after every source (variant 44: BVE velocity, 103: the
+    stream-function kernels): same arithmetic, another instruction schedule -- also not measured yet."""
+    m = get_mesh(M.ICOS_TRI_SPHERE_SEED, 4)
+    zeta = problems.gaussian_vortex(m)
+    av = problems.abs_vorticity(m, zeta, 2.0 * np.pi)
+    got = sym.bve_velocity(m.x, m.y, m.z, zeta, m.area, m.is_active, 1.0)
+    want = oracle.bve_velocity(m.x, m.y, m.z, zeta, m.area, m.is_active, 1.0)
+    for g, w in zip(got, want):
+        assert relerr(g, w) <= TOL
+    gots = sym.bve_stream(m.x, m.y, m.z, zeta, av, m.area, m.is_active, 1.0)
+    wants = oracle.bve_stream(m.x, m.y, m.z, zeta, av, m.area, m.is_active, 1.0)
+    for g, w in zip(gots, wants):
+        assert relerr(g, w) <= TOL
+    q = get_mesh(M.QUAD_RECT_SEED, 4, 7.0)
+    vq = problems.colliding_dipoles(q)
+    assert relerr(sym.plane_stream(q.x, q.y, vq, q.area, q.is_active), oracle.plane_stream(q.x, q.y, vq, q.area, q.is_active)) <= TOL
