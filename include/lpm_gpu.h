@@ -294,7 +294,7 @@ int64_t lpm_launch_count(int reset);
 /* 1: record events around each main kernel (adds a sync at query time only). */
 int lpm_set_profiling(int enable);
 /* Tuning knob for benchmarks: select the BVE kernel variant.  0 = default.
- * 1-99: tilings / statement orders of the one-sided kernel (44: with scheduling fences); 102, 103: shapes of the
+ * 1-99: tilings / statement orders of the one-sided kernel (44, 45: with scheduling fences); 102, 103: shapes of the
  * stream-function kernels (103: with scheduling fences);
  * 200-203: EXPERIMENTAL pair-symmetric evaluation of the velocity sum (csrc/symmetric.cuh; opt-in, results
  * reproducible to rounding but not bit for bit; in rank mode every rank must set the same value). */

@@ -501,6 +501,9 @@ inline int launch_variant<BveVel>(int variant, cudaStream_t st, const BveVel::Pa
         // A/B (not measured yet): variant 41 with a scheduling fence after every source (directsum.cuh, sched_fence);
         // modelled 20.3 instead of 20.8 cycles per pair, 164 registers
         case 44: launch_ds<Fenced<BveVelT<4, 3680>>, 8, 128, 2>(st, prm, g, src, scan, partial); break;
+        // the best of 160 statement orders of the fenced kernel under the fitted model (FENCED=1 tools/search_order.py):
+        // 87.1 ms at icosTri 7 against 89.3 modelled / 88.7 measured for variant 41
+        case 45: launch_ds<Fenced<BveVelT<4, 5248>>, 8, 128, 2>(st, prm, g, src, scan, partial); break;
         default: return set_error(LPM_ERR_INVALID, "unknown BVE kernel variant %d", variant);
     }
     return LPM_OK;

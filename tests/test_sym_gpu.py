@@ -147,7 +147,7 @@ def test_sym_rk4_step(sym, oracle, get_mesh):
         assert relerr(a, b) <= TOL
 
 
-@pytest.mark.parametrize("sym", [44, 103], indirect=True)
+@pytest.mark.parametrize("sym", [44, 45, 103], indirect=True)
 def test_fenced_one_sided_variants(sym, oracle, get_mesh):
     """The one-sided kernels with a scheduling fence after every source (variant 44: BVE velocity, 103: the
     stream-function kernels): same arithmetic, another instruction schedule -- also not measured yet."""

@@ -3,7 +3,8 @@
 Compiles the BVE velocity kernel alone (a one-instantiation translation unit, ~1.5 s) for many
 ORDER seeds, scores each hot loop with the bank model of tools/sass_banks.py
 (fresh operand reads + bank conflicts -> predicted ms at icosTri 7) and prints the best; the GPU sweep
-(tools/sweep_bve.py) then measures the short list.   usage: search_order.py [n_random] [T] [U] [min CTAs per SM]"""
+(tools/sweep_bve.py) then measures the short list.   usage: search_order.py [n_random] [T] [U] [min CTAs per SM]
+FENCED=1 searches the kernel with a scheduling fence after every source (Fenced<>, directsum.cuh)."""
 import concurrent.futures as cf
 import os, random, shutil, subprocess, sys, tempfile
 
@@ -15,7 +16,11 @@ TU = r'''
 #include "directsum.cuh"
 #include "pairs.cuh"
 using namespace lpm;
+#ifdef FENCED
+template __global__ void lpm::ds_kernel<Fenced<BveVelT<4, ORD_SEED>>, TT, 128, UU, LB_MIN>(const BveVelParams, const DsGeom, const double*, const int32_t*, double*);
+#else
 template __global__ void lpm::ds_kernel<BveVelT<4, ORD_SEED>, TT, 128, UU, LB_MIN>(const BveVelParams, const DsGeom, const double*, const int32_t*, double*);
+#endif
 '''
 
 def score(seed, T, U, work, minb=1):
@@ -23,10 +28,10 @@ def score(seed, T, U, work, minb=1):
     out = os.path.join(work, f"o{seed}_{T}_{U}_{minb}.cubin")
     r = subprocess.run(["nvcc", "-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
                         f"-I{ROOT}/include", f"-I{ROOT}/lpm_v2_b200/csrc", f"-DORD_SEED={seed}", f"-DTT={T}", f"-DUU={U}", f"-DLB_MIN={minb}",
-                        "-cubin", "-o", out, cu], capture_output=True, text=True)
+                        *(["-DFENCED"] if os.environ.get("FENCED") == "1" else []), "-cubin", "-o", out, cu], capture_output=True, text=True)
     if r.returncode != 0:
         return seed, None
-    st = bank_stats(hot_loop(function_sass("ds_kernel", out)))
+    st = bank_stats(hot_loop(function_sass("ds_kernel", out), allow_inner=True))
     os.remove(out)
     pairs = T * U
     return seed, {"cost": model_ms_l7(st, pairs), "same2": st["same2"] / pairs, "fresh": st["fresh"] / pairs,
