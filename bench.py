@@ -38,7 +38,7 @@ def parse():
     ap.add_argument("--level", type=int, default=8, help="icosTri refinement level (8 = headline)")
     ap.add_argument("--no-rk4", action="store_true", help="skip the RK4 step-time measurement")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
-    ap.add_argument("--variant", type=int, default=0)
+    ap.add_argument("--variant", type=int, default=0, help="tuning: lpm_set_bve_variant value (0 = the default kernel)")
     ap.add_argument("--max-chunks", type=int, default=0, help="tuning: upper bound on source chunks (0 = library default)")
     return ap.parse_args()
 
@@ -50,8 +50,8 @@ def workload(level):
     return m, zeta
 
 
-def config_dict(level, m, world):
-    return {
+def config_dict(level, m, world, variant=0):
+    cfg = {
         "workload": f"RossbyHaurwitz54 BVE direct sum, icosTri level {level} (faceKind=3, initNest={level}): "
                     f"{m.n} targets x {m.n_active} active panels, RH54 vorticity (examples/rh54.namelist), R=1",
         "interactions_per_step": int(m.n) * int(m.n_active) - int(m.n_active),
@@ -60,6 +60,10 @@ def config_dict(level, m, world):
                       "4-byte NCCL all-reduce barriers") if world > 1 else "all targets on 1 GPU (no exchange)",
         "l2": "256 MiB memset between timed steps (time included); sources (63 MB) are meant to live in L2",
     }
+    if variant:
+        cfg["kernel_variant"] = (f"lpm_set_bve_variant({variant}): NOT the default kernel (tuning / experimental path, "
+                                 "see include/lpm_gpu.h and DESIGN.md 9)")
+    return cfg
 
 
 # ------------------------------------------------------------------ clocks
@@ -289,7 +293,7 @@ def run_b200(args):
         "metric": METRIC, "value": value, "unit": "interactions/s", "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": config_dict(args.level, m, world),
+        "config": config_dict(args.level, m, world, args.variant),
         "roofline": {
             "bound": "fp64", "achieved": achieved_tf, "peak": probe_tf, "unit": "TFLOP/s",
             "frac": achieved_tf / probe_tf, "traffic": traffic,
