@@ -239,6 +239,16 @@ struct SolverBase {
                     continue;
                 }
             }
+            if constexpr (std::is_same<Op, OpBetaVel>::value) {
+                if (sym_applicable(rt().bve_variant, r.sb, r.se, n, r.mp, nrep)) {
+                    Outs<2> o{};
+                    o.nrep = 1;
+                    for (int k = 0; k < 2; ++k) o.p[0][k] = r.A(out[k]);
+                    LPM_TRY(betaplane_velocity_sym(*r.dev, r.dev->stream, r.mp, a, o, rt().bve_variant));
+                    exchanged = true;
+                    continue;
+                }
+            }
             if constexpr (std::is_same<Op, OpBveStream>::value) {
                 if (sym_applicable(variant, r.sb, r.se, n, r.mp, nrep)) {
                     Outs<2> o{};

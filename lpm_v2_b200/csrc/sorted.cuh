@@ -99,6 +99,7 @@ __global__ void scatter_kernel(int64_t count, const int32_t* __restrict__ perm, 
 inline int bve_velocity_sym(Device& dev, cudaStream_t st, MaskPlan& mp, const Args& a, const Outs<3>& out, int variant);
 inline int bve_stream_sym(Device& dev, cudaStream_t st, MaskPlan& mp, const Args& a, const Outs<2>& out, int variant);
 inline int plane_velocity_sym(Device& dev, cudaStream_t st, MaskPlan& mp, const Args& a, const Outs<2>& out, int variant);
+inline int betaplane_velocity_sym(Device& dev, cudaStream_t st, MaskPlan& mp, const Args& a, const Outs<2>& out, int variant);
 inline bool sym_applicable(int variant, int64_t tbeg, int64_t tend, int64_t nt, const MaskPlan& mp, int nrep);
 
 // (key, value) pairs sorted by key into ws.sort_vals[1]; returns that pointer
@@ -171,6 +172,14 @@ inline int evaluate_impl(Device& dev, cudaStream_t st, MaskPlan& mp, const Args&
                 set_outs(o, out);
                 *exchanged = rt().rank_mode && rt().world > 1;
                 return plane_velocity_sym(dev, st, mp, a, o, rt().bve_variant);
+            }
+        }
+        if constexpr (std::is_same<Op, OpBetaVel>::value) {
+            if (sym_applicable(rt().bve_variant, tbeg, tend, nt, mp, 1)) {
+                Outs<2> o{};
+                set_outs(o, out);
+                *exchanged = rt().rank_mode && rt().world > 1;
+                return betaplane_velocity_sym(dev, st, mp, a, o, rt().bve_variant);
             }
         }
         LPM_TRY(Op::pack(dev, st, mp, a));

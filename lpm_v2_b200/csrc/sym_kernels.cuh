@@ -437,6 +437,90 @@ struct SymPlaneVel : NoSharedTable {
     }
 };
 
+// Beta-plane Biot-Savart (BetaVel in pairs.cuh); record sinh(pi y), cosh(pi y), sin(pi x), cos(pi x), zeta A / 2, 0.
+// With S = sinh(pi dy), C = cosh(pi dy), s = sin(pi dx), c = cos(pi dx) from the addition formulas:
+// u_i -= S C w_j / (S^2 + s^2),  v_i += s c w_j / (S^2 + s^2).  Swapping the pair flips the signs of S and s only, so
+// the eight addition-formula operations, the denominator, S C, s c and the reciprocal (15 of 18 FP64 instructions)
+// serve both directions:  u_j += S C w_i / (..),  v_j -= s c w_i / (..):  21 instructions for two interactions.
+// A null TARGET is (-1e10, 1e10, 0, 1) against the null source record's (+1e10, 1e10, 0, 1): no pair has S = s = 0.
+//   ORDER bit 0: a scheduling fence after every source (sched_fence)
+struct SymBetaVel : NoSharedTable {
+    static constexpr int NS = 6, NA = 2, NC = 2;
+    struct Tgt { double sh, ch, sn, cs, w; };
+    __device__ static __forceinline__ Tgt null() { return Tgt{-1.0e10, 1.0e10, 0.0, 1.0, 0.0}; }
+    __device__ static __forceinline__ Tgt from_record(const double2* p2)
+    {
+        const double2 v0 = p2[0], v1 = p2[1], v2 = p2[2];
+        return Tgt{v0.x, v0.y, v1.x, v1.y, v2.x};
+    }
+    template <int T>
+    __device__ static __forceinline__ void pair_terms(const Tgt (&tg)[T], const double (&s)[NS], double (&SC)[T],
+                                                      double (&sc)[T], double (&den)[T])
+    {
+#pragma unroll
+        for (int t = 0; t < T; ++t) {
+            const double S = fma(tg[t].sh, s[1], -(tg[t].ch * s[0]));
+            const double C = fma(tg[t].ch, s[1], -(tg[t].sh * s[0]));
+            const double sn = fma(tg[t].sn, s[3], -(tg[t].cs * s[2]));
+            const double cs = fma(tg[t].cs, s[3], tg[t].sn * s[2]);
+            den[t] = fma(S, S, sn * sn);
+            SC[t] = S * C; sc[t] = sn * cs;
+        }
+    }
+    template <int T, int SB, int ORDER>
+    __device__ static __forceinline__ void batch(const SymParams&, const Tgt (&tg)[T], double (&a)[T][NA],
+                                                 const double* __restrict__ sm, double (&cb)[SB][NC], const SharedCtx&)
+    {
+#pragma unroll
+        for (int u = 0; u < SB; ++u) {
+            double s[NS], SC[T], sc[T], den[T], r[T];
+            const double2* p2 = reinterpret_cast<const double2*>(sm + u * NS);
+#pragma unroll
+            for (int q = 0; q < NS / 2; ++q) {
+                const double2 v = p2[q];
+                s[2 * q] = v.x; s[2 * q + 1] = v.y;
+            }
+            pair_terms<T>(tg, s, SC, sc, den);
+            rcp_batch<T>(den, r);
+#pragma unroll
+            for (int t = 0; t < T; ++t) {
+                const double w = r[t] * s[4];
+                a[t][0] = fma(-SC[t], w, a[t][0]);
+                a[t][1] = fma(sc[t], w, a[t][1]);
+            }
+            {
+                const double w = r[0] * tg[0].w;
+                cb[u][0] = SC[0] * w; cb[u][1] = -sc[0] * w;
+            }
+#pragma unroll
+            for (int t = 1; t < T; ++t) {
+                const double w = r[t] * tg[t].w;
+                cb[u][0] = fma(SC[t], w, cb[u][0]);
+                cb[u][1] = fma(-sc[t], w, cb[u][1]);
+            }
+            if constexpr ((ORDER & 1) != 0) sched_fence(s[1]);
+        }
+    }
+    // as BetaVel::group<T, true>
+    template <int T>
+    __device__ static __forceinline__ void diag(const SymParams&, const Tgt (&tg)[T], double (&a)[T][NA],
+                                                const double (&s)[NS], const bool (&isself)[T], const SharedCtx&)
+    {
+        double SC[T], sc[T], den[T], r[T];
+        pair_terms<T>(tg, s, SC, sc, den);
+#pragma unroll
+        for (int t = 0; t < T; ++t) den[t] = isself[t] ? 1.0 : den[t];
+        rcp_batch<T>(den, r);
+#pragma unroll
+        for (int t = 0; t < T; ++t) {
+            double w = r[t] * s[4];
+            w = isself[t] ? 0.0 : w;
+            a[t][0] = fma(-SC[t], w, a[t][0]);
+            a[t][1] = fma(sc[t], w, a[t][1]);
+        }
+    }
+};
+
 // ---- the kernel ---------------------------------------------------------------
 // acc: [nsrc_pad][NC] doubles, zeroed by the caller (NA == NC: both directions feed the same sums).
 // dynamic shared memory: [2 tiles][K::KS table][2 mbarriers]

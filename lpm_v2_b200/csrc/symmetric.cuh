@@ -137,6 +137,28 @@ struct SymPlane {
     }
 };
 
+// Beta-plane Biot-Savart
+struct SymBeta {
+    using Op = OpBetaVel;
+    using SK = SymBetaVel;
+    static constexpr int NCOORD = 2;
+    static void sym_params(SymParams&, const Args&) {}
+    static void passive_params(BetaVel::Params& p, const double* const* xy, const Args&) { p.x = xy[0]; p.y = xy[1]; }
+    static int launch(int variant, cudaStream_t st, const SymParams& prm, const SymGeom& g, const double* src, double* acc)
+    {
+        switch (variant - kSymVariant) {
+            case 1: return launch_sym<SK, 4, 128, 4, 2, 1>(st, prm, g, src, acc);
+            case 2: return launch_sym<SK, 4, 128, 8, 2, 0>(st, prm, g, src, acc);
+            case 3: return launch_sym<SK, 4, 128, 4, 2, 0>(st, prm, g, src, acc);
+            default: return launch_sym<SK, 4, 128, 8, 2, 1>(st, prm, g, src, acc);
+        }
+    }
+    static void finalize(cudaStream_t st, const MaskPlan& mp, const double*, const double* acc, const Outs<2>& out)
+    {
+        sym_stream_finalize<<<(unsigned)((mp.nsrc + 255) / 256), 256, 0, st>>>(mp.nsrc, mp.active.as<int32_t>(), acc, out);
+    }
+};
+
 // Whole evaluation: one device, or -- rank mode -- collectively on every rank (each must call with its
 // LoadBalance slice, sym_applicable() checks that): target blocks of the active x active part are dealt
 // round-robin to the ranks and the accumulators summed with one ncclAllReduce (NC F doubles); the passive
@@ -256,6 +278,10 @@ inline int bve_stream_sym(Device& dev, cudaStream_t st, MaskPlan& mp, const Args
 inline int plane_velocity_sym(Device& dev, cudaStream_t st, MaskPlan& mp, const Args& a, const Outs<2>& out, int variant)
 {
     return sym_evaluate<SymPlane>(dev, st, mp, a, out, variant);
+}
+inline int betaplane_velocity_sym(Device& dev, cudaStream_t st, MaskPlan& mp, const Args& a, const Outs<2>& out, int variant)
+{
+    return sym_evaluate<SymBeta>(dev, st, mp, a, out, variant);
 }
 
 // May this evaluation take the symmetric path?  One device driving every target, or rank mode with this

@@ -38,7 +38,10 @@ api.pse_laplacian_plane(q.x, q.y, vq, q.area, q.is_active, q.max_edge_length ** 
 api.swe_plane_rhs_integrals(q.x, q.y, vq, 0.1 * vq, 1 + 0 * vq, q.area, q.is_active, q.max_edge_length ** 0.75)
 b = mesh.PolyMesh2d(mesh.BETA_PLANE_SEED, 3)
 zb = problems.betaplane_gaussian(b)
-api.betaplane_velocity(b.x, b.y, zb, b.area, b.is_active)
+for var in (0, 200, 201):
+    api.set_bve_variant(var)
+    api.betaplane_velocity(b.x, b.y, zb, b.area, b.is_active)
+api.set_bve_variant(0)
 api.betaplane_stream(b.x, b.y, zb, zb + 1, b.area, b.is_active)
 sph = solvers.BVEMesh(m, problems.gaussian_vortex(m), 1.0, 2 * np.pi)
 sph.velocity = list(api.bve_velocity(m.x, m.y, m.z, sph.relVort, m.area, m.is_active, 1.0))

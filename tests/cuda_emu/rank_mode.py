@@ -39,6 +39,9 @@ wants = O.bve_stream(m.x, m.y, m.z, zeta, av, m.area, m.is_active, 1.0)
 q = M.PolyMesh2d(M.QUAD_RECT_SEED, 3, 7.0)
 vq = problems.colliding_dipoles(q)
 wantq = O.plane_velocity(q.x, q.y, vq, q.area, q.is_active)
+bp = M.PolyMesh2d(M.BETA_PLANE_SEED, 3)
+zb = problems.betaplane_gaussian(bp)
+wantb = O.betaplane_velocity(bp.x, bp.y, zb, bp.area, bp.is_active, variant="_ld")
 for var in (0, 200, 201):
     api.set_bve_variant(var)
     got = api.bve_velocity(m.x, m.y, m.z, zeta, m.area, m.is_active, 1.0)
@@ -47,6 +50,8 @@ for var in (0, 200, 201):
     assert max(rel(g, w) for g, w in zip(gots, wants)) <= 1e-12, ("stream", var)
     gotq = api.plane_velocity(q.x, q.y, vq, q.area, q.is_active)
     assert max(rel(g, w) for g, w in zip(gotq, wantq)) <= 1e-12, ("plane", var)
+    gotb = api.betaplane_velocity(bp.x, bp.y, zb, bp.area, bp.is_active)
+    assert max(rel(g, w) for g, w in zip(gotb, wantb)) <= 1e-12, ("betaplane", var)
     # the resident solver: every array in one shared slab, four velocity sums and the stream functions per step
     zg = problems.gaussian_vortex(m)
     u0 = O.bve_velocity(m.x, m.y, m.z, zg, m.area, m.is_active, 1.0)

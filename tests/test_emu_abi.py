@@ -50,7 +50,8 @@ def test_symmetric_paths_on_emulator(emu_env):
     """lpm_set_bve_variant(200..203) through the real host code: velocity, stream functions, planar velocity."""
     tail = _run(emu_env, ["tests/test_sym_gpu.py", "-k",
                           "(random_ragged and not 20011 and not 4099 and not 6000) or plane_velocity_mesh and 3-20 "
-                          "or (4099 and (200 or 201) and velocity_random) or fenced_one_sided"], 900)
+                          "or (4099 and (200 or 201) and velocity_random) or fenced_one_sided "
+                          "or (betaplane_velocity and not 4-20) or betaplane_rk4"], 900)
     assert " passed" in tail and "failed" not in tail, tail
 
 

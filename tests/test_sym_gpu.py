@@ -117,6 +117,28 @@ def test_sym_plane_velocity_random_ragged(sym, oracle, n, frac, seed):
     _check(got, want, ld)
 
 
+@pytest.mark.parametrize("sym", [200, 201, 202, 203], indirect=True)
+@pytest.mark.parametrize("L", [2, 3, 4])
+def test_sym_betaplane_velocity(sym, oracle, get_mesh, L):
+    """As tests/test_parity_gpu.py::test_betaplane_velocity, through the symmetric path (ragged sizes: the beta-plane
+    meshes have 3/4 of their particles active and no power-of-two counts)."""
+    m = get_mesh(M.BETA_PLANE_SEED, L)
+    zeta = problems.betaplane_gaussian(m)
+    got = sym.betaplane_velocity(m.x, m.y, zeta, m.area, m.is_active)
+    ld = oracle.betaplane_velocity(m.x, m.y, zeta, m.area, m.is_active, variant="_ld")
+    f64 = oracle.betaplane_velocity(m.x, m.y, zeta, m.area, m.is_active)
+    for g, l, f in zip(got, ld, f64):
+        assert relerr(g, l) <= TOL
+        assert relerr(g, f) <= max(TOL, 2.0 * relerr(f, l) + 1e-14)
+
+
+@pytest.mark.parametrize("sym", [200], indirect=True)
+def test_sym_betaplane_rk4_step(sym, oracle, get_mesh):
+    """The resident beta-plane solver takes the symmetric path for its velocity sums."""
+    import test_parity_gpu as tp
+    tp.test_betaplane_rk4_step(sym, oracle, get_mesh)
+
+
 @pytest.mark.parametrize("sym", [200], indirect=True)
 def test_sym_matches_default_path(sym, get_mesh):
     """Same sum, other order: within a few ulp of the default kernel at icosTri 6."""
