@@ -3,11 +3,14 @@
 // completed when the call returns), events are wall-clock stamps.  LPM_EMU_DEVICES (default 1) emulated
 // devices share that memory, so peer stores simply work.
 #pragma once
+#include <dirent.h>
 #include <fcntl.h>
+#include <signal.h>
 #include <sys/mman.h>
 #include <sys/stat.h>
 #include <unistd.h>
 
+#include <cerrno>
 #include <chrono>
 #include <map>
 #include <mutex>
@@ -62,19 +65,50 @@ struct EmuAlloc { std::string name; size_t bytes; };
 inline std::map<void*, EmuAlloc>& emu_allocs() { static std::map<void*, EmuAlloc> m; return m; }
 inline std::map<void*, size_t>& emu_ipc_maps() { static std::map<void*, size_t> m; return m; }
 inline std::mutex& emu_alloc_mutex() { static std::mutex m; return m; }
+// Segments are unlinked by cudaFree, at exit for whatever the process still holds, and -- for processes that
+// were killed -- by the next emulated process that starts (names carry the owner's pid).
+struct EmuShmJanitor {
+    EmuShmJanitor()
+    {
+        if (DIR* d = opendir("/dev/shm")) {
+            while (dirent* e = readdir(d)) {
+                int pid = 0, k = 0;
+                if (std::sscanf(e->d_name, "lpmemu_%d_%d", &pid, &k) == 2 && pid > 0 && kill(pid, 0) != 0 && errno == ESRCH)
+                    shm_unlink((std::string("/") + e->d_name).c_str());
+            }
+            closedir(d);
+        }
+    }
+    ~EmuShmJanitor()
+    {
+        for (auto& a : emu_allocs())
+            if (!a.second.name.empty()) shm_unlink(a.second.name.c_str());
+    }
+};
+inline EmuShmJanitor& emu_janitor() { static EmuShmJanitor j; return j; }
 inline cudaError_t emu_malloc(void** p, size_t bytes)
 {
     static int counter = 0;
+    emu_allocs();           // constructed before the janitor, so destroyed after it
+    emu_janitor();
     std::lock_guard<std::mutex> lock(emu_alloc_mutex());
     if (bytes == 0) bytes = 1;
     char name[64];
     std::snprintf(name, sizeof(name), "/lpmemu_%d_%d", (int)getpid(), counter++);
+    // posix_fallocate reserves the pages now: a full /dev/shm must not turn into a SIGBUS at first touch.  If the
+    // segment cannot be had, fall back to private memory (such a buffer has no IPC handle).
+    void* q = MAP_FAILED;
     const int fd = shm_open(name, O_CREAT | O_EXCL | O_RDWR, 0600);
-    if (fd < 0) { *p = nullptr; return cudaErrorMemoryAllocation; }
-    if (ftruncate(fd, (off_t)bytes) != 0) { close(fd); shm_unlink(name); *p = nullptr; return cudaErrorMemoryAllocation; }
-    void* q = mmap(nullptr, bytes, PROT_READ | PROT_WRITE, MAP_SHARED, fd, 0);
-    close(fd);
-    if (q == MAP_FAILED) { shm_unlink(name); *p = nullptr; return cudaErrorMemoryAllocation; }
+    if (fd >= 0) {
+        if (posix_fallocate(fd, 0, (off_t)bytes) == 0) q = mmap(nullptr, bytes, PROT_READ | PROT_WRITE, MAP_SHARED, fd, 0);
+        close(fd);
+        if (q == MAP_FAILED) shm_unlink(name);
+    }
+    if (q == MAP_FAILED) {
+        name[0] = 0;
+        q = mmap(nullptr, bytes, PROT_READ | PROT_WRITE, MAP_PRIVATE | MAP_ANONYMOUS, -1, 0);
+        if (q == MAP_FAILED) { *p = nullptr; return cudaErrorMemoryAllocation; }
+    }
     std::memset(q, 0xdb, bytes);        // poison: nothing may rely on fresh device memory being zero
     emu_allocs()[q] = EmuAlloc{name, bytes};
     *p = q;
@@ -88,7 +122,7 @@ inline cudaError_t cudaFree(void* p)
     auto it = emu_allocs().find(p);
     if (it == emu_allocs().end()) return cudaErrorInvalidValue;
     munmap(p, it->second.bytes);
-    shm_unlink(it->second.name.c_str());
+    if (!it->second.name.empty()) shm_unlink(it->second.name.c_str());
     emu_allocs().erase(it);
     return cudaSuccess;
 }
@@ -120,7 +154,7 @@ inline cudaError_t cudaIpcGetMemHandle(cudaIpcMemHandle_t* h, void* p)
 {
     std::lock_guard<std::mutex> lock(emu_alloc_mutex());
     auto it = emu_allocs().find(p);
-    if (it == emu_allocs().end()) return cudaErrorInvalidValue;
+    if (it == emu_allocs().end() || it->second.name.empty()) return cudaErrorInvalidValue;
     std::memset(h, 0, sizeof(*h));
     std::snprintf(h->reserved, 48, "%s", it->second.name.c_str());
     const uint64_t bytes = it->second.bytes;
