@@ -219,43 +219,13 @@ struct SolverBase {
             for (int k = 0; k < Op::NIN; ++k) a.in[k] = r.A(in[k]);
             a.mask = r.mask.as<int32_t>();
             for (int k = 0; k < 3; ++k) a.sc[k] = sc ? sc[k] : 0.0;
-            if constexpr (std::is_same<Op, OpBveVel>::value) {
-                if (sym_applicable(variant, r.sb, r.se, n, r.mp, nrep)) {      // opt-in experiment (symmetric.cuh)
-                    Outs<3> o{};
-                    o.nrep = 1;
-                    for (int k = 0; k < 3; ++k) o.p[0][k] = r.A(out[k]);
-                    LPM_TRY(bve_velocity_sym(*r.dev, r.dev->stream, r.mp, a, o, variant));
+            {   // opt-in experiment (symmetric.cuh): the whole sum in pair-symmetric form
+                double* o[4] = {nullptr, nullptr, nullptr, nullptr};
+                for (int k = 0; k < Op::NOUT; ++k) o[k] = r.A(out[k]);
+                bool taken = false;
+                LPM_TRY(sym_try<Op>(*r.dev, r.dev->stream, r.mp, a, o, r.sb, r.se, n, nrep, &taken));
+                if (taken) {
                     exchanged = true;       // rank mode: every rank already holds all n results
-                    continue;
-                }
-            }
-            if constexpr (std::is_same<Op, OpPlaneVel>::value) {
-                if (sym_applicable(rt().bve_variant, r.sb, r.se, n, r.mp, nrep)) {
-                    Outs<2> o{};
-                    o.nrep = 1;
-                    for (int k = 0; k < 2; ++k) o.p[0][k] = r.A(out[k]);
-                    LPM_TRY(plane_velocity_sym(*r.dev, r.dev->stream, r.mp, a, o, rt().bve_variant));
-                    exchanged = true;
-                    continue;
-                }
-            }
-            if constexpr (std::is_same<Op, OpBetaVel>::value) {
-                if (sym_applicable(rt().bve_variant, r.sb, r.se, n, r.mp, nrep)) {
-                    Outs<2> o{};
-                    o.nrep = 1;
-                    for (int k = 0; k < 2; ++k) o.p[0][k] = r.A(out[k]);
-                    LPM_TRY(betaplane_velocity_sym(*r.dev, r.dev->stream, r.mp, a, o, rt().bve_variant));
-                    exchanged = true;
-                    continue;
-                }
-            }
-            if constexpr (std::is_same<Op, OpBveStream>::value) {
-                if (sym_applicable(variant, r.sb, r.se, n, r.mp, nrep)) {
-                    Outs<2> o{};
-                    o.nrep = 1;
-                    for (int k = 0; k < 2; ++k) o.p[0][k] = r.A(out[k]);
-                    LPM_TRY(bve_stream_sym(*r.dev, r.dev->stream, r.mp, a, o, variant));
-                    exchanged = true;
                     continue;
                 }
             }

@@ -95,12 +95,13 @@ __global__ void scatter_kernel(int64_t count, const int32_t* __restrict__ perm, 
     for (int r = 0; r < dst.nrep; ++r) dst.p[r][i] = v;
 }
 
-// experimental pair-symmetric BVE velocity (symmetric.cuh, included at the end of this file)
-inline int bve_velocity_sym(Device& dev, cudaStream_t st, MaskPlan& mp, const Args& a, const Outs<3>& out, int variant);
-inline int bve_stream_sym(Device& dev, cudaStream_t st, MaskPlan& mp, const Args& a, const Outs<2>& out, int variant);
-inline int plane_velocity_sym(Device& dev, cudaStream_t st, MaskPlan& mp, const Args& a, const Outs<2>& out, int variant);
-inline int betaplane_velocity_sym(Device& dev, cudaStream_t st, MaskPlan& mp, const Args& a, const Outs<2>& out, int variant);
-inline bool sym_applicable(int variant, int64_t tbeg, int64_t tend, int64_t nt, const MaskPlan& mp, int nrep);
+// Experimental pair-symmetric evaluation (symmetric.cuh, included at the end of this file): runs Op's sum that way
+// and sets *taken when lpm_set_bve_variant selects it, Op has a symmetric form and the call covers this device's /
+// rank's whole share of the targets.  out[k]: where the results go (this device's copy; in rank mode every rank
+// ends up with all n results, so nothing is left to exchange).
+template <class Op>
+inline int sym_try(Device& dev, cudaStream_t st, MaskPlan& mp, const Args& a, double* const* out, int64_t tbeg,
+                   int64_t tend, int64_t nt, int nrep, bool* taken);
 
 // (key, value) pairs sorted by key into ws.sort_vals[1]; returns that pointer
 inline int sort_by_cell(Device& dev, cudaStream_t st, int64_t count, int bits, uint32_t* keys_in, int32_t* vals_in,
@@ -150,37 +151,11 @@ inline int evaluate_impl(Device& dev, cudaStream_t st, MaskPlan& mp, const Args&
     bool sorted = false;
     if constexpr (K::CULL) sorted = mode != 0 && mp.nsrc > 2 * kTile && tend - tbeg > 0;
     if (!sorted) {
-        if constexpr (std::is_same<Op, OpBveVel>::value) {
-            if (sym_applicable(Op::variant(), tbeg, tend, nt, mp, 1)) {     // opt-in experiment, one device only
-                Outs<3> o{};
-                set_outs(o, out);
-                *exchanged = rt().rank_mode && rt().world > 1;      // every rank ends up with all n results
-                return bve_velocity_sym(dev, st, mp, a, o, Op::variant());
-            }
-        }
-        if constexpr (std::is_same<Op, OpBveStream>::value) {
-            if (sym_applicable(Op::variant(), tbeg, tend, nt, mp, 1)) {
-                Outs<2> o{};
-                set_outs(o, out);
-                *exchanged = rt().rank_mode && rt().world > 1;
-                return bve_stream_sym(dev, st, mp, a, o, Op::variant());
-            }
-        }
-        if constexpr (std::is_same<Op, OpPlaneVel>::value) {
-            if (sym_applicable(rt().bve_variant, tbeg, tend, nt, mp, 1)) {
-                Outs<2> o{};
-                set_outs(o, out);
-                *exchanged = rt().rank_mode && rt().world > 1;
-                return plane_velocity_sym(dev, st, mp, a, o, rt().bve_variant);
-            }
-        }
-        if constexpr (std::is_same<Op, OpBetaVel>::value) {
-            if (sym_applicable(rt().bve_variant, tbeg, tend, nt, mp, 1)) {
-                Outs<2> o{};
-                set_outs(o, out);
-                *exchanged = rt().rank_mode && rt().world > 1;
-                return betaplane_velocity_sym(dev, st, mp, a, o, rt().bve_variant);
-            }
+        bool taken = false;
+        LPM_TRY(sym_try<Op>(dev, st, mp, a, out, tbeg, tend, nt, 1, &taken));
+        if (taken) {
+            *exchanged = rt().rank_mode && rt().world > 1;
+            return LPM_OK;
         }
         LPM_TRY(Op::pack(dev, st, mp, a));
         typename K::Params prm = Op::params(a);

@@ -521,6 +521,108 @@ struct SymBetaVel : NoSharedTable {
     }
 };
 
+// Planar and beta-plane stream functions (PlaneStream, BetaStream in pairs.cuh): psi_i = sum_j w_j ln(arg_ij) with a
+// symmetric argument (r^2, resp. 2 (S^2 + s^2)), so the argument and its logarithm serve both directions; as
+// SymBveStream with the retry branch per source.  G supplies the geometry:
+//   NS, NW            doubles per record, weights per particle (1 or 2)
+//   Tgt, null(), from_record()
+//   arg(tgt, s)       the logarithm's argument for one pair;  tw(tgt, k), sw(s, k)  the k-th weight of target / source
+template <class G>
+struct SymLogStream : LogSharedTable<32> {
+    static constexpr int NS = G::NS, NA = G::NW, NC = G::NW;
+    using Tgt = typename G::Tgt;
+    __device__ static __forceinline__ Tgt null() { return G::null(); }
+    __device__ static __forceinline__ Tgt from_record(const double2* p2) { return G::from_record(p2); }
+    template <int T, int SB, int ORDER>
+    __device__ static __forceinline__ void batch(const SymParams&, const Tgt (&tg)[T], double (&a)[T][NA],
+                                                 const double* __restrict__ sm, double (&cb)[SB][NC], const SharedCtx& sc)
+    {
+#pragma unroll
+        for (int u = 0; u < SB; ++u) {
+            double s[NS], d[T], l[T];
+            const double2* p2 = reinterpret_cast<const double2*>(sm + u * NS);
+#pragma unroll
+            for (int q = 0; q < NS / 2; ++q) {
+                const double2 v = p2[q];
+                s[2 * q] = v.x; s[2 * q + 1] = v.y;
+            }
+            unsigned worst = 0;
+#pragma unroll
+            for (int t = 0; t < T; ++t) d[t] = G::arg(tg[t], s);
+            log_group_fast<KS, T>(d, l, worst, sc);
+            if (__builtin_expect(needs_retry(worst), 0)) {
+#pragma unroll
+                for (int t = 0; t < T; ++t) l[t] = log_slow_path(d[t]);
+            }
+#pragma unroll
+            for (int k = 0; k < NA; ++k) {
+#pragma unroll
+                for (int t = 0; t < T; ++t) a[t][k] = fma(l[t], G::sw(s, k), a[t][k]);
+                cb[u][k] = l[0] * G::tw(tg[0], k);
+#pragma unroll
+                for (int t = 1; t < T; ++t) cb[u][k] = fma(l[t], G::tw(tg[t], k), cb[u][k]);
+            }
+        }
+    }
+    template <int T>
+    __device__ static __forceinline__ void diag(const SymParams&, const Tgt (&tg)[T], double (&a)[T][NA],
+                                                const double (&s)[NS], const bool (&isself)[T], const SharedCtx& sc)
+    {
+        double d[T], l[T];
+#pragma unroll
+        for (int t = 0; t < T; ++t) {
+            d[t] = G::arg(tg[t], s);
+            d[t] = isself[t] ? 1.0 : d[t];          // any positive value; the pair is zeroed below
+        }
+        log_group<KS, T>(d, l, sc);
+#pragma unroll
+        for (int t = 0; t < T; ++t) {
+            l[t] = isself[t] ? 0.0 : l[t];
+#pragma unroll
+            for (int k = 0; k < NA; ++k) a[t][k] = fma(l[t], G::sw(s, k), a[t][k]);
+        }
+    }
+};
+// record x, y, omega A / (4 pi), 0;  arg = r^2
+struct PlaneStreamGeom {
+    static constexpr int NS = 4, NW = 1;
+    struct Tgt { double x, y, w; };
+    __device__ static __forceinline__ Tgt null() { return Tgt{-LPM_PLANE_FAR, -LPM_PLANE_FAR, 0.0}; }
+    __device__ static __forceinline__ Tgt from_record(const double2* p2)
+    {
+        const double2 v0 = p2[0], v1 = p2[1];
+        return Tgt{v0.x, v0.y, v1.x};
+    }
+    __device__ static __forceinline__ double arg(const Tgt& t, const double (&s)[NS])
+    {
+        const double dx = t.x - s[0], dy = t.y - s[1];
+        return fma(dx, dx, dy * dy);
+    }
+    __device__ static __forceinline__ double tw(const Tgt& t, int) { return t.w; }
+    __device__ static __forceinline__ double sw(const double (&s)[NS], int) { return s[2]; }
+};
+// record sinh(pi y), cosh(pi y), sin(pi x), cos(pi x), zeta A / (4 pi), omega A / (4 pi);  arg = 2 (S^2 + s^2)
+struct BetaStreamGeom {
+    static constexpr int NS = 6, NW = 2;
+    struct Tgt { double sh, ch, sn, cs, w0, w1; };
+    __device__ static __forceinline__ Tgt null() { return Tgt{-1.0e10, 1.0e10, 0.0, 1.0, 0.0, 0.0}; }
+    __device__ static __forceinline__ Tgt from_record(const double2* p2)
+    {
+        const double2 v0 = p2[0], v1 = p2[1], v2 = p2[2];
+        return Tgt{v0.x, v0.y, v1.x, v1.y, v2.x, v2.y};
+    }
+    __device__ static __forceinline__ double arg(const Tgt& t, const double (&s)[NS])
+    {
+        const double S = fma(t.sh, s[1], -(t.ch * s[0]));
+        const double sn = fma(t.sn, s[3], -(t.cs * s[2]));
+        return 2.0 * fma(S, S, sn * sn);
+    }
+    __device__ static __forceinline__ double tw(const Tgt& t, int k) { return k == 0 ? t.w0 : t.w1; }
+    __device__ static __forceinline__ double sw(const double (&s)[NS], int k) { return s[4 + k]; }
+};
+using SymPlaneStream = SymLogStream<PlaneStreamGeom>;
+using SymBetaStream = SymLogStream<BetaStreamGeom>;
+
 // ---- the kernel ---------------------------------------------------------------
 // acc: [nsrc_pad][NC] doubles, zeroed by the caller (NA == NC: both directions feed the same sums).
 // dynamic shared memory: [2 tiles][K::KS table][2 mbarriers]
@@ -657,6 +759,15 @@ sym_stream_finalize(int32_t nsrc, const int32_t* __restrict__ active, const doub
     const int64_t i = active[c];
     out.store(0, i, acc[(size_t)c * 2]);
     out.store(1, i, acc[(size_t)c * 2 + 1]);
+}
+
+// one sum per active particle, copied out (PlaneStream::finalize)
+__global__ void __launch_bounds__(256)
+sym_copy1_finalize(int32_t nsrc, const int32_t* __restrict__ active, const double* __restrict__ acc, Outs<1> out)
+{
+    const int32_t c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= nsrc) return;
+    out.store(0, active[c], acc[c]);
 }
 
 // passive[i - scan[i]] = i for every particle with mask 0 (stable, like the active list)

@@ -159,6 +159,40 @@ struct SymBeta {
     }
 };
 
+// Planar / beta-plane stream functions: 256 threads (variants 200, 202) or 128 (201, 203), retry branch per source
+struct SymPlaneStr {
+    using Op = OpPlaneStream;
+    using SK = SymPlaneStream;
+    static constexpr int NCOORD = 2;
+    static void sym_params(SymParams&, const Args&) {}
+    static void passive_params(PlaneStream::Params& p, const double* const* xy, const Args&) { p.x = xy[0]; p.y = xy[1]; }
+    static int launch(int variant, cudaStream_t st, const SymParams& prm, const SymGeom& g, const double* src, double* acc)
+    {
+        if ((variant - kSymVariant) & 1) return launch_sym<SK, 4, 128, 4, 2, 0>(st, prm, g, src, acc);
+        return launch_sym<SK, 4, 256, 4, 2, 0>(st, prm, g, src, acc);
+    }
+    static void finalize(cudaStream_t st, const MaskPlan& mp, const double*, const double* acc, const Outs<1>& out)
+    {
+        sym_copy1_finalize<<<(unsigned)((mp.nsrc + 255) / 256), 256, 0, st>>>(mp.nsrc, mp.active.as<int32_t>(), acc, out);
+    }
+};
+struct SymBetaStr {
+    using Op = OpBetaStream;
+    using SK = SymBetaStream;
+    static constexpr int NCOORD = 2;
+    static void sym_params(SymParams&, const Args&) {}
+    static void passive_params(BetaStream::Params& p, const double* const* xy, const Args&) { p.x = xy[0]; p.y = xy[1]; }
+    static int launch(int variant, cudaStream_t st, const SymParams& prm, const SymGeom& g, const double* src, double* acc)
+    {
+        if ((variant - kSymVariant) & 1) return launch_sym<SK, 4, 128, 4, 2, 0>(st, prm, g, src, acc);
+        return launch_sym<SK, 4, 256, 4, 2, 0>(st, prm, g, src, acc);
+    }
+    static void finalize(cudaStream_t st, const MaskPlan& mp, const double*, const double* acc, const Outs<2>& out)
+    {
+        sym_stream_finalize<<<(unsigned)((mp.nsrc + 255) / 256), 256, 0, st>>>(mp.nsrc, mp.active.as<int32_t>(), acc, out);
+    }
+};
+
 // Whole evaluation: one device, or -- rank mode -- collectively on every rank (each must call with its
 // LoadBalance slice, sym_applicable() checks that): target blocks of the active x active part are dealt
 // round-robin to the ranks and the accumulators summed with one ncclAllReduce (NC F doubles); the passive
@@ -267,23 +301,6 @@ inline int sym_evaluate(Device& dev, cudaStream_t st, MaskPlan& mp, const Args& 
     return rc;
 }
 
-inline int bve_velocity_sym(Device& dev, cudaStream_t st, MaskPlan& mp, const Args& a, const Outs<3>& out, int variant)
-{
-    return sym_evaluate<SymVel>(dev, st, mp, a, out, variant);
-}
-inline int bve_stream_sym(Device& dev, cudaStream_t st, MaskPlan& mp, const Args& a, const Outs<2>& out, int variant)
-{
-    return sym_evaluate<SymStream>(dev, st, mp, a, out, variant);
-}
-inline int plane_velocity_sym(Device& dev, cudaStream_t st, MaskPlan& mp, const Args& a, const Outs<2>& out, int variant)
-{
-    return sym_evaluate<SymPlane>(dev, st, mp, a, out, variant);
-}
-inline int betaplane_velocity_sym(Device& dev, cudaStream_t st, MaskPlan& mp, const Args& a, const Outs<2>& out, int variant)
-{
-    return sym_evaluate<SymBeta>(dev, st, mp, a, out, variant);
-}
-
 // May this evaluation take the symmetric path?  One device driving every target, or rank mode with this
 // rank's LoadBalance slice (then every rank reaches the same answer and the collectives inside match up).
 inline bool sym_applicable(int variant, int64_t tbeg, int64_t tend, int64_t nt, const MaskPlan& mp, int nrep)
@@ -293,6 +310,32 @@ inline bool sym_applicable(int variant, int64_t tbeg, int64_t tend, int64_t nt, 
     int64_t b = 0, e = nt;
     if (R.rank_mode && R.world > 1) load_balance0(nt, R.world, R.rank, &b, &e);
     return tbeg == b && tend == e;
+}
+
+// Which sums have a symmetric form.
+template <class Op> struct SymFor { using type = void; };
+template <> struct SymFor<OpBveVel> { using type = SymVel; };
+template <> struct SymFor<OpBveStream> { using type = SymStream; };
+template <> struct SymFor<OpPlaneVel> { using type = SymPlane; };
+template <> struct SymFor<OpPlaneStream> { using type = SymPlaneStr; };
+template <> struct SymFor<OpBetaVel> { using type = SymBeta; };
+template <> struct SymFor<OpBetaStream> { using type = SymBetaStr; };
+
+template <class Op>
+inline int sym_try(Device& dev, cudaStream_t st, MaskPlan& mp, const Args& a, double* const* out, int64_t tbeg,
+                   int64_t tend, int64_t nt, int nrep, bool* taken)
+{
+    using S = typename SymFor<Op>::type;
+    *taken = false;
+    if constexpr (!std::is_void<S>::value) {
+        const int variant = rt().bve_variant;
+        if (!sym_applicable(variant, tbeg, tend, nt, mp, nrep)) return LPM_OK;
+        Outs<Op::NOUT> o{};
+        set_outs(o, out);
+        LPM_TRY(sym_evaluate<S>(dev, st, mp, a, o, variant));
+        *taken = true;
+    }
+    return LPM_OK;
 }
 
 }  // namespace lpm

@@ -41,6 +41,8 @@ zb = problems.betaplane_gaussian(b)
 for var in (0, 200, 201):
     api.set_bve_variant(var)
     api.betaplane_velocity(b.x, b.y, zb, b.area, b.is_active)
+    api.betaplane_stream(b.x, b.y, zb, zb + 1, b.area, b.is_active)
+    api.plane_stream(q.x, q.y, vq, q.area, q.is_active)
 api.set_bve_variant(0)
 api.betaplane_stream(b.x, b.y, zb, zb + 1, b.area, b.is_active)
 sph = solvers.BVEMesh(m, problems.gaussian_vortex(m), 1.0, 2 * np.pi)

@@ -42,6 +42,8 @@ wantq = O.plane_velocity(q.x, q.y, vq, q.area, q.is_active)
 bp = M.PolyMesh2d(M.BETA_PLANE_SEED, 3)
 zb = problems.betaplane_gaussian(bp)
 wantb = O.betaplane_velocity(bp.x, bp.y, zb, bp.area, bp.is_active, variant="_ld")
+wantqs = O.plane_stream(q.x, q.y, vq, q.area, q.is_active)
+wantbs = O.betaplane_stream(bp.x, bp.y, zb, zb + 1.0 + 2.0 * bp.y, bp.area, bp.is_active, variant="_ld")
 for var in (0, 200, 201):
     api.set_bve_variant(var)
     got = api.bve_velocity(m.x, m.y, m.z, zeta, m.area, m.is_active, 1.0)
@@ -52,6 +54,9 @@ for var in (0, 200, 201):
     assert max(rel(g, w) for g, w in zip(gotq, wantq)) <= 1e-12, ("plane", var)
     gotb = api.betaplane_velocity(bp.x, bp.y, zb, bp.area, bp.is_active)
     assert max(rel(g, w) for g, w in zip(gotb, wantb)) <= 1e-12, ("betaplane", var)
+    assert rel(api.plane_stream(q.x, q.y, vq, q.area, q.is_active), wantqs) <= 1e-12, ("plane stream", var)
+    gotbs = api.betaplane_stream(bp.x, bp.y, zb, zb + 1.0 + 2.0 * bp.y, bp.area, bp.is_active)
+    assert max(rel(g, w) for g, w in zip(gotbs, wantbs)) <= 1e-12, ("betaplane stream", var)
     # the resident solver: every array in one shared slab, four velocity sums and the stream functions per step
     zg = problems.gaussian_vortex(m)
     u0 = O.bve_velocity(m.x, m.y, m.z, zg, m.area, m.is_active, 1.0)

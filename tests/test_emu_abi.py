@@ -51,7 +51,7 @@ def test_symmetric_paths_on_emulator(emu_env):
     tail = _run(emu_env, ["tests/test_sym_gpu.py", "-k",
                           "(random_ragged and not 20011 and not 4099 and not 6000) or plane_velocity_mesh and 3-20 "
                           "or (4099 and (200 or 201) and velocity_random) or fenced_one_sided "
-                          "or (betaplane_velocity and not 4-20) or betaplane_rk4"], 900)
+                          "or (betaplane_velocity and not 4-20) or betaplane_rk4 or plane_and_betaplane_stream or plane_rk4"], 900)
     assert " passed" in tail and "failed" not in tail, tail
 
 

@@ -132,6 +132,31 @@ def test_sym_betaplane_velocity(sym, oracle, get_mesh, L):
         assert relerr(g, f) <= max(TOL, 2.0 * relerr(f, l) + 1e-14)
 
 
+@pytest.mark.parametrize("sym", [200, 201], indirect=True)
+def test_sym_plane_and_betaplane_stream(sym, oracle, get_mesh):
+    """The planar and beta-plane stream functions through the generic symmetric log kernel (SymLogStream)."""
+    q = get_mesh(M.QUAD_RECT_SEED, 4, 7.0)
+    vq = problems.colliding_dipoles(q)
+    got = sym.plane_stream(q.x, q.y, vq, q.area, q.is_active)
+    assert relerr(got, oracle.plane_stream(q.x, q.y, vq, q.area, q.is_active)) <= TOL
+    m = get_mesh(M.BETA_PLANE_SEED, 4)
+    zeta = problems.betaplane_gaussian(m)
+    absv = zeta + 1.0 + 2.0 * m.y
+    gotb = sym.betaplane_stream(m.x, m.y, zeta, absv, m.area, m.is_active)
+    ld = oracle.betaplane_stream(m.x, m.y, zeta, absv, m.area, m.is_active, variant="_ld")
+    f64 = oracle.betaplane_stream(m.x, m.y, zeta, absv, m.area, m.is_active)
+    for g, l, f in zip(gotb, ld, f64):
+        assert relerr(g, l) <= TOL
+        assert relerr(g, f) <= 1e-11
+
+
+@pytest.mark.parametrize("sym", [200], indirect=True)
+def test_sym_plane_rk4_steps(sym, oracle, get_mesh):
+    """The resident planar solver: symmetric velocity sums and stream function."""
+    import test_parity_gpu as tp
+    tp.test_plane_rk4_steps(sym, oracle, get_mesh)
+
+
 @pytest.mark.parametrize("sym", [200], indirect=True)
 def test_sym_betaplane_rk4_step(sym, oracle, get_mesh):
     """The resident beta-plane solver takes the symmetric path for its velocity sums."""

@@ -49,4 +49,23 @@ for L in levels:
         diff = max(np.abs(a - b).max() for a, b in zip(out, ref)) / scale
         print(f"quadRect L{L + 1} plane_velocity variant {var}: sum ms " + " ".join(f"{t:.3f}" for t in ts) +
               f"  -> {pairs / min(ts) / 1e9:.1f} G interactions/s, max diff from variant {variants[0]}: {diff:.2e}", flush=True)
+for L in levels:
+    b = mesh.PolyMesh2d(mesh.BETA_PLANE_SEED, L)
+    zb = problems.betaplane_gaussian(b)
+    pairs = b.n * b.n_active - b.n_active
+    for name, fn in (("betaplane_velocity", lambda: api.betaplane_velocity(b.x, b.y, zb, b.area, b.is_active)),
+                     ("betaplane_stream", lambda: api.betaplane_stream(b.x, b.y, zb, zb + 1.0, b.area, b.is_active))):
+        ref = None
+        for var in variants:
+            api.set_bve_variant(var)
+            ts = []
+            for _ in range(3):
+                out = fn()
+                ts.append(api.last_sum_ms())
+            if ref is None:
+                ref = out
+            scale = max(np.abs(r).max() for r in ref)
+            diff = max(np.abs(a - c).max() for a, c in zip(out, ref)) / scale
+            print(f"betaPlane L{L} {name} variant {var}: sum ms " + " ".join(f"{t:.3f}" for t in ts) +
+                  f"  -> {pairs / min(ts) / 1e9:.1f} G interactions/s, max diff from variant {variants[0]}: {diff:.2e}", flush=True)
 api.set_bve_variant(0)
