@@ -94,11 +94,12 @@ struct Workspace {
     DevBuf logwin;      // int32 [2]: max |coordinate| high word, window origin of the log table (pairs.cuh)
     // spatially sorted PSE evaluation (sorted.cuh)
     DevBuf sort_tmp, sort_keys[2], sort_vals[2], sorted_active, sorted_targets, gathered[8], sorted_out[4];
-    DevBuf sym_acc;     // double [nsrc_pad][3]: accumulators of the experimental symmetric BVE path (symmetric.cuh)
+    DevBuf sym_acc;     // accumulators of the experimental symmetric paths (symmetric.cuh): doubles or fixed-point limbs
+    DevBuf sym_acc2, sym_fx;    // fixed-point mode: the accumulators as doubles; window scale (2 doubles) + max high word
     void release()
     {
         plan.release(); sources.release(); partial.release(); bounds.release();
-        reduce.release(); logwin.release(); barrier.release(); sym_acc.release();
+        reduce.release(); logwin.release(); barrier.release(); sym_acc.release(); sym_acc2.release(); sym_fx.release();
         for (auto& so : shared_out) so = SharedOut{};      // the slabs themselves are freed by the runtime
         sort_tmp.release(); sorted_active.release(); sorted_targets.release();
         for (auto& s : sort_keys) s.release();

@@ -20,14 +20,42 @@ struct SymGeom {
 // kernel-wide constants of the symmetric functors
 struct SymParams : LogParams {
     double R2;
+    const double* fx;       // fixed-point accumulation: fx[0] = 2^-E0 (see sym_red_add), or nullptr for FP64 atomics
 };
+
+// ---- order-independent accumulation ------------------------------------------------------------
+// RED.ADD.F64 makes the result depend on the order in which the CTAs' contributions land.  Every value that
+// reaches a RED here is itself deterministic (a fixed (block, tile, warp) computes it in a fixed order), so adding
+// those values EXACTLY makes the total independent of the order -- and of how the blocks were dealt to ranks.
+// With fx set, an accumulator is kFxLimbs signed 64-bit limbs, limb k counting units of 2^(E0 + 40 k): a value is
+// split into (at most three non-zero) 40-bit pieces and each is added with an integer atomic; what lies below
+// 2^E0 -- 240 bits under the top of the window, chosen per evaluation by sym_fx_scale_kernel -- is dropped.
+constexpr int kFxLimbs = 6;
+__device__ __forceinline__ void sym_red_add(double* acc, size_t idx, double v, const double* __restrict__ fx)
+{
+    if (fx == nullptr) {
+        atomicAdd(acc + idx, v);
+        return;
+    }
+    unsigned long long* a = reinterpret_cast<unsigned long long*>(acc) + idx * kFxLimbs;
+    constexpr double unit[kFxLimbs] = {0x1p0, 0x1p40, 0x1p80, 0x1p120, 0x1p160, 0x1p200};
+    constexpr double inv[kFxLimbs] = {0x1p0, 0x1p-40, 0x1p-80, 0x1p-120, 0x1p-160, 0x1p-200};
+    double r = v * fx[0];                   // a power of two: exact
+#pragma unroll
+    for (int k = kFxLimbs - 1; k >= 0; --k) {
+        const double t = trunc(r * inv[k]);
+        r = fma(-t, unit[k], r);            // exact: t unit[k] is the part of r at and above 2^(40 k)
+        if (t != 0.0) atomicAdd(a + k, (unsigned long long)(long long)t);
+    }
+}
 
 // Warp reduction of cb[s][a] (thread-local sums for SB sources, NC <= 3 components) by recursive
 // halving, then one RED per (source, component) from the lane that ends up owning it.
 // After the halving levels lane l holds source ((l >> (5 - LV)) & (SB - 1)) summed over the lanes
 // that differ from it in the high LV bits; a butterfly over the remaining low bits finishes the sum.
 template <int SB, int NC>
-__device__ __forceinline__ void sym_reduce_red(double (&cb)[SB][NC], int lane, double* __restrict__ accj)
+__device__ __forceinline__ void sym_reduce_red(double (&cb)[SB][NC], int lane, double* __restrict__ acc, size_t idx0,
+                                               const double* __restrict__ fx)
 {
     static_assert(SB == 8 || SB == 4, "source batch");
     static_assert(NC >= 1 && NC <= 3, "components per source");
@@ -66,7 +94,7 @@ __device__ __forceinline__ void sym_reduce_red(double (&cb)[SB][NC], int lane, d
         }
         sidx = (lane >> 2) & 7;
         const int q = lane & 3;
-        if (q < NC) atomicAdd(accj + sidx * NC + q, q == 0 ? v[0] : (q == 1 ? v[NC > 1 ? 1 : 0] : v[NC > 2 ? 2 : 0]));
+        if (q < NC) sym_red_add(acc, idx0 + sidx * NC + q, q == 0 ? v[0] : (q == 1 ? v[NC > 1 ? 1 : 0] : v[NC > 2 ? 2 : 0]), fx);
     } else {
         const bool b4 = (lane & 16) != 0, b3 = (lane & 8) != 0;
         double v2[2][NC];
@@ -92,7 +120,7 @@ __device__ __forceinline__ void sym_reduce_red(double (&cb)[SB][NC], int lane, d
         }
         sidx = (lane >> 3) & 3;
         const int q = lane & 7;
-        if (q < NC) atomicAdd(accj + sidx * NC + q, q == 0 ? v[0] : (q == 1 ? v[NC > 1 ? 1 : 0] : v[NC > 2 ? 2 : 0]));
+        if (q < NC) sym_red_add(acc, idx0 + sidx * NC + q, q == 0 ? v[0] : (q == 1 ? v[NC > 1 ? 1 : 0] : v[NC > 2 ? 2 : 0]), fx);
     }
 }
 
@@ -624,7 +652,8 @@ using SymPlaneStream = SymLogStream<PlaneStreamGeom>;
 using SymBetaStream = SymLogStream<BetaStreamGeom>;
 
 // ---- the kernel ---------------------------------------------------------------
-// acc: [nsrc_pad][NC] doubles, zeroed by the caller (NA == NC: both directions feed the same sums).
+// acc: [nsrc_pad][NC] doubles -- or, with prm.fx, [nsrc_pad][NC][kFxLimbs] 64-bit limbs -- zeroed by the caller
+// (NA == NC: both directions feed the same sums).
 // dynamic shared memory: [2 tiles][K::KS table][2 mbarriers]
 template <class K, int T, int BLOCK, int SB, int MINB, int ORDER = 0>
 __global__ void __launch_bounds__(BLOCK, MINB)
@@ -698,12 +727,11 @@ sym_kernel(const SymParams prm, const SymGeom g, const double* __restrict__ src,
     // a tile above the diagonal: every pair once, both directions
     auto sym_tile = [&](const int k, const int st) {
         const double* sm = tile[st];
-        double* accj = acc + (size_t)k * TS * NC;
 #pragma unroll 1
         for (int jb = 0; jb < TS; jb += SB) {
             double cb[SB][NC];
             K::template batch<T, SB, ORDER>(prm, tg, a, sm + jb * NS, cb, sctx);
-            sym_reduce_red<SB, NC>(cb, lane, accj + jb * NC);
+            sym_reduce_red<SB, NC>(cb, lane, acc, ((size_t)k * TS + jb) * NC, prm.fx);
         }
     };
 
@@ -725,7 +753,7 @@ sym_kernel(const SymParams prm, const SymGeom g, const double* __restrict__ src,
     for (int t = 0; t < T; ++t)
         if (cidx[t] < g.nsrc) {
 #pragma unroll
-            for (int q = 0; q < NA; ++q) atomicAdd(acc + (size_t)cidx[t] * NA + q, a[t][q]);
+            for (int q = 0; q < NA; ++q) sym_red_add(acc, (size_t)cidx[t] * NA + q, a[t][q], prm.fx);
         }
 }
 
@@ -733,6 +761,47 @@ template <class K, int T, int BLOCK>
 constexpr size_t sym_smem_bytes()
 {
     return 2 * size_t(kTile) * K::NS * sizeof(double) + sizeof(double) * K::KS + 2 * sizeof(uint64_t);
+}
+
+// Window of the fixed-point accumulators for one evaluation.  maxhi: high word of the largest |entry| of the source
+// records (coordinates and strengths; absmax_hi_kernel).  mode 0 (velocity): |sum| <= F M / d_min with
+// d_min >= R^2 2^-110 (two FP64 points cannot be closer); mode 1 (stream functions): |ln| < 2^10.  The top of the
+// window sits there, E0 240 bits below.  fx[0] = 2^-E0, fx[1] = 2^E0.
+__global__ void sym_fx_scale_kernel(int mode, double R2, int32_t nsrc, const int32_t* __restrict__ maxhi, double* __restrict__ fx)
+{
+    const int eM = ((*maxhi >> 20) & 0x7ff) - 1023 + 1;
+    int eF = 1;
+    while ((1 << eF) < nsrc && eF < 31) ++eF;
+    const int eR = ((__double2hiint(R2) >> 20) & 0x7ff) - 1023;
+    int top = eM + eF + (mode == 0 ? 110 - eR : 12);
+    int e0 = top - 40 * kFxLimbs;
+    if (e0 > 700) e0 = 700;
+    if (e0 < -900) e0 = -900;
+    fx[0] = __hiloint2double((1023 - e0) << 20, 0);
+    fx[1] = __hiloint2double((1023 + e0) << 20, 0);
+}
+
+// limbs -> doubles: carries first (so that every limb but the top one is below 2^40), then the sum from the top
+__global__ void __launch_bounds__(256)
+sym_fx_to_double_kernel(int64_t nvalues, const long long* __restrict__ limbs, const double* __restrict__ fx,
+                        double* __restrict__ out)
+{
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nvalues) return;
+    long long l[kFxLimbs];
+#pragma unroll
+    for (int k = 0; k < kFxLimbs; ++k) l[k] = limbs[i * kFxLimbs + k];
+#pragma unroll
+    for (int k = 0; k + 1 < kFxLimbs; ++k) {
+        const long long carry = l[k] >> 40;         // arithmetic shift: floor
+        l[k] -= carry << 40;
+        l[k + 1] += carry;
+    }
+    constexpr double unit[kFxLimbs] = {0x1p0, 0x1p40, 0x1p80, 0x1p120, 0x1p160, 0x1p200};
+    double s = 0.0;
+#pragma unroll
+    for (int k = kFxLimbs - 1; k >= 0; --k) s = fma((double)l[k], unit[k], s);
+    out[i] = s * fx[1];
 }
 
 // u_i = x_i cross a_i for the active particles (BveVelT::finalize)

@@ -36,7 +36,8 @@ namespace lpm {
 //   stream functions  200: 256 threads, retry branch per source (ORDER 1)    201: 128 threads, retry per batch (ORDER 0)
 //                     202: 256 threads, retry per batch                      203: 128 threads, retry per source
 constexpr int kSymVariant = 200;
-constexpr int kSymVariantLast = 203;
+constexpr int kSymVariantLast = 205;        // 204, 205: shapes 200, 201 with fixed-point (order-independent) accumulation
+constexpr int kSymVariantFx = 204;
 
 template <class K, int T, int BLOCK, int SB, int MINB, int ORDER = 0>
 inline int launch_sym(cudaStream_t st, const SymParams& prm, SymGeom g, const double* src, double* acc)
@@ -65,6 +66,7 @@ struct SymVel {
     using Op = OpBveVel;
     using SK = SymBveVel;
     static constexpr int NCOORD = 3;
+    static constexpr int FX_MODE = 0;       // fixed-point window from F max|P| / (R^2 2^-110)
     static void sym_params(SymParams& p, const Args& a) { p.R2 = a.sc[0] * a.sc[0]; }
     static void passive_params(BveVel::Params& p, const double* const* xyz, const Args& a)
     {
@@ -75,7 +77,7 @@ struct SymVel {
     {
         // orders picked with the operand-delivery model (tools/sym_score.py): modelled 15.9 / 15.1 / 17.1 / 16.7
         // cycles per interaction per SM sub-partition (the default one-sided kernel: 20.8 modelled, 20.3 measured)
-        switch (variant - kSymVariant) {
+        switch ((variant - kSymVariant) & 3) {
             case 1: return launch_sym<SK, 8, 128, 4, 1, 35>(st, prm, g, src, acc);
             case 2: return launch_sym<SK, 4, 128, 8, 2, 27>(st, prm, g, src, acc);
             case 3: return launch_sym<SK, 8, 128, 4, 1, 27>(st, prm, g, src, acc);
@@ -91,6 +93,7 @@ struct SymStream {
     using Op = OpBveStream;
     using SK = SymBveStream;
     static constexpr int NCOORD = 3;
+    static constexpr int FX_MODE = 1;       // fixed-point window from F max|w| 2^12
     static void sym_params(SymParams& p, const Args& a) { p.R2 = a.sc[0] * a.sc[0]; }
     static void passive_params(BveStream::Params& p, const double* const* xyz, const Args& a)
     {
@@ -102,7 +105,7 @@ struct SymStream {
         // 64 KB table per CTA, so two CTAs per SM either way: 256 threads under a 128-register cap (121 registers
         // with the per-source retry; the per-batch retry spills 24 bytes there) or 128 threads with ~155.
         // Modelled 17.7 / 18.9 / 18.9 / 18.4 cycles per interaction (the one-sided kernel: 29.6 modelled, 32.3 measured).
-        switch (variant - kSymVariant) {
+        switch ((variant - kSymVariant) & 3) {
             case 1: return launch_sym<SK, 4, 128, 4, 2, 0>(st, prm, g, src, acc);
             case 2: return launch_sym<SK, 4, 256, 4, 2, 0>(st, prm, g, src, acc);
             case 3: return launch_sym<SK, 4, 128, 4, 2, 1>(st, prm, g, src, acc);
@@ -117,6 +120,7 @@ struct SymStream {
 
 // Planar Biot-Savart (variants as for the BVE velocity: 200 / 201 fenced, 202 / 203 not)
 struct SymPlane {
+    static constexpr int FX_MODE = -1;      // FP64 atomics only
     using Op = OpPlaneVel;
     using SK = SymPlaneVel;
     static constexpr int NCOORD = 2;
@@ -124,7 +128,7 @@ struct SymPlane {
     static void passive_params(PlaneVel::Params& p, const double* const* xy, const Args&) { p.x = xy[0]; p.y = xy[1]; }
     static int launch(int variant, cudaStream_t st, const SymParams& prm, const SymGeom& g, const double* src, double* acc)
     {
-        switch (variant - kSymVariant) {
+        switch ((variant - kSymVariant) & 3) {
             case 1: return launch_sym<SK, 8, 128, 4, 1, 1>(st, prm, g, src, acc);
             case 2: return launch_sym<SK, 4, 128, 8, 2, 0>(st, prm, g, src, acc);
             case 3: return launch_sym<SK, 8, 128, 4, 1, 0>(st, prm, g, src, acc);
@@ -139,6 +143,7 @@ struct SymPlane {
 
 // Beta-plane Biot-Savart
 struct SymBeta {
+    static constexpr int FX_MODE = -1;      // FP64 atomics only
     using Op = OpBetaVel;
     using SK = SymBetaVel;
     static constexpr int NCOORD = 2;
@@ -146,7 +151,7 @@ struct SymBeta {
     static void passive_params(BetaVel::Params& p, const double* const* xy, const Args&) { p.x = xy[0]; p.y = xy[1]; }
     static int launch(int variant, cudaStream_t st, const SymParams& prm, const SymGeom& g, const double* src, double* acc)
     {
-        switch (variant - kSymVariant) {
+        switch ((variant - kSymVariant) & 3) {
             case 1: return launch_sym<SK, 4, 128, 4, 2, 1>(st, prm, g, src, acc);
             case 2: return launch_sym<SK, 4, 128, 8, 2, 0>(st, prm, g, src, acc);
             case 3: return launch_sym<SK, 4, 128, 4, 2, 0>(st, prm, g, src, acc);
@@ -161,6 +166,7 @@ struct SymBeta {
 
 // Planar / beta-plane stream functions: 256 threads (variants 200, 202) or 128 (201, 203), retry branch per source
 struct SymPlaneStr {
+    static constexpr int FX_MODE = -1;      // FP64 atomics only
     using Op = OpPlaneStream;
     using SK = SymPlaneStream;
     static constexpr int NCOORD = 2;
@@ -177,6 +183,7 @@ struct SymPlaneStr {
     }
 };
 struct SymBetaStr {
+    static constexpr int FX_MODE = -1;      // FP64 atomics only
     using Op = OpBetaStream;
     using SK = SymBetaStream;
     static constexpr int NCOORD = 2;
@@ -237,14 +244,36 @@ inline int sym_evaluate(Device& dev, cudaStream_t st, MaskPlan& mp, const Args& 
         // ---- active x active
         if (mp.nsrc > 0) {
             const size_t nacc = (size_t)g.nsrc_pad * SK::NC;
-            LPM_TRY(ws.sym_acc.reserve(nacc * sizeof(double)));
-            LPM_CUDA(cudaMemsetAsync(ws.sym_acc.p, 0, nacc * sizeof(double), st));
+            const bool fx = S::FX_MODE >= 0 && variant >= kSymVariantFx;
+            const size_t acc_bytes = nacc * sizeof(double) * (fx ? kFxLimbs : 1);
+            LPM_TRY(ws.sym_acc.reserve(acc_bytes));
+            LPM_CUDA(cudaMemsetAsync(ws.sym_acc.p, 0, acc_bytes, st));
+            const double* acc_final = ws.sym_acc.as<double>();
+            if (fx) {       // the window of the fixed-point accumulators, from the largest entry of the records
+                LPM_TRY(ws.sym_fx.reserve(4 * sizeof(double)));
+                LPM_TRY(ws.sym_acc2.reserve(nacc * sizeof(double)));
+                int32_t* maxhi = reinterpret_cast<int32_t*>(ws.sym_fx.as<double>() + 2);
+                LPM_CUDA(cudaMemsetAsync(maxhi, 0, sizeof(int32_t), st));
+                const int64_t nrec = (int64_t)g.nsrc_pad * SK::NS;
+                const unsigned nb = (unsigned)std::min<int64_t>((nrec + 255) / 256, 4 * (int64_t)dev.sm_count);
+                absmax_hi_kernel<<<nb, 256, 0, st>>>(nrec, src, nullptr, maxhi);
+                sym_fx_scale_kernel<<<1, 1, 0, st>>>(S::FX_MODE, prm.R2, mp.nsrc, maxhi, ws.sym_fx.as<double>());
+                count_launch(2);
+                prm.fx = ws.sym_fx.as<double>();
+            }
             LPM_TRY(S::launch(variant, st, prm, g, src, ws.sym_acc.as<double>()));
             if (g.world > 1) {
                 if (!R.comm) return set_error(LPM_ERR_COMM, "world size %d but no communicator (lpm_comm_init_rank)", R.world);
-                LPM_NCCL(nccl().AllReduce(ws.sym_acc.p, ws.sym_acc.p, nacc, /*ncclDouble*/ 8, /*ncclSum*/ 0, R.comm, st));
+                if (fx) LPM_NCCL(nccl().AllReduce(ws.sym_acc.p, ws.sym_acc.p, nacc * kFxLimbs, /*ncclInt64*/ 4, /*ncclSum*/ 0, R.comm, st));
+                else LPM_NCCL(nccl().AllReduce(ws.sym_acc.p, ws.sym_acc.p, nacc, /*ncclDouble*/ 8, /*ncclSum*/ 0, R.comm, st));
             }
-            S::finalize(st, mp, src, ws.sym_acc.as<double>(), out);
+            if (fx) {
+                sym_fx_to_double_kernel<<<(unsigned)((nacc + 255) / 256), 256, 0, st>>>((int64_t)nacc, ws.sym_acc.as<long long>(),
+                                                                                     ws.sym_fx.as<double>(), ws.sym_acc2.as<double>());
+                count_launch();
+                acc_final = ws.sym_acc2.as<double>();
+            }
+            S::finalize(st, mp, src, acc_final, out);
             count_launch(2);
         }
         // ---- passive targets x all active sources: the one-sided engine on the gathered passive particles

@@ -94,6 +94,10 @@ inline double atomicAdd(double* p, double v)
         if (__atomic_compare_exchange_n(u, &old, nb, false, __ATOMIC_ACQ_REL, __ATOMIC_RELAXED)) return o;
     }
 }
+inline unsigned long long atomicAdd(unsigned long long* p, unsigned long long v)
+{
+    return __atomic_fetch_add(p, v, __ATOMIC_ACQ_REL);
+}
 inline int atomicMax(int* p, int v)
 {
     int old = __atomic_load_n(p, __ATOMIC_RELAXED);
@@ -115,6 +119,7 @@ using std::exp;
 using std::atan2;
 using std::fabs;
 using std::tan;
+using std::trunc;
 using std::ceil;
 using std::ldexp;
 inline double rsqrt(double v) { return 1.0 / std::sqrt(v); }

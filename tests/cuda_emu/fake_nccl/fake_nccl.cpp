@@ -138,7 +138,7 @@ EXPORT int ncclAllGather(const void* send, void* recv, size_t sendcount, int dty
 EXPORT int ncclAllReduce(const void* send, void* recv, size_t count, int dtype, int op, void* comm, void*)
 {
     Comm* c = (Comm*)comm;
-    if (op != 0 || (dtype != 2 && dtype != 8)) return 4;        // sums of int32 / float64 only
+    if (op != 0 || (dtype != 2 && dtype != 8 && dtype != 4)) return 4;        // sums of int32 / int64 / float64 only
     const size_t es = esize(dtype);
     const size_t per = kSlot / es;
     for (size_t off = 0; off < count; off += per) {
@@ -150,6 +150,13 @@ EXPORT int ncclAllReduce(const void* send, void* recv, size_t count, int dtype, 
             for (size_t i = 0; i < n; ++i) {
                 double s = 0.0;
                 for (int r = 0; r < c->nranks; ++r) s += ((const double*)c->slot(r))[i];     // rank order: every rank gets the same bits
+                out[i] = s;
+            }
+        } else if (dtype == 4) {
+            int64_t* out = (int64_t*)recv + off;
+            for (size_t i = 0; i < n; ++i) {
+                int64_t s = 0;
+                for (int r = 0; r < c->nranks; ++r) s += ((const int64_t*)c->slot(r))[i];
                 out[i] = s;
             }
         } else {

@@ -49,9 +49,10 @@ def test_default_paths_on_emulator(emu_env):
 def test_symmetric_paths_on_emulator(emu_env):
     """lpm_set_bve_variant(200..203) through the real host code: velocity, stream functions, planar velocity."""
     tail = _run(emu_env, ["tests/test_sym_gpu.py", "-k",
-                          "(random_ragged and not 20011 and not 4099 and not 6000) or plane_velocity_mesh and 3-20 "
-                          "or (4099 and (200 or 201) and velocity_random) or fenced_one_sided "
-                          "or (betaplane_velocity and not 4-20) or betaplane_rk4 or plane_and_betaplane_stream or plane_rk4"], 900)
+                          "(random_ragged and (200 or 201) and not 20011 and not 4099 and not 6000) "
+                          "or (plane_velocity_mesh and 3-20) or fenced_one_sided or (betaplane_velocity and 3-20) "
+                          "or betaplane_rk4 or plane_rk4 or (plane_and_betaplane_stream and 200) "
+                          "or (fixed_point and 1.0 and 204) or (velocity_random_ragged and 1025 and (202 or 203))"], 900)
     assert " passed" in tail and "failed" not in tail, tail
 
 
@@ -97,6 +98,14 @@ def test_rank_mode_on_emulator(emu_env, tmp_path):
             raise
     for r, (p, out) in enumerate(zip(procs, outs)):
         assert p.returncode == 0 and f"OK rank {r} of {world}" in out, out[-3000:]
+    # variant 204 (fixed-point accumulation of the symmetric sums): one rank alone gets the same BITS as three
+    r1 = subprocess.run([sys.executable, os.path.join(EMU, "rank_mode.py"), "1", "0", idfile], env=env,
+                        capture_output=True, text=True, timeout=600)
+    assert r1.returncode == 0 and "OK rank 0 of 1" in r1.stdout, (r1.stdout + r1.stderr)[-3000:]
+    import numpy as np
+    one = np.load(idfile + ".fx.1.0.npy")
+    for r in range(world):
+        assert np.array_equal(np.load(idfile + f".fx.{world}.{r}.npy"), one), f"rank {r} of {world} differs from the single-rank bits"
 
 
 @pytest.mark.skipif(os.environ.get("LPM_RACE_CHECK") != "1", reason="2 minutes: set LPM_RACE_CHECK=1")

@@ -212,3 +212,20 @@ def test_fenced_one_sided_variants(sym, oracle, get_mesh):
     q = get_mesh(M.QUAD_RECT_SEED, 4, 7.0)
     vq = problems.colliding_dipoles(q)
     assert relerr(sym.plane_stream(q.x, q.y, vq, q.area, q.is_active), oracle.plane_stream(q.x, q.y, vq, q.area, q.is_active)) <= TOL
+
+
+@pytest.mark.parametrize("sym", [204, 205], indirect=True)
+@pytest.mark.parametrize("R", [1.0, 6.371e6, 3.0e-7])
+def test_sym_fixed_point_accumulation(sym, oracle, R):
+    """Variants 204 / 205: the symmetric sums with order-independent (fixed-point) accumulation -- parity as the
+    other variants, and bit-identical results from run to run whatever order the CTAs finish in."""
+    x, y, z, zeta, area, mask = _rand_sphere(1700, 5, 0.7)
+    x, y, z = R * x, R * y, R * z
+    av = zeta + 0.3 * z / R
+    got = sym.bve_velocity(x, y, z, zeta, area, mask, R)
+    _check(got, oracle.bve_velocity(x, y, z, zeta, area, mask, R), oracle.bve_velocity(x, y, z, zeta, area, mask, R, variant="_ld"))
+    gots = sym.bve_stream(x, y, z, zeta, av, area, mask, R)
+    _check(gots, oracle.bve_stream(x, y, z, zeta, av, area, mask, R), oracle.bve_stream(x, y, z, zeta, av, area, mask, R, variant="_ld"))
+    for _ in range(2):
+        again = sym.bve_velocity(x, y, z, zeta, area, mask, R) + sym.bve_stream(x, y, z, zeta, av, area, mask, R)
+        assert all(np.array_equal(a, b) for a, b in zip(again, got + gots))
