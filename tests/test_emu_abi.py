@@ -4,7 +4,7 @@ tests/cuda_emu/build_emu.sh compiles lpm_v2_b200/csrc -- kernels AND host code -
 (convert.py rewrites the <<<>>> launches; emu_runtime.h stands in for the CUDA runtime, device memory = host memory)
 into tests/cuda_emu/liblpmgpu_emu.so, which exports the same symbols as liblpmgpu.so.  A subprocess then runs a
 subset of the GPU parity tests against it (LPM_GPU_LIBRARY): the tests that finish within seconds under emulation
-(tests/cuda_emu/emu_subset.txt: 60-odd of tests/test_parity_gpu.py, test_pse_ops_gpu.py, test_swe_gpu.py) and the small
+(tests/cuda_emu/emu_subset.txt: 40-odd of tests/test_parity_gpu.py, test_pse_ops_gpu.py, test_swe_gpu.py) and the small
 cases of the experimental pair-symmetric paths (tests/test_sym_gpu.py).
 
 What this buys: kernel and host logic (indexing, pipelines, culling, retry paths, chunking, the symmetric schedule
