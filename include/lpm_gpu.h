@@ -296,7 +296,8 @@ int lpm_set_profiling(int enable);
 /* Tuning knob for benchmarks: select the BVE kernel variant.  0 = default.
  * 1-99: tilings / statement orders of the one-sided kernel (44, 45: with scheduling fences); 102, 103: shapes of the
  * stream-function kernels (103: with scheduling fences);
- * 200-205: EXPERIMENTAL pair-symmetric evaluation of the velocity sum (csrc/symmetric.cuh; opt-in, results
+ * 200-205: EXPERIMENTAL pair-symmetric evaluation of the velocity and stream-function sums of the sphere, plane and
+ * beta-plane solvers (csrc/symmetric.cuh; opt-in, results
  * reproducible to rounding but not bit for bit -- except 204, 205, which accumulate in fixed point and give the same
  * bits whatever the order and the rank count; in rank mode every rank must set the same value). */
 int lpm_set_bve_variant(int variant);
