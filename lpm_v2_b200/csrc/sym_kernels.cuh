@@ -20,20 +20,21 @@ struct SymGeom {
 // kernel-wide constants of the symmetric functors
 struct SymParams : LogParams {
     double R2;
-    const double* fx;       // fixed-point accumulation: fx[0] = 2^-E0 (see sym_red_add), or nullptr for FP64 atomics
+    const double* fx;       // fixed-point accumulation (kernels built with FX): fx[0] = 2^-E0, see sym_red_add
 };
 
 // ---- order-independent accumulation ------------------------------------------------------------
 // RED.ADD.F64 makes the result depend on the order in which the CTAs' contributions land.  Every value that
 // reaches a RED here is itself deterministic (a fixed (block, tile, warp) computes it in a fixed order), so adding
 // those values EXACTLY makes the total independent of the order -- and of how the blocks were dealt to ranks.
-// With fx set, an accumulator is kFxLimbs signed 64-bit limbs, limb k counting units of 2^(E0 + 40 k): a value is
+// In a kernel built with FX, an accumulator is kFxLimbs signed 64-bit limbs, limb k counting units of 2^(E0 + 40 k): a value is
 // split into (at most three non-zero) 40-bit pieces and each is added with an integer atomic; what lies below
 // 2^E0 -- 240 bits under the top of the window, chosen per evaluation by sym_fx_scale_kernel -- is dropped.
 constexpr int kFxLimbs = 6;
+template <bool FX>
 __device__ __forceinline__ void sym_red_add(double* acc, size_t idx, double v, const double* __restrict__ fx)
 {
-    if (fx == nullptr) {
+    if constexpr (!FX) {
         atomicAdd(acc + idx, v);
         return;
     }
@@ -53,7 +54,7 @@ __device__ __forceinline__ void sym_red_add(double* acc, size_t idx, double v, c
 // halving, then one RED per (source, component) from the lane that ends up owning it.
 // After the halving levels lane l holds source ((l >> (5 - LV)) & (SB - 1)) summed over the lanes
 // that differ from it in the high LV bits; a butterfly over the remaining low bits finishes the sum.
-template <int SB, int NC>
+template <int SB, int NC, bool FX>
 __device__ __forceinline__ void sym_reduce_red(double (&cb)[SB][NC], int lane, double* __restrict__ acc, size_t idx0,
                                                const double* __restrict__ fx)
 {
@@ -94,7 +95,7 @@ __device__ __forceinline__ void sym_reduce_red(double (&cb)[SB][NC], int lane, d
         }
         sidx = (lane >> 2) & 7;
         const int q = lane & 3;
-        if (q < NC) sym_red_add(acc, idx0 + sidx * NC + q, q == 0 ? v[0] : (q == 1 ? v[NC > 1 ? 1 : 0] : v[NC > 2 ? 2 : 0]), fx);
+        if (q < NC) sym_red_add<FX>(acc, idx0 + sidx * NC + q, q == 0 ? v[0] : (q == 1 ? v[NC > 1 ? 1 : 0] : v[NC > 2 ? 2 : 0]), fx);
     } else {
         const bool b4 = (lane & 16) != 0, b3 = (lane & 8) != 0;
         double v2[2][NC];
@@ -120,7 +121,7 @@ __device__ __forceinline__ void sym_reduce_red(double (&cb)[SB][NC], int lane, d
         }
         sidx = (lane >> 3) & 3;
         const int q = lane & 7;
-        if (q < NC) sym_red_add(acc, idx0 + sidx * NC + q, q == 0 ? v[0] : (q == 1 ? v[NC > 1 ? 1 : 0] : v[NC > 2 ? 2 : 0]), fx);
+        if (q < NC) sym_red_add<FX>(acc, idx0 + sidx * NC + q, q == 0 ? v[0] : (q == 1 ? v[NC > 1 ? 1 : 0] : v[NC > 2 ? 2 : 0]), fx);
     }
 }
 
@@ -655,7 +656,7 @@ using SymBetaStream = SymLogStream<BetaStreamGeom>;
 // acc: [nsrc_pad][NC] doubles -- or, with prm.fx, [nsrc_pad][NC][kFxLimbs] 64-bit limbs -- zeroed by the caller
 // (NA == NC: both directions feed the same sums).
 // dynamic shared memory: [2 tiles][K::KS table][2 mbarriers]
-template <class K, int T, int BLOCK, int SB, int MINB, int ORDER = 0>
+template <class K, int T, int BLOCK, int SB, int MINB, int ORDER = 0, bool FX = false>
 __global__ void __launch_bounds__(BLOCK, MINB)
 sym_kernel(const SymParams prm, const SymGeom g, const double* __restrict__ src, double* __restrict__ acc)
 {
@@ -731,7 +732,7 @@ sym_kernel(const SymParams prm, const SymGeom g, const double* __restrict__ src,
         for (int jb = 0; jb < TS; jb += SB) {
             double cb[SB][NC];
             K::template batch<T, SB, ORDER>(prm, tg, a, sm + jb * NS, cb, sctx);
-            sym_reduce_red<SB, NC>(cb, lane, acc, ((size_t)k * TS + jb) * NC, prm.fx);
+            sym_reduce_red<SB, NC, FX>(cb, lane, acc, ((size_t)k * TS + jb) * NC, prm.fx);
         }
     };
 
@@ -753,7 +754,7 @@ sym_kernel(const SymParams prm, const SymGeom g, const double* __restrict__ src,
     for (int t = 0; t < T; ++t)
         if (cidx[t] < g.nsrc) {
 #pragma unroll
-            for (int q = 0; q < NA; ++q) sym_red_add(acc, (size_t)cidx[t] * NA + q, a[t][q], prm.fx);
+            for (int q = 0; q < NA; ++q) sym_red_add<FX>(acc, (size_t)cidx[t] * NA + q, a[t][q], prm.fx);
         }
 }
 

@@ -39,7 +39,7 @@ constexpr int kSymVariant = 200;
 constexpr int kSymVariantLast = 205;        // 204, 205: shapes 200, 201 with fixed-point (order-independent) accumulation
 constexpr int kSymVariantFx = 204;
 
-template <class K, int T, int BLOCK, int SB, int MINB, int ORDER = 0>
+template <class K, int T, int BLOCK, int SB, int MINB, int ORDER = 0, bool FX = false>
 inline int launch_sym(cudaStream_t st, const SymParams& prm, SymGeom g, const double* src, double* acc)
 {
     constexpr int TB = BLOCK * T;
@@ -53,11 +53,11 @@ inline int launch_sym(cudaStream_t st, const SymParams& prm, SymGeom g, const do
         int devid = 0;
         cudaGetDevice(&devid);
         if (devid < 0 || devid >= 64 || !configured[devid]) {
-            LPM_CUDA(cudaFuncSetAttribute(sym_kernel<K, T, BLOCK, SB, MINB, ORDER>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            LPM_CUDA(cudaFuncSetAttribute(sym_kernel<K, T, BLOCK, SB, MINB, ORDER, FX>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
             if (devid >= 0 && devid < 64) configured[devid] = true;
         }
     }
-    sym_kernel<K, T, BLOCK, SB, MINB, ORDER><<<(unsigned)grid, BLOCK, smem, st>>>(prm, g, src, acc);
+    sym_kernel<K, T, BLOCK, SB, MINB, ORDER, FX><<<(unsigned)grid, BLOCK, smem, st>>>(prm, g, src, acc);
     return LPM_OK;
 }
 
@@ -77,10 +77,12 @@ struct SymVel {
     {
         // orders picked with the operand-delivery model (tools/sym_score.py): modelled 15.9 / 15.1 / 17.1 / 16.7
         // cycles per interaction per SM sub-partition (the default one-sided kernel: 20.8 modelled, 20.3 measured)
-        switch ((variant - kSymVariant) & 3) {
+        switch (variant - kSymVariant) {
             case 1: return launch_sym<SK, 8, 128, 4, 1, 35>(st, prm, g, src, acc);
             case 2: return launch_sym<SK, 4, 128, 8, 2, 27>(st, prm, g, src, acc);
             case 3: return launch_sym<SK, 8, 128, 4, 1, 27>(st, prm, g, src, acc);
+            case 4: return launch_sym<SK, 4, 128, 8, 2, 35, true>(st, prm, g, src, acc);       // fixed-point accumulation
+            case 5: return launch_sym<SK, 8, 128, 4, 1, 35, true>(st, prm, g, src, acc);
             default: return launch_sym<SK, 4, 128, 8, 2, 35>(st, prm, g, src, acc);
         }
     }
@@ -105,10 +107,12 @@ struct SymStream {
         // 64 KB table per CTA, so two CTAs per SM either way: 256 threads under a 128-register cap (121 registers
         // with the per-source retry; the per-batch retry spills 24 bytes there) or 128 threads with ~155.
         // Modelled 17.7 / 18.9 / 18.9 / 18.4 cycles per interaction (the one-sided kernel: 29.6 modelled, 32.3 measured).
-        switch ((variant - kSymVariant) & 3) {
+        switch (variant - kSymVariant) {
             case 1: return launch_sym<SK, 4, 128, 4, 2, 0>(st, prm, g, src, acc);
             case 2: return launch_sym<SK, 4, 256, 4, 2, 0>(st, prm, g, src, acc);
             case 3: return launch_sym<SK, 4, 128, 4, 2, 1>(st, prm, g, src, acc);
+            case 4: return launch_sym<SK, 4, 256, 4, 2, 1, true>(st, prm, g, src, acc);       // fixed-point accumulation
+            case 5: return launch_sym<SK, 4, 128, 4, 2, 0, true>(st, prm, g, src, acc);
             default: return launch_sym<SK, 4, 256, 4, 2, 1>(st, prm, g, src, acc);
         }
     }
