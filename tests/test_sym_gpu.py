@@ -1,9 +1,10 @@
-"""GPU parity of the EXPERIMENTAL pair-symmetric BVE velocity path (lpm_set_bve_variant(200 .. 203),
-lpm_v2_b200/csrc/symmetric.cuh).
+"""GPU parity of the EXPERIMENTAL paths: the pair-symmetric sums (lpm_set_bve_variant(200 .. 205),
+lpm_v2_b200/csrc/symmetric.cuh: BVE / planar / beta-plane velocity and stream functions; 204, 205 with fixed-point
+accumulation) and the fenced one-sided kernels (44, 45, 103).
 
-The path was written at the end of round 1 without GPU time left, so it has not run yet: these tests
-are skipped unless LPM_EXPERIMENTAL=1, and the default path does not depend on them.  First thing to
-run on a B200 in the next round:
+They were written at the end of round 1 without GPU time left, so they have not run on a GPU yet: these tests
+are skipped unless LPM_EXPERIMENTAL=1, and the default path does not depend on them.  On the SIMT emulator
+(tests/test_emu_abi.py) the small cases pass.  First thing to run on a B200 in the next round:
 
     LPM_EXPERIMENTAL=1 python -m pytest tests/test_sym_gpu.py -m gpu -x -q
     python tools/ab_sym.py 7            # default vs symmetric timings, one box
