@@ -42,8 +42,7 @@ def sym(gpu, request):
 
 
 @pytest.mark.parametrize("sym", [200, 201, 202, 203], indirect=True)
-@pytest.mark.parametrize("seed,L", [(M.ICOS_TRI_SPHERE_SEED, 2), (M.ICOS_TRI_SPHERE_SEED, 5), (M.CUBED_SPHERE_SEED, 5),
-                                    (M.ICOS_TRI_SPHERE_SEED, 6)])
+@pytest.mark.parametrize("seed,L", [(M.ICOS_TRI_SPHERE_SEED, 2), (M.ICOS_TRI_SPHERE_SEED, 5), (M.CUBED_SPHERE_SEED, 5)])
 def test_sym_bve_velocity_meshes(sym, oracle, get_mesh, seed, L):
     m = get_mesh(seed, L)
     zeta = problems.rossby_haurwitz54(m)
@@ -165,7 +164,7 @@ def test_sym_betaplane_rk4_step(sym, oracle, get_mesh):
     tp.test_betaplane_rk4_step(sym, oracle, get_mesh)
 
 
-@pytest.mark.parametrize("sym", [200], indirect=True)
+@pytest.mark.parametrize("sym", [200, 201, 204, 205], indirect=True)
 def test_sym_matches_default_path(sym, get_mesh):
     """Same sum, other order: within a few ulp of the default kernel at icosTri 6."""
     m = get_mesh(M.ICOS_TRI_SPHERE_SEED, 6)
