@@ -54,9 +54,9 @@ __device__ __forceinline__ void sym_red_add(double* acc, size_t idx, double v, c
 // halving, then one RED per (source, component) from the lane that ends up owning it.
 // After the halving levels lane l holds source ((l >> (5 - LV)) & (SB - 1)) summed over the lanes
 // that differ from it in the high LV bits; a butterfly over the remaining low bits finishes the sum.
-template <int SB, int NC, bool FX>
+template <int SB, int NC, bool FX, bool COMBINE = false>
 __device__ __forceinline__ void sym_reduce_red(double (&cb)[SB][NC], int lane, double* __restrict__ acc, size_t idx0,
-                                               const double* __restrict__ fx)
+                                               const double* __restrict__ fx, double* __restrict__ slot = nullptr)
 {
     static_assert(SB == 8 || SB == 4, "source batch");
     static_assert(NC >= 1 && NC <= 3, "components per source");
@@ -95,7 +95,11 @@ __device__ __forceinline__ void sym_reduce_red(double (&cb)[SB][NC], int lane, d
         }
         sidx = (lane >> 2) & 7;
         const int q = lane & 3;
-        if (q < NC) sym_red_add<FX>(acc, idx0 + sidx * NC + q, q == 0 ? v[0] : (q == 1 ? v[NC > 1 ? 1 : 0] : v[NC > 2 ? 2 : 0]), fx);
+        if (q < NC) {
+            const double val = q == 0 ? v[0] : (q == 1 ? v[NC > 1 ? 1 : 0] : v[NC > 2 ? 2 : 0]);
+            if constexpr (COMBINE) slot[sidx * NC + q] = val;      // this warp's sum; joined with the other warps' after the tile
+            else sym_red_add<FX>(acc, idx0 + sidx * NC + q, val, fx);
+        }
     } else {
         const bool b4 = (lane & 16) != 0, b3 = (lane & 8) != 0;
         double v2[2][NC];
@@ -121,7 +125,11 @@ __device__ __forceinline__ void sym_reduce_red(double (&cb)[SB][NC], int lane, d
         }
         sidx = (lane >> 3) & 3;
         const int q = lane & 7;
-        if (q < NC) sym_red_add<FX>(acc, idx0 + sidx * NC + q, q == 0 ? v[0] : (q == 1 ? v[NC > 1 ? 1 : 0] : v[NC > 2 ? 2 : 0]), fx);
+        if (q < NC) {
+            const double val = q == 0 ? v[0] : (q == 1 ? v[NC > 1 ? 1 : 0] : v[NC > 2 ? 2 : 0]);
+            if constexpr (COMBINE) slot[sidx * NC + q] = val;      // this warp's sum; joined with the other warps' after the tile
+            else sym_red_add<FX>(acc, idx0 + sidx * NC + q, val, fx);
+        }
     }
 }
 
@@ -655,8 +663,10 @@ using SymBetaStream = SymLogStream<BetaStreamGeom>;
 // ---- the kernel ---------------------------------------------------------------
 // acc: [nsrc_pad][NC] doubles -- or, with prm.fx, [nsrc_pad][NC][kFxLimbs] 64-bit limbs -- zeroed by the caller
 // (NA == NC: both directions feed the same sums).
-// dynamic shared memory: [2 tiles][K::KS table][2 mbarriers]
-template <class K, int T, int BLOCK, int SB, int MINB, int ORDER = 0, bool FX = false>
+// dynamic shared memory: [2 tiles][K::KS table][2 mbarriers] and, with COMBINE, [2][warps][TS][NC] per-warp source sums:
+// the warps' sums for a tile are added in warp order after the tile and ONE RED per (CTA, source, component) is
+// issued instead of one per warp (a quarter of the atomics with 128 threads)
+template <class K, int T, int BLOCK, int SB, int MINB, int ORDER = 0, bool FX = false, bool COMBINE = false>
 __global__ void __launch_bounds__(BLOCK, MINB)
 sym_kernel(const SymParams prm, const SymGeom g, const double* __restrict__ src, double* __restrict__ acc)
 {
@@ -670,6 +680,8 @@ sym_kernel(const SymParams prm, const SymGeom g, const double* __restrict__ src,
     double(*tile)[TS * NS] = reinterpret_cast<double(*)[TS * NS]>(smem_raw);
     double* ks = reinterpret_cast<double*>(smem_raw + 2 * kTileBytes);
     uint64_t* full = reinterpret_cast<uint64_t*>(ks + K::KS);
+    constexpr int NW = BLOCK / 32;
+    double* cT = reinterpret_cast<double*>(full + 2);        // COMBINE only
 
     const int tid = threadIdx.x, lane = tid & 31;
     const int I = blockIdx.x % g.nblocks;           // chunk is the slow index, as in ds_kernel
@@ -726,13 +738,25 @@ sym_kernel(const SymParams prm, const SymGeom g, const double* __restrict__ src,
         }
     };
     // a tile above the diagonal: every pair once, both directions
-    auto sym_tile = [&](const int k, const int st) {
+    auto sym_tile = [&](const int k, const int st, const int parity) {
         const double* sm = tile[st];
+        double* mine = cT + ((size_t)parity * NW + (tid >> 5)) * TS * NC;        // this warp's slots (COMBINE)
 #pragma unroll 1
         for (int jb = 0; jb < TS; jb += SB) {
             double cb[SB][NC];
             K::template batch<T, SB, ORDER>(prm, tg, a, sm + jb * NS, cb, sctx);
-            sym_reduce_red<SB, NC, FX>(cb, lane, acc, ((size_t)k * TS + jb) * NC, prm.fx);
+            sym_reduce_red<SB, NC, FX, COMBINE>(cb, lane, acc, ((size_t)k * TS + jb) * NC, prm.fx, mine + jb * NC);
+        }
+    };
+    // COMBINE: after the barrier that ends tile k, add the warps' sums in warp order and issue the REDs.  The slots are
+    // double-buffered by tile parity: a warp that is already in the next tile writes the other half.
+    auto flush = [&](const int k, const int parity) {
+        const double* base = cT + (size_t)parity * NW * TS * NC;
+        for (int idx = tid; idx < TS * NC; idx += BLOCK) {
+            double sum = base[idx];
+#pragma unroll
+            for (int w = 1; w < NW; ++w) sum += base[(size_t)w * TS * NC + idx];
+            sym_red_add<FX>(acc, (size_t)k * TS * NC + idx, sum, prm.fx);
         }
     };
 
@@ -745,9 +769,12 @@ sym_kernel(const SymParams prm, const SymGeom g, const double* __restrict__ src,
         const int st = it & 1, k = k0 + it;
         mbar_wait(&full[st], (it >> 1) & 1);
         if (k < kdiag + DT) diag_tile(k, st);
-        else sym_tile(k, st);
+        else sym_tile(k, st, it & 1);
         __syncthreads();        // everyone is done with tile[st]
         if (tid == 0 && it + 2 < nt) load_tile(k + 2, st);
+        if constexpr (COMBINE) {
+            if (k >= kdiag + DT) flush(k, it & 1);
+        }
     }
     // this CTA's own sums join the accumulators
 #pragma unroll
@@ -758,10 +785,11 @@ sym_kernel(const SymParams prm, const SymGeom g, const double* __restrict__ src,
         }
 }
 
-template <class K, int T, int BLOCK>
+template <class K, int T, int BLOCK, bool COMBINE = false>
 constexpr size_t sym_smem_bytes()
 {
-    return 2 * size_t(kTile) * K::NS * sizeof(double) + sizeof(double) * K::KS + 2 * sizeof(uint64_t);
+    return 2 * size_t(kTile) * K::NS * sizeof(double) + sizeof(double) * K::KS + 2 * sizeof(uint64_t) +
+           (COMBINE ? 2 * size_t(BLOCK / 32) * kTile * K::NC * sizeof(double) : 0);
 }
 
 // Window of the fixed-point accumulators for one evaluation.  maxhi: high word of the largest |entry| of the source

@@ -36,16 +36,18 @@ namespace lpm {
 //   stream functions  200: 256 threads, retry branch per source (ORDER 1)    201: 128 threads, retry per batch (ORDER 0)
 //                     202: 256 threads, retry per batch                      203: 128 threads, retry per source
 constexpr int kSymVariant = 200;
-constexpr int kSymVariantLast = 205;        // 204, 205: shapes 200, 201 with fixed-point (order-independent) accumulation
-constexpr int kSymVariantFx = 204;
+constexpr int kSymVariantLast = 207;        // 204, 205: shapes 200, 201 with fixed-point (order-independent) accumulation
+constexpr int kSymVariantFx = 204;          // 206, 207: shapes 200, 201 with the warps' source sums combined in shared memory
+// shape 0..3 of a variant for the sums that have no special build for it
+inline int sym_shape(int variant) { const int s = variant - kSymVariant; return s < 4 ? s : (s & 1); }
 
-template <class K, int T, int BLOCK, int SB, int MINB, int ORDER = 0, bool FX = false>
+template <class K, int T, int BLOCK, int SB, int MINB, int ORDER = 0, bool FX = false, bool COMBINE = false>
 inline int launch_sym(cudaStream_t st, const SymParams& prm, SymGeom g, const double* src, double* acc)
 {
     constexpr int TB = BLOCK * T;
     g.nblocks = (g.nsrc_pad + TB - 1) / TB;
     g.half_bin = 1 << (19 - kLogBits);
-    constexpr size_t smem = sym_smem_bytes<K, T, BLOCK>();
+    constexpr size_t smem = sym_smem_bytes<K, T, BLOCK, COMBINE>();
     const int64_t grid = (int64_t)g.nblocks * g.nchunks;
     if (grid <= 0 || grid > 0x7fffffffLL) return set_error(LPM_ERR_INVALID, "symmetric kernel grid %lld", (long long)grid);
     if (smem > 48 * 1024) {     // per device, as in launch_ds
@@ -53,11 +55,11 @@ inline int launch_sym(cudaStream_t st, const SymParams& prm, SymGeom g, const do
         int devid = 0;
         cudaGetDevice(&devid);
         if (devid < 0 || devid >= 64 || !configured[devid]) {
-            LPM_CUDA(cudaFuncSetAttribute(sym_kernel<K, T, BLOCK, SB, MINB, ORDER, FX>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            LPM_CUDA(cudaFuncSetAttribute(sym_kernel<K, T, BLOCK, SB, MINB, ORDER, FX, COMBINE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
             if (devid >= 0 && devid < 64) configured[devid] = true;
         }
     }
-    sym_kernel<K, T, BLOCK, SB, MINB, ORDER, FX><<<(unsigned)grid, BLOCK, smem, st>>>(prm, g, src, acc);
+    sym_kernel<K, T, BLOCK, SB, MINB, ORDER, FX, COMBINE><<<(unsigned)grid, BLOCK, smem, st>>>(prm, g, src, acc);
     return LPM_OK;
 }
 
@@ -83,6 +85,8 @@ struct SymVel {
             case 3: return launch_sym<SK, 8, 128, 4, 1, 27>(st, prm, g, src, acc);
             case 4: return launch_sym<SK, 4, 128, 8, 2, 35, true>(st, prm, g, src, acc);       // fixed-point accumulation
             case 5: return launch_sym<SK, 8, 128, 4, 1, 35, true>(st, prm, g, src, acc);
+            case 6: return launch_sym<SK, 4, 128, 8, 2, 35, false, true>(st, prm, g, src, acc);    // one RED per CTA, source, component
+            case 7: return launch_sym<SK, 8, 128, 4, 1, 35, false, true>(st, prm, g, src, acc);
             default: return launch_sym<SK, 4, 128, 8, 2, 35>(st, prm, g, src, acc);
         }
     }
@@ -113,6 +117,7 @@ struct SymStream {
             case 3: return launch_sym<SK, 4, 128, 4, 2, 1>(st, prm, g, src, acc);
             case 4: return launch_sym<SK, 4, 256, 4, 2, 1, true>(st, prm, g, src, acc);       // fixed-point accumulation
             case 5: return launch_sym<SK, 4, 128, 4, 2, 0, true>(st, prm, g, src, acc);
+            case 7: return launch_sym<SK, 4, 128, 4, 2, 0>(st, prm, g, src, acc);      // (no combined build: the table leaves no room)
             default: return launch_sym<SK, 4, 256, 4, 2, 1>(st, prm, g, src, acc);
         }
     }
@@ -132,7 +137,7 @@ struct SymPlane {
     static void passive_params(PlaneVel::Params& p, const double* const* xy, const Args&) { p.x = xy[0]; p.y = xy[1]; }
     static int launch(int variant, cudaStream_t st, const SymParams& prm, const SymGeom& g, const double* src, double* acc)
     {
-        switch ((variant - kSymVariant) & 3) {
+        switch (sym_shape(variant)) {
             case 1: return launch_sym<SK, 8, 128, 4, 1, 1>(st, prm, g, src, acc);
             case 2: return launch_sym<SK, 4, 128, 8, 2, 0>(st, prm, g, src, acc);
             case 3: return launch_sym<SK, 8, 128, 4, 1, 0>(st, prm, g, src, acc);
@@ -155,7 +160,7 @@ struct SymBeta {
     static void passive_params(BetaVel::Params& p, const double* const* xy, const Args&) { p.x = xy[0]; p.y = xy[1]; }
     static int launch(int variant, cudaStream_t st, const SymParams& prm, const SymGeom& g, const double* src, double* acc)
     {
-        switch ((variant - kSymVariant) & 3) {
+        switch (sym_shape(variant)) {
             case 1: return launch_sym<SK, 4, 128, 4, 2, 1>(st, prm, g, src, acc);
             case 2: return launch_sym<SK, 4, 128, 8, 2, 0>(st, prm, g, src, acc);
             case 3: return launch_sym<SK, 4, 128, 4, 2, 0>(st, prm, g, src, acc);
@@ -178,7 +183,7 @@ struct SymPlaneStr {
     static void passive_params(PlaneStream::Params& p, const double* const* xy, const Args&) { p.x = xy[0]; p.y = xy[1]; }
     static int launch(int variant, cudaStream_t st, const SymParams& prm, const SymGeom& g, const double* src, double* acc)
     {
-        if ((variant - kSymVariant) & 1) return launch_sym<SK, 4, 128, 4, 2, 0>(st, prm, g, src, acc);
+        if (sym_shape(variant) & 1) return launch_sym<SK, 4, 128, 4, 2, 0>(st, prm, g, src, acc);
         return launch_sym<SK, 4, 256, 4, 2, 0>(st, prm, g, src, acc);
     }
     static void finalize(cudaStream_t st, const MaskPlan& mp, const double*, const double* acc, const Outs<1>& out)
@@ -195,7 +200,7 @@ struct SymBetaStr {
     static void passive_params(BetaStream::Params& p, const double* const* xy, const Args&) { p.x = xy[0]; p.y = xy[1]; }
     static int launch(int variant, cudaStream_t st, const SymParams& prm, const SymGeom& g, const double* src, double* acc)
     {
-        if ((variant - kSymVariant) & 1) return launch_sym<SK, 4, 128, 4, 2, 0>(st, prm, g, src, acc);
+        if (sym_shape(variant) & 1) return launch_sym<SK, 4, 128, 4, 2, 0>(st, prm, g, src, acc);
         return launch_sym<SK, 4, 256, 4, 2, 0>(st, prm, g, src, acc);
     }
     static void finalize(cudaStream_t st, const MaskPlan& mp, const double*, const double* acc, const Outs<2>& out)
@@ -248,7 +253,7 @@ inline int sym_evaluate(Device& dev, cudaStream_t st, MaskPlan& mp, const Args& 
         // ---- active x active
         if (mp.nsrc > 0) {
             const size_t nacc = (size_t)g.nsrc_pad * SK::NC;
-            const bool fx = S::FX_MODE >= 0 && variant >= kSymVariantFx;
+            const bool fx = S::FX_MODE >= 0 && (variant == kSymVariantFx || variant == kSymVariantFx + 1);
             const size_t acc_bytes = nacc * sizeof(double) * (fx ? kFxLimbs : 1);
             LPM_TRY(ws.sym_acc.reserve(acc_bytes));
             LPM_CUDA(cudaMemsetAsync(ws.sym_acc.p, 0, acc_bytes, st));

@@ -1,6 +1,6 @@
-"""GPU parity of the EXPERIMENTAL paths: the pair-symmetric sums (lpm_set_bve_variant(200 .. 205),
+"""GPU parity of the EXPERIMENTAL paths: the pair-symmetric sums (lpm_set_bve_variant(200 .. 207),
 lpm_v2_b200/csrc/symmetric.cuh: BVE / planar / beta-plane velocity and stream functions; 204, 205 with fixed-point
-accumulation) and the fenced one-sided kernels (44, 45, 103).
+accumulation, 206, 207 with the warps' sums combined in shared memory) and the fenced one-sided kernels (44, 45, 103).
 
 They were written at the end of round 1 without GPU time left, so they have not run on a GPU yet: these tests
 are skipped unless LPM_EXPERIMENTAL=1, and the default path does not depend on them.  On the SIMT emulator
@@ -52,7 +52,7 @@ def test_sym_bve_velocity_meshes(sym, oracle, get_mesh, seed, L):
     assert max(np.abs(g - w).max() for g, w in zip(got, want)) <= TOL * scale
 
 
-@pytest.mark.parametrize("sym", [200, 201, 202, 203], indirect=True)
+@pytest.mark.parametrize("sym", [200, 201, 202, 203, 206, 207], indirect=True)
 @pytest.mark.parametrize("n,frac,seed", [(1, 1.0, 1), (2, 1.0, 2), (3, 0.5, 3), (127, 0.3, 4), (513, 0.9, 5),
                                          (1025, 0.05, 6), (4099, 0.6, 12345), (20011, 0.55, 7), (20011, 1.0, 8),
                                          (3000, 0.0, 9)])
@@ -164,7 +164,7 @@ def test_sym_betaplane_rk4_step(sym, oracle, get_mesh):
     tp.test_betaplane_rk4_step(sym, oracle, get_mesh)
 
 
-@pytest.mark.parametrize("sym", [200, 201, 204, 205], indirect=True)
+@pytest.mark.parametrize("sym", [200, 201, 204, 205, 206, 207], indirect=True)
 def test_sym_matches_default_path(sym, get_mesh):
     """Same sum, other order: within a few ulp of the default kernel at icosTri 6."""
     m = get_mesh(M.ICOS_TRI_SPHERE_SEED, 6)
