@@ -296,10 +296,10 @@ int lpm_set_profiling(int enable);
 /* Tuning knob for benchmarks: select the BVE kernel variant.  0 = default.
  * 1-99: tilings / statement orders of the one-sided kernel (44, 45: with scheduling fences); 102, 103: shapes of the
  * stream-function kernels (103: with scheduling fences);
- * 200-207: EXPERIMENTAL pair-symmetric evaluation of the velocity and stream-function sums of the sphere, plane and
+ * 200-209: EXPERIMENTAL pair-symmetric evaluation of the velocity and stream-function sums of the sphere, plane and
  * beta-plane solvers (csrc/symmetric.cuh; opt-in, results
  * reproducible to rounding but not bit for bit -- except 204, 205, which accumulate in fixed point and give the same
- * bits whatever the order and the rank count; 206, 207 issue one atomic per CTA instead of one per warp; in rank mode every rank must set the same value). */
+ * bits whatever the order and the rank count; 206, 207 issue one atomic per CTA instead of one per warp, 208, 209 do both; in rank mode every rank must set the same value). */
 int lpm_set_bve_variant(int variant);
 /* Upper bound on the number of source chunks an evaluation is split into (work items = target
  * blocks x chunks).  More chunks = shorter CTAs = a smaller tail when few waves of CTAs fit a

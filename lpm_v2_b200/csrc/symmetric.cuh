@@ -36,8 +36,10 @@ namespace lpm {
 //   stream functions  200: 256 threads, retry branch per source (ORDER 1)    201: 128 threads, retry per batch (ORDER 0)
 //                     202: 256 threads, retry per batch                      203: 128 threads, retry per source
 constexpr int kSymVariant = 200;
-constexpr int kSymVariantLast = 207;        // 204, 205: shapes 200, 201 with fixed-point (order-independent) accumulation
-constexpr int kSymVariantFx = 204;          // 206, 207: shapes 200, 201 with the warps' source sums combined in shared memory
+constexpr int kSymVariantLast = 209;        // 204, 205: shapes 200, 201 with fixed-point (order-independent) accumulation
+constexpr int kSymVariantFx = 204;          // 206, 207: shapes 200, 201 with the warps' source sums combined in shared memory;
+                                            // 208, 209: both (fixed point, a quarter of the atomics)
+inline bool sym_fixed_point(int variant) { const int s = variant - kSymVariant; return s == 4 || s == 5 || s == 8 || s == 9; }
 // shape 0..3 of a variant for the sums that have no special build for it
 inline int sym_shape(int variant) { const int s = variant - kSymVariant; return s < 4 ? s : (s & 1); }
 
@@ -87,6 +89,8 @@ struct SymVel {
             case 5: return launch_sym<SK, 8, 128, 4, 1, 35, true>(st, prm, g, src, acc);
             case 6: return launch_sym<SK, 4, 128, 8, 2, 35, false, true>(st, prm, g, src, acc);    // one RED per CTA, source, component
             case 7: return launch_sym<SK, 8, 128, 4, 1, 35, false, true>(st, prm, g, src, acc);
+            case 8: return launch_sym<SK, 4, 128, 8, 2, 35, true, true>(st, prm, g, src, acc);     // fixed point + combined
+            case 9: return launch_sym<SK, 8, 128, 4, 1, 35, true, true>(st, prm, g, src, acc);
             default: return launch_sym<SK, 4, 128, 8, 2, 35>(st, prm, g, src, acc);
         }
     }
@@ -118,6 +122,8 @@ struct SymStream {
             case 4: return launch_sym<SK, 4, 256, 4, 2, 1, true>(st, prm, g, src, acc);       // fixed-point accumulation
             case 5: return launch_sym<SK, 4, 128, 4, 2, 0, true>(st, prm, g, src, acc);
             case 7: return launch_sym<SK, 4, 128, 4, 2, 0>(st, prm, g, src, acc);      // (no combined build: the table leaves no room)
+            case 8: return launch_sym<SK, 4, 256, 4, 2, 1, true>(st, prm, g, src, acc);
+            case 9: return launch_sym<SK, 4, 128, 4, 2, 0, true>(st, prm, g, src, acc);
             default: return launch_sym<SK, 4, 256, 4, 2, 1>(st, prm, g, src, acc);
         }
     }
@@ -253,7 +259,7 @@ inline int sym_evaluate(Device& dev, cudaStream_t st, MaskPlan& mp, const Args& 
         // ---- active x active
         if (mp.nsrc > 0) {
             const size_t nacc = (size_t)g.nsrc_pad * SK::NC;
-            const bool fx = S::FX_MODE >= 0 && (variant == kSymVariantFx || variant == kSymVariantFx + 1);
+            const bool fx = S::FX_MODE >= 0 && sym_fixed_point(variant);
             const size_t acc_bytes = nacc * sizeof(double) * (fx ? kFxLimbs : 1);
             LPM_TRY(ws.sym_acc.reserve(acc_bytes));
             LPM_CUDA(cudaMemsetAsync(ws.sym_acc.p, 0, acc_bytes, st));

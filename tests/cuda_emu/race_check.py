@@ -16,7 +16,7 @@ from test_parity_gpu import _rand_sphere                  # noqa: E402
 nd = api.init(0)
 x, y, z, zeta, area, mask = _rand_sphere(1500, 5, 0.7)
 av = zeta + 0.3 * z
-for var in (0, 200, 201, 202, 203, 204, 205, 206, 207):
+for var in (0, 200, 201, 202, 203, 204, 205, 206, 207, 208, 209):
     api.set_bve_variant(var)
     api.bve_velocity(x, y, z, zeta, area, mask, 1.0)
     api.bve_stream(x, y, z, zeta, av, area, mask, 1.0)

@@ -52,7 +52,7 @@ def test_symmetric_paths_on_emulator(emu_env):
                           "(random_ragged and (200 or 201) and not 20011 and not 4099 and not 6000) "
                           "or (plane_velocity_mesh and 3-20) or fenced_one_sided or (betaplane_velocity and 3-20) "
                           "or betaplane_rk4 or plane_rk4 or (plane_and_betaplane_stream and 200) "
-                          "or (fixed_point and 1.0 and 204) or (velocity_random_ragged and (1025 or 513 or 127) and (202 or 203 or 206 or 207))"], 900)
+                          "or (fixed_point and 1.0 and (204 or 209)) or (velocity_random_ragged and (1025 or 513 or 127) and (202 or 203 or 206 or 207))"], 900)
     assert " passed" in tail and "failed" not in tail, tail
 
 
@@ -98,7 +98,7 @@ def test_rank_mode_on_emulator(emu_env, tmp_path):
             raise
     for r, (p, out) in enumerate(zip(procs, outs)):
         assert p.returncode == 0 and f"OK rank {r} of {world}" in out, out[-3000:]
-    # variant 204 (fixed-point accumulation of the symmetric sums): one rank alone gets the same BITS as three
+    # variant 208 (fixed-point accumulation of the symmetric sums): one rank alone gets the same BITS as three
     r1 = subprocess.run([sys.executable, os.path.join(EMU, "rank_mode.py"), "1", "0", idfile], env=env,
                         capture_output=True, text=True, timeout=600)
     assert r1.returncode == 0 and "OK rank 0 of 1" in r1.stdout, (r1.stdout + r1.stderr)[-3000:]

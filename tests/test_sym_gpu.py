@@ -1,4 +1,4 @@
-"""GPU parity of the EXPERIMENTAL paths: the pair-symmetric sums (lpm_set_bve_variant(200 .. 207),
+"""GPU parity of the EXPERIMENTAL paths: the pair-symmetric sums (lpm_set_bve_variant(200 .. 209),
 lpm_v2_b200/csrc/symmetric.cuh: BVE / planar / beta-plane velocity and stream functions; 204, 205 with fixed-point
 accumulation, 206, 207 with the warps' sums combined in shared memory) and the fenced one-sided kernels (44, 45, 103).
 
@@ -214,7 +214,7 @@ def test_fenced_one_sided_variants(sym, oracle, get_mesh):
     assert relerr(sym.plane_stream(q.x, q.y, vq, q.area, q.is_active), oracle.plane_stream(q.x, q.y, vq, q.area, q.is_active)) <= TOL
 
 
-@pytest.mark.parametrize("sym", [204, 205], indirect=True)
+@pytest.mark.parametrize("sym", [204, 205, 208, 209], indirect=True)
 @pytest.mark.parametrize("R", [1.0, 6.371e6, 3.0e-7])
 def test_sym_fixed_point_accumulation(sym, oracle, R):
     """Variants 204 / 205: the symmetric sums with order-independent (fixed-point) accumulation -- parity as the

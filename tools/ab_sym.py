@@ -9,7 +9,7 @@ import numpy as np
 from lpm_v2_b200 import api, mesh, problems
 
 levels = [int(a) for a in sys.argv[1].split(",")] if len(sys.argv) > 1 else [6, 7]
-variants = [int(a) for a in sys.argv[2].split(",")] if len(sys.argv) > 2 else [0, 200, 201, 202, 203, 204, 205, 206, 207]
+variants = [int(a) for a in sys.argv[2].split(",")] if len(sys.argv) > 2 else [0, 200, 201, 202, 203, 204, 205, 206, 207, 208, 209]
 api.init(1)
 api.set_profiling(True)
 for L in levels:
