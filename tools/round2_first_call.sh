@@ -7,7 +7,8 @@ mkdir -p gpurun_out
 echo "== 1. GPU parity tests of the default paths"
 timeout 600 python -m pytest tests -m gpu -x -q > gpurun_out/r02_pytest_gpu.log 2>&1; tail -3 gpurun_out/r02_pytest_gpu.log
 echo "== 2. experimental pair-symmetric paths: parity (tests/test_sym_gpu.py)"
-LPM_EXPERIMENTAL=1 timeout 600 python -m pytest tests/test_sym_gpu.py -m gpu -q > gpurun_out/r02_pytest_sym.log 2>&1; tail -5 gpurun_out/r02_pytest_sym.log
+# (the n = 20011 cases spend their time in the long-double oracle on the host: left for a later call)
+LPM_EXPERIMENTAL=1 timeout 900 python -m pytest tests/test_sym_gpu.py -m gpu -q -k "not 20011" > gpurun_out/r02_pytest_sym.log 2>&1; tail -5 gpurun_out/r02_pytest_sym.log
 echo "== 3. default vs fenced one-sided (44: velocity, 103: stream) vs symmetric (200-203), icosTri 7 and 8, one box"
 timeout 600 python tools/ab_sym.py 7,8 0,44,45,103,200,201,202,203,204,205,206,207,208,209 > gpurun_out/r02_ab_sym.log 2>&1; cat gpurun_out/r02_ab_sym.log
 if [ -f build/renamed/lpm_v2_b200/liblpmgpu.so ]; then
