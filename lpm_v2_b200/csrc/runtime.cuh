@@ -231,20 +231,29 @@ inline int free_shared(void* ptr)
     for (size_t k = 0; k < R.slabs.size(); ++k) {
         if (R.slabs[k].local != ptr) continue;
         SharedSlab s = R.slabs[k];
+        // The teardown is unconditional: whatever fails below, the slab leaves the registry and its
+        // memory is freed exactly once; the first error is reported after that.
+        R.slabs.erase(R.slabs.begin() + k);
         Device& dev = R.devs[0];
+        int rc = LPM_OK;
         cudaSetDevice(dev.id);
         cudaStreamSynchronize(dev.stream);
         cudaDeviceSynchronize();
         for (int r = 0; r < R.world; ++r)
-            if (r != R.rank && s.peer[r]) cudaIpcCloseMemHandle(s.peer[r]);
-        // nobody may free while a peer still has stores in flight or the mapping open
+            if (r != R.rank && s.peer[r]) {
+                cudaIpcCloseMemHandle(s.peer[r]);
+                s.peer[r] = nullptr;
+            }
+        // nobody should free while a peer still has stores in flight or the mapping open
         if (R.world > 1 && R.comm) {
-            LPM_TRY(comm_barrier(dev, dev.stream));
-            LPM_CUDA(cudaStreamSynchronize(dev.stream));
+            rc = comm_barrier(dev, dev.stream);
+            if (rc == LPM_OK && cudaStreamSynchronize(dev.stream) != cudaSuccess)
+                rc = set_error(LPM_ERR_CUDA, "lpm_comm_free_shared: barrier did not complete: %s",
+                               cudaGetErrorString(cudaGetLastError()));
         }
         cudaFree(s.local);
-        R.slabs.erase(R.slabs.begin() + k);
-        return LPM_OK;
+        cudaGetLastError();
+        return rc;
     }
     return set_error(LPM_ERR_INVALID, "lpm_comm_free_shared: not a shared allocation");
 }

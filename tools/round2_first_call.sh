@@ -4,6 +4,7 @@
 # Before calling: python __graft_entry__.py (build), and optionally `bash tools/build_renamed.sh` for step 4.
 # Every step writes its log under gpurun_out/; a failing step does not stop the rest.
 mkdir -p gpurun_out
+echo "== 0. toolchain probe"; which gfortran mpirun mpifort flang nvfortran f951 2>&1 | head; nproc; nvidia-smi -L
 echo "== 1. GPU parity tests of the default paths"
 timeout 600 python -m pytest tests -m gpu -x -q > gpurun_out/r02_pytest_gpu.log 2>&1; tail -3 gpurun_out/r02_pytest_gpu.log
 echo "== 2. experimental pair-symmetric paths: parity (tests/test_sym_gpu.py)"
