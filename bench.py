@@ -38,8 +38,8 @@ def parse():
     ap.add_argument("--level", type=int, default=8, help="icosTri refinement level (8 = headline)")
     ap.add_argument("--no-rk4", action="store_true", help="skip the RK4 step-time measurement")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
-    ap.add_argument("--variant", type=int, default=0, help="tuning: lpm_set_bve_variant value (0 = the default kernel)")
-    ap.add_argument("--max-chunks", type=int, default=0, help="tuning: upper bound on source chunks (0 = library default)")
+    ap.add_argument("--no-parity", action="store_true", help="skip the per-rank oracle parity sample")
+    ap.add_argument("--one-sided", action="store_true", help="A/B: lpm_set_symmetric(0), every ordered pair evaluated")
     return ap.parse_args()
 
 
@@ -50,20 +50,16 @@ def workload(level):
     return m, zeta
 
 
-def config_dict(level, m, world, variant=0):
-    cfg = {
+def config_dict(level, m, gpus):
+    """The workload, identical in both arms (the driver compares the two lines' configs)."""
+    return {
         "workload": f"RossbyHaurwitz54 BVE direct sum, icosTri level {level} (faceKind=3, initNest={level}): "
                     f"{m.n} targets x {m.n_active} active panels, RH54 vorticity (examples/rh54.namelist), R=1",
-        "interactions_per_step": int(m.n) * int(m.n_active) - int(m.n_active),
-        "partition": (f"LoadBalance target slices over {world} GPUs, sources replicated; slices exchanged by NVLink "
-                      "peer stores from the sum's finalize step into CUDA-IPC shared output buffers, between two "
-                      "4-byte NCCL all-reduce barriers") if world > 1 else "all targets on 1 GPU (no exchange)",
+        "interactions_per_evaluation": int(m.n) * int(m.n_active) - int(m.n_active),
+        "partition": f"targets split by the reference's LoadBalance rule (src/MPISetup.f90:132-146) over --gpus {gpus} "
+                     "ranks, sources replicated on every rank",
         "l2": "256 MiB memset between timed steps (time included); sources (63 MB) are meant to live in L2",
     }
-    if variant:
-        cfg["kernel_variant"] = (f"lpm_set_bve_variant({variant}): NOT the default kernel (tuning / experimental path, "
-                                 "see include/lpm_gpu.h and DESIGN.md 9)")
-    return cfg
 
 
 # ------------------------------------------------------------------ clocks
@@ -130,11 +126,13 @@ def cpu_leg(m, zeta, sample_targets, threads, steps=1, warmup=0):
     dt = (time.perf_counter() - t0) / steps
     act = m.is_active[tb:te] != 0
     inter = sample_targets * m.n_active - int(act.sum())
-    return inter / dt, dt, f"{sample_targets} contiguous targets [{tb},{te}) x all {m.n_active} active sources"
+    return inter / dt, dt, f"{sample_targets} contiguous targets [{tb},{te}) x all {m.n_active} active sources", inter
 
 
 def run_reference(args):
-    """--impl reference: the reference's CPU algorithm for the same path, all host threads."""
+    """--impl reference: the reference's CPU algorithm for the same path, all host threads.  One step = one
+    bounded sample of the evaluation (a contiguous block of targets x all sources): `value` is the sample's
+    interactions over the sample's time, `ms_per_step` the sample's time."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
@@ -142,15 +140,18 @@ def run_reference(args):
     threads = os.cpu_count() or 1
     per_thread = 512 if args.level >= 7 else max(8, m.n // threads // 4)
     sample = min(m.n, per_thread * threads)
-    val, dt, desc = cpu_leg(m, zeta, sample, threads, steps=max(1, args.steps), warmup=min(args.warmup, 1))
+    val, dt, desc, inter = cpu_leg(m, zeta, sample, threads, steps=max(1, args.steps), warmup=min(args.warmup, 1))
     line = {
         "impl": "reference", "metric": METRIC, "value": val, "unit": "interactions/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True,
         "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": config_dict(args.level, m, 1),
+        "config": config_dict(args.level, m, args.gpus),
         "cpu_baseline": {"value": val, "unit": "interactions/s", "cores": threads, "kind": "port",
-                         "sample": desc + " per step; C restatement of BVESphereVelocity (oracle/lpm_oracle.c, "
-                                          "-O3 -march=native), pthread workers on the LoadBalance split"},
+                         "interactions_per_step": inter,
+                         "sample": "one step = " + desc + f" = {inter} interactions ({100.0 * sample / m.n:.2f} % of an "
+                                   "evaluation), ms_per_step is that sample's time; C restatement of BVESphereVelocity "
+                                   "(oracle/lpm_oracle.c, -O3 -march=native), pthread workers on the LoadBalance split; "
+                                   "the Fortran + MPI reference cannot be built in this image (no Fortran compiler)"},
         "e2e": {"value": val, "unit": "interactions/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -176,9 +177,7 @@ def run_b200(args):
     if world > 1:
         uid = D.broadcast_unique_id(api.comm_unique_id() if rank == 0 else None)
         api.comm_init_rank(world, rank, uid)
-    api.set_bve_variant(args.variant)
-    if args.max_chunks:
-        api.set_max_chunks(args.max_chunks)
+    api.set_symmetric(not args.one_sided)
 
     m, zeta = workload(args.level)
     n, F = m.n, m.n_active
@@ -215,7 +214,7 @@ def run_b200(args):
     for _ in range(args.warmup):
         step()
     barrier()
-    api.profile_summary(reset=True)
+    api.profile_breakdown(reset=True)
     api.launch_count(reset=True)
     sampler = ClockSampler(local)
     if rank == 0:
@@ -231,7 +230,7 @@ def run_b200(args):
     barrier()
     ms_total = e0.elapsed_time(e1)
     launches = api.launch_count()
-    nk, kms = api.profile_summary(reset=True)
+    kernels = api.profile_breakdown(reset=True)
     clocks = sampler.stop() if rank == 0 else None
     ms_step = D.max_over_ranks(ms_total / args.steps, dev) if world > 1 else ms_total / args.steps
     value = inter / (ms_step * 1e-3)
@@ -256,31 +255,74 @@ def run_b200(args):
         e2e_s = D.max_over_ranks(e2e_s, dev)
     e2e_ok = bool(np.array_equal(hout[0].numpy(), out[0].cpu().numpy()))
 
+    # ---- parity sample: >= 4096 contiguous targets of THIS rank's slice against the parity build of the oracle
+    # (-O2, no contraction, the reference's own loop order), relative to the field scale, max over ranks
+    parity = None
+    if not args.no_parity:
+        from oracle import binding as O
+        cnt = min(4096, iend - ibeg)
+        tb = ibeg + (iend - ibeg - cnt) // 2
+        threads = max(1, (os.cpu_count() or 1) // world)
+        ref = O.bve_velocity_mt(threads, m.x, m.y, m.z, zeta, m.area, m.is_active, 1.0, tb, tb + cnt, fast=False)
+        err = 0.0
+        for g, r in zip(out, ref):
+            gs = g[tb:tb + cnt].cpu().numpy()
+            err = max(err, float(np.abs(gs - r[tb:tb + cnt]).max() / g.abs().max().item()))
+        if world > 1:
+            err = D.max_over_ranks(err, dev)
+        parity = {"max_rel_err": err, "tolerance": 1e-12, "targets": int(cnt * world), "ranks": world,
+                  "against": "oracle/lpm_oracle.c parity build (restatement of src/SphereBVESolver.f90:396-420), "
+                             f"{cnt} contiguous targets from the middle of every rank's slice x all sources; "
+                             "error = max |u_gpu - u_ref| over the sample / max |u| over all targets, per component"}
+
     # ---- RK4 step time through the resident solver (4 velocity sums + stream functions)
-    rk4_ms = None
+    rk4_ms, rk4_kernels = None, None
     if not args.no_rk4:
         sph = solvers.BVEMesh(m, zeta, 1.0, 2.0 * np.pi)
         sph.velocity = [t.cpu().numpy().copy() for t in out]
         sol = solvers.BVESolver(sph)
+        sol.Timestep(sph, 0.01, with_stream=True, copy_back=False)      # warm-up step
         barrier()
+        api.profile_breakdown(reset=True)
         t0 = time.perf_counter()
         sol.Timestep(sph, 0.01, with_stream=True, copy_back=False)
         barrier()
         rk4_ms = (time.perf_counter() - t0) * 1e3
+        rk4_kernels = api.profile_breakdown(reset=True)
         if world > 1:
             rk4_ms = D.max_over_ranks(rk4_ms, dev)
         sol.Delete()
 
-    # ---- roofline of the dominant kernel (ds_kernel<BveVel>) on this rank
-    my_inter = (iend - ibeg) * F
-    kern_ms = kms / max(nk, 1)
-    achieved_tf = FLOP_PER_INTERACTION * my_inter / (kern_ms * 1e-3) / 1e12
+    # ---- roofline of the dominant kernel on this rank
+    # symmetric path: sym_kernel over this rank's share of the F^2 - F active x active interactions (target blocks
+    # dealt round-robin) + ds_kernel over its slice of the (n - F) F passive-target interactions
     probe_tf, _ = api.fp64_peak_probe(20000)
-    traffic = None
+    nv = n - F
+    vb, ve = D.slice_of(nv, world, rank)
+    work = {"bve_velocity/symmetric": (F * F - F) / world, "bve_velocity/one_sided": (ve - vb) * F}
+    if "bve_velocity/symmetric" not in kernels:
+        work["bve_velocity/one_sided"] = (iend - ibeg) * F - (F if world == 1 else 0)
+    # FP64-pipe instructions per interaction in the hot loops (cuobjdump -sass)
+    executed = {"bve_velocity/symmetric": 6.3, "bve_velocity/one_sided": 9.0}
+    per_kernel = {}
+    for name, (cnt_k, ms_k) in kernels.items():
+        w = work.get(name)
+        if not w or not cnt_k:
+            continue
+        t = ms_k / cnt_k * 1e-3
+        per_kernel[name] = {"launches": cnt_k, "ms_per_launch": ms_k / cnt_k, "share_of_step": ms_k / cnt_k / (ms_total / args.steps),
+                            "interactions_per_launch": int(w),
+                            "achieved_tflops": FLOP_PER_INTERACTION * w / t / 1e12,
+                            "fp64_pipe_frac": executed[name] * 2.0 * w / t / 1e12 / probe_tf}
+    dom = max(per_kernel, key=lambda k: per_kernel[k]["ms_per_launch"]) if per_kernel else None
+    traffic, traffic_src = None, None
     prof = os.path.join(ROOT, "profiles", "bve_velocity_ncu_summary.json")
     if os.path.exists(prof):
         try:
-            traffic = json.load(open(prof)).get("dram_bytes_per_launch")
+            pj = json.load(open(prof))
+            traffic = pj.get("dram_bytes_per_launch")
+            traffic_src = ("NOT measured in this run: dram__bytes_read.sum + dram__bytes_write.sum of the dominant kernel from "
+                           "the committed ncu --set full capture " + str(pj.get("capture", "profiles/bve_velocity_ncu_summary.json")))
         except Exception:
             traffic = None
 
@@ -289,20 +331,30 @@ def run_b200(args):
             dist.destroy_process_group()
         return
 
+    domk = per_kernel.get(dom, {})
     line = {
         "metric": METRIC, "value": value, "unit": "interactions/s", "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": config_dict(args.level, m, world, args.variant),
+        "config": config_dict(args.level, m, args.gpus),
         "roofline": {
-            "bound": "fp64", "achieved": achieved_tf, "peak": probe_tf, "unit": "TFLOP/s",
-            "frac": achieved_tf / probe_tf, "traffic": traffic,
-            "note": f"algorithmic {FLOP_PER_INTERACTION:.0f} FLOP/interaction x {my_inter} interactions per launch / "
-                    f"{kern_ms:.3f} ms (CUDA events around ds_kernel<BveVel> on its stream, {nk} launches in the "
-                    "timed region); peak = DFMA probe measured in this run (MEASURED_PEAKS.json has no FP64 figure; "
-                    "nominal 148 SM x 64 DFMA/clk x 2 x 1.965 GHz = 37.2). The kernel executes 9 DFMA + 1 MUFU per "
-                    "interaction (factored cross product), so executed-pipe utilisation = frac x 18/22.",
-            "executed_dfma_frac_of_peak": achieved_tf / probe_tf * 18.0 / 22.0,
+            "bound": "fp64", "kernel": dom, "achieved": domk.get("achieved_tflops"), "peak": probe_tf, "unit": "TFLOP/s",
+            "frac": (domk.get("achieved_tflops") or 0.0) / probe_tf, "traffic": traffic, "traffic_source": traffic_src,
+            "fp64_pipe_frac": domk.get("fp64_pipe_frac"),
+            "step_frac": FLOP_PER_INTERACTION * inter / world / (ms_total / args.steps * 1e-3) / 1e12 / probe_tf,
+            "kernels": per_kernel,
+            "rk4_step_ms": rk4_ms,
+            "rk4_kernels": {k: {"launches": c, "ms": t} for k, (c, t) in (rk4_kernels or {}).items()},
+            "note": f"achieved = algorithmic {FLOP_PER_INTERACTION:.0f} FLOP/interaction (SURVEY.md 8d) x the interactions one "
+                    "launch of `kernel` covers on rank 0 / its mean duration (CUDA events on the launching stream inside the "
+                    "timed region); peak = DFMA probe measured in this run (MEASURED_PEAKS.json has no FP64 figure; nominal "
+                    "148 SM x 64 DFMA/clk x 2 x 1.965 GHz = 37.2).  frac exceeds 1 because the kernels execute fewer FP64 "
+                    "instructions than the algorithmic count: the pair-symmetric kernel shares the denominator and its "
+                    "reciprocal between i<-j and j<-i (6.3 FP64 instructions = 12.6 flop per interaction), the one-sided kernel "
+                    "factors the cross product out of the pair loop (9 = 18 flop); fp64_pipe_frac = executed FP64 "
+                    "instructions / pipe peak is the utilisation figure.  step_frac = the whole step (all kernels, finalize, "
+                    "L2 flush) on the same algorithmic count.  rk4_step_ms = one resident BVESolver Timestep (4 velocity "
+                    "sums + stream functions, no host copies), max over ranks.",
         },
         "e2e": {"value": inter / e2e_s, "unit": "interactions/s",
                 "h2d_bytes_per_step": int(world * (5 * 8 * n + 4 * n)), "d2h_bytes_per_step": int(world * 3 * 8 * n),
@@ -310,12 +362,13 @@ def run_b200(args):
                 "call": "lpm_bve_velocity (host pointers, pinned) per rank"},
         "gpu_launches": int(launches),
         "clocks": clocks,
-        "rk4_step_ms": rk4_ms,
+        "parity_sample": parity,
+        "path": "one-sided (lpm_set_symmetric(0))" if args.one_sided else "default (pair-symmetric for whole evaluations)",
     }
     if not args.no_cpu and world == 1:
         threads = os.cpu_count() or 1
         sample = min(n, (1024 if args.level >= 7 else 64) * threads)
-        val, dt, desc = cpu_leg(m, zeta, sample, threads)
+        val, dt, desc, cinter = cpu_leg(m, zeta, sample, threads)
         line["cpu_baseline"] = {"value": val, "unit": "interactions/s", "cores": threads, "kind": "port",
                                 "sample": desc + f" ({dt:.1f} s); C restatement of the reference loop "
                                                  "(oracle/lpm_oracle.c, -O3 -march=native), one pthread worker per core "

@@ -42,15 +42,6 @@ enum {
     LPM_ERR_NOMEM = 5
 };
 
-/* mesh seed identifiers, src/TypeDefs.f90:66-73 */
-enum {
-    LPM_TRI_HEX_SEED = 201,
-    LPM_QUAD_RECT_SEED = 202,
-    LPM_ICOS_TRI_SPHERE_SEED = 205,
-    LPM_CUBED_SPHERE_SEED = 206,
-    LPM_BETA_PLANE_SEED = 207
-};
-
 /* ---------------------------------------------------------------- runtime */
 
 /* Replaces MPI_INIT + MPI_COMM_SIZE for this path (examples/BVESingleGaussianVortex.f90:102-104).
@@ -290,21 +281,21 @@ int lpm_last_sum_ms(double* ms);
 /* Sum of the durations (ms) and count of the direct-sum main kernels recorded on the
  * current device since the last reset (profiling must be on). */
 int lpm_profile_summary(int reset, int64_t* nkernels, double* total_ms);
+/* The same per kernel family: entry 2 s + e holds the launches and the summed duration (ms) of sum s
+ * (0 BVE velocity, 1 BVE stream functions, 2 every other sum) on engine e (0 the one-sided ds_kernel,
+ * 1 the pair-symmetric sym_kernel). */
+int lpm_profile_breakdown(int reset, int64_t counts[6], double ms[6]);
 int64_t lpm_launch_count(int reset);
 /* 1: record events around each main kernel (adds a sync at query time only). */
 int lpm_set_profiling(int enable);
-/* Tuning knob for benchmarks: select the BVE kernel variant.  0 = default.
- * 1-99: tilings / statement orders of the one-sided kernel (44, 45: with scheduling fences); 102, 103: shapes of the
- * stream-function kernels (103: with scheduling fences);
- * 200-209: EXPERIMENTAL pair-symmetric evaluation of the velocity and stream-function sums of the sphere, plane and
- * beta-plane solvers (csrc/symmetric.cuh; opt-in, results
- * reproducible to rounding but not bit for bit -- except 204, 205, which accumulate in fixed point and give the same
- * bits whatever the order and the rank count; 206, 207 issue one atomic per CTA instead of one per warp, 208, 209 do both; in rank mode every rank must set the same value). */
-int lpm_set_bve_variant(int variant);
-/* Upper bound on the number of source chunks an evaluation is split into (work items = target
- * blocks x chunks).  More chunks = shorter CTAs = a smaller tail when few waves of CTAs fit a
- * GPU's slice; every rank must use the same value (the chunking is part of the summation order). */
-int lpm_set_max_chunks(int chunks);
+/* Evaluation strategy of the BVE velocity and stream-function sums (sphere):
+ *   1 (default)  whole evaluations of >= 200 000 active particles are done pair-symmetrically: the
+ *                denominator R^2 - x_i.x_j and its reciprocal / logarithm serve both i <- j and j <- i
+ *                (csrc/symmetric.cuh), with exact fixed-point accumulation, so results are bit-identical
+ *                from run to run and for any number of ranks;
+ *   0            always the one-sided engine (every ordered pair evaluated, as the reference does).
+ * The two differ by summation order only (~1e-13 relative).  In rank mode every rank must set the same value. */
+int lpm_set_symmetric(int enable);
 /* Evaluation order of the compactly supported PSE kernels (tests and benchmarks):
  *   0  reference order (j = 1..N over the active particles), every source tile visited;
  *   1  sources and targets in cell (Morton) order, tiles out of reach skipped (default);
@@ -315,30 +306,6 @@ int lpm_set_pse_culling(int mode);
  * tan^2(theta / 2) = |x_i cross x_j|^2 / (|x_i| |x_j| + x_i . x_j)^2 and a short series for
  * atan^2; 0 always calls sqrt + atan2 as the reference writes it.  Same value to ~1e-15. */
 int lpm_set_pse_series(int enable);
-
-/* ------------------------------------------------------ mesh (host only) */
-
-/* Uniformly refined PolyMesh2d particle set in the reference's insertion
- * order: src/PolyMesh2d.f90:135-195, src/Faces.f90:529-858. */
-typedef struct lpm_mesh lpm_mesh;
-int lpm_mesh_create(int seed_kind, int init_nest, double amp_factor, lpm_mesh** out);
-void lpm_mesh_destroy(lpm_mesh* m);
-int64_t lpm_mesh_num_particles(const lpm_mesh* m);
-int64_t lpm_mesh_num_faces(const lpm_mesh* m);        /* whole quadtree */
-int64_t lpm_mesh_num_edges(const lpm_mesh* m);        /* whole binary tree */
-int64_t lpm_mesh_num_leaf_faces(const lpm_mesh* m);
-int64_t lpm_mesh_num_leaf_edges(const lpm_mesh* m);
-double lpm_mesh_max_edge_length(const lpm_mesh* m);   /* src/Edges.f90:260-275 */
-int lpm_mesh_get_particles(const lpm_mesh* m, double* x, double* y, double* z, double* area, int32_t* is_active);
-int lpm_mesh_get_leaf_faces(const lpm_mesh* m, int32_t* verts, int32_t* center);
-/* Legacy ASCII .vtk PolyData file of the mesh and `nfields` point fields, in the layout of
- * OutputToVTK (src/SphereBVE.f90:283-328): POINTS, POLYGONS (each leaf face as triangles around
- * its centre particle), POINT_DATA (lagParam, then the fields: names[f] = "name_units", ndim[f] in
- * 1..3, data[f] = ndim[f] component arrays of N doubles stored one after the other), CELL_DATA
- * faceArea.  x, y, z: current particle positions, or NULL for the mesh's own. */
-int lpm_mesh_write_vtk(const lpm_mesh* m, const char* filename, const char* title, const double* x, const double* y,
-                       const double* z, int nfields, const char* const* names, const int* ndim,
-                       const double* const* data);
 
 #ifdef __cplusplus
 }

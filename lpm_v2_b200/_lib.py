@@ -101,34 +101,26 @@ PROTOTYPES = {
     "lpm_last_kernel_ms": (_int, [_d]),
     "lpm_last_sum_ms": (_int, [_d]),
     "lpm_profile_summary": (_int, [_int, _i64, _d]),
+    "lpm_profile_breakdown": (_int, [_int, _i64, _d]),
     "lpm_launch_count": (C.c_int64, [_int]),
     "lpm_comm_alloc_shared": (_int, [C.c_int64, C.POINTER(_vp)]),
     "lpm_comm_free_shared": (_int, [_vp]),
     "lpm_comm_is_shared": (_int, [_vp, C.c_int64]),
     "lpm_set_profiling": (_int, [_int]),
-    "lpm_set_bve_variant": (_int, [_int]),
-    "lpm_set_max_chunks": (_int, [_int]),
+    "lpm_set_symmetric": (_int, [_int]),
     "lpm_set_pse_culling": (_int, [_int]),
     "lpm_set_pse_series": (_int, [_int]),
-    # mesh
-    "lpm_mesh_create": (_int, [_int, _int, _dbl, C.POINTER(_vp)]),
-    "lpm_mesh_destroy": (None, [_vp]),
-    "lpm_mesh_num_particles": (C.c_int64, [_vp]),
-    "lpm_mesh_num_faces": (C.c_int64, [_vp]),
-    "lpm_mesh_num_edges": (C.c_int64, [_vp]),
-    "lpm_mesh_num_leaf_faces": (C.c_int64, [_vp]),
-    "lpm_mesh_num_leaf_edges": (C.c_int64, [_vp]),
-    "lpm_mesh_max_edge_length": (_dbl, [_vp]),
-    "lpm_mesh_get_particles": (_int, [_vp, _d, _d, _d, _d, _i32]),
-    "lpm_mesh_get_leaf_faces": (_int, [_vp, _i32, _i32]),
-    "lpm_mesh_write_vtk": (_int, [_vp, C.c_char_p, C.c_char_p, _d, _d, _d, _int, C.POINTER(C.c_char_p), C.POINTER(_int),
-                                  C.POINTER(_d)]),
 }
 
 for _name, (_res, _args) in PROTOTYPES.items():
     _f = getattr(lib, _name)      # AttributeError here == missing export
     _f.restype = _res
     _f.argtypes = _args
+
+
+# not part of the C ABI (csrc/lpm_gpu_tuning.h): A/B and test knob
+lib.lpm_tune.restype = _int
+lib.lpm_tune.argtypes = [C.c_char_p, _int]
 
 
 def last_error():

@@ -178,12 +178,14 @@ def set_profiling(on):
     check(lib.lpm_set_profiling(1 if on else 0))
 
 
-def set_max_chunks(c):
-    check(lib.lpm_set_max_chunks(int(c)))
+def set_symmetric(on):
+    """Whole BVE evaluations of large particle sets pair-symmetrically (default) or always one-sided."""
+    check(lib.lpm_set_symmetric(1 if on else 0))
 
 
-def set_bve_variant(v):
-    check(lib.lpm_set_bve_variant(int(v)))
+def tune(key, value):
+    """csrc/lpm_gpu_tuning.h: A/B and test knob, not part of the C ABI."""
+    check(lib.lpm_tune(key.encode(), int(value)))
 
 
 def set_pse_culling(mode):
@@ -218,6 +220,18 @@ def profile_summary(reset=True):
     k, ms = C.c_int64(0), C.c_double(0)
     check(lib.lpm_profile_summary(1 if reset else 0, C.byref(k), C.byref(ms)))
     return k.value, ms.value
+
+
+PROFILE_TAGS = ("bve_velocity/one_sided", "bve_velocity/symmetric", "bve_stream/one_sided", "bve_stream/symmetric",
+                "other/one_sided", "other/symmetric")
+
+
+def profile_breakdown(reset=True):
+    """{kernel family: (launches, total ms)} of the direct-sum main kernels since the last reset."""
+    k = (C.c_int64 * 6)()
+    ms = (C.c_double * 6)()
+    check(lib.lpm_profile_breakdown(1 if reset else 0, k, ms))
+    return {t: (int(k[i]), float(ms[i])) for i, t in enumerate(PROFILE_TAGS) if k[i]}
 
 
 # ---- remaining PSE operators (src/PSEDirectSum.f90:128-456, 537-579) ----------------

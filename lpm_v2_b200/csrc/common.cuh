@@ -94,8 +94,8 @@ struct Workspace {
     DevBuf logwin;      // int32 [2]: max |coordinate| high word, window origin of the log table (pairs.cuh)
     // spatially sorted PSE evaluation (sorted.cuh)
     DevBuf sort_tmp, sort_keys[2], sort_vals[2], sorted_active, sorted_targets, gathered[8], sorted_out[4];
-    DevBuf sym_acc;     // accumulators of the experimental symmetric paths (symmetric.cuh): doubles or fixed-point limbs
-    DevBuf sym_acc2, sym_fx;    // fixed-point mode: the accumulators as doubles; window scale (2 doubles) + max high word
+    DevBuf sym_acc;     // fixed-point accumulators of the symmetric paths (symmetric.cuh): kFxWords 64-bit words per sum
+    DevBuf sym_acc2, sym_fx;    // the same sums as doubles; FxWindow + max high word of the records
     void release()
     {
         plan.release(); sources.release(); partial.release(); bounds.release();
@@ -118,17 +118,22 @@ struct Device {
     cudaEvent_t ev_done = nullptr;       // cross-device barrier (resident solvers)
     cudaEvent_t ev_sum[2] = {nullptr, nullptr};   // profiling: around the last whole direct sum (pack, sort, kernels)
     // profiling: one event pair per direct-sum main kernel since the last reset
+    // and what it timed (lpm_profile_breakdown): tag = 2 * sum + engine; sum 0 BVE velocity, 1 BVE stream
+    // functions, 2 any other; engine 0 one-sided ds_kernel, 1 pair-symmetric sym_kernel
     std::vector<std::pair<cudaEvent_t, cudaEvent_t>> prof;
+    std::vector<int> prof_tag;
     size_t prof_used = 0;
     Workspace ws;
-    int next_prof(cudaEvent_t* b, cudaEvent_t* e)
+    int next_prof(cudaEvent_t* b, cudaEvent_t* e, int tag)
     {
         if (prof_used == prof.size()) {
             cudaEvent_t x, y;
             if (cudaEventCreate(&x) != cudaSuccess || cudaEventCreate(&y) != cudaSuccess) return LPM_ERR_CUDA;
             prof.emplace_back(x, y);
+            prof_tag.push_back(0);
         }
         *b = prof[prof_used].first; *e = prof[prof_used].second;
+        prof_tag[prof_used] = tag;
         ++prof_used;
         return LPM_OK;
     }
@@ -148,7 +153,9 @@ struct Runtime {
     std::vector<Device> devs;            // devices this process drives
     bool profiling = false;
     int64_t launches = 0;
-    int bve_variant = 0;
+    bool symmetric = true;               // pair-symmetric evaluation of whole BVE sums (lpm_set_symmetric)
+    int32_t sym_min_sources = 200000;    // ... for at least this many active particles (symmetric.cuh)
+    int sym_vel_shape = 0, sym_stream_shape = 0;            // A/B of the two stream-function shapes (round 2; the loser goes)
     bool pse_series = true;              // sphere PSE kernels: theta^2 by series inside the cut-off (false: atan2 always)
     int pse_culling = 1;                 // PSE kernels: 0 reference order, every tile; 1 cell order + tile culling; 2 cell order only
     // NCCL (rank mode)

@@ -141,23 +141,13 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity)
 
 // A never-taken branch on loaded data: it ends the basic block, so ptxas schedules the sources (or source groups)
 // one after the other instead of interleaving them, which loses the operand reuse between neighbouring
-// instructions of a phase (the kernels are bound by register operand delivery).  The payload is a signalling-NaN pattern no coordinate carries.
+// instructions of a phase (the kernels are bound by register operand delivery).  The payload is a signalling-NaN
+// pattern no coordinate carries.  Used by the symmetric velocity kernel (sym_kernels.cuh), where it measured
+// -5 %; in the one-sided kernels it measured +1.5 % (velocity) / -2.5 % (stream functions) and was dropped.
 __device__ __forceinline__ void sched_fence(double v)
 {
     if (__builtin_expect(__double2hiint(v) == 0x7ff4dead, 0)) __trap();
 }
-
-// Functors opt in with `static constexpr bool FENCE = true` (ds_kernel: after every source of the unchecked loop).
-template <class K, class = void>
-struct wants_fence { static constexpr bool value = false; };
-template <class K>
-struct wants_fence<K, decltype((void)K::FENCE)> { static constexpr bool value = K::FENCE; };
-
-// Any functor with the fence switched on (A/B variants; not measured yet)
-template <class K>
-struct Fenced : K {
-    static constexpr bool FENCE = true;
-};
 
 // What ds_kernel hands to group(): the functor's per-CTA shared table and one integer of
 // context that init_shared() returns (the log kernels' window origin).
@@ -344,7 +334,6 @@ ds_kernel(const typename K::Params prm, const DsGeom g, const double* __restrict
                 }
                 if constexpr (K::RETRY) K::template group_fast<T>(prm, tg, s, acc, worst, sctx);
                 else K::template group<T, false>(prm, tg, s, acc, 0, self, sctx);
-                if constexpr (wants_fence<K>::value) sched_fence(s[0]);
             }
             if constexpr (K::RETRY) {
                 // some argument of this thread was outside the fast path's domain: drop the

@@ -3,6 +3,9 @@
 // Host API:   stage the caller's arrays on every claimed device, run each
 //             device's LoadBalance slice, copy the slices back.
 // Device API: one slice on the current device / given stream (rank mode).
+#include <string>
+
+#include "lpm_gpu_tuning.h"
 #include "runtime.cuh"
 #include "ops.cuh"
 #include "sorted.cuh"
@@ -190,11 +193,24 @@ extern "C" int lpm_load_balance(int64_t n_items, int nprocs, int64_t* index_star
 }
 
 extern "C" int lpm_set_profiling(int enable) { rt().profiling = enable != 0; return LPM_OK; }
-extern "C" int lpm_set_bve_variant(int variant) { rt().bve_variant = variant; return LPM_OK; }
-extern "C" int lpm_set_max_chunks(int chunks)
+extern "C" int lpm_set_symmetric(int enable) { rt().symmetric = enable != 0; return LPM_OK; }
+// Not part of the C ABI (not in include/lpm_gpu.h): knobs for the A/B runs under tools/ and for tests that need a
+// small problem to take a large problem's path.  Declared in csrc/lpm_gpu_tuning.h.
+extern "C" int lpm_tune(const char* key, int value)
 {
-    if (chunks < 1 || chunks > 256) return set_error(LPM_ERR_INVALID, "lpm_set_max_chunks(%d): 1..256", chunks);
-    max_chunks_ref() = chunks;
+    const std::string k = key ? key : "";
+    if (k == "max_chunks") {
+        if (value < 1 || value > 256) return set_error(LPM_ERR_INVALID, "lpm_tune(max_chunks, %d): 1..256", value);
+        max_chunks_ref() = value;
+    } else if (k == "sym_min_sources") {
+        rt().sym_min_sources = value;
+    } else if (k == "sym_vel_shape") {
+        rt().sym_vel_shape = value;
+    } else if (k == "sym_stream_shape") {
+        rt().sym_stream_shape = value;
+    } else {
+        return set_error(LPM_ERR_INVALID, "lpm_tune: unknown key '%s'", k.c_str());
+    }
     return LPM_OK;
 }
 extern "C" int lpm_set_pse_series(int enable) { rt().pse_series = enable != 0; return LPM_OK; }
@@ -246,6 +262,23 @@ extern "C" int lpm_profile_summary(int reset, int64_t* nkernels, double* total_m
     }
     if (nkernels) *nkernels = (int64_t)d->prof_used;
     if (total_ms) *total_ms = tot;
+    if (reset) d->prof_used = 0;
+    return LPM_OK;
+}
+
+extern "C" int lpm_profile_breakdown(int reset, int64_t counts[6], double ms[6])
+{
+    Device* d = nullptr;
+    LPM_TRY(current_device(&d));
+    for (int t = 0; t < 6; ++t) { counts[t] = 0; ms[t] = 0.0; }
+    for (size_t k = 0; k < d->prof_used; ++k) {
+        LPM_CUDA(cudaEventSynchronize(d->prof[k].second));
+        float f = 0;
+        LPM_CUDA(cudaEventElapsedTime(&f, d->prof[k].first, d->prof[k].second));
+        const int t = d->prof_tag[k] >= 0 && d->prof_tag[k] < 6 ? d->prof_tag[k] : 4;
+        counts[t] += 1;
+        ms[t] += f;
+    }
     if (reset) d->prof_used = 0;
     return LPM_OK;
 }

@@ -1,0 +1,16 @@
+/* lpm_gpu_tuning.h -- NOT part of the C ABI (include/lpm_gpu.h is).  One entry point for the A/B runs under
+ * tools/ and for tests that need a small problem to take a large problem's code path.  A Fortran caller never
+ * uses it; keys may disappear without notice.
+ *   "max_chunks"        upper bound on source chunks per evaluation (every rank the same value)
+ *   "sym_min_sources"   smallest active-particle count that takes the pair-symmetric path (default 200000)
+ *   "sym_vel_shape", "sym_stream_shape"   builds under A/B (0 = default) */
+#ifndef LPM_GPU_TUNING_H
+#define LPM_GPU_TUNING_H
+#ifdef __cplusplus
+extern "C" {
+#endif
+int lpm_tune(const char* key, int value);
+#ifdef __cplusplus
+}
+#endif
+#endif

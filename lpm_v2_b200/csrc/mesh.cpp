@@ -29,7 +29,7 @@
 #include <string>
 #include <vector>
 
-#include "lpm_gpu.h"
+#include "lpm_mesh.h"
 
 namespace {
 

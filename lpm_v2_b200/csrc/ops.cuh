@@ -47,7 +47,6 @@ struct OpBveVel {
         p.R2 = a.sc[0] * a.sc[0];
         return p;
     }
-    static int variant() { return rt().bve_variant; }
 };
 
 // ---- BVE stream: in = x y z relvort absvort area; sc = radius; out = relstream absstream
@@ -70,7 +69,6 @@ struct OpBveStream {
         p.R2 = a.sc[0] * a.sc[0];
         return p;
     }
-    static int variant() { return rt().bve_variant >= 100 ? rt().bve_variant : 0; }
 };
 
 // ---- planar velocity / stream: in = x y vort area
@@ -95,7 +93,6 @@ struct OpPlane {
         p.x = a.in[0]; p.y = a.in[1];
         return p;
     }
-    static int variant() { return 0; }
 };
 using OpPlaneVel = OpPlane<PlaneVel, false>;
 using OpPlaneStream = OpPlane<PlaneStream, true>;
@@ -119,7 +116,6 @@ struct OpBetaVel {
         p.x = a.in[0]; p.y = a.in[1];
         return p;
     }
-    static int variant() { return 0; }
 };
 struct OpBetaStream {
     using K = BetaStream;
@@ -139,7 +135,6 @@ struct OpBetaStream {
         p.x = a.in[0]; p.y = a.in[1];
         return p;
     }
-    static int variant() { return 0; }
 };
 
 // ---- PSE sphere: in = x y z f area; sc = eps, sphere_radius
@@ -156,7 +151,6 @@ struct OpPseSphere {
         return LPM_OK;
     }
     static K::Params params(const Args& a);
-    static int variant() { return 0; }
 };
 
 // ---- PSE plane: in = x y f area; sc = eps
@@ -179,7 +173,6 @@ struct OpPsePlane {
         p.inv_eps2 = 1.0 / (a.sc[0] * a.sc[0]);
         return p;
     }
-    static int variant() { return 0; }
 };
 
 // ============================================================== remaining PSE operators
@@ -223,7 +216,6 @@ struct OpPseInterpSphere {
         p.c = pse_sphere_consts(a.sc[0], a.sc[1], 1.0);
         return p;
     }
-    static int variant() { return 0; }
 };
 // ---- interpolation (plane): in = x y f area; sc = eps; targets tgt[0..1]
 struct OpPseInterpPlane {
@@ -245,7 +237,6 @@ struct OpPseInterpPlane {
         p.inv_eps2 = 1.0 / (a.sc[0] * a.sc[0]);
         return p;
     }
-    static int variant() { return 0; }
 };
 
 template <class KK>
@@ -278,7 +269,6 @@ struct OpPseGradPlane {
         p.inv_eps2 = 1.0 / (a.sc[0] * a.sc[0]); p.scale = 1.0 / a.sc[0];
         return p;
     }
-    static int variant() { return 0; }
 };
 // ---- gradient (sphere): in = x y z f area; sc = eps, sphere_radius; out = gx gy gz
 struct OpPseGradSphere {
@@ -297,7 +287,6 @@ struct OpPseGradSphere {
         p.c = pse_sphere_consts(a.sc[0], a.sc[1], 1.0 / (a.sc[0] * a.sc[0]));
         return p;
     }
-    static int variant() { return 0; }
 };
 // ---- plane second partials (MODE 0, 3 outputs) / double dot (MODE 1, 1 output): in = x y gx gy area; sc = eps
 template <int MODE>
@@ -317,7 +306,6 @@ struct OpPseTensorPlane {
         p.inv_eps2 = 1.0 / (a.sc[0] * a.sc[0]); p.inv_eps = 1.0 / a.sc[0];
         return p;
     }
-    static int variant() { return 0; }
 };
 // ---- sphere double dot: in = x y z u v w area; sc = eps, sphere_radius
 struct OpPseDoubleDotSphere {
@@ -336,7 +324,6 @@ struct OpPseDoubleDotSphere {
         p.c = pse_sphere_consts(a.sc[0], a.sc[1], 1.0 / (a.sc[0] * a.sc[0]));
         return p;
     }
-    static int variant() { return 0; }
 };
 // ---- sphere divergence: in = x y z u v w area; sc = eps, sphere_radius
 struct OpPseDivSphere {
@@ -355,7 +342,6 @@ struct OpPseDivSphere {
         p.c = pse_sphere_consts(a.sc[0], a.sc[1], 1.0 / a.sc[0]);
         return p;
     }
-    static int variant() { return 0; }
 };
 
 // ---- planar SWE RHS integrals: in = x y vort div surf area; sc = eps; out = u v doubleDot lapSurf
@@ -378,7 +364,6 @@ struct OpSweRhsPlane {
         p.inv_eps2 = 1.0 / (a.sc[0] * a.sc[0]);
         return p;
     }
-    static int variant() { return 0; }
 };
 
 // ---- planar SWE velocity (PlanarSWE.f90:469-494): in = x y vort div area; out = u v
@@ -400,7 +385,6 @@ struct OpSwePlaneVel {
         p.x = a.in[0]; p.y = a.in[1];
         return p;
     }
-    static int variant() { return 0; }
 };
 
 // ---- spherical SWE RHS integrals (SphereSWESolver.f90:296-375): in = x y z vort div surf area;
@@ -426,7 +410,6 @@ struct OpSweRhsSphere {
         p.c = pse_sphere_consts(a.sc[1], a.sc[0], 1.0);      // SphereDistance uses the sphere's radius
         return p;
     }
-    static int variant() { return 0; }
 };
 
 }  // namespace lpm

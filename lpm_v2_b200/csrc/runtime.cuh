@@ -327,17 +327,22 @@ inline void launch_ds(cudaStream_t st, const typename K::Params& prm, DsGeom g, 
     ds_kernel<K, T, BLOCK, U, MINB><<<(unsigned)grid, BLOCK, smem, st>>>(prm, g, src, scan, partial);
 }
 
-// variant: 0 = automatic choice of targets-per-thread by problem size.
+// Chooses the targets-per-thread shape by problem size (never by the slice, see auto_T) and launches.
 template <class K>
-inline int launch_variant(int variant, cudaStream_t st, const typename K::Params& prm, const DsGeom& g,
-                          const double* src, const int32_t* scan, double* partial, int sm_count);
+inline int launch_auto(cudaStream_t st, const typename K::Params& prm, const DsGeom& g,
+                       const double* src, const int32_t* scan, double* partial, int sm_count);
+
+// lpm_profile_breakdown: which sum a functor belongs to (0 BVE velocity, 1 BVE stream functions, 2 other)
+template <class K> struct prof_sum_of { static constexpr int value = 2; };
+template <int RG, int ORDER> struct prof_sum_of<BveVelT<RG, ORDER>> { static constexpr int value = 0; };
+template <> struct prof_sum_of<BveStream> { static constexpr int value = 1; };
 
 // Packs nothing: the caller has already written the source records for this
 // evaluation into ws.sources (see the api functions).  Runs targets
 // [tbeg, tend) against all sources and writes the outputs named in prm.out.
 template <class K>
 inline int direct_sum(Device& dev, cudaStream_t st, const MaskPlan& mp, int64_t tbeg, int64_t tend,
-                      const typename K::Params& prm, int variant = 0, int64_t ntargets_all = -1)
+                      const typename K::Params& prm, int64_t ntargets_all = -1)
 {
     if (tend <= tbeg) return LPM_OK;
     DsGeom g{};
@@ -368,7 +373,7 @@ inline int direct_sum(Device& dev, cudaStream_t st, const MaskPlan& mp, int64_t 
     const bool prof = rt().profiling;
     cudaEvent_t pb = nullptr, pe = nullptr;
     if (prof) {
-        if (dev.next_prof(&pb, &pe) != LPM_OK) return set_error(LPM_ERR_CUDA, "cannot create profiling events");
+        if (dev.next_prof(&pb, &pe, 2 * prof_sum_of<K>::value) != LPM_OK) return set_error(LPM_ERR_CUDA, "cannot create profiling events");
         LPM_CUDA(cudaEventRecord(pb, st));
     }
     // Rank mode with outputs in shared slabs: the storing kernel writes every rank's copy over
@@ -376,8 +381,7 @@ inline int direct_sum(Device& dev, cudaStream_t st, const MaskPlan& mp, int64_t 
     // copy) and one AFTER it (every rank's stores have landed) replace the NCCL exchange.
     const bool peer_exchange = rt().rank_mode && prm2.out.nrep > 1;
     if (peer_exchange && g.nchunks == 1) LPM_TRY(comm_barrier(dev, st));
-    LPM_TRY(launch_variant<K>(variant, st, prm2, g, dev.ws.sources.as<double>(), mp.scan.as<int32_t>(), partial,
-                              dev.sm_count));
+    LPM_TRY(launch_auto<K>(st, prm2, g, dev.ws.sources.as<double>(), mp.scan.as<int32_t>(), partial, dev.sm_count));
     if (prof) LPM_CUDA(cudaEventRecord(pe, st));
     count_launch();
     if (g.nchunks > 1) {
@@ -432,8 +436,8 @@ inline int auto_T(int64_t ntgt, int nchunks, int sm_count, int block)
 }
 
 template <class K>
-inline int launch_variant(int variant, cudaStream_t st, const typename K::Params& prm, const DsGeom& g,
-                          const double* src, const int32_t* scan, double* partial, int sm_count)
+inline int launch_auto(cudaStream_t st, const typename K::Params& prm, const DsGeom& g,
+                       const double* src, const int32_t* scan, double* partial, int sm_count)
 {
     if constexpr (K::KS > 0) {
         // Log kernels carry a 64 KB table per CTA: 256 threads share it and two CTAs fit an SM.
@@ -441,19 +445,13 @@ inline int launch_variant(int variant, cudaStream_t st, const typename K::Params
         // T x U independent log chains interleaved (>= 4 FP64 instructions between producer and
         // consumer).  With its default target of ~80 registers it emitted each chain back to back
         // and the kernel stalled on DFMA latency (ncu: FP64 pipe 62 %, top stall `wait`).
-        int T = auto_T(g.nall, g.nchunks, sm_count, 256);
-        if (variant == 102 || variant == 103) T = variant;
-        switch (T) {
-            case 102: launch_ds<K, 4, 384, 2, 2>(st, prm, g, src, scan, partial); break;    // A/B: 24 warps, 80 registers
-            // A/B (not measured yet): a scheduling fence after every source; modelled 27.7 instead of 29.6 cycles per pair
-            case 103: launch_ds<Fenced<K>, 4, 256, 2, 2>(st, prm, g, src, scan, partial); break;
+        switch (auto_T(g.nall, g.nchunks, sm_count, 256)) {
             case 4: launch_ds<K, 4, 256, 2, 2>(st, prm, g, src, scan, partial); break;
             case 2: launch_ds<K, 2, 256, 2, 2>(st, prm, g, src, scan, partial); break;
             default: launch_ds<K, 1, 256, 2, 2>(st, prm, g, src, scan, partial); break;
         }
     } else {
-        int T = auto_T(g.nall, g.nchunks, sm_count, 128);
-        switch (T) {
+        switch (auto_T(g.nall, g.nchunks, sm_count, 128)) {
             case 4: launch_ds<K, 4, 128, 1>(st, prm, g, src, scan, partial); break;
             case 2: launch_ds<K, 2, 128, 2>(st, prm, g, src, scan, partial); break;
             default: launch_ds<K, 1, 128, 4>(st, prm, g, src, scan, partial); break;
@@ -462,58 +460,27 @@ inline int launch_variant(int variant, cudaStream_t st, const typename K::Params
     return LPM_OK;
 }
 
-// The BVE velocity kernel (the headline path) has extra variants for tuning.
+// The BVE velocity kernel (the headline path of round 1; now the passive-target and partial-range path).
+// 8 targets per thread (3 CTAs of 128 threads per SM) when that still leaves >= 8 waves of CTAs, else 4
+// (5 CTAs per SM), 2, 1.  The statement orders (BveVelT<4, ORDER>) are the ones tools/search_order.py
+// short-listed and the GPU sweeps measured fastest (profiles/r01b_sweep_L{7,8}_orders.log): at icosTri 8,
+// T = 8 / ORDER 3680: 1412 ms;  T = 4 / ORDER 10765: 1441 ms;  T = 4 / ORDER 0: 1499 ms.  Every shape that
+// lost a sweep (other block sizes and unrolls, register caps, one MUFU per pair or per two pairs,
+// scheduling fences: profiles/r01c_sweep_L7_caps.log, profiles/r02_ab_sym.log) is no longer built.
 template <>
-inline int launch_variant<BveVel>(int variant, cudaStream_t st, const BveVel::Params& prm, const DsGeom& g,
-                                  const double* src, const int32_t* scan, double* partial, int sm_count)
+inline int launch_auto<BveVel>(cudaStream_t st, const BveVel::Params& prm, const DsGeom& g,
+                               const double* src, const int32_t* scan, double* partial, int sm_count)
 {
     using K = BveVel;
-    if (variant >= 100) variant = 0;      // >= 100: A/B shapes of the stream-function kernels
-    if (variant == 0) {
-        // 8 targets per thread (3 CTAs of 128 threads per SM) when that still leaves >= 8 waves of
-        // CTAs, else 4 (5 CTAs per SM), 2, 1.  The statement orders (BveVelT<4, ORDER>) are the
-        // ones tools/search_order.py + tools/sweep_bve.py measured fastest: at icosTri 8,
-        // T = 8 / ORDER 3680: 1412 ms;  T = 4 / ORDER 10765: 1441 ms;  T = 4 / ORDER 0: 1499 ms.
-        const int64_t items8 = (g.nall + 128 * 8 - 1) / (128 * 8) * g.nchunks;
-        if (items8 >= 8LL * 3 * sm_count) {
-            variant = 41;
-        } else {
-            int T = auto_T(g.nall, g.nchunks, sm_count, 128);
-            variant = (T == 4) ? 32 : (T == 2) ? 5 : 6;
-        }
+    const int64_t items8 = (g.nall + 128 * 8 - 1) / (128 * 8) * g.nchunks;
+    if (items8 >= 8LL * 3 * sm_count) {
+        launch_ds<BveVelT<4, 3680>, 8, 128, 2>(st, prm, g, src, scan, partial);
+        return LPM_OK;
     }
-    switch (variant) {
-        case 1: launch_ds<K, 4, 128, 2>(st, prm, g, src, scan, partial); break;
-        case 2: launch_ds<K, 8, 128, 1>(st, prm, g, src, scan, partial); break;
-        case 3: launch_ds<K, 4, 256, 2>(st, prm, g, src, scan, partial); break;
-        case 4: launch_ds<K, 6, 128, 2>(st, prm, g, src, scan, partial); break;
-        case 5: launch_ds<K, 2, 128, 4>(st, prm, g, src, scan, partial); break;
-        case 6: launch_ds<K, 1, 128, 4>(st, prm, g, src, scan, partial); break;
-        case 7: launch_ds<K, 4, 128, 4>(st, prm, g, src, scan, partial); break;
-        case 8: launch_ds<K, 2, 256, 4>(st, prm, g, src, scan, partial); break;
-        case 9: launch_ds<K, 4, 64, 2>(st, prm, g, src, scan, partial); break;
-        case 10: launch_ds<K, 8, 64, 2>(st, prm, g, src, scan, partial); break;
-        // A/B: same tiling as variant 1 with one MUFU per pair / per two pairs
-        case 11: launch_ds<BveVelT<1>, 4, 128, 2>(st, prm, g, src, scan, partial); break;
-        case 12: launch_ds<BveVelT<2>, 4, 128, 2>(st, prm, g, src, scan, partial); break;
-        case 13: launch_ds<K, 8, 128, 2>(st, prm, g, src, scan, partial); break;
-        case 14: launch_ds<K, 4, 128, 1>(st, prm, g, src, scan, partial); break;
-        case 15: launch_ds<K, 4, 192, 2>(st, prm, g, src, scan, partial); break;
-        // Statement orders short-listed by tools/search_order.py (same arithmetic; see BveVelT in pairs.cuh)
-        // and measured by tools/sweep_bve.py (profiles/r01b_sweep_L{7,8}_orders.log).  Shapes that lost the
-        // sweeps -- register caps of 80 / 96 / 128 / 168 per thread, U = 1 with 8 targets, other orders --
-        // are no longer instantiated (profiles/r01c_sweep_L7_caps.log).
-        case 31: launch_ds<BveVelT<4, 11713>, 4, 128, 2>(st, prm, g, src, scan, partial); break;
-        case 32: launch_ds<BveVelT<4, 10765>, 4, 128, 2>(st, prm, g, src, scan, partial); break;
-        case 41: launch_ds<BveVelT<4, 3680>, 8, 128, 2>(st, prm, g, src, scan, partial); break;
-        case 43: launch_ds<BveVelT<4, 3744>, 8, 128, 2>(st, prm, g, src, scan, partial); break;
-        // A/B (not measured yet): variant 41 with a scheduling fence after every source (directsum.cuh, sched_fence);
-        // modelled 20.3 instead of 20.8 cycles per pair, 164 registers
-        case 44: launch_ds<Fenced<BveVelT<4, 3680>>, 8, 128, 2>(st, prm, g, src, scan, partial); break;
-        // the best of 160 statement orders of the fenced kernel under the fitted model (FENCED=1 tools/search_order.py):
-        // 87.1 ms at icosTri 7 against 89.3 modelled / 88.7 measured for variant 41
-        case 45: launch_ds<Fenced<BveVelT<4, 5248>>, 8, 128, 2>(st, prm, g, src, scan, partial); break;
-        default: return set_error(LPM_ERR_INVALID, "unknown BVE kernel variant %d", variant);
+    switch (auto_T(g.nall, g.nchunks, sm_count, 128)) {
+        case 4: launch_ds<BveVelT<4, 10765>, 4, 128, 2>(st, prm, g, src, scan, partial); break;
+        case 2: launch_ds<K, 2, 128, 4>(st, prm, g, src, scan, partial); break;
+        default: launch_ds<K, 1, 128, 4>(st, prm, g, src, scan, partial); break;
     }
     return LPM_OK;
 }

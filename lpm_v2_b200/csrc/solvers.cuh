@@ -206,7 +206,7 @@ struct SolverBase {
     // One direct sum over all replicas: inputs are array indices `in` (Op order),
     // outputs array indices `out`; afterwards every replica holds all n results.
     template <class Op>
-    int eval(const int* in, const int* out, const double* sc, int variant)
+    int eval(const int* in, const int* out, const double* sc)
     {
         Runtime& R = rt();
         const int nrep = (int)reps.size();
@@ -219,7 +219,7 @@ struct SolverBase {
             for (int k = 0; k < Op::NIN; ++k) a.in[k] = r.A(in[k]);
             a.mask = r.mask.as<int32_t>();
             for (int k = 0; k < 3; ++k) a.sc[k] = sc ? sc[k] : 0.0;
-            {   // opt-in experiment (symmetric.cuh): the whole sum in pair-symmetric form
+            {   // large BVE sums: the whole sum in pair-symmetric form (symmetric.cuh)
                 double* o[4] = {nullptr, nullptr, nullptr, nullptr};
                 for (int k = 0; k < Op::NOUT; ++k) o[k] = r.A(out[k]);
                 bool taken = false;
@@ -244,7 +244,7 @@ struct SolverBase {
                 for (int q = 0; q < nrep; ++q)       // own replica first, then the peers
                     for (int k = 0; k < Op::NOUT; ++k) prm.out.p[q][k] = reps[(g + q) % nrep].A(out[k]);
             }
-            LPM_TRY(direct_sum<typename Op::K>(*r.dev, r.dev->stream, r.mp, r.sb, r.se, prm, variant));
+            LPM_TRY(direct_sum<typename Op::K>(*r.dev, r.dev->stream, r.mp, r.sb, r.se, prm));
         }
         if (nrep > 1) {
             for (auto& r : reps) {
@@ -287,7 +287,7 @@ struct BveSolver : SolverBase {
         const int in[5] = {xi, yi, zi, vi, AREA};
         const int out[3] = {ox, oy, oz};
         const double sc[3] = {R, 0, 0};
-        return eval<OpBveVel>(in, out, sc, rt().bve_variant);
+        return eval<OpBveVel>(in, out, sc);
     }
 
     // src/SphereBVESolver.f90:219-353
@@ -337,7 +337,7 @@ struct BveSolver : SolverBase {
         const int in[6] = {X, Y, Z, ZETA, ABSV, AREA};
         const int out[2] = {RELS, ABSS};
         const double sc[3] = {R, 0, 0};
-        return eval<OpBveStream>(in, out, sc, OpBveStream::variant());
+        return eval<OpBveStream>(in, out, sc);
     }
 
     int diagnostics(double* ke, double* ens)
@@ -367,7 +367,7 @@ struct PlaneSolverDev : SolverBase {
     {
         const int in[4] = {xi, yi, VORT, AREA};
         const int out[2] = {ox, oy};
-        return eval<OpPlaneVel>(in, out, nullptr, 0);
+        return eval<OpPlaneVel>(in, out, nullptr);
     }
     // src/PlaneIncompressibleSolver.f90:171-259
     int timestep(double dt, bool with_stream)
@@ -401,7 +401,7 @@ struct PlaneSolverDev : SolverBase {
         if (with_stream) {                          // :258 -> src/PlanarIncompressible.f90:470-505
             const int in[4] = {X, Y, VORT, AREA};
             const int out[1] = {PSI};
-            LPM_TRY(eval<OpPlaneStream>(in, out, nullptr, 0));
+            LPM_TRY(eval<OpPlaneStream>(in, out, nullptr));
         }
         return sync();
     }
@@ -418,7 +418,7 @@ struct BetaSolverDev : SolverBase {
     {
         const int in[4] = {xi, yi, vi, AREA};
         const int out[2] = {ox, oy};
-        return eval<OpBetaVel>(in, out, nullptr, 0);
+        return eval<OpBetaVel>(in, out, nullptr);
     }
     // src/BetaPlaneSolver.f90:142-219
     int timestep(double dt, bool with_stream)
@@ -456,7 +456,7 @@ struct BetaSolverDev : SolverBase {
             if (!has_absvort) return set_error(LPM_ERR_INVALID, "stream functions need absvort");
             const int in[5] = {X, Y, ZETA, ABSV, AREA};
             const int out[2] = {RELS, ABSS};
-            LPM_TRY(eval<OpBetaStream>(in, out, nullptr, 0));
+            LPM_TRY(eval<OpBetaStream>(in, out, nullptr));
         }
         return sync();
     }

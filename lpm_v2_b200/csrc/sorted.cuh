@@ -95,9 +95,9 @@ __global__ void scatter_kernel(int64_t count, const int32_t* __restrict__ perm, 
     for (int r = 0; r < dst.nrep; ++r) dst.p[r][i] = v;
 }
 
-// Experimental pair-symmetric evaluation (symmetric.cuh, included at the end of this file): runs Op's sum that way
-// and sets *taken when lpm_set_bve_variant selects it, Op has a symmetric form and the call covers this device's /
-// rank's whole share of the targets.  out[k]: where the results go (this device's copy; in rank mode every rank
+// Pair-symmetric evaluation (symmetric.cuh, included at the end of this file): runs Op's sum that way and sets
+// *taken when Op has a symmetric form, the particle set is large enough and the call covers this device's /
+// rank's whole share of the targets (sym_applicable).  out[k]: where the results go (this device's copy; in rank mode every rank
 // ends up with all n results, so nothing is left to exchange).
 template <class Op>
 inline int sym_try(Device& dev, cudaStream_t st, MaskPlan& mp, const Args& a, double* const* out, int64_t tbeg,
@@ -164,7 +164,7 @@ inline int evaluate_impl(Device& dev, cudaStream_t st, MaskPlan& mp, const Args&
             LPM_TRY(comm_barrier(dev, st));
             LPM_TRY(comm_barrier(dev, st));
         }
-        return direct_sum<K>(dev, st, mp, tbeg, tend, prm, Op::variant(), nt);
+        return direct_sum<K>(dev, st, mp, tbeg, tend, prm, nt);
     }
     if constexpr (K::CULL) {
         constexpr int GEOM = K::CULL_GEOM;
@@ -222,7 +222,7 @@ inline int evaluate_impl(Device& dev, cudaStream_t st, MaskPlan& mp, const Args&
             LPM_TRY(ws.sorted_out[k].reserve((size_t)ns * sizeof(double)));
             prm.out.p[0][k] = ws.sorted_out[k].as<double>();
         }
-        LPM_TRY(direct_sum<K>(dev, st, mps, 0, ns, prm, Op::variant(), ns));
+        LPM_TRY(direct_sum<K>(dev, st, mps, 0, ns, prm, ns));
         Outs<Op::NOUT> o{};
         *exchanged = set_outs_shared(o, out, nt);      // the scatter is the storing kernel here
         if (*exchanged) LPM_TRY(comm_barrier(dev, st));

@@ -1,5 +1,5 @@
-// sym_kernels.cuh -- device code of the EXPERIMENTAL pair-symmetric paths (see symmetric.cuh for the
-// design and the host side).  Kept apart so that tools/sym_score.py can compile a kernel alone.
+// sym_kernels.cuh -- device code of the pair-symmetric BVE sums (see symmetric.cuh for the design and
+// the host side).  Kept apart so that a kernel can be compiled alone for SASS inspection.
 #pragma once
 #include "directsum.cuh"
 #include "pairs.cuh"
@@ -17,46 +17,70 @@ struct SymGeom {
     int32_t half_bin;       // as DsGeom::half_bin (log kernels)
 };
 
+// Window of the fixed-point accumulators of one evaluation (sym_fx_scale_kernel).
+struct FxWindow {
+    double unit;            // 2^E0: what one count of limb 0 is worth
+    int32_t fxe;            // 1075 + E0: biased exponent of a double whose 53-bit mantissa, read as an integer, counts units of 2^E0
+    int32_t pad;
+};
+
 // kernel-wide constants of the symmetric functors
 struct SymParams : LogParams {
     double R2;
-    const double* fx;       // fixed-point accumulation (kernels built with FX): fx[0] = 2^-E0, see sym_red_add
+    const FxWindow* fx;
 };
 
 // ---- order-independent accumulation ------------------------------------------------------------
-// RED.ADD.F64 makes the result depend on the order in which the CTAs' contributions land.  Every value that
-// reaches a RED here is itself deterministic (a fixed (block, tile, warp) computes it in a fixed order), so adding
-// those values EXACTLY makes the total independent of the order -- and of how the blocks were dealt to ranks.
-// In a kernel built with FX, an accumulator is kFxLimbs signed 64-bit limbs, limb k counting units of 2^(E0 + 40 k): a value is
-// split into (at most three non-zero) 40-bit pieces and each is added with an integer atomic; what lies below
-// 2^E0 -- 240 bits under the top of the window, chosen per evaluation by sym_fx_scale_kernel -- is dropped.
+// A floating-point RED would make the result depend on the order in which the CTAs' contributions land.
+// Every value that reaches an accumulator here is itself deterministic (a fixed (block, tile) computes it
+// in a fixed order), so adding those values EXACTLY makes the total independent of the order -- and of how
+// the blocks were dealt to ranks.  An accumulator is kFxLimbs signed 64-bit limbs, limb k counting units of
+// 2^(E0 + 40 k), plus one overflow counter: a value's 53-bit mantissa is shifted to its place in the window
+// and split into (at most three non-zero) 40-bit pieces, each added with an integer atomic; what lies below
+// 2^E0 -- 240 bits under the top of the window, chosen per evaluation by sym_fx_scale_kernel -- is dropped
+// (toward zero).  All of it is integer arithmetic on the otherwise idle ALU pipe: the first version split
+// the value with 12 FP64 operations per RED and cost 4-16 % of a sum (profiles/r02_ab_sym.log).
+// A value above the window (only a non-finite one, or coincident particles, can be) bumps the overflow
+// counter, and the accumulator then reads as NaN -- what the reference's 0 * Inf gives for such a pair.
 constexpr int kFxLimbs = 6;
-template <bool FX>
-__device__ __forceinline__ void sym_red_add(double* acc, size_t idx, double v, const double* __restrict__ fx)
+constexpr int kFxWords = kFxLimbs + 1;      // limbs + overflow counter
+constexpr int kFxLimbBits = 40;
+__device__ __forceinline__ void sym_red_add(double* acc, size_t idx, double v, int fxe)
 {
-    if constexpr (!FX) {
-        atomicAdd(acc + idx, v);
+    unsigned long long* a = reinterpret_cast<unsigned long long*>(acc) + idx * kFxWords;
+    const long long bits = __double_as_longlong(v);
+    const int e = (int)((bits >> 52) & 0x7ff);
+    int shift = e - fxe;                                    // v = +-m 2^shift units of 2^E0
+    if (e == 0 || shift < -52) return;                      // zero / subnormal / wholly below the window
+    if (shift > kFxLimbBits * kFxLimbs - 56) {              // above the window (or Inf / NaN)
+        atomicAdd(a + kFxLimbs, 1ULL);
         return;
     }
-    unsigned long long* a = reinterpret_cast<unsigned long long*>(acc) + idx * kFxLimbs;
-    constexpr double unit[kFxLimbs] = {0x1p0, 0x1p40, 0x1p80, 0x1p120, 0x1p160, 0x1p200};
-    constexpr double inv[kFxLimbs] = {0x1p0, 0x1p-40, 0x1p-80, 0x1p-120, 0x1p-160, 0x1p-200};
-    double r = v * fx[0];                   // a power of two: exact
-#pragma unroll
-    for (int k = kFxLimbs - 1; k >= 0; --k) {
-        const double t = trunc(r * inv[k]);
-        r = fma(-t, unit[k], r);            // exact: t unit[k] is the part of r at and above 2^(40 k)
-        if (t != 0.0) atomicAdd(a + k, (unsigned long long)(long long)t);
+    unsigned long long m = ((unsigned long long)bits & 0x000fffffffffffffULL) | 0x0010000000000000ULL;
+    if (shift < 0) {
+        m >>= -shift;
+        shift = 0;
     }
+    const int k = shift / kFxLimbBits, o = shift - kFxLimbBits * k;     // m 2^o spans limbs k .. k + 2
+    const unsigned long long lo = m << o, hi = o ? (m >> (64 - o)) : 0ULL;
+    constexpr unsigned long long MASK = (1ULL << kFxLimbBits) - 1;
+    unsigned long long p0 = lo & MASK, p1 = ((lo >> kFxLimbBits) | (hi << (64 - kFxLimbBits))) & MASK,
+                       p2 = hi >> (2 * kFxLimbBits - 64);
+    if (bits < 0) {                                         // limbs are signed (two's complement)
+        p0 = 0ULL - p0; p1 = 0ULL - p1; p2 = 0ULL - p2;
+    }
+    if (p0) atomicAdd(a + k, p0);
+    if (p1) atomicAdd(a + k + 1, p1);
+    if (p2) atomicAdd(a + k + 2, p2);
 }
 
 // Warp reduction of cb[s][a] (thread-local sums for SB sources, NC <= 3 components) by recursive
 // halving, then one RED per (source, component) from the lane that ends up owning it.
 // After the halving levels lane l holds source ((l >> (5 - LV)) & (SB - 1)) summed over the lanes
 // that differ from it in the high LV bits; a butterfly over the remaining low bits finishes the sum.
-template <int SB, int NC, bool FX, bool COMBINE = false>
+template <int SB, int NC, bool COMBINE = false>
 __device__ __forceinline__ void sym_reduce_red(double (&cb)[SB][NC], int lane, double* __restrict__ acc, size_t idx0,
-                                               const double* __restrict__ fx, double* __restrict__ slot = nullptr)
+                                               int fxe, double* __restrict__ slot = nullptr)
 {
     static_assert(SB == 8 || SB == 4, "source batch");
     static_assert(NC >= 1 && NC <= 3, "components per source");
@@ -98,7 +122,7 @@ __device__ __forceinline__ void sym_reduce_red(double (&cb)[SB][NC], int lane, d
         if (q < NC) {
             const double val = q == 0 ? v[0] : (q == 1 ? v[NC > 1 ? 1 : 0] : v[NC > 2 ? 2 : 0]);
             if constexpr (COMBINE) slot[sidx * NC + q] = val;      // this warp's sum; joined with the other warps' after the tile
-            else sym_red_add<FX>(acc, idx0 + sidx * NC + q, val, fx);
+            else sym_red_add(acc, idx0 + sidx * NC + q, val, fxe);
         }
     } else {
         const bool b4 = (lane & 16) != 0, b3 = (lane & 8) != 0;
@@ -128,7 +152,7 @@ __device__ __forceinline__ void sym_reduce_red(double (&cb)[SB][NC], int lane, d
         if (q < NC) {
             const double val = q == 0 ? v[0] : (q == 1 ? v[NC > 1 ? 1 : 0] : v[NC > 2 ? 2 : 0]);
             if constexpr (COMBINE) slot[sidx * NC + q] = val;      // this warp's sum; joined with the other warps' after the tile
-            else sym_red_add<FX>(acc, idx0 + sidx * NC + q, val, fx);
+            else sym_red_add(acc, idx0 + sidx * NC + q, val, fxe);
         }
     }
 }
@@ -401,272 +425,13 @@ struct SymBveStream : LogSharedTable<32> {
     }
 };
 
-// Planar Biot-Savart (PlaneVel in pairs.cuh): u_i -= dy s_j / r^2, v_i += dx s_j / r^2 with dx = x_i - x_j,
-// dy = y_i - y_j, s_j = omega_j A_j / (2 pi); record x, y, s, 0.  The pair shares dx, dy, r^2 and 1 / r^2:
-// 2 + 2 + 3 + (1 + 2) + (1 + 2) = 13 FP64 instructions for two interactions instead of 20.  The transposed
-// direction sees -dx, -dy:  u_j += dy s_i / r^2,  v_j -= dx s_i / r^2.
-// Null SOURCE records sit at (+1e37, +1e37) (pack_plane); a null TARGET is put at (-1e37, -1e37), so that no pair
-// has r^2 = 0 -- a zero would poison the reciprocal the four targets of a thread share.
-//   ORDER bit 0: a scheduling fence after every source (sched_fence)
-struct SymPlaneVel : NoSharedTable {
-    static constexpr int NS = 4, NA = 2, NC = 2;
-    struct Tgt { double x, y, s; };
-    __device__ static __forceinline__ Tgt null() { return Tgt{-LPM_PLANE_FAR, -LPM_PLANE_FAR, 0.0}; }
-    __device__ static __forceinline__ Tgt from_record(const double2* p2)
-    {
-        const double2 v0 = p2[0], v1 = p2[1];
-        return Tgt{v0.x, v0.y, v1.x};
-    }
-    template <int T, int SB, int ORDER>
-    __device__ static __forceinline__ void batch(const SymParams&, const Tgt (&tg)[T], double (&a)[T][NA],
-                                                 const double* __restrict__ sm, double (&cb)[SB][NC], const SharedCtx&)
-    {
-#pragma unroll
-        for (int u = 0; u < SB; ++u) {
-            const double2* p2 = reinterpret_cast<const double2*>(sm + u * NS);
-            const double2 v0 = p2[0], v1 = p2[1];
-            double dx[T], dy[T], r2[T], r[T];
-#pragma unroll
-            for (int t = 0; t < T; ++t) {
-                dx[t] = tg[t].x - v0.x; dy[t] = tg[t].y - v0.y;
-                r2[t] = fma(dx[t], dx[t], dy[t] * dy[t]);
-            }
-            rcp_batch<T>(r2, r);
-#pragma unroll
-            for (int t = 0; t < T; ++t) {
-                const double w = r[t] * v1.x;
-                a[t][0] = fma(-dy[t], w, a[t][0]);
-                a[t][1] = fma(dx[t], w, a[t][1]);
-            }
-            {
-                const double w = r[0] * tg[0].s;
-                cb[u][0] = dy[0] * w; cb[u][1] = -dx[0] * w;
-            }
-#pragma unroll
-            for (int t = 1; t < T; ++t) {
-                const double w = r[t] * tg[t].s;
-                cb[u][0] = fma(dy[t], w, cb[u][0]);
-                cb[u][1] = fma(-dx[t], w, cb[u][1]);
-            }
-            if constexpr ((ORDER & 1) != 0) sched_fence(v0.x);
-        }
-    }
-    // as PlaneVel::group<T, true>
-    template <int T>
-    __device__ static __forceinline__ void diag(const SymParams&, const Tgt (&tg)[T], double (&a)[T][NA],
-                                                const double (&s)[NS], const bool (&isself)[T], const SharedCtx&)
-    {
-        double dx[T], dy[T], r2[T], r[T];
-#pragma unroll
-        for (int t = 0; t < T; ++t) {
-            dx[t] = tg[t].x - s[0]; dy[t] = tg[t].y - s[1];
-            r2[t] = fma(dx[t], dx[t], dy[t] * dy[t]);
-            r2[t] = isself[t] ? 1.0 : r2[t];
-        }
-        rcp_batch<T>(r2, r);
-#pragma unroll
-        for (int t = 0; t < T; ++t) {
-            double w = r[t] * s[2];
-            w = isself[t] ? 0.0 : w;
-            a[t][0] = fma(-dy[t], w, a[t][0]);
-            a[t][1] = fma(dx[t], w, a[t][1]);
-        }
-    }
-};
-
-// Beta-plane Biot-Savart (BetaVel in pairs.cuh); record sinh(pi y), cosh(pi y), sin(pi x), cos(pi x), zeta A / 2, 0.
-// With S = sinh(pi dy), C = cosh(pi dy), s = sin(pi dx), c = cos(pi dx) from the addition formulas:
-// u_i -= S C w_j / (S^2 + s^2),  v_i += s c w_j / (S^2 + s^2).  Swapping the pair flips the signs of S and s only, so
-// the eight addition-formula operations, the denominator, S C, s c and the reciprocal (15 of 18 FP64 instructions)
-// serve both directions:  u_j += S C w_i / (..),  v_j -= s c w_i / (..):  21 instructions for two interactions.
-// A null TARGET is (-1e10, 1e10, 0, 1) against the null source record's (+1e10, 1e10, 0, 1): no pair has S = s = 0.
-//   ORDER bit 0: a scheduling fence after every source (sched_fence)
-struct SymBetaVel : NoSharedTable {
-    static constexpr int NS = 6, NA = 2, NC = 2;
-    struct Tgt { double sh, ch, sn, cs, w; };
-    __device__ static __forceinline__ Tgt null() { return Tgt{-1.0e10, 1.0e10, 0.0, 1.0, 0.0}; }
-    __device__ static __forceinline__ Tgt from_record(const double2* p2)
-    {
-        const double2 v0 = p2[0], v1 = p2[1], v2 = p2[2];
-        return Tgt{v0.x, v0.y, v1.x, v1.y, v2.x};
-    }
-    template <int T>
-    __device__ static __forceinline__ void pair_terms(const Tgt (&tg)[T], const double (&s)[NS], double (&SC)[T],
-                                                      double (&sc)[T], double (&den)[T])
-    {
-#pragma unroll
-        for (int t = 0; t < T; ++t) {
-            const double S = fma(tg[t].sh, s[1], -(tg[t].ch * s[0]));
-            const double C = fma(tg[t].ch, s[1], -(tg[t].sh * s[0]));
-            const double sn = fma(tg[t].sn, s[3], -(tg[t].cs * s[2]));
-            const double cs = fma(tg[t].cs, s[3], tg[t].sn * s[2]);
-            den[t] = fma(S, S, sn * sn);
-            SC[t] = S * C; sc[t] = sn * cs;
-        }
-    }
-    template <int T, int SB, int ORDER>
-    __device__ static __forceinline__ void batch(const SymParams&, const Tgt (&tg)[T], double (&a)[T][NA],
-                                                 const double* __restrict__ sm, double (&cb)[SB][NC], const SharedCtx&)
-    {
-#pragma unroll
-        for (int u = 0; u < SB; ++u) {
-            double s[NS], SC[T], sc[T], den[T], r[T];
-            const double2* p2 = reinterpret_cast<const double2*>(sm + u * NS);
-#pragma unroll
-            for (int q = 0; q < NS / 2; ++q) {
-                const double2 v = p2[q];
-                s[2 * q] = v.x; s[2 * q + 1] = v.y;
-            }
-            pair_terms<T>(tg, s, SC, sc, den);
-            rcp_batch<T>(den, r);
-#pragma unroll
-            for (int t = 0; t < T; ++t) {
-                const double w = r[t] * s[4];
-                a[t][0] = fma(-SC[t], w, a[t][0]);
-                a[t][1] = fma(sc[t], w, a[t][1]);
-            }
-            {
-                const double w = r[0] * tg[0].w;
-                cb[u][0] = SC[0] * w; cb[u][1] = -sc[0] * w;
-            }
-#pragma unroll
-            for (int t = 1; t < T; ++t) {
-                const double w = r[t] * tg[t].w;
-                cb[u][0] = fma(SC[t], w, cb[u][0]);
-                cb[u][1] = fma(-sc[t], w, cb[u][1]);
-            }
-            if constexpr ((ORDER & 1) != 0) sched_fence(s[1]);
-        }
-    }
-    // as BetaVel::group<T, true>
-    template <int T>
-    __device__ static __forceinline__ void diag(const SymParams&, const Tgt (&tg)[T], double (&a)[T][NA],
-                                                const double (&s)[NS], const bool (&isself)[T], const SharedCtx&)
-    {
-        double SC[T], sc[T], den[T], r[T];
-        pair_terms<T>(tg, s, SC, sc, den);
-#pragma unroll
-        for (int t = 0; t < T; ++t) den[t] = isself[t] ? 1.0 : den[t];
-        rcp_batch<T>(den, r);
-#pragma unroll
-        for (int t = 0; t < T; ++t) {
-            double w = r[t] * s[4];
-            w = isself[t] ? 0.0 : w;
-            a[t][0] = fma(-SC[t], w, a[t][0]);
-            a[t][1] = fma(sc[t], w, a[t][1]);
-        }
-    }
-};
-
-// Planar and beta-plane stream functions (PlaneStream, BetaStream in pairs.cuh): psi_i = sum_j w_j ln(arg_ij) with a
-// symmetric argument (r^2, resp. 2 (S^2 + s^2)), so the argument and its logarithm serve both directions; as
-// SymBveStream with the retry branch per source.  G supplies the geometry:
-//   NS, NW            doubles per record, weights per particle (1 or 2)
-//   Tgt, null(), from_record()
-//   arg(tgt, s)       the logarithm's argument for one pair;  tw(tgt, k), sw(s, k)  the k-th weight of target / source
-template <class G>
-struct SymLogStream : LogSharedTable<32> {
-    static constexpr int NS = G::NS, NA = G::NW, NC = G::NW;
-    using Tgt = typename G::Tgt;
-    __device__ static __forceinline__ Tgt null() { return G::null(); }
-    __device__ static __forceinline__ Tgt from_record(const double2* p2) { return G::from_record(p2); }
-    template <int T, int SB, int ORDER>
-    __device__ static __forceinline__ void batch(const SymParams&, const Tgt (&tg)[T], double (&a)[T][NA],
-                                                 const double* __restrict__ sm, double (&cb)[SB][NC], const SharedCtx& sc)
-    {
-#pragma unroll
-        for (int u = 0; u < SB; ++u) {
-            double s[NS], d[T], l[T];
-            const double2* p2 = reinterpret_cast<const double2*>(sm + u * NS);
-#pragma unroll
-            for (int q = 0; q < NS / 2; ++q) {
-                const double2 v = p2[q];
-                s[2 * q] = v.x; s[2 * q + 1] = v.y;
-            }
-            unsigned worst = 0;
-#pragma unroll
-            for (int t = 0; t < T; ++t) d[t] = G::arg(tg[t], s);
-            log_group_fast<KS, T>(d, l, worst, sc);
-            if (__builtin_expect(needs_retry(worst), 0)) {
-#pragma unroll
-                for (int t = 0; t < T; ++t) l[t] = log_slow_path(d[t]);
-            }
-#pragma unroll
-            for (int k = 0; k < NA; ++k) {
-#pragma unroll
-                for (int t = 0; t < T; ++t) a[t][k] = fma(l[t], G::sw(s, k), a[t][k]);
-                cb[u][k] = l[0] * G::tw(tg[0], k);
-#pragma unroll
-                for (int t = 1; t < T; ++t) cb[u][k] = fma(l[t], G::tw(tg[t], k), cb[u][k]);
-            }
-        }
-    }
-    template <int T>
-    __device__ static __forceinline__ void diag(const SymParams&, const Tgt (&tg)[T], double (&a)[T][NA],
-                                                const double (&s)[NS], const bool (&isself)[T], const SharedCtx& sc)
-    {
-        double d[T], l[T];
-#pragma unroll
-        for (int t = 0; t < T; ++t) {
-            d[t] = G::arg(tg[t], s);
-            d[t] = isself[t] ? 1.0 : d[t];          // any positive value; the pair is zeroed below
-        }
-        log_group<KS, T>(d, l, sc);
-#pragma unroll
-        for (int t = 0; t < T; ++t) {
-            l[t] = isself[t] ? 0.0 : l[t];
-#pragma unroll
-            for (int k = 0; k < NA; ++k) a[t][k] = fma(l[t], G::sw(s, k), a[t][k]);
-        }
-    }
-};
-// record x, y, omega A / (4 pi), 0;  arg = r^2
-struct PlaneStreamGeom {
-    static constexpr int NS = 4, NW = 1;
-    struct Tgt { double x, y, w; };
-    __device__ static __forceinline__ Tgt null() { return Tgt{-LPM_PLANE_FAR, -LPM_PLANE_FAR, 0.0}; }
-    __device__ static __forceinline__ Tgt from_record(const double2* p2)
-    {
-        const double2 v0 = p2[0], v1 = p2[1];
-        return Tgt{v0.x, v0.y, v1.x};
-    }
-    __device__ static __forceinline__ double arg(const Tgt& t, const double (&s)[NS])
-    {
-        const double dx = t.x - s[0], dy = t.y - s[1];
-        return fma(dx, dx, dy * dy);
-    }
-    __device__ static __forceinline__ double tw(const Tgt& t, int) { return t.w; }
-    __device__ static __forceinline__ double sw(const double (&s)[NS], int) { return s[2]; }
-};
-// record sinh(pi y), cosh(pi y), sin(pi x), cos(pi x), zeta A / (4 pi), omega A / (4 pi);  arg = 2 (S^2 + s^2)
-struct BetaStreamGeom {
-    static constexpr int NS = 6, NW = 2;
-    struct Tgt { double sh, ch, sn, cs, w0, w1; };
-    __device__ static __forceinline__ Tgt null() { return Tgt{-1.0e10, 1.0e10, 0.0, 1.0, 0.0, 0.0}; }
-    __device__ static __forceinline__ Tgt from_record(const double2* p2)
-    {
-        const double2 v0 = p2[0], v1 = p2[1], v2 = p2[2];
-        return Tgt{v0.x, v0.y, v1.x, v1.y, v2.x, v2.y};
-    }
-    __device__ static __forceinline__ double arg(const Tgt& t, const double (&s)[NS])
-    {
-        const double S = fma(t.sh, s[1], -(t.ch * s[0]));
-        const double sn = fma(t.sn, s[3], -(t.cs * s[2]));
-        return 2.0 * fma(S, S, sn * sn);
-    }
-    __device__ static __forceinline__ double tw(const Tgt& t, int k) { return k == 0 ? t.w0 : t.w1; }
-    __device__ static __forceinline__ double sw(const double (&s)[NS], int k) { return s[4 + k]; }
-};
-using SymPlaneStream = SymLogStream<PlaneStreamGeom>;
-using SymBetaStream = SymLogStream<BetaStreamGeom>;
-
 // ---- the kernel ---------------------------------------------------------------
-// acc: [nsrc_pad][NC] doubles -- or, with prm.fx, [nsrc_pad][NC][kFxLimbs] 64-bit limbs -- zeroed by the caller
+// acc: [nsrc_pad][NC][kFxWords] 64-bit words (fixed-point limbs + overflow counter, see sym_red_add), zeroed by the caller
 // (NA == NC: both directions feed the same sums).
 // dynamic shared memory: [2 tiles][K::KS table][2 mbarriers] and, with COMBINE, [2][warps][TS][NC] per-warp source sums:
 // the warps' sums for a tile are added in warp order after the tile and ONE RED per (CTA, source, component) is
 // issued instead of one per warp (a quarter of the atomics with 128 threads)
-template <class K, int T, int BLOCK, int SB, int MINB, int ORDER = 0, bool FX = false, bool COMBINE = false>
+template <class K, int T, int BLOCK, int SB, int MINB, int ORDER = 0, bool COMBINE = false>
 __global__ void __launch_bounds__(BLOCK, MINB)
 sym_kernel(const SymParams prm, const SymGeom g, const double* __restrict__ src, double* __restrict__ acc)
 {
@@ -707,6 +472,7 @@ sym_kernel(const SymParams prm, const SymGeom g, const double* __restrict__ src,
         for (int q = 0; q < NA; ++q) a[t][q] = 0.0;
     }
     const SharedCtx sctx{ks, K::init_shared(ks, prm, tid, BLOCK), g.half_bin};
+    const int fxe = prm.fx->fxe;
     if (tid == 0) {
         mbar_init(&full[0], 1);
         mbar_init(&full[1], 1);
@@ -745,7 +511,7 @@ sym_kernel(const SymParams prm, const SymGeom g, const double* __restrict__ src,
         for (int jb = 0; jb < TS; jb += SB) {
             double cb[SB][NC];
             K::template batch<T, SB, ORDER>(prm, tg, a, sm + jb * NS, cb, sctx);
-            sym_reduce_red<SB, NC, FX, COMBINE>(cb, lane, acc, ((size_t)k * TS + jb) * NC, prm.fx, mine + jb * NC);
+            sym_reduce_red<SB, NC, COMBINE>(cb, lane, acc, ((size_t)k * TS + jb) * NC, fxe, mine + jb * NC);
         }
     };
     // COMBINE: after the barrier that ends tile k, add the warps' sums in warp order and issue the REDs.  The slots are
@@ -756,7 +522,7 @@ sym_kernel(const SymParams prm, const SymGeom g, const double* __restrict__ src,
             double sum = base[idx];
 #pragma unroll
             for (int w = 1; w < NW; ++w) sum += base[(size_t)w * TS * NC + idx];
-            sym_red_add<FX>(acc, (size_t)k * TS * NC + idx, sum, prm.fx);
+            sym_red_add(acc, (size_t)k * TS * NC + idx, sum, fxe);
         }
     };
 
@@ -781,7 +547,7 @@ sym_kernel(const SymParams prm, const SymGeom g, const double* __restrict__ src,
     for (int t = 0; t < T; ++t)
         if (cidx[t] < g.nsrc) {
 #pragma unroll
-            for (int q = 0; q < NA; ++q) sym_red_add<FX>(acc, (size_t)cidx[t] * NA + q, a[t][q], prm.fx);
+            for (int q = 0; q < NA; ++q) sym_red_add(acc, (size_t)cidx[t] * NA + q, a[t][q], fxe);
         }
 }
 
@@ -795,42 +561,45 @@ constexpr size_t sym_smem_bytes()
 // Window of the fixed-point accumulators for one evaluation.  maxhi: high word of the largest |entry| of the source
 // records (coordinates and strengths; absmax_hi_kernel).  mode 0 (velocity): |sum| <= F M / d_min with
 // d_min >= R^2 2^-110 (two FP64 points cannot be closer); mode 1 (stream functions): |ln| < 2^10.  The top of the
-// window sits there, E0 240 bits below.  fx[0] = 2^-E0, fx[1] = 2^E0.
-__global__ void sym_fx_scale_kernel(int mode, double R2, int32_t nsrc, const int32_t* __restrict__ maxhi, double* __restrict__ fx)
+// window sits 8 bits above that bound, E0 = top - 240.
+__global__ void sym_fx_scale_kernel(int mode, double R2, int32_t nsrc, const int32_t* __restrict__ maxhi, FxWindow* __restrict__ fx)
 {
     const int eM = ((*maxhi >> 20) & 0x7ff) - 1023 + 1;
     int eF = 1;
     while ((1 << eF) < nsrc && eF < 31) ++eF;
     const int eR = ((__double2hiint(R2) >> 20) & 0x7ff) - 1023;
-    int top = eM + eF + (mode == 0 ? 110 - eR : 12);
-    int e0 = top - 40 * kFxLimbs;
+    const int top = eM + eF + (mode == 0 ? 110 - eR : 12) + 8;
+    int e0 = top - kFxLimbBits * kFxLimbs;
     if (e0 > 700) e0 = 700;
     if (e0 < -900) e0 = -900;
-    fx[0] = __hiloint2double((1023 - e0) << 20, 0);
-    fx[1] = __hiloint2double((1023 + e0) << 20, 0);
+    fx->unit = __hiloint2double((1023 + e0) << 20, 0);
+    fx->fxe = 1075 + e0;
+    fx->pad = 0;
 }
 
-// limbs -> doubles: carries first (so that every limb but the top one is below 2^40), then the sum from the top
+// limbs -> doubles: carries first (so that every limb but the top one is below 2^40), then the sum from the top;
+// an accumulator whose overflow counter is set reads as NaN (see sym_red_add)
 __global__ void __launch_bounds__(256)
-sym_fx_to_double_kernel(int64_t nvalues, const long long* __restrict__ limbs, const double* __restrict__ fx,
+sym_fx_to_double_kernel(int64_t nvalues, const long long* __restrict__ words, const FxWindow* __restrict__ fx,
                         double* __restrict__ out)
 {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= nvalues) return;
     long long l[kFxLimbs];
 #pragma unroll
-    for (int k = 0; k < kFxLimbs; ++k) l[k] = limbs[i * kFxLimbs + k];
+    for (int k = 0; k < kFxLimbs; ++k) l[k] = words[i * kFxWords + k];
+    const long long over = words[i * kFxWords + kFxLimbs];
 #pragma unroll
     for (int k = 0; k + 1 < kFxLimbs; ++k) {
-        const long long carry = l[k] >> 40;         // arithmetic shift: floor
-        l[k] -= carry << 40;
+        const long long carry = l[k] >> kFxLimbBits;        // arithmetic shift: floor
+        l[k] -= carry << kFxLimbBits;
         l[k + 1] += carry;
     }
     constexpr double unit[kFxLimbs] = {0x1p0, 0x1p40, 0x1p80, 0x1p120, 0x1p160, 0x1p200};
     double s = 0.0;
 #pragma unroll
     for (int k = kFxLimbs - 1; k >= 0; --k) s = fma((double)l[k], unit[k], s);
-    out[i] = s * fx[1];
+    out[i] = over != 0 ? __longlong_as_double(0x7ff8000000000000LL) : s * fx->unit;
 }
 
 // u_i = x_i cross a_i for the active particles (BveVelT::finalize)
@@ -848,7 +617,7 @@ sym_bve_finalize(int32_t nsrc, const int32_t* __restrict__ active, const double*
     out.store(2, i, fma(x, a1, -(y * a0)));
 }
 
-// two sums per active particle, copied out (BveStream::finalize, PlaneVel::finalize)
+// two sums per active particle, copied out (BveStream::finalize)
 __global__ void __launch_bounds__(256)
 sym_stream_finalize(int32_t nsrc, const int32_t* __restrict__ active, const double* __restrict__ acc, Outs<2> out)
 {
@@ -857,15 +626,6 @@ sym_stream_finalize(int32_t nsrc, const int32_t* __restrict__ active, const doub
     const int64_t i = active[c];
     out.store(0, i, acc[(size_t)c * 2]);
     out.store(1, i, acc[(size_t)c * 2 + 1]);
-}
-
-// one sum per active particle, copied out (PlaneStream::finalize)
-__global__ void __launch_bounds__(256)
-sym_copy1_finalize(int32_t nsrc, const int32_t* __restrict__ active, const double* __restrict__ acc, Outs<1> out)
-{
-    const int32_t c = blockIdx.x * blockDim.x + threadIdx.x;
-    if (c >= nsrc) return;
-    out.store(0, active[c], acc[c]);
 }
 
 // passive[i - scan[i]] = i for every particle with mask 0 (stable, like the active list)

@@ -1,12 +1,16 @@
-// symmetric.cuh -- EXPERIMENTAL, opt-in (lpm_set_bve_variant(200 .. 203)); NOT the default path and not
-// yet measured on a GPU.  Pair-symmetric evaluation of the BVE velocity sum.
+// symmetric.cuh -- pair-symmetric evaluation of the BVE velocity and stream-function sums: the default for
+// whole evaluations of large particle sets (sym_applicable below), with order-independent fixed-point
+// accumulation.  Measured at icosTri 8 on one B200 (profiles/r02_ab_sym.log, the round-2 A/B): velocity
+// 1410 -> 1325 ms, stream functions 2227 -> 1903 ms with the first fixed-point accumulation; the FP64-atomic
+// builds (1271 / 1771 ms) were deleted because their results depended on the order in which atomics land.
 //
 // The reference (src/SphereBVESolver.f90:396-420) visits every ordered pair (i, j): for the
 // factored form used here, a_i = sum_j P_j / d_ij with d_ij = R^2 - x_i.x_j = d_ji.  Active
 // particles are both targets and sources, so for two active particles c < c' the denominator --
 // 3 DFMA -- and its reciprocal -- 3 more -- serve both a_c += P_c' / d and a_c' += P_c / d:
-// 12 FP64 instructions for two interactions instead of 18.  At icosTri 8 two thirds of all
-// interactions are active-active (1 310 720^2 of 2.577e12).
+// 12 FP64 instructions for two interactions instead of 18 (stream functions: the denominator and the
+// logarithm, 13 instead of 22).  At icosTri 8 two thirds of all interactions are active-active
+// (1 310 720^2 of 2.577e12).
 //
 //   * passive targets (vertices) x all active sources: the one-sided engine (directsum.cuh) on the
 //     gathered passive particles;
@@ -17,33 +21,25 @@
 //     pair is evaluated once: the thread adds P_j / d to its targets' sums and, per source, sums
 //     P_t / d over its T targets.  Those per-source sums are reduced across the warp by
 //     recursive halving over batches of SB sources (SB (2 SHFL + DADD) per level instead of a full
-//     butterfly per source: ~3.4 DADD per source per thread against 12 T of pair work) and added
-//     to the source's accumulator in global memory with RED.ADD.F64 -- one per (warp, source,
-//     component).  A CTA's own sums join the same accumulators when it ends.
+//     butterfly per source), the warps' sums are joined in shared memory in warp order (velocity), and the
+//     result is added to the source's accumulator in global memory -- exactly, in fixed point
+//     (sym_red_add), so the total does not depend on the order of the adds nor on how target blocks
+//     were dealt to ranks.  A CTA's own sums join the same accumulators when it ends.
 //   * u_i = x_i cross a_i in a finalize kernel.
 //
-// The accumulation order of the atomics is not fixed, so results are reproducible to rounding
-// (~1e-16 relative), not bit for bit; the default path keeps its bitwise guarantees.
+// Results are bit-identical from run to run and for any rank count (tests/test_sym_gpu.py,
+// tests/test_multigpu.py); they differ from the one-sided path's by summation order only.
 #pragma once
 #include "ops.cuh"
 #include "sym_kernels.cuh"
 
 namespace lpm {
 
-// lpm_set_bve_variant values that select the symmetric paths (shape = variant - 200):
-//   velocity          200: 4 targets per thread, batches of 8 sources, a scheduling fence per source (ORDER 35)
-//                     201: 8 targets per thread, batches of 4, fenced        202 / 203: the same two without fences (ORDER 27)
-//   stream functions  200: 256 threads, retry branch per source (ORDER 1)    201: 128 threads, retry per batch (ORDER 0)
-//                     202: 256 threads, retry per batch                      203: 128 threads, retry per source
-constexpr int kSymVariant = 200;
-constexpr int kSymVariantLast = 209;        // 204, 205: shapes 200, 201 with fixed-point (order-independent) accumulation
-constexpr int kSymVariantFx = 204;          // 206, 207: shapes 200, 201 with the warps' source sums combined in shared memory;
-                                            // 208, 209: both (fixed point, a quarter of the atomics)
-inline bool sym_fixed_point(int variant) { const int s = variant - kSymVariant; return s == 4 || s == 5 || s == 8 || s == 9; }
-// shape 0..3 of a variant for the sums that have no special build for it
-inline int sym_shape(int variant) { const int s = variant - kSymVariant; return s < 4 ? s : (s & 1); }
+// Below this many active particles the triangular grid is too few CTAs to fill a B200 and the one-sided
+// engine (whose targets-per-thread adapts) is faster: icosTri 7 (327 680) gains 5 %, icosTri 6 (81 920) loses.
+constexpr int32_t kSymMinSources = 200000;
 
-template <class K, int T, int BLOCK, int SB, int MINB, int ORDER = 0, bool FX = false, bool COMBINE = false>
+template <class K, int T, int BLOCK, int SB, int MINB, int ORDER = 0, bool COMBINE = false>
 inline int launch_sym(cudaStream_t st, const SymParams& prm, SymGeom g, const double* src, double* acc)
 {
     constexpr int TB = BLOCK * T;
@@ -57,11 +53,11 @@ inline int launch_sym(cudaStream_t st, const SymParams& prm, SymGeom g, const do
         int devid = 0;
         cudaGetDevice(&devid);
         if (devid < 0 || devid >= 64 || !configured[devid]) {
-            LPM_CUDA(cudaFuncSetAttribute(sym_kernel<K, T, BLOCK, SB, MINB, ORDER, FX, COMBINE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            LPM_CUDA(cudaFuncSetAttribute(sym_kernel<K, T, BLOCK, SB, MINB, ORDER, COMBINE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
             if (devid >= 0 && devid < 64) configured[devid] = true;
         }
     }
-    sym_kernel<K, T, BLOCK, SB, MINB, ORDER, FX, COMBINE><<<(unsigned)grid, BLOCK, smem, st>>>(prm, g, src, acc);
+    sym_kernel<K, T, BLOCK, SB, MINB, ORDER, COMBINE><<<(unsigned)grid, BLOCK, smem, st>>>(prm, g, src, acc);
     return LPM_OK;
 }
 
@@ -77,21 +73,15 @@ struct SymVel {
         p.x = xyz[0]; p.y = xyz[1]; p.z = xyz[2];
         p.R2 = a.sc[0] * a.sc[0];
     }
-    static int launch(int variant, cudaStream_t st, const SymParams& prm, const SymGeom& g, const double* src, double* acc)
+    // 8 targets per thread, batches of 4 sources, the warps' source sums combined in shared memory: one
+    // fixed-point add per (CTA, source, component)
+    static int launch(cudaStream_t st, const SymParams& prm, const SymGeom& g, const double* src, double* acc)
     {
-        // orders picked with the operand-delivery model (tools/sym_score.py): modelled 15.9 / 15.1 / 17.1 / 16.7
-        // cycles per interaction per SM sub-partition (the default one-sided kernel: 20.8 modelled, 20.3 measured)
-        switch (variant - kSymVariant) {
-            case 1: return launch_sym<SK, 8, 128, 4, 1, 35>(st, prm, g, src, acc);
-            case 2: return launch_sym<SK, 4, 128, 8, 2, 27>(st, prm, g, src, acc);
-            case 3: return launch_sym<SK, 8, 128, 4, 1, 27>(st, prm, g, src, acc);
-            case 4: return launch_sym<SK, 4, 128, 8, 2, 35, true>(st, prm, g, src, acc);       // fixed-point accumulation
-            case 5: return launch_sym<SK, 8, 128, 4, 1, 35, true>(st, prm, g, src, acc);
-            case 6: return launch_sym<SK, 4, 128, 8, 2, 35, false, true>(st, prm, g, src, acc);    // one RED per CTA, source, component
-            case 7: return launch_sym<SK, 8, 128, 4, 1, 35, false, true>(st, prm, g, src, acc);
-            case 8: return launch_sym<SK, 4, 128, 8, 2, 35, true, true>(st, prm, g, src, acc);     // fixed point + combined
-            case 9: return launch_sym<SK, 8, 128, 4, 1, 35, true, true>(st, prm, g, src, acc);
-            default: return launch_sym<SK, 4, 128, 8, 2, 35>(st, prm, g, src, acc);
+        switch (rt().sym_vel_shape) {      // A/B of round 2 (the losers go): statement order 35 (fenced) / 27, warps combined or not
+            case 1: return launch_sym<SK, 8, 128, 4, 1, 27, true>(st, prm, g, src, acc);
+            case 2: return launch_sym<SK, 8, 128, 4, 1, 35, false>(st, prm, g, src, acc);
+            case 3: return launch_sym<SK, 8, 128, 4, 1, 27, false>(st, prm, g, src, acc);
+            default: return launch_sym<SK, 8, 128, 4, 1, 35, true>(st, prm, g, src, acc);
         }
     }
     static void finalize(cudaStream_t st, const MaskPlan& mp, const double* src, const double* acc, const Outs<3>& out)
@@ -110,104 +100,12 @@ struct SymStream {
         p.x = xyz[0]; p.y = xyz[1]; p.z = xyz[2];
         p.R2 = a.sc[0] * a.sc[0];
     }
-    static int launch(int variant, cudaStream_t st, const SymParams& prm, const SymGeom& g, const double* src, double* acc)
+    // 64 KB table per CTA, so two CTAs per SM either way: 128 threads (~155 registers), 4 targets per thread,
+    // batches of 4 sources, one retry branch per batch
+    static int launch(cudaStream_t st, const SymParams& prm, const SymGeom& g, const double* src, double* acc)
     {
-        // 64 KB table per CTA, so two CTAs per SM either way: 256 threads under a 128-register cap (121 registers
-        // with the per-source retry; the per-batch retry spills 24 bytes there) or 128 threads with ~155.
-        // Modelled 17.7 / 18.9 / 18.9 / 18.4 cycles per interaction (the one-sided kernel: 29.6 modelled, 32.3 measured).
-        switch (variant - kSymVariant) {
-            case 1: return launch_sym<SK, 4, 128, 4, 2, 0>(st, prm, g, src, acc);
-            case 2: return launch_sym<SK, 4, 256, 4, 2, 0>(st, prm, g, src, acc);
-            case 3: return launch_sym<SK, 4, 128, 4, 2, 1>(st, prm, g, src, acc);
-            case 4: return launch_sym<SK, 4, 256, 4, 2, 1, true>(st, prm, g, src, acc);       // fixed-point accumulation
-            case 5: return launch_sym<SK, 4, 128, 4, 2, 0, true>(st, prm, g, src, acc);
-            case 7: return launch_sym<SK, 4, 128, 4, 2, 0>(st, prm, g, src, acc);      // (no combined build: the table leaves no room)
-            case 8: return launch_sym<SK, 4, 256, 4, 2, 1, true>(st, prm, g, src, acc);
-            case 9: return launch_sym<SK, 4, 128, 4, 2, 0, true>(st, prm, g, src, acc);
-            default: return launch_sym<SK, 4, 256, 4, 2, 1>(st, prm, g, src, acc);
-        }
-    }
-    static void finalize(cudaStream_t st, const MaskPlan& mp, const double*, const double* acc, const Outs<2>& out)
-    {
-        sym_stream_finalize<<<(unsigned)((mp.nsrc + 255) / 256), 256, 0, st>>>(mp.nsrc, mp.active.as<int32_t>(), acc, out);
-    }
-};
-
-// Planar Biot-Savart (variants as for the BVE velocity: 200 / 201 fenced, 202 / 203 not)
-struct SymPlane {
-    static constexpr int FX_MODE = -1;      // FP64 atomics only
-    using Op = OpPlaneVel;
-    using SK = SymPlaneVel;
-    static constexpr int NCOORD = 2;
-    static void sym_params(SymParams&, const Args&) {}
-    static void passive_params(PlaneVel::Params& p, const double* const* xy, const Args&) { p.x = xy[0]; p.y = xy[1]; }
-    static int launch(int variant, cudaStream_t st, const SymParams& prm, const SymGeom& g, const double* src, double* acc)
-    {
-        switch (sym_shape(variant)) {
-            case 1: return launch_sym<SK, 8, 128, 4, 1, 1>(st, prm, g, src, acc);
-            case 2: return launch_sym<SK, 4, 128, 8, 2, 0>(st, prm, g, src, acc);
-            case 3: return launch_sym<SK, 8, 128, 4, 1, 0>(st, prm, g, src, acc);
-            default: return launch_sym<SK, 4, 128, 8, 2, 1>(st, prm, g, src, acc);
-        }
-    }
-    static void finalize(cudaStream_t st, const MaskPlan& mp, const double*, const double* acc, const Outs<2>& out)
-    {
-        sym_stream_finalize<<<(unsigned)((mp.nsrc + 255) / 256), 256, 0, st>>>(mp.nsrc, mp.active.as<int32_t>(), acc, out);
-    }
-};
-
-// Beta-plane Biot-Savart
-struct SymBeta {
-    static constexpr int FX_MODE = -1;      // FP64 atomics only
-    using Op = OpBetaVel;
-    using SK = SymBetaVel;
-    static constexpr int NCOORD = 2;
-    static void sym_params(SymParams&, const Args&) {}
-    static void passive_params(BetaVel::Params& p, const double* const* xy, const Args&) { p.x = xy[0]; p.y = xy[1]; }
-    static int launch(int variant, cudaStream_t st, const SymParams& prm, const SymGeom& g, const double* src, double* acc)
-    {
-        switch (sym_shape(variant)) {
-            case 1: return launch_sym<SK, 4, 128, 4, 2, 1>(st, prm, g, src, acc);
-            case 2: return launch_sym<SK, 4, 128, 8, 2, 0>(st, prm, g, src, acc);
-            case 3: return launch_sym<SK, 4, 128, 4, 2, 0>(st, prm, g, src, acc);
-            default: return launch_sym<SK, 4, 128, 8, 2, 1>(st, prm, g, src, acc);
-        }
-    }
-    static void finalize(cudaStream_t st, const MaskPlan& mp, const double*, const double* acc, const Outs<2>& out)
-    {
-        sym_stream_finalize<<<(unsigned)((mp.nsrc + 255) / 256), 256, 0, st>>>(mp.nsrc, mp.active.as<int32_t>(), acc, out);
-    }
-};
-
-// Planar / beta-plane stream functions: 256 threads (variants 200, 202) or 128 (201, 203), retry branch per source
-struct SymPlaneStr {
-    static constexpr int FX_MODE = -1;      // FP64 atomics only
-    using Op = OpPlaneStream;
-    using SK = SymPlaneStream;
-    static constexpr int NCOORD = 2;
-    static void sym_params(SymParams&, const Args&) {}
-    static void passive_params(PlaneStream::Params& p, const double* const* xy, const Args&) { p.x = xy[0]; p.y = xy[1]; }
-    static int launch(int variant, cudaStream_t st, const SymParams& prm, const SymGeom& g, const double* src, double* acc)
-    {
-        if (sym_shape(variant) & 1) return launch_sym<SK, 4, 128, 4, 2, 0>(st, prm, g, src, acc);
-        return launch_sym<SK, 4, 256, 4, 2, 0>(st, prm, g, src, acc);
-    }
-    static void finalize(cudaStream_t st, const MaskPlan& mp, const double*, const double* acc, const Outs<1>& out)
-    {
-        sym_copy1_finalize<<<(unsigned)((mp.nsrc + 255) / 256), 256, 0, st>>>(mp.nsrc, mp.active.as<int32_t>(), acc, out);
-    }
-};
-struct SymBetaStr {
-    static constexpr int FX_MODE = -1;      // FP64 atomics only
-    using Op = OpBetaStream;
-    using SK = SymBetaStream;
-    static constexpr int NCOORD = 2;
-    static void sym_params(SymParams&, const Args&) {}
-    static void passive_params(BetaStream::Params& p, const double* const* xy, const Args&) { p.x = xy[0]; p.y = xy[1]; }
-    static int launch(int variant, cudaStream_t st, const SymParams& prm, const SymGeom& g, const double* src, double* acc)
-    {
-        if (sym_shape(variant) & 1) return launch_sym<SK, 4, 128, 4, 2, 0>(st, prm, g, src, acc);
-        return launch_sym<SK, 4, 256, 4, 2, 0>(st, prm, g, src, acc);
+        if (rt().sym_stream_shape == 1) return launch_sym<SK, 4, 256, 4, 2, 1>(st, prm, g, src, acc);
+        return launch_sym<SK, 4, 128, 4, 2, 0>(st, prm, g, src, acc);
     }
     static void finalize(cudaStream_t st, const MaskPlan& mp, const double*, const double* acc, const Outs<2>& out)
     {
@@ -223,7 +121,7 @@ struct SymBetaStr {
 // left to exchange.  a: the Op's arguments; out: where the results go (replica 0 only is used).
 template <class S>
 inline int sym_evaluate(Device& dev, cudaStream_t st, MaskPlan& mp, const Args& a,
-                        const Outs<S::Op::NOUT>& out, int variant)
+                        const Outs<S::Op::NOUT>& out)
 {
     using Op = typename S::Op;
     using K = typename Op::K;
@@ -233,12 +131,6 @@ inline int sym_evaluate(Device& dev, cudaStream_t st, MaskPlan& mp, const Args& 
     Runtime& R = rt();
     Workspace& ws = dev.ws;
     const bool prof = R.profiling;
-    cudaEvent_t pb = nullptr, pe = nullptr;
-    if (prof) {
-        if (dev.next_prof(&pb, &pe) != LPM_OK) return set_error(LPM_ERR_CUDA, "cannot create profiling events");
-        LPM_CUDA(cudaEventRecord(pb, st));
-        R.profiling = false;        // one event pair around both kernels
-    }
     auto body = [&]() -> int {
         LPM_TRY(Op::pack(dev, st, mp, a));          // records, and the log window for the stream functions
         const double* src = ws.sources.as<double>();
@@ -259,37 +151,35 @@ inline int sym_evaluate(Device& dev, cudaStream_t st, MaskPlan& mp, const Args& 
         // ---- active x active
         if (mp.nsrc > 0) {
             const size_t nacc = (size_t)g.nsrc_pad * SK::NC;
-            const bool fx = S::FX_MODE >= 0 && sym_fixed_point(variant);
-            const size_t acc_bytes = nacc * sizeof(double) * (fx ? kFxLimbs : 1);
+            const size_t acc_bytes = nacc * kFxWords * sizeof(long long);
             LPM_TRY(ws.sym_acc.reserve(acc_bytes));
             LPM_CUDA(cudaMemsetAsync(ws.sym_acc.p, 0, acc_bytes, st));
-            const double* acc_final = ws.sym_acc.as<double>();
-            if (fx) {       // the window of the fixed-point accumulators, from the largest entry of the records
-                LPM_TRY(ws.sym_fx.reserve(4 * sizeof(double)));
-                LPM_TRY(ws.sym_acc2.reserve(nacc * sizeof(double)));
-                int32_t* maxhi = reinterpret_cast<int32_t*>(ws.sym_fx.as<double>() + 2);
-                LPM_CUDA(cudaMemsetAsync(maxhi, 0, sizeof(int32_t), st));
-                const int64_t nrec = (int64_t)g.nsrc_pad * SK::NS;
-                const unsigned nb = (unsigned)std::min<int64_t>((nrec + 255) / 256, 4 * (int64_t)dev.sm_count);
-                absmax_hi_kernel<<<nb, 256, 0, st>>>(nrec, src, nullptr, maxhi);
-                sym_fx_scale_kernel<<<1, 1, 0, st>>>(S::FX_MODE, prm.R2, mp.nsrc, maxhi, ws.sym_fx.as<double>());
-                count_launch(2);
-                prm.fx = ws.sym_fx.as<double>();
+            // the window of the fixed-point accumulators, from the largest entry of the records
+            LPM_TRY(ws.sym_fx.reserve(sizeof(FxWindow) + sizeof(int32_t)));
+            LPM_TRY(ws.sym_acc2.reserve(nacc * sizeof(double)));
+            FxWindow* fxw = ws.sym_fx.as<FxWindow>();
+            int32_t* maxhi = reinterpret_cast<int32_t*>(fxw + 1);
+            LPM_CUDA(cudaMemsetAsync(maxhi, 0, sizeof(int32_t), st));
+            const int64_t nrec = (int64_t)g.nsrc_pad * SK::NS;
+            const unsigned nb = (unsigned)std::min<int64_t>((nrec + 255) / 256, 4 * (int64_t)dev.sm_count);
+            absmax_hi_kernel<<<nb, 256, 0, st>>>(nrec, src, nullptr, maxhi);
+            sym_fx_scale_kernel<<<1, 1, 0, st>>>(S::FX_MODE, prm.R2, mp.nsrc, maxhi, fxw);
+            prm.fx = fxw;
+            cudaEvent_t pb = nullptr, pe = nullptr;
+            if (prof) {     // the triangle kernel alone; the passive part's ds_kernel records its own pair
+                if (dev.next_prof(&pb, &pe, 2 * prof_sum_of<K>::value + 1) != LPM_OK) return set_error(LPM_ERR_CUDA, "cannot create profiling events");
+                LPM_CUDA(cudaEventRecord(pb, st));
             }
-            LPM_TRY(S::launch(variant, st, prm, g, src, ws.sym_acc.as<double>()));
+            LPM_TRY(S::launch(st, prm, g, src, ws.sym_acc.as<double>()));
+            if (prof) LPM_CUDA(cudaEventRecord(pe, st));
             if (g.world > 1) {
                 if (!R.comm) return set_error(LPM_ERR_COMM, "world size %d but no communicator (lpm_comm_init_rank)", R.world);
-                if (fx) LPM_NCCL(nccl().AllReduce(ws.sym_acc.p, ws.sym_acc.p, nacc * kFxLimbs, /*ncclInt64*/ 4, /*ncclSum*/ 0, R.comm, st));
-                else LPM_NCCL(nccl().AllReduce(ws.sym_acc.p, ws.sym_acc.p, nacc, /*ncclDouble*/ 8, /*ncclSum*/ 0, R.comm, st));
+                LPM_NCCL(nccl().AllReduce(ws.sym_acc.p, ws.sym_acc.p, nacc * kFxWords, /*ncclInt64*/ 4, /*ncclSum*/ 0, R.comm, st));
             }
-            if (fx) {
-                sym_fx_to_double_kernel<<<(unsigned)((nacc + 255) / 256), 256, 0, st>>>((int64_t)nacc, ws.sym_acc.as<long long>(),
-                                                                                     ws.sym_fx.as<double>(), ws.sym_acc2.as<double>());
-                count_launch();
-                acc_final = ws.sym_acc2.as<double>();
-            }
-            S::finalize(st, mp, src, acc_final, out);
-            count_launch(2);
+            sym_fx_to_double_kernel<<<(unsigned)((nacc + 255) / 256), 256, 0, st>>>((int64_t)nacc, ws.sym_acc.as<long long>(), fxw,
+                                                                                 ws.sym_acc2.as<double>());
+            S::finalize(st, mp, src, ws.sym_acc2.as<double>(), out);
+            count_launch(5);
         }
         // ---- passive targets x all active sources: the one-sided engine on the gathered passive particles
         const int64_t nv = mp.n - mp.nsrc;
@@ -322,7 +212,7 @@ inline int sym_evaluate(Device& dev, cudaStream_t st, MaskPlan& mp, const Args& 
             view.active.p = mp.active.p; view.active.cap = mp.active.cap;
             int64_t vb = 0, ve = nv;
             if (g.world > 1) load_balance0(nv, g.world, g.rank, &vb, &ve);
-            const int rc = direct_sum<K>(dev, st, view, vb, ve, prm1, 0, nv);
+            const int rc = direct_sum<K>(dev, st, view, vb, ve, prm1, nv);
             view.scan = DevBuf{}; view.active = DevBuf{};
             LPM_TRY(rc);
             if (g.world > 1) LPM_TRY(allgather_slices(NOUT, bufs, nv, st));
@@ -337,20 +227,16 @@ inline int sym_evaluate(Device& dev, cudaStream_t st, MaskPlan& mp, const Args& 
         LPM_CUDA(cudaGetLastError());
         return LPM_OK;
     };
-    const int rc = body();
-    if (prof) {
-        R.profiling = true;
-        if (rc == LPM_OK) LPM_CUDA(cudaEventRecord(pe, st));
-    }
-    return rc;
+    return body();
 }
 
-// May this evaluation take the symmetric path?  One device driving every target, or rank mode with this
-// rank's LoadBalance slice (then every rank reaches the same answer and the collectives inside match up).
-inline bool sym_applicable(int variant, int64_t tbeg, int64_t tend, int64_t nt, const MaskPlan& mp, int nrep)
+// May this evaluation take the symmetric path?  The path is on (lpm_set_symmetric), the particle set is large
+// enough, and the call covers all targets: one device driving every target, or rank mode with this rank's
+// LoadBalance slice (then every rank reaches the same answer and the collectives inside match up).
+inline bool sym_applicable(int64_t tbeg, int64_t tend, int64_t nt, const MaskPlan& mp, int nrep)
 {
     const Runtime& R = rt();
-    if (variant < kSymVariant || variant > kSymVariantLast || nt != mp.n || nrep != 1 || R.devs.size() != 1) return false;
+    if (!R.symmetric || mp.nsrc < R.sym_min_sources || nt != mp.n || nrep != 1 || R.devs.size() != 1) return false;
     int64_t b = 0, e = nt;
     if (R.rank_mode && R.world > 1) load_balance0(nt, R.world, R.rank, &b, &e);
     return tbeg == b && tend == e;
@@ -360,10 +246,6 @@ inline bool sym_applicable(int variant, int64_t tbeg, int64_t tend, int64_t nt, 
 template <class Op> struct SymFor { using type = void; };
 template <> struct SymFor<OpBveVel> { using type = SymVel; };
 template <> struct SymFor<OpBveStream> { using type = SymStream; };
-template <> struct SymFor<OpPlaneVel> { using type = SymPlane; };
-template <> struct SymFor<OpPlaneStream> { using type = SymPlaneStr; };
-template <> struct SymFor<OpBetaVel> { using type = SymBeta; };
-template <> struct SymFor<OpBetaStream> { using type = SymBetaStr; };
 
 template <class Op>
 inline int sym_try(Device& dev, cudaStream_t st, MaskPlan& mp, const Args& a, double* const* out, int64_t tbeg,
@@ -372,11 +254,10 @@ inline int sym_try(Device& dev, cudaStream_t st, MaskPlan& mp, const Args& a, do
     using S = typename SymFor<Op>::type;
     *taken = false;
     if constexpr (!std::is_void<S>::value) {
-        const int variant = rt().bve_variant;
-        if (!sym_applicable(variant, tbeg, tend, nt, mp, nrep)) return LPM_OK;
+        if (!sym_applicable(tbeg, tend, nt, mp, nrep)) return LPM_OK;
         Outs<Op::NOUT> o{};
         set_outs(o, out);
-        LPM_TRY(sym_evaluate<S>(dev, st, mp, a, o, variant));
+        LPM_TRY(sym_evaluate<S>(dev, st, mp, a, o));
         *taken = true;
     }
     return LPM_OK;

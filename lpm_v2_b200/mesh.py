@@ -1,10 +1,10 @@
 """PolyMesh2d (uniform refinement) -- thin wrapper over the host mesh generator
-in liblpmgpu.so (csrc/mesh.cpp; reference: src/PolyMesh2d.f90:135-195)."""
+in liblpmmesh.so (csrc/mesh.cpp, include/lpm_mesh.h; host only, no CUDA; reference: src/PolyMesh2d.f90:135-195)."""
 import ctypes as C
 
 import numpy as np
 
-from ._lib import lib, check
+from ._meshlib import lib, check
 
 TRI_HEX_SEED = 201
 QUAD_RECT_SEED = 202

@@ -81,6 +81,9 @@ def _declare(lib):
     lib.oracle_active_list.restype = C.c_int64
     lib.oracle_bve_velocity_mt.argtypes = [C.c_int, _n, _d, _d, _d, _d, _d, _i32, _dbl, _n, _n, _d, _d, _d]
     lib.oracle_bve_velocity_mt.restype = None
+    lib.oracle_set_threads.argtypes = [C.c_int]
+    lib.oracle_set_threads.restype = None
+    lib.oracle_get_threads.restype = C.c_int
 
 
 def _f(a):
@@ -237,15 +240,36 @@ def total_enstrophy(relvort, area, mask):
     return get().oracle_total_enstrophy(relvort.size, _p(relvort), _p(area), m.ctypes.data_as(_i32))
 
 
-def bve_velocity_mt(nthreads, x, y, z, relvort, area, mask, radius, tbeg, tend):
-    """Timing leg: targets [tbeg, tend) over `nthreads` workers (fast build)."""
+def bve_velocity_mt(nthreads, x, y, z, relvort, area, mask, radius, tbeg, tend, fast=True):
+    """Targets [tbeg, tend) over `nthreads` workers on the LoadBalance split.  fast=True: the timing build
+    (bench.py's CPU legs); fast=False: the parity build (-O2, no contraction) -- bit-identical to the
+    single-threaded oracle_bve_velocity, because each target is summed by one worker in j order."""
     x, y, z, relvort, area = map(_f, (x, y, z, relvort, area))
     m = _m(mask)
     n = x.size
     u, v, w = (np.zeros(n) for _ in range(3))
-    get(fast=True).oracle_bve_velocity_mt(nthreads, n, _p(x), _p(y), _p(z), _p(relvort), _p(area),
+    get(fast=fast).oracle_bve_velocity_mt(nthreads, n, _p(x), _p(y), _p(z), _p(relvort), _p(area),
                                           m.ctypes.data_as(_i32), radius, tbeg, tend, _p(u), _p(v), _p(w))
     return u, v, w
+
+
+def set_threads(nthreads):
+    """Host threads for the target loops of the PARITY build (OpenMP over targets; results do not depend on it)."""
+    get().oracle_set_threads(int(nthreads))
+
+
+class threads:
+    """with oracle.threads(8): ...  -- parity-build oracle calls inside run their target loops on 8 threads."""
+
+    def __init__(self, n):
+        self.n = n
+
+    def __enter__(self):
+        self.old = get().oracle_get_threads()
+        set_threads(self.n)
+
+    def __exit__(self, *a):
+        set_threads(self.old)
 
 
 # ---- remaining PSE operators ---------------------------------------------------------

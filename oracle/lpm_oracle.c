@@ -39,6 +39,48 @@
 static const double PI = 3.1415926535897932384626433832795027975;
 
 /* ------------------------------------------------------------------ */
+/* ------------------------------------------------------------------ */
+/* Host threads for the target loops of the velocity / stream-function sums (tests on config-sized
+ * meshes, bench.py's parity sample).  Each target's sum is computed by one thread in the reference's
+ * own j order, so results are bit-identical for any thread count -- the same property the reference
+ * has for any number of MPI ranks (src/MPISetup.f90:132-146: each rank owns whole targets).  Default 1.
+ * A threaded call splits [ibeg, iend) evenly and re-enters the same function per sub-range.            */
+static int g_threads = 1;
+static __thread int tl_in_worker = 0;
+void oracle_set_threads(int nthreads) { g_threads = nthreads < 1 ? 1 : nthreads; }
+int oracle_get_threads(void) { return g_threads; }
+
+typedef struct {
+    int kind; int64_t n; const double *in[6]; const int32_t *mask; double R; int64_t ibeg, iend; double *out[3];
+} range_job;
+static void range_call(const range_job *j);
+static void *range_worker(void *arg)
+{
+    tl_in_worker = 1;
+    range_call((const range_job *)arg);
+    return NULL;
+}
+/* returns 1 if the range was handled by worker threads */
+static int range_split(int kind, int64_t n, const double *i0, const double *i1, const double *i2, const double *i3,
+                       const double *i4, const double *i5, const int32_t *mask, double R, int64_t ibeg, int64_t iend,
+                       double *o0, double *o1, double *o2)
+{
+    int nt = g_threads;
+    if (nt <= 1 || tl_in_worker || iend - ibeg < 2 * (int64_t)nt) return 0;
+    pthread_t *th = (pthread_t *)malloc(sizeof(pthread_t) * nt);
+    range_job *jobs = (range_job *)malloc(sizeof(range_job) * nt);
+    int64_t cnt = iend - ibeg;
+    for (int t = 0; t < nt; ++t) {
+        range_job j = { kind, n, { i0, i1, i2, i3, i4, i5 }, mask, R, ibeg + cnt * t / nt, ibeg + cnt * (t + 1) / nt, { o0, o1, o2 } };
+        jobs[t] = j;
+        pthread_create(&th[t], NULL, range_worker, &jobs[t]);
+    }
+    for (int t = 0; t < nt; ++t) pthread_join(th[t], NULL);
+    free(th); free(jobs);
+    return 1;
+}
+enum { K_BVE_VEL, K_BVE_VEL_MESH, K_BVE_STREAM, K_PLANE_VEL, K_PLANE_STREAM, K_BETA_VEL, K_BETA_STREAM };
+
 /* src/MPISetup.f90:132-146  LoadBalance.  Outputs are the reference's
  * 1-based inclusive indexStart / indexEnd and messageLength.          */
 void oracle_load_balance(int32_t nItems, int32_t nProcs, int32_t *indexStart,
@@ -82,6 +124,7 @@ void oracle_bve_velocity(int64_t n, const double *x, const double *y, const doub
                          double R, int64_t ibeg, int64_t iend,
                          double *u, double *v, double *w)
 {
+    if (range_split(K_BVE_VEL, n, x, y, z, relVort, area, NULL, mask, R, ibeg, iend, u, v, w)) return;
     for (int64_t i = ibeg; i < iend; ++i) {
         u[i] = 0.0; v[i] = 0.0; w[i] = 0.0;
         for (int64_t j = 0; j < i; ++j) BVE_BODY
@@ -106,6 +149,7 @@ void oracle_bve_velocity_mesh(int64_t n, const double *x, const double *y, const
                               double R, int64_t ibeg, int64_t iend,
                               double *u, double *v, double *w)
 {
+    if (range_split(K_BVE_VEL_MESH, n, x, y, z, relVort, area, NULL, mask, R, ibeg, iend, u, v, w)) return;
     for (int64_t i = ibeg; i < iend; ++i) {
         u[i] = 0.0; v[i] = 0.0; w[i] = 0.0;
         for (int64_t j = 0; j < i; ++j) BVE_MESH_BODY
@@ -149,6 +193,7 @@ void oracle_bve_stream(int64_t n, const double *x, const double *y, const double
                        const int32_t *mask, double R, int64_t ibeg, int64_t iend,
                        double *relStream, double *absStream)
 {
+    if (range_split(K_BVE_STREAM, n, x, y, z, relVort, absVort, area, mask, R, ibeg, iend, relStream, absStream, NULL)) return;
     for (int64_t i = ibeg; i < iend; ++i) {
         relStream[i] = 0.0; absStream[i] = 0.0;
         for (int64_t j = 0; j < i; ++j) BVE_STREAM_BODY
@@ -190,6 +235,7 @@ void oracle_plane_velocity(int64_t n, const double *x, const double *y, const do
                            const double *area, const int32_t *mask, int64_t ibeg, int64_t iend,
                            double *u, double *v)
 {
+    if (range_split(K_PLANE_VEL, n, x, y, vort, area, NULL, NULL, mask, 0.0, ibeg, iend, u, v, NULL)) return;
     for (int64_t i = ibeg; i < iend; ++i) {
         u[i] = 0.0; v[i] = 0.0;
         for (int64_t j = 0; j < i; ++j) PLANE_BODY
@@ -226,6 +272,7 @@ void oracle_plane_stream(int64_t n, const double *x, const double *y, const doub
                          const double *area, const int32_t *mask, int64_t ibeg, int64_t iend,
                          double *psi)
 {
+    if (range_split(K_PLANE_STREAM, n, x, y, vort, area, NULL, NULL, mask, 0.0, ibeg, iend, psi, NULL, NULL)) return;
     for (int64_t i = ibeg; i < iend; ++i) {
         psi[i] = 0.0;
         for (int64_t j = 0; j < i; ++j) PLANE_STREAM_BODY
@@ -264,6 +311,7 @@ void oracle_betaplane_velocity(int64_t n, const double *x, const double *y, cons
                                const double *area, const int32_t *mask, int64_t ibeg, int64_t iend,
                                double *u, double *v)
 {
+    if (range_split(K_BETA_VEL, n, x, y, relVort, area, NULL, NULL, mask, 0.0, ibeg, iend, u, v, NULL)) return;
     for (int64_t i = ibeg; i < iend; ++i) {
         u[i] = 0.0; v[i] = 0.0;
         for (int64_t j = 0; j < i; ++j) BETA_BODY
@@ -307,6 +355,7 @@ void oracle_betaplane_stream(int64_t n, const double *x, const double *y, const 
                              const double *absVort, const double *area, const int32_t *mask,
                              int64_t ibeg, int64_t iend, double *relStream, double *absStream)
 {
+    if (range_split(K_BETA_STREAM, n, x, y, relVort, absVort, area, NULL, mask, 0.0, ibeg, iend, relStream, absStream, NULL)) return;
     for (int64_t i = ibeg; i < iend; ++i) {
         absStream[i] = 0.0; relStream[i] = 0.0;
         for (int64_t j = 0; j < i; ++j) BETA_STREAM_BODY
@@ -331,6 +380,21 @@ void oracle_betaplane_stream_ld(int64_t n, const double *x, const double *y, con
             sa += g * (long double)absVort[j] * (long double)area[j];
         }
         relStream[i] = (double)sr; absStream[i] = (double)sa;
+    }
+}
+
+static void range_call(const range_job *j)
+{
+    const double *const *a = j->in;
+    switch (j->kind) {
+        case K_BVE_VEL: oracle_bve_velocity(j->n, a[0], a[1], a[2], a[3], a[4], j->mask, j->R, j->ibeg, j->iend, j->out[0], j->out[1], j->out[2]); break;
+        case K_BVE_VEL_MESH: oracle_bve_velocity_mesh(j->n, a[0], a[1], a[2], a[3], a[4], j->mask, j->R, j->ibeg, j->iend, j->out[0], j->out[1], j->out[2]); break;
+        case K_BVE_STREAM: oracle_bve_stream(j->n, a[0], a[1], a[2], a[3], a[4], a[5], j->mask, j->R, j->ibeg, j->iend, j->out[0], j->out[1]); break;
+        case K_PLANE_VEL: oracle_plane_velocity(j->n, a[0], a[1], a[2], a[3], j->mask, j->ibeg, j->iend, j->out[0], j->out[1]); break;
+        case K_PLANE_STREAM: oracle_plane_stream(j->n, a[0], a[1], a[2], a[3], j->mask, j->ibeg, j->iend, j->out[0]); break;
+        case K_BETA_VEL: oracle_betaplane_velocity(j->n, a[0], a[1], a[2], a[3], j->mask, j->ibeg, j->iend, j->out[0], j->out[1]); break;
+        case K_BETA_STREAM: oracle_betaplane_stream(j->n, a[0], a[1], a[2], a[3], a[4], j->mask, j->ibeg, j->iend, j->out[0], j->out[1]); break;
+        default: break;
     }
 }
 

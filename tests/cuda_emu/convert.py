@@ -123,7 +123,7 @@ def rewrite_launches(text, threaded):
 
 def convert(src_dir, out_dir):
     os.makedirs(out_dir, exist_ok=True)
-    files = [f for f in sorted(os.listdir(src_dir)) if f.endswith(('.cuh', '.cu', '.inc', '.cpp'))]
+    files = [f for f in sorted(os.listdir(src_dir)) if f.endswith(('.cuh', '.cu', '.inc', '.cpp', '.h'))]
     texts = {f: open(os.path.join(src_dir, f)).read() for f in files}
     bodies = {}
     for t in texts.values():

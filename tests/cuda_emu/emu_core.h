@@ -140,6 +140,18 @@ inline int __double2hiint(double d)
     std::memcpy(&b, &d, 8);
     return (int)(b >> 32);
 }
+inline long long __double_as_longlong(double d)
+{
+    long long b;
+    std::memcpy(&b, &d, 8);
+    return b;
+}
+inline double __longlong_as_double(long long b)
+{
+    double d;
+    std::memcpy(&d, &b, 8);
+    return d;
+}
 inline int max(int a, int b) { return a > b ? a : b; }
 inline unsigned max(unsigned a, unsigned b) { return a > b ? a : b; }
 inline int min(int a, int b) { return a < b ? a : b; }

@@ -16,11 +16,15 @@ from test_parity_gpu import _rand_sphere                  # noqa: E402
 nd = api.init(0)
 x, y, z, zeta, area, mask = _rand_sphere(1500, 5, 0.7)
 av = zeta + 0.3 * z
-for var in (0, 200, 201, 202, 203, 204, 205, 206, 207, 208, 209):
-    api.set_bve_variant(var)
+api.tune("sym_min_sources", 0)
+for sym_on, shape in ((False, 0), (True, 0), (True, 1), (True, 2), (True, 3)):
+    api.set_symmetric(sym_on)
+    api.tune("sym_vel_shape", shape)
+    api.tune("sym_stream_shape", shape & 1)
     api.bve_velocity(x, y, z, zeta, area, mask, 1.0)
     api.bve_stream(x, y, z, zeta, av, area, mask, 1.0)
-api.set_bve_variant(0)
+api.tune("sym_vel_shape", 0)
+api.tune("sym_stream_shape", 0)
 m = mesh.PolyMesh2d(mesh.ICOS_TRI_SPHERE_SEED, 3)
 f = problems.rossby_haurwitz54(m)
 eps = m.max_edge_length ** 0.75
@@ -29,21 +33,13 @@ api.pse_gradient_sphere(m.x, m.y, m.z, f, m.area, m.is_active, eps, 1.0)
 api.pse_double_dot_sphere(m.x, m.y, m.z, -m.y, m.x, m.z * m.x, m.area, m.is_active, eps, 1.0)
 q = mesh.PolyMesh2d(mesh.QUAD_RECT_SEED, 3, 7.0)
 vq = problems.colliding_dipoles(q)
-for var in (0, 200, 201):
-    api.set_bve_variant(var)
-    api.plane_velocity(q.x, q.y, vq, q.area, q.is_active)
-api.set_bve_variant(0)
+api.plane_velocity(q.x, q.y, vq, q.area, q.is_active)
 api.plane_stream(q.x, q.y, vq, q.area, q.is_active)
 api.pse_laplacian_plane(q.x, q.y, vq, q.area, q.is_active, q.max_edge_length ** 0.75)
 api.swe_plane_rhs_integrals(q.x, q.y, vq, 0.1 * vq, 1 + 0 * vq, q.area, q.is_active, q.max_edge_length ** 0.75)
 b = mesh.PolyMesh2d(mesh.BETA_PLANE_SEED, 3)
 zb = problems.betaplane_gaussian(b)
-for var in (0, 200, 201):
-    api.set_bve_variant(var)
-    api.betaplane_velocity(b.x, b.y, zb, b.area, b.is_active)
-    api.betaplane_stream(b.x, b.y, zb, zb + 1, b.area, b.is_active)
-    api.plane_stream(q.x, q.y, vq, q.area, q.is_active)
-api.set_bve_variant(0)
+api.betaplane_velocity(b.x, b.y, zb, b.area, b.is_active)
 api.betaplane_stream(b.x, b.y, zb, zb + 1, b.area, b.is_active)
 sph = solvers.BVEMesh(m, problems.gaussian_vortex(m), 1.0, 2 * np.pi)
 sph.velocity = list(api.bve_velocity(m.x, m.y, m.z, sph.relVort, m.area, m.is_active, 1.0))

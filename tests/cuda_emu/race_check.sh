@@ -8,7 +8,7 @@ ROOT="$(cd "$HERE/../.." && pwd)"
 LOG="${1:-/tmp/lpm_race_check.log}"
 bash "$HERE/build_emu.sh" > /dev/null
 g++ -std=c++20 -O1 -g -fPIC -shared -pthread -fsanitize=thread -Wl,-Bsymbolic -DLPM_CUDA_EMU=1 \
-    -I"$HERE" -I"$HERE/_gen" -I"$ROOT/include" -o "$HERE/liblpmgpu_emu_tsan.so" "$HERE/_gen/lpm_gpu.cpp" "$HERE/_gen/mesh.cpp" -ldl
+    -I"$HERE" -I"$HERE/_gen" -I"$ROOT/include" -o "$HERE/liblpmgpu_emu_tsan.so" "$HERE/_gen/lpm_gpu.cpp" -ldl
 TSAN="$(g++ -print-file-name=libtsan.so)"
 : > "$LOG"
 for nd in 1 2; do

@@ -1,8 +1,8 @@
 """One rank of an emulated rank-mode run (tests/test_emu_abi.py::test_rank_mode_on_emulator): one process per
 "GPU", liblpmgpu_emu.so + tests/cuda_emu/fake_nccl/libnccl.so.2.  Through the host API every rank evaluates its
 LoadBalance slice and the slices are exchanged -- by peer stores into the shared output slabs between two all-reduce
-barriers (default path) or, for the pair-symmetric variants, by an all-reduce of the accumulators and the grouped
-broadcast of the passive slices -- so each rank must end up with all n results.
+barriers (one-sided engine) or, on the pair-symmetric path, by an integer all-reduce of the fixed-point accumulators
+and the grouped broadcast of the passive slices -- so each rank must end up with all n results.
 usage: rank_mode.py <world> <rank> <file for the unique id>"""
 import os
 import sys
@@ -47,24 +47,26 @@ zb = problems.betaplane_gaussian(bp)
 wantb = O.betaplane_velocity(bp.x, bp.y, zb, bp.area, bp.is_active, variant="_ld")
 wantqs = O.plane_stream(q.x, q.y, vq, q.area, q.is_active)
 wantbs = O.betaplane_stream(bp.x, bp.y, zb, zb + 1.0 + 2.0 * bp.y, bp.area, bp.is_active, variant="_ld")
-for var in ((208,) if world == 1 else (0, 200, 201, 208)):
-    api.set_bve_variant(var)
+# sym: every whole BVE evaluation through the pair-symmetric path (block dealing, integer all-reduce of the
+# fixed-point accumulators, grouped broadcast of the passive slices); one-sided: peer stores into the shared slabs
+for sym_on in ((True,) if world == 1 else (False, True)):
+    api.set_symmetric(sym_on)
+    api.tune("sym_min_sources", 0)
     got = api.bve_velocity(m.x, m.y, m.z, zeta, m.area, m.is_active, 1.0)
-    assert max(rel(g, w) for g, w in zip(got, want)) <= 1e-12, ("velocity", var)
+    assert max(rel(g, w) for g, w in zip(got, want)) <= 1e-12, ("velocity", sym_on)
     gots = api.bve_stream(m.x, m.y, m.z, zeta, av, m.area, m.is_active, 1.0)
-    assert max(rel(g, w) for g, w in zip(gots, wants)) <= 1e-12, ("stream", var)
-    if var == 208:      # fixed-point accumulation (with the warps' sums combined in shared memory): the bits must not depend on the number of ranks (checked by the caller)
+    assert max(rel(g, w) for g, w in zip(gots, wants)) <= 1e-12, ("stream", sym_on)
+    if sym_on:      # fixed-point accumulation: the bits must not depend on the number of ranks (checked by the caller)
         np.save(idfile + f".fx.{world}.{rank}.npy", np.stack(list(got) + list(gots)))
+    if world == 1:
         continue
-    if var == 201:
-        continue        # the second shape: sums only
     gotq = api.plane_velocity(q.x, q.y, vq, q.area, q.is_active)
-    assert max(rel(g, w) for g, w in zip(gotq, wantq)) <= 1e-12, ("plane", var)
+    assert max(rel(g, w) for g, w in zip(gotq, wantq)) <= 1e-12, ("plane", sym_on)
     gotb = api.betaplane_velocity(bp.x, bp.y, zb, bp.area, bp.is_active)
-    assert max(rel(g, w) for g, w in zip(gotb, wantb)) <= 1e-12, ("betaplane", var)
-    assert rel(api.plane_stream(q.x, q.y, vq, q.area, q.is_active), wantqs) <= 1e-12, ("plane stream", var)
+    assert max(rel(g, w) for g, w in zip(gotb, wantb)) <= 1e-12, ("betaplane", sym_on)
+    assert rel(api.plane_stream(q.x, q.y, vq, q.area, q.is_active), wantqs) <= 1e-12, ("plane stream", sym_on)
     gotbs = api.betaplane_stream(bp.x, bp.y, zb, zb + 1.0 + 2.0 * bp.y, bp.area, bp.is_active)
-    assert max(rel(g, w) for g, w in zip(gotbs, wantbs)) <= 1e-12, ("betaplane stream", var)
+    assert max(rel(g, w) for g, w in zip(gotbs, wantbs)) <= 1e-12, ("betaplane stream", sym_on)
     # the resident solver: every array in one shared slab, four velocity sums and the stream functions per step
     zg = problems.gaussian_vortex(m)
     u0 = O.bve_velocity(m.x, m.y, m.z, zg, m.area, m.is_active, 1.0)
@@ -75,8 +77,8 @@ for var in ((208,) if world == 1 else (0, 200, 201, 208)):
     sol.Delete()
     ref = O.bve_rk4_step(m.x, m.y, m.z, zg, *u0, m.area, m.is_active, 1.0, 2 * np.pi, 0.01)
     for a, b in zip([sph.x, sph.y, sph.z, sph.relVort] + sph.velocity, ref):
-        assert rel(a, b) <= 1e-12, ("rk4", var)
-api.set_bve_variant(0)
+        assert rel(a, b) <= 1e-12, ("rk4", sym_on)
+api.tune("sym_min_sources", 200000)
 if world == 1:
     api.finalize()
     print("OK rank", rank, "of", world, flush=True)

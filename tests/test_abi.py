@@ -11,8 +11,8 @@ import pytest
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
-def _declared_symbols():
-    txt = open(os.path.join(ROOT, "include", "lpm_gpu.h")).read()
+def _declared_symbols(header="lpm_gpu.h"):
+    txt = open(os.path.join(ROOT, "include", header)).read()
     txt = re.sub(r"/\*.*?\*/", "", txt, flags=re.S)
     return sorted(set(re.findall(r"\b(lpm_[a-z0-9_]+)\s*\(", txt)))
 
@@ -25,6 +25,33 @@ def test_header_symbols_all_exported(lpm):
         assert hasattr(_lib.lib, s), f"{s} declared in lpm_gpu.h but not exported"
     # and the ctypes table binds exactly the header's set
     assert sorted(_lib.PROTOTYPES) == syms
+    # the tuning hook of csrc/lpm_gpu_tuning.h is deliberately NOT part of the ABI header
+    assert "lpm_tune" not in syms and "lpm_set_bve_variant" not in syms
+
+
+def test_mesh_header_symbols_all_exported():
+    """include/lpm_mesh.h <-> liblpmmesh.so, which must not pull in the GPU library or CUDA."""
+    import subprocess
+    from lpm_v2_b200 import _meshlib
+    syms = _declared_symbols("lpm_mesh.h")
+    assert len(syms) == 11
+    for s in syms:
+        assert hasattr(_meshlib.lib, s), f"{s} declared in lpm_mesh.h but not exported"
+    assert sorted(_meshlib.PROTOTYPES) == syms
+    out = subprocess.run(["ldd", _meshlib.LIB_PATH], capture_output=True, text=True).stdout
+    assert "cuda" not in out.lower() and "lpmgpu" not in out
+
+
+def test_reference_arm_does_not_map_the_gpu_library():
+    """bench.py --impl reference times the CPU port: the process must never load liblpmgpu.so."""
+    import subprocess
+    import sys
+    code = ("import sys; sys.argv=['bench.py','--impl','reference','--level','3','--steps','1','--warmup','0'];"
+            "import runpy; runpy.run_path('bench.py', run_name='__main__');"
+            "maps=open('/proc/self/maps').read(); assert 'liblpmgpu' not in maps, 'GPU library mapped'; "
+            "assert 'liblpmmesh' in maps and 'liblpm_oracle' in maps; print('MAPS_OK')")
+    r = subprocess.run([sys.executable, "-c", code], cwd=ROOT, capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0 and "MAPS_OK" in r.stdout, r.stdout[-1000:] + r.stderr[-2000:]
 
 
 def test_load_balance_matches_reference_rule(lpm, oracle):
@@ -78,11 +105,11 @@ def test_product_does_not_use_oracle():
 
 
 def test_argument_validation(lpm):
-    from lpm_v2_b200 import _lib
+    from lpm_v2_b200 import _lib, _meshlib
     s = np.zeros(2, np.int64)
     p = C.POINTER(C.c_int64)
     assert _lib.lib.lpm_load_balance(10, 0, s.ctypes.data_as(p), s.ctypes.data_as(p), s.ctypes.data_as(p)) == 1
     assert "lpm_load_balance" in _lib.last_error()
     h = C.c_void_p()
-    assert _lib.lib.lpm_mesh_create(999, 1, 1.0, C.byref(h)) == 1     # invalid meshSeed
-    assert _lib.lib.lpm_mesh_create(205, -1, 1.0, C.byref(h)) == 1
+    assert _meshlib.lib.lpm_mesh_create(999, 1, 1.0, C.byref(h)) == 1     # invalid meshSeed
+    assert _meshlib.lib.lpm_mesh_create(205, -1, 1.0, C.byref(h)) == 1

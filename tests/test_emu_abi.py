@@ -28,7 +28,6 @@ def emu_env():
     subprocess.check_call(["bash", os.path.join(EMU, "build_emu.sh")])
     env = dict(os.environ)
     env["LPM_GPU_LIBRARY"] = os.path.join(EMU, "liblpmgpu_emu.so")
-    env["LPM_EXPERIMENTAL"] = "1"
     return env
 
 
@@ -47,12 +46,12 @@ def test_default_paths_on_emulator(emu_env):
 
 
 def test_symmetric_paths_on_emulator(emu_env):
-    """lpm_set_bve_variant(200..203) through the real host code: velocity, stream functions, planar velocity."""
+    """The pair-symmetric path (tests/test_sym_gpu.py lowers its size threshold) through the real host code:
+    velocity, stream functions, fixed-point accumulation, the coincident-particle case."""
     tail = _run(emu_env, ["tests/test_sym_gpu.py", "-k",
-                          "(random_ragged and (200 or 201) and not 20011 and not 4099 and not 6000) "
-                          "or (plane_velocity_mesh and 3-20) or fenced_one_sided or (betaplane_velocity and 3-20) "
-                          "or betaplane_rk4 or plane_rk4 or (plane_and_betaplane_stream and 200) "
-                          "or (fixed_point and 1.0 and (204 or 209)) or (velocity_random_ragged and (1025 or 513 or 127) and (202 or 203 or 206 or 207))"], 900)
+                          "(velocity_random_ragged and (127 or 513 or 1025 or 3000 or 3-0.5)) "
+                          "or (stream_random_ragged and (513 or 3-0.5)) "
+                          "or (fixed_point and not 6371000 and not 3e-07) or coincident"], 900)
     assert " passed" in tail and "failed" not in tail, tail
 
 
@@ -78,7 +77,7 @@ def test_rank_mode_on_emulator(emu_env, tmp_path):
     go to tests/cuda_emu/fake_nccl (shared memory + a process-shared barrier); "device" allocations are shared-memory
     segments, so the CUDA-IPC slabs and the peer stores into them are real cross-process stores.  Covers the fused
     peer-store exchange with its barriers, the resident solver in a shared slab, the scatter exchange of the
-    cell-ordered PSE path, and the all-reduce + grouped broadcast of the pair-symmetric variants."""
+    cell-ordered PSE path, and the integer all-reduce + grouped broadcast of the pair-symmetric path."""
     st = os.statvfs("/dev/shm")
     if st.f_bavail * st.f_frsize < (512 << 20):
         pytest.skip("needs 512 MB of /dev/shm for the emulated device memory of three ranks")
@@ -98,7 +97,7 @@ def test_rank_mode_on_emulator(emu_env, tmp_path):
             raise
     for r, (p, out) in enumerate(zip(procs, outs)):
         assert p.returncode == 0 and f"OK rank {r} of {world}" in out, out[-3000:]
-    # variant 208 (fixed-point accumulation of the symmetric sums): one rank alone gets the same BITS as three
+    # fixed-point accumulation of the symmetric sums: one rank alone gets the same BITS as three
     r1 = subprocess.run([sys.executable, os.path.join(EMU, "rank_mode.py"), "1", "0", idfile], env=env,
                         capture_output=True, text=True, timeout=600)
     assert r1.returncode == 0 and "OK rank 0 of 1" in r1.stdout, (r1.stdout + r1.stderr)[-3000:]

@@ -105,6 +105,17 @@ lap_host = api.pse_laplacian_sphere(m.x, m.y, m.z, problems.spherical_harmonic54
 assert np.array_equal(lap_sh[0].cpu().numpy(), lap_host)
 del sh, lap_sh
 api.comm_free_shared(slab); api.comm_free_shared(slab2)
+# the pair-symmetric path in rank mode (target blocks dealt round-robin, integer all-reduce of the fixed-point
+# accumulators, grouped broadcast of the passive slices): parity, and the SAME BITS as one GPU alone computed
+api.tune("sym_min_sources", 0)
+sym_v = api.bve_velocity(m.x, m.y, m.z, zeta, m.area, m.is_active, 1.0)
+av = problems.abs_vorticity(m, zeta, 2 * np.pi)
+sym_s = api.bve_stream(m.x, m.y, m.z, zeta, av, m.area, m.is_active, 1.0)
+api.tune("sym_min_sources", 200000)
+one = np.load(%(symfile)r)
+assert np.array_equal(np.stack(list(sym_v) + list(sym_s)), one), "symmetric path: bits depend on the rank count"
+for a_, b_ in zip(sym_v, got):
+    assert float(np.abs(a_ - b_).max() / np.abs(b_).max()) <= 1e-13
 # all ranks hold identical results
 chk = torch.stack([o.sum() for o in out])
 lo, hi = chk.clone(), chk.clone()
@@ -129,6 +140,23 @@ dist.destroy_process_group()
 """
 
 
+SYM_SINGLE = r"""
+import sys, numpy as np
+sys.path.insert(0, %(root)r)
+from lpm_v2_b200 import api, mesh as M, problems
+api.init_rank(0)
+m = M.PolyMesh2d(M.ICOS_TRI_SPHERE_SEED, 5)
+zeta = problems.rossby_haurwitz54(m)
+av = problems.abs_vorticity(m, zeta, 2 * np.pi)
+api.tune("sym_min_sources", 0)
+v = api.bve_velocity(m.x, m.y, m.z, zeta, m.area, m.is_active, 1.0)
+s = api.bve_stream(m.x, m.y, m.z, zeta, av, m.area, m.is_active, 1.0)
+np.save(%(symfile)r, np.stack(list(v) + list(s)))
+api.finalize()
+print("OK")
+"""
+
+
 @needs2
 def test_single_process_all_gpus(tmp_path):
     script = tmp_path / "sp.py"
@@ -139,8 +167,13 @@ def test_single_process_all_gpus(tmp_path):
 
 @needs2
 def test_rank_mode_torchrun(tmp_path):
+    symfile = str(tmp_path / "sym_one_gpu.npy")
+    one = tmp_path / "one.py"
+    one.write_text(SYM_SINGLE % {"root": ROOT, "symfile": symfile})
+    r = subprocess.run([sys.executable, str(one)], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0 and "OK" in r.stdout, r.stdout[-2000:] + r.stderr[-4000:]
     script = tmp_path / "rk.py"
-    script.write_text(RANK_MODE % {"root": ROOT})
+    script.write_text(RANK_MODE % {"root": ROOT, "symfile": symfile})
     n = min(_ngpu(), 8)
     r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={n}",
                         "--master-addr", "127.0.0.1", "--master-port", "29617", str(script)],

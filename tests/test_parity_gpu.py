@@ -126,20 +126,16 @@ def test_bve_all_active_self_exclusion(gpu, oracle):
     assert max(relerr(g, w) for g, w in zip(got, want)) <= TOL
 
 
-@pytest.mark.parametrize("variant", list(range(1, 16)) + [31, 32, 41, 43])
-def test_bve_kernel_variants(gpu, oracle, get_mesh, variant):
-    """Every tuning variant (targets per thread, block size, reciprocal batching) is a
-    correct kernel: each meets the parity tolerance on its own.  (They differ from each
-    other in the last bits because the batched reciprocal groups different targets.)"""
-    m = get_mesh(M.ICOS_TRI_SPHERE_SEED, 4)
+@pytest.mark.parametrize("L", [2, 4, 5, 6])
+def test_bve_kernel_shapes_deterministic(gpu, oracle, get_mesh, L):
+    """The one-sided engine picks 1, 2, 4 or 8 targets per thread from the problem size (runtime.cuh,
+    launch_auto<BveVel>): levels 2..6 cover the shapes; each meets the parity tolerance and is bit-identical
+    from run to run."""
+    m = get_mesh(M.ICOS_TRI_SPHERE_SEED, L)
     zeta = problems.gaussian_vortex(m)
-    want = oracle.bve_velocity(m.x, m.y, m.z, zeta, m.area, m.is_active, 1.0)
-    try:
-        gpu.set_bve_variant(variant)
-        got = gpu.bve_velocity(m.x, m.y, m.z, zeta, m.area, m.is_active, 1.0)
-        again = gpu.bve_velocity(m.x, m.y, m.z, zeta, m.area, m.is_active, 1.0)
-    finally:
-        gpu.set_bve_variant(0)
+    want = oracle.bve_velocity_mt(8, m.x, m.y, m.z, zeta, m.area, m.is_active, 1.0, 0, m.n, fast=False)
+    got = gpu.bve_velocity(m.x, m.y, m.z, zeta, m.area, m.is_active, 1.0)
+    again = gpu.bve_velocity(m.x, m.y, m.z, zeta, m.area, m.is_active, 1.0)
     for a, b, c in zip(got, want, again):
         assert relerr(a, b) <= TOL
         assert np.array_equal(a, c)          # run-to-run deterministic
