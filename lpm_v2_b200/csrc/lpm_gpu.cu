@@ -206,8 +206,6 @@ extern "C" int lpm_tune(const char* key, int value)
         rt().sym_min_sources = value;
     } else if (k == "sym_vel_shape") {
         rt().sym_vel_shape = value;
-    } else if (k == "sym_stream_shape") {
-        rt().sym_stream_shape = value;
     } else {
         return set_error(LPM_ERR_INVALID, "lpm_tune: unknown key '%s'", k.c_str());
     }

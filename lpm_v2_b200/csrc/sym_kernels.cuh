@@ -304,9 +304,9 @@ struct SymBveVel : NoSharedTable {
 // BVE stream functions (BveStream in pairs.cuh): psi_i = sum_j w_j ln(R^2 - x_i.x_j) for two weights;
 // record x, y, z, w_rel, w_abs, 0.  One dot product and ONE logarithm serve both directions of a pair:
 // 3 + 6 + 2 + 2 = 13 FP64 instructions for two interactions instead of 22.
-// The branch-free table logarithm (log_group_fast) is evaluated for the whole batch first; if any
-// argument of this thread was outside the table window the batch's logarithms are recomputed with
-// the library log() before anything is accumulated (the one-sided kernel redoes a whole tile instead).
+// The branch-free table logarithm (log_group_fast) is evaluated for a source's T pairs; if any argument
+// of this thread was outside the table window those logarithms are recomputed with the library log()
+// before anything is accumulated (the one-sided kernel redoes a whole tile instead).
 struct SymBveStream : LogSharedTable<32> {
     static constexpr int NS = 6, NA = 2, NC = 2;
     struct Tgt { double x, y, z, w0, w1; };
@@ -316,89 +316,39 @@ struct SymBveStream : LogSharedTable<32> {
         const double2 v0 = p2[0], v1 = p2[1], v2 = p2[2];
         return Tgt{v0.x, v0.y, v1.x, v1.y, v2.x};
     }
-    // ORDER bit 0: retry per source instead of per batch -- a branch after every source's logarithms, which also
-    // keeps ptxas from interleaving the whole batch (see sched_fence)
+    // The retry is per source: a branch after every source's logarithms also keeps ptxas from interleaving the whole
+    // batch (see sched_fence); a retry per batch measured 5 % slower (profiles/r02b_ab_paths.log).
     template <int T, int SB, int ORDER>
     __device__ static __forceinline__ void batch(const SymParams& p, const Tgt (&tg)[T], double (&a)[T][NA],
                                                  const double* __restrict__ sm, double (&cb)[SB][NC], const SharedCtx& sc)
     {
-        if constexpr ((ORDER & 1) != 0) {
-#pragma unroll
-            for (int u = 0; u < SB; ++u) {
-                const double2* p2 = reinterpret_cast<const double2*>(sm + u * NS);
-                const double2 v0 = p2[0], v1 = p2[1], v2 = p2[2];
-                double d[T], l[T];
-                unsigned worst = 0;
-#pragma unroll
-                for (int t = 0; t < T; ++t) {
-                    d[t] = fma(-tg[t].x, v0.x, p.R2);
-                    d[t] = fma(-tg[t].y, v0.y, d[t]);
-                    d[t] = fma(-tg[t].z, v1.x, d[t]);
-                }
-                log_group_fast<KS, T>(d, l, worst, sc);
-                if (__builtin_expect(needs_retry(worst), 0)) {
-#pragma unroll
-                    for (int t = 0; t < T; ++t) l[t] = log_slow_path(d[t]);
-                }
-#pragma unroll
-                for (int t = 0; t < T; ++t) {
-                    a[t][0] = fma(l[t], v1.y, a[t][0]);
-                    a[t][1] = fma(l[t], v2.x, a[t][1]);
-                }
-                cb[u][0] = l[0] * tg[0].w0; cb[u][1] = l[0] * tg[0].w1;
-#pragma unroll
-                for (int t = 1; t < T; ++t) {
-                    cb[u][0] = fma(l[t], tg[t].w0, cb[u][0]);
-                    cb[u][1] = fma(l[t], tg[t].w1, cb[u][1]);
-                }
-            }
-            return;
-        }
-        double w[SB][2], l[SB][T];
-        unsigned worst = 0;
 #pragma unroll
         for (int u = 0; u < SB; ++u) {
             const double2* p2 = reinterpret_cast<const double2*>(sm + u * NS);
             const double2 v0 = p2[0], v1 = p2[1], v2 = p2[2];
-            w[u][0] = v1.y; w[u][1] = v2.x;
-            double d[T];
+            double d[T], l[T];
+            unsigned worst = 0;
 #pragma unroll
             for (int t = 0; t < T; ++t) {
                 d[t] = fma(-tg[t].x, v0.x, p.R2);
                 d[t] = fma(-tg[t].y, v0.y, d[t]);
                 d[t] = fma(-tg[t].z, v1.x, d[t]);
             }
-            log_group_fast<KS, T>(d, l[u], worst, sc);
-        }
-        if (__builtin_expect(needs_retry(worst), 0)) {
-#pragma unroll 1
-            for (int u = 0; u < SB; ++u) {
-                const double2* p2 = reinterpret_cast<const double2*>(sm + u * NS);
-                const double2 v0 = p2[0], v1 = p2[1];
+            log_group_fast<KS, T>(d, l, worst, sc);
+            if (__builtin_expect(needs_retry(worst), 0)) {
 #pragma unroll
-                for (int t = 0; t < T; ++t) {
-                    double d = fma(-tg[t].x, v0.x, p.R2);
-                    d = fma(-tg[t].y, v0.y, d);
-                    d = fma(-tg[t].z, v1.x, d);
-                    const double lv = log_slow_path(d);
-#pragma unroll
-                    for (int uu = 0; uu < SB; ++uu)         // static indexing keeps l in registers
-                        if (uu == u) l[uu][t] = lv;
-                }
+                for (int t = 0; t < T; ++t) l[t] = log_slow_path(d[t]);
             }
-        }
-#pragma unroll
-        for (int u = 0; u < SB; ++u) {
 #pragma unroll
             for (int t = 0; t < T; ++t) {
-                a[t][0] = fma(l[u][t], w[u][0], a[t][0]);
-                a[t][1] = fma(l[u][t], w[u][1], a[t][1]);
+                a[t][0] = fma(l[t], v1.y, a[t][0]);
+                a[t][1] = fma(l[t], v2.x, a[t][1]);
             }
-            cb[u][0] = l[u][0] * tg[0].w0; cb[u][1] = l[u][0] * tg[0].w1;
+            cb[u][0] = l[0] * tg[0].w0; cb[u][1] = l[0] * tg[0].w1;
 #pragma unroll
             for (int t = 1; t < T; ++t) {
-                cb[u][0] = fma(l[u][t], tg[t].w0, cb[u][0]);
-                cb[u][1] = fma(l[u][t], tg[t].w1, cb[u][1]);
+                cb[u][0] = fma(l[t], tg[t].w0, cb[u][0]);
+                cb[u][1] = fma(l[t], tg[t].w1, cb[u][1]);
             }
         }
     }

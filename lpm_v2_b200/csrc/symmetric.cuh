@@ -77,11 +77,12 @@ struct SymVel {
     // fixed-point add per (CTA, source, component)
     static int launch(cudaStream_t st, const SymParams& prm, const SymGeom& g, const double* src, double* acc)
     {
-        switch (rt().sym_vel_shape) {      // A/B of round 2 (the losers go): statement order 35 (fenced) / 27, warps combined or not
-            case 1: return launch_sym<SK, 8, 128, 4, 1, 27, true>(st, prm, g, src, acc);
-            case 2: return launch_sym<SK, 8, 128, 4, 1, 35, false>(st, prm, g, src, acc);
-            case 3: return launch_sym<SK, 8, 128, 4, 1, 27, false>(st, prm, g, src, acc);
-            default: return launch_sym<SK, 8, 128, 4, 1, 35, true>(st, prm, g, src, acc);
+        switch (rt().sym_vel_shape) {      // A/B of round 2 (the losers go)
+            case 1: return launch_sym<SK, 6, 128, 4, 3, 27, true>(st, prm, g, src, acc);      // 6 targets, 3 CTAs per SM (<= 168 registers)
+            case 2: return launch_sym<SK, 6, 128, 4, 2, 27, true>(st, prm, g, src, acc);
+            case 3: return launch_sym<SK, 8, 128, 8, 1, 27, true>(st, prm, g, src, acc);      // batches of 8 sources
+            case 4: return launch_sym<SK, 4, 128, 8, 3, 27, true>(st, prm, g, src, acc);
+            default: return launch_sym<SK, 8, 128, 4, 1, 27, true>(st, prm, g, src, acc);
         }
     }
     static void finalize(cudaStream_t st, const MaskPlan& mp, const double* src, const double* acc, const Outs<3>& out)
@@ -100,12 +101,12 @@ struct SymStream {
         p.x = xyz[0]; p.y = xyz[1]; p.z = xyz[2];
         p.R2 = a.sc[0] * a.sc[0];
     }
-    // 64 KB table per CTA, so two CTAs per SM either way: 128 threads (~155 registers), 4 targets per thread,
-    // batches of 4 sources, one retry branch per batch
+    // 64 KB table per CTA, so two CTAs per SM: 256 threads under a 128-register cap, 4 targets per thread, batches
+    // of 4 sources, a retry branch per source (1131 ms at icosTri 8 against 1187 for 128 threads with ~155 registers
+    // and a retry branch per batch: profiles/r02b_ab_paths.log)
     static int launch(cudaStream_t st, const SymParams& prm, const SymGeom& g, const double* src, double* acc)
     {
-        if (rt().sym_stream_shape == 1) return launch_sym<SK, 4, 256, 4, 2, 1>(st, prm, g, src, acc);
-        return launch_sym<SK, 4, 128, 4, 2, 0>(st, prm, g, src, acc);
+        return launch_sym<SK, 4, 256, 4, 2, 1>(st, prm, g, src, acc);
     }
     static void finalize(cudaStream_t st, const MaskPlan& mp, const double*, const double* acc, const Outs<2>& out)
     {

@@ -80,10 +80,18 @@ def test_config2_colliding_dipoles_level5_two_steps(gpu, oracle, get_mesh):
         sol.Delete()
 
 
-def _solid_body_error(api, m):
+def _solid_body_error(api, m, oracle=None):
+    """(RMS, max) over all particles of |u - u_exact| / (2 pi).  With `oracle`, also checks that the oracle has
+    the same analytic error at the particle where the GPU's is largest (so that maximum is the formula's)."""
     zeta, (ue, ve, we) = problems.solid_body(m)
     u, v, w = api.bve_velocity(m.x, m.y, m.z, zeta, m.area, m.is_active, 1.0)
-    return float(np.sqrt((u - ue) ** 2 + (v - ve) ** 2 + (w - we) ** 2).max() / (2 * PI))
+    e = np.sqrt((u - ue) ** 2 + (v - ve) ** 2 + (w - we) ** 2) / (2 * PI)
+    if oracle is not None:
+        i = int(np.argmax(e))
+        ou, ov, ow = oracle.bve_velocity(m.x, m.y, m.z, zeta, m.area, m.is_active, 1.0, rng=(i, i + 1))
+        eo = np.sqrt((ou[i] - ue[i]) ** 2 + (ov[i] - ve[i]) ** 2 + (ow[i] - we[i]) ** 2) / (2 * PI)
+        assert abs(eo - e[i]) <= 1e-9 * eo, (i, eo, e[i])
+    return float(np.sqrt((e ** 2).mean())), float(e.max())
 
 
 def _rh54_stream_error(api, m):
@@ -100,24 +108,28 @@ def test_analytic_convergence_at_headline_sizes(gpu, oracle, get_mesh):
     """Levels 3-5: oracle and GPU agree on the discretisation error itself (so the rate the GPU shows above
     is the rate of the reference's formula); level 6: against the oracle's values computed once in the build
     container (35 s on 8 threads).  Levels 7-8 (328 K and 1.3 M panels, the pair-symmetric path): the error
-    keeps falling at the oracle's rate -- the max-norm error of the midpoint rule with the self panel skipped
-    is O(h) for the velocity (1.9x per level at levels 3-6) and O(h^2 log h) for the stream function (3.5x per
-    level) -- and any indexing, sign or normalisation fault at these sizes would stop the decrease at once."""
-    vel, psi = {}, {}
+    keeps falling at the oracle's rate -- the midpoint rule with the self panel skipped is O(h) in RMS for the
+    velocity (2.0x per level at levels 3-6) and O(h^2 log h) for the stream function (3.5x per level) -- and any
+    indexing, sign or normalisation fault at these sizes would stop the decrease at once.  The velocity's MAXIMUM
+    error is not monotone in the reference's own formula (0.00138 / 0.00067 / 0.00088 at levels 6 / 7 / 8, always
+    at a centre particle of a level-0 face): there the GPU is checked against the oracle at that very particle."""
+    rms, vmax, psi = {}, {}, {}
     for L in (3, 4, 5):
         m = get_mesh(M.ICOS_TRI_SPHERE_SEED, L)
-        vel[L], psi[L] = _solid_body_error(gpu, m), _rh54_stream_error(gpu, m)
+        (rms[L], vmax[L]), psi[L] = _solid_body_error(gpu, m), _rh54_stream_error(gpu, m)
         with oracle.threads(THREADS):
-            ov, op = _solid_body_error(oracle, m), _rh54_stream_error(oracle, m)
-        assert abs(vel[L] - ov) <= 1e-9 * ov and abs(psi[L] - op) <= 1e-9 * op
+            (orms, omax), op = _solid_body_error(oracle, m), _rh54_stream_error(oracle, m)
+        assert abs(rms[L] - orms) <= 1e-9 * orms and abs(vmax[L] - omax) <= 1e-9 * omax and abs(psi[L] - op) <= 1e-9 * op
     for L in (6, 7, 8):
         m = get_mesh(M.ICOS_TRI_SPHERE_SEED, L)
-        vel[L], psi[L] = _solid_body_error(gpu, m), _rh54_stream_error(gpu, m)
-    print("solid-body velocity error by level:", {k: f"{v:.3e}" for k, v in vel.items()})
+        (rms[L], vmax[L]), psi[L] = _solid_body_error(gpu, m, oracle), _rh54_stream_error(gpu, m)
+    print("solid-body velocity RMS error by level:", {k: f"{v:.3e}" for k, v in rms.items()})
+    print("solid-body velocity max error by level:", {k: f"{v:.3e}" for k, v in vmax.items()})
     print("RH54 stream-function error by level:", {k: f"{v:.3e}" for k, v in psi.items()})
     # oracle (parity build) at level 6, from the build container
-    assert abs(vel[6] - 0.0013848088219147) <= 1e-9 * vel[6] and abs(psi[6] - 0.00490481975440235) <= 1e-9 * psi[6]
+    assert abs(rms[6] - 0.0003562560009639269) <= 1e-9 * rms[6] and abs(vmax[6] - 0.0013848088219147) <= 1e-9 * vmax[6]
+    assert abs(psi[6] - 0.00490481975440235) <= 1e-9 * psi[6]
     for L in (4, 5, 6, 7, 8):
-        assert vel[L - 1] / 2.2 < vel[L] < vel[L - 1] / 1.7, (L, vel)
+        assert rms[L - 1] / 2.2 < rms[L] < rms[L - 1] / 1.8, (L, rms)
         assert psi[L - 1] / 4.5 < psi[L] < psi[L - 1] / 2.8, (L, psi)
-    assert vel[8] < 5e-4 and psi[8] < 6e-4
+    assert rms[8] < 1.2e-4 and vmax[8] < 1.0e-3 and psi[8] < 6e-4

@@ -60,17 +60,12 @@ def test_sym_bve_velocity_random_ragged(sym, oracle, n, frac, seed):
     _check(got, want, ld)
 
 
-@pytest.mark.parametrize("shape", [0, 1])
 @pytest.mark.parametrize("seed,L", [(M.ICOS_TRI_SPHERE_SEED, 2), (M.ICOS_TRI_SPHERE_SEED, 5), (M.CUBED_SPHERE_SEED, 5)])
-def test_sym_bve_stream_meshes(sym, oracle, get_mesh, seed, L, shape):
+def test_sym_bve_stream_meshes(sym, oracle, get_mesh, seed, L):
     m = get_mesh(seed, L)
     zeta = problems.rossby_haurwitz54(m)
     av = problems.abs_vorticity(m, zeta, 2.0 * np.pi)
-    sym.tune("sym_stream_shape", shape)
-    try:
-        got = sym.bve_stream(m.x, m.y, m.z, zeta, av, m.area, m.is_active, 1.0)
-    finally:
-        sym.tune("sym_stream_shape", 0)
+    got = sym.bve_stream(m.x, m.y, m.z, zeta, av, m.area, m.is_active, 1.0)
     want = oracle.bve_stream(m.x, m.y, m.z, zeta, av, m.area, m.is_active, 1.0)
     for g, w in zip(got, want):
         assert relerr(g, w) <= TOL
@@ -90,20 +85,18 @@ def test_sym_bve_stream_random_ragged(sym, oracle, n, frac, seed, R):
     _check(got, want, ld)
 
 
-@pytest.mark.parametrize("shape", [0, 1, 2, 3])
+@pytest.mark.parametrize("shape", [0, 1, 2, 3, 4])
 def test_sym_matches_one_sided_path(sym, get_mesh, shape):
     """Same sum, other order: within a few ulp of the one-sided engine at icosTri 6."""
     m = get_mesh(M.ICOS_TRI_SPHERE_SEED, 6)
     zeta = problems.gaussian_vortex(m)
     av = problems.abs_vorticity(m, zeta, 2.0 * np.pi)
     sym.tune("sym_vel_shape", shape)
-    sym.tune("sym_stream_shape", shape & 1)
     try:
         a = sym.bve_velocity(m.x, m.y, m.z, zeta, m.area, m.is_active, 1.0)
         sa = sym.bve_stream(m.x, m.y, m.z, zeta, av, m.area, m.is_active, 1.0)
     finally:
         sym.tune("sym_vel_shape", 0)
-        sym.tune("sym_stream_shape", 0)
     sym.set_symmetric(False)
     try:
         b = sym.bve_velocity(m.x, m.y, m.z, zeta, m.area, m.is_active, 1.0)

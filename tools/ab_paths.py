@@ -1,9 +1,9 @@
 """A/B on one box (run under gpurun): the one-sided engine against the pair-symmetric path of the BVE velocity and
 stream-function sums at icosTri levels argv[1] (default "7,8"), with the builds still under A/B
-(csrc/lpm_gpu_tuning.h: "sym_vel_shape", "sym_stream_shape").  Prints, per build, the whole-sum time (pack,
+(csrc/lpm_gpu_tuning.h: "sym_vel_shape").  Prints, per build, the whole-sum time (pack,
 kernels, fixed-point conversion, finalize / gather / scatter), the main kernels' own times, interactions/s, and
 the largest difference from the one-sided result relative to the field scale.
-    python tools/ab_paths.py 7,8 [vel shapes, e.g. 0,1,2,3] [stream shapes, e.g. 0,1]"""
+    python tools/ab_paths.py 7,8 [velocity builds, e.g. 0,1,2,3]"""
 import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np
@@ -11,7 +11,7 @@ from lpm_v2_b200 import api, mesh, problems
 
 levels = [int(a) for a in sys.argv[1].split(",")] if len(sys.argv) > 1 else [7, 8]
 vshapes = [int(a) for a in sys.argv[2].split(",")] if len(sys.argv) > 2 else [0]
-sshapes = [int(a) for a in sys.argv[3].split(",")] if len(sys.argv) > 3 else [0]
+sshapes = [0]
 api.init(1)
 api.set_profiling(True)
 api.tune("sym_min_sources", 0)
@@ -21,12 +21,12 @@ for L in levels:
     pairs = m.n * m.n_active - m.n_active
     av = problems.abs_vorticity(m, z, 2 * np.pi)
     sums = (("bve_velocity", "sym_vel_shape", vshapes, lambda: api.bve_velocity(m.x, m.y, m.z, z, m.area, m.is_active, 1.0)),
-            ("bve_stream", "sym_stream_shape", sshapes, lambda: api.bve_stream(m.x, m.y, m.z, z, av, m.area, m.is_active, 1.0)))
+            ("bve_stream", None, sshapes, lambda: api.bve_stream(m.x, m.y, m.z, z, av, m.area, m.is_active, 1.0)))
     for name, key, shapes, fn in sums:
         ref = None
         for build in [None] + list(shapes):
             api.set_symmetric(build is not None)
-            if build is not None:
+            if build is not None and key:
                 api.tune(key, build)
             ts, ks = [], None
             for _ in range(3 if L < 8 else 2):
@@ -42,6 +42,7 @@ for L in levels:
             kern = ", ".join(f"{k.split('/')[1]} {v[1] / v[0]:.3f}" for k, v in ks.items())
             print(f"L{L} {name} {label}: sum ms " + " ".join(f"{t:.3f}" for t in ts) + f"  (kernels: {kern})"
                   f"  -> {pairs / min(ts) / 1e9:.1f} G interactions/s, max diff from one-sided: {diff:.2e}", flush=True)
-        api.tune(key, 0)
+        if key:
+            api.tune(key, 0)
 api.set_symmetric(True)
 api.tune("sym_min_sources", 200000)
