@@ -39,6 +39,8 @@ def parse():
     ap.add_argument("--no-rk4", action="store_true", help="skip the RK4 step-time measurement")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-parity", action="store_true", help="skip the per-rank oracle parity sample")
+    ap.add_argument("--parity-targets", type=int, default=4096, help="contiguous targets per rank in the parity sample")
+    ap.add_argument("--e2e-reps", type=int, default=0, help="timed end-to-end calls (0 = min(steps, 3))")
     ap.add_argument("--one-sided", action="store_true", help="A/B: lpm_set_symmetric(0), every ordered pair evaluated")
     return ap.parse_args()
 
@@ -246,7 +248,7 @@ def run_b200(args):
     e2e_step()
     barrier()
     t0 = time.perf_counter()
-    e2e_reps = max(1, min(args.steps, 3))
+    e2e_reps = args.e2e_reps or max(1, min(args.steps, 3))
     for _ in range(e2e_reps):
         e2e_step()
     barrier()
@@ -260,7 +262,7 @@ def run_b200(args):
     parity = None
     if not args.no_parity:
         from oracle import binding as O
-        cnt = min(4096, iend - ibeg)
+        cnt = min(args.parity_targets, iend - ibeg)
         tb = ibeg + (iend - ibeg - cnt) // 2
         threads = max(1, (os.cpu_count() or 1) // world)
         ref = O.bve_velocity_mt(threads, m.x, m.y, m.z, zeta, m.area, m.is_active, 1.0, tb, tb + cnt, fast=False)
@@ -281,11 +283,15 @@ def run_b200(args):
         sph = solvers.BVEMesh(m, zeta, 1.0, 2.0 * np.pi)
         sph.velocity = [t.cpu().numpy().copy() for t in out]
         sol = solvers.BVESolver(sph)
-        sol.Timestep(sph, 0.01, with_stream=True, copy_back=False)      # warm-up step
+        # examples/rh54.namelist ships dt = 0.01 for 6144 panels; scaled with the mesh spacing, because the reference's
+        # RK4 does not re-project stage positions onto the sphere: at dt |u| >> h the denominators R^2 - x_i.x_j of
+        # neighbouring particles change sign (in the reference too) and the step is no longer a meaningful workload
+        dt = 0.01 * float(np.sqrt(6144.0 / F))
+        sol.Timestep(sph, dt, with_stream=True, copy_back=False)      # warm-up step
         barrier()
         api.profile_breakdown(reset=True)
         t0 = time.perf_counter()
-        sol.Timestep(sph, 0.01, with_stream=True, copy_back=False)
+        sol.Timestep(sph, dt, with_stream=True, copy_back=False)
         barrier()
         rk4_ms = (time.perf_counter() - t0) * 1e3
         rk4_kernels = api.profile_breakdown(reset=True)
@@ -344,6 +350,7 @@ def run_b200(args):
             "step_frac": FLOP_PER_INTERACTION * inter / world / (ms_total / args.steps * 1e-3) / 1e12 / probe_tf,
             "kernels": per_kernel,
             "rk4_step_ms": rk4_ms,
+            "rk4_dt": 0.01 * float(np.sqrt(6144.0 / F)),
             "rk4_kernels": {k: {"launches": c, "ms": t} for k, (c, t) in (rk4_kernels or {}).items()},
             "note": f"achieved = algorithmic {FLOP_PER_INTERACTION:.0f} FLOP/interaction (SURVEY.md 8d) x the interactions one "
                     "launch of `kernel` covers on rank 0 / its mean duration (CUDA events on the launching stream inside the "

@@ -155,7 +155,6 @@ struct Runtime {
     int64_t launches = 0;
     bool symmetric = true;               // pair-symmetric evaluation of whole BVE sums (lpm_set_symmetric)
     int32_t sym_min_sources = 200000;    // ... for at least this many active particles (symmetric.cuh)
-    int sym_vel_shape = 0;               // builds under A/B (csrc/lpm_gpu_tuning.h)
     bool pse_series = true;              // sphere PSE kernels: theta^2 by series inside the cut-off (false: atan2 always)
     int pse_culling = 1;                 // PSE kernels: 0 reference order, every tile; 1 cell order + tile culling; 2 cell order only
     // NCCL (rank mode)

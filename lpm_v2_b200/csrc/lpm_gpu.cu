@@ -204,8 +204,6 @@ extern "C" int lpm_tune(const char* key, int value)
         max_chunks_ref() = value;
     } else if (k == "sym_min_sources") {
         rt().sym_min_sources = value;
-    } else if (k == "sym_vel_shape") {
-        rt().sym_vel_shape = value;
     } else {
         return set_error(LPM_ERR_INVALID, "lpm_tune: unknown key '%s'", k.c_str());
     }

@@ -3,7 +3,7 @@
  * uses it; keys may disappear without notice.
  *   "max_chunks"        upper bound on source chunks per evaluation (every rank the same value)
  *   "sym_min_sources"   smallest active-particle count that takes the pair-symmetric path (default 200000)
- *   "sym_vel_shape"     builds of the symmetric velocity kernel under A/B (0 = default) */
+ * (Builds under A/B get a key here while a round measures them; none is pending.) */
 #ifndef LPM_GPU_TUNING_H
 #define LPM_GPU_TUNING_H
 #ifdef __cplusplus

@@ -73,17 +73,14 @@ struct SymVel {
         p.x = xyz[0]; p.y = xyz[1]; p.z = xyz[2];
         p.R2 = a.sc[0] * a.sc[0];
     }
-    // 8 targets per thread, batches of 4 sources, the warps' source sums combined in shared memory: one
-    // fixed-point add per (CTA, source, component)
+    // 8 targets per thread, batches of 8 sources (two groups of 4, phase by phase: statement order 27), the warps'
+    // source sums combined in shared memory: one fixed-point add per (CTA, source, component).  246 registers, two
+    // CTAs of 128 threads per SM.  Measured at icosTri 8 (profiles/r02b_ab_paths.log, r02c_ab_paths.log; the
+    // triangle kernel alone): this build 791 ms; batches of 4: 824; statement order 35 (one source at a time, fenced):
+    // 848; warps not combined: 869; 6 targets per thread at 2 / 3 CTAs per SM: 837 / 859; 4 targets, 3 CTAs: 881.
     static int launch(cudaStream_t st, const SymParams& prm, const SymGeom& g, const double* src, double* acc)
     {
-        switch (rt().sym_vel_shape) {      // A/B of round 2 (the losers go)
-            case 1: return launch_sym<SK, 6, 128, 4, 3, 27, true>(st, prm, g, src, acc);      // 6 targets, 3 CTAs per SM (<= 168 registers)
-            case 2: return launch_sym<SK, 6, 128, 4, 2, 27, true>(st, prm, g, src, acc);
-            case 3: return launch_sym<SK, 8, 128, 8, 1, 27, true>(st, prm, g, src, acc);      // batches of 8 sources
-            case 4: return launch_sym<SK, 4, 128, 8, 3, 27, true>(st, prm, g, src, acc);
-            default: return launch_sym<SK, 8, 128, 4, 1, 27, true>(st, prm, g, src, acc);
-        }
+        return launch_sym<SK, 8, 128, 8, 1, 27, true>(st, prm, g, src, acc);
     }
     static void finalize(cudaStream_t st, const MaskPlan& mp, const double* src, const double* acc, const Outs<3>& out)
     {

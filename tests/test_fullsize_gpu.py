@@ -56,11 +56,21 @@ def test_l8_linearity(gpu, l8, l8_rh54):
 
 
 def test_l8_slices_are_bitwise_independent_of_partition(gpu, l8, l8_rh54):
-    """Device-pointer API on LoadBalance slices for 8 ranks == the 1-GPU result, bit for
-    bit (a target's sum does not depend on the slice it is in)."""
+    """One-sided engine: the device-pointer API on LoadBalance slices for 8 ranks == the 1-GPU one-sided result,
+    bit for bit (a target's sum does not depend on the slice it is in).  The default whole evaluation
+    (pair-symmetric at this size) differs from it by summation order only; its own independence of the rank
+    count is tested in tests/test_multigpu.py and tests/test_emu_abi.py."""
     import torch
     from lpm_v2_b200 import torch_api, api
-    zeta, (u, v, w) = l8_rh54
+    zeta, sym_uvw = l8_rh54
+    gpu.set_symmetric(False)
+    try:
+        u, v, w = gpu.bve_velocity(l8.x, l8.y, l8.z, zeta, l8.area, l8.is_active, 1.0)
+    finally:
+        gpu.set_symmetric(True)
+    for a, b in zip(sym_uvw, (u, v, w)):
+        assert relerr(a, b) <= 1e-12
+        assert not np.array_equal(a, b)          # the default did take the other path
     dev = torch.device("cuda:0")
     torch.cuda.set_device(0)
     t = {k: torch.from_numpy(np.ascontiguousarray(a)).to(dev) for k, a in

@@ -85,18 +85,13 @@ def test_sym_bve_stream_random_ragged(sym, oracle, n, frac, seed, R):
     _check(got, want, ld)
 
 
-@pytest.mark.parametrize("shape", [0, 1, 2, 3, 4])
-def test_sym_matches_one_sided_path(sym, get_mesh, shape):
+def test_sym_matches_one_sided_path(sym, get_mesh):
     """Same sum, other order: within a few ulp of the one-sided engine at icosTri 6."""
     m = get_mesh(M.ICOS_TRI_SPHERE_SEED, 6)
     zeta = problems.gaussian_vortex(m)
     av = problems.abs_vorticity(m, zeta, 2.0 * np.pi)
-    sym.tune("sym_vel_shape", shape)
-    try:
-        a = sym.bve_velocity(m.x, m.y, m.z, zeta, m.area, m.is_active, 1.0)
-        sa = sym.bve_stream(m.x, m.y, m.z, zeta, av, m.area, m.is_active, 1.0)
-    finally:
-        sym.tune("sym_vel_shape", 0)
+    a = sym.bve_velocity(m.x, m.y, m.z, zeta, m.area, m.is_active, 1.0)
+    sa = sym.bve_stream(m.x, m.y, m.z, zeta, av, m.area, m.is_active, 1.0)
     sym.set_symmetric(False)
     try:
         b = sym.bve_velocity(m.x, m.y, m.z, zeta, m.area, m.is_active, 1.0)
