@@ -162,6 +162,11 @@ struct Runtime {
     void* comm = nullptr;
     int world = 1, rank = 0;
     std::vector<SharedSlab> slabs;
+    // live resident solvers: handle -> how to destroy it.  lpm_gpu_finalize destroys what the caller left behind
+    // (their device memory, streams and events go with the runtime); a later *_delete of such a handle is a no-op
+    // and any other use of it an error, instead of a dereference of freed memory.
+    struct LiveSolver { void* handle; void (*destroy)(void*); };
+    std::vector<LiveSolver> live_solvers;
 };
 
 inline Runtime& rt()

@@ -97,6 +97,11 @@ extern "C" int lpm_gpu_finalize(void)
 {
     Runtime& R = rt();
     if (!R.initialised) return LPM_OK;
+    while (!R.live_solvers.empty()) {        // solvers the caller never deleted: their memory lives on these devices
+        auto l = R.live_solvers.back();
+        R.live_solvers.pop_back();
+        l.destroy(l.handle);
+    }
     while (!R.slabs.empty()) free_shared(R.slabs.back().local);
     if (R.comm && nccl().loaded) nccl().CommDestroy(R.comm);
     R.comm = nullptr;

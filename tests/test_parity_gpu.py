@@ -389,6 +389,30 @@ def test_betaplane_rk4_step(gpu, oracle, get_mesh):
 
 
 # ---------------------------------------------------------------- error behaviour
+def test_solver_handles_and_finalize(gpu, get_mesh):
+    """lpm_gpu_finalize with a solver still alive frees it; afterwards Delete of that handle is a no-op and any
+    other use is an error (not a dereference of freed device state), and the library can be initialised again."""
+    from lpm_v2_b200 import LpmError
+    m = get_mesh(M.ICOS_TRI_SPHERE_SEED, 2)
+    sph = solvers.BVEMesh(m, problems.gaussian_vortex(m), 1.0, 2 * PI)
+    sph.SetVelocityOnMesh()
+    sol = solvers.BVESolver(sph)
+    sol.Timestep(sph, 0.01, with_stream=True)
+    try:
+        gpu.finalize()
+        with pytest.raises(LpmError) as ei:
+            sol.Timestep(sph, 0.01, with_stream=True)
+        assert ei.value.code == 1 and "stale solver handle" in str(ei.value)
+        sol.Delete()                                    # no-op, no crash
+        sol.Delete()
+    finally:
+        gpu.init(1)
+    sol2 = solvers.BVESolver(sph)                       # a fresh runtime works as before
+    sol2.Timestep(sph, 0.01, with_stream=False)
+    sol2.Delete()
+    sol2.Delete()                                       # deleting twice is harmless too
+
+
 def test_invalid_arguments_are_reported_not_fatal(gpu):
     from lpm_v2_b200 import LpmError
     x = np.ones(4)
