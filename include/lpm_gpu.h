@@ -22,7 +22,14 @@
  *   - "host" entry points take host pointers and are synchronous: outputs
  *     are complete on return.  "_dev" entry points take device pointers on
  *     the current CUDA device and enqueue on `stream` (a cudaStream_t passed
- *     as void*; NULL = default stream) without synchronising.
+ *     as void*; NULL = default stream); the first evaluation for a mask
+ *     synchronises that stream once (to read the active count).
+ *     ONE STREAM PER DEVICE AT A TIME: every evaluation on a device packs its
+ *     sources and partial sums into that device's single workspace, so two
+ *     evaluations must not be in flight on different streams of the same
+ *     device (the host entry points and the resident solvers use the
+ *     library's own stream and are subject to the same rule: finish or
+ *     synchronise one before starting the next on another stream).
  */
 #ifndef LPM_GPU_H
 #define LPM_GPU_H

@@ -117,6 +117,16 @@ struct Device {
     cudaStream_t stream = nullptr;       // library-owned stream (host API, resident solvers)
     cudaEvent_t ev_done = nullptr;       // cross-device barrier (resident solvers)
     cudaEvent_t ev_sum[2] = {nullptr, nullptr};   // profiling: around the last whole direct sum (pack, sort, kernels)
+    cudaStream_t comm_stream = nullptr;  // rank mode: collectives that overlap a sum's compute (symmetric.cuh)
+    cudaEvent_t ev_comm[2] = {nullptr, nullptr};
+    int ensure_comm_stream()
+    {
+        if (comm_stream) return LPM_OK;
+        if (cudaStreamCreateWithFlags(&comm_stream, cudaStreamNonBlocking) != cudaSuccess) return LPM_ERR_CUDA;
+        for (auto& e : ev_comm)
+            if (cudaEventCreateWithFlags(&e, cudaEventDisableTiming) != cudaSuccess) return LPM_ERR_CUDA;
+        return LPM_OK;
+    }
     // profiling: one event pair per direct-sum main kernel since the last reset
     // and what it timed (lpm_profile_breakdown): tag = 2 * sum + engine; sum 0 BVE velocity, 1 BVE stream
     // functions, 2 any other; engine 0 one-sided ds_kernel, 1 pair-symmetric sym_kernel
@@ -154,7 +164,9 @@ struct Runtime {
     bool profiling = false;
     int64_t launches = 0;
     bool symmetric = true;               // pair-symmetric evaluation of whole BVE sums (lpm_set_symmetric)
-    int32_t sym_min_sources = 200000;    // ... for at least this many active particles (symmetric.cuh)
+    int force_T = 0;                     // A/B: targets per thread of the one-sided engine (0 = automatic)
+    int32_t sym_min_sources = 200000;
+    int32_t sym_chunk_tiles = 16;        // ... in chunks of this many source tiles per CTA (symmetric.cuh, kSymChunkTiles)    // ... for at least this many active particles (symmetric.cuh)
     bool pse_series = true;              // sphere PSE kernels: theta^2 by series inside the cut-off (false: atan2 always)
     int pse_culling = 1;                 // PSE kernels: 0 reference order, every tile; 1 cell order + tile culling; 2 cell order only
     // NCCL (rank mode)

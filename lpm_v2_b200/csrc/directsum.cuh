@@ -35,7 +35,16 @@ inline int& max_chunks_ref()
     static int v = kMaxChunksDefault;
     return v;
 }
-constexpr int kChunkMin = 8192;     // do not split the source list finer than this
+// Do not split the source list finer than this.  1024 rather than round 1's 8192: a rank of an 8-GPU run at icosTri 6
+// launches only 30 target blocks, and with 10 chunks of 8192 sources its 300 CTAs filled less than one wave (kernel at
+// 0.54 of its FP64 bound); 64 chunks of 1280 sources with 4 targets per thread reach 0.84 (profiles/r02d_slice_sweep_L6.log).
+// From icosTri 8 upwards the cap of 64 chunks was binding already, so nothing changes there.
+constexpr int kChunkMinDefault = 1024;
+inline int& chunk_min_ref()
+{
+    static int v = kChunkMinDefault;
+    return v;
+}
 constexpr int kTile = 256;          // sources per shared-memory tile (all kernels)
 constexpr int kMaxNeedWords = 256;  // tile culling: bitmap words per CTA (<= 8192 tiles per chunk)
 
@@ -59,7 +68,8 @@ inline void ds_chunks(int64_t nsrc, int32_t* nsrc_pad, int32_t* chunk, int32_t* 
 {
     int64_t pad = (nsrc + kTile - 1) / kTile * kTile;
     if (pad == 0) pad = kTile;
-    int64_t nc = (pad + kChunkMin - 1) / kChunkMin;
+    const int64_t cmin = chunk_min_ref();
+    int64_t nc = (pad + cmin - 1) / cmin;
     int cap = max_chunks_ref();
     if (nall > (16LL << 20)) cap = cap < 16 ? cap : 16;
     else if (nall > (8LL << 20)) cap = cap < 32 ? cap : 32;

@@ -111,6 +111,8 @@ extern "C" int lpm_gpu_finalize(void)
         d.ws.release();
         cudaEventDestroy(d.ev_done);
         for (auto& e : d.ev_sum) { if (e) cudaEventDestroy(e); e = nullptr; }
+        for (auto& e : d.ev_comm) { if (e) cudaEventDestroy(e); e = nullptr; }
+        if (d.comm_stream) { cudaStreamSynchronize(d.comm_stream); cudaStreamDestroy(d.comm_stream); d.comm_stream = nullptr; }
         for (auto& pr : d.prof) { cudaEventDestroy(pr.first); cudaEventDestroy(pr.second); }
         d.prof.clear(); d.prof_used = 0;
         cudaStreamDestroy(d.stream);
@@ -207,6 +209,14 @@ extern "C" int lpm_tune(const char* key, int value)
     if (k == "max_chunks") {
         if (value < 1 || value > 256) return set_error(LPM_ERR_INVALID, "lpm_tune(max_chunks, %d): 1..256", value);
         max_chunks_ref() = value;
+    } else if (k == "chunk_min") {
+        if (value < kTile || value % kTile) return set_error(LPM_ERR_INVALID, "lpm_tune(chunk_min, %d): a multiple of %d", value, kTile);
+        chunk_min_ref() = value;
+    } else if (k == "force_T") {
+        rt().force_T = value;
+    } else if (k == "sym_chunk_tiles") {
+        if (value < 1) return set_error(LPM_ERR_INVALID, "lpm_tune(sym_chunk_tiles, %d)", value);
+        rt().sym_chunk_tiles = value;
     } else if (k == "sym_min_sources") {
         rt().sym_min_sources = value;
     } else {

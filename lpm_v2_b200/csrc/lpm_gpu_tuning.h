@@ -2,6 +2,9 @@
  * tools/ and for tests that need a small problem to take a large problem's code path.  A Fortran caller never
  * uses it; keys may disappear without notice.
  *   "max_chunks"        upper bound on source chunks per evaluation (every rank the same value)
+ *   "chunk_min"         smallest source chunk (a multiple of 256; every rank the same value)
+ *   "force_T"           targets per thread of the one-sided engine: 1, 2, 4, 8 (0 = automatic)
+ *   "sym_chunk_tiles"   source tiles per CTA of the symmetric triangle kernel (default 16; every rank the same value)
  *   "sym_min_sources"   smallest active-particle count that takes the pair-symmetric path (default 200000)
  * (Builds under A/B get a key here while a round measures them; none is pending.) */
 #ifndef LPM_GPU_TUNING_H

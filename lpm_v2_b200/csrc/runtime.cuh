@@ -427,6 +427,7 @@ inline int reserve_sources(Device& dev, const MaskPlan& mp, int32_t* nsrc_pad)
 // batched reciprocals -- is the same on 1 and on 8 GPUs.
 inline int auto_T(int64_t ntgt, int nchunks, int sm_count, int block)
 {
+    if (rt().force_T == 1 || rt().force_T == 2 || rt().force_T == 4) return rt().force_T;
     const int64_t want = 2LL * sm_count;
     for (int T : {4, 2}) {
         int64_t items = (ntgt + (int64_t)block * T - 1) / ((int64_t)block * T) * nchunks;
@@ -461,8 +462,7 @@ inline int launch_auto(cudaStream_t st, const typename K::Params& prm, const DsG
 }
 
 // The BVE velocity kernel (the headline path of round 1; now the passive-target and partial-range path).
-// 8 targets per thread (3 CTAs of 128 threads per SM) when that still leaves >= 8 waves of CTAs, else 4
-// (5 CTAs per SM), 2, 1.  The statement orders (BveVelT<4, ORDER>) are the ones tools/search_order.py
+// 8 targets per thread (3 CTAs of 128 threads per SM) for large sets, else 4 (5 CTAs per SM), 2, 1.  The statement orders (BveVelT<4, ORDER>) are the ones tools/search_order.py
 // short-listed and the GPU sweeps measured fastest (profiles/r01b_sweep_L{7,8}_orders.log): at icosTri 8,
 // T = 8 / ORDER 3680: 1412 ms;  T = 4 / ORDER 10765: 1441 ms;  T = 4 / ORDER 0: 1499 ms.  Every shape that
 // lost a sweep (other block sizes and unrolls, register caps, one MUFU per pair or per two pairs,
@@ -472,8 +472,11 @@ inline int launch_auto<BveVel>(cudaStream_t st, const BveVel::Params& prm, const
                                const double* src, const int32_t* scan, double* partial, int sm_count)
 {
     using K = BveVel;
+    // 8 targets per thread only when the WHOLE particle set gives >= 32 waves of such CTAs (3 per SM), so that a rank
+    // of an 8-GPU run still has >= 4 waves: icosTri 7 and up; icosTri 6 takes 4 targets per thread (0.84 against 0.80 of
+    // the FP64 bound on a rank's slice).  Decided from the whole set, never the slice: the bits must not depend on G.
     const int64_t items8 = (g.nall + 128 * 8 - 1) / (128 * 8) * g.nchunks;
-    if (items8 >= 8LL * 3 * sm_count) {
+    if (rt().force_T == 8 || (rt().force_T == 0 && items8 >= 32LL * 3 * sm_count)) {
         launch_ds<BveVelT<4, 3680>, 8, 128, 2>(st, prm, g, src, scan, partial);
         return LPM_OK;
     }

@@ -401,7 +401,12 @@ sym_kernel(const SymParams prm, const SymGeom g, const double* __restrict__ src,
     const int tid = threadIdx.x, lane = tid & 31;
     const int I = blockIdx.x % g.nblocks;           // chunk is the slow index, as in ds_kernel
     const int ck = blockIdx.x / g.nblocks;
-    if (g.world > 1 && (I % g.world) != g.rank) return;
+    // Blocks are dealt to ranks in serpentine order (0 .. w-1, w-1 .. 0, ...): a block's work falls linearly with
+    // its index (the triangle), so plain round-robin would give rank 0 the longest block of every round.
+    if (g.world > 1) {
+        const int q = I / g.world, p = I % g.world;
+        if (((q & 1) ? g.world - 1 - p : p) != g.rank) return;
+    }
     const int kdiag = I * DT;                        // first of this block's DT diagonal tiles
     int k0 = ck * g.chunk_tiles;
     const int k1 = min(k0 + g.chunk_tiles, g.ntiles);

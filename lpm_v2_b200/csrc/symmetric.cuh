@@ -38,6 +38,7 @@ namespace lpm {
 // Below this many active particles the triangular grid is too few CTAs to fill a B200 and the one-sided
 // engine (whose targets-per-thread adapts) is faster: icosTri 7 (327 680) gains 5 %, icosTri 6 (81 920) loses.
 constexpr int32_t kSymMinSources = 200000;
+constexpr int32_t kSymChunkTiles = 16;      // source tiles (of 256) per CTA of the triangle kernel
 
 template <class K, int T, int BLOCK, int SB, int MINB, int ORDER = 0, bool COMBINE = false>
 inline int launch_sym(cudaStream_t st, const SymParams& prm, SymGeom g, const double* src, double* acc)
@@ -137,7 +138,12 @@ inline int sym_evaluate(Device& dev, cudaStream_t st, MaskPlan& mp, const Args& 
         ds_chunks(mp.nsrc, &g.nsrc_pad, &chunk, &g.nchunks, mp.n);
         g.nsrc = mp.nsrc;
         g.ntiles = g.nsrc_pad / kTile;
-        g.chunk_tiles = chunk / kTile;
+        // The triangle kernel keeps no partial sums, so its chunks can be much shorter than the one-sided
+        // engine's (whose chunk count is capped by its scratch): kSymChunkTiles tiles per CTA keep the last wave of
+        // CTAs -- the tail -- below 1 % of a rank's share even on 8 GPUs (icosTri 8, 8 ranks: 101.3 ms with chunks
+        // of 80 tiles, 17 waves of 4 ms CTAs).  Depends on the active count only, like ds_chunks.
+        g.chunk_tiles = std::min<int32_t>(chunk / kTile, rt().sym_chunk_tiles);
+        g.nchunks = (g.ntiles + g.chunk_tiles - 1) / g.chunk_tiles;
         g.world = R.rank_mode ? R.world : 1;
         g.rank = R.rank_mode ? R.rank : 0;
         SymParams prm{};
@@ -171,13 +177,17 @@ inline int sym_evaluate(Device& dev, cudaStream_t st, MaskPlan& mp, const Args& 
             LPM_TRY(S::launch(st, prm, g, src, ws.sym_acc.as<double>()));
             if (prof) LPM_CUDA(cudaEventRecord(pe, st));
             if (g.world > 1) {
+                // The integer all-reduce of the accumulators (7 x 8 B per sum: 220 MB at icosTri 8) runs on the device's
+                // communication stream while the passive part below computes on `st`; the conversion and the finalize
+                // kernel wait for it at the end.  NCCL sees the same call order on every rank: this all-reduce, then
+                // the grouped broadcast of the passive slices.
                 if (!R.comm) return set_error(LPM_ERR_COMM, "world size %d but no communicator (lpm_comm_init_rank)", R.world);
-                LPM_NCCL(nccl().AllReduce(ws.sym_acc.p, ws.sym_acc.p, nacc * kFxWords, /*ncclInt64*/ 4, /*ncclSum*/ 0, R.comm, st));
+                LPM_TRY(dev.ensure_comm_stream());
+                LPM_CUDA(cudaEventRecord(dev.ev_comm[0], st));
+                LPM_CUDA(cudaStreamWaitEvent(dev.comm_stream, dev.ev_comm[0], 0));
+                LPM_NCCL(nccl().AllReduce(ws.sym_acc.p, ws.sym_acc.p, nacc * kFxWords, /*ncclInt64*/ 4, /*ncclSum*/ 0, R.comm, dev.comm_stream));
+                LPM_CUDA(cudaEventRecord(dev.ev_comm[1], dev.comm_stream));
             }
-            sym_fx_to_double_kernel<<<(unsigned)((nacc + 255) / 256), 256, 0, st>>>((int64_t)nacc, ws.sym_acc.as<long long>(), fxw,
-                                                                                 ws.sym_acc2.as<double>());
-            S::finalize(st, mp, src, ws.sym_acc2.as<double>(), out);
-            count_launch(5);
         }
         // ---- passive targets x all active sources: the one-sided engine on the gathered passive particles
         const int64_t nv = mp.n - mp.nsrc;
@@ -221,6 +231,15 @@ inline int sym_evaluate(Device& dev, cudaStream_t st, MaskPlan& mp, const Args& 
                 scatter_kernel<<<gb, 256, 0, st>>>(nv, perm, bufs[k], dst);
             }
             count_launch(NOUT);
+        }
+        // ---- active x active, second half: limbs -> doubles, cross product / copy into `out`
+        if (mp.nsrc > 0) {
+            const size_t nacc = (size_t)g.nsrc_pad * SK::NC;
+            if (g.world > 1) LPM_CUDA(cudaStreamWaitEvent(st, dev.ev_comm[1], 0));
+            sym_fx_to_double_kernel<<<(unsigned)((nacc + 255) / 256), 256, 0, st>>>((int64_t)nacc, ws.sym_acc.as<long long>(),
+                                                                                 ws.sym_fx.as<FxWindow>(), ws.sym_acc2.as<double>());
+            S::finalize(st, mp, src, ws.sym_acc2.as<double>(), out);
+            count_launch(5);
         }
         LPM_CUDA(cudaGetLastError());
         return LPM_OK;

@@ -44,6 +44,6 @@ for L in levels:
             print(f"L{L} {name} {label}: sum ms " + " ".join(f"{t:.3f}" for t in ts) + f"  (kernels: {kern})"
                   f"  -> {pairs / min(ts) / 1e9:.1f} G interactions/s, max diff from one-sided: {diff:.2e}", flush=True)
         if key:
-            api.tune(key, 0)
+            api.tune(key, shapes[0])        # the first value listed is the default
 api.set_symmetric(True)
 api.tune("sym_min_sources", 200000)
