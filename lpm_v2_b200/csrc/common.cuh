@@ -164,6 +164,7 @@ struct Runtime {
     bool profiling = false;
     int64_t launches = 0;
     bool symmetric = true;               // pair-symmetric evaluation of whole BVE sums (lpm_set_symmetric)
+    int sym_vel_order = 43;              // LPM_SYM_ORDER_SWEEP builds only
     int force_T = 0;                     // A/B: targets per thread of the one-sided engine (0 = automatic)
     int32_t sym_min_sources = 200000;
     int32_t sym_chunk_tiles = 16;        // ... in chunks of this many source tiles per CTA (symmetric.cuh, kSymChunkTiles)    // ... for at least this many active particles (symmetric.cuh)

@@ -212,6 +212,8 @@ extern "C" int lpm_tune(const char* key, int value)
     } else if (k == "chunk_min") {
         if (value < kTile || value % kTile) return set_error(LPM_ERR_INVALID, "lpm_tune(chunk_min, %d): a multiple of %d", value, kTile);
         chunk_min_ref() = value;
+    } else if (k == "sym_vel_order") {
+        rt().sym_vel_order = value;
     } else if (k == "force_T") {
         rt().force_T = value;
     } else if (k == "sym_chunk_tiles") {

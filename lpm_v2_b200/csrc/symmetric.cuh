@@ -74,14 +74,26 @@ struct SymVel {
         p.x = xyz[0]; p.y = xyz[1]; p.z = xyz[2];
         p.R2 = a.sc[0] * a.sc[0];
     }
-    // 8 targets per thread, batches of 8 sources (two groups of 4, phase by phase: statement order 27), the warps'
-    // source sums combined in shared memory: one fixed-point add per (CTA, source, component).  246 registers, two
-    // CTAs of 128 threads per SM.  Measured at icosTri 8 (profiles/r02b_ab_paths.log, r02c_ab_paths.log; the
-    // triangle kernel alone): this build 791 ms; batches of 4: 824; statement order 35 (one source at a time, fenced):
-    // 848; warps not combined: 869; 6 targets per thread at 2 / 3 CTAs per SM: 837 / 859; 4 targets, 3 CTAs: 881.
+    // 8 targets per thread, batches of 8 sources (two groups of 4, phase by phase, a scheduling fence after each group:
+    // statement order 43), the warps' source sums combined in shared memory: one fixed-point add per (CTA, source,
+    // component).  244 registers, two CTAs of 128 threads per SM.  Measured at icosTri 8 (profiles/r02b_ab_paths.log,
+    // r02c_ab_paths.log, r02e_order_sweep.log; the triangle kernel alone): this build 769 ms; the same unfenced
+    // (order 27): 790; batches of 4: 824; one source at a time, fenced (order 35): 848; warps not combined: 869;
+    // 6 targets per thread at 2 / 3 CTAs per SM: 837 / 859; 4 targets, 3 CTAs: 881.  The 31 other statement orders
+    // of the sweep lie within 783 ... 800 ms.
     static int launch(cudaStream_t st, const SymParams& prm, const SymGeom& g, const double* src, double* acc)
     {
-        return launch_sym<SK, 8, 128, 8, 1, 27, true>(st, prm, g, src, acc);
+#ifdef LPM_SYM_ORDER_SWEEP      // tools/order_sweep.py: one instantiation per statement order behind lpm_tune("sym_vel_order")
+        switch (rt().sym_vel_order) {
+#define LPM_O(n) case n: return launch_sym<SK, 8, 128, 8, 1, n, true>(st, prm, g, src, acc);
+            LPM_O(0) LPM_O(1) LPM_O(2) LPM_O(3) LPM_O(4) LPM_O(5) LPM_O(6) LPM_O(7) LPM_O(8) LPM_O(9) LPM_O(10) LPM_O(11)
+            LPM_O(16) LPM_O(17) LPM_O(18) LPM_O(19) LPM_O(20) LPM_O(21) LPM_O(22) LPM_O(23) LPM_O(24) LPM_O(25) LPM_O(26)
+            LPM_O(32 + 8) LPM_O(32 + 9) LPM_O(32 + 10) LPM_O(32 + 11) LPM_O(32 + 24) LPM_O(32 + 25) LPM_O(32 + 26) LPM_O(32 + 27)
+#undef LPM_O
+            default: break;
+        }
+#endif
+        return launch_sym<SK, 8, 128, 8, 1, 43, true>(st, prm, g, src, acc);
     }
     static void finalize(cudaStream_t st, const MaskPlan& mp, const double* src, const double* acc, const Outs<3>& out)
     {
