@@ -271,6 +271,26 @@ int lpm_betaplane_solver_get_state(lpm_betaplane_solver* s, double* x, double* y
                                    double* u, double* v, double* relstream, double* absstream);
 int lpm_betaplane_solver_delete(lpm_betaplane_solver* s);
 
+/* type SWESolver (planar shallow water) + New/Timestep/Delete, src/SWEPlaneSolver.f90:47-110, 137-205, 298-429:
+ * RK4 on x, y, relVort, divergence, area and depth, with one fused right-hand-side sum per stage
+ * (SWEPlaneRHSIntegrals, :457-565).  f0, beta, g, pse_eps: plane%f0, plane%beta, plane%g, plane%pseEps.
+ * topo(x, y, topo_user) is the bottom topography (the reference's topoFn argument; NULL = flat bottom): it is called
+ * on the host for every particle at every stage, as the reference calls topoFn inside its loops.  New() evaluates
+ * the right-hand side at the initial state (:202-204), so u, v, doubleDot, lapSurf are defined before the first step.
+ * The step reproduces the reference AS WRITTEN, including the whole-array assignment of the stage-1 vorticity and
+ * divergence tendencies (:312-315; every particle gets the last particle's value). */
+typedef struct lpm_swe_plane_solver lpm_swe_plane_solver;
+typedef double (*lpm_topography_fn)(double x, double y, void* user);
+int lpm_swe_plane_solver_new(int64_t n, const double* x, const double* y, const double* relvort, const double* div,
+                             const double* h, const double* area, const int32_t* mask, double f0, double beta,
+                             double g, double pse_eps, lpm_topography_fn topo, void* topo_user,
+                             lpm_swe_plane_solver** out);
+int lpm_swe_plane_solver_timestep(lpm_swe_plane_solver* s, double dt);
+/* copies back the particles, the prognostic fields and the last right-hand side (any pointer may be NULL) */
+int lpm_swe_plane_solver_get_state(lpm_swe_plane_solver* s, double* x, double* y, double* relvort, double* div,
+                                   double* h, double* area, double* u, double* v, double* double_dot, double* lap_surf);
+int lpm_swe_plane_solver_delete(lpm_swe_plane_solver* s);
+
 /* -------------------------------------------------------- measurement */
 
 /* Dependent-free DFMA probe: runs `iters` rounds of independent FMA chains on

@@ -96,6 +96,10 @@ PROTOTYPES = {
     "lpm_betaplane_solver_timestep": (_int, [_vp, _dbl, _int]),
     "lpm_betaplane_solver_get_state": (_int, [_vp, _d, _d, _d, _d, _d, _d, _d]),
     "lpm_betaplane_solver_delete": (_int, [_vp]),
+    "lpm_swe_plane_solver_new": (_int, [_n, _d, _d, _d, _d, _d, _d, _i32, _dbl, _dbl, _dbl, _dbl, _vp, _vp, C.POINTER(_vp)]),
+    "lpm_swe_plane_solver_timestep": (_int, [_vp, _dbl]),
+    "lpm_swe_plane_solver_get_state": (_int, [_vp, _d, _d, _d, _d, _d, _d, _d, _d, _d, _d]),
+    "lpm_swe_plane_solver_delete": (_int, [_vp]),
     # measurement
     "lpm_fp64_peak_probe": (_int, [_int, _d, _d]),
     "lpm_last_kernel_ms": (_int, [_d]),
@@ -117,6 +121,8 @@ for _name, (_res, _args) in PROTOTYPES.items():
     _f.restype = _res
     _f.argtypes = _args
 
+
+TOPOGRAPHY_FN = C.CFUNCTYPE(C.c_double, C.c_double, C.c_double, C.c_void_p)      # lpm_topography_fn
 
 # not part of the C ABI (csrc/lpm_gpu_tuning.h): A/B and test knob
 lib.lpm_tune.restype = _int

@@ -462,4 +462,110 @@ struct BetaSolverDev : SolverBase {
     }
 };
 
+// ---------------------------------------------------------------- planar shallow water
+// type SWESolver + Timestep, src/SWEPlaneSolver.f90:47-110, 298-429.  Six prognostic arrays per particle
+// (x, y, relVort, div, area, h), one fused right-hand-side sum per stage (SWEPlaneRHSIntegrals :457-565 ->
+// OpSweRhsPlane: velocity, double dot product, PSE Laplacian of the surface), classical RK4.
+//
+// Stage tendencies with round-to-nearest intrinsics in the reference's operation order (:337-346):
+//   relVort' = dt * ( -(zeta + f0 + beta y) * delta - beta * v )
+//   div'     = dt * ( -doubleDot + (f0 + beta y) * zeta - g * lapSurf )
+//   h'       = dt * ( -h * delta ),   area' = dt * ( area * delta ),   x' = dt u,  y' = dt v
+__global__ void swe_stage(int64_t n, double dt, double f0, double beta, double g, const double* __restrict__ y,
+                          const double* __restrict__ rv, const double* __restrict__ dv, const double* __restrict__ area,
+                          const double* __restrict__ h, const double* __restrict__ u, const double* __restrict__ v,
+                          const double* __restrict__ dd, const double* __restrict__ lap, double* __restrict__ xs,
+                          double* __restrict__ ys, double* __restrict__ rvs, double* __restrict__ dvs,
+                          double* __restrict__ as, double* __restrict__ hs, int whole_array_stage1)
+{
+    LPM_GRID_STRIDE(i, n)
+    {
+        xs[i] = __dmul_rn(dt, u[i]);
+        ys[i] = __dmul_rn(dt, v[i]);
+        hs[i] = __dmul_rn(dt, __dmul_rn(-h[i], dv[i]));
+        as[i] = __dmul_rn(dt, __dmul_rn(area[i], dv[i]));
+        // Stage 1 of the reference assigns these two to the WHOLE arrays inside its particle loop (:312-315, no
+        // `(i)`), so every entry ends up with the LAST particle's value: k = n - 1 reproduces that.
+        const int64_t k = whole_array_stage1 ? n - 1 : i;
+        const double fy = __dadd_rn(f0, __dmul_rn(beta, y[k]));
+        const double s = __dadd_rn(__dadd_rn(rv[k], f0), __dmul_rn(beta, y[k]));
+        rvs[i] = __dmul_rn(dt, __dsub_rn(__dmul_rn(-s, dv[k]), __dmul_rn(beta, v[k])));
+        dvs[i] = __dmul_rn(dt, __dsub_rn(__dadd_rn(-dd[k], __dmul_rn(fy, rv[k])), __dmul_rn(g, lap[k])));
+    }
+}
+// surface height = h + topography (topo == nullptr: flat bottom, h + 0)
+__global__ void swe_surface(int64_t n, const double* __restrict__ h, const double* __restrict__ topo, double* __restrict__ surf)
+{
+    LPM_GRID_STRIDE(i, n) surf[i] = __dadd_rn(h[i], topo ? topo[i] : 0.0);
+}
+
+typedef double (*TopoFn)(double x, double y, void* user);
+
+struct SwePlaneSolverDev : SolverBase {
+    // start state, right-hand side, stage inputs, then the four stages of the six prognostic arrays
+    enum { X, Y, RV, DIV, AREA, H, U, V, DD, LAP, SURF, TOPO, XIN, YIN, RVIN, DIVIN, AREAIN, HIN, S1, NARR = S1 + 24 };
+    double f0 = 0.0, beta = 0.0, g = 0.0, eps = 0.0;
+    TopoFn topo = nullptr;
+    void* topo_user = nullptr;
+    std::vector<double> hx, hy, ht;
+
+    // SWEPlaneRHSIntegrals at the state held in arrays (xi ... hi) -> U, V, DD, LAP
+    int rhs(int xi, int yi, int rvi, int divi, int areai, int hi)
+    {
+        if (topo) {
+            // the reference calls topoFn(x, y) inside its pair loop (:483, :490); here once per particle and stage,
+            // on the host (a user-supplied Fortran / C function): two O(N) downloads and one upload per evaluation
+            hx.resize((size_t)n); hy.resize((size_t)n); ht.resize((size_t)n);
+            LPM_TRY(download(xi, hx.data()));
+            LPM_TRY(download(yi, hy.data()));
+            LPM_TRY(sync());
+            for (int64_t i = 0; i < n; ++i) ht[(size_t)i] = topo(hx[(size_t)i], hy[(size_t)i], topo_user);
+            LPM_TRY(upload(TOPO, ht.data()));
+            LPM_TRY(sync());        // ht is reused by the next evaluation
+        }
+        LPM_TRY(each([&](Replica& r, unsigned gr, cudaStream_t s) {
+            swe_surface<<<gr, 256, 0, s>>>(n, r.A(hi), topo ? r.A(TOPO) : nullptr, r.A(SURF));
+            return 1;
+        }));
+        const int in[6] = {xi, yi, rvi, divi, SURF, areai};
+        const int out[4] = {U, V, DD, LAP};
+        const double sc[3] = {eps, 0, 0};
+        return eval<OpSweRhsPlane>(in, out, sc);
+    }
+
+    int stage(int s, double dt, int yi, int rvi, int divi, int areai, int hi, bool whole_array)
+    {
+        const int b = S1 + 6 * s;
+        return each([&](Replica& r, unsigned gr, cudaStream_t st) {
+            swe_stage<<<gr, 256, 0, st>>>(n, dt, f0, beta, g, r.A(yi), r.A(rvi), r.A(divi), r.A(areai), r.A(hi), r.A(U), r.A(V),
+                                         r.A(DD), r.A(LAP), r.A(b + 0), r.A(b + 1), r.A(b + 2), r.A(b + 3), r.A(b + 4), r.A(b + 5),
+                                         whole_array ? 1 : 0);
+            return 1;
+        });
+    }
+
+    // src/SWEPlaneSolver.f90:298-429
+    int timestep(double dt)
+    {
+        LPM_TRY(stage(0, dt, Y, RV, DIV, AREA, H, true));                     // :309-320
+        for (int s = 1; s < 4; ++s) {
+            const double c = s < 3 ? 0.5 : 1.0;
+            const int prev = S1 + 6 * (s - 1);
+            LPM_TRY(each([&](Replica& r, unsigned gr, cudaStream_t st) {       // :325-332, :350-357, :375-382
+                for (int k = 0; k < 6; ++k) rk_input<<<gr, 256, 0, st>>>(n, c, r.A(X + k), r.A(prev + k), r.A(XIN + k));
+                return 6;
+            }));
+            LPM_TRY(rhs(XIN, YIN, RVIN, DIVIN, AREAIN, HIN));
+            LPM_TRY(stage(s, dt, YIN, RVIN, DIVIN, AREAIN, HIN, false));       // :337-346
+        }
+        LPM_TRY(each([&](Replica& r, unsigned gr, cudaStream_t st) {           // :400-413
+            for (int k = 0; k < 6; ++k)
+                rk_update<<<gr, 256, 0, st>>>(n, r.A(X + k), r.A(S1 + k), r.A(S1 + 6 + k), r.A(S1 + 12 + k), r.A(S1 + 18 + k));
+            return 6;
+        }));
+        LPM_TRY(rhs(X, Y, RV, DIV, AREA, H));                                  // :416-417
+        return sync();
+    }
+};
+
 }  // namespace lpm

@@ -258,3 +258,59 @@ def SWEPlaneRHSIntegrals(mesh, vort, div, h, topo_fn, pse_eps):
     bottom topography function the reference passes as a procedure argument."""
     surf = np.asarray(h, dtype=np.float64) + topo_fn(mesh.x, mesh.y)
     return api.swe_plane_rhs_integrals(mesh.x, mesh.y, vort, div, surf, mesh.area, mesh.is_active, pse_eps)
+
+
+class SWEMeshPlane:
+    """The fields of type SWEMesh (src/PlanarSWE.f90) that the planar shallow-water solver reads and writes."""
+
+    def __init__(self, mesh, relVort, divergence, h, f0=0.0, beta=0.0, g=1.0, pseEps=None):
+        self.mesh = mesh
+        self.x, self.y = mesh.x.copy(), mesh.y.copy()
+        self.area = np.array(mesh.area, dtype=np.float64)          # the SWE solver advances the areas too
+        self.is_active = mesh.is_active
+        self.relVort = np.array(relVort, dtype=np.float64)
+        self.divergence = np.array(divergence, dtype=np.float64)
+        self.h = np.array(h, dtype=np.float64)
+        self.f0, self.beta, self.g = float(f0), float(beta), float(g)
+        self.pseEps = float(pseEps if pseEps is not None else mesh.max_edge_length ** 0.75)
+        self.velocity = [np.zeros(mesh.n), np.zeros(mesh.n)]
+        self.doubleDot = np.zeros(mesh.n)
+        self.lapSurf = np.zeros(mesh.n)
+
+
+class SWEPlaneSolver:
+    """type SWESolver: New / Timestep / Delete (src/SWEPlaneSolver.f90:137-205, 298-429).  `topoFn(x, y) -> float`
+    is the bottom topography, as in the reference's interfaces (None = flat bottom)."""
+
+    def __init__(self, plane: SWEMeshPlane, topoFn=None):        # New(solver, plane, topoFn)
+        from ._lib import TOPOGRAPHY_FN
+        self._h = C.c_void_p()
+        self.n = plane.mesh.n
+        self._cb = TOPOGRAPHY_FN(lambda x, y, user: float(topoFn(x, y))) if topoFn is not None else None
+        m = np.ascontiguousarray((np.asarray(plane.is_active) != 0).astype(np.int32))
+        arrs = [np.ascontiguousarray(a, dtype=np.float64) for a in
+                (plane.x, plane.y, plane.relVort, plane.divergence, plane.h, plane.area)]
+        cb = C.cast(self._cb, C.c_void_p) if self._cb is not None else None
+        check(lib.lpm_swe_plane_solver_new(self.n, *[_pd(a) for a in arrs], m.ctypes.data_as(_i32), plane.f0, plane.beta,
+                                           plane.g, plane.pseEps, cb, None, C.byref(self._h)))
+        self.CopyToMesh(plane)
+
+    def Timestep(self, plane: SWEMeshPlane, dt):                  # Timestep(solver, plane, dt, topoFn), :298-429
+        check(lib.lpm_swe_plane_solver_timestep(self._h, float(dt)))
+        self.CopyToMesh(plane)
+
+    def CopyToMesh(self, plane: SWEMeshPlane):                    # :419-426
+        check(lib.lpm_swe_plane_solver_get_state(self._h, _pd(plane.x), _pd(plane.y), _pd(plane.relVort), _pd(plane.divergence),
+                                                 _pd(plane.h), _pd(plane.area), _pd(plane.velocity[0]), _pd(plane.velocity[1]),
+                                                 _pd(plane.doubleDot), _pd(plane.lapSurf)))
+
+    def Delete(self):
+        if self._h:
+            check(lib.lpm_swe_plane_solver_delete(self._h))
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.Delete()
+        except Exception:
+            pass

@@ -372,6 +372,22 @@ def swe_plane_rhs(x, y, vort, div, surf, area, mask, pse_eps):
     return o
 
 
+ORACLE_TOPO_FN = C.CFUNCTYPE(C.c_double, C.c_double, C.c_double)
+
+
+def swe_plane_rk4_step(x, y, relvort, div, h, area, u, v, double_dot, lap_surf, mask, f0, beta, g, pse_eps, dt, topo=None):
+    """src/SWEPlaneSolver.f90:298-429 as written.  Returns the new (x, y, relvort, div, h, area, u, v, double_dot,
+    lap_surf); `topo` is a Python callable topo(x, y) -> float or None (flat bottom)."""
+    arrs = [np.array(a, dtype=np.float64, copy=True) for a in (x, y, relvort, div, h, area, u, v, double_dot, lap_surf)]
+    m = _m(mask)
+    lib = get()
+    lib.oracle_swe_plane_rk4_step.argtypes = [_n] + [_d] * 10 + [_i32] + [_dbl] * 5 + [ORACLE_TOPO_FN]
+    lib.oracle_swe_plane_rk4_step.restype = None
+    cb = ORACLE_TOPO_FN(topo) if topo is not None else C.cast(None, ORACLE_TOPO_FN)
+    lib.oracle_swe_plane_rk4_step(arrs[0].size, *[_p(a) for a in arrs], m.ctypes.data_as(_i32), f0, beta, g, pse_eps, dt, cb)
+    return arrs
+
+
 def swe_plane_velocity(x, y, vort, div, area, mask):
     x, y, vort, div, area = map(_f, (x, y, vort, div, area))
     m = _m(mask)

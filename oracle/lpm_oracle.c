@@ -900,6 +900,65 @@ void oracle_swe_plane_rhs(int64_t n, const double *x, const double *y, const dou
     }
 }
 
+/* src/SWEPlaneSolver.f90:298-429  timestepPrivate (planar shallow-water RK4), AS WRITTEN.  State arrays
+ * x, y, relVort, div, h, area are updated in place; u, v, doubleDot, lapSurf enter as the right-hand-side
+ * integrals at the old state (what New() leaves, :202-204) and leave as those at the new state (:416-417).
+ * topo(x, y) is the bottom topography (NULL = flat: topoFn == 0); the reference evaluates it inside the pair
+ * loop, here once per particle and stage (same values).
+ * Latent reference bug preserved: in stage 1 the relative-vorticity and divergence tendencies are assigned to the
+ * WHOLE arrays inside the particle loop (`self%relVortStage1 = dt * (...)`, `self%divStage1 = dt * (...)`,
+ * :312-315, no `(i)`), so after the loop every entry holds the value computed for the LAST particle.        */
+typedef double (*oracle_topo_fn)(double x, double y);
+static void swe_surface(int64_t n, const double *x, const double *y, const double *h, oracle_topo_fn topo, double *surf)
+{
+    for (int64_t i = 0; i < n; ++i) surf[i] = h[i] + (topo ? topo(x[i], y[i]) : 0.0);
+}
+void oracle_swe_plane_rk4_step(int64_t n, double *x, double *y, double *relVort, double *div, double *h, double *area,
+                               double *u, double *v, double *doubleDot, double *lapSurf, const int32_t *mask,
+                               double f0, double beta, double g, double pseEps, double dt, oracle_topo_fn topo)
+{
+    double *buf = (double *)malloc((size_t)n * sizeof(double) * 31);
+    double *in[6], *st[4][6], *surf = buf + 30 * n;          /* order: x, y, relVort, div, area, h */
+    double *start[6] = { x, y, relVort, div, area, h };
+    for (int k = 0; k < 6; ++k) in[k] = buf + k * n;
+    for (int s = 0; s < 4; ++s)
+        for (int k = 0; k < 6; ++k) st[s][k] = buf + (6 + 6 * s + k) * n;
+    /* stage 1 (:309-320) */
+    for (int64_t i = 0; i < n; ++i) {
+        st[0][0][i] = dt * u[i];
+        st[0][1][i] = dt * v[i];
+        st[0][5][i] = dt * (-h[i] * div[i]);
+        st[0][4][i] = dt * (area[i] * div[i]);
+    }
+    {   /* the whole-array assignments: the last particle's value everywhere */
+        const int64_t i = n - 1;
+        const double rvs = dt * (-(relVort[i] + f0 + beta * y[i]) * div[i] - beta * v[i]);
+        const double dvs = dt * (-doubleDot[i] + (f0 + beta * y[i]) * relVort[i] - g * lapSurf[i]);
+        for (int64_t k = 0; k < n; ++k) { st[0][2][k] = rvs; st[0][3][k] = dvs; }
+    }
+    for (int s = 1; s < 4; ++s) {
+        const double c = s < 3 ? 0.5 : 1.0;                 /* :325-332, :350-357, :375-382 (stage 4 adds the whole stage) */
+        for (int k = 0; k < 6; ++k)
+            for (int64_t i = 0; i < n; ++i) in[k][i] = (s < 3) ? start[k][i] + c * st[s - 1][k][i] : start[k][i] + st[s - 1][k][i];
+        swe_surface(n, in[0], in[1], in[5], topo, surf);
+        oracle_swe_plane_rhs(n, in[0], in[1], in[2], in[3], surf, in[4], mask, pseEps, 0, n, u, v, doubleDot, lapSurf);
+        for (int64_t i = 0; i < n; ++i) {                   /* :337-346 */
+            st[s][0][i] = dt * u[i];
+            st[s][1][i] = dt * v[i];
+            st[s][2][i] = dt * (-(in[2][i] + f0 + beta * in[1][i]) * in[3][i] - beta * v[i]);
+            st[s][3][i] = dt * (-doubleDot[i] + (f0 + beta * in[1][i]) * in[2][i] - g * lapSurf[i]);
+            st[s][5][i] = dt * (-in[5][i] * in[3][i]);
+            st[s][4][i] = dt * (in[4][i] * in[3][i]);
+        }
+    }
+    for (int k = 0; k < 6; ++k)                             /* :400-413 */
+        for (int64_t i = 0; i < n; ++i)
+            start[k][i] = start[k][i] + st[0][k][i] / 6.0 + st[1][k][i] / 3.0 + st[2][k][i] / 3.0 + st[3][k][i] / 6.0;
+    swe_surface(n, x, y, h, topo, surf);
+    oracle_swe_plane_rhs(n, x, y, relVort, div, surf, area, mask, pseEps, 0, n, u, v, doubleDot, lapSurf);   /* :416-417 */
+    free(buf);
+}
+
 /* src/PlanarSWE.f90:469-494  SetVelocityFromFieldData (private body; SWEComputeVelocity :261-290
  * is the same sum): planar velocity from relative vorticity and divergence,
  *   u_i = sum_{j /= i, active} [ -(y_i - y_j) rot + (x_i - x_j) pot ],  v_i = sum [ (x_i - x_j) rot + (y_i - y_j) pot ],

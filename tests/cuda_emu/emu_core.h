@@ -126,6 +126,7 @@ inline double rsqrt(double v) { return 1.0 / std::sqrt(v); }
 inline void sincospi(double v, double* s, double* c) { *s = std::sin(M_PI * v); *c = std::cos(M_PI * v); }
 inline double __dadd_rn(double a, double b) { return a + b; }
 inline double __dmul_rn(double a, double b) { return a * b; }
+inline double __dsub_rn(double a, double b) { return a - b; }
 inline double __ddiv_rn(double a, double b) { return a / b; }
 inline double __hiloint2double(int hi, int lo)
 {

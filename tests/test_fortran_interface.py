@@ -41,7 +41,7 @@ def test_every_entry_point_is_bound_with_matching_arguments():
             assert len(decl) == 1, (fn, p["name"])
             by_value = ", value" in decl[0]
             is_scalar_c = p["stars"] == 0 and p["dim"] is None
-            assert by_value == (is_scalar_c or "type(c_ptr), value" in decl[0]), (fn, p["name"], decl[0])
+            assert by_value == (is_scalar_c or "type(c_ptr), value" in decl[0] or "type(c_funptr), value" in decl[0]), (fn, p["name"], decl[0])
 
 
 def test_wrapper_module_includes_the_interface_and_binds_solvers():

@@ -113,3 +113,37 @@ def test_swe_sphere_rhs_integrals(gpu, oracle, get_mesh, L, power, R):
     assert max(relerr(u0, bu / R), relerr(v0, bv / R), relerr(w0, bw / R)) <= 1e-13
     pl = gpu.pse_laplacian_sphere(x, y, z, surf, area, m.is_active, eps, R)
     assert relerr(got[4], pl * eps * eps) <= 1e-13
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("with_topo", [False, True])
+def test_swe_plane_rk4_steps(gpu, oracle, get_mesh, with_topo):
+    """type SWESolver New / Timestep (src/SWEPlaneSolver.f90:137-205, 298-429): three RK4 steps of the planar
+    shallow-water equations on quadRect 3 against the as-written restatement (including the whole-array assignment of
+    the stage-1 vorticity / divergence tendencies, :312-315), with a flat bottom and with a user topography function
+    called on the host at every stage."""
+    from lpm_v2_b200 import solvers
+    q = get_mesh(M.QUAD_RECT_SEED, 3, 3.0)
+    x, y = q.x, q.y
+    rv = np.exp(-2.0 * (x ** 2 + y ** 2))
+    dv = 0.1 * rv * x
+    h = 1.0 + 0.1 * rv
+    f0, beta, g, dt = 1.0, 0.5, 9.80616, 0.01
+    eps = q.max_edge_length ** 0.75
+    topo = (lambda a, b: 0.05 * float(np.exp(-(a * a + b * b)))) if with_topo else None
+    plane = solvers.SWEMeshPlane(q, rv, dv, h, f0=f0, beta=beta, g=g, pseEps=eps)
+    sol = solvers.SWEPlaneSolver(plane, topo)
+    surf = h + (np.array([topo(a, b) for a, b in zip(x, y)]) if with_topo else 0.0)
+    ref = [x.copy(), y.copy(), rv.copy(), dv.copy(), h.copy(), q.area.copy()] + list(
+        oracle.swe_plane_rhs(x, y, rv, dv, surf, q.area, q.is_active, eps))
+    names = "x y relVort div h area u v doubleDot lapSurf".split()
+    got = [plane.x, plane.y, plane.relVort, plane.divergence, plane.h, plane.area] + plane.velocity + [plane.doubleDot, plane.lapSurf]
+    for nm, a, b in zip(names, got, ref):                     # New(): the right-hand side at the initial state
+        assert relerr(a, b) <= TOL, ("new", nm)
+    for step in range(3):
+        sol.Timestep(plane, dt)
+        ref = oracle.swe_plane_rk4_step(*ref, q.is_active, f0, beta, g, eps, dt, topo)
+        got = [plane.x, plane.y, plane.relVort, plane.divergence, plane.h, plane.area] + plane.velocity + [plane.doubleDot, plane.lapSurf]
+        for nm, a, b in zip(names, got, ref):
+            assert relerr(a, b) <= TOL, (step, nm, relerr(a, b))
+    sol.Delete()
