@@ -167,6 +167,7 @@ struct Runtime {
     int sym_vel_order = 43;              // LPM_SYM_ORDER_SWEEP builds only
     int force_T = 0;                     // A/B: targets per thread of the one-sided engine (0 = automatic)
     int32_t sym_min_sources = 200000;
+    int32_t sym_panel_blocks = 256;      // ... launched in panels of this many target blocks (kSymPanelBlocks)
     int32_t sym_chunk_tiles = 16;        // ... in chunks of this many source tiles per CTA (symmetric.cuh, kSymChunkTiles)    // ... for at least this many active particles (symmetric.cuh)
     bool pse_series = true;              // sphere PSE kernels: theta^2 by series inside the cut-off (false: atan2 always)
     int pse_culling = 1;                 // PSE kernels: 0 reference order, every tile; 1 cell order + tile culling; 2 cell order only

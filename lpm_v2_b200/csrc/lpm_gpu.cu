@@ -216,6 +216,9 @@ extern "C" int lpm_tune(const char* key, int value)
         rt().sym_vel_order = value;
     } else if (k == "force_T") {
         rt().force_T = value;
+    } else if (k == "sym_panel_blocks") {
+        if (value < 1) return set_error(LPM_ERR_INVALID, "lpm_tune(sym_panel_blocks, %d)", value);
+        rt().sym_panel_blocks = value;
     } else if (k == "sym_chunk_tiles") {
         if (value < 1) return set_error(LPM_ERR_INVALID, "lpm_tune(sym_chunk_tiles, %d)", value);
         rt().sym_chunk_tiles = value;

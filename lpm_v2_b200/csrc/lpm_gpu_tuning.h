@@ -4,6 +4,7 @@
  *   "max_chunks"        upper bound on source chunks per evaluation (every rank the same value)
  *   "chunk_min"         smallest source chunk (a multiple of 256; every rank the same value)
  *   "force_T"           targets per thread of the one-sided engine: 1, 2, 4, 8 (0 = automatic)
+ *   "sym_panel_blocks"  target blocks per panel of the triangle kernel's launch order (default 256)
  *   "sym_chunk_tiles"   source tiles per CTA of the symmetric triangle kernel (default 16; every rank the same value)
  *   "sym_min_sources"   smallest active-particle count that takes the pair-symmetric path (default 200000)
  *   "sym_vel_order"     statement order of the symmetric velocity kernel, in builds with -DLPM_SYM_ORDER_SWEEP only

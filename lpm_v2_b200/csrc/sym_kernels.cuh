@@ -13,6 +13,7 @@ struct SymGeom {
     int32_t nblocks;        // target blocks of BLOCK*T compact indices
     int32_t chunk_tiles;    // source tiles per chunk
     int32_t nchunks;
+    int32_t panel_blocks;   // target blocks per panel of the launch order (see sym_kernel)
     int32_t world, rank;    // target blocks are dealt round-robin to ranks (sums joined by the caller)
     int32_t half_bin;       // as DsGeom::half_bin (log kernels)
 };
@@ -399,8 +400,17 @@ sym_kernel(const SymParams prm, const SymGeom g, const double* __restrict__ src,
     double* cT = reinterpret_cast<double*>(full + 2);        // COMBINE only
 
     const int tid = threadIdx.x, lane = tid & 31;
-    const int I = blockIdx.x % g.nblocks;           // chunk is the slow index, as in ds_kernel
-    const int ck = blockIdx.x / g.nblocks;
+    // Launch order: panels of `panel_blocks` target blocks; inside a panel the chunk is the slow index, so the CTAs
+    // in flight read the same few source tiles (and hit the same few accumulators) while the panel's target
+    // records stay in L2.  With one panel over all blocks (round 2's first version) every chunk re-read all target
+    // records -- 63 MB at icosTri 8, which the L2 does not hold beside 220 MB of accumulators: ncu showed 58 GB of
+    // DRAM traffic per launch (harmless at 75 GB/s, but 370 x the algorithmic bytes).  A panel of 256 blocks keeps
+    // 12.5 MB of targets hot and passes over the sources and accumulators once per panel.
+    const int per_panel = g.panel_blocks * g.nchunks;
+    const int pnl = blockIdx.x / per_panel, rem = blockIdx.x % per_panel;
+    const int ck = rem / g.panel_blocks;
+    const int I = pnl * g.panel_blocks + rem % g.panel_blocks;
+    if (I >= g.nblocks) return;
     // Blocks are dealt to ranks in serpentine order (0 .. w-1, w-1 .. 0, ...): a block's work falls linearly with
     // its index (the triangle), so plain round-robin would give rank 0 the longest block of every round.
     if (g.world > 1) {

@@ -39,6 +39,7 @@ namespace lpm {
 // engine (whose targets-per-thread adapts) is faster: icosTri 7 (327 680) gains 5 %, icosTri 6 (81 920) loses.
 constexpr int32_t kSymMinSources = 200000;
 constexpr int32_t kSymChunkTiles = 16;      // source tiles (of 256) per CTA of the triangle kernel
+constexpr int32_t kSymPanelBlocks = 256;    // target blocks per panel of its launch order (sym_kernel)
 
 template <class K, int T, int BLOCK, int SB, int MINB, int ORDER = 0, bool COMBINE = false>
 inline int launch_sym(cudaStream_t st, const SymParams& prm, SymGeom g, const double* src, double* acc)
@@ -46,8 +47,10 @@ inline int launch_sym(cudaStream_t st, const SymParams& prm, SymGeom g, const do
     constexpr int TB = BLOCK * T;
     g.nblocks = (g.nsrc_pad + TB - 1) / TB;
     g.half_bin = 1 << (19 - kLogBits);
+    g.panel_blocks = std::min<int32_t>(g.nblocks, rt().sym_panel_blocks);
+    const int64_t npanels = (g.nblocks + g.panel_blocks - 1) / g.panel_blocks;
     constexpr size_t smem = sym_smem_bytes<K, T, BLOCK, COMBINE>();
-    const int64_t grid = (int64_t)g.nblocks * g.nchunks;
+    const int64_t grid = npanels * g.panel_blocks * g.nchunks;
     if (grid <= 0 || grid > 0x7fffffffLL) return set_error(LPM_ERR_INVALID, "symmetric kernel grid %lld", (long long)grid);
     if (smem > 48 * 1024) {     // per device, as in launch_ds
         static bool configured[64] = {};

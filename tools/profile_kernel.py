@@ -7,6 +7,9 @@ name = sys.argv[1]
 L = int(sys.argv[2]) if len(sys.argv) > 2 else 6
 api.init(1)
 api.set_profiling(True)
+for kv in filter(None, os.environ.get("LPM_TUNE", "").split(",")):      # e.g. LPM_TUNE=sym_panel_blocks=4096
+    k, v = kv.split("=")
+    api.tune(k, int(v))
 if name in ("bve_stream", "bve_velocity", "pse_sphere"):
     m = mesh.PolyMesh2d(mesh.ICOS_TRI_SPHERE_SEED, L)
     z = problems.rossby_haurwitz54(m)
