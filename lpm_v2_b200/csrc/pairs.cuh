@@ -883,10 +883,38 @@ tile_bounds_kernel(int32_t nsrc, const double* __restrict__ src, double* __restr
     }
 }
 
+// exp(-t) for the PSE kernels, 0 <= t <= 708 (they call it for t = k^2 <= kPseCut^2 = 64).  The library exp() is ~28
+// FP64-pipe instructions with its range checks; here m = rint(64 t / ln 2) comes from a magic-number add,
+// r = t - m ln2/64 (two steps: m < 2^16 times a 37-bit constant is exact), exp(-r) for |r| <= ln2/128 is a degree-5
+// polynomial (truncation r^6/720 < 4e-17), 2^(-(m mod 64)/64) comes from a 64-entry table filled at init
+// (g_exp2_tab, read through the read-only path), and 2^(-(m div 64)) is subtracted from the exponent field:
+// 10 FP64 instructions + a load + 5 integer instructions, <= 2.5 ulp (tests/test_kernel_math.py).
+__device__ double g_exp2_tab[64];
+__device__ __forceinline__ double pse_exp_neg(double t)
+{
+    constexpr double kMagic = 6755399441055744.0;                      // 1.5 * 2^52
+    const double u = fma(t, 92.33248261689366 /* 64 / ln 2 */, kMagic);
+    const int m = __double2loint(u);
+    const double mf = u - kMagic;
+    double r = fma(mf, -0x1.62e42fefa0000p-7, t);                      // ln2/64, high 37 bits
+    r = fma(mf, -0x1.cf79abc9e3b3ap-46, r);                            // ... and the rest
+    double p = fma(r, -1.0 / 120.0, 1.0 / 24.0);
+    p = fma(r, p, -1.0 / 6.0);
+    p = fma(r, p, 0.5);
+    p = fma(r, p, -1.0);
+    p = fma(r, p, 1.0);
+#ifdef LPM_CUDA_EMU
+    const double v = g_exp2_tab[m & 63] * p;
+#else
+    const double v = __ldg(&g_exp2_tab[m & 63]) * p;
+#endif
+    return __hiloint2double(__double2hiint(v) - ((m >> 6) << 20), __double2loint(v));
+}
+
 __device__ __forceinline__ double pse_eta_pi(double k2)    // pi * eta
 {
     double poly = fma(fma(fma(-2.0 / 3.0, k2, 10.0), k2, -40.0), k2, 40.0);
-    return poly * exp(-k2);
+    return poly * pse_exp_neg(k2);
 }
 
 // (d_ij / eps)^2 on the sphere.  The reference evaluates d_ij = R atan2(|x_i cross x_j|, x_i . x_j)

@@ -15,11 +15,11 @@ namespace lpm {
 // pi * bivariateDeltaKernel8 (PSEDirectSum.f90:611-616) and pi * bivariateFirstDerivativeKernel8 (:629-634)
 __device__ __forceinline__ double pse_delta_pi(double k2)
 {
-    return fma(fma(fma(-1.0 / 6.0, k2, 2.0), k2, -6.0), k2, 4.0) * exp(-k2);
+    return fma(fma(fma(-1.0 / 6.0, k2, 2.0), k2, -6.0), k2, 4.0) * pse_exp_neg(k2);
 }
 __device__ __forceinline__ double pse_dphi_pi(double k2)
 {
-    return fma(fma(fma(1.0 / 3.0, k2, -5.0), k2, 20.0), k2, -20.0) * exp(-k2);
+    return fma(fma(fma(1.0 / 3.0, k2, -5.0), k2, 20.0), k2, -20.0) * pse_exp_neg(k2);
 }
 
 // ---------------------------------------------------------------- interpolation

@@ -47,6 +47,11 @@ inline int init_device(Device& d, int id)
         LPM_CUDA(cudaGetSymbolAddress(&sym, g_log_full));
         d.logtab = (const double*)sym;
     }
+    {   // table for pse_exp_neg(): 2^(-j/64), correctly rounded from long double
+        double tab[64];
+        for (int j = 0; j < 64; ++j) tab[j] = (double)exp2l(-(long double)j / 64.0L);
+        LPM_CUDA(cudaMemcpyToSymbol(g_exp2_tab, tab, sizeof(tab)));
+    }
     LPM_CUDA(cudaStreamCreateWithFlags(&d.stream, cudaStreamNonBlocking));
     LPM_CUDA(cudaEventCreateWithFlags(&d.ev_done, cudaEventDisableTiming));
     return LPM_OK;

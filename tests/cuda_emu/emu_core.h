@@ -141,6 +141,12 @@ inline int __double2hiint(double d)
     std::memcpy(&b, &d, 8);
     return (int)(b >> 32);
 }
+inline int __double2loint(double d)
+{
+    uint64_t b;
+    std::memcpy(&b, &d, 8);
+    return (int)(uint32_t)b;
+}
 inline long long __double_as_longlong(double d)
 {
     long long b;

@@ -123,3 +123,32 @@ def test_sphere_distance_series(theta_cut):
     series = float(np.max(np.abs(th2[ok] - ref[ok]) / ref[ok]))
     atan2_form = float(np.max(np.abs(np.arctan2(np.sqrt(s2), dot)[ok] ** 2 - ref[ok]) / ref[ok]))
     assert series <= 2e-15 and series <= 3.0 * atan2_form + 1e-16
+
+
+def test_pse_exp_neg_accuracy():
+    """csrc/pairs.cuh pse_exp_neg: exp(-t) from m = rint(64 t / ln 2), a two-step reduction, a degree-5 polynomial
+    and a 64-entry table of 2^(-j/64): <= 2.5 ulp on [0, 700] (the PSE kernels use k^2 <= 64)."""
+    rng = np.random.default_rng(11)
+    tab = np.exp2(-(np.arange(64, dtype=np.longdouble)) / 64).astype(np.float64)
+    magic = 6755399441055744.0
+    hi, lo = float.fromhex("0x1.62e42fefa0000p-7"), float.fromhex("0x1.cf79abc9e3b3ap-46")
+    for a, b in ((0.0, 1e-3), (0.0, 1.0), (1.0, 8.0), (8.0, 64.0), (64.0, 700.0)):
+        t = np.concatenate([rng.uniform(a, b, 200000), [a, b]])
+        u = _fma(t, 92.33248261689366, magic)
+        m = (u.view(np.uint64) & np.uint64(0xffffffff)).astype(np.int64)
+        mf = u - magic
+        assert np.array_equal(mf, np.rint(mf)) and np.array_equal(m, mf.astype(np.int64))
+        r = _fma(mf, -hi, t)
+        r = _fma(mf, -lo, r)
+        assert np.abs(r).max() <= np.log(2.0) / 128 * (1 + 1e-3)      # (the long-double emulation of the fma double-rounds ties)
+        p = _fma(r, -1.0 / 120.0, 1.0 / 24.0)
+        p = _fma(r, p, -1.0 / 6.0)
+        p = _fma(r, p, 0.5)
+        p = _fma(r, p, -1.0)
+        p = _fma(r, p, 1.0)
+        v = tab[m & 63] * p
+        got = _from_hi(_hi(v) - ((m >> 6) << 20)) + 0.0
+        got = (got.view(np.uint64) | (v.view(np.uint64) & np.uint64(0xffffffff))).view(np.float64)
+        ref = np.exp(-t.astype(np.longdouble))
+        err = np.abs(got.astype(np.longdouble) - ref) / np.spacing(ref.astype(np.float64))
+        assert float(err.max()) <= 2.5, (a, b, float(err.max()))
