@@ -102,6 +102,28 @@ def test_sym_matches_one_sided_path(sym, get_mesh):
         assert relerr(g, w) <= 1e-13
 
 
+@pytest.mark.parametrize("panel,chunk", [(3, 1), (2, 2), (1, 16), (256, 16)])
+def test_sym_launch_geometry_does_not_change_the_bits(sym, oracle, panel, chunk):
+    """Panels of target blocks (ragged last panel) and the chunk length of the triangle kernel only reorder exact
+    fixed-point additions ... of per-(block, tile) values.  The chunk length also regroups each CTA's own running
+    sums, so bits are compared per chunk length; every geometry must meet parity."""
+    x, y, z, zeta, area, mask = _rand_sphere(7001, 31, 0.8)          # 5601 active: 6 blocks of 1024, 22 tiles
+    av = zeta + 0.3 * z
+    want = oracle.bve_velocity(x, y, z, zeta, area, mask, 1.0)
+    ld = oracle.bve_velocity(x, y, z, zeta, area, mask, 1.0, variant="_ld")
+    sym.tune("sym_chunk_tiles", chunk)
+    try:
+        sym.tune("sym_panel_blocks", 256)
+        base = sym.bve_velocity(x, y, z, zeta, area, mask, 1.0) + sym.bve_stream(x, y, z, zeta, av, area, mask, 1.0)
+        sym.tune("sym_panel_blocks", panel)
+        got = sym.bve_velocity(x, y, z, zeta, area, mask, 1.0) + sym.bve_stream(x, y, z, zeta, av, area, mask, 1.0)
+    finally:
+        sym.tune("sym_panel_blocks", 256)
+        sym.tune("sym_chunk_tiles", 16)
+    _check(got[:3], want, ld)
+    assert all(np.array_equal(a, b) for a, b in zip(got, base))
+
+
 def test_sym_rk4_step(sym, oracle, get_mesh):
     """The resident solver takes the symmetric path for its four velocity sums and the stream functions."""
     m = get_mesh(M.ICOS_TRI_SPHERE_SEED, 4)
