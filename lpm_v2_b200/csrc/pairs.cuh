@@ -84,12 +84,28 @@ __device__ __forceinline__ void rcp_batch(const double (&d)[T], double (&r)[T])
     }
 }
 
+// What the functors call.  The unchecked tile loop (CHECK = false) shares one MUFU between the targets of a thread;
+// the careful loop (CHECK = true: tiles that contain self pairs, and tiles ds_kernel re-runs because a sum came out
+// non-finite) takes each reciprocal on its own, so that a zero or non-finite denominator -- coincident particles --
+// reaches only its own target, as in the reference's loops (e.g. src/SphereBVESolver.f90:403-407).
+template <int T, bool CHECK>
+__device__ __forceinline__ void rcp_group(const double (&d)[T], double (&r)[T])
+{
+    if constexpr (CHECK) {
+#pragma unroll
+        for (int k = 0; k < T; ++k) r[k] = rcp_fast(d[k]);
+    } else {
+        rcp_batch<T>(d, r);
+    }
+}
+
 // Tile culling (directsum.cuh) is for the compactly supported PSE kernels only; they
 // derive from CullSphere / CullPlane below and provide cull_dist(Params).
 struct NoCull {
     static constexpr bool CULL = false;
     static constexpr int CULL_GEOM = 0;
     static constexpr bool RETRY = false;     // no group_fast(); see LogSharedTable
+    static constexpr bool BATCHED_RCP = false;   // true: ds_kernel re-runs a tile whose sums are non-finite (rcp_group)
 };
 
 // Kernels without a per-CTA shared table.
@@ -336,6 +352,7 @@ template <int RG, int ORDER = 0>
 struct BveVelT : NoSharedTable {
     static constexpr int NS = 6, NA = 3;
     static constexpr bool SKIP_SELF = true;
+    static constexpr bool BATCHED_RCP = RG >= 2;
     using Params = BveVelParams;
     using Tgt = BveVelTgt;
     __device__ static __forceinline__ Tgt load_target(const Params& p, int64_t i)
@@ -371,7 +388,9 @@ struct BveVelT : NoSharedTable {
 #pragma unroll
             for (int k = 0; k < T; ++k) d[k] = (j == self[k]) ? 1.0 : d[k];     // keep the self pair out of the shared product
         }
-        if constexpr (RG >= 4 && T == 4) {
+        if constexpr (CHECK) {
+            rcp_group<T, true>(d, r);
+        } else if constexpr (RG >= 4 && T == 4) {
             // rcp_batch<4> with the pairing chosen by PT
             constexpr int a0 = 0, a1 = (PT == 0) ? 1 : (PT == 1) ? 2 : 3;
             constexpr int b0 = (PT == 0) ? 2 : 1, b1 = (PT == 2) ? 2 : 3;
@@ -537,6 +556,7 @@ __global__ void pack_bve_stream(int32_t nsrc, int32_t nsrc_pad, const int32_t* _
 struct PlaneVel : NoSharedTable {
     static constexpr int NS = 4, NA = 2;
     static constexpr bool SKIP_SELF = true;
+    static constexpr bool BATCHED_RCP = true;
     struct Params {
         const double *x, *y;
         Outs<2> out;
@@ -554,7 +574,7 @@ struct PlaneVel : NoSharedTable {
             r2[k] = fma(dx[k], dx[k], dy[k] * dy[k]);
             if (CHECK) r2[k] = (j == self[k]) ? 1.0 : r2[k];
         }
-        rcp_batch<T>(r2, r);
+        rcp_group<T, CHECK>(r2, r);
 #pragma unroll
         for (int k = 0; k < T; ++k) {
             double w = r[k] * s[2];
@@ -655,6 +675,7 @@ struct PlaneStream : LogSharedTable<32> {
 struct BetaVel : NoSharedTable {
     static constexpr int NS = 6, NA = 2;
     static constexpr bool SKIP_SELF = true;
+    static constexpr bool BATCHED_RCP = true;
     struct Params {
         const double *x, *y;
         Outs<2> out;
@@ -683,7 +704,7 @@ struct BetaVel : NoSharedTable {
             if (CHECK) den[k] = (j == self[k]) ? 1.0 : den[k];
             SC[k] = S * C; sc[k] = sn * cs;
         }
-        rcp_batch<T>(den, r);
+        rcp_group<T, CHECK>(den, r);
 #pragma unroll
         for (int k = 0; k < T; ++k) {
             double w = r[k] * s[4];

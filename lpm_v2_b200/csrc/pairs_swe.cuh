@@ -15,6 +15,7 @@ namespace lpm {
 struct SweRhsPlane : NoSharedTable {
     static constexpr int NS = 6, NA = 7;
     static constexpr bool SKIP_SELF = true;
+    static constexpr bool BATCHED_RCP = true;
     struct Params {
         const double *x, *y, *surf;
         double inv_eps2;
@@ -37,7 +38,7 @@ struct SweRhsPlane : NoSharedTable {
                 acc[k][6] = fma(pse_eta_pi(k2) * (s[4] - t[k].s), s[5], acc[k][6]);
             if (CHECK) r2[k] = (j == self[k]) ? 1.0 : r2[k];
         }
-        rcp_batch<T>(r2, r);
+        rcp_group<T, CHECK>(r2, r);
 #pragma unroll
         for (int k = 0; k < T; ++k) {
             double w = r[k];
@@ -93,6 +94,7 @@ __global__ void pack_swe_plane(int32_t nsrc, int32_t nsrc_pad, const int32_t* __
 struct SwePlaneVel : NoSharedTable {
     static constexpr int NS = 4, NA = 2;
     static constexpr bool SKIP_SELF = true;
+    static constexpr bool BATCHED_RCP = true;
     struct Params {
         const double *x, *y;
         Outs<2> out;
@@ -110,7 +112,7 @@ struct SwePlaneVel : NoSharedTable {
             r2[k] = fma(dx[k], dx[k], dy[k] * dy[k]);
             if (CHECK) r2[k] = (j == self[k]) ? 1.0 : r2[k];
         }
-        rcp_batch<T>(r2, r);
+        rcp_group<T, CHECK>(r2, r);
 #pragma unroll
         for (int k = 0; k < T; ++k) {
             double w = r[k];
@@ -158,6 +160,7 @@ __global__ void pack_swe_plane_vel(int32_t nsrc, int32_t nsrc_pad, const int32_t
 struct SweRhsSphere : NoSharedTable {
     static constexpr int NS = 8, NA = 7;
     static constexpr bool SKIP_SELF = true;
+    static constexpr bool BATCHED_RCP = true;
     struct Params {
         const double *x, *y, *z, *surf;
         double R2;
@@ -189,7 +192,7 @@ struct SweRhsSphere : NoSharedTable {
             d[k] = fma(-t[k].z, s[2], d[k]);
             if (CHECK) d[k] = (j == self[k]) ? 1.0 : d[k];
         }
-        rcp_batch<T>(d, r);
+        rcp_group<T, CHECK>(d, r);
 #pragma unroll
         for (int k = 0; k < T; ++k) {
             double w = r[k];

@@ -289,9 +289,9 @@ struct SymBveVel : NoSharedTable {
             d[t] = fma(-tg[t].x, s[0], p.R2);
             d[t] = fma(-tg[t].y, s[1], d[t]);
             d[t] = fma(-tg[t].z, s[2], d[t]);
-            d[t] = isself[t] ? 1.0 : d[t];          // keep the self pair out of the shared product
+            d[t] = isself[t] ? 1.0 : d[t];          // the self pair is zeroed below
         }
-        rcp_batch<T>(d, r);
+        rcp_group<T, true>(d, r);                   // one by one: a coincident pair stays with its own targets
 #pragma unroll
         for (int t = 0; t < T; ++t) {
             r[t] = isself[t] ? 0.0 : r[t];

@@ -168,16 +168,20 @@ def test_sym_bitwise_reproducible_large(sym, get_mesh):
 
 
 @pytest.mark.parametrize("symmetric", [True, False])
-def test_coincident_particles_fail_loudly(sym, oracle, symmetric):
+@pytest.mark.parametrize("n,other", [(900, 400), (3000, 2500)])
+def test_coincident_particles_fail_loudly(sym, oracle, symmetric, n, other):
     """Two coincident active particles: the reference's strength is -zeta A / (4 pi R * 0) = Inf and the cross
-    product 0, so both targets get NaN (src/SphereBVESolver.f90:403-407).  Here too -- the fixed-point
-    accumulators cannot hold Inf or NaN, so a value above their window raises the accumulator's overflow
-    counter and it reads as NaN -- and, because the reciprocals of the targets that share a thread share one
-    MUFU (rcp_batch), the NaN may also reach those targets (at most 7 per coincident particle; documented in
-    INTEGRATION.md).  Every other target must be finite and correct: the failure is loud and local."""
-    x, y, z, zeta, area, mask = _rand_sphere(900, 21, 1.0)
+    product 0, so both targets get NaN (src/SphereBVESolver.f90:403-407) and every other target is untouched.
+    One-sided engine: the same -- a tile whose sums come out non-finite is re-run with the reciprocals taken one by
+    one (rcp_group), so the NaN stays with its two targets.  Pair-symmetric path: the fixed-point accumulators
+    cannot hold Inf or NaN, so a value above their window raises the accumulator's overflow counter and it reads as
+    NaN; the block's own (diagonal) tiles also take reciprocals one by one (n = 900: one block), but above the
+    diagonal the reciprocals of the 8 targets a thread holds share one MUFU, so the NaN may also reach those
+    thread-mates (n = 3000, particles 17 and 2500 in different blocks: at most 7 more per coincident particle;
+    documented in INTEGRATION.md).  Every other target must be finite and correct: the failure is loud and local."""
+    x, y, z, zeta, area, mask = _rand_sphere(n, 21, 1.0)
     x[17], y[17], z[17] = 1.0, 0.0, 0.0
-    x[400], y[400], z[400] = 1.0, 0.0, 0.0
+    x[other], y[other], z[other] = 1.0, 0.0, 0.0
     sym.set_symmetric(symmetric)
     try:
         got = sym.bve_velocity(x, y, z, zeta, area, mask, 1.0)
@@ -185,12 +189,33 @@ def test_coincident_particles_fail_loudly(sym, oracle, symmetric):
         sym.set_symmetric(True)
     with np.errstate(all="ignore"):
         want = oracle.bve_velocity(x, y, z, zeta, area, mask, 1.0)
-    bad = np.zeros(900, bool)
-    bad[[17, 400]] = True
+    bad = np.zeros(n, bool)
+    bad[[17, other]] = True
     assert not np.any(np.isfinite(want[1][bad])) and not np.any(np.isfinite(want[2][bad]))
     nonfinite = ~(np.isfinite(got[0]) & np.isfinite(got[1]) & np.isfinite(got[2]))
     assert np.all(nonfinite[bad])
-    assert nonfinite.sum() <= 2 + 14
+    if not symmetric or n == 900:
+        assert nonfinite.sum() == 2
+    else:
+        assert nonfinite.sum() <= 2 + 14
     ok = ~nonfinite
     for g, w in zip(got, want):
         assert np.abs(g[ok] - w[ok]).max() <= 1e-11 * np.abs(w[ok]).max()
+
+
+def test_coincident_particles_planar_kernel(gpu, oracle):
+    """The planar velocity kernel (one-sided engine): r = 0 gives 0 * Inf = NaN at the two coincident targets in the
+    reference (src/PlaneIncompressibleSolver.f90:294-307) and here, and nowhere else."""
+    rng = np.random.default_rng(5)
+    n = 1500
+    x, y = rng.uniform(0.05, 0.95, n), rng.uniform(-0.4, 0.4, n)
+    q, area, mask = rng.uniform(-1, 1, n), np.full(n, 1.0 / n), np.ones(n, np.int32)
+    x[700], y[700] = x[33], y[33]
+    with np.errstate(all="ignore"):
+        got, want = gpu.plane_velocity(x, y, q, area, mask), oracle.plane_velocity(x, y, q, area, mask)
+    bad = np.zeros(n, bool)
+    bad[[33, 700]] = True
+    for g, w in zip(got, want):
+        assert not np.any(np.isfinite(w[bad])) and not np.any(np.isfinite(g[bad]))
+        assert np.all(np.isfinite(g[~bad]))
+        assert np.abs(g[~bad] - w[~bad]).max() <= 1e-10 * np.abs(w[~bad]).max()
