@@ -309,9 +309,9 @@ int lpm_last_sum_ms(double* ms);
  * current device since the last reset (profiling must be on). */
 int lpm_profile_summary(int reset, int64_t* nkernels, double* total_ms);
 /* The same per kernel family: entry 2 s + e holds the launches and the summed duration (ms) of sum s
- * (0 BVE velocity, 1 BVE stream functions, 2 every other sum) on engine e (0 the one-sided ds_kernel,
- * 1 the pair-symmetric sym_kernel). */
-int lpm_profile_breakdown(int reset, int64_t counts[6], double ms[6]);
+ * (0 BVE velocity, 1 BVE stream functions, 2 every other sum, 3 the fused velocity + stream functions that end a
+ * resident BVE time step) on engine e (0 the one-sided ds_kernel, 1 the pair-symmetric sym_kernel). */
+int lpm_profile_breakdown(int reset, int64_t counts[8], double ms[8]);
 int64_t lpm_launch_count(int reset);
 /* 1: record events around each main kernel (adds a sync at query time only). */
 int lpm_set_profiling(int enable);

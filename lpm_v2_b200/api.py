@@ -223,13 +223,13 @@ def profile_summary(reset=True):
 
 
 PROFILE_TAGS = ("bve_velocity/one_sided", "bve_velocity/symmetric", "bve_stream/one_sided", "bve_stream/symmetric",
-                "other/one_sided", "other/symmetric")
+                "other/one_sided", "other/symmetric", "bve_velocity+stream/one_sided", "bve_velocity+stream/symmetric")
 
 
 def profile_breakdown(reset=True):
     """{kernel family: (launches, total ms)} of the direct-sum main kernels since the last reset."""
-    k = (C.c_int64 * 6)()
-    ms = (C.c_double * 6)()
+    k = (C.c_int64 * 8)()
+    ms = (C.c_double * 8)()
     check(lib.lpm_profile_breakdown(1 if reset else 0, k, ms))
     return {t: (int(k[i]), float(ms[i])) for i, t in enumerate(PROFILE_TAGS) if k[i]}
 

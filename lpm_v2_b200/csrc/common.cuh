@@ -93,7 +93,7 @@ struct Workspace {
     SharedOut shared_out[4];   // host API in rank mode: outputs staged where the peers can store (freed with the slabs)
     DevBuf logwin;      // int32 [2]: max |coordinate| high word, window origin of the log table (pairs.cuh)
     // spatially sorted PSE evaluation (sorted.cuh)
-    DevBuf sort_tmp, sort_keys[2], sort_vals[2], sorted_active, sorted_targets, gathered[8], sorted_out[4];
+    DevBuf sort_tmp, sort_keys[2], sort_vals[2], sorted_active, sorted_targets, gathered[8], sorted_out[8];
     DevBuf sym_acc;     // fixed-point accumulators of the symmetric paths (symmetric.cuh): kFxWords 64-bit words per sum
     DevBuf sym_acc2, sym_fx;    // the same sums as doubles; FxWindow + max high word of the records
     void release()
@@ -129,7 +129,7 @@ struct Device {
     }
     // profiling: one event pair per direct-sum main kernel since the last reset
     // and what it timed (lpm_profile_breakdown): tag = 2 * sum + engine; sum 0 BVE velocity, 1 BVE stream
-    // functions, 2 any other; engine 0 one-sided ds_kernel, 1 pair-symmetric sym_kernel
+    // functions, 2 any other, 3 the fused velocity + stream functions; engine 0 one-sided ds_kernel, 1 pair-symmetric sym_kernel
     std::vector<std::pair<cudaEvent_t, cudaEvent_t>> prof;
     std::vector<int> prof_tag;
     size_t prof_used = 0;
@@ -165,6 +165,7 @@ struct Runtime {
     int64_t launches = 0;
     bool symmetric = true;               // pair-symmetric evaluation of whole BVE sums (lpm_set_symmetric)
     int sym_vel_order = 43;              // LPM_SYM_ORDER_SWEEP builds only
+    bool fuse_step_end = true;           // BVE RK4 step: final velocity + stream functions in one pass (A/B: lpm_tune)
     int force_T = 0;                     // A/B: targets per thread of the one-sided engine (0 = automatic)
     int32_t sym_min_sources = 200000;
     int32_t sym_panel_blocks = 256;      // ... launched in panels of this many target blocks (kSymPanelBlocks)

@@ -349,7 +349,8 @@ ds_kernel(const typename K::Params prm, const DsGeom g, const double* __restrict
                 // some argument of this thread was outside the fast path's domain: drop the
                 // tile's sums and redo the tile with the general code (per thread; no barrier inside)
                 careful = K::needs_retry(worst);
-            } else if constexpr (K::BATCHED_RCP) {
+            }
+            if constexpr (K::BATCHED_RCP) {
                 // The targets of a thread share one MUFU per source here, so a zero or non-finite denominator
                 // (coincident particles) poisons its thread-mates' sums too.  Any non-finite tile sum sends the
                 // thread through the careful loop, whose reciprocals are taken one by one: the Inf / NaN then
@@ -359,7 +360,7 @@ ds_kernel(const typename K::Params prm, const DsGeom g, const double* __restrict
                 for (int t = 0; t < T; ++t)
 #pragma unroll
                     for (int a = 0; a < NA; ++a) chk += acc[t][a];
-                careful = !(fabs(chk) <= 1.7976931348623157e308);
+                careful = careful || !(fabs(chk) <= 1.7976931348623157e308);
             }
             if (careful) {
 #pragma unroll

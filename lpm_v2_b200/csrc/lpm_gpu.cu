@@ -214,6 +214,8 @@ extern "C" int lpm_tune(const char* key, int value)
         chunk_min_ref() = value;
     } else if (k == "sym_vel_order") {
         rt().sym_vel_order = value;
+    } else if (k == "fuse_step_end") {
+        rt().fuse_step_end = value != 0;
     } else if (k == "force_T") {
         rt().force_T = value;
     } else if (k == "sym_panel_blocks") {
@@ -282,16 +284,16 @@ extern "C" int lpm_profile_summary(int reset, int64_t* nkernels, double* total_m
     return LPM_OK;
 }
 
-extern "C" int lpm_profile_breakdown(int reset, int64_t counts[6], double ms[6])
+extern "C" int lpm_profile_breakdown(int reset, int64_t counts[8], double ms[8])
 {
     Device* d = nullptr;
     LPM_TRY(current_device(&d));
-    for (int t = 0; t < 6; ++t) { counts[t] = 0; ms[t] = 0.0; }
+    for (int t = 0; t < 8; ++t) { counts[t] = 0; ms[t] = 0.0; }
     for (size_t k = 0; k < d->prof_used; ++k) {
         LPM_CUDA(cudaEventSynchronize(d->prof[k].second));
         float f = 0;
         LPM_CUDA(cudaEventElapsedTime(&f, d->prof[k].first, d->prof[k].second));
-        const int t = d->prof_tag[k] >= 0 && d->prof_tag[k] < 6 ? d->prof_tag[k] : 4;
+        const int t = d->prof_tag[k] >= 0 && d->prof_tag[k] < 8 ? d->prof_tag[k] : 4;
         counts[t] += 1;
         ms[t] += f;
     }

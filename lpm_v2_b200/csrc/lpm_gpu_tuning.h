@@ -3,6 +3,7 @@
  * uses it; keys may disappear without notice.
  *   "max_chunks"        upper bound on source chunks per evaluation (every rank the same value)
  *   "chunk_min"         smallest source chunk (a multiple of 256; every rank the same value)
+ *   "fuse_step_end"     0: the BVE RK4 step ends with separate velocity and stream-function sums (A/B; default 1: fused)
  *   "force_T"           targets per thread of the one-sided engine: 1, 2, 4, 8 (0 = automatic)
  *   "sym_panel_blocks"  target blocks per panel of the triangle kernel's launch order (default 256)
  *   "sym_chunk_tiles"   source tiles per CTA of the symmetric triangle kernel (default 16; every rank the same value)

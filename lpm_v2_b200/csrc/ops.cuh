@@ -71,6 +71,29 @@ struct OpBveStream {
     }
 };
 
+// ---- BVE velocity + stream functions fused (the end of an RK4 step): in = x y z relvort absvort area; sc = radius;
+//      out = u v w relstream absstream
+struct OpBveVelStream {
+    using K = BveVelStream;
+    static constexpr int NIN = 6, NOUT = 5, NTGT = 0;
+    static int pack(Device& dev, cudaStream_t st, const MaskPlan& mp, const Args& a)
+    {
+        int32_t pad;
+        LPM_TRY(reserve_sources<K>(dev, mp, &pad));
+        pack_bve_velstream<<<pack_grid(pad), 256, 0, st>>>(mp.nsrc, pad, mp.active.as<int32_t>(), a.in[0], a.in[1], a.in[2],
+                                                           a.in[3], a.in[4], a.in[5], a.sc[0], dev.ws.sources.as<double>());
+        count_launch();
+        return log_window<K>(dev, st, 0, 2.0 * a.sc[0] * a.sc[0], 0, nullptr, nullptr);     // d <= 2 R^2
+    }
+    static K::Params params(const Args& a)
+    {
+        K::Params p{};
+        p.x = a.in[0]; p.y = a.in[1]; p.z = a.in[2];
+        p.R2 = a.sc[0] * a.sc[0];
+        return p;
+    }
+};
+
 // ---- planar velocity / stream: in = x y vort area
 template <class KK, bool STREAM>
 struct OpPlane {

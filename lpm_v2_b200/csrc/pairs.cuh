@@ -548,6 +548,109 @@ __global__ void pack_bve_stream(int32_t nsrc, int32_t nsrc_pad, const int32_t* _
 }
 
 // =============================================================================
+// BVE velocity AND stream functions in one pass: the end of every RK4 step (src/SphereBVESolver.f90:345-352: the
+// velocity at the new state, then SetStreamFunctionsOnMesh on the same particles).  Both sums depend on the pair
+// through d = R^2 - x_i.x_j only, so the denominator (3 DFMA) is computed once: 3 + 3 (reciprocal) + 3 + 6 (logarithm)
+// + 2 = 17 FP64 instructions per interaction instead of 9 + 11 = 20 for the two kernels.
+// Source record: x, y, z, Px, Py, Pz (P = -zeta A/(4 pi R) x), -zeta A/(4 pi), -omega A/(4 pi).
+struct BveVelStream : LogSharedTable<32> {
+    static constexpr int NS = 8, NA = 5;
+    static constexpr bool SKIP_SELF = true;
+    static constexpr bool BATCHED_RCP = true;
+    struct Params : LogParams {
+        const double *x, *y, *z;
+        double R2;
+        Outs<5> out;
+    };
+    struct Tgt { double x, y, z; };
+    __device__ static __forceinline__ Tgt load_target(const Params& p, int64_t i)
+    {
+        return Tgt{p.x[i], p.y[i], p.z[i]};
+    }
+    template <int T, bool CHECK>
+    __device__ static __forceinline__ void group(const Params& p, const Tgt (&t)[T], const double (&s)[NS],
+                                                 double (&acc)[T][NA], int32_t j, const int32_t (&self)[T],
+                                                 const SharedCtx& sc)
+    {
+        double d[T], r[T], l[T];
+#pragma unroll
+        for (int k = 0; k < T; ++k) {
+            d[k] = fma(-t[k].x, s[0], p.R2);
+            d[k] = fma(-t[k].y, s[1], d[k]);
+            d[k] = fma(-t[k].z, s[2], d[k]);
+            if (CHECK) d[k] = (j == self[k]) ? p.R2 : d[k];     // any in-window value; the pair is zeroed below
+        }
+        rcp_group<T, CHECK>(d, r);
+        log_group<KS, T>(d, l, sc);
+#pragma unroll
+        for (int k = 0; k < T; ++k) {
+            if (CHECK) {
+                r[k] = (j == self[k]) ? 0.0 : r[k];
+                l[k] = (j == self[k]) ? 0.0 : l[k];
+            }
+            acc[k][0] = fma(r[k], s[3], acc[k][0]);
+            acc[k][1] = fma(r[k], s[4], acc[k][1]);
+            acc[k][2] = fma(r[k], s[5], acc[k][2]);
+            acc[k][3] = fma(l[k], s[6], acc[k][3]);
+            acc[k][4] = fma(l[k], s[7], acc[k][4]);
+        }
+    }
+    template <int T>
+    __device__ static __forceinline__ void group_fast(const Params& p, const Tgt (&t)[T], const double (&s)[NS],
+                                                      double (&acc)[T][NA], unsigned& worst, const SharedCtx& sc)
+    {
+        double d[T], r[T], l[T];
+#pragma unroll
+        for (int k = 0; k < T; ++k) d[k] = fma(-t[k].x, s[0], p.R2);
+#pragma unroll
+        for (int k = 0; k < T; ++k) d[k] = fma(-t[k].y, s[1], d[k]);
+#pragma unroll
+        for (int k = 0; k < T; ++k) d[k] = fma(-t[k].z, s[2], d[k]);
+        rcp_batch<T>(d, r);
+        log_group_fast<KS, T>(d, l, worst, sc);
+#pragma unroll
+        for (int k = 0; k < T; ++k) {
+            acc[k][0] = fma(r[k], s[3], acc[k][0]);
+            acc[k][1] = fma(r[k], s[4], acc[k][1]);
+            acc[k][2] = fma(r[k], s[5], acc[k][2]);
+            acc[k][3] = fma(l[k], s[6], acc[k][3]);
+            acc[k][4] = fma(l[k], s[7], acc[k][4]);
+        }
+    }
+    __device__ static __forceinline__ void finalize(const Params& p, const Tgt& t, const double (&a)[NA], int64_t i)
+    {
+        p.out.store(0, i, fma(t.y, a[2], -(t.z * a[1])));
+        p.out.store(1, i, fma(t.z, a[0], -(t.x * a[2])));
+        p.out.store(2, i, fma(t.x, a[1], -(t.y * a[0])));
+        p.out.store(3, i, a[3]);
+        p.out.store(4, i, a[4]);
+    }
+};
+
+__global__ void pack_bve_velstream(int32_t nsrc, int32_t nsrc_pad, const int32_t* __restrict__ active,
+                                   const double* __restrict__ x, const double* __restrict__ y,
+                                   const double* __restrict__ z, const double* __restrict__ zeta,
+                                   const double* __restrict__ omega, const double* __restrict__ area,
+                                   double R, double* __restrict__ src)
+{
+    int32_t c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= nsrc_pad) return;
+    double r[8] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0};     // null source: d = R^2, all weights 0
+    if (c < nsrc) {
+        int32_t j = active[c];
+        // the same expressions as pack_bve_vel / pack_bve_stream, so the fused sums see the same records
+        double s = -zeta[j] * area[j] / (4.0 * LPM_PI * R);
+        r[0] = x[j]; r[1] = y[j]; r[2] = z[j];
+        r[3] = s * r[0]; r[4] = s * r[1]; r[5] = s * r[2];
+        r[6] = -zeta[j] * area[j] / (4.0 * LPM_PI);
+        r[7] = -omega[j] * area[j] / (4.0 * LPM_PI);
+    }
+    double2* o = reinterpret_cast<double2*>(src + (size_t)c * 8);
+    o[0] = make_double2(r[0], r[1]); o[1] = make_double2(r[2], r[3]);
+    o[2] = make_double2(r[4], r[5]); o[3] = make_double2(r[6], r[7]);
+}
+
+// =============================================================================
 // Planar Biot-Savart (singular).  src/PlaneIncompressibleSolver.f90:294-307
 // (== src/PlanarIncompressible.f90:437-456):
 //   strength = omega_j A_j / (2 pi ((x_i-x_j)^2 + (y_i-y_j)^2))

@@ -337,10 +337,12 @@ template <class K>
 inline int launch_auto(cudaStream_t st, const typename K::Params& prm, const DsGeom& g,
                        const double* src, const int32_t* scan, double* partial, int sm_count);
 
-// lpm_profile_breakdown: which sum a functor belongs to (0 BVE velocity, 1 BVE stream functions, 2 other)
+// lpm_profile_breakdown: which sum a functor belongs to (0 BVE velocity, 1 BVE stream functions, 2 other, 3 the
+// fused velocity + stream functions of an RK4 step's end)
 template <class K> struct prof_sum_of { static constexpr int value = 2; };
 template <int RG, int ORDER> struct prof_sum_of<BveVelT<RG, ORDER>> { static constexpr int value = 0; };
 template <> struct prof_sum_of<BveStream> { static constexpr int value = 1; };
+template <> struct prof_sum_of<BveVelStream> { static constexpr int value = 3; };
 
 // Packs nothing: the caller has already written the source records for this
 // evaluation into ws.sources (see the api functions).  Runs targets
@@ -462,6 +464,21 @@ inline int launch_auto(cudaStream_t st, const typename K::Params& prm, const DsG
             case 2: launch_ds<K, 2, 128, 2>(st, prm, g, src, scan, partial); break;
             default: launch_ds<K, 1, 128, 4>(st, prm, g, src, scan, partial); break;
         }
+    }
+    return LPM_OK;
+}
+
+// The fused velocity + stream kernel: 64 KB table, 2 x 16 KB of tiles and BLOCK*T*5 running sums -- one CTA of 256
+// threads per SM (136 KB with 4 targets per thread), so no register cap: __launch_bounds__(256, 1).
+template <>
+inline int launch_auto<BveVelStream>(cudaStream_t st, const BveVelStream::Params& prm, const DsGeom& g,
+                                     const double* src, const int32_t* scan, double* partial, int sm_count)
+{
+    using K = BveVelStream;
+    switch (auto_T(g.nall, g.nchunks, sm_count, 256)) {
+        case 4: launch_ds<K, 4, 256, 2, 1>(st, prm, g, src, scan, partial); break;
+        case 2: launch_ds<K, 2, 256, 2, 1>(st, prm, g, src, scan, partial); break;
+        default: launch_ds<K, 1, 256, 2, 1>(st, prm, g, src, scan, partial); break;
     }
     return LPM_OK;
 }

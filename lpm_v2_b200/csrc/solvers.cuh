@@ -220,7 +220,8 @@ struct SolverBase {
             a.mask = r.mask.as<int32_t>();
             for (int k = 0; k < 3; ++k) a.sc[k] = sc ? sc[k] : 0.0;
             {   // large BVE sums: the whole sum in pair-symmetric form (symmetric.cuh)
-                double* o[4] = {nullptr, nullptr, nullptr, nullptr};
+                double* o[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+                static_assert(Op::NOUT <= 8, "outputs per sum");
                 for (int k = 0; k < Op::NOUT; ++k) o[k] = r.A(out[k]);
                 bool taken = false;
                 LPM_TRY(sym_try<Op>(*r.dev, r.dev->stream, r.mp, a, o, r.sb, r.se, n, nrep, &taken));
@@ -232,7 +233,7 @@ struct SolverBase {
             LPM_TRY(Op::pack(*r.dev, r.dev->stream, r.mp, a));
             typename Op::K::Params prm = Op::params(a);
             if (R.rank_mode) {                   // one replica per process: the peers' copies through the shared slab
-                double* o[4];
+                double* o[8];
                 for (int k = 0; k < Op::NOUT; ++k) o[k] = r.A(out[k]);
                 exchanged = set_outs_shared(prm.out, o, n);
                 if (exchanged && r.se <= r.sb) {
@@ -255,7 +256,7 @@ struct SolverBase {
                 for (int h = 0; h < nrep; ++h)
                     if (h != g) LPM_CUDA(cudaStreamWaitEvent(reps[g].dev->stream, reps[h].dev->ev_done, 0));
         } else if (R.rank_mode && R.world > 1 && !exchanged) {
-            double* bufs[4];
+            double* bufs[8];
             for (int k = 0; k < Op::NOUT; ++k) bufs[k] = reps[0].A(out[k]);
             LPM_TRY(allgather_slices(Op::NOUT, bufs, n, reps[0].dev->stream));
         }
@@ -325,6 +326,16 @@ struct BveSolver : SolverBase {
                 rk_update<<<g, 256, 0, s>>>(n, r.A(X + c), r.A(XS1 + c), r.A(XS2 + c), r.A(XS3 + c), r.A(XS4 + c));
             return 4;
         }));
+        if (with_stream && rt().fuse_step_end) {
+            // :345-346 and :352 in one pass over the pairs: the velocity and the stream functions of the new state
+            // share the denominator R^2 - x_i.x_j (BveVelStream / SymBveVelStream)
+            if (!has_absvort) return set_error(LPM_ERR_INVALID, "stream functions need absvort (pass it to lpm_bve_solver_new)");
+            const int in[6] = {X, Y, Z, ZETA, ABSV, AREA};
+            const int out[5] = {U, V, W, RELS, ABSS};
+            const double sc[3] = {R, 0, 0};
+            LPM_TRY(eval<OpBveVelStream>(in, out, sc));
+            return sync();
+        }
         LPM_TRY(velocity(X, Y, Z, ZETA, U, V, W));                       // :345-346
         if (with_stream) LPM_TRY(stream());                              // :352
         return sync();

@@ -28,7 +28,7 @@ struct FxWindow {
 // kernel-wide constants of the symmetric functors
 struct SymParams : LogParams {
     double R2;
-    const FxWindow* fx;
+    const FxWindow* fx;     // fx[w]: the window of component class w (K::window)
 };
 
 // ---- order-independent accumulation ------------------------------------------------------------
@@ -75,16 +75,26 @@ __device__ __forceinline__ void sym_red_add(double* acc, size_t idx, double v, i
     if (p2) atomicAdd(a + k + 2, p2);
 }
 
-// Warp reduction of cb[s][a] (thread-local sums for SB sources, NC <= 3 components) by recursive
-// halving, then one RED per (source, component) from the lane that ends up owning it.
+// Warp reduction of cb[s][a] (thread-local sums for SB sources, NC components: <= 3 with batches of 8, <= 7 with
+// batches of 4) by recursive halving, then one add per (source, component) from the lane that ends up owning it;
+// fxe[w]: the fixed-point window of component class w = WIN(q) (the fused kernel's velocity and stream sums differ).
 // After the halving levels lane l holds source ((l >> (5 - LV)) & (SB - 1)) summed over the lanes
 // that differ from it in the high LV bits; a butterfly over the remaining low bits finishes the sum.
-template <int SB, int NC, bool COMBINE = false>
+// v[q] for a run-time q with static register indexing
+template <int NC>
+__device__ __forceinline__ double sym_pick(const double (&v)[NC], int q)
+{
+    double val = v[0];
+#pragma unroll
+    for (int a = 1; a < NC; ++a) val = (q == a) ? v[a] : val;
+    return val;
+}
+template <class K, int SB, int NC, bool COMBINE = false>
 __device__ __forceinline__ void sym_reduce_red(double (&cb)[SB][NC], int lane, double* __restrict__ acc, size_t idx0,
-                                               int fxe, double* __restrict__ slot = nullptr)
+                                               const int (&fxe)[2], double* __restrict__ slot = nullptr)
 {
     static_assert(SB == 8 || SB == 4, "source batch");
-    static_assert(NC >= 1 && NC <= 3, "components per source");
+    static_assert(NC >= 1 && NC <= (SB == 8 ? 3 : 7), "components per source");
     constexpr unsigned FULL = 0xffffffffu;
     double v[NC];
     int sidx;
@@ -121,9 +131,9 @@ __device__ __forceinline__ void sym_reduce_red(double (&cb)[SB][NC], int lane, d
         sidx = (lane >> 2) & 7;
         const int q = lane & 3;
         if (q < NC) {
-            const double val = q == 0 ? v[0] : (q == 1 ? v[NC > 1 ? 1 : 0] : v[NC > 2 ? 2 : 0]);
+            const double val = sym_pick<NC>(v, q);
             if constexpr (COMBINE) slot[sidx * NC + q] = val;      // this warp's sum; joined with the other warps' after the tile
-            else sym_red_add(acc, idx0 + sidx * NC + q, val, fxe);
+            else sym_red_add(acc, idx0 + sidx * NC + q, val, fxe[K::window(q)]);
         }
     } else {
         const bool b4 = (lane & 16) != 0, b3 = (lane & 8) != 0;
@@ -151,9 +161,9 @@ __device__ __forceinline__ void sym_reduce_red(double (&cb)[SB][NC], int lane, d
         sidx = (lane >> 3) & 3;
         const int q = lane & 7;
         if (q < NC) {
-            const double val = q == 0 ? v[0] : (q == 1 ? v[NC > 1 ? 1 : 0] : v[NC > 2 ? 2 : 0]);
+            const double val = sym_pick<NC>(v, q);
             if constexpr (COMBINE) slot[sidx * NC + q] = val;      // this warp's sum; joined with the other warps' after the tile
-            else sym_red_add(acc, idx0 + sidx * NC + q, val, fxe);
+            else sym_red_add(acc, idx0 + sidx * NC + q, val, fxe[K::window(q)]);
         }
     }
 }
@@ -179,6 +189,7 @@ __device__ __forceinline__ void sym_reduce_red(double (&cb)[SB][NC], int lane, d
 //   bit 5     a scheduling fence after every source group (sched_fence below)
 struct SymBveVel : NoSharedTable {
     static constexpr int NS = 6, NA = 3, NC = 3;
+    __host__ __device__ static constexpr int window(int) { return 0; }
     struct Tgt { double x, y, z, px, py, pz; };
     __device__ static __forceinline__ Tgt null() { return Tgt{0.0, 0.0, 0.0, 0.0, 0.0, 0.0}; }
     __device__ static __forceinline__ Tgt from_record(const double2* p2)
@@ -310,6 +321,7 @@ struct SymBveVel : NoSharedTable {
 // before anything is accumulated (the one-sided kernel redoes a whole tile instead).
 struct SymBveStream : LogSharedTable<32> {
     static constexpr int NS = 6, NA = 2, NC = 2;
+    __host__ __device__ static constexpr int window(int) { return 0; }
     struct Tgt { double x, y, z, w0, w1; };
     __device__ static __forceinline__ Tgt null() { return Tgt{0.0, 0.0, 0.0, 0.0, 0.0}; }
     __device__ static __forceinline__ Tgt from_record(const double2* p2)
@@ -376,6 +388,95 @@ struct SymBveStream : LogSharedTable<32> {
     }
 };
 
+// BVE velocity and stream functions fused (BveVelStream in pairs.cuh; the end of every RK4 step): one denominator, one
+// reciprocal and one logarithm serve a_c += P_c' / d, a_c' += P_c / d, psi_c += w_c' ln d and psi_c' += w_c ln d:
+// 3 + 3 + 6 + (3 + 2) + (3 + 2) = 22 FP64 instructions for two interactions of each kind, against 12 + 13 in the two
+// separate kernels.  Record x, y, z, Px, Py, Pz, w_rel, w_abs.  Components 0-2 (velocity) and 3-4 (stream functions)
+// have their own fixed-point windows.
+struct SymBveVelStream : LogSharedTable<32> {
+    static constexpr int NS = 8, NA = 5, NC = 5;
+    __host__ __device__ static constexpr int window(int q) { return q >= 3 ? 1 : 0; }
+    struct Tgt { double x, y, z, px, py, pz, w0, w1; };
+    __device__ static __forceinline__ Tgt null() { return Tgt{0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0}; }
+    __device__ static __forceinline__ Tgt from_record(const double2* p2)
+    {
+        const double2 v0 = p2[0], v1 = p2[1], v2 = p2[2], v3 = p2[3];
+        return Tgt{v0.x, v0.y, v1.x, v1.y, v2.x, v2.y, v3.x, v3.y};
+    }
+    template <int T, int SB, int ORDER>
+    __device__ static __forceinline__ void batch(const SymParams& p, const Tgt (&tg)[T], double (&a)[T][NA],
+                                                 const double* __restrict__ sm, double (&cb)[SB][NC], const SharedCtx& sc)
+    {
+#pragma unroll
+        for (int u = 0; u < SB; ++u) {
+            double s[NS], d[T], r[T], l[T];
+            const double2* p2 = reinterpret_cast<const double2*>(sm + u * NS);
+#pragma unroll
+            for (int q = 0; q < NS / 2; ++q) {
+                const double2 v = p2[q];
+                s[2 * q] = v.x; s[2 * q + 1] = v.y;
+            }
+            unsigned worst = 0;
+#pragma unroll
+            for (int t = 0; t < T; ++t) d[t] = fma(-tg[t].x, s[0], p.R2);
+#pragma unroll
+            for (int t = 0; t < T; ++t) d[t] = fma(-tg[t].y, s[1], d[t]);
+#pragma unroll
+            for (int t = 0; t < T; ++t) d[t] = fma(-tg[t].z, s[2], d[t]);
+            rcp_batch<T>(d, r);
+            log_group_fast<KS, T>(d, l, worst, sc);
+            if (__builtin_expect(needs_retry(worst), 0)) {
+#pragma unroll
+                for (int t = 0; t < T; ++t) l[t] = log_slow_path(d[t]);
+            }
+#pragma unroll
+            for (int t = 0; t < T; ++t) {
+                a[t][0] = fma(r[t], s[3], a[t][0]);
+                a[t][1] = fma(r[t], s[4], a[t][1]);
+                a[t][2] = fma(r[t], s[5], a[t][2]);
+                a[t][3] = fma(l[t], s[6], a[t][3]);
+                a[t][4] = fma(l[t], s[7], a[t][4]);
+            }
+            cb[u][0] = r[0] * tg[0].px; cb[u][1] = r[0] * tg[0].py; cb[u][2] = r[0] * tg[0].pz;
+            cb[u][3] = l[0] * tg[0].w0; cb[u][4] = l[0] * tg[0].w1;
+#pragma unroll
+            for (int t = 1; t < T; ++t) {
+                cb[u][0] = fma(r[t], tg[t].px, cb[u][0]);
+                cb[u][1] = fma(r[t], tg[t].py, cb[u][1]);
+                cb[u][2] = fma(r[t], tg[t].pz, cb[u][2]);
+                cb[u][3] = fma(l[t], tg[t].w0, cb[u][3]);
+                cb[u][4] = fma(l[t], tg[t].w1, cb[u][4]);
+            }
+        }
+    }
+    // as BveVelStream::group<T, true>
+    template <int T>
+    __device__ static __forceinline__ void diag(const SymParams& p, const Tgt (&tg)[T], double (&a)[T][NA],
+                                                const double (&s)[NS], const bool (&isself)[T], const SharedCtx& sc)
+    {
+        double d[T], r[T], l[T];
+#pragma unroll
+        for (int t = 0; t < T; ++t) {
+            d[t] = fma(-tg[t].x, s[0], p.R2);
+            d[t] = fma(-tg[t].y, s[1], d[t]);
+            d[t] = fma(-tg[t].z, s[2], d[t]);
+            d[t] = isself[t] ? p.R2 : d[t];         // any in-window value; the pair is zeroed below
+        }
+        rcp_group<T, true>(d, r);
+        log_group<KS, T>(d, l, sc);
+#pragma unroll
+        for (int t = 0; t < T; ++t) {
+            r[t] = isself[t] ? 0.0 : r[t];
+            l[t] = isself[t] ? 0.0 : l[t];
+            a[t][0] = fma(r[t], s[3], a[t][0]);
+            a[t][1] = fma(r[t], s[4], a[t][1]);
+            a[t][2] = fma(r[t], s[5], a[t][2]);
+            a[t][3] = fma(l[t], s[6], a[t][3]);
+            a[t][4] = fma(l[t], s[7], a[t][4]);
+        }
+    }
+};
+
 // ---- the kernel ---------------------------------------------------------------
 // acc: [nsrc_pad][NC][kFxWords] 64-bit words (fixed-point limbs + overflow counter, see sym_red_add), zeroed by the caller
 // (NA == NC: both directions feed the same sums).
@@ -437,7 +538,7 @@ sym_kernel(const SymParams prm, const SymGeom g, const double* __restrict__ src,
         for (int q = 0; q < NA; ++q) a[t][q] = 0.0;
     }
     const SharedCtx sctx{ks, K::init_shared(ks, prm, tid, BLOCK), g.half_bin};
-    const int fxe = prm.fx->fxe;
+    const int fxe[2] = {prm.fx[0].fxe, prm.fx[K::window(NC - 1)].fxe};      // one window per component class
     if (tid == 0) {
         mbar_init(&full[0], 1);
         mbar_init(&full[1], 1);
@@ -476,7 +577,7 @@ sym_kernel(const SymParams prm, const SymGeom g, const double* __restrict__ src,
         for (int jb = 0; jb < TS; jb += SB) {
             double cb[SB][NC];
             K::template batch<T, SB, ORDER>(prm, tg, a, sm + jb * NS, cb, sctx);
-            sym_reduce_red<SB, NC, COMBINE>(cb, lane, acc, ((size_t)k * TS + jb) * NC, fxe, mine + jb * NC);
+            sym_reduce_red<K, SB, NC, COMBINE>(cb, lane, acc, ((size_t)k * TS + jb) * NC, fxe, mine + jb * NC);
         }
     };
     // COMBINE: after the barrier that ends tile k, add the warps' sums in warp order and issue the REDs.  The slots are
@@ -487,7 +588,7 @@ sym_kernel(const SymParams prm, const SymGeom g, const double* __restrict__ src,
             double sum = base[idx];
 #pragma unroll
             for (int w = 1; w < NW; ++w) sum += base[(size_t)w * TS * NC + idx];
-            sym_red_add(acc, (size_t)k * TS * NC + idx, sum, fxe);
+            sym_red_add(acc, (size_t)k * TS * NC + idx, sum, fxe[K::window(idx % NC)]);
         }
     };
 
@@ -512,7 +613,7 @@ sym_kernel(const SymParams prm, const SymGeom g, const double* __restrict__ src,
     for (int t = 0; t < T; ++t)
         if (cidx[t] < g.nsrc) {
 #pragma unroll
-            for (int q = 0; q < NA; ++q) sym_red_add(acc, (size_t)cidx[t] * NA + q, a[t][q], fxe);
+            for (int q = 0; q < NA; ++q) sym_red_add(acc, (size_t)cidx[t] * NA + q, a[t][q], fxe[K::window(q)]);
         }
 }
 
@@ -542,11 +643,11 @@ __global__ void sym_fx_scale_kernel(int mode, double R2, int32_t nsrc, const int
     fx->pad = 0;
 }
 
-// limbs -> doubles: carries first (so that every limb but the top one is below 2^40), then the sum from the top;
+// limbs -> doubles (values are [sum][component], nc components per sum): carries first (so that every limb but the top one is below 2^40), then the sum from the top;
 // an accumulator whose overflow counter is set reads as NaN (see sym_red_add)
 __global__ void __launch_bounds__(256)
 sym_fx_to_double_kernel(int64_t nvalues, const long long* __restrict__ words, const FxWindow* __restrict__ fx,
-                        double* __restrict__ out)
+                        double* __restrict__ out, int nc, int split)
 {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= nvalues) return;
@@ -564,7 +665,8 @@ sym_fx_to_double_kernel(int64_t nvalues, const long long* __restrict__ words, co
     double s = 0.0;
 #pragma unroll
     for (int k = kFxLimbs - 1; k >= 0; --k) s = fma((double)l[k], unit[k], s);
-    out[i] = over != 0 ? __longlong_as_double(0x7ff8000000000000LL) : s * fx->unit;
+    const double win = fx[(int)(i % nc) >= split ? 1 : 0].unit;       // components >= split use the second window
+    out[i] = over != 0 ? __longlong_as_double(0x7ff8000000000000LL) : s * win;
 }
 
 // u_i = x_i cross a_i for the active particles (BveVelT::finalize)
@@ -580,6 +682,23 @@ sym_bve_finalize(int32_t nsrc, const int32_t* __restrict__ active, const double*
     out.store(0, i, fma(y, a2, -(z * a1)));
     out.store(1, i, fma(z, a0, -(x * a2)));
     out.store(2, i, fma(x, a1, -(y * a0)));
+}
+
+// fused sums: u_i = x_i cross a_i, and the two stream functions copied out
+__global__ void __launch_bounds__(256)
+sym_bve_velstream_finalize(int32_t nsrc, const int32_t* __restrict__ active, const double* __restrict__ src,
+                           const double* __restrict__ acc, Outs<5> out)
+{
+    const int32_t c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= nsrc) return;
+    const int64_t i = active[c];
+    const double x = src[(size_t)c * 8], y = src[(size_t)c * 8 + 1], z = src[(size_t)c * 8 + 2];
+    const double* a = acc + (size_t)c * 5;
+    out.store(0, i, fma(y, a[2], -(z * a[1])));
+    out.store(1, i, fma(z, a[0], -(x * a[2])));
+    out.store(2, i, fma(x, a[1], -(y * a[0])));
+    out.store(3, i, a[3]);
+    out.store(4, i, a[4]);
 }
 
 // two sums per active particle, copied out (BveStream::finalize)

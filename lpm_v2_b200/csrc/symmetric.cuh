@@ -71,6 +71,7 @@ struct SymVel {
     using SK = SymBveVel;
     static constexpr int NCOORD = 3;
     static constexpr int FX_MODE = 0;       // fixed-point window from F max|P| / (R^2 2^-110)
+    static constexpr int FX_MODE2 = -1;     // no second window
     static void sym_params(SymParams& p, const Args& a) { p.R2 = a.sc[0] * a.sc[0]; }
     static void passive_params(BveVel::Params& p, const double* const* xyz, const Args& a)
     {
@@ -108,6 +109,7 @@ struct SymStream {
     using SK = SymBveStream;
     static constexpr int NCOORD = 3;
     static constexpr int FX_MODE = 1;       // fixed-point window from F max|w| 2^12
+    static constexpr int FX_MODE2 = -1;
     static void sym_params(SymParams& p, const Args& a) { p.R2 = a.sc[0] * a.sc[0]; }
     static void passive_params(BveStream::Params& p, const double* const* xyz, const Args& a)
     {
@@ -124,6 +126,31 @@ struct SymStream {
     static void finalize(cudaStream_t st, const MaskPlan& mp, const double*, const double* acc, const Outs<2>& out)
     {
         sym_stream_finalize<<<(unsigned)((mp.nsrc + 255) / 256), 256, 0, st>>>(mp.nsrc, mp.active.as<int32_t>(), acc, out);
+    }
+};
+
+// The end of an RK4 step (src/SphereBVESolver.f90:345-352): velocity and stream functions of the new state in one
+// pass (SymBveVelStream / BveVelStream).  4 targets per thread, 128 threads, batches of 4 sources, a retry branch per
+// source; 64 KB log table + 32 KB of tiles per CTA: two CTAs per SM.
+struct SymVelStream {
+    using Op = OpBveVelStream;
+    using SK = SymBveVelStream;
+    static constexpr int NCOORD = 3;
+    static constexpr int FX_MODE = 0;       // components 0-2: the velocity window
+    static constexpr int FX_MODE2 = 1;      // components 3-4: the stream-function window
+    static void sym_params(SymParams& p, const Args& a) { p.R2 = a.sc[0] * a.sc[0]; }
+    static void passive_params(BveVelStream::Params& p, const double* const* xyz, const Args& a)
+    {
+        p.x = xyz[0]; p.y = xyz[1]; p.z = xyz[2];
+        p.R2 = a.sc[0] * a.sc[0];
+    }
+    static int launch(cudaStream_t st, const SymParams& prm, const SymGeom& g, const double* src, double* acc)
+    {
+        return launch_sym<SK, 4, 128, 4, 2, 0>(st, prm, g, src, acc);
+    }
+    static void finalize(cudaStream_t st, const MaskPlan& mp, const double* src, const double* acc, const Outs<5>& out)
+    {
+        sym_bve_velstream_finalize<<<(unsigned)((mp.nsrc + 255) / 256), 256, 0, st>>>(mp.nsrc, mp.active.as<int32_t>(), src, acc, out);
     }
 };
 
@@ -174,15 +201,17 @@ inline int sym_evaluate(Device& dev, cudaStream_t st, MaskPlan& mp, const Args& 
             LPM_TRY(ws.sym_acc.reserve(acc_bytes));
             LPM_CUDA(cudaMemsetAsync(ws.sym_acc.p, 0, acc_bytes, st));
             // the window of the fixed-point accumulators, from the largest entry of the records
-            LPM_TRY(ws.sym_fx.reserve(sizeof(FxWindow) + sizeof(int32_t)));
+            LPM_TRY(ws.sym_fx.reserve(2 * sizeof(FxWindow) + sizeof(int32_t)));
             LPM_TRY(ws.sym_acc2.reserve(nacc * sizeof(double)));
             FxWindow* fxw = ws.sym_fx.as<FxWindow>();
-            int32_t* maxhi = reinterpret_cast<int32_t*>(fxw + 1);
+            int32_t* maxhi = reinterpret_cast<int32_t*>(fxw + 2);
             LPM_CUDA(cudaMemsetAsync(maxhi, 0, sizeof(int32_t), st));
             const int64_t nrec = (int64_t)g.nsrc_pad * SK::NS;
             const unsigned nb = (unsigned)std::min<int64_t>((nrec + 255) / 256, 4 * (int64_t)dev.sm_count);
             absmax_hi_kernel<<<nb, 256, 0, st>>>(nrec, src, nullptr, maxhi);
             sym_fx_scale_kernel<<<1, 1, 0, st>>>(S::FX_MODE, prm.R2, mp.nsrc, maxhi, fxw);
+            if constexpr (S::FX_MODE2 >= 0)     // second component class (the fused sums' stream functions)
+                sym_fx_scale_kernel<<<1, 1, 0, st>>>(S::FX_MODE2, prm.R2, mp.nsrc, maxhi, fxw + 1);
             prm.fx = fxw;
             cudaEvent_t pb = nullptr, pe = nullptr;
             if (prof) {     // the triangle kernel alone; the passive part's ds_kernel records its own pair
@@ -251,8 +280,11 @@ inline int sym_evaluate(Device& dev, cudaStream_t st, MaskPlan& mp, const Args& 
         if (mp.nsrc > 0) {
             const size_t nacc = (size_t)g.nsrc_pad * SK::NC;
             if (g.world > 1) LPM_CUDA(cudaStreamWaitEvent(st, dev.ev_comm[1], 0));
+            constexpr int kSplit = S::FX_MODE2 >= 0 ? 3 : SK::NC;      // SK::window(): components >= 3 of the fused sums
+            static_assert(SK::window(SK::NC - 1) == (S::FX_MODE2 >= 0 ? 1 : 0), "window classes");
             sym_fx_to_double_kernel<<<(unsigned)((nacc + 255) / 256), 256, 0, st>>>((int64_t)nacc, ws.sym_acc.as<long long>(),
-                                                                                 ws.sym_fx.as<FxWindow>(), ws.sym_acc2.as<double>());
+                                                                                 ws.sym_fx.as<FxWindow>(), ws.sym_acc2.as<double>(),
+                                                                                 SK::NC, kSplit);
             S::finalize(st, mp, src, ws.sym_acc2.as<double>(), out);
             count_launch(5);
         }
@@ -278,6 +310,7 @@ inline bool sym_applicable(int64_t tbeg, int64_t tend, int64_t nt, const MaskPla
 template <class Op> struct SymFor { using type = void; };
 template <> struct SymFor<OpBveVel> { using type = SymVel; };
 template <> struct SymFor<OpBveStream> { using type = SymStream; };
+template <> struct SymFor<OpBveVelStream> { using type = SymVelStream; };
 
 template <class Op>
 inline int sym_try(Device& dev, cudaStream_t st, MaskPlan& mp, const Args& a, double* const* out, int64_t tbeg,

@@ -357,6 +357,41 @@ def test_bve_rk4_steps(gpu, oracle, get_mesh):
     sol.Delete()
 
 
+@pytest.mark.parametrize("symmetric", [False, True])
+def test_bve_step_end_fused_equals_separate_sums(gpu, oracle, get_mesh, symmetric):
+    """The resident BVE step ends with ONE pass that yields the velocity and the stream functions of the new state
+    (src/SphereBVESolver.f90:345-352; BveVelStream / SymBveVelStream).  With the fusion switched off the same step
+    ends with the two separate sums: both must meet parity, and they agree with each other to rounding."""
+    m = get_mesh(M.ICOS_TRI_SPHERE_SEED, 4)
+    omega = 2 * PI
+    zeta = problems.rossby_haurwitz54(m)
+    u0 = oracle.bve_velocity(m.x, m.y, m.z, zeta, m.area, m.is_active, 1.0)
+    ref = oracle.bve_rk4_step(m.x, m.y, m.z, zeta, *u0, m.area, m.is_active, 1.0, omega, 0.002)
+    res = {}
+    gpu.set_symmetric(symmetric)
+    gpu.tune("sym_min_sources", 0 if symmetric else 200000)
+    try:
+        for fused in (1, 0):
+            gpu.tune("fuse_step_end", fused)
+            sph = solvers.BVEMesh(m, zeta, 1.0, omega)
+            sph.velocity = [a.copy() for a in u0]
+            sol = solvers.BVESolver(sph)
+            sol.Timestep(sph, 0.002, with_stream=True)
+            sol.Delete()
+            got = [sph.x, sph.y, sph.z, sph.relVort] + sph.velocity
+            for name, a, b in zip("x y z zeta u v w".split(), got, ref):
+                assert relerr(a, b) <= TOL, (fused, name)
+            rs, as_ = oracle.bve_stream(ref[0], ref[1], ref[2], ref[3], sph.absVort, m.area, m.is_active, 1.0)
+            assert relerr(sph.relStream, rs) <= TOL and relerr(sph.absStream, as_) <= TOL
+            res[fused] = sph.velocity + [sph.relStream, sph.absStream]
+    finally:
+        gpu.tune("fuse_step_end", 1)
+        gpu.set_symmetric(True)
+        gpu.tune("sym_min_sources", 200000)
+    for a, b in zip(res[1], res[0]):
+        assert relerr(a, b) <= 1e-13
+
+
 def test_plane_rk4_steps(gpu, oracle, get_mesh):
     m = get_mesh(M.QUAD_RECT_SEED, 3, 7.0)
     vort = problems.colliding_dipoles(m)
