@@ -164,7 +164,7 @@ struct Runtime {
     bool profiling = false;
     int64_t launches = 0;
     bool symmetric = true;               // pair-symmetric evaluation of whole BVE sums (lpm_set_symmetric)
-    int sym_vel_order = 43;              // LPM_SYM_ORDER_SWEEP builds only
+    int sym_vel_order = 11;              // LPM_SYM_ORDER_SWEEP builds only
     bool fuse_step_end = true;           // BVE RK4 step: final velocity + stream functions in one pass (A/B: lpm_tune)
     int force_T = 0;                     // A/B: targets per thread of the one-sided engine (0 = automatic)
     int32_t sym_min_sources = 200000;

@@ -9,7 +9,8 @@
  *   "sym_chunk_tiles"   source tiles per CTA of the symmetric triangle kernel (default 16; every rank the same value)
  *   "sym_min_sources"   smallest active-particle count that takes the pair-symmetric path (default 200000)
  *   "sym_vel_order"     statement order of the symmetric velocity kernel, in builds with -DLPM_SYM_ORDER_SWEEP only
- * (Builds under A/B get a key here while a round measures them; none is pending.) */
+ * (Builds under A/B get a key here while a round measures them -- tools/ab_builds.py drove "sym_vel_build",
+ * "sym_stream_build" and "sym_velstream_build" in round 2; none is pending.) */
 #ifndef LPM_GPU_TUNING_H
 #define LPM_GPU_TUNING_H
 #ifdef __cplusplus

@@ -9,7 +9,7 @@ namespace lpm {
 struct SymGeom {
     int32_t nsrc;           // active particles F
     int32_t nsrc_pad;       // padded to whole tiles (null records)
-    int32_t ntiles;         // nsrc_pad / kTile
+    int32_t ntiles;         // nsrc_pad / (the kernel's tile size TS; launch_sym converts from tiles of kTile)
     int32_t nblocks;        // target blocks of BLOCK*T compact indices
     int32_t chunk_tiles;    // source tiles per chunk
     int32_t nchunks;
@@ -78,8 +78,16 @@ __device__ __forceinline__ void sym_red_add(double* acc, size_t idx, double v, i
 // Warp reduction of cb[s][a] (thread-local sums for SB sources, NC components: <= 3 with batches of 8, <= 7 with
 // batches of 4) by recursive halving, then one add per (source, component) from the lane that ends up owning it;
 // fxe[w]: the fixed-point window of component class w = WIN(q) (the fused kernel's velocity and stream sums differ).
-// After the halving levels lane l holds source ((l >> (5 - LV)) & (SB - 1)) summed over the lanes
-// that differ from it in the high LV bits; a butterfly over the remaining low bits finishes the sum.
+// At each halving level a lane keeps the sums of one half of the sources it still holds and sends the other half to
+// its partner (lane ^ 16, ^ 8, ^ 4).  Which half a lane keeps follows from its lane bits, so the lanes take the batch's
+// sources in ROTATED order -- lane l reads source u ^ sym_rot<SB>(l) as its u-th (the functors' batch()) -- and slot k
+// of cb always holds a source of the half this lane keeps: every lane keeps the low slots and sends the high ones, with
+// no selects (round 2's first version selected keep / send per value: 84 FSEL per batch of 8 sources x 3 components,
+// 8 % of the velocity kernel's instructions; 765 -> 730 ms at icosTri 8, profiles/r02m_ab_builds.log).  After the
+// halving levels lane l holds source sym_rot<SB>(l) summed over the lanes that differ from it in the high bits; a
+// butterfly over the remaining low bits finishes the sum.
+template <int SB>
+__device__ __forceinline__ int sym_rot(int lane) { return SB == 8 ? (lane >> 2) & 7 : (lane >> 3) & 3; }
 // v[q] for a run-time q with static register indexing
 template <int NC>
 __device__ __forceinline__ double sym_pick(const double (&v)[NC], int q)
@@ -97,74 +105,44 @@ __device__ __forceinline__ void sym_reduce_red(double (&cb)[SB][NC], int lane, d
     static_assert(NC >= 1 && NC <= (SB == 8 ? 3 : 7), "components per source");
     constexpr unsigned FULL = 0xffffffffu;
     double v[NC];
-    int sidx;
     if constexpr (SB == 8) {
-        const bool b4 = (lane & 16) != 0, b3 = (lane & 8) != 0, b2 = (lane & 4) != 0;
         double v4[4][NC], v2[2][NC];
 #pragma unroll
         for (int k = 0; k < 4; ++k)
 #pragma unroll
-            for (int a = 0; a < NC; ++a) {
-                const double lo = cb[k][a], hi = cb[k + 4][a];
-                const double keep = b4 ? hi : lo, send = b4 ? lo : hi;
-                v4[k][a] = keep + __shfl_xor_sync(FULL, send, 16);
-            }
+            for (int a = 0; a < NC; ++a) v4[k][a] = cb[k][a] + __shfl_xor_sync(FULL, cb[k + 4][a], 16);
 #pragma unroll
         for (int k = 0; k < 2; ++k)
 #pragma unroll
-            for (int a = 0; a < NC; ++a) {
-                const double lo = v4[k][a], hi = v4[k + 2][a];
-                const double keep = b3 ? hi : lo, send = b3 ? lo : hi;
-                v2[k][a] = keep + __shfl_xor_sync(FULL, send, 8);
-            }
+            for (int a = 0; a < NC; ++a) v2[k][a] = v4[k][a] + __shfl_xor_sync(FULL, v4[k + 2][a], 8);
 #pragma unroll
-        for (int a = 0; a < NC; ++a) {
-            const double lo = v2[0][a], hi = v2[1][a];
-            const double keep = b2 ? hi : lo, send = b2 ? lo : hi;
-            v[a] = keep + __shfl_xor_sync(FULL, send, 4);
-        }
+        for (int a = 0; a < NC; ++a) v[a] = v2[0][a] + __shfl_xor_sync(FULL, v2[1][a], 4);
 #pragma unroll
         for (int a = 0; a < NC; ++a) {
             v[a] += __shfl_xor_sync(FULL, v[a], 2);
             v[a] += __shfl_xor_sync(FULL, v[a], 1);
         }
-        sidx = (lane >> 2) & 7;
-        const int q = lane & 3;
-        if (q < NC) {
-            const double val = sym_pick<NC>(v, q);
-            if constexpr (COMBINE) slot[sidx * NC + q] = val;      // this warp's sum; joined with the other warps' after the tile
-            else sym_red_add(acc, idx0 + sidx * NC + q, val, fxe[K::window(q)]);
-        }
     } else {
-        const bool b4 = (lane & 16) != 0, b3 = (lane & 8) != 0;
         double v2[2][NC];
 #pragma unroll
         for (int k = 0; k < 2; ++k)
 #pragma unroll
-            for (int a = 0; a < NC; ++a) {
-                const double lo = cb[k][a], hi = cb[k + 2][a];
-                const double keep = b4 ? hi : lo, send = b4 ? lo : hi;
-                v2[k][a] = keep + __shfl_xor_sync(FULL, send, 16);
-            }
+            for (int a = 0; a < NC; ++a) v2[k][a] = cb[k][a] + __shfl_xor_sync(FULL, cb[k + 2][a], 16);
 #pragma unroll
-        for (int a = 0; a < NC; ++a) {
-            const double lo = v2[0][a], hi = v2[1][a];
-            const double keep = b3 ? hi : lo, send = b3 ? lo : hi;
-            v[a] = keep + __shfl_xor_sync(FULL, send, 8);
-        }
+        for (int a = 0; a < NC; ++a) v[a] = v2[0][a] + __shfl_xor_sync(FULL, v2[1][a], 8);
 #pragma unroll
         for (int a = 0; a < NC; ++a) {
             v[a] += __shfl_xor_sync(FULL, v[a], 4);
             v[a] += __shfl_xor_sync(FULL, v[a], 2);
             v[a] += __shfl_xor_sync(FULL, v[a], 1);
         }
-        sidx = (lane >> 3) & 3;
-        const int q = lane & 7;
-        if (q < NC) {
-            const double val = sym_pick<NC>(v, q);
-            if constexpr (COMBINE) slot[sidx * NC + q] = val;      // this warp's sum; joined with the other warps' after the tile
-            else sym_red_add(acc, idx0 + sidx * NC + q, val, fxe[K::window(q)]);
-        }
+    }
+    const int sidx = sym_rot<SB>(lane);
+    const int q = lane & (SB == 8 ? 3 : 7);
+    if (q < NC) {
+        const double val = sym_pick<NC>(v, q);
+        if constexpr (COMBINE) slot[sidx * NC + q] = val;      // this warp's sum; joined with the other warps' after the tile
+        else sym_red_add(acc, idx0 + sidx * NC + q, val, fxe[K::window(q)]);
     }
 }
 
@@ -199,7 +177,8 @@ struct SymBveVel : NoSharedTable {
     }
     template <int T, int SB, int ORDER>
     __device__ static __forceinline__ void batch(const SymParams& p, const Tgt (&tg)[T], double (&a)[T][NA],
-                                                 const double* __restrict__ sm, double (&cb)[SB][NC], const SharedCtx&)
+                                                 const double* __restrict__ sm, double (&cb)[SB][NC], const SharedCtx&,
+                                                 const int rot)
     {
         constexpr int DN = ORDER & 1, AN = (ORDER >> 1) & 1, GS = (ORDER >> 2) & 3, CU = (ORDER >> 4) & 1, FENCE = (ORDER >> 5) & 1;
         constexpr int G = GS == 0 ? 1 : GS == 1 ? 2 : GS == 2 ? 4 : SB;
@@ -209,7 +188,7 @@ struct SymBveVel : NoSharedTable {
             double s[G][NS], d[G][T], r[G][T];
 #pragma unroll
             for (int u = 0; u < G; ++u) {
-                const double2* p2 = reinterpret_cast<const double2*>(sm + (g0 + u) * NS);
+                const double2* p2 = reinterpret_cast<const double2*>(sm + ((g0 + u) ^ rot) * NS);     // this lane's u-th source (sym_reduce_red)
 #pragma unroll
                 for (int q = 0; q < NS / 2; ++q) {
                     const double2 v = p2[q];
@@ -286,7 +265,9 @@ struct SymBveVel : NoSharedTable {
                     for (int u = 0; u < G; ++u) cb[g0 + u][2] = fma(r[u][t], tg[t].pz, cb[g0 + u][2]);
                 }
             }
-            if constexpr (FENCE != 0) sched_fence(s[0][0]);
+            // (the lanes' records differ, and a branch on lane-dependent data would make ptxas guard the shuffles that
+            // follow against divergence -- the fence tests a warp-uniform load)
+            if constexpr (FENCE != 0) sched_fence(sm[g0 * NS]);
         }
     }
     // as BveVelT::group<T, true>
@@ -333,11 +314,12 @@ struct SymBveStream : LogSharedTable<32> {
     // batch (see sched_fence); a retry per batch measured 5 % slower (profiles/r02b_ab_paths.log).
     template <int T, int SB, int ORDER>
     __device__ static __forceinline__ void batch(const SymParams& p, const Tgt (&tg)[T], double (&a)[T][NA],
-                                                 const double* __restrict__ sm, double (&cb)[SB][NC], const SharedCtx& sc)
+                                                 const double* __restrict__ sm, double (&cb)[SB][NC], const SharedCtx& sc,
+                                                 const int rot)
     {
 #pragma unroll
         for (int u = 0; u < SB; ++u) {
-            const double2* p2 = reinterpret_cast<const double2*>(sm + u * NS);
+            const double2* p2 = reinterpret_cast<const double2*>(sm + (u ^ rot) * NS);     // this lane's u-th source (sym_reduce_red)
             const double2 v0 = p2[0], v1 = p2[1], v2 = p2[2];
             double d[T], l[T];
             unsigned worst = 0;
@@ -405,12 +387,13 @@ struct SymBveVelStream : LogSharedTable<32> {
     }
     template <int T, int SB, int ORDER>
     __device__ static __forceinline__ void batch(const SymParams& p, const Tgt (&tg)[T], double (&a)[T][NA],
-                                                 const double* __restrict__ sm, double (&cb)[SB][NC], const SharedCtx& sc)
+                                                 const double* __restrict__ sm, double (&cb)[SB][NC], const SharedCtx& sc,
+                                                 const int rot)
     {
 #pragma unroll
         for (int u = 0; u < SB; ++u) {
             double s[NS], d[T], r[T], l[T];
-            const double2* p2 = reinterpret_cast<const double2*>(sm + u * NS);
+            const double2* p2 = reinterpret_cast<const double2*>(sm + (u ^ rot) * NS);     // this lane's u-th source (sym_reduce_red)
 #pragma unroll
             for (int q = 0; q < NS / 2; ++q) {
                 const double2 v = p2[q];
@@ -483,11 +466,14 @@ struct SymBveVelStream : LogSharedTable<32> {
 // dynamic shared memory: [2 tiles][K::KS table][2 mbarriers] and, with COMBINE, [2][warps][TS][NC] per-warp source sums:
 // the warps' sums for a tile are added in warp order after the tile and ONE RED per (CTA, source, component) is
 // issued instead of one per warp (a quarter of the atomics with 128 threads)
-template <class K, int T, int BLOCK, int SB, int MINB, int ORDER = 0, bool COMBINE = false>
+// TS: sources per shared-memory tile (SymGeom's ntiles and chunk_tiles count tiles of TS); the kernels that carry the
+// 64 KB log table take tiles shorter than kTile so that the combine buffers fit beside it with two CTAs per SM.
+template <class K, int T, int BLOCK, int SB, int MINB, int ORDER = 0, bool COMBINE = false, int TS = kTile>
 __global__ void __launch_bounds__(BLOCK, MINB)
 sym_kernel(const SymParams prm, const SymGeom g, const double* __restrict__ src, double* __restrict__ acc)
 {
-    constexpr int NS = K::NS, NA = K::NA, NC = K::NC, TS = kTile, TB = BLOCK * T, DT = TB / TS;
+    constexpr int NS = K::NS, NA = K::NA, NC = K::NC, TB = BLOCK * T, DT = TB / TS;
+    static_assert(kTile % TS == 0, "records are padded to whole tiles of kTile");
     static_assert(NS % 2 == 0, "records are read as double2");
     static_assert(NA == NC, "one accumulator array for both directions");
     static_assert(TB % TS == 0, "a target block must be whole source tiles");
@@ -576,7 +562,7 @@ sym_kernel(const SymParams prm, const SymGeom g, const double* __restrict__ src,
 #pragma unroll 1
         for (int jb = 0; jb < TS; jb += SB) {
             double cb[SB][NC];
-            K::template batch<T, SB, ORDER>(prm, tg, a, sm + jb * NS, cb, sctx);
+            K::template batch<T, SB, ORDER>(prm, tg, a, sm + jb * NS, cb, sctx, sym_rot<SB>(lane));
             sym_reduce_red<K, SB, NC, COMBINE>(cb, lane, acc, ((size_t)k * TS + jb) * NC, fxe, mine + jb * NC);
         }
     };
@@ -617,11 +603,11 @@ sym_kernel(const SymParams prm, const SymGeom g, const double* __restrict__ src,
         }
 }
 
-template <class K, int T, int BLOCK, bool COMBINE = false>
+template <class K, int T, int BLOCK, bool COMBINE = false, int TS = kTile>
 constexpr size_t sym_smem_bytes()
 {
-    return 2 * size_t(kTile) * K::NS * sizeof(double) + sizeof(double) * K::KS + 2 * sizeof(uint64_t) +
-           (COMBINE ? 2 * size_t(BLOCK / 32) * kTile * K::NC * sizeof(double) : 0);
+    return 2 * size_t(TS) * K::NS * sizeof(double) + sizeof(double) * K::KS + 2 * sizeof(uint64_t) +
+           (COMBINE ? 2 * size_t(BLOCK / 32) * TS * K::NC * sizeof(double) : 0);
 }
 
 // Window of the fixed-point accumulators for one evaluation.  maxhi: high word of the largest |entry| of the source

@@ -41,15 +41,18 @@ constexpr int32_t kSymMinSources = 200000;
 constexpr int32_t kSymChunkTiles = 16;      // source tiles (of 256) per CTA of the triangle kernel
 constexpr int32_t kSymPanelBlocks = 256;    // target blocks per panel of its launch order (sym_kernel)
 
-template <class K, int T, int BLOCK, int SB, int MINB, int ORDER = 0, bool COMBINE = false>
+template <class K, int T, int BLOCK, int SB, int MINB, int ORDER = 0, bool COMBINE = false, int TS = kTile>
 inline int launch_sym(cudaStream_t st, const SymParams& prm, SymGeom g, const double* src, double* acc)
 {
     constexpr int TB = BLOCK * T;
     g.nblocks = (g.nsrc_pad + TB - 1) / TB;
+    g.ntiles *= kTile / TS;             // the caller counts tiles of kTile; the kernel tiles of TS
+    g.chunk_tiles *= kTile / TS;
     g.half_bin = 1 << (19 - kLogBits);
     g.panel_blocks = std::min<int32_t>(g.nblocks, rt().sym_panel_blocks);
     const int64_t npanels = (g.nblocks + g.panel_blocks - 1) / g.panel_blocks;
-    constexpr size_t smem = sym_smem_bytes<K, T, BLOCK, COMBINE>();
+    constexpr size_t smem = sym_smem_bytes<K, T, BLOCK, COMBINE, TS>();
+    static_assert(smem <= 227 * 1024, "shared memory of one CTA");
     const int64_t grid = npanels * g.panel_blocks * g.nchunks;
     if (grid <= 0 || grid > 0x7fffffffLL) return set_error(LPM_ERR_INVALID, "symmetric kernel grid %lld", (long long)grid);
     if (smem > 48 * 1024) {     // per device, as in launch_ds
@@ -57,11 +60,11 @@ inline int launch_sym(cudaStream_t st, const SymParams& prm, SymGeom g, const do
         int devid = 0;
         cudaGetDevice(&devid);
         if (devid < 0 || devid >= 64 || !configured[devid]) {
-            LPM_CUDA(cudaFuncSetAttribute(sym_kernel<K, T, BLOCK, SB, MINB, ORDER, COMBINE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            LPM_CUDA(cudaFuncSetAttribute(sym_kernel<K, T, BLOCK, SB, MINB, ORDER, COMBINE, TS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
             if (devid >= 0 && devid < 64) configured[devid] = true;
         }
     }
-    sym_kernel<K, T, BLOCK, SB, MINB, ORDER, COMBINE><<<(unsigned)grid, BLOCK, smem, st>>>(prm, g, src, acc);
+    sym_kernel<K, T, BLOCK, SB, MINB, ORDER, COMBINE, TS><<<(unsigned)grid, BLOCK, smem, st>>>(prm, g, src, acc);
     return LPM_OK;
 }
 
@@ -78,13 +81,13 @@ struct SymVel {
         p.x = xyz[0]; p.y = xyz[1]; p.z = xyz[2];
         p.R2 = a.sc[0] * a.sc[0];
     }
-    // 8 targets per thread, batches of 8 sources (two groups of 4, phase by phase, a scheduling fence after each group:
-    // statement order 43), the warps' source sums combined in shared memory: one fixed-point add per (CTA, source,
-    // component).  244 registers, two CTAs of 128 threads per SM.  Measured at icosTri 8 (profiles/r02b_ab_paths.log,
-    // r02c_ab_paths.log, r02e_order_sweep.log; the triangle kernel alone): this build 769 ms; the same unfenced
-    // (order 27): 790; batches of 4: 824; one source at a time, fenced (order 35): 848; warps not combined: 869;
-    // 6 targets per thread at 2 / 3 CTAs per SM: 837 / 859; 4 targets, 3 CTAs: 881.  The 31 other statement orders
-    // of the sweep lie within 783 ... 800 ms.
+    // 8 targets per thread, batches of 8 sources taken in the lane-rotated order of sym_reduce_red (two groups of 4, phase by
+    // phase: statement order 11), the warps' source sums combined in shared memory: one fixed-point add per (CTA, source,
+    // component).  246 registers, two CTAs of 128 threads per SM.  Measured at icosTri 8, the triangle kernel alone:
+    // 729-732 ms (profiles/r02m_ab_builds.log; with a scheduling fence after each group, order 43: 737; orders 27 / 59: 733 /
+    // 738).  Before the rotated order (selects in the warp reduction; profiles/r02b_ab_paths.log, r02c_ab_paths.log,
+    // r02e_order_sweep.log): order 43 765-769 ms, unfenced 790; batches of 4: 824; one source at a time, fenced: 848; warps
+    // not combined: 869; 6 targets per thread at 2 / 3 CTAs per SM: 837 / 859; 4 targets, 3 CTAs: 881.
     static int launch(cudaStream_t st, const SymParams& prm, const SymGeom& g, const double* src, double* acc)
     {
 #ifdef LPM_SYM_ORDER_SWEEP      // tools/order_sweep.py: one instantiation per statement order behind lpm_tune("sym_vel_order")
@@ -97,7 +100,7 @@ struct SymVel {
             default: break;
         }
 #endif
-        return launch_sym<SK, 8, 128, 8, 1, 43, true>(st, prm, g, src, acc);
+        return launch_sym<SK, 8, 128, 8, 1, 11, true>(st, prm, g, src, acc);
     }
     static void finalize(cudaStream_t st, const MaskPlan& mp, const double* src, const double* acc, const Outs<3>& out)
     {
@@ -116,12 +119,14 @@ struct SymStream {
         p.x = xyz[0]; p.y = xyz[1]; p.z = xyz[2];
         p.R2 = a.sc[0] * a.sc[0];
     }
-    // 64 KB table per CTA, so two CTAs per SM: 256 threads under a 128-register cap, 4 targets per thread, batches
-    // of 4 sources, a retry branch per source (1131 ms at icosTri 8 against 1187 for 128 threads with ~155 registers
-    // and a retry branch per batch: profiles/r02b_ab_paths.log)
+    // 64 KB table per CTA, two CTAs per SM: 8 targets per thread, 128 threads, batches of 8 sources in the rotated order, a
+    // retry branch per source, and source tiles of 128 so that the combine buffers (16 KB) fit beside the table: 933 ms for
+    // the triangle at icosTri 8 (profiles/r02m_ab_builds.log).  The same with selects in the reduction: 945; batches of 4:
+    // 963; 4 targets per thread at 256 threads (128-register cap), combined: 1010 (rotated: 986; batches of 8, which spill:
+    // 1035; tiles of 64: 1008; one CTA of 512 threads: 1015); not combined (round 2's first default): 1134 (rotated: 1125).
     static int launch(cudaStream_t st, const SymParams& prm, const SymGeom& g, const double* src, double* acc)
     {
-        return launch_sym<SK, 4, 256, 4, 2, 1>(st, prm, g, src, acc);
+        return launch_sym<SK, 8, 128, 8, 2, 1, true, 128>(st, prm, g, src, acc);
     }
     static void finalize(cudaStream_t st, const MaskPlan& mp, const double*, const double* acc, const Outs<2>& out)
     {
@@ -130,8 +135,11 @@ struct SymStream {
 };
 
 // The end of an RK4 step (src/SphereBVESolver.f90:345-352): velocity and stream functions of the new state in one
-// pass (SymBveVelStream / BveVelStream).  4 targets per thread, 128 threads, batches of 4 sources, a retry branch per
-// source; 64 KB log table + 32 KB of tiles per CTA: two CTAs per SM.
+// pass (SymBveVelStream / BveVelStream).  4 targets per thread, 128 threads, batches of 4 sources in the rotated order, a
+// retry branch per source; 64 KB log table + source tiles of 64 (8 KB) + 20 KB of combine buffers per CTA: two CTAs per
+// SM.  Triangle kernel at icosTri 8 (profiles/r02m_ab_builds.log): 1690 ms; with selects in the reduction 1803; not
+// combined, tiles of 256 (round 2's first version) 1947 (rotated: 1836); one CTA of 256 threads per SM, tiles of 128,
+// combined 1831 (rotated: 1705), not combined 2090.
 struct SymVelStream {
     using Op = OpBveVelStream;
     using SK = SymBveVelStream;
@@ -146,7 +154,7 @@ struct SymVelStream {
     }
     static int launch(cudaStream_t st, const SymParams& prm, const SymGeom& g, const double* src, double* acc)
     {
-        return launch_sym<SK, 4, 128, 4, 2, 0>(st, prm, g, src, acc);
+        return launch_sym<SK, 4, 128, 4, 2, 0, true, 64>(st, prm, g, src, acc);
     }
     static void finalize(cudaStream_t st, const MaskPlan& mp, const double* src, const double* acc, const Outs<5>& out)
     {
