@@ -11,7 +11,15 @@ lane-rotated source order, now unconditional in sym_reduce_red):
              3 <8,128,8,2,-,comb,128>  4 = 1 with tiles of 64  5 <4,512,4,1,-,comb,128>  6 = 1 rot  7 = 0 rot
              8 = 3 rot (won)  9 <4,256,8,2,-,comb,128> rot
   fused end  0 <4,128,4,2,0,no,256> (the default until then)  1 <4,128,4,2,0,comb,64>  2 <4,256,4,1,0,comb,128>
-             3 <4,256,4,1,0,no,256>  4 = 1 rot (won)  5 = 0 rot  6 = 2 rot"""
+             3 <4,256,4,1,0,no,256>  4 = 1 rot (won)  5 = 0 rot  6 = 2 rot
+profiles/r02n_ab_builds.log (this version of the script; none of these beat the defaults and all were deleted):
+  "sym_vel_build"        0 order 11 (default)  1 order 43 + the last group's transposed sums first (the warp reduction overlaps
+                         that group's own sums), fence after the first group only  2 the same in groups of 2 sources
+                         3 = 1 with the batch loop unrolled by 2  4 order 43 unrolled by 2  5 order 11, last group's
+                         transposed sums first  6 groups of 2 sources, fenced
+  "ds_stream_T"          0 default (4 targets per thread, 2 CTAs of 256 threads)  8: 8 targets, one CTA per SM (ds_kernel<BveStream>)
+  "sym_velstream_build"  0 default  1 transposed sums before own sums per source
+  "ds_velstream_T"       0 default (4)  6 / 8 targets per thread (ds_kernel<BveVelStream>)"""
 import os, sys, time
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np
@@ -24,7 +32,8 @@ def lst(i, default):
 
 
 L = int(sys.argv[1]) if len(sys.argv) > 1 else 8
-vel, stream, velstream = lst(2, "0,1,2,3,4"), lst(3, "0,1,2,3,4,5,6,7,8,9"), lst(4, "0,1,2,3,4,5,6")
+vel, stream, velstream = lst(2, "0,1,2,3,4,5,6"), lst(3, "0,8"), lst(4, "0,1,0")
+steps_T = lst(5, "0,6,8")      # "ds_velstream_T" of the RK4 steps, paired with the velstream builds
 api.init(1)
 api.set_profiling(True)
 api.tune("sym_min_sources", 0)
@@ -32,7 +41,7 @@ m = mesh.PolyMesh2d(mesh.ICOS_TRI_SPHERE_SEED, L)
 z = problems.rossby_haurwitz54(m)
 av = problems.abs_vorticity(m, z, 2 * np.pi)
 for name, key, builds, fn in (("bve_velocity", "sym_vel_build", vel, lambda: api.bve_velocity(m.x, m.y, m.z, z, m.area, m.is_active, 1.0)),
-                              ("bve_stream", "sym_stream_build", stream, lambda: api.bve_stream(m.x, m.y, m.z, z, av, m.area, m.is_active, 1.0))):
+                              ("bve_stream", "ds_stream_T", stream, lambda: api.bve_stream(m.x, m.y, m.z, z, av, m.area, m.is_active, 1.0))):
     ref = None
     for b in builds:
         api.tune(key, b)
@@ -46,15 +55,17 @@ for name, key, builds, fn in (("bve_velocity", "sym_vel_build", vel, lambda: api
             ref = out
         scale = max(np.abs(r).max() for r in ref)
         diff = max(np.abs(a - c).max() for a, c in zip(out, ref)) / scale
-        print(f"L{L} {name} build {b}: " + " | ".join(", ".join(f"{k} {v:.2f}" for k, v in t.items()) for t in ts) +
-              f" ms; whole sum {api.last_sum_ms():.2f} ms; max diff from build {builds[0]}: {diff:.2e}", flush=True)
+        print(f"L{L} {name} {key} {b}: " + " | ".join(", ".join(f"{k} {v:.2f}" for k, v in t.items()) for t in ts) +
+              f" ms; whole sum {api.last_sum_ms():.2f} ms; max diff from {builds[0]}: {diff:.2e}", flush=True)
     if builds:
         api.tune(key, 0)
 if velstream:
     dt = 0.01 * float(np.sqrt(6144.0 / m.n_active))
     ref = None
-    for i, b in enumerate([velstream[0]] + velstream):        # the first step also warms the solver's buffers up
+    combos = list(zip(velstream, steps_T))
+    for i, (b, T) in enumerate([combos[0]] + combos):        # the first step also warms the solver's buffers up
         api.tune("sym_velstream_build", b)
+        api.tune("ds_velstream_T", T)
         sph = solvers.BVEMesh(m, z, 1.0, 2 * np.pi)
         sph.SetVelocityOnMesh()
         sol = solvers.BVESolver(sph)
@@ -71,7 +82,8 @@ if velstream:
         if ref is None:
             ref = out
         diff = max(np.abs(a - c).max() / max(np.abs(c).max(), 1e-300) for a, c in zip(out, ref))
-        print(f"L{L} RK4 step, fused end build {b}: step {ms:.1f} ms; kernels " +
-              ", ".join(f"{k} {c}x {t / c:.1f}" for k, (c, t) in ks.items()) + f" ms; max diff from build {velstream[0]}: {diff:.2e}", flush=True)
+        print(f"L{L} RK4 step, sym_velstream_build {b}, ds_velstream_T {T}: step {ms:.1f} ms; kernels " +
+              ", ".join(f"{k} {c}x {t / c:.1f}" for k, (c, t) in ks.items()) + f" ms; max diff from the first: {diff:.2e}", flush=True)
     api.tune("sym_velstream_build", 0)
+    api.tune("ds_velstream_T", 0)
 api.tune("sym_min_sources", 200000)
