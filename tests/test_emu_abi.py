@@ -47,10 +47,12 @@ def test_default_paths_on_emulator(emu_env):
 
 def test_symmetric_paths_on_emulator(emu_env):
     """The pair-symmetric path (tests/test_sym_gpu.py lowers its size threshold) through the real host code:
-    velocity, stream functions, fixed-point accumulation, the coincident-particle case."""
+    velocity, stream functions (several target blocks, so tiles above the diagonal; a radius whose logarithms leave the
+    table's default window), fixed-point accumulation, panels and chunks of the launch order (with the stream kernel's
+    shorter source tiles), the coincident-particle case."""
     tail = _run(emu_env, ["tests/test_sym_gpu.py", "-k",
                           "(velocity_random_ragged and (127 or 513 or 1025 or 3000 or 3-0.5)) "
-                          "or (stream_random_ragged and (513 or 3-0.5)) "
+                          "or (stream_random_ragged and (513 or 3-0.5 or 4099 or 6000)) or (launch_geometry and 2-2) "
                           "or (fixed_point and not 6371000 and not 3e-07) or coincident"], 900)
     assert " passed" in tail and "failed" not in tail, tail
 
