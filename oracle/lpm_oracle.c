@@ -17,13 +17,19 @@
  *   - PSE Laplacian (sphere): pinned by the reference's own regression
  *     thresholds, tests/SpherePSEConvTest.f90:373-390 (checked in
  *     tests/test_oracle_golden.py).
- *   - BVE / planar / beta-plane velocity and stream-function sums:
- *     "parity unpinned" -- the reference holds no test, golden vector or
- *     fixture that asserts any value of these sums, and the reference cannot
- *     be compiled in this environment (no Fortran compiler, no MPI).  They
- *     are checked only against the analytic solutions the reference's own
- *     examples log (solid-body rotation, examples/BVESolidBody.f90:231-243;
- *     Rossby-Haurwitz eigenfunction) to discretisation accuracy.
+ *   - Every sum and the three RK4 steps (BVE / planar / beta-plane velocity,
+ *     the mesh-side twins, the stream functions, the PSE Laplacians,
+ *     LoadBalance): pinned BIT FOR BIT against the reference's own source text,
+ *     executed by the Fortran-subset interpreter oracle/fortran_subset.py on
+ *     small cases (oracle/make_refsrc_fixtures.py -> tests/golden/refsrc_*.npz,
+ *     checked by tests/test_refsrc_golden.py).  That removes the hand-written
+ *     restatement from the pin; it is not a compiled run of the reference (no
+ *     Fortran compiler, no MPI in this environment): FMA contraction by a
+ *     compiler and a different libm are outside what it can show.
+ *   - In addition the BVE / planar / beta-plane sums are checked against the
+ *     analytic solutions the reference's own examples log (solid-body
+ *     rotation, examples/BVESolidBody.f90:231-243; Rossby-Haurwitz
+ *     eigenfunction) to discretisation accuracy.
  *
  * Index convention: all ranges are 0-based half-open [ibeg, iend); the
  * Fortran slice indexStart(r)..indexEnd(r) is [indexStart-1, indexEnd).
