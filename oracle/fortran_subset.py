@@ -13,7 +13,8 @@ left-to-right evaluation of operators of equal precedence, integer division, do 
 assignment, argument association, and the libm intrinsics (Python's math module calls the same glibc functions a
 gfortran build links).  It is not a compiler: a gfortran build may still differ from these vectors where the compiler
 contracts a*b+c into an FMA (-march=native) or where libm versions differ; on baseline x86-64 without -ffast-math
-gfortran evaluates these expressions as written (parentheses are protected, no reassociation).
+gfortran evaluates these expressions as written (parentheses are protected, no reassociation) -- and that is how the
+reference builds itself: CMakeLists.txt:27 sets "-O3 -fopenmp -ffree-form -cpp" for gfortran, no -march, no -ffast-math.
 
 Semantics implemented
   values        int, float (IEEE double; Python floats), bool, FArr (rank-1 array view: storage list, offset, length,
@@ -23,8 +24,10 @@ Semantics implemented
                 is repeated multiplication (what gfortran emits for small n); array operands work element by element;
                 division by zero, log(0), overflow give the IEEE result instead of a Python exception.
   sum(a)        elements added in index order starting from the first (gfortran's inline expansion).
-  statements    assignment (scalar, element, section, whole array, component), do / enddo (with step), if / else if /
-                else / endif, one-line if, call, return; declarations only allocate local arrays of constant size
+  statements    assignment (scalar, element, section, whole array, component), do / enddo (with step; cycle, exit), if /
+                else if / else / endif, one-line if, call, return, allocate; rank-2 arrays as far as the sphere operators'
+                3 x 3 projection needs them (elements, whole-array assignment, MATMUL(matrix, vector) in gfortran's inline
+                order); procedure dummy arguments; declarations only allocate local arrays of constant size
                 (dimension(3) :: xi) and evaluate parameter constants; "!$acc" lines are comments; calls to MPI_BCAST,
                 LogMessage and the like are no-ops (one rank: numProcs = 1, procRank = 0 -- a broadcast to oneself).
   procedures    looked up by name in the files given to Program(); dummy arguments are associated by reference for arrays
@@ -104,6 +107,46 @@ class FArr:
             self.v[self.off:self.off + self.n] = val.tolist()       # the right-hand side is evaluated first
         else:
             self.v[self.off:self.off + self.n] = [val] * self.n
+
+
+class FMat:
+    """Rank-2 array with constant bounds 1..n1, 1..n2 (column-major), as far as the path needs one: the 3 x 3 projection
+    of the sphere operators (element access, whole-array assignment, MATMUL with a vector)."""
+    __slots__ = ("v", "n1", "n2")
+
+    def __init__(self, n1, n2, v=None):
+        self.n1, self.n2 = n1, n2
+        self.v = [0.0] * (n1 * n2) if v is None else v
+
+    def _k(self, i, j):
+        if not (1 <= i <= self.n1 and 1 <= j <= self.n2):
+            raise FortranError(f"index ({i}, {j}) outside a {self.n1} x {self.n2} array")
+        return (i - 1) + (j - 1) * self.n1
+
+    def get(self, i, j):
+        return self.v[self._k(i, j)]
+
+    def set(self, i, j, x):
+        self.v[self._k(i, j)] = x
+
+    def assign(self, val):
+        if isinstance(val, FMat):
+            if (val.n1, val.n2) != (self.n1, self.n2):
+                raise FortranError("array assignment of another shape")
+            self.v[:] = list(val.v)
+        else:
+            self.v[:] = [val] * len(self.v)
+
+
+def _matmul(a, b):
+    """MATMUL(matrix, vector) as gfortran expands it inline: c = 0; do k; do i; c(i) = c(i) + a(i,k) * b(k)."""
+    if not isinstance(a, FMat) or not isinstance(b, FArr) or a.n2 != b.n:
+        raise FortranError("matmul: only matrix x vector is supported")
+    bv, c = b.tolist(), [0.0] * a.n1
+    for k in range(a.n2):
+        for i in range(a.n1):
+            c[i] = c[i] + a.v[i + k * a.n1] * bv[k]
+    return FArr(c)
 
 
 # ---- source text -> logical lines ------------------------------------------------------------------------------------
@@ -538,6 +581,14 @@ class _Return(Exception):
     pass
 
 
+class _Cycle(Exception):
+    pass
+
+
+class _Exit(Exception):
+    pass
+
+
 def _idiv(a, b):
     q = abs(a) // abs(b)
     return q if (a >= 0) == (b >= 0) else -q
@@ -611,15 +662,17 @@ INTRINSICS = {
     "mod": lambda a, b: _elementwise(lambda p, q: math.fmod(p, q) if isinstance(p, float) or isinstance(q, float) else p - _idiv(p, q) * q, a, b),
     "sum": _sum, "size": lambda a, dim=None: a.n, "allocated": lambda a: a is not None, "associated": lambda a: a is not None,
     "dot_product": lambda a, b: _sum(_elementwise(lambda p, q: p * q, a, b)),
-    "maxval": lambda a: max(a.tolist()), "minval": lambda a: min(a.tolist()),
+    "maxval": lambda a: max(a.tolist()), "minval": lambda a: min(a.tolist()), "matmul": _matmul,
+    "trim": lambda a: a, "present": lambda a: a is not None,
 }
 
 
 class Program:
     """Procedures of the given reference source files (paths relative to REFERENCE_ROOT), ready to call()."""
 
-    def __init__(self, files, root=None, constants_from=("src/TypeDefs.f90",), num_procs=1, proc_rank=0):
+    def __init__(self, files, root=None, constants_from=("src/TypeDefs.f90",), num_procs=1, proc_rank=0, ignore_calls=()):
         self.root = REFERENCE_ROOT if root is None else root
+        self.ignore_calls = IGNORED_CALLS | {c.lower() for c in ignore_calls}   # subroutines off the path (logging, MPI, ...)
         self.files, self.procs, self.by_file = [], {}, {}
         self.globals = {"numprocs": num_procs, "procrank": proc_rank, "mpi_double_precision": 0, "mpi_comm_world": 0,
                         "mpi_integer": 0, "mpi_sum": 0}
@@ -675,12 +728,12 @@ class Program:
                 (self.globals if module_level else env)[name] = val
             elif dims is not None and name not in dummies and not module_level:
                 d = _split_top(dims)
-                if len(d) == 1 and ":" not in d[0]:
+                if all(":" not in x for x in d) and len(d) in (1, 2):
                     try:
-                        n = self._eval(parse_expr(d[0]), env, file)
+                        n = [int(self._eval(parse_expr(x), env, file)) for x in d]
                     except (KeyError, FortranError):
                         continue
-                    env[name] = FArr.zeros(int(n))
+                    env[name] = FArr.zeros(n[0]) if len(n) == 1 else FMat(n[0], n[1])
 
     # -- expressions
     def _eval(self, e, env, file=None):
@@ -749,6 +802,12 @@ class Program:
         raise FortranError(f"cannot evaluate {e!r}")
 
     def _index(self, val, args, env, file):
+        if isinstance(val, FMat):
+            if len(args) != 2 or any(a[0] == "sec" for a in args):
+                raise FortranError("rank-2 arrays: element access only")
+            return val.get(self._eval(args[0], env, file), self._eval(args[1], env, file))
+        if callable(val):                           # a procedure dummy argument (topoFn)
+            return val(*[self._eval(a, env, file) for a in args])
         if not isinstance(val, FArr):
             raise FortranError(f"subscript on a non-array value {val!r}")
         if len(args) != 1:
@@ -774,7 +833,11 @@ class Program:
         elif args is not None:
             val = self._call(self._find(name, file, len(args)), args, env, file)
         else:
-            raise KeyError(name)
+            try:
+                proc = self._find(name, file)       # a procedure name passed as an actual argument
+            except FortranError:
+                raise KeyError(name)
+            val = lambda *a, _p=proc: self._invoke(_p, list(a))
         for comp, cargs in parts[1:]:
             if not isinstance(val, Obj):
                 raise FortranError(f"component {comp} of a non-derived-type value")
@@ -801,6 +864,11 @@ class Program:
         args = parts[-1][1]
         if args is not None:
             target = holder[key]
+            if isinstance(target, FMat):
+                if len(args) != 2:
+                    raise FortranError("rank-2 arrays: element access only")
+                target.set(self._eval(args[0], env, file), self._eval(args[1], env, file), value)
+                return
             if len(args) != 1:
                 raise FortranError("only rank-1 arrays are supported")
             a = args[0]
@@ -813,7 +881,7 @@ class Program:
                 target.set(self._eval(a, env, file), value)
             return
         cur = holder.get(key)
-        if isinstance(cur, FArr):
+        if isinstance(cur, (FArr, FMat)):
             cur.assign(value)                       # whole-array assignment into existing storage
         elif isinstance(value, FArr):
             holder[key] = FArr(value.tolist())      # allocation on assignment (a copy)
@@ -834,9 +902,15 @@ class Program:
                 i = lo
                 while (i <= hi) if step > 0 else (i >= hi):
                     env[st[2]] = i
-                    self._exec(st[6], env, file)
+                    try:
+                        self._exec(st[6], env, file)
+                    except _Cycle:
+                        pass
+                    except _Exit:
+                        break
                     i += step
-                env[st[2]] = i
+                else:
+                    env[st[2]] = i
             elif k == "while":
                 while self._eval(st[2], env, file):
                     self._exec(st[3], env, file)
@@ -849,18 +923,26 @@ class Program:
                     if st[3] is not None:
                         self._exec(st[3], env, file)
             elif k == "call":
-                if st[2] in IGNORED_CALLS:
+                if st[2] in self.ignore_calls:
                     continue
                 self._call(self._find(st[2], file, len(st[3])), st[3], env, file)
             elif k == "allocate":               # allocate(a(n)): a fresh array of n zeros, lower bound 1
                 parts = st[2][1]
                 name, args = parts[-1]
-                if args is None or len(args) != 1 or args[0][0] == "sec":
+                if args is None or len(args) != 1:
                     raise FortranError(f"line {st[1]}: unsupported allocate")
                 holder = env if len(parts) == 1 else self._ref(parts[:-1], env, file).f
-                holder[name] = FArr.zeros(int(self._eval(args[0], env, file)))
+                if args[0][0] == "sec":             # allocate(a(lo:hi))
+                    lo, hi = int(self._eval(args[0][1], env, file)), int(self._eval(args[0][2], env, file))
+                    holder[name] = FArr.zeros(hi - lo + 1, lb=lo)
+                else:
+                    holder[name] = FArr.zeros(int(self._eval(args[0], env, file)))
             elif k == "return":
                 raise _Return()
+            elif k == "cycle":
+                raise _Cycle()
+            elif k == "exit":
+                raise _Exit()
             elif k in ("decl", "continue"):
                 continue
             else:
@@ -873,13 +955,13 @@ class Program:
         for dummy, a in zip(proc.args, args):
             val = self._eval(a, env, file)
             local[dummy] = val
-            if not isinstance(val, (FArr, Obj)) and a[0] == "ref" and (a[1][-1][1] is None or a[1][-1][1][0][0] != "sec"):
+            if not isinstance(val, (FArr, FMat, Obj)) and not callable(val) and a[0] == "ref" and (a[1][-1][1] is None or a[1][-1][1][0][0] != "sec"):
                 is_var = a[1][0][0] in env or len(a[1]) > 1
                 if is_var:
                     writeback.append((dummy, a))
         self._run(proc, local)
         for dummy, a in writeback:
-            if dummy in local and not isinstance(local[dummy], (FArr, Obj)):
+            if dummy in local and not isinstance(local[dummy], (FArr, FMat, Obj)) and not callable(local[dummy]):
                 self._assign(a, local[dummy], env, file)
         if proc.kind == "function":
             return local[proc.result]
@@ -898,6 +980,11 @@ class Program:
             self._exec(proc.body, local, proc.file)
         except _Return:
             pass
+
+    def _invoke(self, proc, values):
+        local = dict(zip(proc.args, values))
+        self._run(proc, local)
+        return local[proc.result] if proc.kind == "function" else None
 
     def call(self, name, *actuals, file=None):
         """Calls procedure `name` with Python values (FArr / Obj / int / float / bool); returns the function result or,

@@ -17,9 +17,11 @@
  *   - PSE Laplacian (sphere): pinned by the reference's own regression
  *     thresholds, tests/SpherePSEConvTest.f90:373-390 (checked in
  *     tests/test_oracle_golden.py).
- *   - Every sum and the three RK4 steps (BVE / planar / beta-plane velocity,
- *     the mesh-side twins, the stream functions, the PSE Laplacians,
- *     LoadBalance): pinned BIT FOR BIT against the reference's own source text,
+ *   - Every sum and RK4 step (BVE / planar / beta-plane velocity, the
+ *     mesh-side twins, the stream functions, the PSE Laplacians and the other
+ *     PSE operators, the shallow-water right-hand sides and the planar
+ *     shallow-water step, TotalKE / TotalEnstrophy, LoadBalance): pinned BIT
+ *     FOR BIT against the reference's own source text,
  *     executed by the Fortran-subset interpreter oracle/fortran_subset.py on
  *     small cases (oracle/make_refsrc_fixtures.py -> tests/golden/refsrc_*.npz,
  *     checked by tests/test_refsrc_golden.py).  That removes the hand-written
@@ -690,7 +692,14 @@ static void sphere_project(const double x[3], const double g[3], double out[3])
     P[0][0] = 1.0 - x[0] * x[0]; P[1][0] = -x[1] * x[0]; P[2][0] = -x[2] * x[0];
     P[0][1] = -x[0] * x[1]; P[1][1] = 1.0 - x[1] * x[1]; P[2][1] = -x[2] * x[1];
     P[0][2] = -x[0] * x[2]; P[1][2] = -x[1] * x[2]; P[2][2] = 1.0 - x[2] * x[2];
-    for (int r = 0; r < 3; ++r) out[r] = P[r][0] * g[0] + P[r][1] * g[1] + P[r][2] * g[2];   /* MATMUL */
+    /* MATMUL as gfortran evaluates it (inline expansion and libgfortran alike): the result is zeroed, then
+     * c(i) = c(i) + a(i,k) * b(k) for k = 1, 2, 3 -- the leading 0.0 only matters for the sign of a zero result
+     * (found by tests/test_refsrc_golden.py against the interpreted reference text) */
+    for (int r = 0; r < 3; ++r) {
+        double c = 0.0;
+        for (int k = 0; k < 3; ++k) c = c + P[r][k] * g[k];
+        out[r] = c;
+    }
 }
 
 /* src/PSEDirectSum.f90:128-168  PSE{Plane,Sphere}InterpolateScalar at m

@@ -14,6 +14,7 @@ procedures take (a mesh's particles, fields, an MPISetup for one rank) and calls
 Inputs are small meshes from the repo's mesh generator (reference refinement order) and ragged random sets; the
 interpreter costs tens of microseconds per pair, so the sizes are a few hundred particles.
 """
+import math
 import os
 import sys
 import time
@@ -248,6 +249,115 @@ def main():
               field(n, f), lap, ms)
     save("pse_plane_quad2", prog.where("PSEPlaneLaplacianAtParticles"), x=q.x, y=q.y, f=f, area=q.area,
          mask=q.is_active.astype(bool), eps=eps, lap=N(lap.scalar))
+    # ---- the other PSE operators (src/PSEDirectSum.f90:128-456, 537-579) ---------------------------------------------------
+    prog = F.Program(["src/PSEDirectSum.f90", "src/SphereGeometry.f90", "src/Particles.f90", "src/Field.f90", "src/MPISetup.f90"])
+    q = M.PolyMesh2d(M.QUAD_RECT_SEED, 2, 3.0)
+    n, eps = q.n, float(q.max_edge_length ** 0.75)
+    ms = mpi_setup(prog, n)
+    pse = F.Obj(eps=eps)
+    qmesh = F.Obj(particles=particles(q.x, q.y, None, q.area, q.is_active.astype(bool)))
+    f = problems.colliding_dipoles(q)
+    rng = np.random.default_rng(21)
+    tx, ty = rng.uniform(-2, 2, 24), rng.uniform(-2, 2, 24)
+    interp = [prog.call("PSEPlaneInterpolateScalar", pse, qmesh, field(n, f), F.FArr([float(a), float(b), 0.0])) for a, b in zip(tx, ty)]
+    grad = field(n, ndim=2)
+    prog.call("PSEPlaneGradientAtParticles", pse, qmesh, field(n, f), grad, ms)
+    second = field(n, ndim=3)
+    prog.call("PSEPlaneSecondPartialsAtParticles", pse, qmesh, grad, second, ms)
+    uu, vv = np.sin(q.x) * np.cos(0.5 * q.y), np.cos(0.7 * q.x) + q.y * q.y
+    vec = field(n, ndim=2)
+    vec.xComp.assign(A(uu))
+    vec.yComp.assign(A(vv))
+    dd = field(n)
+    prog.call("PSEPlaneDoubleDotProductAtParticles", pse, qmesh, vec, dd, ms)
+    save("pse_ops_plane_quad2", prog.where("PSEPlaneInterpolateScalar") + ", " + prog.where("PSEPlaneGradientAtParticles") + ", " +
+         prog.where("PSEPlaneSecondPartialsAtParticles") + ", " + prog.where("PSEPlaneDoubleDotProductAtParticles"),
+         x=q.x, y=q.y, f=f, area=q.area, mask=q.is_active.astype(bool), eps=eps, tx=tx, ty=ty, interp=np.array(interp),
+         gx=N(grad.xComp), gy=N(grad.yComp), dxx=N(second.xComp), dxy=N(second.yComp), dyy=N(second.zComp), u=uu, v=vv,
+         double_dot=N(dd.scalar))
+    m = M.PolyMesh2d(M.ICOS_TRI_SPHERE_SEED, 1)
+    n, R, eps = m.n, 1.0, float(m.max_edge_length ** 0.6)
+    prog.globals["sphereradius"] = R
+    ms = mpi_setup(prog, n)
+    pse = F.Obj(eps=eps)
+    smesh = F.Obj(particles=particles(m.x, m.y, m.z, m.area, m.is_active.astype(bool)))
+    f = problems.rossby_haurwitz54(m)
+    pts = rng.normal(size=(16, 3))
+    pts /= np.linalg.norm(pts, axis=1)[:, None]
+    interp = [prog.call("PSESphereInterpolateScalar", pse, smesh, field(n, f), F.FArr([float(c) for c in pnt])) for pnt in pts]
+    grad = field(n, ndim=3)
+    prog.call("PSESphereGradientAtParticles", pse, smesh, field(n, f), grad, ms)
+    uu, vv, ww = -m.y + 0.3 * m.z * m.x, m.x + 0.2 * m.y * m.z, 0.1 * m.x * m.y
+    vec = field(n, ndim=3)
+    for comp, val in zip((vec.xComp, vec.yComp, vec.zComp), (uu, vv, ww)):
+        comp.assign(A(val))
+    dd, dv = field(n), field(n)
+    prog.call("PSESphereDoubleDotProductAtParticles", pse, smesh, vec, dd, ms)
+    prog.call("PSESphereDivergenceAtParticles", pse, smesh, vec, dv, ms)
+    save("pse_ops_sphere_icos1", prog.where("PSESphereInterpolateScalar") + ", " + prog.where("PSESphereGradientAtParticles") + ", " +
+         prog.where("PSESphereDoubleDotProductAtParticles") + ", " + prog.where("PSESphereDivergenceAtParticles"),
+         x=m.x, y=m.y, z=m.z, f=f, area=m.area, mask=m.is_active.astype(bool), eps=eps, R=R, tx=pts[:, 0], ty=pts[:, 1],
+         tz=pts[:, 2], interp=np.array(interp), gx=N(grad.xComp), gy=N(grad.yComp), gz=N(grad.zComp), u=uu, v=vv, w=ww,
+         double_dot=N(dd.scalar), divergence=N(dv.scalar))
+
+    # ---- shallow water: the fused right-hand sides and the planar RK4 step ------------------------------------------------
+    prog = F.Program(["src/SWEPlaneSolver.f90", "src/SphereSWESolver.f90", "src/PSEDirectSum.f90", "src/SphereGeometry.f90",
+                      "src/MPISetup.f90"], ignore_calls=("setbottomheightonmesh",))
+    q = M.PolyMesh2d(M.QUAD_RECT_SEED, 2, 3.0)
+    n, eps = q.n, float(q.max_edge_length ** 0.75)
+    ms = mpi_setup(prog, n)
+    vort = problems.colliding_dipoles(q)
+    div = 0.1 * np.cos(q.x) * np.sin(q.y)
+    h = 1.0 + 0.05 * np.exp(-(q.x ** 2 + q.y ** 2))
+    flat = lambda x, y: 0.0
+    u, v, ddot, lap = (F.FArr.zeros(n) for _ in range(4))
+    prog.call("SWEPlaneRHSIntegrals", u, v, ddot, lap, A(q.x), A(q.y), A(vort), A(div), A(h), flat, A(q.area),
+              A(q.is_active, bool), eps, ms)
+    save("swe_plane_rhs_quad2", prog.where("SWEPlaneRHSIntegrals"), x=q.x, y=q.y, vort=vort, div=div, h=h, area=q.area,
+         mask=q.is_active.astype(bool), eps=eps, u=N(u), v=N(v), double_dot=N(ddot), lap_surf=N(lap))
+    hill = lambda x, y: 0.1 * math.exp(-2.0 * (x * x + y * y))          # the bottom topography handed to the solver
+    f0, beta, g, dt = 0.5, 0.2, 9.80616, 0.005
+    vel = field(n, ndim=2)
+    plane = F.Obj(mesh=F.Obj(particles=particles(q.x, q.y, None, q.area, q.is_active.astype(bool))), relVort=field(n, vort),
+                  potVort=field(n, (vort + f0) / h), divergence=field(n, div), h=field(n, h), velocity=vel, pseEps=eps,
+                  mpiParticles=ms, f0=f0, beta=beta, g=g)
+    solver = F.Obj()
+    prog.call("newPrivate", solver, plane, hill, file="src/SWEPlaneSolver.f90")
+    start = [N(solver.u), N(solver.v), N(solver.doubleDot), N(solver.lapSurf)]
+    steps = []
+    for _ in range(2):
+        prog.call("timestepPrivate", solver, plane, dt, hill, file="src/SWEPlaneSolver.f90")
+        p = plane.mesh.particles
+        steps.append([N(p.x), N(p.y), N(plane.relVort.scalar), N(plane.divergence.scalar), N(plane.h.scalar), N(p.area),
+                      N(plane.velocity.xComp), N(plane.velocity.yComp), N(solver.doubleDot), N(solver.lapSurf)])
+    save("swe_plane_rk4_quad2", prog.where("timestepPrivate", "src/SWEPlaneSolver.f90"), x=q.x, y=q.y, vort=vort, div=div, h=h,
+         area=q.area, mask=q.is_active.astype(bool), eps=eps, f0=f0, beta=beta, g=g, dt=dt, start=np.array(start),
+         steps=np.array(steps), topo=np.array("0.1 * exp(-2 (x^2 + y^2))"))
+    m = M.PolyMesh2d(M.ICOS_TRI_SPHERE_SEED, 1)
+    n, R, eps = m.n, 1.0, float(m.max_edge_length ** 0.6)
+    prog.globals["sphereradius"] = R
+    ms = mpi_setup(prog, n)
+    vort = problems.rossby_haurwitz54(m)
+    div = 0.05 * m.x * m.z
+    h = 1.0 + 0.02 * m.y
+    flat3 = lambda x, y, z: 0.0
+    u, v, w, ddot, lap = (F.FArr.zeros(n) for _ in range(5))
+    prog.call("SWESphereRHSIntegrals", u, v, w, ddot, lap, A(m.x), A(m.y), A(m.z), A(vort), A(div), A(h), A(m.area), flat3,
+              A(m.is_active, bool), R, eps, ms)
+    save("swe_sphere_rhs_icos1", prog.where("SWESphereRHSIntegrals"), x=m.x, y=m.y, z=m.z, vort=vort, div=div, h=h, area=m.area,
+         mask=m.is_active.astype(bool), R=R, eps=eps, u=N(u), v=N(v), w=N(w), double_dot=N(ddot), lap_surf=N(lap))
+
+    # ---- diagnostics (src/SphereBVE.f90:410-441) -------------------------------------------------------------------------------
+    prog = F.Program(["src/SphereBVE.f90"])
+    d = np.load(os.path.join(GOLDEN, "refsrc_bve_mesh_icos2.npz"))
+    n = d["x"].size
+    vel = field(n, ndim=3)
+    for comp, val in zip((vel.xComp, vel.yComp, vel.zComp), (d["u"], d["v"], d["w"])):
+        comp.assign(A(val))
+    bve = F.Obj(mesh=F.Obj(particles=particles(d["x"], d["y"], d["z"], d["area"], d["mask"])), velocity=vel,
+                relVort=field(n, d["relvort"]))
+    save("bve_diagnostics_icos2", prog.where("TotalKE") + ", " + prog.where("TotalEnstrophy"), u=d["u"], v=d["v"], w=d["w"],
+         relvort=d["relvort"], area=d["area"], mask=d["mask"], ke=prog.call("TotalKE", bve), enstrophy=prog.call("TotalEnstrophy", bve))
     print(f"done in {time.time() - t0:.0f} s")
 
 

@@ -38,7 +38,9 @@ def test_fixture_set_is_complete():
     names = sorted(os.path.basename(p)[7:-4] for p in glob.glob(os.path.join(GOLDEN, "refsrc_*.npz")))
     assert names == sorted(["load_balance", "bve_velocity_icos2", "bve_velocity_rand157", "bve_mesh_icos2", "bve_mesh_rand157",
                             "bve_rk4_icos1", "plane_quad3", "plane_rand149", "plane_rk4_quad2", "beta_beta2", "beta_rand131",
-                            "beta_rk4_beta1", "pse_sphere_icos1", "pse_sphere_rand97", "pse_plane_quad2"])
+                            "beta_rk4_beta1", "pse_sphere_icos1", "pse_sphere_rand97", "pse_plane_quad2", "pse_ops_plane_quad2",
+                            "pse_ops_sphere_icos1", "swe_plane_rhs_quad2", "swe_plane_rk4_quad2", "swe_sphere_rhs_icos1",
+                            "bve_diagnostics_icos2"])
     for n in names:
         assert "src/" in str(load(n)["reference"])      # every fixture names the reference file:line it came from
 
@@ -136,6 +138,67 @@ def test_pse_sphere_laplacian_bits(tag):
 def test_pse_plane_laplacian_bits():
     d = load("pse_plane_quad2")
     assert same_bits(O.pse_laplacian_plane(d["x"], d["y"], d["f"], d["area"], d["mask"], float(d["eps"])), d["lap"])
+
+
+def test_pse_operators_plane_bits():
+    """Interpolation, gradient, second partials and double dot product in the plane (src/PSEDirectSum.f90:128-365)."""
+    d = load("pse_ops_plane_quad2")
+    a = (d["x"], d["y"])
+    eps = float(d["eps"])
+    assert same_bits(O.pse_interpolate(*a, None, d["f"], d["area"], d["mask"], eps, d["tx"], d["ty"]), d["interp"])
+    gx, gy = O.pse_gradient_plane(*a, d["f"], d["area"], d["mask"], eps)
+    assert same_bits(gx, d["gx"]) and same_bits(gy, d["gy"])
+    for g, name in zip(O.pse_second_partials_plane(*a, d["gx"], d["gy"], d["area"], d["mask"], eps), ("dxx", "dxy", "dyy")):
+        assert same_bits(g, d[name]), name
+    assert same_bits(O.pse_double_dot_plane(*a, d["u"], d["v"], d["area"], d["mask"], eps), d["double_dot"])
+
+
+def test_pse_operators_sphere_bits():
+    """Interpolation, gradient (with SphereProjection and MATMUL), double dot product -- including the reference's
+    yComp(i) in the w rows (:408-413) -- and divergence on the sphere (src/PSEDirectSum.f90:149-267, 367-420, 537-579)."""
+    d = load("pse_ops_sphere_icos1")
+    a = (d["x"], d["y"], d["z"])
+    eps, R = float(d["eps"]), float(d["R"])
+    assert same_bits(O.pse_interpolate(*a, d["f"], d["area"], d["mask"], eps, d["tx"], d["ty"], d["tz"], R), d["interp"])
+    for g, name in zip(O.pse_gradient_sphere(*a, d["f"], d["area"], d["mask"], eps, R), ("gx", "gy", "gz")):
+        assert same_bits(g, d[name]), name
+    assert same_bits(O.pse_double_dot_sphere(*a, d["u"], d["v"], d["w"], d["area"], d["mask"], eps, R), d["double_dot"])
+    assert same_bits(O.pse_divergence_sphere(*a, d["u"], d["v"], d["w"], d["area"], d["mask"], eps, R), d["divergence"])
+
+
+def test_swe_right_hand_sides_bits():
+    d = load("swe_plane_rhs_quad2")
+    got = O.swe_plane_rhs(d["x"], d["y"], d["vort"], d["div"], d["h"], d["area"], d["mask"], float(d["eps"]))   # flat bottom
+    for g, name in zip(got, ("u", "v", "double_dot", "lap_surf")):
+        assert same_bits(g, d[name]), name
+    d = load("swe_sphere_rhs_icos1")
+    got = O.swe_sphere_rhs(d["x"], d["y"], d["z"], d["vort"], d["div"], d["h"], d["area"], d["mask"], float(d["R"]), float(d["eps"]))
+    for g, name in zip(got, ("u", "v", "w", "double_dot", "lap_surf")):
+        assert same_bits(g, d[name]), name
+
+
+def test_swe_plane_rk4_steps_bits():
+    """The planar shallow-water solver's own New + two timestepPrivate calls (src/SWEPlaneSolver.f90:136-180, 298-429) over a
+    Gaussian hill, as written (the whole-array assignments of stage 1 included)."""
+    import math
+    d = load("swe_plane_rk4_quad2")
+    topo = lambda x, y: 0.1 * math.exp(-2.0 * (x * x + y * y))
+    eps = float(d["eps"])
+    surf = d["h"] + np.array([topo(a, b) for a, b in zip(d["x"], d["y"])])
+    start = O.swe_plane_rhs(d["x"], d["y"], d["vort"], d["div"], surf, d["area"], d["mask"], eps)        # New's call, :178-179
+    for g, w, name in zip(start, d["start"], ("u", "v", "double_dot", "lap_surf")):
+        assert same_bits(g, w), name
+    st = [d["x"], d["y"], d["vort"], d["div"], d["h"], d["area"]] + list(start)
+    for k, want in enumerate(d["steps"]):
+        st = O.swe_plane_rk4_step(*st, d["mask"], float(d["f0"]), float(d["beta"]), float(d["g"]), eps, float(d["dt"]), topo)
+        for g, w, name in zip(st, want, "x y relvort div h area u v double_dot lap_surf".split()):
+            assert same_bits(g, w), (k, name)
+
+
+def test_bve_diagnostics_bits():
+    d = load("bve_diagnostics_icos2")
+    assert O.total_ke(d["u"], d["v"], d["w"], d["area"], d["mask"]) == float(d["ke"])
+    assert O.total_enstrophy(d["relvort"], d["area"], d["mask"]) == float(d["enstrophy"])
 
 
 # ---- the vectors regenerate from the reference tree (development container only) -----------------------------------------
