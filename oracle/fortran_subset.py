@@ -682,6 +682,7 @@ class Program:
             env = {}
             for d in decls:
                 self._declare(d[2], env, set(), module_level=True)
+        self.globals.update(numprocs=num_procs, procrank=proc_rank)     # over TypeDefs.f90's initial values (1 and 0)
         for rel in files:
             procs, decls, generics = parse_file(os.path.join(self.root, rel))
             for d in decls:                         # initialised module variables (logInit = .false.) and parameters

@@ -132,6 +132,18 @@ def main():
              x=x, y=y, z=z, relvort=zeta, absvort=absv, area=area, mask=mask, R=R,
              u=N(bve.velocity.xComp), v=N(bve.velocity.yComp), w=N(bve.velocity.zComp),
              relstream=N(bve.relStream.scalar), absstream=N(bve.absStream.scalar))
+    # three ranks: each evaluates its LoadBalance slice (the MPI_BCAST that follows is the exchange the library replaces)
+    x, y, z, zeta, area, mask = rand_sphere(157, 11, 0.6, 1.7)
+    n, P = len(x), 3
+    u, v, w = (F.FArr.zeros(n) for _ in range(3))
+    bounds = []
+    for r in range(P):
+        pr = F.Program(["src/SphereBVESolver.f90", "src/MPISetup.f90"], num_procs=P, proc_rank=r)
+        ms3 = mpi_setup(pr, n, P)
+        pr.call("BVESphereVelocity", u, v, w, A(x), A(y), A(z), A(zeta), A(area), 1.7, 2 * np.pi, A(mask, bool), ms3)
+        bounds.append((ms3.indexStart.get(r), ms3.indexEnd.get(r)))
+    save("bve_velocity_rand157_3ranks", prog.where("BVESphereVelocity"), x=x, y=y, z=z, relvort=zeta, area=area, mask=mask,
+         R=1.7, bounds=np.array(bounds, dtype=np.int64), u=N(u), v=N(v), w=N(w))
     # RK4: icosTri 1 (122 particles), two steps of dt = 0.01 through the reference's BVESolver New + timestepPrivate
     from lpm_v2_b200 import mesh as M, problems
     m = M.PolyMesh2d(M.ICOS_TRI_SPHERE_SEED, 1)

@@ -40,7 +40,7 @@ def test_fixture_set_is_complete():
                             "bve_rk4_icos1", "plane_quad3", "plane_rand149", "plane_rk4_quad2", "beta_beta2", "beta_rand131",
                             "beta_rk4_beta1", "pse_sphere_icos1", "pse_sphere_rand97", "pse_plane_quad2", "pse_ops_plane_quad2",
                             "pse_ops_sphere_icos1", "swe_plane_rhs_quad2", "swe_plane_rk4_quad2", "swe_sphere_rhs_icos1",
-                            "bve_diagnostics_icos2"])
+                            "bve_diagnostics_icos2", "bve_velocity_rand157_3ranks"])
     for n in names:
         assert "src/" in str(load(n)["reference"])      # every fixture names the reference file:line it came from
 
@@ -65,6 +65,25 @@ def test_bve_velocity_and_stream_bits(tag):
         assert same_bits(g, m[name]), "mesh " + name
     rs, as_ = O.bve_stream(m["x"], m["y"], m["z"], m["relvort"], m["absvort"], m["area"], m["mask"], float(m["R"]))
     assert same_bits(rs, m["relstream"]) and same_bits(as_, m["absstream"])
+
+
+def test_bve_velocity_three_rank_slices_bits():
+    """numProcs = 3: every rank runs the reference's loop over its own LoadBalance slice (src/SphereBVESolver.f90:396,
+    src/MPISetup.f90:138-144).  The slices tile the targets, the union has the one-rank bits, and the oracle evaluated
+    slice by slice reproduces it."""
+    d = load("bve_velocity_rand157_3ranks")
+    one = load("bve_velocity_rand157")
+    n = d["x"].size
+    assert d["bounds"][0][0] == 1 and d["bounds"][-1][1] == n and all(d["bounds"][r][1] + 1 == d["bounds"][r + 1][0] for r in range(2))
+    for name in "uvw":
+        assert same_bits(d[name], one[name])
+    got = [np.zeros(n) for _ in range(3)]
+    for b, e in d["bounds"]:
+        part = O.bve_velocity(d["x"], d["y"], d["z"], d["relvort"], d["area"], d["mask"], float(d["R"]), rng=(b - 1, e))
+        for g, p_ in zip(got, part):
+            g[b - 1:e] = p_[b - 1:e]
+    for g, name in zip(got, "uvw"):
+        assert same_bits(g, d[name]), name
 
 
 def test_bve_rk4_steps_bits():
