@@ -633,8 +633,10 @@ def _elementwise(fn, *a):
     return FArr([fn(*row) for row in zip(*cols)], 0, n, 1)
 
 
-def _sum(a):
+def _sum(a, mask=None):
     v = a.tolist()
+    if mask is not None:
+        v = [x for x, m in zip(v, mask.tolist()) if m]
     if not v:
         return 0.0
     s = v[0]
@@ -825,8 +827,10 @@ class Program:
             val = env[name]
             if args is not None:
                 val = self._index(val, args, env, file)
-        elif name in self.globals and args is None:
+        elif name in self.globals and (args is None or isinstance(self.globals[name], (FArr, FMat))):
             val = self.globals[name]
+            if args is not None:
+                val = self._index(val, args, env, file)
         elif args is not None and name in INTRINSICS:
             pos = [self._eval(a, env, file) for a in args if a[0] != "kw"]
             kw = {a[1][1][0][0]: self._eval(a[2], env, file) for a in args if a[0] == "kw"}

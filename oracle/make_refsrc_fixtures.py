@@ -370,6 +370,23 @@ def main():
                 relVort=field(n, d["relvort"]))
     save("bve_diagnostics_icos2", prog.where("TotalKE") + ", " + prog.where("TotalEnstrophy"), u=d["u"], v=d["v"], w=d["w"],
          relvort=d["relvort"], area=d["area"], mask=d["mask"], ke=prog.call("TotalKE", bve), enstrophy=prog.call("TotalEnstrophy", bve))
+    # ---- the workloads' vorticity fields (examples/RossbyHaurwitz54.f90:413-428 with rh54.namelist; config 1's Gaussian vortex,
+    # examples/BVESingleGaussianVortex.f90:120-124, 335-357 with bveSingleGaussVort.namelist) -------------------------------------
+    prog = F.Program(["examples/RossbyHaurwitz54.f90", "examples/BVESingleGaussianVortex.f90", "src/SphereGeometry.f90"])
+    m = M.PolyMesh2d(M.ICOS_TRI_SPHERE_SEED, 2)
+    prog.globals.update(radius=1.0, zonalwind=0.0, rhwaveamplitude=1.0)             # rh54.namelist
+    rh = [prog.call("RossbyHaurwitz54Vorticity", float(a), float(b), float(c)) for a, b, c in zip(m.x, m.y, m.z)]
+    init_lat, init_lon, R = 0.157079632679490, 0.0, 1.0                             # bveSingleGaussVort.namelist
+    center = [R * math.cos(init_lon) * math.cos(init_lat), R * math.sin(init_lon) * math.cos(init_lat), R * math.sin(init_lat)]
+    prog.globals.update(radius=R, shapeparam=4.0, vortstrength=12.566370614359172, vortcenter=F.FArr(center), gauss_const=0.0)
+    g0 = [prog.call("GaussianVortexVorticity", float(a), float(b), float(c)) for a, b, c in zip(m.x, m.y, m.z)]
+    bve = F.Obj(mesh=F.Obj(particles=particles(m.x, m.y, m.z, m.area, m.is_active.astype(bool))), relVort=field(m.n, g0), radius=R)
+    const = prog.call("SetGaussConst", bve)
+    prog.globals["gauss_const"] = const
+    g1 = [prog.call("GaussianVortexVorticity", float(a), float(b), float(c)) for a, b, c in zip(m.x, m.y, m.z)]
+    save("workload_vorticity_icos2", prog.where("RossbyHaurwitz54Vorticity") + ", " + prog.where("GaussianVortexVorticity") + ", " +
+         prog.where("SetGaussConst"), x=m.x, y=m.y, z=m.z, area=m.area, mask=m.is_active.astype(bool), rh54=np.array(rh),
+         gauss_const=const, gaussian=np.array(g1))
     print(f"done in {time.time() - t0:.0f} s")
 
 

@@ -40,7 +40,7 @@ def test_fixture_set_is_complete():
                             "bve_rk4_icos1", "plane_quad3", "plane_rand149", "plane_rk4_quad2", "beta_beta2", "beta_rand131",
                             "beta_rk4_beta1", "pse_sphere_icos1", "pse_sphere_rand97", "pse_plane_quad2", "pse_ops_plane_quad2",
                             "pse_ops_sphere_icos1", "swe_plane_rhs_quad2", "swe_plane_rk4_quad2", "swe_sphere_rhs_icos1",
-                            "bve_diagnostics_icos2", "bve_velocity_rand157_3ranks"])
+                            "bve_diagnostics_icos2", "bve_velocity_rand157_3ranks", "workload_vorticity_icos2"])
     for n in names:
         assert "src/" in str(load(n)["reference"])      # every fixture names the reference file:line it came from
 
@@ -218,6 +218,19 @@ def test_bve_diagnostics_bits():
     d = load("bve_diagnostics_icos2")
     assert O.total_ke(d["u"], d["v"], d["w"], d["area"], d["mask"]) == float(d["ke"])
     assert O.total_enstrophy(d["relvort"], d["area"], d["mask"]) == float(d["enstrophy"])
+
+
+def test_workload_vorticity_fields():
+    """The vorticity of the headline workload (RH54, examples/RossbyHaurwitz54.f90:419-428 with rh54.namelist) and of
+    config 1 (the Gaussian vortex with its two-pass constant, examples/BVESingleGaussianVortex.f90:335-357): the numpy
+    functions bench.py and the tests use against the reference text -- to a few ulp (numpy's cos / exp are not glibc's)."""
+    from lpm_v2_b200 import problems
+    d = load("workload_vorticity_icos2")
+
+    class Mesh:
+        x, y, z, area, is_active = d["x"], d["y"], d["z"], d["area"], d["mask"].astype(np.int32)
+    for got, want in ((problems.rossby_haurwitz54(Mesh), d["rh54"]), (problems.gaussian_vortex(Mesh), d["gaussian"])):
+        assert np.abs(got - want).max() <= 4e-15 * np.abs(want).max()
 
 
 # ---- the vectors regenerate from the reference tree (development container only) -----------------------------------------
