@@ -42,7 +42,7 @@ def test_fixture_set_is_complete():
                             "pse_ops_sphere_icos1", "swe_plane_rhs_quad2", "swe_plane_rk4_quad2", "swe_sphere_rhs_icos1",
                             "bve_diagnostics_icos2", "bve_velocity_rand157_3ranks", "workload_vorticity_icos2"])
     for n in names:
-        assert "src/" in str(load(n)["reference"])      # every fixture names the reference file:line it came from
+        assert ".f90:" in str(load(n)["reference"])    # every fixture names the reference file:line it came from
 
 
 def test_load_balance_bits():
