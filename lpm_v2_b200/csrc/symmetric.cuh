@@ -3,6 +3,7 @@
 // accumulation.  Measured at icosTri 8 on one B200 (profiles/r02_ab_sym.log, the round-2 A/B): velocity
 // 1410 -> 1325 ms, stream functions 2227 -> 1903 ms with the first fixed-point accumulation; the FP64-atomic
 // builds (1271 / 1771 ms) were deleted because their results depended on the order in which atomics land.
+// End of round 2 (profiles/r02o_bench_n1.json, r02m_ab_builds.log): 1201 ms and 1677 ms.
 //
 // The reference (src/SphereBVESolver.f90:396-420) visits every ordered pair (i, j): for the
 // factored form used here, a_i = sum_j P_j / d_ij with d_ij = R^2 - x_i.x_j = d_ji.  Active
@@ -21,7 +22,9 @@
 //     pair is evaluated once: the thread adds P_j / d to its targets' sums and, per source, sums
 //     P_t / d over its T targets.  Those per-source sums are reduced across the warp by
 //     recursive halving over batches of SB sources (SB (2 SHFL + DADD) per level instead of a full
-//     butterfly per source), the warps' sums are joined in shared memory in warp order (velocity), and the
+//     butterfly per source; the lanes take the batch in rotated order so that no level needs a select,
+//     sym_reduce_red), the warps' sums are joined in shared memory in warp order (all three kernels; the
+//     ones that carry the 64 KB log table use source tiles of 128 / 64 so that the buffers fit), and the
 //     result is added to the source's accumulator in global memory -- exactly, in fixed point
 //     (sym_red_add), so the total does not depend on the order of the adds nor on how target blocks
 //     were dealt to ranks.  A CTA's own sums join the same accumulators when it ends.
