@@ -20,6 +20,12 @@
 // (vertex coordinates, edge orig/dest/left/right, face vertices/edges, 0-based
 // as stored there); they are input data, not code.
 //
+//
+// Pinned: tests/test_refsrc_golden.py::test_mesh_generator_bits compares this generator, bit for bit, with the
+// reference's own PolyMesh2d New executed from its source text (and its own *Seed.dat) by oracle/fortran_subset.py --
+// coordinates, areas, particle order, active flags, tree sizes, MaxEdgeLength and leaf-face connectivity for all five
+// seeds at levels 0-3.
+//
 // Only uniform refinement is implemented (no AMR); remeshing stays in the
 // reference Fortran (out of scope).
 #include <cmath>

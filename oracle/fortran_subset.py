@@ -6,7 +6,7 @@ Why it exists.  The image has no Fortran compiler, so the reference cannot be bu
 the BVE / planar / beta-plane sums.  oracle/lpm_oracle.c restates those loops by hand.  This interpreter removes the
 "by hand" from the check of that restatement: it reads the reference's OWN source text from /root/reference at
 fixture-generation time, parses the procedures on the path (BVESphereVelocity, timestepPrivate, SetStreamFunctionsOnMesh,
-LoadBalance, ...) and executes them statement by statement.  oracle/make_refsrc_fixtures.py stores inputs and outputs
+LoadBalance, the PSE operators, the PolyMesh2d mesh builder with its seed files, ...) and executes them statement by statement.  oracle/make_refsrc_fixtures.py stores inputs and outputs
 under tests/golden/refsrc_*.npz, and tests/test_refsrc_golden.py demands that the C oracle reproduces them BIT FOR BIT.
 What is interpreted is the reference's text; what this file supplies is only the language: operator precedence,
 left-to-right evaluation of operators of equal precedence, integer division, do / if, array sections and whole-array
@@ -25,13 +25,16 @@ Semantics implemented
                 division by zero, log(0), overflow give the IEEE result instead of a Python exception.
   sum(a)        elements added in index order starting from the first (gfortran's inline expansion).
   statements    assignment (scalar, element, section, whole array, component), do / enddo (with step; cycle, exit), if /
-                else if / else / endif, one-line if, call, return, allocate; rank-2 arrays as far as the sphere operators'
-                3 x 3 projection needs them (elements, whole-array assignment, MATMUL(matrix, vector) in gfortran's inline
-                order); procedure dummy arguments; declarations only allocate local arrays of constant size
+                else if / else / endif, one-line if, select case, call, return, allocate; rank-2 arrays as far as the path
+                needs them (elements, column sections a(lo:hi, j), whole-array assignment and arithmetic,
+                MATMUL(matrix, vector) in gfortran's inline order); open / list-directed read / close on the reference's
+                own data files (the mesh seeds); write / print / deallocate are no-ops; procedure dummy arguments;
+                declarations only allocate local arrays of constant size
                 (dimension(3) :: xi) and evaluate parameter constants; "!$acc" lines are comments; calls to MPI_BCAST,
                 LogMessage and the like are no-ops (one rank: numProcs = 1, procRank = 0 -- a broadcast to oneself).
-  procedures    looked up by name in the files given to Program(); dummy arguments are associated by reference for arrays
-                and derived types and copied in / out for scalars.
+  procedures    looked up by name in the files given to Program(); generic interfaces pick the specific procedure by
+                argument count and, where that is ambiguous (New), by the derived type of the first argument; dummy
+                arguments are associated by reference for arrays and derived types and copied in / out for scalars.
 """
 import math
 import os
@@ -47,8 +50,10 @@ class FortranError(Exception):
 class Obj:
     """A derived-type value: components by (lower-case) name."""
 
-    def __init__(self, **kw):
+    def __init__(self, _type=None, **kw):
         self.__dict__["f"] = {k.lower(): v for k, v in kw.items()}
+        self.__dict__["tname"] = None if _type is None else _type.lower()     # derived-type name: picks the specific
+                                                                              # procedure of a generic like New(...)
 
     def __getattr__(self, k):
         try:
@@ -137,6 +142,14 @@ class FMat:
         else:
             self.v[:] = [val] * len(self.v)
 
+    def column(self, lo, hi, j):
+        """a(lo:hi, j) as a rank-1 view (contiguous in column-major storage)"""
+        lo = 1 if lo is None else lo
+        hi = self.n1 if hi is None else hi
+        if not (1 <= lo and hi <= self.n1 and 1 <= j <= self.n2):
+            raise FortranError(f"section ({lo}:{hi}, {j}) outside a {self.n1} x {self.n2} array")
+        return FArr(self.v, (j - 1) * self.n1 + lo - 1, max(hi - lo + 1, 0), 1)
+
 
 def _matmul(a, b):
     """MATMUL(matrix, vector) as gfortran expands it inline: c = 0; do k; do i; c(i) = c(i) + a(i,k) * b(k)."""
@@ -163,6 +176,20 @@ def _strip_comment(line):
     return line
 
 
+def _lower_outside_strings(line):
+    out, q = [], None
+    for c in line:
+        if q:
+            out.append(c)
+            if c == q:
+                q = None
+        else:
+            if c in "'\"":
+                q = c
+            out.append(c.lower())
+    return "".join(out)
+
+
 def logical_lines(text):
     """Comment-free, continuation-joined, lower-cased statements with their first source line number."""
     out, cur, start = [], "", None
@@ -181,7 +208,7 @@ def logical_lines(text):
         cur += line
         for part in cur.split(";") if "'" not in cur and '"' not in cur else [cur]:
             if part.strip():
-                out.append((start, part.strip().lower()))
+                out.append((start, _lower_outside_strings(part.strip())))
         cur = ""
     return out
 
@@ -438,6 +465,7 @@ def _parse_decl(stmt):
         j = _match_paren(head, dim.end() - 1)
         hdims = head[dim.end():j]
     is_param = bool(re.search(r"\bparameter\b", head))
+    base = re.sub(r"\s+", "", re.match(r"^(double\s+precision|\w+\s*(\([^)]*\))?)", head).group(1))   # real(kreal), type(faces), ...
     out = []
     for ent in _split_top(ents):
         init = None
@@ -446,7 +474,7 @@ def _parse_decl(stmt):
         m = re.match(r"^(\w+)\s*(?:\((.*)\))?$", ent.strip())
         if not m:
             continue
-        out.append((m.group(1), m.group(2) if m.group(2) is not None else hdims, init, is_param))
+        out.append((m.group(1), m.group(2) if m.group(2) is not None else hdims, init, is_param, base))
     return out
 
 
@@ -456,7 +484,8 @@ def parse_block(lines, k, enders):
     while k < len(lines):
         no, s = lines[k]
         word = (re.match(r"^(end\s*(?:do|if|subroutine|function|module|program|type|interface|select|where)?)(?:\s+\w+)?\s*$", s)
-                or re.match(r"^(else\s*if|elseif)\s*\(", s) or re.match(r"^(else)\s*$", s))
+                or re.match(r"^(else\s*if|elseif)\s*\(", s) or re.match(r"^(else)\s*$", s)
+                or re.match(r"^(case)\s*(\(|default)", s))
         if word:
             w = re.sub(r"\s+", "", word.group(1))
             if w in enders or (w.startswith("end") and "end" in enders):
@@ -505,6 +534,33 @@ def parse_block(lines, k, enders):
                 stmts.append(("if", no, [(cond, inner)], None))
                 k += 1
             continue
+        m = re.match(r"^select\s*case\s*\((.*)\)\s*$", s)
+        if m:
+            sel, arms, default = parse_expr(m.group(1)), [], None
+            _, k2, end = parse_block(lines, k + 1, {"case", "endselect"})
+            while end == "case":
+                head = lines[k2][1]
+                body, k3, end = parse_block(lines, k2 + 1, {"case", "endselect"})
+                if re.match(r"^case\s*default", head):
+                    default = body
+                else:
+                    vals = head[head.index("(") + 1:_match_paren(head, head.index("("))]
+                    arms.append(([parse_expr(v) for v in _split_top(vals)], body))
+                k2 = k3
+            stmts.append(("select", no, sel, arms, default))
+            k = k2 + 1
+            continue
+        m = re.match(r"^(open|close|read)\s*\((.*)$", s)
+        if m:
+            j = _match_paren(s, s.index("("))
+            ctl = Parser(tokenize(s[s.index("("):j + 1].replace("*", "0"))).p_args()      # read(unit, *): the format is not used
+            items = [parse_expr(x) for x in _split_top(s[j + 1:])] if m.group(1) == "read" else []
+            stmts.append((m.group(1), no, ctl, items))
+            k += 1
+            continue
+        if re.match(r"^(write|print|deallocate|nullify)\b", s):      # logging and clean-up: nothing to do
+            k += 1
+            continue
         m = re.match(r"^call\s+(\w+)\s*(\(.*\))?\s*$", s)
         if m:
             args = Parser(tokenize(m.group(2))).p_args() if m.group(2) and m.group(1) not in IGNORED_CALLS else []
@@ -522,7 +578,7 @@ def parse_block(lines, k, enders):
                     stmts.append(("allocate", no, parse_expr(item)))
             k += 1
             continue
-        if re.match(r"^(print|write|read|open|close|deallocate|nullify|stop)\b", s):
+        if re.match(r"^(stop|rewind|backspace|inquire)\b", s):
             stmts.append(("unsupported", no, s))
             k += 1
             continue
@@ -564,7 +620,7 @@ def parse_file(path):
             kind, name = m.group(1), m.group(2)
             args = [a.strip() for a in (m.group(3) or "").split(",") if a.strip()]
             k2 = k + 1
-            while k2 < len(lines) and not re.match(r"^end\s*(subroutine|function)?(\s+\w+)?\s*$", lines[k2][1]):
+            while k2 < len(lines) and not re.match(r"^end(\s*(subroutine|function)(\s+\w+)?)?\s*$", lines[k2][1]):
                 k2 += 1
             # parsed on first use: most procedures of these files are off the path and use statements outside the subset
             procs.setdefault(name, Proc(kind, name, args, m.group(4) or name, lines[k + 1:k2], None, path, no))
@@ -587,6 +643,10 @@ class _Cycle(Exception):
 
 class _Exit(Exception):
     pass
+
+
+def _zero_of(base):
+    return 0 if base.startswith("integer") else False if base.startswith("logical") else "" if base.startswith("character") else 0.0
 
 
 def _idiv(a, b):
@@ -623,6 +683,13 @@ def _log(x):
 
 
 def _elementwise(fn, *a):
+    mats = [x for x in a if isinstance(x, FMat)]
+    if mats:
+        m = mats[0]
+        if any((x.n1, x.n2) != (m.n1, m.n2) for x in mats) or any(isinstance(x, FArr) for x in a):
+            raise FortranError("array operands of different shapes")
+        cols = [x.v if isinstance(x, FMat) else [x] * len(m.v) for x in a]
+        return FMat(m.n1, m.n2, [fn(*row) for row in zip(*cols)])
     arrs = [x for x in a if isinstance(x, FArr)]
     if not arrs:
         return fn(*a)
@@ -662,7 +729,7 @@ INTRINSICS = {
     "int": lambda x, kind=None: _elementwise(int, x),
     "min": lambda *a: _elementwise(min, *a), "max": lambda *a: _elementwise(max, *a),
     "mod": lambda a, b: _elementwise(lambda p, q: math.fmod(p, q) if isinstance(p, float) or isinstance(q, float) else p - _idiv(p, q) * q, a, b),
-    "sum": _sum, "size": lambda a, dim=None: a.n, "allocated": lambda a: a is not None, "associated": lambda a: a is not None,
+    "sum": _sum, "size": lambda a, dim=None: (a.n1 if dim == 1 else a.n2 if dim == 2 else a.n1 * a.n2) if isinstance(a, FMat) else a.n, "allocated": lambda a: a is not None, "associated": lambda a: a is not None,
     "dot_product": lambda a, b: _sum(_elementwise(lambda p, q: p * q, a, b)),
     "maxval": lambda a: max(a.tolist()), "minval": lambda a: min(a.tolist()), "matmul": _matmul,
     "trim": lambda a: a, "present": lambda a: a is not None,
@@ -678,7 +745,7 @@ class Program:
         self.files, self.procs, self.by_file = [], {}, {}
         self.globals = {"numprocs": num_procs, "procrank": proc_rank, "mpi_double_precision": 0, "mpi_comm_world": 0,
                         "mpi_integer": 0, "mpi_sum": 0}
-        self.generics = {}
+        self.generics, self.units = {}, {}
         for rel in constants_from:
             _, decls, _ = parse_file(os.path.join(self.root, rel))
             env = {}
@@ -700,7 +767,12 @@ class Program:
         p = self._find(name.lower(), file)
         return f"{os.path.relpath(p.file, self.root)}:{p.line}"
 
-    def _find(self, name, file=None, nargs=None):
+    def _decls_of(self, proc):
+        if proc.decls is None:
+            return [d for _, ln in proc.body if _DECL.match(ln) and "::" in ln for d in _parse_decl(ln)]
+        return proc.decls
+
+    def _find(self, name, file=None, nargs=None, first=None):
         """The procedure `name` as seen from `file`: a procedure of that file first, then a generic interface (the
         specific procedure with `nargs` dummies; generics of `file` first), then a procedure of any loaded file."""
         here = None
@@ -712,17 +784,24 @@ class Program:
                         return procs[name]
         if name in self.generics:
             cands = sorted(self.generics[name], key=lambda c: c[0] != here)
-            for rel, sp in cands:
-                p = self.by_file[rel].get(sp)
-                if p is not None and (nargs is None or len(p.args) == nargs):
-                    return p
+            fits = [p for p in (self.by_file[rel].get(sp) for rel, sp in cands)
+                    if p is not None and (nargs is None or len(p.args) == nargs)]
+            if len(fits) > 1 and isinstance(first, Obj) and first.tname:     # New(particles, ...) / New(faces, ...): by type
+                for p in fits:
+                    t = [d[4] for d in self._decls_of(p) if p.args and d[0] == p.args[0]]
+                    if t and t[0] in (f"type({first.tname})", f"class({first.tname})"):
+                        return p
+            if fits:
+                return fits[0]
         if name in self.procs:
             return self.procs[name]
         raise FortranError(f"procedure {name} not found in {self.files}")
 
     # -- declarations: constants and local arrays of constant size
     def _declare(self, ents, env, dummies, module_level=False, file=None):
-        for name, dims, init, is_param in ents:
+        types = env.setdefault("%types", {}) if not module_level else {}
+        for name, dims, init, is_param, base in ents:
+            types[name] = base
             if (is_param or module_level) and init is not None:
                 try:
                     val = self._eval(parse_expr(init), env, file)
@@ -736,7 +815,8 @@ class Program:
                         n = [int(self._eval(parse_expr(x), env, file)) for x in d]
                     except (KeyError, FortranError):
                         continue
-                    env[name] = FArr.zeros(n[0]) if len(n) == 1 else FMat(n[0], n[1])
+                    zero = _zero_of(base)
+                    env[name] = FArr.zeros(n[0], value=zero) if len(n) == 1 else FMat(n[0], n[1], [zero] * (n[0] * n[1]))
 
     # -- expressions
     def _eval(self, e, env, file=None):
@@ -806,9 +886,13 @@ class Program:
 
     def _index(self, val, args, env, file):
         if isinstance(val, FMat):
-            if len(args) != 2 or any(a[0] == "sec" for a in args):
-                raise FortranError("rank-2 arrays: element access only")
-            return val.get(self._eval(args[0], env, file), self._eval(args[1], env, file))
+            if len(args) != 2 or args[1][0] == "sec":
+                raise FortranError("rank-2 arrays: a(i, j) and a(lo:hi, j) only")
+            j = self._eval(args[1], env, file)
+            if args[0][0] == "sec":
+                return val.column(None if args[0][1] is None else self._eval(args[0][1], env, file),
+                                  None if args[0][2] is None else self._eval(args[0][2], env, file), j)
+            return val.get(self._eval(args[0], env, file), j)
         if callable(val):                           # a procedure dummy argument (topoFn)
             return val(*[self._eval(a, env, file) for a in args])
         if not isinstance(val, FArr):
@@ -831,6 +915,11 @@ class Program:
             val = self.globals[name]
             if args is not None:
                 val = self._index(val, args, env, file)
+        elif args is not None and name in ("allocated", "associated", "present"):
+            try:                                    # a component that was never allocated does not exist here
+                val = self._eval(args[0], env, file) is not None
+            except (KeyError, FortranError):
+                val = False
         elif args is not None and name in INTRINSICS:
             pos = [self._eval(a, env, file) for a in args if a[0] != "kw"]
             kw = {a[1][1][0][0]: self._eval(a[2], env, file) for a in args if a[0] == "kw"}
@@ -870,9 +959,14 @@ class Program:
         if args is not None:
             target = holder[key]
             if isinstance(target, FMat):
-                if len(args) != 2:
-                    raise FortranError("rank-2 arrays: element access only")
-                target.set(self._eval(args[0], env, file), self._eval(args[1], env, file), value)
+                if len(args) != 2 or args[1][0] == "sec":
+                    raise FortranError("rank-2 arrays: a(i, j) and a(lo:hi, j) only")
+                j = self._eval(args[1], env, file)
+                if args[0][0] == "sec":
+                    target.column(None if args[0][1] is None else self._eval(args[0][1], env, file),
+                                  None if args[0][2] is None else self._eval(args[0][2], env, file), j).assign(value)
+                else:
+                    target.set(self._eval(args[0], env, file), j, value)
                 return
             if len(args) != 1:
                 raise FortranError("only rank-1 arrays are supported")
@@ -930,18 +1024,39 @@ class Program:
             elif k == "call":
                 if st[2] in self.ignore_calls:
                     continue
-                self._call(self._find(st[2], file, len(st[3])), st[3], env, file)
+                first = None
+                if st[3] and st[3][0][0] == "ref":
+                    try:
+                        first = self._eval(st[3][0], env, file)
+                    except (KeyError, FortranError):
+                        first = None
+                self._call(self._find(st[2], file, len(st[3]), first), st[3], env, file)
             elif k == "allocate":               # allocate(a(n)): a fresh array of n zeros, lower bound 1
                 parts = st[2][1]
                 name, args = parts[-1]
-                if args is None or len(args) != 1:
+                if args is None or len(args) not in (1, 2):
                     raise FortranError(f"line {st[1]}: unsupported allocate")
                 holder = env if len(parts) == 1 else self._ref(parts[:-1], env, file).f
-                if args[0][0] == "sec":             # allocate(a(lo:hi))
+                zero = _zero_of(env.get("%types", {}).get(name, "real")) if len(parts) == 1 else 0.0
+                if len(args) == 2:                  # allocate(a(n1, n2)); components are initialised by the caller's next statement
+                    n1, n2 = (int(self._eval(a, env, file)) for a in args)
+                    holder[name] = FMat(n1, n2, [zero] * (n1 * n2))
+                elif args[0][0] == "sec":           # allocate(a(lo:hi))
                     lo, hi = int(self._eval(args[0][1], env, file)), int(self._eval(args[0][2], env, file))
-                    holder[name] = FArr.zeros(hi - lo + 1, lb=lo)
+                    holder[name] = FArr.zeros(hi - lo + 1, lb=lo, value=zero)
                 else:
-                    holder[name] = FArr.zeros(int(self._eval(args[0], env, file)))
+                    holder[name] = FArr.zeros(int(self._eval(args[0], env, file)), value=zero)
+            elif k == "select":
+                v = self._eval(st[2], env, file)
+                for vals, body in st[3]:
+                    if any(self._eval(x, env, file) == v for x in vals):
+                        self._exec(body, env, file)
+                        break
+                else:
+                    if st[4] is not None:
+                        self._exec(st[4], env, file)
+            elif k in ("open", "close", "read"):
+                self._io(st, env, file)
             elif k == "return":
                 raise _Return()
             elif k == "cycle":
@@ -952,6 +1067,44 @@ class Program:
                 continue
             else:
                 raise FortranError(f"line {st[1]}: unsupported statement {st!r}")
+
+    # -- list-directed input from the reference's own data files (the mesh seeds)
+    def _io(self, st, env, file):
+        kind, ctl, items = st[0], st[2], st[3]
+        kw = {a[1][1][0][0]: a[2] for a in ctl if a[0] == "kw"}
+        pos = [a for a in ctl if a[0] != "kw"]
+        unit = self._eval(kw["unit"] if "unit" in kw else pos[0], env, file)
+        if kind == "open":
+            name = str(self._eval(kw["file"], env, file)).strip()
+            path = name if os.path.isabs(name) else os.path.join(self.root, name)
+            ok = os.path.isfile(path)
+            if ok:
+                recs = [re.split(r"[\s,]+", ln.strip()) for ln in open(path).read().splitlines()]
+                self.units[unit] = [r for r in recs if r != [""]]
+            if "iostat" in kw:
+                self._assign(kw["iostat"], 0 if ok else 2, env, file)
+            elif not ok:
+                raise FortranError(f"cannot open {path}")
+        elif kind == "close":
+            self.units.pop(unit, None)
+        else:                                       # read(unit, *) a, b, ...: a new record per statement, more as needed
+            recs, toks = self.units[unit], []
+            while len(toks) < len(items):
+                if not recs:
+                    raise FortranError("end of file")
+                toks += recs.pop(0)
+            for item, tok in zip(items, toks):
+                try:
+                    cur = self._eval(item, env, file)
+                except (KeyError, FortranError):
+                    cur = None
+                if isinstance(cur, str) or (cur is None and env.get("%types", {}).get(item[1][0][0], "").startswith("character")):
+                    val = tok
+                elif isinstance(cur, float) or (cur is None and env.get("%types", {}).get(item[1][0][0], "real").startswith("real")):
+                    val = float(tok.lower().replace("d", "e"))
+                else:
+                    val = int(tok)
+                self._assign(item, val, env, file)
 
     def _call(self, proc, args, env, file):
         if len(args) > len(proc.args):

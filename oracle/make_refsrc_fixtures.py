@@ -387,6 +387,30 @@ def main():
     save("workload_vorticity_icos2", prog.where("RossbyHaurwitz54Vorticity") + ", " + prog.where("GaussianVortexVorticity") + ", " +
          prog.where("SetGaussConst"), x=m.x, y=m.y, z=m.z, area=m.area, mask=m.is_active.astype(bool), rh54=np.array(rh),
          gauss_const=const, gaussian=np.array(g1))
+    # ---- the mesh itself: the reference's PolyMesh2d New (seed file, uniform refinement) -------------------------------------
+    # src/PolyMesh2d.f90:135-195 (newPrivate), :795-939 (initializeMeshFromSeed), :956-1043 (readSeedFile, reading the
+    # reference's own *Seed.dat), src/Faces.f90:529-858 (DivideQuadFace, DivideTriFace), :917-975 (face areas),
+    # src/Edges.f90:211-233, 567-621 (InsertEdge, divideLinearEdge), src/Particles.f90 (New, InsertParticle, ...),
+    # src/SphereGeometry.f90 / PlaneGeometry.f90 (midpoints, centroids, triangle areas), src/Edges.f90:260-275 (MaxEdgeLength).
+    # Left out: the per-particle incident-edge lists (RecordIncidentEdgeAtParticles, SortIncidentEdgesAtParticle: they do
+    # not enter positions, areas, order or face connectivity).
+    files = ["src/PolyMesh2d.f90", "src/Particles.f90", "src/Edges.f90", "src/Faces.f90", "src/SphereGeometry.f90", "src/PlaneGeometry.f90"]
+    off_path = ("recordincidentedgeatparticles", "replaceincidentedgewithchild", "sortincidentedgesatparticle", "startsection", "endsection")
+    for seed, amp, levels in ((M.ICOS_TRI_SPHERE_SEED, 1.0, (0, 1, 2, 3)), (M.CUBED_SPHERE_SEED, 1.0, (0, 1, 2, 3)),
+                              (M.QUAD_RECT_SEED, 3.0, (0, 1, 2, 3)), (M.TRI_HEX_SEED, 1.0, (0, 1, 2)), (M.BETA_PLANE_SEED, 1.0, (0, 1, 2))):
+        for L in levels:
+            prog = F.Program(files, ignore_calls=off_path)
+            mesh = F.Obj(_type="polymesh2d", particles=F.Obj(_type="particles"), edges=F.Obj(_type="edges"), faces=F.Obj(_type="faces"))
+            prog.call("newPrivate", mesh, int(seed), L, L, 0, float(amp), file="src/PolyMesh2d.f90")
+            p, fc = mesh.particles, mesh.faces
+            n = p.n
+            col = lambda name: np.array(p.f[name].tolist()[:n]) if p.f.get(name) is not None else np.zeros(n)
+            leaf = [i for i in range(1, fc.n + 1) if not fc.hasChildren.get(i)]
+            verts = np.array([[fc.vertices.get(r, i) for r in range(1, fc.vertices.n1 + 1)] for i in leaf], dtype=np.int32)
+            save(f"mesh_seed{int(seed)}_L{L}", prog.where("newPrivate", "src/PolyMesh2d.f90"), seed=int(seed), level=L, amp=amp, n=n,
+                 n_faces=fc.n, n_edges=mesh.edges.n, x=col("x"), y=col("y"), z=col("z"), area=col("area"),
+                 mask=np.array(p.isActive.tolist()[:n], dtype=bool), max_edge_length=prog.call("MaxEdgeLength", mesh.edges, p),
+                 leaf_face_vertices=verts, leaf_face_center=np.array([fc.centerParticle.get(i) for i in leaf], dtype=np.int32))
     print(f"done in {time.time() - t0:.0f} s")
 
 

@@ -34,15 +34,38 @@ def same_bits(a, b):
     return a.shape == b.shape and np.array_equal(a.view(np.int64), b.view(np.int64))
 
 
+MESHES = [(205, L) for L in range(4)] + [(206, L) for L in range(4)] + [(202, L) for L in range(4)] + \
+         [(201, L) for L in range(3)] + [(207, L) for L in range(3)]
+
+
 def test_fixture_set_is_complete():
     names = sorted(os.path.basename(p)[7:-4] for p in glob.glob(os.path.join(GOLDEN, "refsrc_*.npz")))
-    assert names == sorted(["load_balance", "bve_velocity_icos2", "bve_velocity_rand157", "bve_mesh_icos2", "bve_mesh_rand157",
+    assert names == sorted([f"mesh_seed{s}_L{L}" for s, L in MESHES] + ["load_balance", "bve_velocity_icos2", "bve_velocity_rand157", "bve_mesh_icos2", "bve_mesh_rand157",
                             "bve_rk4_icos1", "plane_quad3", "plane_rand149", "plane_rk4_quad2", "beta_beta2", "beta_rand131",
                             "beta_rk4_beta1", "pse_sphere_icos1", "pse_sphere_rand97", "pse_plane_quad2", "pse_ops_plane_quad2",
                             "pse_ops_sphere_icos1", "swe_plane_rhs_quad2", "swe_plane_rk4_quad2", "swe_sphere_rhs_icos1",
                             "bve_diagnostics_icos2", "bve_velocity_rand157_3ranks", "workload_vorticity_icos2"])
     for n in names:
         assert ".f90:" in str(load(n)["reference"])    # every fixture names the reference file:line it came from
+
+
+@pytest.mark.parametrize("seed,level", MESHES)
+def test_mesh_generator_bits(seed, level):
+    """The input side: the host mesh generator (lpm_v2_b200/csrc/mesh.cpp -> liblpmmesh.so) against the reference's own
+    PolyMesh2d New executed from its source -- seed file read from the lpm-v2 tree, uniform refinement by DivideTriFace /
+    DivideQuadFace, edge midpoints, face centres and areas (src/PolyMesh2d.f90:135-195, 795-1043, src/Faces.f90:529-975,
+    src/Edges.f90:211-233, 567-621): every particle's coordinates and area bit for bit, in the reference's order, with the
+    same active flags, tree sizes, MaxEdgeLength (the PSE eps = h^pow, src/PSEDirectSum.f90:93-113) and leaf-face
+    connectivity.  icosTri, cubed sphere, quadRect (amplified), triHex, beta plane."""
+    from lpm_v2_b200 import mesh as M
+    d = load(f"mesh_seed{seed}_L{level}")
+    m = M.PolyMesh2d(seed, level, float(d["amp"]))
+    assert (m.n, m.n_faces_total, m.n_edges_total) == (int(d["n"]), int(d["n_faces"]), int(d["n_edges"]))
+    for name, got in (("x", m.x), ("y", m.y), ("z", m.z), ("area", m.area)):
+        assert same_bits(got, d[name]), name
+    assert np.array_equal(m.is_active.astype(bool), d["mask"])
+    assert m.max_edge_length == float(d["max_edge_length"])
+    assert np.array_equal(m.face_verts, d["leaf_face_vertices"] - 1) and np.array_equal(m.face_center, d["leaf_face_center"] - 1)
 
 
 def test_load_balance_bits():
