@@ -22,7 +22,8 @@
 //
 //
 // Pinned: tests/test_refsrc_golden.py::test_mesh_generator_bits compares this generator, bit for bit, with the
-// reference's own PolyMesh2d New executed from its source text (and its own *Seed.dat) by oracle/fortran_subset.py --
+// reference's own PolyMesh2d New executed from its source text (and its own *Seed.dat) by the test infrastructure's
+// Fortran-subset interpreter --
 // coordinates, areas, particle order, active flags, tree sizes, MaxEdgeLength and leaf-face connectivity for all five
 // seeds at levels 0-3.
 //
