@@ -284,7 +284,7 @@ def run_b200(args):
         parity = {"max_rel_err": err, "tolerance": 1e-12, "targets": int(cnt * world), "ranks": world,
                   "reference_vs_extended_precision": ref_ld, "gpu_vs_extended_precision": gpu_ld,
                   "extended_precision_targets": int(nld * world),
-                  "against": "oracle/lpm_oracle.c parity build (restatement of src/SphereBVESolver.f90:396-420), "
+                  "against": "oracle/lpm_oracle.c parity build (restatement of src/SphereBVESolver.f90:396-420; it reproduces the reference's own source text, executed by oracle/fortran_subset.py, bit for bit: tests/test_refsrc_golden.py), "
                              f"{cnt} contiguous targets from the middle of every rank's slice x all sources; "
                              "error = max |u_gpu - u_ref| over the sample / max |u| over all targets, per component"}
 
